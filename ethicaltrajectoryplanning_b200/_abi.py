@@ -1,0 +1,161 @@
+"""ctypes binding of ``libetp_b200.so`` (C ABI declared in ``include/etp_b200.h``).
+
+There is no CPU fallback: if the CUDA library has not been built, importing the product
+functions raises.  ``build_library()`` compiles it in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libetp_b200.so")
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_abi.cu")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_launch.h")] + [
+    os.path.join(os.path.dirname(HERE), "include", "etp_b200.h")]
+
+NUM_WEIGHTS = 14
+NUM_FIELDS = 13
+NUM_RED = 4
+NUM_COST = 13
+MAX_ANGLE_BINS = 8
+LEVEL_SKIPPED = 255
+PRECISION_FP32, PRECISION_FP64 = 0, 1
+OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NO_CANDIDATE, ERR_STATE = 0, -1, -2, -3, -4, -5
+
+FIELD_NAMES = ("d", "d_d", "d_dd", "d_ddd", "s", "s_d", "s_dd", "s_ddd", "x", "y", "yaw", "v", "curv")
+RED_NAMES = ("ego_risk", "obst_risk", "ego_harm", "obst_harm")
+COST_NAMES = ("bayes", "equality", "maximin", "responsibility", "ego", "risk_cost", "velocity",
+              "dist_to_global_path", "lon_jerk", "lat_jerk", "travelled_dist", "factor", "total")
+REASON_NAMES = ("", "velocity", "acceleration", "curvature (lvc)", "curvature (hvc)", "collision",
+                "boundaries", "max_risk")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("weights", C.c_double * NUM_WEIGHTS),
+        ("planner_mode", C.c_int32),
+        ("fast_prob_mahalanobis", C.c_int32),
+        ("multiple_cost_functions", C.c_int32),
+        ("n_angle_thresholds", C.c_int32),
+        ("max_acceptable_risk", C.c_double),
+        ("angle_thr", C.c_double * MAX_ANGLE_BINS),
+        ("angle_coef_pos", C.c_double * (MAX_ANGLE_BINS + 1)),
+        ("angle_coef_neg", C.c_double * (MAX_ANGLE_BINS + 1)),
+        ("lr_const", C.c_double), ("lr_speed", C.c_double),
+        ("lr1s_const", C.c_double), ("lr1s_speed", C.c_double),
+        ("ped_const", C.c_double), ("ped_speed", C.c_double),
+        ("veh_l", C.c_double), ("veh_w", C.c_double), ("veh_l_r", C.c_double), ("veh_m", C.c_double),
+        ("veh_steer_max", C.c_double), ("veh_lat_a_max", C.c_double), ("veh_v_max", C.c_double),
+        ("veh_a_max", C.c_double),
+    ]
+
+
+class Obstacles(C.Structure):
+    _fields_ = [
+        ("n_obstacles", C.c_int32), ("max_pred", C.c_int32),
+        ("pred_len", _ip), ("pos", _dp), ("cov", _dp), ("yaw", _dp), ("vel", _dp),
+        ("length", _dp), ("width", _dp), ("mass", _dp), ("is_protected", _ip), ("responsibility", _ip),
+    ]
+
+
+class Step(C.Structure):
+    _fields_ = [
+        ("c_s", C.c_double), ("c_s_d", C.c_double), ("c_s_dd", C.c_double),
+        ("c_d", C.c_double), ("c_d_d", C.c_double), ("c_d_dd", C.c_double),
+        ("v_list", _dp), ("nv", C.c_int32),
+        ("t_list", _dp), ("nt", C.c_int32),
+        ("n_samples", _ip),
+        ("d_list", _dp), ("nd", C.c_int32),
+        ("dt", C.c_double), ("v_thr", C.c_double),
+        ("velocity_cost_mode", C.c_int32),
+        ("velocity_target", C.c_double),
+        ("cost_factor", C.c_double),
+        ("ext_level", _bp),
+        ("bd_harm", _dp),
+        ("c_begin", C.c_int32), ("c_end", C.c_int32),
+    ]
+
+
+class Out(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int32),
+        ("traj", C.c_void_p), ("prob", C.c_void_p), ("red", C.c_void_p), ("cost", C.c_void_p),
+        ("level", C.c_void_p), ("reason", C.c_void_p),
+    ]
+
+
+class Best(C.Structure):
+    _fields_ = [
+        ("key_hi", C.c_uint64), ("key_lo", C.c_uint64), ("cost", C.c_double),
+        ("index", C.c_int32), ("level", C.c_int32), ("n_scored", C.c_int32), ("list_index", C.c_int32),
+    ]
+
+
+# every symbol include/etp_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "etp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "etp_destroy": (C.c_int, [C.c_void_p]),
+    "etp_last_error": (C.c_char_p, [C.c_void_p]),
+    "etp_version": (C.c_char_p, []),
+    "etp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "etp_set_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
+    "etp_set_spline": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int]),
+    "etp_set_obstacles": (C.c_int, [C.c_void_p, C.POINTER(Obstacles), C.c_int]),
+    "etp_plan_step": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Out)]),
+    "etp_tmax": (C.c_int, [C.POINTER(Step)]),
+    "etp_get_best": (C.c_int, [C.c_void_p, C.POINTER(Best)]),
+    "etp_get_trajectory": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),
+    "etp_combine_best": (C.c_int, [C.POINTER(Best), C.c_int, C.POINTER(Best)]),
+}
+
+
+def nvcc_command(out_path=LIB_PATH, extra=()):
+    return ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out_path, *SOURCES, *extra]
+
+
+def library_is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build_library(force=False, verbose=False):
+    """Compile the kernels + C ABI in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    if not force and not library_is_stale():
+        return LIB_PATH
+    cmd = nvcc_command()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises (no fallback) when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the scoring path has no CPU fallback. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib

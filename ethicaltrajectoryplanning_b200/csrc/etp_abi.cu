@@ -1,0 +1,444 @@
+// C ABI of the scoring path (include/etp_b200.h): context, input staging, launches, readback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "etp_launch.h"
+
+using namespace etp;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    unsigned char* p = nullptr;
+    size_t cap = 0, used = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct etp_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t staged = nullptr;
+    bool staged_pending = false;
+    std::string err;
+    bool have_params = false, have_spline = false, have_obs = false, have_step = false;
+    DevParams pr{};
+    int precision = ETP_PRECISION_FP32;
+    // spline
+    DevBuf knots, cx, cy;
+    int nseg = 0;
+    // obstacles
+    DevBuf o_pos, o_cov, o_yaw, o_vel, o_len, o_mass, o_plen, o_prot, o_resp, o_tile, o_const;
+    int O = 0, Tp = 0, has_pred = 0;
+    // step
+    DevBuf grids, ext_level, bd_harm, prof, prof_meta, nskip;
+    DevBuf block_best, counters, best_dev, traj_dev, traj_n;
+    PinnedBuf stage, best_host, traj_host;
+    DevStep st{};
+    int last_grid = 0;
+};
+
+#define ETP_FAIL(ctx, code, ...)                            \
+    do {                                                    \
+        char _b[512];                                       \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);              \
+        (ctx)->err = _b;                                    \
+        return (code);                                      \
+    } while (0)
+
+#define ETP_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            ETP_FAIL(ctx, ETP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+// host bytes -> pinned staging -> device, asynchronous on the context stream
+int stage_to_device(etp_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return ETP_OK;
+    const size_t aligned = (bytes + 255) & ~size_t(255);
+    if (c->stage.used + aligned > c->stage.cap) {
+        // drain the copies in flight, then reuse (or grow) the staging area
+        ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->stage.used = 0;
+        if (aligned > c->stage.cap) {
+            size_t want = c->stage.cap ? c->stage.cap : (size_t)1 << 20;
+            while (want < aligned) want *= 2;
+            ETP_CUDA(c, c->stage.reserve(want));
+        }
+    }
+    unsigned char* h = c->stage.p + c->stage.used;
+    memcpy(h, src, bytes);
+    c->stage.used += aligned;
+    ETP_CUDA(c, cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return ETP_OK;
+}
+
+int begin_staging(etp_ctx* c) {
+    if (c->staged_pending) {
+        ETP_CUDA(c, cudaEventSynchronize(c->staged));
+        c->staged_pending = false;
+    }
+    c->stage.used = 0;
+    return ETP_OK;
+}
+
+int end_staging(etp_ctx* c) {
+    ETP_CUDA(c, cudaEventRecord(c->staged, c->stream));
+    c->staged_pending = true;
+    return ETP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* etp_version(void) { return "etp_b200 0.1 (sm_100a)"; }
+
+int etp_create(etp_ctx** out, int device) {
+    if (!out) return ETP_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return ETP_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ETP_ERR_CUDA;
+    etp_ctx* c = new etp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
+    c->stream = c->own_stream;
+    if (cudaEventCreateWithFlags(&c->staged, cudaEventDisableTiming) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
+    bool ok = c->stage.reserve((size_t)4 << 20) == cudaSuccess && c->best_host.reserve(sizeof(BestRec)) == cudaSuccess &&
+              c->block_best.reserve(sizeof(BestRec) * kMaxGrid) == cudaSuccess &&
+              c->counters.reserve(64) == cudaSuccess && c->best_dev.reserve(sizeof(BestRec)) == cudaSuccess &&
+              c->traj_n.reserve(sizeof(int)) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->counters.p, 0, 64) == cudaSuccess && cudaMemset(c->best_dev.p, 0, sizeof(BestRec)) == cudaSuccess;
+    if (!ok) { etp_destroy(c); return ETP_ERR_CUDA; }
+    *out = c;
+    return ETP_OK;
+}
+
+int etp_destroy(etp_ctx* c) {
+    if (!c) return ETP_OK;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
+                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->grids, &c->ext_level, &c->bd_harm,
+                      &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
+                      &c->traj_n};
+    for (DevBuf* b : bufs) b->release();
+    c->stage.release();
+    c->best_host.release();
+    c->traj_host.release();
+    if (c->staged) cudaEventDestroy(c->staged);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return ETP_OK;
+}
+
+const char* etp_last_error(const etp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int etp_set_stream(etp_ctx* c, void* s) {
+    if (!c) return ETP_ERR_INVALID;
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return ETP_OK;
+}
+
+int etp_set_params(etp_ctx* c, const etp_params* p) {
+    if (!c || !p) return ETP_ERR_INVALID;
+    if (p->weights[ETP_W_RESPONSIBILITY] > 0.0)
+        ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "weights['responsibility'] > 0 needs reachable sets (planner/utils/reachable_set.py): out of scope");
+    if (p->weights[ETP_W_VISIBLE_AREA] > 0.0 || p->weights[ETP_W_DIST_TO_GOAL_POS] > 0.0 ||
+        p->weights[ETP_W_DIST_TO_LANE_CENTER] > 0.0)
+        ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "visible_area / dist_to_goal_pos / dist_to_lane_center are host-side cost terms");
+    if (p->n_angle_thresholds < 0 || p->n_angle_thresholds > ETP_MAX_ANGLE_BINS)
+        ETP_FAIL(c, ETP_ERR_INVALID, "n_angle_thresholds out of range");
+    if (p->planner_mode < ETP_MODE_RISK || p->planner_mode > ETP_MODE_GROUND_TRUTH) ETP_FAIL(c, ETP_ERR_INVALID, "planner_mode");
+    DevParams& d = c->pr;
+    for (int i = 0; i < ETP_NUM_WEIGHTS; ++i) d.w[i] = p->weights[i];
+    d.planner_mode = p->planner_mode;
+    d.mahalanobis = p->fast_prob_mahalanobis;
+    d.multi_cost = p->multiple_cost_functions;
+    d.n_thr = p->n_angle_thresholds;
+    d.max_risk = p->max_acceptable_risk;
+    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) d.thr[i] = p->angle_thr[i];
+    for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { d.coef_pos[i] = p->angle_coef_pos[i]; d.coef_neg[i] = p->angle_coef_neg[i]; }
+    d.lr_const = p->lr_const; d.lr_speed = p->lr_speed;
+    d.lr1s_const = p->lr1s_const; d.lr1s_speed = p->lr1s_speed;
+    d.ped_const = p->ped_const; d.ped_speed = p->ped_speed;
+    d.veh_l = p->veh_l; d.veh_w = p->veh_w; d.veh_m = p->veh_m; d.v_max = p->veh_v_max;
+    // validity_checks.py:193-199
+    const double tn = std::tan(p->veh_steer_max);
+    const double radius = std::sqrt((p->veh_l * p->veh_l / (tn * tn)) + (p->veh_l_r * p->veh_l_r));
+    d.inv_turn_radius = 1.0 / radius;
+    d.v_thr_curv = std::sqrt(p->veh_lat_a_max * radius);
+    d.lat_a_max = p->veh_lat_a_max;
+    c->have_params = true;
+    return ETP_OK;
+}
+
+int etp_set_spline(etp_ctx* c, const double* knots, const double* coef_x, const double* coef_y, int n_seg) {
+    if (!c || !knots || !coef_x || !coef_y || n_seg < 1) return ETP_ERR_INVALID;
+    for (int i = 0; i < n_seg; ++i)
+        if (!(knots[i + 1] > knots[i])) ETP_FAIL(c, ETP_ERR_INVALID, "spline knots must be strictly increasing");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    int r = begin_staging(c);
+    if (r) return r;
+    ETP_CUDA(c, c->knots.reserve(sizeof(double) * (n_seg + 1)));
+    ETP_CUDA(c, c->cx.reserve(sizeof(double) * 4 * n_seg));
+    ETP_CUDA(c, c->cy.reserve(sizeof(double) * 4 * n_seg));
+    if ((r = stage_to_device(c, c->knots.p, knots, sizeof(double) * (n_seg + 1)))) return r;
+    if ((r = stage_to_device(c, c->cx.p, coef_x, sizeof(double) * 4 * n_seg))) return r;
+    if ((r = stage_to_device(c, c->cy.p, coef_y, sizeof(double) * 4 * n_seg))) return r;
+    c->nseg = n_seg;
+    c->have_spline = true;
+    return end_staging(c);
+}
+
+int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
+    if (!c || !o) return ETP_ERR_INVALID;
+    if (precision != ETP_PRECISION_FP32 && precision != ETP_PRECISION_FP64) ETP_FAIL(c, ETP_ERR_INVALID, "precision");
+    if (!c->have_params) ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params must precede etp_set_obstacles (mass ratios use the ego mass)");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    c->precision = precision;
+    if (o->n_obstacles < 0) {  // predictions is None
+        c->has_pred = 0; c->O = 0; c->Tp = 0; c->have_obs = true;
+        return ETP_OK;
+    }
+    c->has_pred = 1;
+    const int O = o->n_obstacles, Tp = o->max_pred;
+    if (O > 0) {
+        if (Tp < 1 || !o->pred_len || !o->pos || !o->cov || !o->yaw || !o->vel || !o->length || !o->mass || !o->is_protected ||
+            !o->responsibility)
+            ETP_FAIL(c, ETP_ERR_INVALID, "obstacle arrays missing");
+        for (int i = 0; i < O; ++i) {
+            if (o->pred_len[i] < 1 || o->pred_len[i] > Tp)
+                ETP_FAIL(c, ETP_ERR_INVALID, "pred_len[%d]=%d outside [1, max_pred]; empty predictions are dropped by the caller "
+                         "(prediction_helpers.py:98-100)", i, o->pred_len[i]);
+            if (o->is_protected[i] != 0 && o->is_protected[i] != 1)
+                ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "obstacle %d has no protection class (harm_estimation.py:52-56): unsupported input", i);
+        }
+        int r = begin_staging(c);
+        if (r) return r;
+        const size_t n = (size_t)O * Tp;
+        ETP_CUDA(c, c->o_pos.reserve(sizeof(double) * 2 * n));
+        ETP_CUDA(c, c->o_cov.reserve(sizeof(double) * 4 * n));
+        ETP_CUDA(c, c->o_yaw.reserve(sizeof(double) * n));
+        ETP_CUDA(c, c->o_vel.reserve(sizeof(double) * n));
+        ETP_CUDA(c, c->o_len.reserve(sizeof(double) * O));
+        ETP_CUDA(c, c->o_mass.reserve(sizeof(double) * O));
+        ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_resp.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_tile.reserve(sizeof(double) * OF_COUNT * n));
+        ETP_CUDA(c, c->o_const.reserve(sizeof(double) * OC_COUNT * O));
+        if ((r = stage_to_device(c, c->o_pos.p, o->pos, sizeof(double) * 2 * n))) return r;
+        if ((r = stage_to_device(c, c->o_cov.p, o->cov, sizeof(double) * 4 * n))) return r;
+        if ((r = stage_to_device(c, c->o_yaw.p, o->yaw, sizeof(double) * n))) return r;
+        if ((r = stage_to_device(c, c->o_vel.p, o->vel, sizeof(double) * n))) return r;
+        if ((r = stage_to_device(c, c->o_len.p, o->length, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_mass.p, o->mass, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_plen.p, o->pred_len, sizeof(int) * O))) return r;
+        if ((r = stage_to_device(c, c->o_prot.p, o->is_protected, sizeof(int) * O))) return r;
+        if ((r = stage_to_device(c, c->o_resp.p, o->responsibility, sizeof(int) * O))) return r;
+        if ((r = end_staging(c))) return r;
+        ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
+                                          c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
+                                          c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
+                                          c->o_tile.p, c->o_const.as<double>(), c->stream));
+    }
+    c->O = O;
+    c->Tp = Tp;
+    c->have_obs = true;
+    return ETP_OK;
+}
+
+int etp_tmax(const etp_step* s) {
+    if (!s || !s->n_samples || s->nt < 1) return ETP_ERR_INVALID;
+    int m = 0;
+    for (int i = 0; i < s->nt; ++i) m = s->n_samples[i] > m ? s->n_samples[i] : m;
+    return m;
+}
+
+int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
+    if (!c || !s) return ETP_ERR_INVALID;
+    if (!c->have_params || !c->have_spline || !c->have_obs)
+        ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params / etp_set_spline / etp_set_obstacles must be called before etp_plan_step");
+    if (s->nv < 1 || s->nt < 1 || s->nd < 1 || !s->v_list || !s->t_list || !s->d_list || !s->n_samples)
+        ETP_FAIL(c, ETP_ERR_INVALID, "empty sampling grid");
+    const long long dense = (long long)s->nv * s->nt * s->nd;
+    if (dense >= (1ll << 31)) ETP_FAIL(c, ETP_ERR_INVALID, "more than 2^31 candidates");
+    if (s->c_begin < 0 || s->c_end > dense || s->c_begin >= s->c_end) ETP_FAIL(c, ETP_ERR_INVALID, "candidate range");
+    if (s->c_begin % s->nd != 0 || s->c_end % s->nd != 0)
+        ETP_FAIL(c, ETP_ERR_INVALID, "candidate range must be aligned to whole (v,t) profiles (multiples of nd=%d)", s->nd);
+    const int Tmax = etp_tmax(s);
+    for (int i = 0; i < s->nt; ++i)
+        if (s->n_samples[i] < 2) ETP_FAIL(c, ETP_ERR_INVALID, "n_samples[%d] < 2", i);
+    if (Tmax > 256) ETP_FAIL(c, ETP_ERR_INVALID, "more than 256 samples per trajectory");
+    if (out && out->precision != c->precision)
+        ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.precision differs from the precision given to etp_set_obstacles");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    int r = begin_staging(c);
+    if (r) return r;
+
+    // grids blob: v_list | t_list | d_list | n_samples
+    const size_t off_v = 0, off_t = off_v + sizeof(double) * s->nv, off_d = off_t + sizeof(double) * s->nt,
+                 off_n = off_d + sizeof(double) * s->nd, total = off_n + sizeof(int) * s->nt;
+    ETP_CUDA(c, c->grids.reserve(total));
+    {
+        std::vector<unsigned char> blob(total);
+        memcpy(blob.data() + off_v, s->v_list, sizeof(double) * s->nv);
+        memcpy(blob.data() + off_t, s->t_list, sizeof(double) * s->nt);
+        memcpy(blob.data() + off_d, s->d_list, sizeof(double) * s->nd);
+        memcpy(blob.data() + off_n, s->n_samples, sizeof(int) * s->nt);
+        if ((r = stage_to_device(c, c->grids.p, blob.data(), total))) return r;
+    }
+    DevStep& st = c->st;
+    st = DevStep{};
+    if (s->ext_level) {
+        ETP_CUDA(c, c->ext_level.reserve((size_t)dense));
+        if ((r = stage_to_device(c, c->ext_level.p, s->ext_level, (size_t)dense))) return r;
+        st.ext_level = c->ext_level.as<uint8_t>();
+    }
+    if (s->bd_harm) {
+        ETP_CUDA(c, c->bd_harm.reserve(sizeof(double) * (size_t)dense));
+        if ((r = stage_to_device(c, c->bd_harm.p, s->bd_harm, sizeof(double) * (size_t)dense))) return r;
+        st.bd_harm = c->bd_harm.as<double>();
+    }
+    if ((r = end_staging(c))) return r;
+
+    unsigned char* g = c->grids.as<unsigned char>();
+    st.c_s = s->c_s; st.c_s_d = s->c_s_d; st.c_s_dd = s->c_s_dd;
+    st.c_d = s->c_d; st.c_d_d = s->c_d_d; st.c_d_dd = s->c_d_dd;
+    st.dt = s->dt; st.v_thr = s->v_thr;
+    st.v_list = reinterpret_cast<const double*>(g + off_v);
+    st.t_list = reinterpret_cast<const double*>(g + off_t);
+    st.d_list = reinterpret_cast<const double*>(g + off_d);
+    st.nsamp = reinterpret_cast<const int*>(g + off_n);
+    st.nv = s->nv; st.nt = s->nt; st.nd = s->nd; st.Tmax = Tmax;
+    st.c_begin = s->c_begin; st.c_end = s->c_end;
+    st.p_begin = s->c_begin / s->nd; st.p_end = s->c_end / s->nd;
+    st.vel_mode = s->velocity_cost_mode; st.vel_target = s->velocity_target; st.factor = s->cost_factor;
+    st.knots = c->knots.as<double>(); st.cx = c->cx.as<double>(); st.cy = c->cy.as<double>(); st.nseg = c->nseg;
+    const int n_prof = st.p_end - st.p_begin;
+    ETP_CUDA(c, c->prof.reserve(sizeof(double) * PF_COUNT * Tmax * (size_t)n_prof));
+    ETP_CUDA(c, c->prof_meta.reserve(sizeof(double) * PM_COUNT * (size_t)n_prof));
+    ETP_CUDA(c, c->nskip.reserve(sizeof(int) * (size_t)n_prof));
+    st.prof = c->prof.as<double>();
+    st.prof_meta = c->prof_meta.as<double>();
+    st.has_pred = c->has_pred; st.O = c->O; st.Tp = c->Tp;
+    st.obs = c->o_tile.p; st.obs_const = c->o_const.as<double>(); st.pred_len = c->o_plen.as<int>();
+    st.raw_pos = c->o_pos.as<double>(); st.raw_yaw = c->o_yaw.as<double>();
+
+    DevOut dout{};
+    if (out) {
+        dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
+        dout.level = out->level; dout.reason = out->reason;
+    }
+    ETP_CUDA(c, launch_profiles(st, c->pr, c->nskip.as<int>(), c->stream));
+    ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, c->block_best.as<BestRec>(), c->counters.as<unsigned>(),
+                             c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, &c->last_grid, c->stream));
+    c->have_step = true;
+    return ETP_OK;
+}
+
+int etp_get_best(etp_ctx* c, etp_best* best) {
+    if (!c || !best) return ETP_ERR_INVALID;
+    if (!c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "no planning step has run on this context");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    ETP_CUDA(c, cudaMemcpyAsync(c->best_host.p, c->best_dev.p, sizeof(BestRec), cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    const BestRec* b = reinterpret_cast<const BestRec*>(c->best_host.p);
+    best->key_hi = b->key_hi; best->key_lo = b->key_lo; best->cost = b->cost; best->index = b->index;
+    best->level = b->level; best->n_scored = b->n_scored; best->list_index = b->list_index;
+    if (b->index < 0)
+        ETP_FAIL(c, ETP_ERR_NO_CANDIDATE, "every candidate of the range was skipped (ds <= |dT|); the reference raises ValueError here");
+    return ETP_OK;
+}
+
+int etp_get_trajectory(etp_ctx* c, int index, double* fields, int* n_samples) {
+    if (!c || !fields) return ETP_ERR_INVALID;
+    if (!c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "no planning step has run on this context");
+    const DevStep& st = c->st;
+    if (index < st.c_begin || index >= st.c_end) ETP_FAIL(c, ETP_ERR_INVALID, "candidate %d outside the last scored range", index);
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * ETP_NUM_FIELDS * st.Tmax;
+    ETP_CUDA(c, c->traj_dev.reserve(bytes));
+    ETP_CUDA(c, c->traj_host.reserve(bytes + sizeof(int)));
+    ETP_CUDA(c, launch_trajectory(st, index, c->traj_dev.as<double>(), c->traj_n.as<int>(), c->stream));
+    ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, c->traj_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p + bytes, c->traj_n.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(fields, c->traj_host.p, bytes);
+    if (n_samples) memcpy(n_samples, c->traj_host.p + bytes, sizeof(int));
+    return ETP_OK;
+}
+
+int etp_combine_best(const etp_best* b, int n, etp_best* out) {
+    if (!b || !out || n < 1) return ETP_ERR_INVALID;
+    int win = -1, scored_before_win = 0, scored = 0;
+    for (int i = 0; i < n; ++i) {
+        if (b[i].index >= 0 &&
+            (win < 0 || b[i].key_hi < b[win].key_hi || (b[i].key_hi == b[win].key_hi && b[i].key_lo < b[win].key_lo))) {
+            win = i;
+            scored_before_win = scored;
+        }
+        scored += b[i].n_scored;
+    }
+    if (win < 0) {
+        *out = b[0];
+        out->index = -1;
+        out->n_scored = scored;
+        return ETP_ERR_NO_CANDIDATE;
+    }
+    *out = b[win];
+    out->n_scored = scored;
+    out->list_index = scored_before_win + b[win].list_index;  // shards are given in dense order
+    return ETP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// Device-side structures and math shared by the scoring kernels (sm_100a).
+//
+// Citations are to the reference tree (TUMFTM/EthicalTrajectoryPlanning), paths relative to its root.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/etp_b200.h"
+
+namespace etp {
+
+// rows of the per-profile table written by profile_kernel (all fp64)
+enum { PF_S = 0, PF_S_D, PF_S_DD, PF_S_DDD, PF_GX, PF_GY, PF_YAW, PF_CURV, PF_CURV_D, PF_SIN, PF_COS, PF_COUNT };
+// per-profile scalars
+enum { PM_DS = 0, PM_LOW, PM_T, PM_VEL_OK, PM_TEND, PM_COUNT };
+
+// rows of the packed obstacle tile, layout [field][o][t], element type R
+enum {
+    OF_MX = 0, OF_MY,      // pos_list[t]
+    OF_EX, OF_EY,          // (length/2) * (cos, sin)(orientation_list[t+1])   (collision_probability.py:175)
+    OF_ISX, OF_ISY, OF_RHO,// 1/stdev_x, 1/stdev_y, correlation of cov_list[t] (zero matrix -> 0.1*I, :205-212)
+    OF_PSI, OF_VO,         // orientation_list[t], v_list[t]                     (harm_estimation.py:313-328)
+    OF_CPSI, OF_SPSI,      // cos / sin of orientation_list[t]
+    OF_I00, OF_I01, OF_I11,// inverse covariance (Mahalanobis mode, collision_probability.py:279)
+    OF_COUNT
+};
+// per-obstacle constants [o][OC_COUNT], fp64
+enum { OC_KE = 0, OC_KO, OC_PROT, OC_RESP, OC_HALFLEN, OC_COUNT };
+
+struct DevParams {
+    double w[ETP_NUM_WEIGHTS];
+    int planner_mode, mahalanobis, multi_cost, n_thr;
+    double max_risk;
+    double thr[ETP_MAX_ANGLE_BINS];
+    double coef_pos[ETP_MAX_ANGLE_BINS + 1];
+    double coef_neg[ETP_MAX_ANGLE_BINS + 1];
+    double lr_const, lr_speed, lr1s_const, lr1s_speed, ped_const, ped_speed;
+    double veh_l, veh_w, veh_m, v_max;
+    double inv_turn_radius, v_thr_curv, lat_a_max;
+};
+
+struct DevStep {
+    double c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd, dt, v_thr;
+    const double* v_list;
+    const double* t_list;
+    const double* d_list;
+    const int* nsamp;
+    int nv, nt, nd, Tmax;
+    int c_begin, c_end, p_begin, p_end;
+    int vel_mode;
+    double vel_target, factor;
+    const uint8_t* ext_level;  // device copy, indexed by dense candidate, or null
+    const double* bd_harm;     // device copy, indexed by dense candidate, or null
+    // spline tables
+    const double* knots;
+    const double* cx;
+    const double* cy;
+    int nseg;
+    // per-profile table [p - p_begin][PF_COUNT][Tmax] and scalars [p - p_begin][PM_COUNT]
+    double* prof;
+    double* prof_meta;
+    // obstacles
+    int has_pred;  // 0: predictions is None
+    int O, Tp;
+    const void* obs;         // packed tile [OF_COUNT][O][Tp] of R
+    const double* obs_const; // [O][OC_COUNT]
+    const int* pred_len;     // [O]
+    // raw fp64 copies for the exact gate re-check of the fp32 path
+    const double* raw_pos;   // [O][Tp][2]
+    const double* raw_yaw;   // [O][Tp]
+};
+
+struct DevOut {
+    void* traj;
+    void* prob;
+    void* red;
+    void* cost;
+    uint8_t* level;
+    uint8_t* reason;
+};
+
+struct BestRec {
+    unsigned long long key_hi, key_lo;
+    double cost;
+    int index, level, n_scored, list_index;
+};
+
+__host__ __device__ inline int level_rank(int level) { return level == 10 ? 4 : level; }
+
+// monotone map of a double to u64 (smaller double -> smaller key); NaN maps to the maximum
+__device__ __forceinline__ unsigned long long monotone_key(double x) {
+    if (x != x) return ~0ull;
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ unsigned long long make_key_hi(int level, double cost) {
+    return ((unsigned long long)(4 - level_rank(level)) << 60) | (monotone_key(cost) >> 4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lateral quintic with end velocity / acceleration zero (polynomials.py:9-55, closed form of the
+// 3x3 solve) and the longitudinal quartic (polynomials.py:146-177)
+// ---------------------------------------------------------------------------------------------
+struct Poly5 {
+    double a0, a1, a2, a3, a4, a5;
+    __device__ __forceinline__ double p(double t) const {
+        double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
+        return a0 + a1 * t + a2 * t2 + a3 * t3 + a4 * t4 + a5 * t5;
+    }
+    __device__ __forceinline__ double d1(double t) const {
+        double t2 = t * t, t3 = t2 * t, t4 = t2 * t2;
+        return a1 + 2 * a2 * t + 3 * a3 * t2 + 4 * a4 * t3 + 5 * a5 * t4;
+    }
+    __device__ __forceinline__ double d2(double t) const {
+        double t2 = t * t, t3 = t2 * t;
+        return 2 * a2 + 6 * a3 * t + 12 * a4 * t2 + 20 * a5 * t3;
+    }
+    __device__ __forceinline__ double d3(double t) const {
+        double t2 = t * t;
+        return 6 * a3 + 24 * a4 * t + 60 * a5 * t2;
+    }
+};
+
+__device__ __forceinline__ Poly5 make_quintic(double xs, double vxs, double axs, double xe, double T) {
+    Poly5 q;
+    q.a0 = xs;
+    q.a1 = vxs;
+    q.a2 = axs / 2.0;
+    double T2 = T * T, T3 = T2 * T, T4 = T2 * T2, T5 = T4 * T;
+    double b0 = xe - q.a0 - q.a1 * T - q.a2 * T2;
+    double b1 = 0.0 - q.a1 - 2 * q.a2 * T;
+    double b2 = 0.0 - 2 * q.a2;
+    q.a3 = (10.0 * b0 - 4.0 * b1 * T + 0.5 * b2 * T2) / T3;
+    q.a4 = (-15.0 * b0 + 7.0 * b1 * T - b2 * T2) / T4;
+    q.a5 = (6.0 * b0 - 3.0 * b1 * T + 0.5 * b2 * T2) / T5;
+    return q;
+}
+
+// lateral polynomial of candidate (profile, dT): time parametrised for high velocities, arclength
+// parametrised for low velocities (frenet_functions.py:336-411)
+__device__ __forceinline__ Poly5 lateral_poly(const DevStep& st, bool low, double dT, double t_end, double ds) {
+    if (!low) return make_quintic(st.c_d, st.c_d_d, st.c_d_dd, dT, t_end);
+    double dd_nt = 0.0, ddd_nt = 0.0;
+    if (st.c_s_d != 0.0) {
+        dd_nt = st.c_d_d / st.c_s_d;
+        ddd_nt = (st.c_d_dd - st.c_s_dd * dd_nt) / (st.c_s_d * st.c_s_d);
+    }
+    return make_quintic(st.c_d, dd_nt, ddd_nt, dT, ds);
+}
+
+struct TrajPoint {
+    double f[ETP_NUM_FIELDS];
+    double cos_yaw, sin_yaw;
+};
+
+// One sample of one candidate: frenet_functions.py:357-365 / 404-411 (lateral state) and 420-435
+// (Frenet -> Cartesian).  `pf` points at the profile rows, stride `ts` between rows.
+__device__ __forceinline__ TrajPoint traj_point(const Poly5& q, bool low, const double* pf, int ts, int t, double dt) {
+    TrajPoint r;
+    const double s = pf[PF_S * ts + t], s_d = pf[PF_S_D * ts + t], s_dd = pf[PF_S_DD * ts + t];
+    const double kr = pf[PF_CURV * ts + t], krd = pf[PF_CURV_D * ts + t];
+    const double sr = pf[PF_SIN * ts + t], cr = pf[PF_COS * ts + t];
+    double d, dp, dpp, d3, d_d_time, d_dd_time;
+    if (!low) {
+        const double tau = t * dt;
+        d = q.p(tau);
+        d_d_time = q.d1(tau);
+        d_dd_time = q.d2(tau);
+        d3 = q.d3(tau);
+        dp = d_d_time / s_d;
+        dpp = (d_dd_time - dp * s_dd) / (s_d * s_d);
+    } else {
+        const double tau = s - pf[PF_S * ts + 0];
+        d = q.p(tau);
+        dp = q.d1(tau);
+        dpp = q.d2(tau);
+        d3 = q.d3(tau);
+        d_d_time = s_d * dp;
+        d_dd_time = s_dd * dp + (s_d * s_d) * dpp;
+    }
+    const double om = 1.0 - kr * d;
+    const double z = dp / om;
+    const double dpsi = atan(z);
+    const double cd = 1.0 / sqrt(1.0 + z * z);  // cos(atan z)
+    const double sd = z * cd;                   // sin(atan z)
+    r.f[ETP_F_D] = d;
+    r.f[ETP_F_D_D] = d_d_time;
+    r.f[ETP_F_D_DD] = d_dd_time;
+    r.f[ETP_F_D_DDD] = d3;
+    r.f[ETP_F_S] = s;
+    r.f[ETP_F_S_D] = s_d;
+    r.f[ETP_F_S_DD] = s_dd;
+    r.f[ETP_F_S_DDD] = pf[PF_S_DDD * ts + t];
+    r.f[ETP_F_X] = pf[PF_GX * ts + t] - d * sr;
+    r.f[ETP_F_Y] = pf[PF_GY * ts + t] + d * cr;
+    r.f[ETP_F_YAW] = dpsi + pf[PF_YAW * ts + t];
+    r.f[ETP_F_V] = (s_d * om) / cd;
+    r.f[ETP_F_CURV] = (((dpp + (krd * d + kr * dp) * z) * ((cd * cd) / om)) + kr) * (cd / om);
+    r.cos_yaw = cd * cr - sd * sr;
+    r.sin_yaw = sd * cr + cd * sr;
+    return r;
+}
+
+// curvature test of validity_checks.py:180-213 for one sample: 0 ok, 1 "lvc", 2 "hvc"
+__device__ __forceinline__ int curvature_fail(const DevParams& pr, double v, double curv) {
+    const double c = fabs(curv);
+    if (v < pr.v_thr_curv) return (c > pr.inv_turn_radius) ? 1 : 0;
+    const double cmax = pr.lat_a_max / (v * v);
+    return (c > cmax) ? 2 : 0;
+}
+
+}  // namespace etp

@@ -1,0 +1,935 @@
+// Scoring kernels of the B200-native candidate-trajectory path (sm_100a).
+//
+//   pack_obstacles_kernel : predictions (SoA fp64) -> packed obstacle tile [field][o][t] of R
+//   profile_kernel        : per (v,t) profile stage in fp64: quartic, spline lookup, chained
+//                           non-uniform gradients, reference yaw / curvature / curvature'
+//                           (frenet_functions.py:258-325)
+//   score_kernel<R>       : fused per-candidate pass: quintic + Frenet->Cartesian + validity masks,
+//                           collision probability, harm, risk maxima over time, ethical principle
+//                           costs, weighted cost, validity level, block arg-min; last block
+//                           finishes the grid arg-min (frenet_functions.py:330-474, 529-593;
+//                           collision_probability.py:136-256; harm_estimation.py:306-332;
+//                           risk_costs.py:87-101,128-255; calc_trajectory_cost.py:103-146,279-346)
+//   trajectory_kernel     : one candidate recomputed in fp64 for the host (frenet_planner.py:564-576)
+#include <cooperative_groups.h>
+
+#include "etp_bvn.cuh"
+#include "etp_device.cuh"
+#include "etp_launch.h"
+
+namespace etp {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kQueue = 64;  // per-warp deferred (un-gated) evaluations
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// small typed helpers
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct Enc;
+template <> struct Enc<float> {
+    using U = unsigned int;
+    static __device__ __forceinline__ U enc(float x) {
+        U b = __float_as_uint(x);
+        return (b >> 31) ? ~b : (b | 0x80000000u);
+    }
+    static __device__ __forceinline__ float dec(U k) {
+        U b = (k >> 31) ? (k & 0x7fffffffu) : ~k;
+        return __uint_as_float(b);
+    }
+};
+template <> struct Enc<double> {
+    using U = unsigned long long;
+    static __device__ __forceinline__ U enc(double x) {
+        U b = (U)__double_as_longlong(x);
+        return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double dec(U k) {
+        U b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        return __longlong_as_double((long long)b);
+    }
+};
+
+template <typename R> __device__ __forceinline__ R rmax_(R a, R b) { return a > b ? a : b; }
+__device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float cos_(float x) { return cosf(x); }
+__device__ __forceinline__ double cos_(double x) { return cos(x); }
+__device__ __forceinline__ float exp_(float x) { return expf(x); }
+__device__ __forceinline__ double exp_(double x) { return exp(x); }
+__device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_(double x) { return fabs(x); }
+
+template <typename T> __device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(kFull, v, o);
+        v = u > v ? u : v;
+    }
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack_obstacles_kernel
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
+                                      const double* __restrict__ cov, const double* __restrict__ yaw,
+                                      const double* __restrict__ vel, const double* __restrict__ length,
+                                      const double* __restrict__ mass, const int* __restrict__ prot,
+                                      const int* __restrict__ resp, double veh_m, R* __restrict__ tile,
+                                      double* __restrict__ oconst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= O * Tp) return;
+    const int o = i / Tp, t = i % Tp;
+    const int n = pred_len[o];
+    const size_t plane = (size_t)O * Tp;
+    R* out = tile + (size_t)o * Tp + t;
+    double v[OF_COUNT];
+    for (int f = 0; f < OF_COUNT; ++f) v[f] = 0.0;
+    if (t < n) {
+        const double* p = pos + ((size_t)o * Tp + t) * 2;
+        const double* c = cov + ((size_t)o * Tp + t) * 4;
+        v[OF_MX] = p[0];
+        v[OF_MY] = p[1];
+        if (t + 1 < n) {
+            const double y1 = yaw[(size_t)o * Tp + t + 1];
+            // np.stack((cos, sin)) * length / 2   (collision_probability.py:175)
+            v[OF_EX] = cos(y1) * length[o] / 2;
+            v[OF_EY] = sin(y1) * length[o] / 2;
+        }
+        double c00 = c[0], c01 = c[1], c10 = c[2], c11 = c[3];
+        if (c00 == 0.0 && c01 == 0.0 && c10 == 0.0 && c11 == 0.0) {  // collision_probability.py:210-212
+            c00 = 0.1; c11 = 0.1;
+        }
+        const double sx = sqrt(c00), sy = sqrt(c11);
+        v[OF_ISX] = 1.0 / sx;
+        v[OF_ISY] = 1.0 / sy;
+        v[OF_RHO] = c10 / sy / sx;  // mvnun takes the correlation from the lower triangle
+        const double psi = yaw[(size_t)o * Tp + t];
+        v[OF_PSI] = psi;
+        v[OF_VO] = vel[(size_t)o * Tp + t];
+        v[OF_CPSI] = cos(psi);
+        v[OF_SPSI] = sin(psi);
+        // Mahalanobis mode inverts cov_list itself (collision_probability.py:279), not the 0.1*I stand-in
+        const double r00 = c[0], r01 = c[1], r10 = c[2], r11 = c[3];
+        const double det = r00 * r11 - r01 * r10;
+        v[OF_I00] = r11 / det;
+        v[OF_I01] = -(r01 + r10) / det;
+        v[OF_I11] = r00 / det;
+    }
+    for (int f = 0; f < OF_COUNT; ++f) out[f * plane] = (R)v[f];
+    if (t == 0) {
+        const double mo = mass[o];
+        oconst[o * OC_COUNT + OC_KE] = mo / (veh_m + mo);     // harm_estimation.py:327
+        oconst[o * OC_COUNT + OC_KO] = veh_m / (veh_m + mo);  // harm_estimation.py:328
+        oconst[o * OC_COUNT + OC_PROT] = prot[o] ? 1.0 : 0.0;
+        oconst[o * OC_COUNT + OC_RESP] = (double)resp[o];
+        oconst[o * OC_COUNT + OC_HALFLEN] = length[o] / 2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// profile_kernel: one block per (v, t) profile, everything fp64
+// ---------------------------------------------------------------------------------------------
+// 32-ary search of the spline segment with warp ballots: the whole warp locates one abscissa.
+__device__ __forceinline__ int warp_find_segment(const double* __restrict__ knots, int nseg, double s, int lane) {
+    // largest i in [0, nseg-1] with knots[i] <= s (clamped): searchsorted(side='right') - 1
+    int lo = 0, hi = nseg;  // candidates lo .. hi-1
+    while (hi - lo > 1) {
+        const int span = hi - lo;
+        const int step = (span + 31) / 32;
+        const int idx = lo + lane * step;
+        const bool le = (idx < hi) && (knots[idx] <= s);
+        const unsigned m = __ballot_sync(kFull, le);
+        // lanes are monotone: knots increasing -> predicate is a prefix of ones (possibly empty)
+        const int ones = __popc(m);
+        if (ones == 0) return lo;  // s below the first knot of the window: clamp
+        const int base = lo + (ones - 1) * step;
+        lo = base;
+        hi = min(base + step, hi);
+    }
+    return lo;
+}
+
+// numpy.gradient(f, s) for non-uniform spacing: second order inside, first order at the ends
+__device__ __forceinline__ double np_gradient(const double* f, const double* s, int i, int n) {
+    if (i == 0) return (f[1] - f[0]) / (s[1] - s[0]);
+    if (i == n - 1) return (f[n - 1] - f[n - 2]) / (s[n - 1] - s[n - 2]);
+    const double dx1 = s[i] - s[i - 1], dx2 = s[i + 1] - s[i];
+    const double a = -(dx2) / (dx1 * (dx1 + dx2));
+    const double b = (dx2 - dx1) / (dx1 * dx2);
+    const double c = dx1 / (dx2 * (dx1 + dx2));
+    return a * f[i - 1] + b * f[i] + c * f[i + 1];
+}
+
+__global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr) {
+    extern __shared__ double sm[];
+    const int Tmax = st.Tmax;
+    double* s_s = sm;
+    double* s_x = sm + Tmax;
+    double* s_y = sm + 2 * Tmax;
+    double* s_a = sm + 3 * Tmax;  // dx   -> dddx
+    double* s_b = sm + 4 * Tmax;  // dy   -> dddy
+    double* s_c = sm + 5 * Tmax;  // ddx
+    double* s_d = sm + 6 * Tmax;  // ddy
+    const int p = st.p_begin + blockIdx.x;
+    const int iv = p / st.nt, it = p % st.nt;
+    const double vT = st.v_list[iv], tT = st.t_list[it];
+    const int T = st.nsamp[it];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* pf = st.prof + (size_t)blockIdx.x * PF_COUNT * Tmax;
+
+    // quartic_polynomial(xs=c_s, vxs=c_s_d, axs=c_s_dd, vxe=vT, axe=0, T=tT-dt)  (frenet_functions.py:258-260)
+    const double Te = tT - st.dt;
+    const double a0 = st.c_s, a1 = st.c_s_d, a2 = st.c_s_dd / 2.0;
+    const double b1 = vT - a1 - 2 * a2 * Te, b2 = 0.0 - 2 * a2;
+    const double a3 = (3.0 * b1 - b2 * Te) / (3.0 * Te * Te);
+    const double a4 = (b2 * Te - 2.0 * b1) / (4.0 * Te * Te * Te);
+
+    int vel_ok = 1;
+    for (int t = tid; t < T; t += blockDim.x) {
+        const double tt = t * st.dt;
+        const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2;
+        const double s = a0 + a1 * tt + a2 * t2 + a3 * t3 + a4 * t4;
+        const double sd = a1 + 2 * a2 * tt + 3 * a3 * t2 + 4 * a4 * t3;
+        s_s[t] = s;
+        pf[PF_S * Tmax + t] = s;
+        pf[PF_S_D * Tmax + t] = sd;
+        pf[PF_S_DD * Tmax + t] = 2 * a2 + 6 * a3 * tt + 12 * a4 * t2;
+        pf[PF_S_DDD * Tmax + t] = 6 * a3 + 24 * a4 * tt;
+        if (!(fabs(sd) <= pr.v_max)) vel_ok = 0;  // validity_checks.py:158
+    }
+    vel_ok = __syncthreads_and(vel_ok);
+    // reference position: one warp per abscissa, 32-ary segment search (csp.calc_position, :278)
+    for (int t = warp; t < T; t += blockDim.x / 32) {
+        const double s = s_s[t];
+        const int seg = warp_find_segment(st.knots, st.nseg, s, lane);
+        if (lane == 0) {
+            const double ds = s - st.knots[seg];
+            const double* cx = st.cx + 4 * seg;
+            const double* cy = st.cy + 4 * seg;
+            s_x[t] = cx[0] + cx[1] * ds + cx[2] * ds * ds + cx[3] * ds * ds * ds;
+            s_y[t] = cy[0] + cy[1] * ds + cy[2] * ds * ds + cy[3] * ds * ds * ds;
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) {  // dx, dy (:291,294)
+        s_a[t] = np_gradient(s_x, s_s, t, T);
+        s_b[t] = np_gradient(s_y, s_s, t, T);
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) {  // ddx, ddy (:292,295)
+        s_c[t] = np_gradient(s_a, s_s, t, T);
+        s_d[t] = np_gradient(s_b, s_s, t, T);
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) {
+        const double dx = s_a[t], dy = s_b[t], ddx = s_c[t], ddy = s_d[t];
+        const double dddx = np_gradient(s_c, s_s, t, T), dddy = np_gradient(s_d, s_s, t, T);  // :293,296
+        const double yaw = atan2(dy, dx);  // :302
+        // :308-310 -- the denominator is dx^2 + (dy^2)^(3/2) in the reference (operator precedence)
+        const double curv = (dx * ddy - ddx * dy) / (dx * dx + pow(dy * dy, 1.5));
+        // :316-325
+        const double z = dx * ddy - ddx * dy;
+        const double z_d = dx * dddy - dddx * dy;
+        const double q = dx * dx + dy * dy;
+        const double n = pow(q, 1.5);
+        const double n_d = 1.5 * (sqrt(q) * (2 * (dx * ddx) + 2 * (dy * ddy)));
+        const double curv_d = (z_d * n - z * n_d) / (n * n);
+        pf[PF_GX * Tmax + t] = s_x[t];
+        pf[PF_GY * Tmax + t] = s_y[t];
+        pf[PF_YAW * Tmax + t] = yaw;
+        pf[PF_CURV * Tmax + t] = curv;
+        pf[PF_CURV_D * Tmax + t] = curv_d;
+        pf[PF_SIN * Tmax + t] = sin(yaw);
+        pf[PF_COS * Tmax + t] = cos(yaw);
+    }
+    for (int t = T + tid; t < Tmax; t += blockDim.x)
+        for (int f = 0; f < PF_COUNT; ++f) pf[f * Tmax + t] = 0.0;
+    if (tid == 0) {
+        double* pm = st.prof_meta + (size_t)blockIdx.x * PM_COUNT;
+        pm[PM_DS] = s_s[T - 1] - s_s[0];                                                  // :327-328
+        pm[PM_LOW] = (fabs(st.c_s_d) < st.v_thr || fabs(vT) < st.v_thr) ? 1.0 : 0.0;  // :248-251
+        pm[PM_T] = (double)T;
+        pm[PM_VEL_OK] = (double)vel_ok;
+        pm[PM_TEND] = Te;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// score_kernel
+// ---------------------------------------------------------------------------------------------
+struct TileSmem {
+    // carved from dynamic shared memory by carve()
+    double* prof;    // [PF_COUNT][Ts]
+    double* xd;      // [ND][Ts] exact ego x (gate re-check, travelled distance)
+    double* yd;      // [ND][Ts]
+    void* ego;       // [6][ND][Ts] of R: x, y, cos yaw, sin yaw, v, yaw
+    void* hmax;      // [2][ND*O] of R
+    void* rmax;      // [2][ND*O] of Enc<R>::U
+    double* cstat;   // [ND][8]: sum v, sum |d|, sum s_ddd^2, sum d_ddd^2, travelled, first curvature failure, skip, -
+    unsigned* queue; // [kWarps][kQueue]
+    unsigned long long* red_hi;  // [kWarps]
+    unsigned long long* red_lo;  // [kWarps]
+};
+
+enum { CS_SUMV = 0, CS_SUMD, CS_JLON, CS_JLAT, CS_TRAV, CS_CURVFAIL, CS_SKIP, CS_COUNT = 8 };
+enum { EG_X = 0, EG_Y, EG_C, EG_S, EG_V, EG_YAW, EG_COUNT };
+
+template <typename R> __host__ __device__ inline size_t tile_smem_bytes(int ND, int Ts, int O) {
+    size_t b = 0;
+    b += sizeof(double) * PF_COUNT * Ts;
+    b += sizeof(double) * 2 * ND * Ts;
+    b += sizeof(R) * EG_COUNT * ND * Ts;
+    b += sizeof(double) * 2 * 2 * ND * (O > 0 ? O : 1);  // hmax + rmax, sized for the fp64 case
+    b += sizeof(double) * ND * CS_COUNT;
+    b += sizeof(unsigned) * kWarps * kQueue;
+    b += sizeof(unsigned long long) * 2 * kWarps;
+    return b + 64;
+}
+
+template <typename R> __device__ __forceinline__ TileSmem carve(unsigned char* base, int ND, int Ts, int O) {
+    TileSmem s;
+    const int On = O > 0 ? O : 1;
+    double* d = reinterpret_cast<double*>(base);
+    s.prof = d; d += PF_COUNT * Ts;
+    s.xd = d; d += ND * Ts;
+    s.yd = d; d += ND * Ts;
+    s.hmax = d; d += 2 * ND * On;
+    s.rmax = d; d += 2 * ND * On;
+    s.cstat = d; d += ND * CS_COUNT;
+    s.red_hi = reinterpret_cast<unsigned long long*>(d); d += kWarps;
+    s.red_lo = reinterpret_cast<unsigned long long*>(d); d += kWarps;
+    s.ego = d;
+    R* e = reinterpret_cast<R*>(d) + (size_t)EG_COUNT * ND * Ts;
+    s.queue = reinterpret_cast<unsigned*>(e);
+    return s;
+}
+
+template <typename R> struct Obs {
+    const R* base;
+    size_t plane;
+    int Tp;
+    __device__ __forceinline__ R get(int f, int o, int t) const { return __ldg(base + f * plane + (size_t)o * Tp + t); }
+};
+
+// impact-area coefficient (logistic_regression_*.py): thresholds on |angle|, sign picks the side
+template <typename R> __device__ __forceinline__ R angle_coef(const DevParams& pr, R angle) {
+    const R a = abs_(angle);
+    int i = 0;
+    while (i < pr.n_thr && !(a < (R)pr.thr[i])) ++i;
+    return (R)(angle < (R)0 ? pr.coef_neg[i] : pr.coef_pos[i]);
+}
+
+// harm "logit arguments" of ego and obstacle at trajectory index t against obstacle sample t
+// (harm_estimation.py:313-332); harm = 1 / (1 + exp(-(const + arg))).
+template <typename R>
+__device__ __forceinline__ void harm_args(const DevParams& pr, bool prot, R ke, R ko, R ex, R ey, R ec, R es, R ev, R eyaw,
+                                          R mx, R my, R opsi, R ovo, R ocp, R osp, R& arg_e, R& arg_o) {
+    // delta_v = sqrt(v_e^2 + v_o^2 + 2 v_e v_o cos(pdof)), pdof = psi_o - psi_e + pi
+    const R cpd = -(ocp * ec + osp * es);
+    const R dv = sqrt_(ev * ev + ovo * ovo + 2 * ev * ovo * cpd);
+    const R dve = ke * dv, dvo = ko * dv;
+    if (prot) {
+        const R rel = atan2_(my - ey, mx - ex);
+        const R a_e = rel - eyaw;
+        const R a_o = (R)3.14159265358979323846 + rel - opsi;
+        arg_e = (R)pr.lr_speed * dve + angle_coef<R>(pr, a_e);
+        arg_o = (R)pr.lr_speed * dvo + angle_coef<R>(pr, a_o);
+    } else {
+        arg_e = (R)pr.lr1s_speed * dve;
+        arg_o = (R)pr.ped_speed * dvo;
+    }
+}
+// fp64 check mode evaluates pdof with the reference's own expression
+template <>
+__device__ __forceinline__ void harm_args<double>(const DevParams& pr, bool prot, double ke, double ko, double ex, double ey,
+                                                  double ec, double es, double ev, double eyaw, double mx, double my,
+                                                  double opsi, double ovo, double ocp, double osp, double& arg_e,
+                                                  double& arg_o) {
+    const double pdof = opsi - eyaw + 3.14159265358979323846;
+    const double dv = sqrt(ev * ev + ovo * ovo + 2 * ev * ovo * cos(pdof));
+    const double dve = ke * dv, dvo = ko * dv;
+    if (prot) {
+        const double rel = atan2(my - ey, mx - ex);
+        const double a_e = rel - eyaw;
+        const double a_o = 3.14159265358979323846 + rel - opsi;
+        arg_e = pr.lr_speed * dve + angle_coef<double>(pr, a_e);
+        arg_o = pr.lr_speed * dvo + angle_coef<double>(pr, a_o);
+    } else {
+        arg_e = pr.lr1s_speed * dve;
+        arg_o = pr.ped_speed * dvo;
+    }
+}
+
+template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { return (R)1 / ((R)1 + exp_(-cst - arg)); }
+
+// collision probability of one (ego sample i = t+1, obstacle sample t) pair
+// (collision_probability.py:205-252, 329-364): 3 means x 3 axis-aligned ego boxes.
+template <typename R>
+__device__ R collision_prob(const DevParams& pr, R x, R y, R c, R s, R mx, R my, R ex, R ey, R isx, R isy, R rho) {
+    const R hx = (R)(pr.veh_l / 6), hy = (R)(pr.veh_w / 2);
+    const R rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
+    R prob = 0;
+#pragma unroll 1
+    for (int km = 0; km < 3; ++km) {
+        const R sg = km == 0 ? (R)0 : (km == 1 ? (R)1 : (R)-1);
+        const R ux = mx + sg * ex, uy = my + sg * ey;
+#pragma unroll 1
+        for (int jb = 0; jb < 3; ++jb) {
+            const R sb = jb == 0 ? (R)0 : (jb == 1 ? (R)1 : (R)-1);
+            const R bx = x + sb * (rr * c), by = y + sb * (rr * s);
+            const R xl = ((bx - hx) - ux) * isx, xu = ((bx + hx) - ux) * isx;
+            const R yl = ((by - hy) - uy) * isy, yu = ((by + hy) - uy) * isy;
+            prob += rect_prob(xl, xu, yl, yu, rho);
+        }
+    }
+    return prob / 3;
+}
+
+// 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
+template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R mx, R my, R i00, R i01, R i11) {
+    const R dx = x - mx, dy = y - my;
+    const R m2 = dx * dx * i00 + dx * dy * i01 + dy * dy * i11;
+    return (R)1e-4 / sqrt_(m2);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams pr, DevOut out, int ND, int tiles_per_profile,
+                                                         BestRec* __restrict__ block_best, unsigned int* __restrict__ counters,
+                                                         BestRec* __restrict__ best_out, const int* __restrict__ prof_nskip) {
+    using U = typename Enc<R>::U;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Ts = st.Tmax;
+    const int O = st.has_pred ? st.O : 0;
+    TileSmem sm = carve<R>(smem_raw, ND, Ts, O);
+    R* ego = reinterpret_cast<R*>(sm.ego);
+    R* hmax = reinterpret_cast<R*>(sm.hmax);
+    U* rmaxs = reinterpret_cast<U*>(sm.rmax);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_prof = st.p_end - st.p_begin;
+    const int n_tiles = n_prof * tiles_per_profile;
+    const int Cs = st.c_end - st.c_begin;
+    const int rows_max = ND * O;
+    Obs<R> ob{reinterpret_cast<const R*>(st.obs), (size_t)st.O * st.Tp, st.Tp};
+    R* o_traj = reinterpret_cast<R*>(out.traj);
+    R* o_prob = reinterpret_cast<R*>(out.prob);
+    R* o_red = reinterpret_cast<R*>(out.red);
+    R* o_cost = reinterpret_cast<R*>(out.cost);
+    const size_t ego_plane = (size_t)ND * Ts;
+
+    unsigned long long my_hi = ~0ull, my_lo = ~0ull;  // running best of this thread (phase D owner threads)
+    double my_cost = 0.0;
+    int my_level = -1, my_scored = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int pl = tile / tiles_per_profile;  // local profile
+        const int d0 = (tile % tiles_per_profile) * ND;
+        const int nd_here = min(ND, st.nd - d0);
+        const int p = st.p_begin + pl;
+        const double* gp = st.prof + (size_t)pl * PF_COUNT * Ts;
+        const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+        const double ds = pm[PM_DS];
+        const bool low = pm[PM_LOW] != 0.0;
+        const int T = (int)pm[PM_T];
+        const bool vel_ok = pm[PM_VEL_OK] != 0.0;
+        const double t_end = pm[PM_TEND];
+        const int c_tile0 = p * st.nd + d0;          // dense index of the tile's first candidate
+        const int cl0 = c_tile0 - st.c_begin;        // index local to the scored range
+
+        // ---- phase A: profile rows to shared memory -------------------------------------------
+        for (int i = tid; i < PF_COUNT * Ts; i += kThreads) sm.prof[i] = gp[i];
+        for (int i = tid; i < 2 * rows_max; i += kThreads) rmaxs[i] = Enc<R>::enc((R)-INFINITY);
+        __syncthreads();
+
+        // ---- phase B: one warp per candidate, lanes over time ----------------------------------
+        for (int cl = warp; cl < nd_here; cl += kWarps) {
+            const double dT = st.d_list[d0 + cl];
+            const bool skip = ds <= fabs(dT);  // frenet_functions.py:333-334
+            const Poly5 q = lateral_poly(st, low, dT, t_end, ds);
+            double sv = 0, sd = 0, jl = 0, jq = 0;
+            int first_fail = 0x7fffffff;
+            for (int t = lane; t < Ts; t += 32) {
+                const size_t gi = (size_t)(cl0 + cl) * Ts + t;
+                if (t < T && !skip) {
+                    const TrajPoint tp = traj_point(q, low, sm.prof, Ts, t, st.dt);
+                    if (o_traj) {
+#pragma unroll
+                        for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[(size_t)f * Cs * Ts + gi] = (R)tp.f[f];
+                    }
+                    const int e = cl * Ts + t;
+                    sm.xd[e] = tp.f[ETP_F_X];
+                    sm.yd[e] = tp.f[ETP_F_Y];
+                    ego[EG_X * ego_plane + e] = (R)tp.f[ETP_F_X];
+                    ego[EG_Y * ego_plane + e] = (R)tp.f[ETP_F_Y];
+                    ego[EG_C * ego_plane + e] = (R)tp.cos_yaw;
+                    ego[EG_S * ego_plane + e] = (R)tp.sin_yaw;
+                    ego[EG_V * ego_plane + e] = (R)tp.f[ETP_F_V];
+                    ego[EG_YAW * ego_plane + e] = (R)tp.f[ETP_F_YAW];
+                    sv += tp.f[ETP_F_V];
+                    sd += fabs(tp.f[ETP_F_D]);
+                    jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
+                    jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
+                    const int cf = curvature_fail(pr, tp.f[ETP_F_V], tp.f[ETP_F_CURV]);
+                    if (cf) first_fail = min(first_fail, t * 4 + cf);
+                } else if (o_traj) {
+#pragma unroll
+                    for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[(size_t)f * Cs * Ts + gi] = (R)0;
+                }
+            }
+            __syncwarp();
+            double trav = 0;
+            if (!skip)
+                for (int t = lane; t + 1 < T; t += 32) {  // calc_trajectory_cost.py:739-757
+                    const int e = cl * Ts + t;
+                    const double dx = sm.xd[e] - sm.xd[e + 1], dy = sm.yd[e] - sm.yd[e + 1];
+                    trav += sqrt(dx * dx + dy * dy);
+                }
+            sv = warp_sum(sv); sd = warp_sum(sd); jl = warp_sum(jl); jq = warp_sum(jq); trav = warp_sum(trav);
+            first_fail = -warp_max(-first_fail);
+            if (lane == 0) {
+                double* cs = sm.cstat + cl * CS_COUNT;
+                cs[CS_SUMV] = sv; cs[CS_SUMD] = sd; cs[CS_JLON] = jl; cs[CS_JLAT] = jq; cs[CS_TRAV] = trav;
+                cs[CS_CURVFAIL] = first_fail == 0x7fffffff ? 0.0 : (double)(first_fail & 3);
+                cs[CS_SKIP] = skip ? 1.0 : 0.0;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase C: rows (candidate, obstacle), lanes over time; un-gated work deferred to a
+        //      warp-private queue and executed densely ------------------------------------------
+        if (O > 0) {
+            unsigned* q = sm.queue + warp * kQueue;
+            int q_n = 0;
+            const int rows = nd_here * O;
+            auto run_entry = [&](unsigned entry) {
+                const int row = entry >> 8, t = entry & 255;
+                const int cl = row / O, o = row % O;
+                const int e1 = cl * Ts + t + 1, e0 = cl * Ts + t;
+                R prob;
+                if (pr.mahalanobis) {
+                    prob = inv_mahalanobis<R>(ego[EG_X * ego_plane + e1], ego[EG_Y * ego_plane + e1], ob.get(OF_MX, o, t),
+                                              ob.get(OF_MY, o, t), ob.get(OF_I00, o, t), ob.get(OF_I01, o, t),
+                                              ob.get(OF_I11, o, t));
+                } else {
+                    prob = collision_prob<R>(pr, ego[EG_X * ego_plane + e1], ego[EG_Y * ego_plane + e1],
+                                             ego[EG_C * ego_plane + e1], ego[EG_S * ego_plane + e1], ob.get(OF_MX, o, t),
+                                             ob.get(OF_MY, o, t), ob.get(OF_EX, o, t), ob.get(OF_EY, o, t),
+                                             ob.get(OF_ISX, o, t), ob.get(OF_ISY, o, t), ob.get(OF_RHO, o, t));
+                }
+                const double* oc = st.obs_const + o * OC_COUNT;
+                const bool prot = oc[OC_PROT] != 0.0;
+                R ae, ao;
+                harm_args<R>(pr, prot, (R)oc[OC_KE], (R)oc[OC_KO], ego[EG_X * ego_plane + e0], ego[EG_Y * ego_plane + e0],
+                             ego[EG_C * ego_plane + e0], ego[EG_S * ego_plane + e0], ego[EG_V * ego_plane + e0],
+                             ego[EG_YAW * ego_plane + e0], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t), ob.get(OF_PSI, o, t),
+                             ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t), ob.get(OF_SPSI, o, t), ae, ao);
+                const R he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), ae);
+                const R ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), ao);
+                atomicMax(&rmaxs[row], Enc<R>::enc(he * prob));               // risk_costs.py:88-95
+                atomicMax(&rmaxs[rows_max + row], Enc<R>::enc(ho * prob));
+                if (o_prob) o_prob[((size_t)(cl0 + cl) * O + o) * (Ts - 1) + t] = prob;
+            };
+            for (int row = warp; row < rows; row += kWarps) {
+                const int cl = row / O, o = row % O;
+                const bool skip = sm.cstat[cl * CS_COUNT + CS_SKIP] != 0.0;
+                const int n_pred = st.pred_len[o];
+                const double* oc = st.obs_const + o * OC_COUNT;
+                const bool prot = oc[OC_PROT] != 0.0;
+                const R ke = (R)oc[OC_KE], ko = (R)oc[OC_KO];
+                R hm_e = -INFINITY, hm_o = -INFINITY, rm = -INFINITY;
+                for (int t0 = 0; t0 < Ts - 1; t0 += 32) {
+                    const int t = t0 + lane;
+                    bool defer = false;
+                    if (t < Ts - 1) {
+                        const bool in_traj = !skip && t < T - 1;
+                        bool gated = true;
+                        if (in_traj && t < n_pred) {
+                            // harm sample t: ego[t] against prediction[t] (harm_estimation.py:234, 313-332)
+                            const int e0 = cl * Ts + t;
+                            R ae, ao;
+                            harm_args<R>(pr, prot, ke, ko, ego[EG_X * ego_plane + e0], ego[EG_Y * ego_plane + e0],
+                                         ego[EG_C * ego_plane + e0], ego[EG_S * ego_plane + e0], ego[EG_V * ego_plane + e0],
+                                         ego[EG_YAW * ego_plane + e0], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
+                                         ob.get(OF_PSI, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t),
+                                         ob.get(OF_SPSI, o, t), ae, ao);
+                            hm_e = rmax_(hm_e, ae);
+                            hm_o = rmax_(hm_o, ao);
+                            if (t + 1 < n_pred) {
+                                // probability sample t: ego[t+1] against mean[t], orientation[t+1]
+                                // (collision_probability.py:168-203)
+                                const int e1 = e0 + 1;
+                                if (pr.mahalanobis) {
+                                    gated = false;
+                                } else {
+                                    const R x = ego[EG_X * ego_plane + e1], y = ego[EG_Y * ego_plane + e1];
+                                    const R mx = ob.get(OF_MX, o, t), my = ob.get(OF_MY, o, t);
+                                    const R ex = ob.get(OF_EX, o, t), ey = ob.get(OF_EY, o, t);
+                                    R dx = mx - x, dy = my - y;
+                                    R d2 = dx * dx + dy * dy;
+                                    dx = (mx + ex) - x; dy = (my + ey) - y;
+                                    d2 = fmin(d2, dx * dx + dy * dy);
+                                    dx = (mx - ex) - x; dy = (my - ey) - y;
+                                    d2 = fmin(d2, dx * dx + dy * dy);
+                                    gated = sqrt_(d2) > (R)5.0;
+                                    if (sizeof(R) == 4 && abs_(d2 - (R)25) < (R)2e-3) {
+                                        // fp32 cannot decide the 5 m gate here: repeat it in fp64 from the exact inputs
+                                        const double xe = sm.xd[e1], ye = sm.yd[e1];
+                                        const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                                        const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+                                        const double hl = oc[OC_HALFLEN];
+                                        const double fx = cos(y1) * (2 * hl) / 2, fy = sin(y1) * (2 * hl) / 2;
+                                        double ax = rp[0] - xe, ay = rp[1] - ye;
+                                        double m = sqrt(ax * ax + ay * ay);
+                                        ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
+                                        m = fmin(m, sqrt(ax * ax + ay * ay));
+                                        ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
+                                        m = fmin(m, sqrt(ax * ax + ay * ay));
+                                        gated = m > 5.0;
+                                    }
+                                }
+                            }
+                            if (gated) rm = rmax_(rm, (R)0);  // harm * 0.0
+                            else defer = true;
+                        }
+                        if (!defer && o_prob) o_prob[((size_t)(cl0 + cl) * O + o) * (Ts - 1) + t] = (R)0;
+                    }
+                    const unsigned m = __ballot_sync(kFull, defer);
+                    if (m) {
+                        if (defer) q[(q_n + __popc(m & ((1u << lane) - 1))) % kQueue] = ((unsigned)row << 8) | (unsigned)t;
+                        q_n += __popc(m);
+                        __syncwarp();
+                        if (q_n >= 32) {
+                            q_n -= 32;
+                            run_entry(q[(q_n + lane) % kQueue]);
+                            __syncwarp();
+                        }
+                    }
+                }
+                hm_e = warp_max(hm_e); hm_o = warp_max(hm_o); rm = warp_max(rm);
+                if (lane == 0) {
+                    hmax[row] = hm_e;
+                    hmax[rows_max + row] = hm_o;
+                    if (rm > (R)-INFINITY) {
+                        atomicMax(&rmaxs[row], Enc<R>::enc(rm));
+                        atomicMax(&rmaxs[rows_max + row], Enc<R>::enc(rm));
+                    }
+                }
+            }
+            // drain: entries live at ring positions [0, q_n) by construction (pops take the top 32)
+            if (q_n > 0) {
+                if (lane < q_n) run_entry(q[lane % kQueue]);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase D: per-candidate principles, cost, level, key -------------------------------
+        if (o_red && O > 0) {
+            for (int i = tid; i < nd_here * O; i += kThreads) {
+                const int cl = i / O, o = i % O;
+                const bool skip = sm.cstat[cl * CS_COUNT + CS_SKIP] != 0.0;
+                const double* oc = st.obs_const + o * OC_COUNT;
+                const bool prot = oc[OC_PROT] != 0.0;
+                const size_t g = (size_t)(cl0 + cl) * O + o;
+                const size_t plane = (size_t)Cs * O;
+                R re = 0, ro = 0, he = 0, ho = 0;
+                if (!skip) {
+                    re = Enc<R>::dec(rmaxs[i]);
+                    ro = Enc<R>::dec(rmaxs[rows_max + i]);
+                    he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), hmax[i]);
+                    ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), hmax[rows_max + i]);
+                }
+                o_red[ETP_R_EGO_RISK * plane + g] = re;
+                o_red[ETP_R_OBST_RISK * plane + g] = ro;
+                o_red[ETP_R_EGO_HARM * plane + g] = he;
+                o_red[ETP_R_OBST_HARM * plane + g] = ho;
+            }
+        }
+        if (tid < nd_here) {
+            const int cl = tid;
+            const int c_dense = c_tile0 + cl;
+            const size_t g = (size_t)(cl0 + cl);
+            const double* cs = sm.cstat + cl * CS_COUNT;
+            const bool skip = cs[CS_SKIP] != 0.0;
+            double c[ETP_NUM_COST];
+#pragma unroll
+            for (int k = 0; k < ETP_NUM_COST; ++k) c[k] = 0.0;
+            int level = ETP_LEVEL_SKIPPED, reason = ETP_REASON_NONE;
+            if (!skip) {
+                const double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
+                const int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
+                double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
+                for (int o = 0; o < O; ++o) {
+                    const double* oc = st.obs_const + o * OC_COUNT;
+                    const bool prot = oc[OC_PROT] != 0.0;
+                    const double re = (double)Enc<R>::dec(rmaxs[cl * O + o]);
+                    const double ro = (double)Enc<R>::dec(rmaxs[rows_max + cl * O + o]);
+                    const double he = (double)sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), hmax[cl * O + o]);
+                    const double ho = (double)sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), hmax[rows_max + cl * O + o]);
+                    sum_e += re;
+                    sum_o += ro;
+                    sum_abs += fabs(re - ro);
+                    resp -= oc[OC_RESP] * ro;                       // risk_costs.py:250-253
+                    mm = fmax(mm, he * (re < 10e-10 ? 1.0 : 0.0));  // risk_costs.py:205-206 (quirk Q3)
+                    mm = fmax(mm, ho * (ro < 10e-10 ? 1.0 : 0.0));
+                    max_o = fmax(max_o, ro);
+                }
+                if (O > 0) {
+                    c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);     // risk_costs.py:148-150
+                    c[ETP_C_EQUALITY] = sum_abs / (double)O;                     // :176-178
+                    c[ETP_C_MAXIMIN] = pow(fmax(mm, bd), 10.0);                  // :208
+                    c[ETP_C_EGO] = sum_e + bd;                                   // :226
+                    c[ETP_C_RESPONSIBILITY] = resp;
+                }
+                const bool risk_in_cost = pr.w[ETP_W_RISK_COST] > 0.0 && st.has_pred && pr.planner_mode == ETP_MODE_RISK;
+                if (risk_in_cost)  // calc_trajectory_cost.py:130-136
+                    c[ETP_C_RISK_TOTAL] = pr.w[ETP_W_BAYES] * c[ETP_C_BAYES] + pr.w[ETP_W_EQUALITY] * c[ETP_C_EQUALITY] +
+                                          pr.w[ETP_W_MAXIMIN] * c[ETP_C_MAXIMIN] +
+                                          pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES] * c[ETP_C_RESPONSIBILITY] +
+                                          pr.w[ETP_W_EGO] * c[ETP_C_EGO];
+                const double mean_v = cs[CS_SUMV] / (double)T;
+                switch (st.vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
+                    case 0: c[ETP_C_VELOCITY] = fabs(st.vel_target - mean_v); break;
+                    case 1: c[ETP_C_VELOCITY] = 30.0 - mean_v; break;
+                    case 2: c[ETP_C_VELOCITY] = mean_v; break;
+                    default: c[ETP_C_VELOCITY] = 0.0;
+                }
+                c[ETP_C_DIST_TO_GLOBAL_PATH] = cs[CS_SUMD] / (double)T;  // :726-736
+                c[ETP_C_LON_JERK] = cs[CS_JLON] / (double)T;             // :418-435
+                c[ETP_C_LAT_JERK] = cs[CS_JLAT] / (double)T;
+                c[ETP_C_TRAVELLED_DIST] = cs[CS_TRAV];
+                c[ETP_C_FACTOR] = st.factor;
+                // validity level (validity_checks.py:31-122)
+                const int cf = (int)cs[CS_CURVFAIL];
+                if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
+                else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
+                else if (ext == 1) { level = 1; reason = ETP_REASON_COLLISION; }
+                else if (st.has_pred ? (bd != 0.0) : (ext == 2)) { level = 2; reason = ETP_REASON_BOUNDARIES; }
+                else if (pr.planner_mode == ETP_MODE_RISK && st.has_pred && O > 0 &&
+                         (sum_e > pr.max_risk || max_o > pr.max_risk)) { level = 3; reason = ETP_REASON_MAX_RISK; }
+                else { level = 10; reason = ETP_REASON_NONE; }
+                // weighted sum (calc_trajectory_cost.py:321-346); risk-only weights below level 10 if requested
+                const bool risk_only = level < 10 && pr.multi_cost;
+                double cost = 0.0;
+                if (risk_in_cost) cost += pr.w[ETP_W_RISK_COST] * c[ETP_C_RISK_TOTAL];
+                if (pr.w[ETP_W_LON_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LON_JERK]) * c[ETP_C_LON_JERK];
+                if (pr.w[ETP_W_LAT_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LAT_JERK]) * c[ETP_C_LAT_JERK];
+                if (pr.w[ETP_W_VELOCITY] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_VELOCITY]) * c[ETP_C_VELOCITY];
+                if (pr.w[ETP_W_DIST_TO_GLOBAL_PATH] > 0.0)
+                    cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GLOBAL_PATH]) * c[ETP_C_DIST_TO_GLOBAL_PATH];
+                if (pr.w[ETP_W_TRAVELLED_DIST] > 0.0)
+                    cost += (risk_only ? 0.0 : pr.w[ETP_W_TRAVELLED_DIST]) * c[ETP_C_TRAVELLED_DIST];
+                c[ETP_C_TOTAL] = st.factor * cost;
+                const unsigned long long hi = make_key_hi(level, c[ETP_C_TOTAL]);
+                const unsigned long long lo = (unsigned long long)c_dense;
+                if (hi < my_hi || (hi == my_hi && lo < my_lo)) {
+                    my_hi = hi; my_lo = lo; my_cost = c[ETP_C_TOTAL]; my_level = level;
+                }
+                my_scored += 1;
+            }
+            if (o_cost) {
+#pragma unroll
+                for (int k = 0; k < ETP_NUM_COST; ++k) o_cost[(size_t)k * Cs + g] = (R)c[k];
+            }
+            if (out.level) out.level[g] = (uint8_t)level;
+            if (out.reason) out.reason[g] = (uint8_t)reason;
+        }
+        __syncthreads();
+    }
+
+    // ---- block arg-min, then grid arg-min by the last block to finish ---------------------------
+    {
+        // lexicographic min over (hi, lo) with shuffles
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ohi = __shfl_xor_sync(kFull, my_hi, o), olo = __shfl_xor_sync(kFull, my_lo, o);
+            const double oc = __shfl_xor_sync(kFull, my_cost, o);
+            const int ol = __shfl_xor_sync(kFull, my_level, o);
+            my_scored += __shfl_xor_sync(kFull, my_scored, o);
+            if (ohi < my_hi || (ohi == my_hi && olo < my_lo)) { my_hi = ohi; my_lo = olo; my_cost = oc; my_level = ol; }
+        }
+        __shared__ BestRec wbest[kWarps];
+        __shared__ bool is_last;
+        if (lane == 0) {
+            wbest[warp].key_hi = my_hi; wbest[warp].key_lo = my_lo; wbest[warp].cost = my_cost;
+            wbest[warp].level = my_level; wbest[warp].n_scored = my_scored;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            BestRec b = wbest[0];
+            for (int w = 1; w < kWarps; ++w) {
+                b.n_scored += wbest[w].n_scored;
+                if (wbest[w].key_hi < b.key_hi || (wbest[w].key_hi == b.key_hi && wbest[w].key_lo < b.key_lo)) {
+                    const int n = b.n_scored;
+                    b = wbest[w];
+                    b.n_scored = n;
+                }
+            }
+            b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
+            b.list_index = -1;
+            block_best[blockIdx.x] = b;
+            __threadfence();
+            const unsigned done = atomicAdd(&counters[0], 1u);
+            is_last = (done == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            unsigned long long hi = ~0ull, lo = ~0ull;
+            double cst = 0.0;
+            int lvl = -1, scored = 0;
+            for (int b = tid; b < (int)gridDim.x; b += kThreads) {
+                const volatile BestRec* r = block_best + b;
+                const unsigned long long bhi = r->key_hi, blo = r->key_lo;
+                scored += r->n_scored;
+                if (bhi < hi || (bhi == hi && blo < lo)) { hi = bhi; lo = blo; cst = r->cost; lvl = r->level; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ohi = __shfl_xor_sync(kFull, hi, o), olo = __shfl_xor_sync(kFull, lo, o);
+                const double oc = __shfl_xor_sync(kFull, cst, o);
+                const int ol = __shfl_xor_sync(kFull, lvl, o);
+                scored += __shfl_xor_sync(kFull, scored, o);
+                if (ohi < hi || (ohi == hi && olo < lo)) { hi = ohi; lo = olo; cst = oc; lvl = ol; }
+            }
+            if (lane == 0) {
+                wbest[warp].key_hi = hi; wbest[warp].key_lo = lo; wbest[warp].cost = cst; wbest[warp].level = lvl;
+                wbest[warp].n_scored = scored;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                BestRec b = wbest[0];
+                for (int w = 1; w < kWarps; ++w) {
+                    b.n_scored += wbest[w].n_scored;
+                    if (wbest[w].key_hi < b.key_hi || (wbest[w].key_hi == b.key_hi && wbest[w].key_lo < b.key_lo)) {
+                        const int n = b.n_scored;
+                        b = wbest[w];
+                        b.n_scored = n;
+                    }
+                }
+                b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
+                b.list_index = -1;
+                if (b.index >= 0) {
+                    // rank among non-skipped candidates of this range = position in the reference's fp_list
+                    const int pb = b.index / st.nd, idb = b.index % st.nd;
+                    int li = 0;
+                    for (int pp = st.p_begin; pp < pb; ++pp) li += st.nd - prof_nskip[pp - st.p_begin];
+                    const double dsb = st.prof_meta[(size_t)(pb - st.p_begin) * PM_COUNT + PM_DS];
+                    for (int id = 0; id < idb; ++id) li += (dsb <= fabs(st.d_list[id])) ? 0 : 1;
+                    b.list_index = li;
+                }
+                *best_out = b;
+                counters[0] = 0;  // re-arm for the next launch
+            }
+        }
+    }
+}
+
+// number of skipped lateral targets per profile (frenet_functions.py:333-334)
+__global__ void profile_skip_kernel(DevStep st, int* __restrict__ nskip) {
+    const int pl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pl >= st.p_end - st.p_begin) return;
+    const double ds = st.prof_meta[(size_t)pl * PM_COUNT + PM_DS];
+    int n = 0;
+    for (int id = 0; id < st.nd; ++id) n += (ds <= fabs(st.d_list[id])) ? 1 : 0;
+    nskip[pl] = n;
+}
+
+// one candidate, all 13 fields in fp64 -> [ETP_NUM_FIELDS][Tmax]; requires its profile in st.prof
+__global__ void trajectory_kernel(DevStep st, int c_dense, double* __restrict__ fields, int* __restrict__ n_out) {
+    const int p = c_dense / st.nd, id = c_dense % st.nd;
+    const int pl = p - st.p_begin;
+    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+    const bool low = pm[PM_LOW] != 0.0;
+    const int T = (int)pm[PM_T];
+    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+    for (int t = threadIdx.x; t < st.Tmax; t += blockDim.x) {
+        if (t < T) {
+            const TrajPoint tp = traj_point(q, low, gp, st.Tmax, t, st.dt);
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = tp.f[f];
+        } else {
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0) *n_out = T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (called from etp_abi.cpp)
+// ---------------------------------------------------------------------------------------------
+int pick_nd(int O) { return O > 16 ? 8 : 16; }
+
+cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_len, const double* pos, const double* cov,
+                                  const double* yaw, const double* vel, const double* length, const double* mass,
+                                  const int* prot, const int* resp, double veh_m, void* tile, double* oconst,
+                                  cudaStream_t stream) {
+    const int n = O * Tp;
+    if (n <= 0) return cudaSuccess;
+    const int blocks = (n + 127) / 128;
+    if (precision == ETP_PRECISION_FP64)
+        pack_obstacles_kernel<double><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, mass, prot, resp,
+                                                                  veh_m, (double*)tile, oconst);
+    else
+        pack_obstacles_kernel<float><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, mass, prot, resp,
+                                                                 veh_m, (float*)tile, oconst);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, cudaStream_t stream) {
+    const int n_prof = st.p_end - st.p_begin;
+    if (n_prof <= 0) return cudaSuccess;
+    const size_t smem = sizeof(double) * 7 * st.Tmax;
+    profile_kernel<<<n_prof, 128, smem, stream>>>(st, pr);
+    profile_skip_kernel<<<(n_prof + 127) / 128, 128, 0, stream>>>(st, nskip);
+    return cudaGetLastError();
+}
+
+template <typename R>
+static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
+                                  unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
+                                  cudaStream_t stream) {
+    const int O = st.has_pred ? st.O : 0;
+    const int ND = pick_nd(O);
+    const int tiles_per_profile = (st.nd + ND - 1) / ND;
+    const int n_tiles = (st.p_end - st.p_begin) * tiles_per_profile;
+    const size_t smem = tile_smem_bytes<R>(ND, st.Tmax, O);
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R>, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    int grid = num_sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    if (grid < 1) grid = 1;
+    *grid_out = grid;
+    score_kernel<R><<<grid, kThreads, smem, stream>>>(st, pr, out, ND, tiles_per_profile, block_best, counters, best_out, nskip);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
+                         unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
+                         cudaStream_t stream) {
+    if (precision == ETP_PRECISION_FP64)
+        return launch_score_t<double>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
+    return launch_score_t<float>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
+}
+
+cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream) {
+    trajectory_kernel<<<1, 64, 0, stream>>>(st, c_dense, fields, n_out);
+    return cudaGetLastError();
+}
+
+}  // namespace etp

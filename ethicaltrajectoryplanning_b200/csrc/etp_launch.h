@@ -1,0 +1,27 @@
+// Host-callable launchers implemented in etp_kernels.cu (internal to the shared library).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "etp_device.cuh"
+
+namespace etp {
+
+constexpr int kMaxGrid = 4096;  // upper bound of persistent CTAs (148 SMs x resident CTAs per SM)
+
+int pick_nd(int O);
+
+cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_len, const double* pos, const double* cov,
+                                  const double* yaw, const double* vel, const double* length, const double* mass,
+                                  const int* prot, const int* resp, double veh_m, void* tile, double* oconst,
+                                  cudaStream_t stream);
+
+cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, cudaStream_t stream);
+
+cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
+                         unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
+                         cudaStream_t stream);
+
+cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream);
+
+}  // namespace etp

@@ -1,0 +1,374 @@
+"""Host side of the fused scoring path: packs the reference's data contracts into the C ABI,
+owns the device tensors (PyTorch) and returns the selection.
+
+PyTorch is used for device memory and streams only; all arithmetic of the path runs in the
+hand-written kernels of ``csrc/`` reached through ``libetp_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from .configs import WEIGHT_KEYS
+from .spline import CubicSpline2D
+from .synthetic import PROTECTED_TYPES, UNPROTECTED_TYPES, PlanningStep, obstacle_mass
+
+MODE_CODES = {"risk": 0, "WaleNet": 1, "ground_truth": 2}
+
+
+class EtpError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"etp_b200 error {code}: {message}")
+        self.code = code
+
+
+class NoCandidateError(ValueError):
+    """Every candidate was skipped: the reference's ``max([])`` ValueError (frenet_functions.py:562-564)."""
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def harm_model_tables(modes, coeffs):
+    """Thresholds on |angle| and per-band coefficients of the protected-occupant model selected by
+    risk.json (harm_estimation.py:358-400; logistic_regression_symmetrical.py / _asymmetrical.py)."""
+    if modes["harm_mode"] != "log_reg":
+        if modes["harm_mode"] in ("ref_speed", "gidas"):
+            raise NotImplementedError(
+                f"harm_mode {modes['harm_mode']!r} is not part of the scored path: the reference's "
+                "own implementations raise on array input (SURVEY.md Q10, Q11)")
+        raise ValueError("Please select a valid mode for harm estimation (log_reg, ref_speed, gidas)")
+    if modes["crash_angle_simplified"] is False:
+        raise NotImplementedError("comprehensive crash-angle estimation needs pycrcc and is out of scope")
+    lr = coeffs["log_reg"]
+    if modes["ignore_angle"]:
+        p = lr["ignore_angle"]
+        return [], [0.0], [0.0], p["const"], p["speed"]
+    sym, red = modes["sym_angle"], modes["reduced_angle_areas"]
+    if red and sym:
+        p = lr["reduced_sym_angle_areas"]
+        t_a = 45 / 180 * np.pi
+        thr = [t_a, 3 * t_a]
+        pos = neg = [0.0, p["side"], p["rear"]]
+    elif red:
+        p = lr["reduced_angle_areas"]
+        thr = [45 / 180 * np.pi, 135 / 180 * np.pi]
+        pos = [0.0, p["driver_side"], p["rear"]]
+        neg = [0.0, p["right_side"], p["rear"]]
+    elif sym:
+        p = lr["complete_sym_angle_areas"]
+        thr = [k / 180 * np.pi for k in (15, 45, 75, 105, 135, 165)]
+        pos = neg = [0.0, p["Imp_1_11"], p["Imp_2_10"], p["Imp_3_9"], p["Imp_4_8"], p["Imp_5_7"], p["Imp_6"]]
+    else:
+        p = lr["complete_angle_areas"]
+        thr = [k / 180 * np.pi for k in (15, 45, 75, 105, 135, 165)]
+        pos = [0.0, p["Imp_11"], p["Imp_10"], p["Imp_9"], p["Imp_8"], p["Imp_7"], p["Imp_6"]]
+        neg = [0.0, p["Imp_1"], p["Imp_2"], p["Imp_3"], p["Imp_4"], p["Imp_5"], p["Imp_6"]]
+    return thr, list(pos), list(neg), p["const"], p["speed"]
+
+
+def make_params(params, vehicle, mode="risk") -> _abi.Params:
+    """Flatten params_dict (frenet_planner.py:149-153) + vehicle constants into the ABI struct."""
+    weights, modes, coeffs = params["weights"], params["modes"], params["harm"]
+    thr, pos, neg, const, speed = harm_model_tables(modes, coeffs)
+    p = _abi.Params()
+    for i, k in enumerate(WEIGHT_KEYS):
+        p.weights[i] = float(weights.get(k, 0.0))
+    if mode not in MODE_CODES:
+        raise ValueError("mode must be ground_truth, WaleNet, or risk")
+    p.planner_mode = MODE_CODES[mode]
+    p.fast_prob_mahalanobis = int(bool(modes["fast_prob_mahalanobis"]))
+    p.multiple_cost_functions = int(bool(modes["multiple_cost_functions"]))
+    p.n_angle_thresholds = len(thr)
+    p.max_acceptable_risk = float(modes["max_acceptable_risk"])
+    for i, v in enumerate(thr):
+        p.angle_thr[i] = v
+    for i in range(_abi.MAX_ANGLE_BINS + 1):
+        p.angle_coef_pos[i] = pos[min(i, len(pos) - 1)]
+        p.angle_coef_neg[i] = neg[min(i, len(neg) - 1)]
+    p.lr_const, p.lr_speed = const, speed
+    ia = coeffs["log_reg"]["ignore_angle"]
+    p.lr1s_const, p.lr1s_speed = ia["const"], ia["speed"]
+    p.ped_const, p.ped_speed = coeffs["pedestrian"]["const"], coeffs["pedestrian"]["speed"]
+    p.veh_l, p.veh_w, p.veh_l_r, p.veh_m = vehicle.l, vehicle.w, vehicle.l_r, vehicle.m
+    p.veh_steer_max = vehicle.steering.max
+    p.veh_lat_a_max = vehicle.lateral_a_max
+    p.veh_v_max = vehicle.longitudinal.v_max
+    p.veh_a_max = vehicle.longitudinal.a_max
+    return p
+
+
+def pack_predictions(predictions, obstacle_types=None, masses=None, protections=None):
+    """`predictions` dict (SURVEY.md 8b data contract 1) -> SoA host arrays, dict order kept.
+
+    Obstacle class comes from ``obstacle_types[id]`` (an ObstacleType name such as "CAR") like the
+    reference's ``scenario.obstacle_by_id(id).obstacle_type`` lookups (harm_estimation.py:258-260,356),
+    or from explicit ``masses`` / ``protections``.
+    """
+    oids = list(predictions.keys())
+    O = len(oids)
+    lens = np.array([len(predictions[o]["pos_list"]) for o in oids], dtype=np.int32)
+    Tp = int(lens.max()) if O else 1
+    pos = np.zeros((O, Tp, 2))
+    cov = np.zeros((O, Tp, 4))
+    yaw = np.zeros((O, Tp))
+    vel = np.zeros((O, Tp))
+    length = np.zeros(O)
+    width = np.zeros(O)
+    mass = np.zeros(O)
+    prot = np.zeros(O, dtype=np.int32)
+    resp = np.zeros(O, dtype=np.int32)
+    for j, oid in enumerate(oids):
+        p = predictions[oid]
+        n = lens[j]
+        pos[j, :n] = np.asarray(p["pos_list"], dtype=np.float64).reshape(n, 2)
+        cov[j, :n] = np.asarray(p["cov_list"], dtype=np.float64).reshape(n, 4)
+        yaw[j, :n] = np.asarray(p["orientation_list"], dtype=np.float64)[:n]
+        vel[j, :n] = np.asarray(p["v_list"], dtype=np.float64)[:n]
+        length[j] = p["shape"]["length"]
+        width[j] = p["shape"]["width"]
+        resp[j] = int(p.get("responsibility", 0))
+        if masses is not None:
+            mass[j] = masses[oid]
+            prot[j] = int(protections[oid])
+        else:
+            t = obstacle_types[oid]
+            t = getattr(t, "name", t)
+            if t in PROTECTED_TYPES:
+                prot[j] = 1
+            elif t in UNPROTECTED_TYPES:
+                prot[j] = 0
+            else:
+                raise ValueError(f"obstacle type {t!r} has no protection class (harm_estimation.py:52-56)")
+            mass[j] = obstacle_mass(t, length[j] * width[j])
+    return dict(ids=oids, O=O, Tp=Tp, pred_len=lens, pos=pos, cov=cov, yaw=yaw, vel=vel, length=length,
+                width=width, mass=mass, prot=prot, resp=resp)
+
+
+@dataclass
+class ScoreResult:
+    """Outputs of one planning step.  Tensors live on the device; ``numpy()`` copies them."""
+
+    n_dense: int
+    c_begin: int
+    c_end: int
+    Tmax: int
+    n_samples: np.ndarray
+    obstacle_ids: list
+    best: Optional[dict]
+    traj: object = None
+    prob: object = None
+    red: object = None
+    cost: object = None
+    level: object = None
+    reason: object = None
+    _ctx: object = field(default=None, repr=False)
+
+    def numpy(self):
+        out = {}
+        for k in ("traj", "prob", "red", "cost", "level", "reason"):
+            v = getattr(self, k)
+            out[k] = None if v is None else v.detach().cpu().numpy()
+        return out
+
+    def best_trajectory(self):
+        """The 11 arrays FrenetPlanner stores in ``self._trajectory`` (frenet_planner.py:564-576),
+        recomputed in fp64 on the device.  Note ``v_mps`` is ``s_d`` (quirk Q7)."""
+        f, T = self._ctx.trajectory(self.best["index"])
+        names = _abi.FIELD_NAMES
+        g = {n: f[i, :T] for i, n in enumerate(names)}
+        dt = self._ctx.last_dt
+        return {
+            "s_loc_m": g["s"], "d_loc_m": g["d"], "d_d_loc_mps": g["d_d"], "d_dd_loc_mps2": g["d_dd"],
+            "x_m": g["x"], "y_m": g["y"], "psi_rad": g["yaw"], "kappa_radpm": g["curv"],
+            "v_mps": g["s_d"], "ax_mps2": g["s_dd"], "time_s": np.arange(T) * dt,
+        }
+
+
+class ScoringContext:
+    """One ``etp_ctx``: one device, one stream, reusable across planning steps."""
+
+    def __init__(self, device=0, precision="fp32"):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("the scoring path runs on CUDA only (no CPU fallback)")
+        self.torch = torch
+        self.lib = _abi.load_library()
+        self.device = torch.device("cuda", device)
+        self.precision = {"fp32": _abi.PRECISION_FP32, "fp64": _abi.PRECISION_FP64}[precision]
+        self.dtype = torch.float32 if self.precision == _abi.PRECISION_FP32 else torch.float64
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        h = C.c_void_p()
+        rc = self.lib.etp_create(C.byref(h), device)
+        if rc != 0:
+            raise EtpError(rc, "etp_create failed")
+        self.h = h
+        self._check(self.lib.etp_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        self.obstacle_ids = []
+        self.O = 0
+        self.has_pred = False
+        self.last_dt = 0.1
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.etp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == _abi.OK:
+            return
+        msg = self.lib.etp_last_error(self.h).decode()
+        if rc == _abi.ERR_NO_CANDIDATE:
+            raise NoCandidateError(msg)
+        if rc == _abi.ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise EtpError(rc, msg)
+
+    # -- inputs -----------------------------------------------------------------------------
+    def set_params(self, params, vehicle, mode="risk"):
+        p = make_params(params, vehicle, mode)
+        self._check(self.lib.etp_set_params(self.h, C.byref(p)))
+
+    def set_spline(self, csp):
+        csp = CubicSpline2D.from_foreign(csp)
+        k = np.ascontiguousarray(csp.s, dtype=np.float64)
+        cx = np.ascontiguousarray(csp.coef_x, dtype=np.float64)
+        cy = np.ascontiguousarray(csp.coef_y, dtype=np.float64)
+        self._check(self.lib.etp_set_spline(self.h, _dptr(k), _dptr(cx), _dptr(cy), len(k) - 1))
+
+    def set_predictions(self, predictions, obstacle_types=None, masses=None, protections=None):
+        o = _abi.Obstacles()
+        if predictions is None:
+            o.n_obstacles = -1
+            self.obstacle_ids, self.O, self.has_pred = [], 0, False
+            self._check(self.lib.etp_set_obstacles(self.h, C.byref(o), self.precision))
+            return
+        pk = pack_predictions(predictions, obstacle_types, masses, protections)
+        o.n_obstacles, o.max_pred = pk["O"], pk["Tp"]
+        o.pred_len = _iptr(pk["pred_len"])
+        o.pos, o.cov, o.yaw, o.vel = _dptr(pk["pos"]), _dptr(pk["cov"]), _dptr(pk["yaw"]), _dptr(pk["vel"])
+        o.length, o.width, o.mass = _dptr(pk["length"]), _dptr(pk["width"]), _dptr(pk["mass"])
+        o.is_protected, o.responsibility = _iptr(pk["prot"]), _iptr(pk["resp"])
+        self._check(self.lib.etp_set_obstacles(self.h, C.byref(o), self.precision))
+        self.obstacle_ids, self.O, self.has_pred = pk["ids"], pk["O"], True
+
+    def configure(self, step: PlanningStep):
+        """params + spline + predictions of a PlanningStep."""
+        self.set_params(step.params, step.vehicle, step.mode)
+        self.set_spline(step.csp)
+        self.set_predictions(step.predictions, step.obstacle_types)
+
+    # -- one planning step --------------------------------------------------------------------
+    def make_step_struct(self, step, c_begin=None, c_end=None):
+        v = np.ascontiguousarray(step.v_list, dtype=np.float64)
+        t = np.ascontiguousarray(step.t_list, dtype=np.float64)
+        d = np.ascontiguousarray(step.d_list, dtype=np.float64)
+        n = np.ascontiguousarray([len(np.arange(0.0, tT, step.dt)) for tT in t], dtype=np.int32)
+        s = _abi.Step()
+        s.c_s, s.c_s_d, s.c_s_dd = step.c_s, step.c_s_d, step.c_s_dd
+        s.c_d, s.c_d_d, s.c_d_dd = step.c_d, step.c_d_d, step.c_d_dd
+        s.v_list, s.nv = _dptr(v), len(v)
+        s.t_list, s.nt = _dptr(t), len(t)
+        s.n_samples = _iptr(n)
+        s.d_list, s.nd = _dptr(d), len(d)
+        s.dt, s.v_thr = step.dt, step.v_thr
+        s.velocity_cost_mode = int(step.velocity_cost_mode)
+        s.velocity_target = float(step.velocity_target)
+        s.cost_factor = float(step.cost_factor)
+        keep = [v, t, d, n]
+        if step.ext_level is not None:
+            e = np.ascontiguousarray(step.ext_level, dtype=np.uint8)
+            s.ext_level = e.ctypes.data_as(C.POINTER(C.c_uint8))
+            keep.append(e)
+        if step.bd_harm is not None:
+            b = np.ascontiguousarray(step.bd_harm, dtype=np.float64)
+            s.bd_harm = _dptr(b)
+            keep.append(b)
+        dense = len(v) * len(t) * len(d)
+        s.c_begin = 0 if c_begin is None else int(c_begin)
+        s.c_end = dense if c_end is None else int(c_end)
+        return s, keep, n
+
+    def allocate_outputs(self, Cs, Tmax, O, traj=True, prob=True, red=True, cost=True):
+        torch = self.torch
+        kw = dict(device=self.device, dtype=self.dtype)
+        return dict(
+            traj=torch.empty((_abi.NUM_FIELDS, Cs, Tmax), **kw) if traj else None,
+            prob=torch.empty((Cs, O, Tmax - 1), **kw) if prob else None,
+            red=torch.empty((_abi.NUM_RED, Cs, O), **kw) if red else None,
+            cost=torch.empty((_abi.NUM_COST, Cs), **kw) if cost else None,
+            level=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
+            reason=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
+        )
+
+    def launch(self, s, bufs=None):
+        """Asynchronous etp_plan_step; ``bufs`` is a dict from allocate_outputs or None (argmin only)."""
+        if bufs is None:
+            self._check(self.lib.etp_plan_step(self.h, C.byref(s), None))
+            return
+        o = _abi.Out()
+        o.precision = self.precision
+        for k in ("traj", "prob", "red", "cost", "level", "reason"):
+            t = bufs.get(k)
+            setattr(o, k, None if t is None else C.c_void_p(t.data_ptr()))
+        self._check(self.lib.etp_plan_step(self.h, C.byref(s), C.byref(o)))
+
+    def best(self):
+        b = _abi.Best()
+        self._check(self.lib.etp_get_best(self.h, C.byref(b)))
+        return dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored, list_index=b.list_index,
+                    key_hi=b.key_hi, key_lo=b.key_lo)
+
+    def best_raw(self):
+        """Best record without raising on 'no candidate' (used by the sharded arg-min)."""
+        b = _abi.Best()
+        rc = self.lib.etp_get_best(self.h, C.byref(b))
+        if rc not in (_abi.OK, _abi.ERR_NO_CANDIDATE):
+            self._check(rc)
+        return b
+
+    def trajectory(self, index):
+        f = np.zeros((_abi.NUM_FIELDS, self._last_tmax), dtype=np.float64)
+        n = C.c_int32(0)
+        self._check(self.lib.etp_get_trajectory(self.h, int(index), _dptr(f), C.byref(n)))
+        return f, int(n.value)
+
+    def plan(self, step: PlanningStep, materialize=True, c_begin=None, c_end=None, bufs=None,
+             configure=True) -> ScoreResult:
+        """calc_frenet_trajectories + sort_frenet_trajectories + selection of one step
+        (frenet_planner.py:326-340, 433-457, 555-558)."""
+        if configure:
+            self.configure(step)
+        s, keep, n = self.make_step_struct(step, c_begin, c_end)
+        Tmax = int(n.max())
+        Cs = s.c_end - s.c_begin
+        if materialize and bufs is None:
+            bufs = self.allocate_outputs(Cs, Tmax, self.O)
+        self.launch(s, bufs if materialize else None)
+        self._last_tmax = Tmax
+        self.last_dt = step.dt
+        best = self.best()
+        res = ScoreResult(n_dense=step.n_dense, c_begin=s.c_begin, c_end=s.c_end, Tmax=Tmax, n_samples=n,
+                          obstacle_ids=list(self.obstacle_ids), best=best, _ctx=self)
+        if materialize:
+            for k, v in bufs.items():
+                setattr(res, k, v)
+        return res

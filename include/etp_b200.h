@@ -1,0 +1,212 @@
+/*
+ * etp_b200.h - C ABI of the B200-native candidate-trajectory scoring path.
+ *
+ * The reference (TUMFTM/EthicalTrajectoryPlanning) is pure Python and has no FFI: its
+ * boundary for this path is a set of Python call signatures.  Each
+ * entry point below names the reference interface it replaces (paths relative to the
+ * reference root).  Signatures carry only plain pointers and sizes; no torch types.
+ *
+ * Conventions
+ *   - every function returns ETP_OK (0) or a negative etp_status; no exceptions cross the ABI;
+ *     etp_last_error() returns a human-readable message for the last failure on that context;
+ *   - one etp_ctx per (device, stream); a context is not thread-safe, distinct contexts are
+ *     independent;
+ *   - INPUT pointers (parameters, spline, obstacles, grids, optional host masks) are HOST
+ *     memory: they are small (KBs) and are staged through pinned memory by the library;
+ *   - OUTPUT tensors in etp_out are caller-allocated DEVICE memory (e.g. torch tensors'
+ *     data_ptr()); any of them may be NULL, in which case that tensor is not materialised;
+ *   - etp_plan_step() is asynchronous on the context's stream; etp_get_best() /
+ *     etp_get_best_trajectory() synchronise and read back a few hundred bytes.
+ *
+ * Index conventions
+ *   dense candidate index  c = (iv * nt + it) * nd + id   (generation order v -> t -> d of
+ *   planner/Frenet/utils/frenet_functions.py:247,253,330).  Candidates the reference skips
+ *   (`ds <= |dT|`, frenet_functions.py:333-334) keep their dense slot with level ETP_LEVEL_SKIPPED.
+ */
+#ifndef ETP_B200_H
+#define ETP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct etp_ctx etp_ctx;
+
+typedef enum {
+    ETP_OK = 0,
+    ETP_ERR_CUDA = -1,         /* a CUDA runtime call failed */
+    ETP_ERR_INVALID = -2,      /* bad argument / inconsistent sizes */
+    ETP_ERR_UNSUPPORTED = -3,  /* mode outside the scored path (e.g. gidas harm, reach-set responsibility) */
+    ETP_ERR_NO_CANDIDATE = -4, /* every candidate skipped: the reference raises ValueError (frenet_functions.py:562-564) */
+    ETP_ERR_STATE = -5         /* params / spline / obstacles not set before plan_step */
+} etp_status;
+
+/* order of etp_params.weights: keys of planner/Frenet/configs/weights*.json */
+enum {
+    ETP_W_BAYES = 0, ETP_W_EQUALITY, ETP_W_MAXIMIN, ETP_W_RESPONSIBILITY, ETP_W_EGO, ETP_W_RISK_COST,
+    ETP_W_VISIBLE_AREA, ETP_W_LON_JERK, ETP_W_LAT_JERK, ETP_W_VELOCITY, ETP_W_DIST_TO_GLOBAL_PATH,
+    ETP_W_TRAVELLED_DIST, ETP_W_DIST_TO_GOAL_POS, ETP_W_DIST_TO_LANE_CENTER, ETP_NUM_WEIGHTS
+};
+
+/* rows of etp_out.traj: fields of FrenetTrajectory (frenet_functions.py:32-102) minus the shared t */
+enum {
+    ETP_F_D = 0, ETP_F_D_D, ETP_F_D_DD, ETP_F_D_DDD, ETP_F_S, ETP_F_S_D, ETP_F_S_DD, ETP_F_S_DDD,
+    ETP_F_X, ETP_F_Y, ETP_F_YAW, ETP_F_V, ETP_F_CURV, ETP_NUM_FIELDS
+};
+
+/* rows of etp_out.red: per (candidate, obstacle) reductions over time (risk_costs.py:98-101) */
+enum { ETP_R_EGO_RISK = 0, ETP_R_OBST_RISK, ETP_R_EGO_HARM, ETP_R_OBST_HARM, ETP_NUM_RED };
+
+/* rows of etp_out.cost (calc_trajectory_cost.py:130-146, 269-298, 321-346) */
+enum {
+    ETP_C_BAYES = 0, ETP_C_EQUALITY, ETP_C_MAXIMIN, ETP_C_RESPONSIBILITY, ETP_C_EGO, ETP_C_RISK_TOTAL,
+    ETP_C_VELOCITY, ETP_C_DIST_TO_GLOBAL_PATH, ETP_C_LON_JERK, ETP_C_LAT_JERK, ETP_C_TRAVELLED_DIST,
+    ETP_C_FACTOR, ETP_C_TOTAL, ETP_NUM_COST
+};
+
+/* validity levels (validity_checks.py:22-28) and the slot marker for skipped candidates */
+enum { ETP_LEVEL_PHYSICAL = 0, ETP_LEVEL_COLLISION = 1, ETP_LEVEL_BOUNDARY = 2, ETP_LEVEL_MAX_RISK = 3,
+       ETP_LEVEL_VALID = 10, ETP_LEVEL_SKIPPED = 255 };
+
+/* reason_invalid strings of validity_checks.py:68-122 as codes */
+enum { ETP_REASON_NONE = 0, ETP_REASON_VELOCITY = 1, ETP_REASON_ACCELERATION = 2, ETP_REASON_CURV_LVC = 3,
+       ETP_REASON_CURV_HVC = 4, ETP_REASON_COLLISION = 5, ETP_REASON_BOUNDARIES = 6, ETP_REASON_MAX_RISK = 7 };
+
+/* planner mode (frenet_planner.py:199-202, frenet_functions.py:524-527, validity_checks.py:287) */
+enum { ETP_MODE_RISK = 0, ETP_MODE_WALENET = 1, ETP_MODE_GROUND_TRUTH = 2 };
+
+/* element type of the real-valued output tensors and of the risk arithmetic */
+enum { ETP_PRECISION_FP32 = 0, ETP_PRECISION_FP64 = 1 };
+
+#define ETP_MAX_ANGLE_BINS 8
+
+/*
+ * Flattened params_dict = {'weights', 'modes', 'harm'} (frenet_planner.py:149-153) plus the
+ * vehicle constants of planner/utils/vehicleparams.py:63-91.
+ *
+ * The protected-occupant log-reg model selected by risk.json (harm_estimation.py:358-400) is
+ * passed as thresholds on |angle| plus one coefficient per band and sign:
+ *   band 0: |a| < thr[0]  (front, coefficient 0), band i: thr[i-1] <= |a| < thr[i], last band: else.
+ * (logistic_regression_symmetrical.py:7-130, logistic_regression_asymmetrical.py:7-96.)
+ */
+typedef struct {
+    double weights[ETP_NUM_WEIGHTS];
+    int32_t planner_mode;            /* ETP_MODE_* */
+    int32_t fast_prob_mahalanobis;   /* risk.json: collision_probability.py:259-292 instead of 136-256 */
+    int32_t multiple_cost_functions; /* risk.json: calc_trajectory_cost.py:322-327 */
+    int32_t n_angle_thresholds;      /* 0 = ignore angle (LR1S) */
+    double max_acceptable_risk;      /* validity_checks.py:277-294 */
+    double angle_thr[ETP_MAX_ANGLE_BINS];
+    double angle_coef_pos[ETP_MAX_ANGLE_BINS + 1];
+    double angle_coef_neg[ETP_MAX_ANGLE_BINS + 1];
+    double lr_const, lr_speed;       /* selected protected model */
+    double lr1s_const, lr1s_speed;   /* ignore-angle model: ego harm against unprotected obstacles */
+    double ped_const, ped_speed;     /* harm_parameters.json "pedestrian" (harm_estimation.py:408-414) */
+    double veh_l, veh_w, veh_l_r, veh_m, veh_steer_max, veh_lat_a_max, veh_v_max, veh_a_max;
+} etp_params;
+
+/*
+ * Data contract 1 of SURVEY.md 8b: the `predictions` dict after
+ * get_orientation_velocity_and_shape_of_prediction (prediction_helpers.py:75-135) and
+ * assign_responsibility_by_action_space (responsibility.py:57-75), as SoA host arrays.
+ * n_obstacles = -1 means `predictions is None` (no risk assessment at all).
+ */
+typedef struct {
+    int32_t n_obstacles;          /* O */
+    int32_t max_pred;             /* row stride Tp of the arrays below */
+    const int32_t* pred_len;      /* [O] valid prediction length per obstacle (>= 1) */
+    const double* pos;            /* [O][max_pred][2]  pos_list */
+    const double* cov;            /* [O][max_pred][4]  cov_list, row major 2x2 */
+    const double* yaw;            /* [O][max_pred]     orientation_list */
+    const double* vel;            /* [O][max_pred]     v_list */
+    const double* length;         /* [O] shape['length'] (margin included) */
+    const double* width;          /* [O] shape['width'] */
+    const double* mass;           /* [O] get_obstacle_mass (properties.py:14-46) */
+    const int32_t* is_protected;  /* [O] obstacle_protection (harm_estimation.py:41-58): 1 / 0 */
+    const int32_t* responsibility;/* [O] predictions[id]['responsibility'] */
+} etp_obstacles;
+
+/*
+ * Arguments of calc_frenet_trajectories (frenet_functions.py:207-221) plus the host-only
+ * cost context of sort_frenet_trajectories the GPU cannot derive (last row).
+ */
+typedef struct {
+    double c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd;
+    const double* v_list; int32_t nv;
+    const double* t_list; int32_t nt;
+    const int32_t* n_samples;       /* [nt] len(np.arange(0, tT, dt)) (frenet_functions.py:267) */
+    const double* d_list; int32_t nd;
+    double dt, v_thr;
+    int32_t velocity_cost_mode;     /* outcome of velocity_costs (calc_trajectory_cost.py:438-519):
+                                       0 |target - mean v|, 1 30 - mean v, 2 mean v, 3 zero */
+    double velocity_target;
+    double cost_factor;             /* get_cost_factor (calc_trajectory_cost.py:349-415) */
+    const uint8_t* ext_level;       /* optional [nv*nt*nd]: 1 collision, 2 boundary, else pass (pycrcc results) */
+    const double* bd_harm;          /* optional [nv*nt*nd]: boundary harm (risk_costs.py:104-123) */
+    int32_t c_begin, c_end;         /* dense candidate range scored by this call (shard); must be profile aligned */
+} etp_step;
+
+/* Caller-allocated device tensors for the scored range [c_begin, c_end); Cs = c_end - c_begin. */
+typedef struct {
+    int32_t precision;   /* ETP_PRECISION_*; element type of traj/prob/red/cost */
+    void* traj;          /* [ETP_NUM_FIELDS][Cs][Tmax]   (entries past a candidate's T are 0) */
+    void* prob;          /* [Cs][O][Tmax-1]              collision probability per timestep */
+    void* red;           /* [ETP_NUM_RED][Cs][O] */
+    void* cost;          /* [ETP_NUM_COST][Cs] */
+    uint8_t* level;      /* [Cs] validity level or ETP_LEVEL_SKIPPED */
+    uint8_t* reason;     /* [Cs] ETP_REASON_* */
+} etp_out;
+
+/* Selected candidate: sort by (highest non-empty level, cost, generation order)
+ * (frenet_functions.py:562-570, frenet_planner.py:457,555-558). */
+typedef struct {
+    uint64_t key_hi;     /* (4 - level rank) << 60 | monotone(cost) >> 4 : smaller is better */
+    uint64_t key_lo;     /* dense candidate index */
+    double cost;
+    int32_t index;       /* dense index, -1 if no candidate */
+    int32_t level;
+    int32_t n_scored;    /* non-skipped candidates in the range */
+    int32_t list_index;  /* position in the reference's fp_list (rank among non-skipped), shard-local count */
+} etp_best;
+
+int etp_create(etp_ctx** ctx, int device);
+int etp_destroy(etp_ctx* ctx);
+const char* etp_last_error(const etp_ctx* ctx);
+const char* etp_version(void);
+
+/* Use an existing CUDA stream (cudaStream_t as void*); NULL restores the context's own stream. */
+int etp_set_stream(etp_ctx* ctx, void* cuda_stream);
+
+/* replaces params_dict / vehicle_params arguments of sort_frenet_trajectories (frenet_functions.py:477-495) */
+int etp_set_params(etp_ctx* ctx, const etp_params* params);
+
+/* replaces the `csp` argument of calc_frenet_trajectories (frenet_functions.py:218,278):
+ * knots[n_seg+1], coef_x/coef_y[n_seg][4] with value = a + b*ds + c*ds^2 + d*ds^3 */
+int etp_set_spline(etp_ctx* ctx, const double* knots, const double* coef_x, const double* coef_y, int n_seg);
+
+/* replaces the `predictions` argument (frenet_functions.py:481; collision_probability.py:136; harm_estimation.py:202) */
+int etp_set_obstacles(etp_ctx* ctx, const etp_obstacles* obstacles, int precision);
+
+/* calc_frenet_trajectories + sort_frenet_trajectories + selection for the dense range of `step`:
+ * frenet_planner.py:326-340, 433-457, 555-558.  `out` may be NULL (argmin-only mode). */
+int etp_plan_step(etp_ctx* ctx, const etp_step* step, const etp_out* out);
+
+/* number of timesteps Tmax the output tensors must be strided with for `step` */
+int etp_tmax(const etp_step* step);
+
+/* synchronises; best of the last etp_plan_step on this context */
+int etp_get_best(etp_ctx* ctx, etp_best* best);
+
+/* synchronises; the 13 fp64 field rows [ETP_NUM_FIELDS][Tmax] of dense candidate `index` of the last
+ * step (recomputed in fp64) -> `self._trajectory` (frenet_planner.py:564-576). n_samples receives T. */
+int etp_get_trajectory(etp_ctx* ctx, int index, double* fields, int* n_samples);
+
+/* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks) */
+int etp_combine_best(const etp_best* bests, int n, etp_best* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETP_B200_H */
