@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native candidate-trajectory scoring path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+One JSON line on stdout (rank 0).  Metric: candidates scored per second (BASELINE.json), on the
+synthetic dense grid of SURVEY.md section 8d ("cfg3": 1000 x 1000 candidates, T = 50, 32 obstacles),
+candidate-sharded over the ranks with an all-gather arg-min when N > 1 (strong scaling).  A "step"
+is one planning step: profile stage + fused scoring kernel (+ the 40-byte collective).
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidates_scored_per_sec"
+UNIT = "candidates/s"
+
+
+def algorithmic_bytes_per_candidate(T, O):
+    """13 trajectory fields + probability tensor + 4 per-obstacle reductions +
+    10 cost scalars (fp32) + level + skip flag, each written once."""
+    return 4 * (13 * T + O * (T - 1) + 4 * O + 10) + 2
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(workload):
+    """dram bytes per launch of the scoring kernel from the committed ncu summary, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle's loop-structured port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(sub):
+    from oracle import bvn, port
+
+    t0 = time.perf_counter()
+    try:
+        _, valid, invalid, allfp = port.plan_step(sub, mvnun=bvn.mvnun_fast)
+        n = len(allfp)
+    except ValueError:  # every candidate of the chunk skipped
+        n = 0
+    return n, time.perf_counter() - t0
+
+
+def cpu_sample_steps(step, n_candidates, seed=0):
+    """A uniform random sub-grid of about ``n_candidates`` candidates of the same planning step."""
+    rng = np.random.default_rng(seed)
+    nv, nd = len(step.v_list), len(step.d_list)
+    k = max(1, int(round(np.sqrt(n_candidates))))
+    kv, kd = min(nv, k), min(nd, max(1, n_candidates // max(1, min(nv, k))))
+    sub = copy.copy(step)
+    sub.v_list = np.sort(rng.choice(step.v_list, size=kv, replace=False))
+    sub.d_list = np.sort(rng.choice(step.d_list, size=kd, replace=False))
+    sub.ext_level = None
+    sub.bd_harm = None
+    return sub
+
+
+def cpu_rate(step, n_candidates, cores, pool, seed=0):
+    """candidates/s of the port on ``cores`` processes over a bounded sample."""
+    sub = cpu_sample_steps(step, n_candidates, seed)
+    chunks = []
+    for vs in np.array_split(sub.v_list, cores):
+        if len(vs) == 0:
+            continue
+        c = copy.copy(sub)
+        c.v_list = vs
+        chunks.append(c)
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, chunks)
+    wall = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    return n / wall, n, wall
+
+
+def run_reference_arm(args, step, workload_cfg):
+    import multiprocessing as mp
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    T = int(step.n_samples.max())
+    O = len(step.predictions)
+    with ctx.Pool(cores) as pool:
+        # calibrate: about one second of work per step
+        r, n, wall = cpu_rate(step, cores * 8, cores, pool, seed=99)
+        per_step = max(cores, int(r * args.ref_step_seconds))
+        for i in range(args.warmup):
+            cpu_rate(step, per_step, cores, pool, seed=i)
+        tot_n, tot_t = 0, 0.0
+        for i in range(args.steps):
+            r, n, wall = cpu_rate(step, per_step, cores, pool, seed=100 + i)
+            tot_n += n
+            tot_t += wall
+    value = tot_n / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_cfg,
+        "evals_per_sec": value * (T - 1) * O,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} uniformly sampled candidates of the same planning step per step "
+                                   f"({tot_n} scored in {tot_t:.1f} s), oracle/port.py on {cores} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args, step, workload_cfg):
+    import torch
+    import torch.distributed as dist
+
+    from ethicaltrajectoryplanning_b200 import _abi
+    from ethicaltrajectoryplanning_b200.distributed import ShardedPlanner, profile_shard
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+
+        cores = os.cpu_count() or 1
+        with mp.get_context("spawn").Pool(cores) as pool:
+            r, n, wall = cpu_rate(step, cores * 8, cores, pool, seed=99)
+            target = max(cores, int(r * args.cpu_seconds))
+            r, n, wall = cpu_rate(step, target, cores, pool, seed=7)
+        cpu_base = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{n} uniformly sampled candidates of the same planning step in {wall:.1f} s, "
+                              f"oracle/port.py (loop-structured fp64 restatement of the reference) on {cores} processes"}
+
+    ctx = ScoringContext(local_rank, "fp32")
+    ctx.configure(step)
+    n_prof = len(step.v_list) * len(step.t_list)
+    nd = len(step.d_list)
+    c0, c1 = profile_shard(n_prof, nd, rank, world)
+    s, keep, nsamp = ctx.make_step_struct(step, c0, c1)
+    Tmax = int(nsamp.max())
+    Cs = c1 - c0
+    O = ctx.O
+    bufs = ctx.allocate_outputs(Cs, Tmax, O)
+    sharded = ShardedPlanner(ctx) if world > 1 else None
+
+    def one_step():
+        if sharded is not None:
+            sharded.launch(s, bufs)
+        else:
+            ctx.launch(s, bufs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    # events are recorded on the stream the kernels are launched on (the context's own stream)
+    with torch.cuda.stream(ctx.stream):
+        ev0.record()
+        for _ in range(args.steps):
+            one_step()
+        ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    best = sharded.best() if sharded is not None else ctx.best()
+
+    # kernel-only duration of the fused scoring kernel (CUDA events around the launch, same steps)
+    ctx.enable_timing(True)
+    k_ms, p_ms = [], []
+    for _ in range(args.steps):
+        ctx.launch(s, bufs)
+        a, b = ctx.timing()
+        p_ms.append(a)
+        k_ms.append(b)
+    ctx.enable_timing(False)
+    kernel_ms = float(np.mean(k_ms))
+
+    # end to end through the public API with host buffers: configure (H2D), plan, best + trajectory (D2H)
+    h2d = (8 * (len(step.csp.s) + 8 * (len(step.csp.s) - 1)) + O * ctx_tp(step) * 8 * 8 + O * (3 * 8 + 3 * 4)
+           + 8 * (len(step.v_list) + len(step.t_list) + len(step.d_list)) + 4 * len(step.t_list))
+    d2h = 40 * world + 13 * Tmax * 8 + 4
+    for _ in range(2):
+        e2e_step(ctx, step, sharded, c0, c1, bufs)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ctx.stream):
+        e0.record()
+        for _ in range(args.steps):
+            e2e_best = e2e_step(ctx, step, sharded, c0, c1, bufs)
+        e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    total_candidates = step.n_dense
+    value = total_candidates * args.steps / (ms_total * 1e-3)
+    e2e_value = total_candidates * args.steps / (e2e_ms * 1e-3)
+    bytes_per_launch = Cs * algorithmic_bytes_per_candidate(Tmax, O)
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    prob_nonzero = None
+    if rank == 0:
+        prob_nonzero = float((bufs["prob"] != 0).float().mean().item())
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = latency_extras(ctx, torch)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg,
+            "evals_per_sec": value * (Tmax - 1) * O,
+            "nonzero_probability_fraction": prob_nonzero,
+            "selected": {"index": best["index"], "level": best["level"], "cost": best["cost"]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps, "selected_index": e2e_best["index"]},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": profiled_traffic(workload_cfg["workload"]), "peak_source": peak_src,
+                         "kernel": "etp::score_kernel<float>", "kernel_ms": kernel_ms, "profile_stage_ms": float(np.mean(p_ms)),
+                         "algorithmic_bytes_per_launch": int(bytes_per_launch)},
+            "cpu_baseline": cpu_base,
+            "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctx_tp(step):
+    return max((len(p["pos_list"]) for p in step.predictions.values()), default=0) if step.predictions else 0
+
+
+def e2e_step(ctx, step, sharded, c0, c1, bufs):
+    """The call a user makes: host inputs in, selected trajectory out."""
+    ctx.configure(step)
+    s, keep, nsamp = ctx.make_step_struct(step, c0, c1)
+    ctx._last_tmax = int(nsamp.max())
+    ctx.last_dt = step.dt
+    if sharded is not None:
+        sharded.launch(s, bufs)
+        best = sharded.best()
+        if c0 <= best["index"] < c1:
+            ctx.trajectory(best["index"])
+    else:
+        ctx.launch(s, bufs)
+        best = ctx.best()
+        ctx.trajectory(best["index"])
+    return best
+
+
+def latency_extras(ctx, torch):
+    """Single-step latency of the 10k-candidate configuration (BASELINE.json configs[1])."""
+    from ethicaltrajectoryplanning_b200.synthetic import make_step
+
+    step = make_step("cfg2")
+    ctx.configure(step)
+    s, keep, nsamp = ctx.make_step_struct(step)
+    Tmax = int(nsamp.max())
+    bufs = ctx.allocate_outputs(step.n_dense, Tmax, ctx.O)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, b in (("materialised", bufs), ("argmin_only", None)):
+        lat = []
+        for i in range(60):
+            flush.zero_()  # evict the previous step's outputs from L2
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.launch(s, b)
+            ctx.best()
+            lat.append(time.perf_counter() - t0)
+        lat = np.array(lat[10:]) * 1e3
+        out[name] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99))}
+    ctx.enable_timing(True)
+    ks = []
+    for i in range(30):
+        flush.zero_()
+        ctx.launch(s, bufs)
+        ks.append(ctx.timing()[1])
+    ctx.enable_timing(False)
+    k = float(np.median(ks))
+    bytes_ = step.n_dense * algorithmic_bytes_per_candidate(Tmax, ctx.O)
+    out["kernel_ms"] = k
+    out["candidates_per_sec_kernel"] = step.n_dense / (k * 1e-3)
+    out["hbm_gbs_kernel"] = bytes_ / (k * 1e-3) / 1e9
+    out["workload"] = "cfg2: 100x100 candidates, T=30, 8 obstacles; L2 flushed between steps (256 MiB write)"
+    return {"cfg2_single_step": out}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "planning", "cfg2", "cfg3"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget (ours arm)")
+    ap.add_argument("--ref-step-seconds", type=float, default=1.0, help="CPU work per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+
+    from ethicaltrajectoryplanning_b200.synthetic import GRIDS, make_step
+
+    step = make_step(args.workload)
+    nv, nd, dmax, tl, no = GRIDS[args.workload]
+    T = int(step.n_samples.max())
+    workload_cfg = {
+        "workload": args.workload,
+        "description": f"synthetic dense grid: {nv} end velocities x {nd} lateral offsets = {nv * nd} candidates, "
+                       f"T={T} samples, {no} Gaussian-predicted obstacles, weights_ethical.json, one planning step",
+        "candidates": nv * nd, "timesteps": T, "obstacles": no,
+        "sharding": "contiguous whole-profile candidate ranges per rank + all-gather arg-min of 40-byte records",
+        "l2": "materialised outputs per step exceed L2 (streamed once); inputs (<200 KB) are L2/shared-memory resident by design",
+    }
+    if args.impl == "reference":
+        run_reference_arm(args, step, workload_cfg)
+    else:
+        run_gpu_arm(args, step, workload_cfg)
+
+
+if __name__ == "__main__":
+    main()

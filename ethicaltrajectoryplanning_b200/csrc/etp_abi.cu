@@ -75,6 +75,8 @@ struct etp_ctx {
     PinnedBuf stage, best_host, traj_host;
     DevStep st{};
     int last_grid = 0;
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
 #define ETP_FAIL(ctx, code, ...)                            \
@@ -173,6 +175,8 @@ int etp_destroy(etp_ctx* c) {
     c->best_host.release();
     c->traj_host.release();
     if (c->staged) cudaEventDestroy(c->staged);
+    for (int i = 0; i < 3; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return ETP_OK;
@@ -184,7 +188,7 @@ int etp_set_stream(etp_ctx* c, void* s) {
     if (!c) return ETP_ERR_INVALID;
     ETP_CUDA(c, cudaSetDevice(c->device));
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (s == (void*)-1) ? c->own_stream : (cudaStream_t)s;
     return ETP_OK;
 }
 
@@ -205,7 +209,10 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
     d.multi_cost = p->multiple_cost_functions;
     d.n_thr = p->n_angle_thresholds;
     d.max_risk = p->max_acceptable_risk;
-    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) d.thr[i] = p->angle_thr[i];
+    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) {
+        d.thr[i] = p->angle_thr[i];
+        d.fcos[i] = std::cos(p->angle_thr[i]) * std::fabs(std::cos(p->angle_thr[i]));
+    }
     for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { d.coef_pos[i] = p->angle_coef_pos[i]; d.coef_neg[i] = p->angle_coef_neg[i]; }
     d.lr_const = p->lr_const; d.lr_speed = p->lr_speed;
     d.lr1s_const = p->lr1s_const; d.lr1s_speed = p->lr1s_speed;
@@ -379,9 +386,12 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
         dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
         dout.level = out->level; dout.reason = out->reason;
     }
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     ETP_CUDA(c, launch_profiles(st, c->pr, c->nskip.as<int>(), c->stream));
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, c->block_best.as<BestRec>(), c->counters.as<unsigned>(),
                              c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, &c->last_grid, c->stream));
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     c->have_step = true;
     return ETP_OK;
 }
@@ -415,6 +425,33 @@ int etp_get_trajectory(etp_ctx* c, int index, double* fields, int* n_samples) {
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(fields, c->traj_host.p, bytes);
     if (n_samples) memcpy(n_samples, c->traj_host.p + bytes, sizeof(int));
+    return ETP_OK;
+}
+
+int etp_best_device_ptr(etp_ctx* c, void** ptr) {
+    if (!c || !ptr) return ETP_ERR_INVALID;
+    *ptr = c->best_dev.p;
+    return ETP_OK;
+}
+
+int etp_enable_timing(etp_ctx* c, int enable) {
+    if (!c) return ETP_ERR_INVALID;
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    if (enable && !c->ev[0])
+        for (int i = 0; i < 3; ++i) ETP_CUDA(c, cudaEventCreate(&c->ev[i]));
+    c->timing = enable != 0;
+    return ETP_OK;
+}
+
+int etp_get_timing(etp_ctx* c, float* profile_ms, float* score_ms) {
+    if (!c) return ETP_ERR_INVALID;
+    if (!c->timing || !c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "timing not enabled or no step run");
+    ETP_CUDA(c, cudaEventSynchronize(c->ev[2]));
+    float a = 0.f, b = 0.f;
+    ETP_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    ETP_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    if (profile_ms) *profile_ms = a;
+    if (score_ms) *score_ms = b;
     return ETP_OK;
 }
 

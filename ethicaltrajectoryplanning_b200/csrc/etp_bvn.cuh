@@ -89,59 +89,79 @@ __device__ __forceinline__ double rect_prob(double xl, double xu, double yl, dou
     return bvu_d(xl, yl, r) - bvu_d(xu, yl, r) - bvu_d(xl, yu, r) + bvu_d(xu, yu, r);
 }
 
-// Phi(b) - Phi(a), a <= b, from the tail side (no cancellation)
+// Phi(b) - Phi(a), a <= b.  The interval is reflected so that a + b >= 0: then either 0 <= a (both
+// erfc values are tails, no cancellation) or a < 0 < b with |a| <= b (difference of O(1) numbers whose
+// result is at least Phi(b) - 1/2).  Branch free.
 __device__ __forceinline__ float dphi_f(float a, float b) {
     const float is2 = 0.70710678118654752440f;
-    if (a >= 0.0f) return 0.5f * (erfcf(a * is2) - erfcf(b * is2));
-    if (b <= 0.0f) return 0.5f * (erfcf(-b * is2) - erfcf(-a * is2));
-    return 0.5f * (erff(b * is2) + erff(-a * is2));
+    const bool neg = (a + b) < 0.0f;
+    const float lo = neg ? -b : a, hi = neg ? -a : b;
+    return 0.5f * (erfcf(lo * is2) - erfcf(hi * is2));
 }
 
-__device__ __forceinline__ float corner_sum_f(float xl, float xu, float yl, float yu, float s, float q) {
-    // q = log2(e) / (1 - s^2); E = exp2(q * (s*h*k - (h^2+k^2)/2))
-    const float hxu = 0.5f * xu * xu, hxl = 0.5f * xl * xl, hyu = 0.5f * yu * yu, hyl = 0.5f * yl * yl;
-    const float e_uu = exp2f(q * (s * (xu * yu) - (hxu + hyu)));
-    const float e_lu = exp2f(q * (s * (xl * yu) - (hxl + hyu)));
-    const float e_ul = exp2f(q * (s * (xu * yl) - (hxu + hyl)));
-    const float e_ll = exp2f(q * (s * (xl * yl) - (hxl + hyl)));
-    return (e_uu - e_lu) - (e_ul - e_ll);
-}
+// Gauss-Legendre nodes on theta in [0, asin r]: s_i = sin(theta_i), q_i = log2(e) / (1 - s_i^2),
+// c_i = w_i * asin(r) / (4 pi).  They depend on the correlation only and are shared by the nine
+// rectangles of one evaluation.
+template <int N> struct RhoNodes {
+    float s[N > 0 ? N : 1], q[N > 0 ? N : 1], c[N > 0 ? N : 1];
+};
 
-// fp32 rectangle probability, see file header.  `asr` = asin(r).
-__device__ float rect_prob(float xl, float xu, float yl, float yu, float r) {
-    const float ar = fabsf(r);
-    if (ar > 0.55f) return (float)rect_prob((double)xl, (double)xu, (double)yl, (double)yu, (double)r);
-    const float marg = dphi_f(xl, xu) * dphi_f(yl, yu);
-    if (r == 0.0f) return marg;
+template <int N> __device__ __forceinline__ RhoNodes<N> make_rho_nodes(float r) {
+    RhoNodes<N> n;
+    if (N == 0) return n;
     const float asr = asinf(r);
     const float LOG2E = 1.4426950408889634f;
-    float acc = 0.0f;
-    if (ar <= 0.35f) {
-        const float gx[2] = {0.3399810435848563f, 0.8611363115940526f};
-        const float gw[2] = {0.6521451548625461f, 0.3478548451374538f};
+    const float gx4[2] = {0.3399810435848563f, 0.8611363115940526f};
+    const float gw4[2] = {0.6521451548625461f, 0.3478548451374538f};
+    const float gx6[3] = {0.2386191860831969f, 0.6612093864662645f, 0.9324695142031521f};
+    const float gw6[3] = {0.4679139345726910f, 0.3607615730481386f, 0.1713244923791704f};
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-            for (int sg = -1; sg <= 1; sg += 2) {
-                const float s = sinf(asr * (0.5f + 0.5f * sg * gx[i]));
-                const float q = LOG2E / (1.0f - s * s);
-                acc += gw[i] * corner_sum_f(xl, xu, yl, yu, s, q);
-            }
-        }
-    } else {
-        const float gx[3] = {0.2386191860831969f, 0.6612093864662645f, 0.9324695142031521f};
-        const float gw[3] = {0.4679139345726910f, 0.3607615730481386f, 0.1713244923791704f};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int sg = -1; sg <= 1; sg += 2) {
-                const float s = sinf(asr * (0.5f + 0.5f * sg * gx[i]));
-                const float q = LOG2E / (1.0f - s * s);
-                acc += gw[i] * corner_sum_f(xl, xu, yl, yu, s, q);
-            }
-        }
+    for (int i = 0; i < N; ++i) {
+        const float g = (N == 4) ? gx4[i >> 1] : gx6[i >> 1];
+        const float w = (N == 4) ? gw4[i >> 1] : gw6[i >> 1];
+        const float th = asr * (0.5f + ((i & 1) ? 0.5f : -0.5f) * g);
+        // theta <= asin(0.55) = 0.58: odd Taylor polynomial of sin to x^9 (error < 1e-9)
+        const float t2 = th * th;
+        const float sn = th * (1.0f + t2 * (-1.6666667e-1f + t2 * (8.3333333e-3f + t2 * (-1.9841270e-4f + t2 * 2.7557319e-6f))));
+        n.s[i] = sn;
+        n.q[i] = __fdividef(LOG2E, 1.0f - sn * sn);
+        n.c[i] = w * asr * 0.07957747154594767f;  // 1 / (4 pi)
     }
-    return marg + acc * asr * 0.07957747154594767f;  // 1 / (4 pi)
+    return n;
+}
+
+// sum_i c_i * [E(xu,yu) - E(xl,yu) - E(xu,yl) + E(xl,yl)](theta_i)
+template <int N>
+__device__ __forceinline__ float rho_correction_f(const RhoNodes<N>& n, float xl, float xu, float yl, float yu) {
+    if (N == 0) return 0.0f;
+    const float huu = 0.5f * (xu * xu + yu * yu), hlu = 0.5f * (xl * xl + yu * yu);
+    const float hul = 0.5f * (xu * xu + yl * yl), hll = 0.5f * (xl * xl + yl * yl);
+    const float puu = xu * yu, plu = xl * yu, pul = xu * yl, pll = xl * yl;
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float s = n.s[i], q = n.q[i];
+        const float e_uu = exp2f(q * fmaf(s, puu, -huu));
+        const float e_lu = exp2f(q * fmaf(s, plu, -hlu));
+        const float e_ul = exp2f(q * fmaf(s, pul, -hul));
+        const float e_ll = exp2f(q * fmaf(s, pll, -hll));
+        acc = fmaf(n.c[i], (e_uu - e_lu) - (e_ul - e_ll), acc);
+    }
+    return acc;
+}
+
+// rectangles farther than this many standard deviations from the mean contribute < 1e-19
+#define ETP_PRUNE_SIGMA 9.0f
+
+template <int N>
+__device__ __forceinline__ float rect_prob_nodes_f(const RhoNodes<N>& n, float xl, float xu, float yl, float yu) {
+    if (xl > ETP_PRUNE_SIGMA || xu < -ETP_PRUNE_SIGMA || yl > ETP_PRUNE_SIGMA || yu < -ETP_PRUNE_SIGMA) return 0.0f;
+    return dphi_f(xl, xu) * dphi_f(yl, yu) + rho_correction_f<N>(n, xl, xu, yl, yu);
+}
+
+// strongly correlated predictions: fp64 Genz evaluation (kept out of line, rare)
+__device__ __noinline__ float rect_prob_fallback_f(float xl, float xu, float yl, float yu, float r) {
+    return (float)rect_prob((double)xl, (double)xu, (double)yl, (double)yu, (double)r);
 }
 
 }  // namespace etp

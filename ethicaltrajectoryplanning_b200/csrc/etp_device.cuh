@@ -15,7 +15,7 @@ enum { PF_S = 0, PF_S_D, PF_S_DD, PF_S_DDD, PF_GX, PF_GY, PF_YAW, PF_CURV, PF_CU
 // per-profile scalars
 enum { PM_DS = 0, PM_LOW, PM_T, PM_VEL_OK, PM_TEND, PM_COUNT };
 
-// rows of the packed obstacle tile, layout [field][o][t], element type R
+// rows of the packed obstacle tile, layout [field][t][o] (obstacle fastest: lanes map to obstacles), element type R
 enum {
     OF_MX = 0, OF_MY,      // pos_list[t]
     OF_EX, OF_EY,          // (length/2) * (cos, sin)(orientation_list[t+1])   (collision_probability.py:175)
@@ -23,6 +23,7 @@ enum {
     OF_PSI, OF_VO,         // orientation_list[t], v_list[t]                     (harm_estimation.py:313-328)
     OF_CPSI, OF_SPSI,      // cos / sin of orientation_list[t]
     OF_I00, OF_I01, OF_I11,// inverse covariance (Mahalanobis mode, collision_probability.py:279)
+    OF_WRAP,               // ceil((orientation_list[t] - pi) / 2pi): turns to bring the yaw into (-pi, pi]
     OF_COUNT
 };
 // per-obstacle constants [o][OC_COUNT], fp64
@@ -33,6 +34,7 @@ struct DevParams {
     int planner_mode, mahalanobis, multi_cost, n_thr;
     double max_risk;
     double thr[ETP_MAX_ANGLE_BINS];
+    double fcos[ETP_MAX_ANGLE_BINS];  // cos(thr) * |cos(thr)|: band tests on direction vectors (fp32 path)
     double coef_pos[ETP_MAX_ANGLE_BINS + 1];
     double coef_neg[ETP_MAX_ANGLE_BINS + 1];
     double lr_const, lr_speed, lr1s_const, lr1s_speed, ped_const, ped_speed;
@@ -63,7 +65,7 @@ struct DevStep {
     // obstacles
     int has_pred;  // 0: predictions is None
     int O, Tp;
-    const void* obs;         // packed tile [OF_COUNT][O][Tp] of R
+    const void* obs;         // packed tile [OF_COUNT][Tp][O] of R
     const double* obs_const; // [O][OC_COUNT]
     const int* pred_len;     // [O]
     // raw fp64 copies for the exact gate re-check of the fp32 path
@@ -153,6 +155,7 @@ __device__ __forceinline__ Poly5 lateral_poly(const DevStep& st, bool low, doubl
 struct TrajPoint {
     double f[ETP_NUM_FIELDS];
     double cos_yaw, sin_yaw;
+    double wrap;  // ceil((yaw - pi) / 2pi)
 };
 
 // One sample of one candidate: frenet_functions.py:357-365 / 404-411 (lateral state) and 420-435
@@ -200,6 +203,7 @@ __device__ __forceinline__ TrajPoint traj_point(const Poly5& q, bool low, const 
     r.f[ETP_F_CURV] = (((dpp + (krd * d + kr * dp) * z) * ((cd * cd) / om)) + kr) * (cd / om);
     r.cos_yaw = cd * cr - sd * sr;
     r.sin_yaw = sd * cr + cd * sr;
+    r.wrap = ceil((r.f[ETP_F_YAW] - 3.14159265358979323846) / 6.28318530717958647692);
     return r;
 }
 

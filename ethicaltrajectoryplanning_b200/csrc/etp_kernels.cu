@@ -93,7 +93,7 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
     const int o = i / Tp, t = i % Tp;
     const int n = pred_len[o];
     const size_t plane = (size_t)O * Tp;
-    R* out = tile + (size_t)o * Tp + t;
+    R* out = tile + (size_t)t * O + o;  // [field][t][o]
     double v[OF_COUNT];
     for (int f = 0; f < OF_COUNT; ++f) v[f] = 0.0;
     if (t < n) {
@@ -120,6 +120,7 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
         v[OF_VO] = vel[(size_t)o * Tp + t];
         v[OF_CPSI] = cos(psi);
         v[OF_SPSI] = sin(psi);
+        v[OF_WRAP] = ceil((psi - 3.14159265358979323846) / 6.28318530717958647692);
         // Mahalanobis mode inverts cov_list itself (collision_probability.py:279), not the 0.1*I stand-in
         const double r00 = c[0], r01 = c[1], r10 = c[2], r11 = c[3];
         const double det = r00 * r11 - r01 * r10;
@@ -267,60 +268,53 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// score_kernel
+// score_kernel: persistent warps, one candidate per warp at a time
 // ---------------------------------------------------------------------------------------------
-struct TileSmem {
-    // carved from dynamic shared memory by carve()
-    double* prof;    // [PF_COUNT][Ts]
-    double* xd;      // [ND][Ts] exact ego x (gate re-check, travelled distance)
-    double* yd;      // [ND][Ts]
-    void* ego;       // [6][ND][Ts] of R: x, y, cos yaw, sin yaw, v, yaw
-    void* hmax;      // [2][ND*O] of R
-    void* rmax;      // [2][ND*O] of Enc<R>::U
-    double* cstat;   // [ND][8]: sum v, sum |d|, sum s_ddd^2, sum d_ddd^2, travelled, first curvature failure, skip, -
-    unsigned* queue; // [kWarps][kQueue]
-    unsigned long long* red_hi;  // [kWarps]
-    unsigned long long* red_lo;  // [kWarps]
-};
+// Work decomposition.  A candidate (one lateral target of one (v,t) profile) is owned by ONE warp for
+// its whole life: generation and Frenet->Cartesian transform (lanes over time), risk rows
+// (obstacle by obstacle, lanes over time, reductions over time with warp shuffles), principle
+// costs (lanes over obstacles), level, cost and arg-min key.  Warps pull chunks of consecutive
+// candidates from a global counter, so there is no block barrier inside the loop and no static
+// imbalance between obstacles or profiles.  Evaluations that pass the 5 m gate are deferred to a
+// warp-private queue and executed 32 at a time so that the expensive path runs with full warps.
+enum { EG_X = 0, EG_Y, EG_C, EG_S, EG_V, EG_YAW, EG_WRAP, EG_COUNT };
+constexpr int kChunk = 4;  // consecutive candidates per work grab (same profile rows stay in L1)
 
-enum { CS_SUMV = 0, CS_SUMD, CS_JLON, CS_JLAT, CS_TRAV, CS_CURVFAIL, CS_SKIP, CS_COUNT = 8 };
-enum { EG_X = 0, EG_Y, EG_C, EG_S, EG_V, EG_YAW, EG_COUNT };
-
-template <typename R> __host__ __device__ inline size_t tile_smem_bytes(int ND, int Ts, int O) {
-    size_t b = 0;
-    b += sizeof(double) * PF_COUNT * Ts;
-    b += sizeof(double) * 2 * ND * Ts;
-    b += sizeof(R) * EG_COUNT * ND * Ts;
-    b += sizeof(double) * 2 * 2 * ND * (O > 0 ? O : 1);  // hmax + rmax, sized for the fp64 case
-    b += sizeof(double) * ND * CS_COUNT;
-    b += sizeof(unsigned) * kWarps * kQueue;
-    b += sizeof(unsigned long long) * 2 * kWarps;
-    return b + 64;
-}
-
-template <typename R> __device__ __forceinline__ TileSmem carve(unsigned char* base, int ND, int Ts, int O) {
-    TileSmem s;
+template <typename R> __host__ __device__ inline size_t warp_smem_bytes(int Ts, int O) {
     const int On = O > 0 ? O : 1;
-    double* d = reinterpret_cast<double*>(base);
-    s.prof = d; d += PF_COUNT * Ts;
-    s.xd = d; d += ND * Ts;
-    s.yd = d; d += ND * Ts;
-    s.hmax = d; d += 2 * ND * On;
-    s.rmax = d; d += 2 * ND * On;
-    s.cstat = d; d += ND * CS_COUNT;
-    s.red_hi = reinterpret_cast<unsigned long long*>(d); d += kWarps;
-    s.red_lo = reinterpret_cast<unsigned long long*>(d); d += kWarps;
-    s.ego = d;
-    R* e = reinterpret_cast<R*>(d) + (size_t)EG_COUNT * ND * Ts;
-    s.queue = reinterpret_cast<unsigned*>(e);
-    return s;
+    size_t b = sizeof(double) * 2 * Ts;                 // exact ego x, y
+    b += sizeof(double) * 2 * On;                       // risk maxima (ordered-int encoded), sized for fp64
+    b += sizeof(R) * EG_COUNT * Ts;                     // ego stash
+    b += sizeof(R) * 2 * On;                            // harm logit maxima
+    b += sizeof(unsigned) * kQueue;                     // deferred evaluations
+    return (b + 15) & ~size_t(15);
 }
+
+template <typename R> struct WarpSmem {
+    double* xd;
+    double* yd;
+    typename Enc<R>::U* rmax;  // [2][On]
+    R* ego;                    // [EG_COUNT][Ts]
+    R* hmax;                   // [2][On]
+    unsigned* queue;
+    __device__ __forceinline__ WarpSmem(unsigned char* base, int Ts, int O) {
+        const int On = O > 0 ? O : 1;
+        double* d = reinterpret_cast<double*>(base);
+        xd = d; d += Ts;
+        yd = d; d += Ts;
+        rmax = reinterpret_cast<typename Enc<R>::U*>(d); d += 2 * On;
+        ego = reinterpret_cast<R*>(d);
+        hmax = ego + EG_COUNT * Ts;
+        queue = reinterpret_cast<unsigned*>(hmax + 2 * On);
+    }
+};
 
 template <typename R> struct Obs {
     const R* base;
     size_t plane;
     int Tp;
-    __device__ __forceinline__ R get(int f, int o, int t) const { return __ldg(base + f * plane + (size_t)o * Tp + t); }
+    int O;
+    __device__ __forceinline__ R get(int f, int o, int t) const { return __ldg(base + f * plane + (size_t)t * O + o); }
 };
 
 // impact-area coefficient (logistic_regression_*.py): thresholds on |angle|, sign picks the side
@@ -333,19 +327,50 @@ template <typename R> __device__ __forceinline__ R angle_coef(const DevParams& p
 
 // harm "logit arguments" of ego and obstacle at trajectory index t against obstacle sample t
 // (harm_estimation.py:313-332); harm = 1 / (1 + exp(-(const + arg))).
+// Band of an impact angle given as a direction: P = |d| cos(angle), d2 = |d|^2.  |angle| < thr is
+// cos(angle) > cos(thr), compared through the sign-preserving squares P|P| > d2 * cos(thr)|cos(thr)|.
+__device__ __forceinline__ int direction_band(const DevParams& pr, float P, float d2) {
+    const float fp = P * fabsf(P);
+    int i = 0;
+    while (i < pr.n_thr && !(fp > d2 * (float)pr.fcos[i])) ++i;
+    return i;
+}
+
+// fp32 path.  `ewrap` / `owrap` are the whole turns that bring the ego / obstacle yaw into (-pi, pi].
+// The reference bins the UN-wrapped angles rel - yaw_e and pi + rel - psi_o (quirk Q4) with
+// rel = atan2(dy, dx); instead of evaluating atan2, the relative direction is rotated into the ego /
+// obstacle frame (P, Q) and the number of 2 pi wraps of the un-wrapped difference is recovered from
+// the half planes of the two directions.  |angle| > pi always lands in the last ("rear") band.
 template <typename R>
-__device__ __forceinline__ void harm_args(const DevParams& pr, bool prot, R ke, R ko, R ex, R ey, R ec, R es, R ev, R eyaw,
-                                          R mx, R my, R opsi, R ovo, R ocp, R osp, R& arg_e, R& arg_o) {
+__device__ __forceinline__ void harm_args(const DevParams& pr, bool prot, R ke, R ko, R ex, R ey, R ec, R es, R ev, R ewrap,
+                                          R mx, R my, R owrap, R ovo, R ocp, R osp, R& arg_e, R& arg_o) {
     // delta_v = sqrt(v_e^2 + v_o^2 + 2 v_e v_o cos(pdof)), pdof = psi_o - psi_e + pi
     const R cpd = -(ocp * ec + osp * es);
     const R dv = sqrt_(ev * ev + ovo * ovo + 2 * ev * ovo * cpd);
     const R dve = ke * dv, dvo = ko * dv;
     if (prot) {
-        const R rel = atan2_(my - ey, mx - ex);
-        const R a_e = rel - eyaw;
-        const R a_o = (R)3.14159265358979323846 + rel - opsi;
-        arg_e = (R)pr.lr_speed * dve + angle_coef<R>(pr, a_e);
-        arg_o = (R)pr.lr_speed * dvo + angle_coef<R>(pr, a_o);
+        const R dx = mx - ex, dy = my - ey;
+        const R d2 = dx * dx + dy * dy;
+        const int last = pr.n_thr;
+        // ego: angle = rel - yaw_e
+        const R p = dx * ec + dy * es, q = dy * ec - dx * es;
+        int n0 = 0;
+        if (dy >= 0 && es < 0 && q < 0) n0 = 1;
+        if (dy < 0 && es >= 0 && q > 0) n0 = -1;
+        const int be = ((R)n0 != ewrap) ? last : direction_band(pr, p, d2);
+        const R ce = (R)(q < 0 ? pr.coef_neg[be] : pr.coef_pos[be]);
+        // obstacle: angle = pi + rel - psi_o
+        const R po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
+        n0 = 0;
+        if (dy >= 0 && osp < 0 && qo < 0) n0 = 1;
+        if (dy < 0 && osp >= 0 && qo > 0) n0 = -1;
+        const R k = (R)n0 - owrap;
+        const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
+        const bool neg_side = (k == (R)-1) && (qo >= 0);
+        const int bo = (pos_side || neg_side) ? direction_band(pr, -po, d2) : last;
+        const R co = (R)(neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo]);
+        arg_e = (R)pr.lr_speed * dve + ce;
+        arg_o = (R)pr.lr_speed * dvo + co;
     } else {
         arg_e = (R)pr.lr1s_speed * dve;
         arg_o = (R)pr.ped_speed * dvo;
@@ -376,8 +401,26 @@ template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { 
 
 // collision probability of one (ego sample i = t+1, obstacle sample t) pair
 // (collision_probability.py:205-252, 329-364): 3 means x 3 axis-aligned ego boxes.
-template <typename R>
-__device__ R collision_prob(const DevParams& pr, R x, R y, R c, R s, R mx, R my, R ex, R ey, R isx, R isy, R rho) {
+struct RectDouble {
+    __device__ __forceinline__ double operator()(double xl, double xu, double yl, double yu, double r) const {
+        return rect_prob(xl, xu, yl, yu, r);
+    }
+};
+struct RectFallbackF {
+    __device__ __forceinline__ float operator()(float xl, float xu, float yl, float yu, float r) const {
+        return rect_prob_fallback_f(xl, xu, yl, yu, r);
+    }
+};
+template <int N> struct RectNodesF {
+    RhoNodes<N> n;
+    __device__ __forceinline__ float operator()(float xl, float xu, float yl, float yu, float) const {
+        return rect_prob_nodes_f<N>(n, xl, xu, yl, yu);
+    }
+};
+
+template <typename R, typename Rect>
+__device__ __forceinline__ R nine_rectangles(const DevParams& pr, const Rect& rect, R x, R y, R c, R s, R mx, R my, R ex, R ey,
+                                             R isx, R isy, R rho) {
     const R hx = (R)(pr.veh_l / 6), hy = (R)(pr.veh_w / 2);
     const R rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
     R prob = 0;
@@ -391,10 +434,35 @@ __device__ R collision_prob(const DevParams& pr, R x, R y, R c, R s, R mx, R my,
             const R bx = x + sb * (rr * c), by = y + sb * (rr * s);
             const R xl = ((bx - hx) - ux) * isx, xu = ((bx + hx) - ux) * isx;
             const R yl = ((by - hy) - uy) * isy, yu = ((by + hy) - uy) * isy;
-            prob += rect_prob(xl, xu, yl, yu, rho);
+            prob += rect(xl, xu, yl, yu, rho);
         }
     }
     return prob / 3;
+}
+
+__device__ __forceinline__ double collision_prob(const DevParams& pr, double x, double y, double c, double s, double mx,
+                                                 double my, double ex, double ey, double isx, double isy, double rho) {
+    return nine_rectangles<double>(pr, RectDouble{}, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
+}
+
+__device__ float collision_prob(const DevParams& pr, float x, float y, float c, float s, float mx, float my, float ex,
+                                float ey, float isx, float isy, float rho) {
+    const float ar = fabsf(rho);
+    if (rho == 0.0f) {
+        RectNodesF<0> r;
+        return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
+    }
+    if (ar <= 0.35f) {
+        RectNodesF<4> r;
+        r.n = make_rho_nodes<4>(rho);
+        return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
+    }
+    if (ar <= 0.55f) {
+        RectNodesF<6> r;
+        r.n = make_rho_nodes<6>(rho);
+        return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
+    }
+    return nine_rectangles<float>(pr, RectFallbackF{}, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
 }
 
 // 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
@@ -404,291 +472,280 @@ template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R m
     return (R)1e-4 / sqrt_(m2);
 }
 
+struct WarpBest {
+    unsigned long long hi, lo;
+    double cost;
+    int level, scored;
+};
+
 template <typename R>
-__global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams pr, DevOut out, int ND, int tiles_per_profile,
-                                                         BestRec* __restrict__ block_best, unsigned int* __restrict__ counters,
-                                                         BestRec* __restrict__ best_out, const int* __restrict__ prof_nskip) {
+__global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams pr, DevOut out, BestRec* __restrict__ block_best,
+                                                         unsigned int* __restrict__ counters, BestRec* __restrict__ best_out,
+                                                         const int* __restrict__ prof_nskip) {
     using U = typename Enc<R>::U;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Ts = st.Tmax;
     const int O = st.has_pred ? st.O : 0;
-    TileSmem sm = carve<R>(smem_raw, ND, Ts, O);
-    R* ego = reinterpret_cast<R*>(sm.ego);
-    R* hmax = reinterpret_cast<R*>(sm.hmax);
-    U* rmaxs = reinterpret_cast<U*>(sm.rmax);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_prof = st.p_end - st.p_begin;
-    const int n_tiles = n_prof * tiles_per_profile;
+    WarpSmem<R> sm(smem_raw + (size_t)warp * warp_smem_bytes<R>(Ts, O), Ts, O);
     const int Cs = st.c_end - st.c_begin;
-    const int rows_max = ND * O;
-    Obs<R> ob{reinterpret_cast<const R*>(st.obs), (size_t)st.O * st.Tp, st.Tp};
+    const int On = O > 0 ? O : 1;
+    Obs<R> ob{reinterpret_cast<const R*>(st.obs), (size_t)st.O * st.Tp, st.Tp, st.O};
     R* o_traj = reinterpret_cast<R*>(out.traj);
     R* o_prob = reinterpret_cast<R*>(out.prob);
     R* o_red = reinterpret_cast<R*>(out.red);
     R* o_cost = reinterpret_cast<R*>(out.cost);
-    const size_t ego_plane = (size_t)ND * Ts;
+    R* ego = sm.ego;
 
-    unsigned long long my_hi = ~0ull, my_lo = ~0ull;  // running best of this thread (phase D owner threads)
-    double my_cost = 0.0;
-    int my_level = -1, my_scored = 0;
+    WarpBest wb{~0ull, ~0ull, 0.0, -1, 0};
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int pl = tile / tiles_per_profile;  // local profile
-        const int d0 = (tile % tiles_per_profile) * ND;
-        const int nd_here = min(ND, st.nd - d0);
-        const int p = st.p_begin + pl;
-        const double* gp = st.prof + (size_t)pl * PF_COUNT * Ts;
-        const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
-        const double ds = pm[PM_DS];
-        const bool low = pm[PM_LOW] != 0.0;
-        const int T = (int)pm[PM_T];
-        const bool vel_ok = pm[PM_VEL_OK] != 0.0;
-        const double t_end = pm[PM_TEND];
-        const int c_tile0 = p * st.nd + d0;          // dense index of the tile's first candidate
-        const int cl0 = c_tile0 - st.c_begin;        // index local to the scored range
-
-        // ---- phase A: profile rows to shared memory -------------------------------------------
-        for (int i = tid; i < PF_COUNT * Ts; i += kThreads) sm.prof[i] = gp[i];
-        for (int i = tid; i < 2 * rows_max; i += kThreads) rmaxs[i] = Enc<R>::enc((R)-INFINITY);
-        __syncthreads();
-
-        // ---- phase B: one warp per candidate, lanes over time ----------------------------------
-        for (int cl = warp; cl < nd_here; cl += kWarps) {
-            const double dT = st.d_list[d0 + cl];
+    for (;;) {
+        int chunk0 = 0;
+        if (lane == 0) chunk0 = (int)atomicAdd(&counters[1], (unsigned)kChunk);
+        chunk0 = __shfl_sync(kFull, chunk0, 0);
+        if (chunk0 >= Cs) break;
+        const int chunk1 = min(chunk0 + kChunk, Cs);
+        for (int cl = chunk0; cl < chunk1; ++cl) {
+            const int c_dense = st.c_begin + cl;
+            const int p = c_dense / st.nd, id = c_dense - p * st.nd;
+            const int pl = p - st.p_begin;
+            const double* gp = st.prof + (size_t)pl * PF_COUNT * Ts;
+            const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+            const double ds = pm[PM_DS];
+            const bool low = pm[PM_LOW] != 0.0;
+            const int T = (int)pm[PM_T];
+            const bool vel_ok = pm[PM_VEL_OK] != 0.0;
+            const double dT = st.d_list[id];
             const bool skip = ds <= fabs(dT);  // frenet_functions.py:333-334
-            const Poly5 q = lateral_poly(st, low, dT, t_end, ds);
-            double sv = 0, sd = 0, jl = 0, jq = 0;
-            int first_fail = 0x7fffffff;
-            for (int t = lane; t < Ts; t += 32) {
-                const size_t gi = (size_t)(cl0 + cl) * Ts + t;
-                if (t < T && !skip) {
-                    const TrajPoint tp = traj_point(q, low, sm.prof, Ts, t, st.dt);
-                    if (o_traj) {
-#pragma unroll
-                        for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[(size_t)f * Cs * Ts + gi] = (R)tp.f[f];
-                    }
-                    const int e = cl * Ts + t;
-                    sm.xd[e] = tp.f[ETP_F_X];
-                    sm.yd[e] = tp.f[ETP_F_Y];
-                    ego[EG_X * ego_plane + e] = (R)tp.f[ETP_F_X];
-                    ego[EG_Y * ego_plane + e] = (R)tp.f[ETP_F_Y];
-                    ego[EG_C * ego_plane + e] = (R)tp.cos_yaw;
-                    ego[EG_S * ego_plane + e] = (R)tp.sin_yaw;
-                    ego[EG_V * ego_plane + e] = (R)tp.f[ETP_F_V];
-                    ego[EG_YAW * ego_plane + e] = (R)tp.f[ETP_F_YAW];
-                    sv += tp.f[ETP_F_V];
-                    sd += fabs(tp.f[ETP_F_D]);
-                    jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
-                    jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
-                    const int cf = curvature_fail(pr, tp.f[ETP_F_V], tp.f[ETP_F_CURV]);
-                    if (cf) first_fail = min(first_fail, t * 4 + cf);
-                } else if (o_traj) {
-#pragma unroll
-                    for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[(size_t)f * Cs * Ts + gi] = (R)0;
-                }
-            }
-            __syncwarp();
-            double trav = 0;
-            if (!skip)
-                for (int t = lane; t + 1 < T; t += 32) {  // calc_trajectory_cost.py:739-757
-                    const int e = cl * Ts + t;
-                    const double dx = sm.xd[e] - sm.xd[e + 1], dy = sm.yd[e] - sm.yd[e + 1];
-                    trav += sqrt(dx * dx + dy * dy);
-                }
-            sv = warp_sum(sv); sd = warp_sum(sd); jl = warp_sum(jl); jq = warp_sum(jq); trav = warp_sum(trav);
-            first_fail = -warp_max(-first_fail);
-            if (lane == 0) {
-                double* cs = sm.cstat + cl * CS_COUNT;
-                cs[CS_SUMV] = sv; cs[CS_SUMD] = sd; cs[CS_JLON] = jl; cs[CS_JLAT] = jq; cs[CS_TRAV] = trav;
-                cs[CS_CURVFAIL] = first_fail == 0x7fffffff ? 0.0 : (double)(first_fail & 3);
-                cs[CS_SKIP] = skip ? 1.0 : 0.0;
-            }
-        }
-        __syncthreads();
 
-        // ---- phase C: rows (candidate, obstacle), lanes over time; un-gated work deferred to a
-        //      warp-private queue and executed densely ------------------------------------------
-        if (O > 0) {
-            unsigned* q = sm.queue + warp * kQueue;
-            int q_n = 0;
-            const int rows = nd_here * O;
-            auto run_entry = [&](unsigned entry) {
-                const int row = entry >> 8, t = entry & 255;
-                const int cl = row / O, o = row % O;
-                const int e1 = cl * Ts + t + 1, e0 = cl * Ts + t;
-                R prob;
-                if (pr.mahalanobis) {
-                    prob = inv_mahalanobis<R>(ego[EG_X * ego_plane + e1], ego[EG_Y * ego_plane + e1], ob.get(OF_MX, o, t),
-                                              ob.get(OF_MY, o, t), ob.get(OF_I00, o, t), ob.get(OF_I01, o, t),
-                                              ob.get(OF_I11, o, t));
-                } else {
-                    prob = collision_prob<R>(pr, ego[EG_X * ego_plane + e1], ego[EG_Y * ego_plane + e1],
-                                             ego[EG_C * ego_plane + e1], ego[EG_S * ego_plane + e1], ob.get(OF_MX, o, t),
-                                             ob.get(OF_MY, o, t), ob.get(OF_EX, o, t), ob.get(OF_EY, o, t),
-                                             ob.get(OF_ISX, o, t), ob.get(OF_ISY, o, t), ob.get(OF_RHO, o, t));
+            // ---- generation + transform: lanes over time ------------------------------------------
+            double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
+            int first_fail = 0x7fffffff;
+            {
+                const Poly5 q = lateral_poly(st, low, dT, pm[PM_TEND], ds);
+                for (int t = lane; t < Ts; t += 32) {
+                    const size_t gi = (size_t)cl * Ts + t;
+                    if (t < T && !skip) {
+                        const TrajPoint tp = traj_point(q, low, gp, Ts, t, st.dt);
+                        if (o_traj) {
+#pragma unroll
+                            for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[(size_t)f * Cs * Ts + gi] = (R)tp.f[f];
+                        }
+                        sm.xd[t] = tp.f[ETP_F_X];
+                        sm.yd[t] = tp.f[ETP_F_Y];
+                        ego[EG_X * Ts + t] = (R)tp.f[ETP_F_X];
+                        ego[EG_Y * Ts + t] = (R)tp.f[ETP_F_Y];
+                        ego[EG_C * Ts + t] = (R)tp.cos_yaw;
+                        ego[EG_S * Ts + t] = (R)tp.sin_yaw;
+                        ego[EG_V * Ts + t] = (R)tp.f[ETP_F_V];
+                        ego[EG_YAW * Ts + t] = (R)tp.f[ETP_F_YAW];
+                        ego[EG_WRAP * Ts + t] = (R)tp.wrap;
+                        sv += tp.f[ETP_F_V];
+                        sd += fabs(tp.f[ETP_F_D]);
+                        jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
+                        jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
+                        const int cf = curvature_fail(pr, tp.f[ETP_F_V], tp.f[ETP_F_CURV]);
+                        if (cf) first_fail = min(first_fail, t * 4 + cf);
+                    } else if (o_traj) {
+#pragma unroll
+                        for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[(size_t)f * Cs * Ts + gi] = (R)0;
+                    }
                 }
-                const double* oc = st.obs_const + o * OC_COUNT;
-                const bool prot = oc[OC_PROT] != 0.0;
-                R ae, ao;
-                harm_args<R>(pr, prot, (R)oc[OC_KE], (R)oc[OC_KO], ego[EG_X * ego_plane + e0], ego[EG_Y * ego_plane + e0],
-                             ego[EG_C * ego_plane + e0], ego[EG_S * ego_plane + e0], ego[EG_V * ego_plane + e0],
-                             ego[EG_YAW * ego_plane + e0], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t), ob.get(OF_PSI, o, t),
-                             ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t), ob.get(OF_SPSI, o, t), ae, ao);
-                const R he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), ae);
-                const R ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), ao);
-                atomicMax(&rmaxs[row], Enc<R>::enc(he * prob));               // risk_costs.py:88-95
-                atomicMax(&rmaxs[rows_max + row], Enc<R>::enc(ho * prob));
-                if (o_prob) o_prob[((size_t)(cl0 + cl) * O + o) * (Ts - 1) + t] = prob;
-            };
-            for (int row = warp; row < rows; row += kWarps) {
-                const int cl = row / O, o = row % O;
-                const bool skip = sm.cstat[cl * CS_COUNT + CS_SKIP] != 0.0;
-                const int n_pred = st.pred_len[o];
-                const double* oc = st.obs_const + o * OC_COUNT;
-                const bool prot = oc[OC_PROT] != 0.0;
-                const R ke = (R)oc[OC_KE], ko = (R)oc[OC_KO];
-                R hm_e = -INFINITY, hm_o = -INFINITY, rm = -INFINITY;
-                for (int t0 = 0; t0 < Ts - 1; t0 += 32) {
-                    const int t = t0 + lane;
-                    bool defer = false;
-                    if (t < Ts - 1) {
-                        const bool in_traj = !skip && t < T - 1;
-                        bool gated = true;
-                        if (in_traj && t < n_pred) {
-                            // harm sample t: ego[t] against prediction[t] (harm_estimation.py:234, 313-332)
-                            const int e0 = cl * Ts + t;
-                            R ae, ao;
-                            harm_args<R>(pr, prot, ke, ko, ego[EG_X * ego_plane + e0], ego[EG_Y * ego_plane + e0],
-                                         ego[EG_C * ego_plane + e0], ego[EG_S * ego_plane + e0], ego[EG_V * ego_plane + e0],
-                                         ego[EG_YAW * ego_plane + e0], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
-                                         ob.get(OF_PSI, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t),
-                                         ob.get(OF_SPSI, o, t), ae, ao);
-                            hm_e = rmax_(hm_e, ae);
-                            hm_o = rmax_(hm_o, ao);
-                            if (t + 1 < n_pred) {
-                                // probability sample t: ego[t+1] against mean[t], orientation[t+1]
-                                // (collision_probability.py:168-203)
-                                const int e1 = e0 + 1;
-                                if (pr.mahalanobis) {
-                                    gated = false;
-                                } else {
-                                    const R x = ego[EG_X * ego_plane + e1], y = ego[EG_Y * ego_plane + e1];
-                                    const R mx = ob.get(OF_MX, o, t), my = ob.get(OF_MY, o, t);
-                                    const R ex = ob.get(OF_EX, o, t), ey = ob.get(OF_EY, o, t);
-                                    R dx = mx - x, dy = my - y;
-                                    R d2 = dx * dx + dy * dy;
-                                    dx = (mx + ex) - x; dy = (my + ey) - y;
-                                    d2 = fmin(d2, dx * dx + dy * dy);
-                                    dx = (mx - ex) - x; dy = (my - ey) - y;
-                                    d2 = fmin(d2, dx * dx + dy * dy);
-                                    gated = sqrt_(d2) > (R)5.0;
-                                    if (sizeof(R) == 4 && abs_(d2 - (R)25) < (R)2e-3) {
-                                        // fp32 cannot decide the 5 m gate here: repeat it in fp64 from the exact inputs
-                                        const double xe = sm.xd[e1], ye = sm.yd[e1];
-                                        const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
-                                        const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
-                                        const double hl = oc[OC_HALFLEN];
-                                        const double fx = cos(y1) * (2 * hl) / 2, fy = sin(y1) * (2 * hl) / 2;
-                                        double ax = rp[0] - xe, ay = rp[1] - ye;
-                                        double m = sqrt(ax * ax + ay * ay);
-                                        ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
-                                        m = fmin(m, sqrt(ax * ax + ay * ay));
-                                        ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
-                                        m = fmin(m, sqrt(ax * ax + ay * ay));
-                                        gated = m > 5.0;
+                for (int o = lane; o < 2 * On; o += 32) sm.rmax[o] = Enc<R>::enc((R)-INFINITY);
+                __syncwarp();
+                if (!skip)
+                    for (int t = lane; t + 1 < T; t += 32) {  // calc_trajectory_cost.py:739-757
+                        const double dx = sm.xd[t] - sm.xd[t + 1], dy = sm.yd[t] - sm.yd[t + 1];
+                        trav += sqrt(dx * dx + dy * dy);
+                    }
+                sv = warp_sum(sv); sd = warp_sum(sd); jl = warp_sum(jl); jq = warp_sum(jq); trav = warp_sum(trav);
+                first_fail = -warp_max(-first_fail);
+            }
+
+            // ---- risk rows: lanes over obstacles, loop over time -------------------------------------
+            // Lane l owns obstacle ob + (l & (Op-1)) of the current block of <= 32 obstacles; when the
+            // block has fewer than 17 obstacles the spare lanes take further timesteps (tt = l / Op).
+            // Running maxima over time stay in registers; obstacle rows of the tile are read coalesced
+            // ([field][t][o]) and the ego sample of the step is a shared-memory broadcast.
+            if (O > 0 && !skip) {
+                constexpr int kEgoAng = sizeof(R) == 4 ? EG_WRAP : EG_YAW;
+                constexpr int kObsAng = sizeof(R) == 4 ? OF_WRAP : OF_PSI;
+                unsigned* q = sm.queue;
+                int q_n = 0;
+                auto run_entry = [&](unsigned entry) {
+                    const int o = entry >> 8, t = entry & 255;
+                    const int e1 = t + 1, e0 = t;
+                    R prob;
+                    if (pr.mahalanobis) {
+                        prob = inv_mahalanobis<R>(ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ob.get(OF_MX, o, t),
+                                                  ob.get(OF_MY, o, t), ob.get(OF_I00, o, t), ob.get(OF_I01, o, t),
+                                                  ob.get(OF_I11, o, t));
+                    } else {
+                        prob = collision_prob(pr, ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ego[EG_C * Ts + e1],
+                                              ego[EG_S * Ts + e1], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
+                                              ob.get(OF_EX, o, t), ob.get(OF_EY, o, t), ob.get(OF_ISX, o, t),
+                                              ob.get(OF_ISY, o, t), ob.get(OF_RHO, o, t));
+                    }
+                    const double* oc = st.obs_const + o * OC_COUNT;
+                    const bool prot = oc[OC_PROT] != 0.0;
+                    R ae, ao;
+                    harm_args<R>(pr, prot, (R)oc[OC_KE], (R)oc[OC_KO], ego[EG_X * Ts + e0], ego[EG_Y * Ts + e0],
+                                 ego[EG_C * Ts + e0], ego[EG_S * Ts + e0], ego[EG_V * Ts + e0], ego[kEgoAng * Ts + e0],
+                                 ob.get(OF_MX, o, t), ob.get(OF_MY, o, t), ob.get(kObsAng, o, t), ob.get(OF_VO, o, t),
+                                 ob.get(OF_CPSI, o, t), ob.get(OF_SPSI, o, t), ae, ao);
+                    const R he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), ae);
+                    const R ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), ao);
+                    atomicMax(&sm.rmax[o], Enc<R>::enc(he * prob));  // risk_costs.py:88-95
+                    atomicMax(&sm.rmax[On + o], Enc<R>::enc(ho * prob));
+                    if (o_prob) o_prob[((size_t)cl * (Ts - 1) + t) * O + o] = prob;
+                };
+                for (int ob0 = 0; ob0 < O; ob0 += 32) {
+                    const int rem = min(32, O - ob0);
+                    int Op = 32;
+                    while ((Op >> 1) >= rem) Op >>= 1;  // smallest power of two >= rem
+                    const int TT = 32 / Op;
+                    const int ol = lane & (Op - 1), tt = lane / Op;
+                    const int o = ob0 + ol;
+                    const bool o_ok = ol < rem;
+                    int n_pred = 0;
+                    bool prot = false;
+                    R ke = 0, ko = 0;
+                    double halflen = 0;
+                    if (o_ok) {
+                        const double* oc = st.obs_const + o * OC_COUNT;
+                        n_pred = st.pred_len[o];
+                        prot = oc[OC_PROT] != 0.0;
+                        ke = (R)oc[OC_KE];
+                        ko = (R)oc[OC_KO];
+                        halflen = oc[OC_HALFLEN];
+                    }
+                    R hm_e = -INFINITY, hm_o = -INFINITY, rm = -INFINITY;
+                    for (int t0 = 0; t0 < Ts - 1; t0 += TT) {
+                        const int t = t0 + tt;
+                        bool defer = false;
+                        if (o_ok && t < Ts - 1) {
+                            bool gated = true;
+                            if (t < T - 1 && t < n_pred) {
+                                // harm sample t: ego[t] against prediction[t] (harm_estimation.py:234, 313-332)
+                                const R mx = ob.get(OF_MX, o, t), my = ob.get(OF_MY, o, t);
+                                R ae, ao;
+                                harm_args<R>(pr, prot, ke, ko, ego[EG_X * Ts + t], ego[EG_Y * Ts + t], ego[EG_C * Ts + t],
+                                             ego[EG_S * Ts + t], ego[EG_V * Ts + t], ego[kEgoAng * Ts + t], mx, my,
+                                             ob.get(kObsAng, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t),
+                                             ob.get(OF_SPSI, o, t), ae, ao);
+                                hm_e = rmax_(hm_e, ae);
+                                hm_o = rmax_(hm_o, ao);
+                                if (t + 1 < n_pred) {
+                                    // probability sample t: ego[t+1] against mean[t], orientation[t+1]
+                                    // (collision_probability.py:168-203)
+                                    if (pr.mahalanobis) {
+                                        gated = false;
+                                    } else {
+                                        const R x = ego[EG_X * Ts + t + 1], y = ego[EG_Y * Ts + t + 1];
+                                        const R ex = ob.get(OF_EX, o, t), ey = ob.get(OF_EY, o, t);
+                                        R dx = mx - x, dy = my - y;
+                                        R d2 = dx * dx + dy * dy;
+                                        dx = (mx + ex) - x; dy = (my + ey) - y;
+                                        d2 = fmin(d2, dx * dx + dy * dy);
+                                        dx = (mx - ex) - x; dy = (my - ey) - y;
+                                        d2 = fmin(d2, dx * dx + dy * dy);
+                                        gated = sqrt_(d2) > (R)5.0;
+                                        if (sizeof(R) == 4 && abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y))) {
+                                            // fp32 cannot decide the 5 m gate here: repeat it in fp64 from the exact inputs
+                                            const double xe = sm.xd[t + 1], ye = sm.yd[t + 1];
+                                            const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                                            const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+                                            const double len = 2 * halflen;
+                                            const double fx = cos(y1) * len / 2, fy = sin(y1) * len / 2;
+                                            double ax = rp[0] - xe, ay = rp[1] - ye;
+                                            double m = sqrt(ax * ax + ay * ay);
+                                            ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
+                                            m = fmin(m, sqrt(ax * ax + ay * ay));
+                                            ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
+                                            m = fmin(m, sqrt(ax * ax + ay * ay));
+                                            gated = m > 5.0;
+                                        }
                                     }
                                 }
+                                if (gated) rm = rmax_(rm, (R)0);  // harm * 0.0
+                                else defer = true;
                             }
-                            if (gated) rm = rmax_(rm, (R)0);  // harm * 0.0
-                            else defer = true;
+                            if (!defer && o_prob) o_prob[((size_t)cl * (Ts - 1) + t) * O + o] = (R)0;
                         }
-                        if (!defer && o_prob) o_prob[((size_t)(cl0 + cl) * O + o) * (Ts - 1) + t] = (R)0;
-                    }
-                    const unsigned m = __ballot_sync(kFull, defer);
-                    if (m) {
-                        if (defer) q[(q_n + __popc(m & ((1u << lane) - 1))) % kQueue] = ((unsigned)row << 8) | (unsigned)t;
-                        q_n += __popc(m);
-                        __syncwarp();
-                        if (q_n >= 32) {
-                            q_n -= 32;
-                            run_entry(q[(q_n + lane) % kQueue]);
+                        const unsigned m = __ballot_sync(kFull, defer);
+                        if (m) {
+                            if (defer) q[q_n + __popc(m & ((1u << lane) - 1))] = ((unsigned)o << 8) | (unsigned)t;
+                            q_n += __popc(m);
                             __syncwarp();
+                            if (q_n >= 32) {
+                                q_n -= 32;
+                                run_entry(q[q_n + lane]);
+                                __syncwarp();
+                            }
+                        }
+                    }
+                    // lanes that share an obstacle (different tt) combine their maxima
+                    for (int off = Op; off < 32; off <<= 1) {
+                        hm_e = rmax_(hm_e, __shfl_xor_sync(kFull, hm_e, off));
+                        hm_o = rmax_(hm_o, __shfl_xor_sync(kFull, hm_o, off));
+                        rm = rmax_(rm, __shfl_xor_sync(kFull, rm, off));
+                    }
+                    if (o_ok && tt == 0) {
+                        sm.hmax[o] = hm_e;
+                        sm.hmax[On + o] = hm_o;
+                        if (rm > (R)-INFINITY) {
+                            atomicMax(&sm.rmax[o], Enc<R>::enc(rm));
+                            atomicMax(&sm.rmax[On + o], Enc<R>::enc(rm));
                         }
                     }
                 }
-                hm_e = warp_max(hm_e); hm_o = warp_max(hm_o); rm = warp_max(rm);
-                if (lane == 0) {
-                    hmax[row] = hm_e;
-                    hmax[rows_max + row] = hm_o;
-                    if (rm > (R)-INFINITY) {
-                        atomicMax(&rmaxs[row], Enc<R>::enc(rm));
-                        atomicMax(&rmaxs[rows_max + row], Enc<R>::enc(rm));
-                    }
-                }
+                if (lane < q_n) run_entry(q[lane]);  // drain: entries live at [0, q_n)
+                __syncwarp();
+            } else if (O > 0 && o_prob) {
+                for (int i = lane; i < O * (Ts - 1); i += 32) o_prob[(size_t)cl * O * (Ts - 1) + i] = (R)0;
             }
-            // drain: entries live at ring positions [0, q_n) by construction (pops take the top 32)
-            if (q_n > 0) {
-                if (lane < q_n) run_entry(q[lane % kQueue]);
-            }
-        }
-        __syncthreads();
 
-        // ---- phase D: per-candidate principles, cost, level, key -------------------------------
-        if (o_red && O > 0) {
-            for (int i = tid; i < nd_here * O; i += kThreads) {
-                const int cl = i / O, o = i % O;
-                const bool skip = sm.cstat[cl * CS_COUNT + CS_SKIP] != 0.0;
-                const double* oc = st.obs_const + o * OC_COUNT;
-                const bool prot = oc[OC_PROT] != 0.0;
-                const size_t g = (size_t)(cl0 + cl) * O + o;
-                const size_t plane = (size_t)Cs * O;
-                R re = 0, ro = 0, he = 0, ho = 0;
-                if (!skip) {
-                    re = Enc<R>::dec(rmaxs[i]);
-                    ro = Enc<R>::dec(rmaxs[rows_max + i]);
-                    he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), hmax[i]);
-                    ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), hmax[rows_max + i]);
-                }
-                o_red[ETP_R_EGO_RISK * plane + g] = re;
-                o_red[ETP_R_OBST_RISK * plane + g] = ro;
-                o_red[ETP_R_EGO_HARM * plane + g] = he;
-                o_red[ETP_R_OBST_HARM * plane + g] = ho;
-            }
-        }
-        if (tid < nd_here) {
-            const int cl = tid;
-            const int c_dense = c_tile0 + cl;
-            const size_t g = (size_t)(cl0 + cl);
-            const double* cs = sm.cstat + cl * CS_COUNT;
-            const bool skip = cs[CS_SKIP] != 0.0;
+            // ---- principles (lanes over obstacles), cost, level, key --------------------------------
             double c[ETP_NUM_COST];
 #pragma unroll
             for (int k = 0; k < ETP_NUM_COST; ++k) c[k] = 0.0;
             int level = ETP_LEVEL_SKIPPED, reason = ETP_REASON_NONE;
-            if (!skip) {
-                const double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
-                const int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
-                double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
-                for (int o = 0; o < O; ++o) {
+            double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
+            for (int o = lane; o < O; o += 32) {
+                R re = 0, ro = 0, he = 0, ho = 0;
+                if (!skip) {
                     const double* oc = st.obs_const + o * OC_COUNT;
                     const bool prot = oc[OC_PROT] != 0.0;
-                    const double re = (double)Enc<R>::dec(rmaxs[cl * O + o]);
-                    const double ro = (double)Enc<R>::dec(rmaxs[rows_max + cl * O + o]);
-                    const double he = (double)sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), hmax[cl * O + o]);
-                    const double ho = (double)sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), hmax[rows_max + cl * O + o]);
-                    sum_e += re;
-                    sum_o += ro;
-                    sum_abs += fabs(re - ro);
-                    resp -= oc[OC_RESP] * ro;                       // risk_costs.py:250-253
-                    mm = fmax(mm, he * (re < 10e-10 ? 1.0 : 0.0));  // risk_costs.py:205-206 (quirk Q3)
-                    mm = fmax(mm, ho * (ro < 10e-10 ? 1.0 : 0.0));
-                    max_o = fmax(max_o, ro);
+                    re = Enc<R>::dec(sm.rmax[o]);
+                    ro = Enc<R>::dec(sm.rmax[On + o]);
+                    he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), sm.hmax[o]);
+                    ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), sm.hmax[On + o]);
+                    sum_e += (double)re;
+                    sum_o += (double)ro;
+                    sum_abs += fabs((double)re - (double)ro);
+                    resp -= oc[OC_RESP] * (double)ro;                                // risk_costs.py:250-253
+                    mm = fmax(mm, (double)he * ((double)re < 10e-10 ? 1.0 : 0.0));  // risk_costs.py:205-206 (Q3)
+                    mm = fmax(mm, (double)ho * ((double)ro < 10e-10 ? 1.0 : 0.0));
+                    max_o = fmax(max_o, (double)ro);
                 }
+                if (o_red) {
+                    const size_t g = (size_t)cl * O + o, plane = (size_t)Cs * O;
+                    o_red[ETP_R_EGO_RISK * plane + g] = re;
+                    o_red[ETP_R_OBST_RISK * plane + g] = ro;
+                    o_red[ETP_R_EGO_HARM * plane + g] = he;
+                    o_red[ETP_R_OBST_HARM * plane + g] = ho;
+                }
+            }
+            if (!skip) {
+                sum_e = warp_sum(sum_e); sum_o = warp_sum(sum_o); sum_abs = warp_sum(sum_abs); resp = warp_sum(resp);
+                mm = warp_max(mm); max_o = warp_max(max_o);
+                const double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
+                const int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
                 if (O > 0) {
-                    c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);     // risk_costs.py:148-150
-                    c[ETP_C_EQUALITY] = sum_abs / (double)O;                     // :176-178
-                    c[ETP_C_MAXIMIN] = pow(fmax(mm, bd), 10.0);                  // :208
-                    c[ETP_C_EGO] = sum_e + bd;                                   // :226
+                    c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
+                    c[ETP_C_EQUALITY] = sum_abs / (double)O;                  // :176-178
+                    c[ETP_C_MAXIMIN] = pow(fmax(mm, bd), 10.0);               // :208
+                    c[ETP_C_EGO] = sum_e + bd;                                // :226
                     c[ETP_C_RESPONSIBILITY] = resp;
                 }
                 const bool risk_in_cost = pr.w[ETP_W_RISK_COST] > 0.0 && st.has_pred && pr.planner_mode == ETP_MODE_RISK;
@@ -697,20 +754,20 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                                           pr.w[ETP_W_MAXIMIN] * c[ETP_C_MAXIMIN] +
                                           pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES] * c[ETP_C_RESPONSIBILITY] +
                                           pr.w[ETP_W_EGO] * c[ETP_C_EGO];
-                const double mean_v = cs[CS_SUMV] / (double)T;
+                const double mean_v = sv / (double)T;
                 switch (st.vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
                     case 0: c[ETP_C_VELOCITY] = fabs(st.vel_target - mean_v); break;
                     case 1: c[ETP_C_VELOCITY] = 30.0 - mean_v; break;
                     case 2: c[ETP_C_VELOCITY] = mean_v; break;
                     default: c[ETP_C_VELOCITY] = 0.0;
                 }
-                c[ETP_C_DIST_TO_GLOBAL_PATH] = cs[CS_SUMD] / (double)T;  // :726-736
-                c[ETP_C_LON_JERK] = cs[CS_JLON] / (double)T;             // :418-435
-                c[ETP_C_LAT_JERK] = cs[CS_JLAT] / (double)T;
-                c[ETP_C_TRAVELLED_DIST] = cs[CS_TRAV];
+                c[ETP_C_DIST_TO_GLOBAL_PATH] = sd / (double)T;  // :726-736
+                c[ETP_C_LON_JERK] = jl / (double)T;             // :418-435
+                c[ETP_C_LAT_JERK] = jq / (double)T;
+                c[ETP_C_TRAVELLED_DIST] = trav;
                 c[ETP_C_FACTOR] = st.factor;
                 // validity level (validity_checks.py:31-122)
-                const int cf = (int)cs[CS_CURVFAIL];
+                const int cf = first_fail == 0x7fffffff ? 0 : (first_fail & 3);
                 if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
                 else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
                 else if (ext == 1) { level = 1; reason = ETP_REASON_COLLISION; }
@@ -732,48 +789,40 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                 c[ETP_C_TOTAL] = st.factor * cost;
                 const unsigned long long hi = make_key_hi(level, c[ETP_C_TOTAL]);
                 const unsigned long long lo = (unsigned long long)c_dense;
-                if (hi < my_hi || (hi == my_hi && lo < my_lo)) {
-                    my_hi = hi; my_lo = lo; my_cost = c[ETP_C_TOTAL]; my_level = level;
+                if (hi < wb.hi || (hi == wb.hi && lo < wb.lo)) {
+                    wb.hi = hi; wb.lo = lo; wb.cost = c[ETP_C_TOTAL]; wb.level = level;
                 }
-                my_scored += 1;
+                wb.scored += 1;
             }
-            if (o_cost) {
+            if (o_cost && lane < ETP_NUM_COST) {
+                double v = 0.0;
 #pragma unroll
-                for (int k = 0; k < ETP_NUM_COST; ++k) o_cost[(size_t)k * Cs + g] = (R)c[k];
+                for (int k = 0; k < ETP_NUM_COST; ++k) v = (lane == k) ? c[k] : v;
+                o_cost[(size_t)lane * Cs + cl] = (R)v;
             }
-            if (out.level) out.level[g] = (uint8_t)level;
-            if (out.reason) out.reason[g] = (uint8_t)reason;
+            if (lane == 0) {
+                if (out.level) out.level[cl] = (uint8_t)level;
+                if (out.reason) out.reason[cl] = (uint8_t)reason;
+            }
+            __syncwarp();
         }
-        __syncthreads();
     }
 
     // ---- block arg-min, then grid arg-min by the last block to finish ---------------------------
     {
-        // lexicographic min over (hi, lo) with shuffles
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ohi = __shfl_xor_sync(kFull, my_hi, o), olo = __shfl_xor_sync(kFull, my_lo, o);
-            const double oc = __shfl_xor_sync(kFull, my_cost, o);
-            const int ol = __shfl_xor_sync(kFull, my_level, o);
-            my_scored += __shfl_xor_sync(kFull, my_scored, o);
-            if (ohi < my_hi || (ohi == my_hi && olo < my_lo)) { my_hi = ohi; my_lo = olo; my_cost = oc; my_level = ol; }
-        }
         __shared__ BestRec wbest[kWarps];
         __shared__ bool is_last;
         if (lane == 0) {
-            wbest[warp].key_hi = my_hi; wbest[warp].key_lo = my_lo; wbest[warp].cost = my_cost;
-            wbest[warp].level = my_level; wbest[warp].n_scored = my_scored;
+            wbest[warp].key_hi = wb.hi; wbest[warp].key_lo = wb.lo; wbest[warp].cost = wb.cost;
+            wbest[warp].level = wb.level; wbest[warp].n_scored = wb.scored;
         }
         __syncthreads();
         if (tid == 0) {
             BestRec b = wbest[0];
             for (int w = 1; w < kWarps; ++w) {
-                b.n_scored += wbest[w].n_scored;
-                if (wbest[w].key_hi < b.key_hi || (wbest[w].key_hi == b.key_hi && wbest[w].key_lo < b.key_lo)) {
-                    const int n = b.n_scored;
-                    b = wbest[w];
-                    b.n_scored = n;
-                }
+                const int n = b.n_scored + wbest[w].n_scored;
+                if (wbest[w].key_hi < b.key_hi || (wbest[w].key_hi == b.key_hi && wbest[w].key_lo < b.key_lo)) b = wbest[w];
+                b.n_scored = n;
             }
             b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
             b.list_index = -1;
@@ -810,12 +859,9 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
             if (tid == 0) {
                 BestRec b = wbest[0];
                 for (int w = 1; w < kWarps; ++w) {
-                    b.n_scored += wbest[w].n_scored;
-                    if (wbest[w].key_hi < b.key_hi || (wbest[w].key_hi == b.key_hi && wbest[w].key_lo < b.key_lo)) {
-                        const int n = b.n_scored;
-                        b = wbest[w];
-                        b.n_scored = n;
-                    }
+                    const int n = b.n_scored + wbest[w].n_scored;
+                    if (wbest[w].key_hi < b.key_hi || (wbest[w].key_hi == b.key_hi && wbest[w].key_lo < b.key_lo)) b = wbest[w];
+                    b.n_scored = n;
                 }
                 b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
                 b.list_index = -1;
@@ -829,7 +875,8 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                     b.list_index = li;
                 }
                 *best_out = b;
-                counters[0] = 0;  // re-arm for the next launch
+                counters[0] = 0;  // re-arm both counters for the next launch
+                counters[1] = 0;
             }
         }
     }
@@ -868,8 +915,6 @@ __global__ void trajectory_kernel(DevStep st, int c_dense, double* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from etp_abi.cpp)
 // ---------------------------------------------------------------------------------------------
-int pick_nd(int O) { return O > 16 ? 8 : 16; }
-
 cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_len, const double* pos, const double* cov,
                                   const double* yaw, const double* vel, const double* length, const double* mass,
                                   const int* prot, const int* resp, double veh_m, void* tile, double* oconst,
@@ -900,22 +945,22 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
                                   unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                                   cudaStream_t stream) {
     const int O = st.has_pred ? st.O : 0;
-    const int ND = pick_nd(O);
-    const int tiles_per_profile = (st.nd + ND - 1) / ND;
-    const int n_tiles = (st.p_end - st.p_begin) * tiles_per_profile;
-    const size_t smem = tile_smem_bytes<R>(ND, st.Tmax, O);
+    const size_t smem = kWarps * warp_smem_bytes<R>(st.Tmax, O);
     cudaError_t e = cudaFuncSetAttribute(score_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R>, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    int grid = num_sms * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
+    // persistent grid: every SM fully occupied, never more CTAs than there are work chunks
+    const long long chunks = ((long long)(st.c_end - st.c_begin) + kChunk - 1) / kChunk;
+    long long grid = (long long)num_sms * per_sm;
+    const long long need = (chunks + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid < 1) grid = 1;
-    *grid_out = grid;
-    score_kernel<R><<<grid, kThreads, smem, stream>>>(st, pr, out, ND, tiles_per_profile, block_best, counters, best_out, nskip);
+    *grid_out = (int)grid;
+    score_kernel<R><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
     return cudaGetLastError();
 }
 

@@ -9,8 +9,6 @@ namespace etp {
 
 constexpr int kMaxGrid = 4096;  // upper bound of persistent CTAs (148 SMs x resident CTAs per SM)
 
-int pick_nd(int O);
-
 cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_len, const double* pos, const double* cov,
                                   const double* yaw, const double* vel, const double* length, const double* mass,
                                   const int* prot, const int* resp, double veh_m, void* tile, double* oconst,

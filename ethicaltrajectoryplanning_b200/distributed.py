@@ -1,0 +1,107 @@
+"""Multi-GPU partitioning of the scoring path (one process per GPU, torch.distributed).
+
+Two shardings, as the path offers them:
+
+* candidate sharding inside one planning step: the dense (v,t,d) index space is split into
+  contiguous ranges of whole (v,t) profiles; every rank scores its range with the fused kernel
+  and the shard-local arg-min records (40 bytes, level|cost|index key) are exchanged with one
+  all-gather and reduced lexicographically -- the "min-reduce of (cost, index)".  The validity
+  level is part of the key, so the reference's "highest non-empty level" rule
+  (frenet_functions.py:562-564) holds globally;
+* scenario sharding for sweeps: scenario i goes to rank ``i % world`` (the reference's
+  ``Pool(10).imap_unordered`` over scenarios, planner/plannertools/evaluate.py:160-169), no
+  data-path collective.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+def profile_shard(n_profiles: int, nd: int, rank: int, world: int):
+    """Dense candidate range [c_begin, c_end) of ``rank``: contiguous, aligned to whole profiles."""
+    base, rem = divmod(n_profiles, world)
+    p0 = rank * base + min(rank, rem)
+    p1 = p0 + base + (1 if rank < rem else 0)
+    return p0 * nd, p1 * nd
+
+
+def scenario_shard(n_scenarios: int, rank: int, world: int):
+    """Round-robin scenario ids of ``rank``."""
+    return list(range(rank, n_scenarios, world))
+
+
+def combine_best_records(records):
+    """Lexicographic min over shard-local etp_best records given in rank (= dense) order."""
+    n = len(records)
+    arr = (_abi.Best * n)(*records)
+    out = _abi.Best()
+    lib = _abi.load_library()
+    rc = lib.etp_combine_best(arr, n, C.byref(out))
+    return rc, out
+
+
+def records_from_bytes(buf: np.ndarray, n: int):
+    size = C.sizeof(_abi.Best)
+    raw = np.ascontiguousarray(buf, dtype=np.uint8).tobytes()
+    return [_abi.Best.from_buffer_copy(raw[i * size:(i + 1) * size]) for i in range(n)]
+
+
+def python_combine(records):
+    """Pure-Python twin of etp_combine_best for hosts without the CUDA library (gloo tests)."""
+    win, scored, before = -1, 0, 0
+    for i, b in enumerate(records):
+        if b["index"] >= 0 and (win < 0 or (b["key_hi"], b["key_lo"]) < (records[win]["key_hi"], records[win]["key_lo"])):
+            win, before = i, scored
+        scored += b["n_scored"]
+    if win < 0:
+        return None
+    out = dict(records[win])
+    out["n_scored"] = scored
+    out["list_index"] = before + records[win]["list_index"]
+    return out
+
+
+class ShardedPlanner:
+    """Candidate-sharded planning step over the ranks of a process group."""
+
+    def __init__(self, ctx, group=None):
+        import torch.distributed as dist
+
+        self.ctx = ctx
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._gather = None
+
+    def shard_range(self, step):
+        n_prof = len(step.v_list) * len(step.t_list)
+        return profile_shard(n_prof, len(step.d_list), self.rank, self.world)
+
+    def launch(self, s, bufs=None):
+        """Local fused launch + all-gather of the 40-byte best records (asynchronous)."""
+        torch = self.ctx.torch
+        self.ctx.launch(s, bufs)
+        local = self.ctx.best_device_tensor()
+        if self._gather is None:
+            self._gather = torch.empty((self.world * local.numel(),), dtype=torch.uint8, device=local.device)
+        with torch.cuda.stream(self.ctx.stream):  # ordered after the fused kernel on the context's stream
+            self.dist.all_gather_into_tensor(self._gather, local, group=self.group)
+        return self._gather
+
+    def best(self):
+        """Synchronise and reduce the gathered records -> global selection (same on every rank)."""
+        with self.ctx.torch.cuda.stream(self.ctx.stream):
+            host = self._gather.cpu()
+        recs = records_from_bytes(host.numpy(), self.world)
+        rc, out = combine_best_records(recs)
+        if rc == _abi.ERR_NO_CANDIDATE:
+            from .scoring import NoCandidateError
+
+            raise NoCandidateError("every candidate of every shard was skipped")
+        return dict(index=out.index, level=out.level, cost=out.cost, n_scored=out.n_scored,
+                    list_index=out.list_index, key_hi=out.key_hi, key_lo=out.key_lo)

@@ -175,6 +175,7 @@ class ScoreResult:
 
     def numpy(self):
         out = {}
+        self._ctx.stream.synchronize()
         for k in ("traj", "prob", "red", "cost", "level", "reason"):
             v = getattr(self, k)
             out[k] = None if v is None else v.detach().cpu().numpy()
@@ -214,7 +215,9 @@ class ScoringContext:
         if rc != 0:
             raise EtpError(rc, "etp_create failed")
         self.h = h
-        self._check(self.lib.etp_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        # a dedicated (non-default) stream: every launch, copy and event of this context is ordered on it
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._check(self.lib.etp_set_stream(self.h, C.c_void_p(self.stream.cuda_stream)))
         self.obstacle_ids = []
         self.O = 0
         self.has_pred = False
@@ -310,14 +313,19 @@ class ScoringContext:
     def allocate_outputs(self, Cs, Tmax, O, traj=True, prob=True, red=True, cost=True):
         torch = self.torch
         kw = dict(device=self.device, dtype=self.dtype)
-        return dict(
+        bufs = dict(
             traj=torch.empty((_abi.NUM_FIELDS, Cs, Tmax), **kw) if traj else None,
-            prob=torch.empty((Cs, O, Tmax - 1), **kw) if prob else None,
+            prob=torch.empty((Cs, Tmax - 1, O), **kw) if prob else None,  # obstacle fastest
             red=torch.empty((_abi.NUM_RED, Cs, O), **kw) if red else None,
             cost=torch.empty((_abi.NUM_COST, Cs), **kw) if cost else None,
             level=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
             reason=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
         )
+        for t in bufs.values():
+            if t is not None:
+                t.record_stream(self.stream)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        return bufs
 
     def launch(self, s, bufs=None):
         """Asynchronous etp_plan_step; ``bufs`` is a dict from allocate_outputs or None (argmin only)."""
@@ -344,6 +352,26 @@ class ScoringContext:
         if rc not in (_abi.OK, _abi.ERR_NO_CANDIDATE):
             self._check(rc)
         return b
+
+    def enable_timing(self, enable=True):
+        self._check(self.lib.etp_enable_timing(self.h, int(enable)))
+
+    def timing(self):
+        """(profile stage ms, fused scoring kernel ms) of the last step, from CUDA events."""
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(self.lib.etp_get_timing(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def best_device_tensor(self):
+        """uint8 view (torch) of the device-resident etp_best record, for collectives."""
+        p = C.c_void_p()
+        self._check(self.lib.etp_best_device_ptr(self.h, C.byref(p)))
+        n = C.sizeof(_abi.Best)
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p.value, False), "version": 2}
+
+        return self.torch.as_tensor(_Raw(), device=self.device)
 
     def trajectory(self, index):
         f = np.zeros((_abi.NUM_FIELDS, self._last_tmax), dtype=np.float64)

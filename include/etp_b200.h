@@ -152,7 +152,7 @@ typedef struct {
 typedef struct {
     int32_t precision;   /* ETP_PRECISION_*; element type of traj/prob/red/cost */
     void* traj;          /* [ETP_NUM_FIELDS][Cs][Tmax]   (entries past a candidate's T are 0) */
-    void* prob;          /* [Cs][O][Tmax-1]              collision probability per timestep */
+    void* prob;          /* [Cs][Tmax-1][O]              collision probability per timestep (obstacle fastest) */
     void* red;           /* [ETP_NUM_RED][Cs][O] */
     void* cost;          /* [ETP_NUM_COST][Cs] */
     uint8_t* level;      /* [Cs] validity level or ETP_LEVEL_SKIPPED */
@@ -176,7 +176,8 @@ int etp_destroy(etp_ctx* ctx);
 const char* etp_last_error(const etp_ctx* ctx);
 const char* etp_version(void);
 
-/* Use an existing CUDA stream (cudaStream_t as void*); NULL restores the context's own stream. */
+/* Use an existing CUDA stream (cudaStream_t as void*; NULL is CUDA's legacy default stream);
+ * (void*)-1 restores the context's own non-blocking stream. */
 int etp_set_stream(etp_ctx* ctx, void* cuda_stream);
 
 /* replaces params_dict / vehicle_params arguments of sort_frenet_trajectories (frenet_functions.py:477-495) */
@@ -202,6 +203,14 @@ int etp_get_best(etp_ctx* ctx, etp_best* best);
 /* synchronises; the 13 fp64 field rows [ETP_NUM_FIELDS][Tmax] of dense candidate `index` of the last
  * step (recomputed in fp64) -> `self._trajectory` (frenet_planner.py:564-576). n_samples receives T. */
 int etp_get_trajectory(etp_ctx* ctx, int index, double* fields, int* n_samples);
+
+/* Device address of the etp_best record the last etp_plan_step wrote (for collectives on it). */
+int etp_best_device_ptr(etp_ctx* ctx, void** ptr);
+
+/* Optional CUDA-event timing of the kernels inside etp_plan_step (off by default).
+ * etp_get_timing synchronises on the recorded events and returns milliseconds of the last step. */
+int etp_enable_timing(etp_ctx* ctx, int enable);
+int etp_get_timing(etp_ctx* ctx, float* profile_ms, float* score_ms);
 
 /* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks) */
 int etp_combine_best(const etp_best* bests, int n, etp_best* out);

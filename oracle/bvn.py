@@ -170,3 +170,20 @@ def mvnun(lower, upper, mean, cov):
     yl = (lower[1] - mean[1]) / s1
     yu = (upper[1] - mean[1]) / s1
     return float(rect_prob_std(xl, xu, yl, yu, r)), 0
+
+
+def mvnun_fast(lower, upper, mean, cov):
+    """Same contract as :func:`mvnun`, using scipy's compiled port of BVU when it is importable
+    (scalar calls are then as cheap as the reference's Fortran routine); used for CPU baselines."""
+    try:
+        from scipy.special._ufuncs import _bivariate_normal_cdf as _bvu_c
+    except Exception:  # pragma: no cover - scipy layout changed
+        return mvnun(lower, upper, mean, cov)
+    s0 = math.sqrt(cov[0][0])
+    s1 = math.sqrt(cov[1][1])
+    r = cov[1][0] / s1 / s0
+    xl = (lower[0] - mean[0]) / s0
+    xu = (upper[0] - mean[0]) / s0
+    yl = (lower[1] - mean[1]) / s1
+    yu = (upper[1] - mean[1]) / s1
+    return float(_bvu_c(xl, yl, r) - _bvu_c(xu, yl, r) - _bvu_c(xl, yu, r) + _bvu_c(xu, yu, r)), 0

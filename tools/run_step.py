@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Run a few planning steps of a synthetic workload (used under ncu / compute-sanitizer)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--nv", type=int, default=None)
+    ap.add_argument("--nd", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--argmin-only", action="store_true")
+    ap.add_argument("--lateral-spread", type=float, default=4.0)
+    args = ap.parse_args()
+    import torch
+
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from ethicaltrajectoryplanning_b200.synthetic import make_step
+
+    step = make_step(args.workload, nv=args.nv, nd=args.nd, lateral_spread=args.lateral_spread)
+    ctx = ScoringContext(0, args.precision)
+    ctx.configure(step)
+    s, keep, nsamp = ctx.make_step_struct(step)
+    bufs = None if args.argmin_only else ctx.allocate_outputs(step.n_dense, int(nsamp.max()), ctx.O)
+    ctx.enable_timing(True)
+    for i in range(args.steps):
+        ctx.launch(s, bufs)
+        print("step", i, "profile_ms %.4f score_ms %.4f" % ctx.timing(), ctx.best())
+    if bufs is not None:
+        print("nonzero prob fraction", float((bufs["prob"] != 0).float().mean()))
+    torch.cuda.synchronize()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
