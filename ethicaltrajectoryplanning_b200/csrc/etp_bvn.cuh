@@ -92,11 +92,36 @@ __device__ __forceinline__ double rect_prob(double xl, double xu, double yl, dou
 // Phi(b) - Phi(a), a <= b.  The interval is reflected so that a + b >= 0: then either 0 <= a (both
 // erfc values are tails, no cancellation) or a < 0 < b with |a| <= b (difference of O(1) numbers whose
 // result is at least Phi(b) - 1/2).  Branch free.
+// Branch-free complementary error function: erfc(z) = t exp(-z^2 + P(t)), t = 1 / (1 + z/2), z >= 0
+// (Chebyshev fit of Numerical Recipes' erfcc, fractional error 1.2e-7 in exact arithmetic; measured
+// <= 2.2e-6 in fp32 for |x| <= 6.5 with the z^2 rounding residual folded back in).  libdevice's erfcf
+// branches on the magnitude of its argument, which serialises a warp whose lanes hold different
+// rectangles.
+__device__ __forceinline__ float erfc_f(float x) {
+    const float z = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.5f, z, 1.0f));
+    float p = 0.17087277f;
+    p = fmaf(p, t, -0.82215223f);
+    p = fmaf(p, t, 1.48851587f);
+    p = fmaf(p, t, -1.13520398f);
+    p = fmaf(p, t, 0.27886807f);
+    p = fmaf(p, t, -0.18628806f);
+    p = fmaf(p, t, 0.09678418f);
+    p = fmaf(p, t, 0.37409196f);
+    p = fmaf(p, t, 1.00002368f);
+    p = fmaf(p, t, -1.26551223f);
+    const float zz = z * z;
+    const float e = fmaf(z, z, -zz);  // exact rounding residual of z*z
+    float r = t * __expf(p - zz);
+    r = fmaf(-r, e, r);
+    return x >= 0.0f ? r : 2.0f - r;
+}
+
 __device__ __forceinline__ float dphi_f(float a, float b) {
     const float is2 = 0.70710678118654752440f;
     const bool neg = (a + b) < 0.0f;
     const float lo = neg ? -b : a, hi = neg ? -a : b;
-    return 0.5f * (erfcf(lo * is2) - erfcf(hi * is2));
+    return 0.5f * (erfc_f(lo * is2) - erfc_f(hi * is2));
 }
 
 // Gauss-Legendre nodes on theta in [0, asin r]: s_i = sin(theta_i), q_i = log2(e) / (1 - s_i^2),

@@ -317,22 +317,40 @@ template <typename R> struct Obs {
     __device__ __forceinline__ R get(int f, int o, int t) const { return __ldg(base + f * plane + (size_t)t * O + o); }
 };
 
+// Constants of the risk model in the arithmetic type R, resident in shared memory (one copy per CTA):
+// dynamic indexing into kernel parameters would force a per-thread local-memory copy of DevParams.
+template <typename R> struct Tab {
+    R thr[ETP_MAX_ANGLE_BINS], fcos[ETP_MAX_ANGLE_BINS], coef_pos[ETP_MAX_ANGLE_BINS + 1], coef_neg[ETP_MAX_ANGLE_BINS + 1];
+    R lr_speed, lr1s_speed, ped_speed, lr_const, lr1s_const, neg_ped_const;
+    R hx, hy, rr;  // ego box half extents (l/6, w/2) and centre offset (l/2)(2/3)  (collision_probability.py:157,349-362)
+    int n_thr;
+};
+
+template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const DevParams& pr) {
+    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) { tb.thr[i] = (R)pr.thr[i]; tb.fcos[i] = (R)pr.fcos[i]; }
+    for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { tb.coef_pos[i] = (R)pr.coef_pos[i]; tb.coef_neg[i] = (R)pr.coef_neg[i]; }
+    tb.lr_speed = (R)pr.lr_speed; tb.lr1s_speed = (R)pr.lr1s_speed; tb.ped_speed = (R)pr.ped_speed;
+    tb.lr_const = (R)pr.lr_const; tb.lr1s_const = (R)pr.lr1s_const; tb.neg_ped_const = (R)(-pr.ped_const);
+    tb.hx = (R)(pr.veh_l / 6); tb.hy = (R)(pr.veh_w / 2); tb.rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
+    tb.n_thr = pr.n_thr;
+}
+
 // impact-area coefficient (logistic_regression_*.py): thresholds on |angle|, sign picks the side
-template <typename R> __device__ __forceinline__ R angle_coef(const DevParams& pr, R angle) {
+template <typename R> __device__ __forceinline__ R angle_coef(const Tab<R>& pr, R angle) {
     const R a = abs_(angle);
     int i = 0;
-    while (i < pr.n_thr && !(a < (R)pr.thr[i])) ++i;
-    return (R)(angle < (R)0 ? pr.coef_neg[i] : pr.coef_pos[i]);
+    while (i < pr.n_thr && !(a < pr.thr[i])) ++i;
+    return angle < (R)0 ? pr.coef_neg[i] : pr.coef_pos[i];
 }
 
 // harm "logit arguments" of ego and obstacle at trajectory index t against obstacle sample t
 // (harm_estimation.py:313-332); harm = 1 / (1 + exp(-(const + arg))).
 // Band of an impact angle given as a direction: P = |d| cos(angle), d2 = |d|^2.  |angle| < thr is
 // cos(angle) > cos(thr), compared through the sign-preserving squares P|P| > d2 * cos(thr)|cos(thr)|.
-__device__ __forceinline__ int direction_band(const DevParams& pr, float P, float d2) {
+__device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, float d2) {
     const float fp = P * fabsf(P);
     int i = 0;
-    while (i < pr.n_thr && !(fp > d2 * (float)pr.fcos[i])) ++i;
+    while (i < pr.n_thr && !(fp > d2 * pr.fcos[i])) ++i;
     return i;
 }
 
@@ -342,7 +360,7 @@ __device__ __forceinline__ int direction_band(const DevParams& pr, float P, floa
 // obstacle frame (P, Q) and the number of 2 pi wraps of the un-wrapped difference is recovered from
 // the half planes of the two directions.  |angle| > pi always lands in the last ("rear") band.
 template <typename R>
-__device__ __forceinline__ void harm_args(const DevParams& pr, bool prot, R ke, R ko, R ex, R ey, R ec, R es, R ev, R ewrap,
+__device__ __forceinline__ void harm_args(const Tab<R>& pr, bool prot, R ke, R ko, R ex, R ey, R ec, R es, R ev, R ewrap,
                                           R mx, R my, R owrap, R ovo, R ocp, R osp, R& arg_e, R& arg_o) {
     // delta_v = sqrt(v_e^2 + v_o^2 + 2 v_e v_o cos(pdof)), pdof = psi_o - psi_e + pi
     const R cpd = -(ocp * ec + osp * es);
@@ -358,7 +376,7 @@ __device__ __forceinline__ void harm_args(const DevParams& pr, bool prot, R ke, 
         if (dy >= 0 && es < 0 && q < 0) n0 = 1;
         if (dy < 0 && es >= 0 && q > 0) n0 = -1;
         const int be = ((R)n0 != ewrap) ? last : direction_band(pr, p, d2);
-        const R ce = (R)(q < 0 ? pr.coef_neg[be] : pr.coef_pos[be]);
+        const R ce = q < 0 ? pr.coef_neg[be] : pr.coef_pos[be];
         // obstacle: angle = pi + rel - psi_o
         const R po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
         n0 = 0;
@@ -368,17 +386,17 @@ __device__ __forceinline__ void harm_args(const DevParams& pr, bool prot, R ke, 
         const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
         const bool neg_side = (k == (R)-1) && (qo >= 0);
         const int bo = (pos_side || neg_side) ? direction_band(pr, -po, d2) : last;
-        const R co = (R)(neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo]);
-        arg_e = (R)pr.lr_speed * dve + ce;
-        arg_o = (R)pr.lr_speed * dvo + co;
+        const R co = neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo];
+        arg_e = pr.lr_speed * dve + ce;
+        arg_o = pr.lr_speed * dvo + co;
     } else {
-        arg_e = (R)pr.lr1s_speed * dve;
-        arg_o = (R)pr.ped_speed * dvo;
+        arg_e = pr.lr1s_speed * dve;
+        arg_o = pr.ped_speed * dvo;
     }
 }
 // fp64 check mode evaluates pdof with the reference's own expression
 template <>
-__device__ __forceinline__ void harm_args<double>(const DevParams& pr, bool prot, double ke, double ko, double ex, double ey,
+__device__ __forceinline__ void harm_args<double>(const Tab<double>& pr, bool prot, double ke, double ko, double ex, double ey,
                                                   double ec, double es, double ev, double eyaw, double mx, double my,
                                                   double opsi, double ovo, double ocp, double osp, double& arg_e,
                                                   double& arg_o) {
@@ -419,10 +437,9 @@ template <int N> struct RectNodesF {
 };
 
 template <typename R, typename Rect>
-__device__ __forceinline__ R nine_rectangles(const DevParams& pr, const Rect& rect, R x, R y, R c, R s, R mx, R my, R ex, R ey,
+__device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect, R x, R y, R c, R s, R mx, R my, R ex, R ey,
                                              R isx, R isy, R rho) {
-    const R hx = (R)(pr.veh_l / 6), hy = (R)(pr.veh_w / 2);
-    const R rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
+    const R hx = pr.hx, hy = pr.hy, rr = pr.rr;
     R prob = 0;
 #pragma unroll 1
     for (int km = 0; km < 3; ++km) {
@@ -440,12 +457,12 @@ __device__ __forceinline__ R nine_rectangles(const DevParams& pr, const Rect& re
     return prob / 3;
 }
 
-__device__ __forceinline__ double collision_prob(const DevParams& pr, double x, double y, double c, double s, double mx,
+__device__ __forceinline__ double collision_prob(const Tab<double>& pr, double x, double y, double c, double s, double mx,
                                                  double my, double ex, double ey, double isx, double isy, double rho) {
     return nine_rectangles<double>(pr, RectDouble{}, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
 }
 
-__device__ float collision_prob(const DevParams& pr, float x, float y, float c, float s, float mx, float my, float ex,
+__device__ float collision_prob(const Tab<float>& pr, float x, float y, float c, float s, float mx, float my, float ex,
                                 float ey, float isx, float isy, float rho) {
     const float ar = fabsf(rho);
     if (rho == 0.0f) {
@@ -472,6 +489,51 @@ template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R m
     return (R)1e-4 / sqrt_(m2);
 }
 
+// One deferred (un-gated) evaluation: collision probability of ego sample t+1 against prediction
+// sample t, harm of sample t, risk = harm * probability folded into the per-obstacle maxima.
+// Kept out of line so that its register demand does not leak into the gated streaming loop.
+template <typename R> struct EntryCtx {
+    const Tab<R>* tab;
+    const R* ego;
+    Obs<R> ob;
+    typename Enc<R>::U* rmax;
+    const double* obs_const;
+    R* o_prob;
+    int Ts, O, On, mahalanobis;
+    size_t prob_base;
+};
+
+template <typename R> __device__ __noinline__ void run_entry_fn(const EntryCtx<R>& c, unsigned entry) {
+    constexpr int kEgoAng = sizeof(R) == 4 ? EG_WRAP : EG_YAW;
+    constexpr int kObsAng = sizeof(R) == 4 ? OF_WRAP : OF_PSI;
+    const Tab<R>& tab = *c.tab;
+    const R* ego = c.ego;
+    const Obs<R>& ob = c.ob;
+    const int Ts = c.Ts;
+    const int o = entry >> 8, t = entry & 255;
+    const int e1 = t + 1, e0 = t;
+    R prob;
+    if (c.mahalanobis) {
+        prob = inv_mahalanobis<R>(ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
+                                  ob.get(OF_I00, o, t), ob.get(OF_I01, o, t), ob.get(OF_I11, o, t));
+    } else {
+        prob = collision_prob(tab, ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ego[EG_C * Ts + e1], ego[EG_S * Ts + e1],
+                              ob.get(OF_MX, o, t), ob.get(OF_MY, o, t), ob.get(OF_EX, o, t), ob.get(OF_EY, o, t),
+                              ob.get(OF_ISX, o, t), ob.get(OF_ISY, o, t), ob.get(OF_RHO, o, t));
+    }
+    const double* oc = c.obs_const + o * OC_COUNT;
+    const bool prot = oc[OC_PROT] != 0.0;
+    R ae, ao;
+    harm_args<R>(tab, prot, (R)oc[OC_KE], (R)oc[OC_KO], ego[EG_X * Ts + e0], ego[EG_Y * Ts + e0], ego[EG_C * Ts + e0],
+                 ego[EG_S * Ts + e0], ego[EG_V * Ts + e0], ego[kEgoAng * Ts + e0], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
+                 ob.get(kObsAng, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t), ob.get(OF_SPSI, o, t), ae, ao);
+    const R he = sigmoid_harm<R>(prot ? tab.lr_const : tab.lr1s_const, ae);
+    const R ho = sigmoid_harm<R>(prot ? tab.lr_const : tab.neg_ped_const, ao);
+    atomicMax(&c.rmax[o], Enc<R>::enc(he * prob));  // risk_costs.py:88-95
+    atomicMax(&c.rmax[c.On + o], Enc<R>::enc(ho * prob));
+    if (c.o_prob) c.o_prob[c.prob_base + (size_t)t * c.O + o] = prob;
+}
+
 struct WarpBest {
     unsigned long long hi, lo;
     double cost;
@@ -479,7 +541,7 @@ struct WarpBest {
 };
 
 template <typename R>
-__global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams pr, DevOut out, BestRec* __restrict__ block_best,
+__global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParams pr, DevOut out, BestRec* __restrict__ block_best,
                                                          unsigned int* __restrict__ counters, BestRec* __restrict__ best_out,
                                                          const int* __restrict__ prof_nskip) {
     using U = typename Enc<R>::U;
@@ -496,6 +558,11 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
     R* o_red = reinterpret_cast<R*>(out.red);
     R* o_cost = reinterpret_cast<R*>(out.cost);
     R* ego = sm.ego;
+
+    const bool mahal = pr.mahalanobis != 0;
+    __shared__ Tab<R> tab;
+    if (tid == 0) fill_tab<R>(tab, pr);
+    __syncthreads();
 
     WarpBest wb{~0ull, ~0ull, 0.0, -1, 0};
 
@@ -572,33 +639,9 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                 constexpr int kObsAng = sizeof(R) == 4 ? OF_WRAP : OF_PSI;
                 unsigned* q = sm.queue;
                 int q_n = 0;
-                auto run_entry = [&](unsigned entry) {
-                    const int o = entry >> 8, t = entry & 255;
-                    const int e1 = t + 1, e0 = t;
-                    R prob;
-                    if (pr.mahalanobis) {
-                        prob = inv_mahalanobis<R>(ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ob.get(OF_MX, o, t),
-                                                  ob.get(OF_MY, o, t), ob.get(OF_I00, o, t), ob.get(OF_I01, o, t),
-                                                  ob.get(OF_I11, o, t));
-                    } else {
-                        prob = collision_prob(pr, ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ego[EG_C * Ts + e1],
-                                              ego[EG_S * Ts + e1], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
-                                              ob.get(OF_EX, o, t), ob.get(OF_EY, o, t), ob.get(OF_ISX, o, t),
-                                              ob.get(OF_ISY, o, t), ob.get(OF_RHO, o, t));
-                    }
-                    const double* oc = st.obs_const + o * OC_COUNT;
-                    const bool prot = oc[OC_PROT] != 0.0;
-                    R ae, ao;
-                    harm_args<R>(pr, prot, (R)oc[OC_KE], (R)oc[OC_KO], ego[EG_X * Ts + e0], ego[EG_Y * Ts + e0],
-                                 ego[EG_C * Ts + e0], ego[EG_S * Ts + e0], ego[EG_V * Ts + e0], ego[kEgoAng * Ts + e0],
-                                 ob.get(OF_MX, o, t), ob.get(OF_MY, o, t), ob.get(kObsAng, o, t), ob.get(OF_VO, o, t),
-                                 ob.get(OF_CPSI, o, t), ob.get(OF_SPSI, o, t), ae, ao);
-                    const R he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), ae);
-                    const R ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), ao);
-                    atomicMax(&sm.rmax[o], Enc<R>::enc(he * prob));  // risk_costs.py:88-95
-                    atomicMax(&sm.rmax[On + o], Enc<R>::enc(ho * prob));
-                    if (o_prob) o_prob[((size_t)cl * (Ts - 1) + t) * O + o] = prob;
-                };
+                EntryCtx<R> ectx{&tab, ego, ob, sm.rmax, st.obs_const, o_prob, Ts, O, On, pr.mahalanobis,
+                                 (size_t)cl * (Ts - 1) * O};
+                auto run_entry = [&](unsigned entry) { run_entry_fn<R>(ectx, entry); };
                 for (int ob0 = 0; ob0 < O; ob0 += 32) {
                     const int rem = min(32, O - ob0);
                     int Op = 32;
@@ -629,7 +672,7 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                                 // harm sample t: ego[t] against prediction[t] (harm_estimation.py:234, 313-332)
                                 const R mx = ob.get(OF_MX, o, t), my = ob.get(OF_MY, o, t);
                                 R ae, ao;
-                                harm_args<R>(pr, prot, ke, ko, ego[EG_X * Ts + t], ego[EG_Y * Ts + t], ego[EG_C * Ts + t],
+                                harm_args<R>(tab, prot, ke, ko, ego[EG_X * Ts + t], ego[EG_Y * Ts + t], ego[EG_C * Ts + t],
                                              ego[EG_S * Ts + t], ego[EG_V * Ts + t], ego[kEgoAng * Ts + t], mx, my,
                                              ob.get(kObsAng, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t),
                                              ob.get(OF_SPSI, o, t), ae, ao);
@@ -638,7 +681,7 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                                 if (t + 1 < n_pred) {
                                     // probability sample t: ego[t+1] against mean[t], orientation[t+1]
                                     // (collision_probability.py:168-203)
-                                    if (pr.mahalanobis) {
+                                    if (mahal) {
                                         gated = false;
                                     } else {
                                         const R x = ego[EG_X * Ts + t + 1], y = ego[EG_Y * Ts + t + 1];
@@ -718,8 +761,8 @@ __global__ void __launch_bounds__(kThreads) score_kernel(DevStep st, DevParams p
                     const bool prot = oc[OC_PROT] != 0.0;
                     re = Enc<R>::dec(sm.rmax[o]);
                     ro = Enc<R>::dec(sm.rmax[On + o]);
-                    he = sigmoid_harm<R>((R)(prot ? pr.lr_const : pr.lr1s_const), sm.hmax[o]);
-                    ho = sigmoid_harm<R>((R)(prot ? pr.lr_const : -pr.ped_const), sm.hmax[On + o]);
+                    he = sigmoid_harm<R>(prot ? tab.lr_const : tab.lr1s_const, sm.hmax[o]);
+                    ho = sigmoid_harm<R>(prot ? tab.lr_const : tab.neg_ped_const, sm.hmax[On + o]);
                     sum_e += (double)re;
                     sum_o += (double)ro;
                     sum_abs += fabs((double)re - (double)ro);
