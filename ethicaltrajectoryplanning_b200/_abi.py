@@ -114,6 +114,7 @@ SYMBOLS = {
     "etp_best_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "etp_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "etp_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "etp_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "etp_combine_best": (C.c_int, [C.POINTER(Best), C.c_int, C.POINTER(Best)]),
 }
 

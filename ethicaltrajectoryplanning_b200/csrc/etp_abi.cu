@@ -281,7 +281,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_resp.reserve(sizeof(int) * O));
-        ETP_CUDA(c, c->o_tile.reserve(sizeof(double) * OF_COUNT * n));
+        ETP_CUDA(c, c->o_tile.reserve(sizeof(double) * (OF_COUNT + 8) * n));
         ETP_CUDA(c, c->o_const.reserve(sizeof(double) * OC_COUNT * O));
         if ((r = stage_to_device(c, c->o_pos.p, o->pos, sizeof(double) * 2 * n))) return r;
         if ((r = stage_to_device(c, c->o_cov.p, o->cov, sizeof(double) * 4 * n))) return r;
@@ -452,6 +452,16 @@ int etp_get_timing(etp_ctx* c, float* profile_ms, float* score_ms) {
     ETP_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
     if (profile_ms) *profile_ms = a;
     if (score_ms) *score_ms = b;
+    return ETP_OK;
+}
+
+int etp_debug_counters(etp_ctx* c, uint64_t* out, int n) {
+    if (!c || !out || n < 1) return ETP_ERR_INVALID;
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long v[1] = {0};
+    ETP_CUDA(c, read_debug_counters(v, 1));
+    out[0] = v[0];
     return ETP_OK;
 }
 

@@ -51,7 +51,23 @@ template <> struct Enc<double> {
     }
 };
 
+template <typename R> struct alignas(16) Vec4 { R x, y, z, w; };
+template <typename R> struct alignas(2 * sizeof(R)) Vec2 { R x, y; };
+// read-only 16-byte loads of the obstacle vector planes
+template <typename R> __device__ __forceinline__ Vec4<R> ldg4(const Vec4<R>* p);
+template <> __device__ __forceinline__ Vec4<float> ldg4<float>(const Vec4<float>* p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return Vec4<float>{v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Vec4<double> ldg4<double>(const Vec4<double>* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return Vec4<double>{a.x, a.y, b.x, b.y};
+}
+
 template <typename R> __device__ __forceinline__ R rmax_(R a, R b) { return a > b ? a : b; }
+// square root of the fp32 streaming path: MUFU.RSQ based (2 ulp); the fp64 check mode stays IEEE
+__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+__device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
 __device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
@@ -93,7 +109,10 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
     const int o = i / Tp, t = i % Tp;
     const int n = pred_len[o];
     const size_t plane = (size_t)O * Tp;
-    R* out = tile + (size_t)t * O + o;  // [field][t][o]
+    // tile = [V0: (mx,my,ex,ey)][V1: (vo,cos psi,sin psi,angle)] as Vec4 planes [t][o], then the scalar planes [field][t][o]
+    Vec4<R>* v0 = reinterpret_cast<Vec4<R>*>(tile);
+    Vec4<R>* v1 = v0 + plane;
+    R* out = reinterpret_cast<R*>(v1 + plane) + (size_t)t * O + o;
     double v[OF_COUNT];
     for (int f = 0; f < OF_COUNT; ++f) v[f] = 0.0;
     if (t < n) {
@@ -129,6 +148,9 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
         v[OF_I11] = r00 / det;
     }
     for (int f = 0; f < OF_COUNT; ++f) out[f * plane] = (R)v[f];
+    const size_t vi = (size_t)t * O + o;
+    v0[vi] = Vec4<R>{(R)v[OF_MX], (R)v[OF_MY], (R)v[OF_EX], (R)v[OF_EY]};
+    v1[vi] = Vec4<R>{(R)v[OF_VO], (R)v[OF_CPSI], (R)v[OF_SPSI], (R)v[sizeof(R) == 4 ? OF_WRAP : OF_PSI]};
     if (t == 0) {
         const double mo = mass[o];
         oconst[o * OC_COUNT + OC_KE] = mo / (veh_m + mo);     // harm_estimation.py:327
@@ -282,39 +304,50 @@ constexpr int kChunk = 4;  // consecutive candidates per work grab (same profile
 
 template <typename R> __host__ __device__ inline size_t warp_smem_bytes(int Ts, int O) {
     const int On = O > 0 ? O : 1;
-    size_t b = sizeof(double) * 2 * Ts;                 // exact ego x, y
+    size_t b = sizeof(R) * 4 * Ts;                      // ego (x, y, cos yaw, sin yaw)
+    b += sizeof(double) * 2 * Ts;                       // exact ego x, y
     b += sizeof(double) * 2 * On;                       // risk maxima (ordered-int encoded), sized for fp64
-    b += sizeof(R) * EG_COUNT * Ts;                     // ego stash
+    b += sizeof(R) * 2 * Ts;                            // ego (v, yaw angle or its wrap count)
     b += sizeof(R) * 2 * On;                            // harm logit maxima
     b += sizeof(unsigned) * kQueue;                     // deferred evaluations
     return (b + 15) & ~size_t(15);
 }
 
 template <typename R> struct WarpSmem {
+    Vec4<R>* e0;               // [Ts] x, y, cos yaw, sin yaw
     double* xd;
     double* yd;
     typename Enc<R>::U* rmax;  // [2][On]
-    R* ego;                    // [EG_COUNT][Ts]
+    Vec2<R>* e1;               // [Ts] v, angle (fp32: wrap count of the yaw; fp64: the yaw)
     R* hmax;                   // [2][On]
     unsigned* queue;
     __device__ __forceinline__ WarpSmem(unsigned char* base, int Ts, int O) {
         const int On = O > 0 ? O : 1;
-        double* d = reinterpret_cast<double*>(base);
+        e0 = reinterpret_cast<Vec4<R>*>(base);
+        double* d = reinterpret_cast<double*>(e0 + Ts);
         xd = d; d += Ts;
         yd = d; d += Ts;
         rmax = reinterpret_cast<typename Enc<R>::U*>(d); d += 2 * On;
-        ego = reinterpret_cast<R*>(d);
-        hmax = ego + EG_COUNT * Ts;
+        e1 = reinterpret_cast<Vec2<R>*>(d);
+        hmax = reinterpret_cast<R*>(e1 + Ts);
         queue = reinterpret_cast<unsigned*>(hmax + 2 * On);
     }
 };
 
 template <typename R> struct Obs {
-    const R* base;
-    size_t plane;
-    int Tp;
+    const Vec4<R>* v0;  // (mx, my, ex, ey)            [t][o]
+    const Vec4<R>* v1;  // (vo, cos psi, sin psi, angle) [t][o]
+    const R* base;      // scalar planes [field][t][o]
+    int plane;
     int O;
-    __device__ __forceinline__ R get(int f, int o, int t) const { return __ldg(base + f * plane + (size_t)t * O + o); }
+    __device__ __forceinline__ Obs(const void* tile, int O_, int Tp_) {
+        plane = O_ * Tp_;
+        O = O_;
+        v0 = reinterpret_cast<const Vec4<R>*>(tile);
+        v1 = v0 + plane;
+        base = reinterpret_cast<const R*>(v1 + plane);
+    }
+    __device__ __forceinline__ R get(int f, int o, int t) const { return __ldg(base + (f * plane + t * O + o)); }
 };
 
 // Constants of the risk model in the arithmetic type R, resident in shared memory (one copy per CTA):
@@ -348,10 +381,11 @@ template <typename R> __device__ __forceinline__ R angle_coef(const Tab<R>& pr, 
 // Band of an impact angle given as a direction: P = |d| cos(angle), d2 = |d|^2.  |angle| < thr is
 // cos(angle) > cos(thr), compared through the sign-preserving squares P|P| > d2 * cos(thr)|cos(thr)|.
 __device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, float d2) {
+    // thresholds increase, so the tests pass from some band on: the band is the number of failed tests
     const float fp = P * fabsf(P);
-    int i = 0;
-    while (i < pr.n_thr && !(fp > d2 * pr.fcos[i])) ++i;
-    return i;
+    int band = 0;
+    for (int i = 0; i < pr.n_thr; ++i) band += (fp > d2 * pr.fcos[i]) ? 0 : 1;
+    return band;
 }
 
 // fp32 path.  `ewrap` / `owrap` are the whole turns that bring the ego / obstacle yaw into (-pi, pi].
@@ -364,7 +398,7 @@ __device__ __forceinline__ void harm_args(const Tab<R>& pr, bool prot, R ke, R k
                                           R mx, R my, R owrap, R ovo, R ocp, R osp, R& arg_e, R& arg_o) {
     // delta_v = sqrt(v_e^2 + v_o^2 + 2 v_e v_o cos(pdof)), pdof = psi_o - psi_e + pi
     const R cpd = -(ocp * ec + osp * es);
-    const R dv = sqrt_(ev * ev + ovo * ovo + 2 * ev * ovo * cpd);
+    const R dv = sqrt_fast(ev * ev + ovo * ovo + 2 * ev * ovo * cpd);
     const R dve = ke * dv, dvo = ko * dv;
     if (prot) {
         const R dx = mx - ex, dy = my - ey;
@@ -419,6 +453,9 @@ template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { 
 
 // collision probability of one (ego sample i = t+1, obstacle sample t) pair
 // (collision_probability.py:205-252, 329-364): 3 means x 3 axis-aligned ego boxes.
+// diagnostics: evaluations of the fp32 path that took the fp64 fallback (|rho| > 0.55 or NaN)
+__device__ unsigned long long g_fallback_evals = 0ull;
+
 struct RectDouble {
     __device__ __forceinline__ double operator()(double xl, double xu, double yl, double yu, double r) const {
         return rect_prob(xl, xu, yl, yu, r);
@@ -464,22 +501,29 @@ __device__ __forceinline__ double collision_prob(const Tab<double>& pr, double x
 
 __device__ float collision_prob(const Tab<float>& pr, float x, float y, float c, float s, float mx, float my, float ex,
                                 float ey, float isx, float isy, float rho) {
+    // Node count by |rho|: 0 (rho = 0), 4 (<= 0.35), 6 (<= 0.55), fp64 fallback beyond.  The lanes of a
+    // warp hold different (obstacle, timestep) pairs; to keep them on ONE code path every lane uses the
+    // largest node count any of them needs (more nodes are never less accurate; rho = 0 gives zero weights).
     const float ar = fabsf(rho);
-    if (rho == 0.0f) {
+    const int cls = !(ar <= 0.55f) ? 3 : (ar > 0.35f ? 2 : (rho != 0.0f ? 1 : 0));
+    const unsigned act = __activemask();
+    const int wcls = __reduce_max_sync(act, cls == 3 ? 0 : cls);
+    if (cls == 3) {
+        atomicAdd(&g_fallback_evals, 1ull);
+        return nine_rectangles<float>(pr, RectFallbackF{}, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
+    }
+    if (wcls == 0) {
         RectNodesF<0> r;
         return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
     }
-    if (ar <= 0.35f) {
+    if (wcls == 1) {
         RectNodesF<4> r;
         r.n = make_rho_nodes<4>(rho);
         return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
     }
-    if (ar <= 0.55f) {
-        RectNodesF<6> r;
-        r.n = make_rho_nodes<6>(rho);
-        return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
-    }
-    return nine_rectangles<float>(pr, RectFallbackF{}, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
+    RectNodesF<6> r;
+    r.n = make_rho_nodes<6>(rho);
+    return nine_rectangles<float>(pr, r, x, y, c, s, mx, my, ex, ey, isx, isy, rho);
 }
 
 // 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
@@ -494,44 +538,41 @@ template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R m
 // Kept out of line so that its register demand does not leak into the gated streaming loop.
 template <typename R> struct EntryCtx {
     const Tab<R>* tab;
-    const R* ego;
+    const Vec4<R>* e0;
+    const Vec2<R>* e1;
     Obs<R> ob;
     typename Enc<R>::U* rmax;
     const double* obs_const;
     R* o_prob;
-    int Ts, O, On, mahalanobis;
+    int On, mahalanobis;
     size_t prob_base;
 };
 
 template <typename R> __device__ __noinline__ void run_entry_fn(const EntryCtx<R>& c, unsigned entry) {
-    constexpr int kEgoAng = sizeof(R) == 4 ? EG_WRAP : EG_YAW;
-    constexpr int kObsAng = sizeof(R) == 4 ? OF_WRAP : OF_PSI;
     const Tab<R>& tab = *c.tab;
-    const R* ego = c.ego;
     const Obs<R>& ob = c.ob;
-    const int Ts = c.Ts;
     const int o = entry >> 8, t = entry & 255;
-    const int e1 = t + 1, e0 = t;
+    const int vi = t * ob.O + o;
+    const Vec4<R> g0 = ldg4<R>(ob.v0 + vi), g1 = ldg4<R>(ob.v1 + vi);
+    const Vec4<R> a1 = c.e0[t + 1], a0 = c.e0[t];
+    const Vec2<R> b0 = c.e1[t];
     R prob;
     if (c.mahalanobis) {
-        prob = inv_mahalanobis<R>(ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
-                                  ob.get(OF_I00, o, t), ob.get(OF_I01, o, t), ob.get(OF_I11, o, t));
+        prob = inv_mahalanobis<R>(a1.x, a1.y, g0.x, g0.y, ob.get(OF_I00, o, t), ob.get(OF_I01, o, t), ob.get(OF_I11, o, t));
     } else {
-        prob = collision_prob(tab, ego[EG_X * Ts + e1], ego[EG_Y * Ts + e1], ego[EG_C * Ts + e1], ego[EG_S * Ts + e1],
-                              ob.get(OF_MX, o, t), ob.get(OF_MY, o, t), ob.get(OF_EX, o, t), ob.get(OF_EY, o, t),
-                              ob.get(OF_ISX, o, t), ob.get(OF_ISY, o, t), ob.get(OF_RHO, o, t));
+        prob = collision_prob(tab, a1.x, a1.y, a1.z, a1.w, g0.x, g0.y, g0.z, g0.w, ob.get(OF_ISX, o, t), ob.get(OF_ISY, o, t),
+                              ob.get(OF_RHO, o, t));
     }
     const double* oc = c.obs_const + o * OC_COUNT;
     const bool prot = oc[OC_PROT] != 0.0;
     R ae, ao;
-    harm_args<R>(tab, prot, (R)oc[OC_KE], (R)oc[OC_KO], ego[EG_X * Ts + e0], ego[EG_Y * Ts + e0], ego[EG_C * Ts + e0],
-                 ego[EG_S * Ts + e0], ego[EG_V * Ts + e0], ego[kEgoAng * Ts + e0], ob.get(OF_MX, o, t), ob.get(OF_MY, o, t),
-                 ob.get(kObsAng, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t), ob.get(OF_SPSI, o, t), ae, ao);
+    harm_args<R>(tab, prot, (R)oc[OC_KE], (R)oc[OC_KO], a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, g0.x, g0.y, g1.w, g1.x, g1.y, g1.z,
+                 ae, ao);
     const R he = sigmoid_harm<R>(prot ? tab.lr_const : tab.lr1s_const, ae);
     const R ho = sigmoid_harm<R>(prot ? tab.lr_const : tab.neg_ped_const, ao);
     atomicMax(&c.rmax[o], Enc<R>::enc(he * prob));  // risk_costs.py:88-95
     atomicMax(&c.rmax[c.On + o], Enc<R>::enc(ho * prob));
-    if (c.o_prob) c.o_prob[c.prob_base + (size_t)t * c.O + o] = prob;
+    if (c.o_prob) c.o_prob[c.prob_base + vi] = prob;
 }
 
 struct WarpBest {
@@ -552,12 +593,11 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
     WarpSmem<R> sm(smem_raw + (size_t)warp * warp_smem_bytes<R>(Ts, O), Ts, O);
     const int Cs = st.c_end - st.c_begin;
     const int On = O > 0 ? O : 1;
-    Obs<R> ob{reinterpret_cast<const R*>(st.obs), (size_t)st.O * st.Tp, st.Tp, st.O};
+    Obs<R> ob(st.obs, st.O, st.Tp);
     R* o_traj = reinterpret_cast<R*>(out.traj);
     R* o_prob = reinterpret_cast<R*>(out.prob);
     R* o_red = reinterpret_cast<R*>(out.red);
     R* o_cost = reinterpret_cast<R*>(out.cost);
-    R* ego = sm.ego;
 
     const bool mahal = pr.mahalanobis != 0;
     __shared__ Tab<R> tab;
@@ -600,13 +640,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
                         }
                         sm.xd[t] = tp.f[ETP_F_X];
                         sm.yd[t] = tp.f[ETP_F_Y];
-                        ego[EG_X * Ts + t] = (R)tp.f[ETP_F_X];
-                        ego[EG_Y * Ts + t] = (R)tp.f[ETP_F_Y];
-                        ego[EG_C * Ts + t] = (R)tp.cos_yaw;
-                        ego[EG_S * Ts + t] = (R)tp.sin_yaw;
-                        ego[EG_V * Ts + t] = (R)tp.f[ETP_F_V];
-                        ego[EG_YAW * Ts + t] = (R)tp.f[ETP_F_YAW];
-                        ego[EG_WRAP * Ts + t] = (R)tp.wrap;
+                        sm.e0[t] = Vec4<R>{(R)tp.f[ETP_F_X], (R)tp.f[ETP_F_Y], (R)tp.cos_yaw, (R)tp.sin_yaw};
+                        sm.e1[t] = Vec2<R>{(R)tp.f[ETP_F_V], (R)(sizeof(R) == 4 ? tp.wrap : tp.f[ETP_F_YAW])};
                         sv += tp.f[ETP_F_V];
                         sd += fabs(tp.f[ETP_F_D]);
                         jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
@@ -632,16 +667,15 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
             // ---- risk rows: lanes over obstacles, loop over time -------------------------------------
             // Lane l owns obstacle ob + (l & (Op-1)) of the current block of <= 32 obstacles; when the
             // block has fewer than 17 obstacles the spare lanes take further timesteps (tt = l / Op).
-            // Running maxima over time stay in registers; obstacle rows of the tile are read coalesced
-            // ([field][t][o]) and the ego sample of the step is a shared-memory broadcast.
+            // Running maxima over time stay in registers; the obstacle samples of a step are two
+            // coalesced 16-byte loads per lane ([t][o] vector planes) and the ego sample is a
+            // shared-memory broadcast.
             if (O > 0 && !skip) {
-                constexpr int kEgoAng = sizeof(R) == 4 ? EG_WRAP : EG_YAW;
-                constexpr int kObsAng = sizeof(R) == 4 ? OF_WRAP : OF_PSI;
                 unsigned* q = sm.queue;
                 int q_n = 0;
-                EntryCtx<R> ectx{&tab, ego, ob, sm.rmax, st.obs_const, o_prob, Ts, O, On, pr.mahalanobis,
+                R* prob_c = o_prob ? o_prob + (size_t)cl * (Ts - 1) * O : nullptr;
+                EntryCtx<R> ectx{&tab, sm.e0, sm.e1, ob, sm.rmax, st.obs_const, o_prob, On, pr.mahalanobis,
                                  (size_t)cl * (Ts - 1) * O};
-                auto run_entry = [&](unsigned entry) { run_entry_fn<R>(ectx, entry); };
                 for (int ob0 = 0; ob0 < O; ob0 += 32) {
                     const int rem = min(32, O - ob0);
                     int Op = 32;
@@ -662,58 +696,64 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
                         ko = (R)oc[OC_KO];
                         halflen = oc[OC_HALFLEN];
                     }
+                    const int t_harm = min(T - 1, n_pred);  // harm samples: t < min(T-1, Tp)   (harm_estimation.py:234)
                     R hm_e = -INFINITY, hm_o = -INFINITY, rm = -INFINITY;
                     for (int t0 = 0; t0 < Ts - 1; t0 += TT) {
                         const int t = t0 + tt;
                         bool defer = false;
                         if (o_ok && t < Ts - 1) {
-                            bool gated = true;
-                            if (t < T - 1 && t < n_pred) {
-                                // harm sample t: ego[t] against prediction[t] (harm_estimation.py:234, 313-332)
-                                const R mx = ob.get(OF_MX, o, t), my = ob.get(OF_MY, o, t);
+                            const int vi = t * O + o;
+                            if (t < t_harm) {
+                                const Vec4<R> g0 = ldg4<R>(ob.v0 + vi), g1 = ldg4<R>(ob.v1 + vi);
+                                const Vec4<R> a0 = sm.e0[t];
+                                const Vec2<R> b0 = sm.e1[t];
+                                // harm sample t: ego[t] against prediction[t] (harm_estimation.py:313-332)
                                 R ae, ao;
-                                harm_args<R>(tab, prot, ke, ko, ego[EG_X * Ts + t], ego[EG_Y * Ts + t], ego[EG_C * Ts + t],
-                                             ego[EG_S * Ts + t], ego[EG_V * Ts + t], ego[kEgoAng * Ts + t], mx, my,
-                                             ob.get(kObsAng, o, t), ob.get(OF_VO, o, t), ob.get(OF_CPSI, o, t),
-                                             ob.get(OF_SPSI, o, t), ae, ao);
+                                harm_args<R>(tab, prot, ke, ko, a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, g0.x, g0.y, g1.w, g1.x, g1.y,
+                                             g1.z, ae, ao);
                                 hm_e = rmax_(hm_e, ae);
                                 hm_o = rmax_(hm_o, ao);
+                                bool gated = true;
                                 if (t + 1 < n_pred) {
                                     // probability sample t: ego[t+1] against mean[t], orientation[t+1]
                                     // (collision_probability.py:168-203)
                                     if (mahal) {
                                         gated = false;
                                     } else {
-                                        const R x = ego[EG_X * Ts + t + 1], y = ego[EG_Y * Ts + t + 1];
-                                        const R ex = ob.get(OF_EX, o, t), ey = ob.get(OF_EY, o, t);
-                                        R dx = mx - x, dy = my - y;
+                                        const Vec4<R> a1 = sm.e0[t + 1];
+                                        const R x = a1.x, y = a1.y;
+                                        R dx = g0.x - x, dy = g0.y - y;
                                         R d2 = dx * dx + dy * dy;
-                                        dx = (mx + ex) - x; dy = (my + ey) - y;
+                                        dx = (g0.x + g0.z) - x; dy = (g0.y + g0.w) - y;
                                         d2 = fmin(d2, dx * dx + dy * dy);
-                                        dx = (mx - ex) - x; dy = (my - ey) - y;
+                                        dx = (g0.x - g0.z) - x; dy = (g0.y - g0.w) - y;
                                         d2 = fmin(d2, dx * dx + dy * dy);
-                                        gated = sqrt_(d2) > (R)5.0;
-                                        if (sizeof(R) == 4 && abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y))) {
-                                            // fp32 cannot decide the 5 m gate here: repeat it in fp64 from the exact inputs
-                                            const double xe = sm.xd[t + 1], ye = sm.yd[t + 1];
-                                            const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
-                                            const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
-                                            const double len = 2 * halflen;
-                                            const double fx = cos(y1) * len / 2, fy = sin(y1) * len / 2;
-                                            double ax = rp[0] - xe, ay = rp[1] - ye;
-                                            double m = sqrt(ax * ax + ay * ay);
-                                            ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
-                                            m = fmin(m, sqrt(ax * ax + ay * ay));
-                                            ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
-                                            m = fmin(m, sqrt(ax * ax + ay * ay));
-                                            gated = m > 5.0;
+                                        if (sizeof(R) == 8) {
+                                            gated = sqrt_(d2) > (R)5.0;
+                                        } else {
+                                            gated = d2 > (R)25.0;
+                                            if (abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y))) {
+                                                // fp32 cannot decide the 5 m gate here: repeat it in fp64 from the exact inputs
+                                                const double xe = sm.xd[t + 1], ye = sm.yd[t + 1];
+                                                const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                                                const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+                                                const double len = 2 * halflen;
+                                                const double fx = cos(y1) * len / 2, fy = sin(y1) * len / 2;
+                                                double ax = rp[0] - xe, ay = rp[1] - ye;
+                                                double m = sqrt(ax * ax + ay * ay);
+                                                ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
+                                                m = fmin(m, sqrt(ax * ax + ay * ay));
+                                                ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
+                                                m = fmin(m, sqrt(ax * ax + ay * ay));
+                                                gated = m > 5.0;
+                                            }
                                         }
                                     }
                                 }
                                 if (gated) rm = rmax_(rm, (R)0);  // harm * 0.0
                                 else defer = true;
                             }
-                            if (!defer && o_prob) o_prob[((size_t)cl * (Ts - 1) + t) * O + o] = (R)0;
+                            if (!defer && prob_c) prob_c[vi] = (R)0;
                         }
                         const unsigned m = __ballot_sync(kFull, defer);
                         if (m) {
@@ -722,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
                             __syncwarp();
                             if (q_n >= 32) {
                                 q_n -= 32;
-                                run_entry(q[q_n + lane]);
+                                run_entry_fn<R>(ectx, q[q_n + lane]);
                                 __syncwarp();
                             }
                         }
@@ -742,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
                         }
                     }
                 }
-                if (lane < q_n) run_entry(q[lane]);  // drain: entries live at [0, q_n)
+                if (lane < q_n) run_entry_fn<R>(ectx, q[lane]);  // drain: entries live at [0, q_n)
                 __syncwarp();
             } else if (O > 0 && o_prob) {
                 for (int i = lane; i < O * (Ts - 1); i += 32) o_prob[(size_t)cl * O * (Ts - 1) + i] = (R)0;
@@ -1013,6 +1053,13 @@ cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, 
     if (precision == ETP_PRECISION_FP64)
         return launch_score_t<double>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
     return launch_score_t<float>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
+}
+
+cudaError_t read_debug_counters(unsigned long long* out, int n) {
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_fallback_evals, sizeof(v));
+    if (n > 0) out[0] = v;
+    return e;
 }
 
 cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream) {

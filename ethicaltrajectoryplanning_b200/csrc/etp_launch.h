@@ -20,6 +20,8 @@ cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, 
                          unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                          cudaStream_t stream);
 
+cudaError_t read_debug_counters(unsigned long long* out, int n);
+
 cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream);
 
 }  // namespace etp

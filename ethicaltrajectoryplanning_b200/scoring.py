@@ -362,6 +362,11 @@ class ScoringContext:
         self._check(self.lib.etp_get_timing(self.h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
 
+    def debug_counters(self):
+        v = (C.c_uint64 * 1)()
+        self._check(self.lib.etp_debug_counters(self.h, v, 1))
+        return {"fp64_fallback_evals": int(v[0])}
+
     def best_device_tensor(self):
         """uint8 view (torch) of the device-resident etp_best record, for collectives."""
         p = C.c_void_p()

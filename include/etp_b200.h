@@ -212,6 +212,9 @@ int etp_best_device_ptr(etp_ctx* ctx, void** ptr);
 int etp_enable_timing(etp_ctx* ctx, int enable);
 int etp_get_timing(etp_ctx* ctx, float* profile_ms, float* score_ms);
 
+/* Diagnostics: out[0] = fp32-path evaluations that needed the fp64 fallback (|rho| > 0.55) since load. */
+int etp_debug_counters(etp_ctx* ctx, uint64_t* out, int n);
+
 /* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks) */
 int etp_combine_best(const etp_best* bests, int n, etp_best* out);
 

@@ -36,6 +36,7 @@ def main():
     if bufs is not None:
         print("nonzero prob fraction", float((bufs["prob"] != 0).float().mean()))
     torch.cuda.synchronize()
+    print("debug counters", ctx.debug_counters())
     ctx.close()
 
 
