@@ -50,6 +50,32 @@ def records_from_bytes(buf: np.ndarray, n: int):
     return [_abi.Best.from_buffer_copy(raw[i * size:(i + 1) * size]) for i in range(n)]
 
 
+def key_hi_from(level: int, cost: float) -> int:
+    """Host twin of the device key: (4 - level rank) << 60 | monotone(cost) >> 4 (smaller wins)."""
+    import struct
+
+    rank = 4 if level == 10 else level
+    if cost != cost:
+        mono = (1 << 64) - 1
+    else:
+        b = struct.unpack("<Q", struct.pack("<d", float(cost)))[0]
+        mono = (~b & ((1 << 64) - 1)) if (b >> 63) else (b | (1 << 63))
+    return ((4 - rank) << 60) | (mono >> 4)
+
+
+def gather_best_records(local: "np.ndarray", dist, group=None, device=None):
+    """all_gather of one 40-byte etp_best record per rank (works on NCCL and gloo tensors)."""
+    import torch
+
+    world = dist.get_world_size(group)
+    t = torch.as_tensor(np.ascontiguousarray(local, dtype=np.uint8))
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * t.numel(),), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return records_from_bytes(out.cpu().numpy(), world)
+
+
 def python_combine(records):
     """Pure-Python twin of etp_combine_best for hosts without the CUDA library (gloo tests)."""
     win, scored, before = -1, 0, 0

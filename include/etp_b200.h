@@ -16,7 +16,7 @@
  *   - OUTPUT tensors in etp_out are caller-allocated DEVICE memory (e.g. torch tensors'
  *     data_ptr()); any of them may be NULL, in which case that tensor is not materialised;
  *   - etp_plan_step() is asynchronous on the context's stream; etp_get_best() /
- *     etp_get_best_trajectory() synchronise and read back a few hundred bytes.
+ *     etp_get_trajectory() synchronise and read back a few hundred bytes.
  *
  * Index conventions
  *   dense candidate index  c = (iv * nt + it) * nd + id   (generation order v -> t -> d of
