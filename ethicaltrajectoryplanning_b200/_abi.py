@@ -79,6 +79,7 @@ class Step(C.Structure):
         ("ext_level", _bp),
         ("bd_harm", _dp),
         ("c_begin", C.c_int32), ("c_end", C.c_int32),
+        ("shard_index", C.c_int32), ("shard_count", C.c_int32),
     ]
 
 
@@ -115,7 +116,7 @@ SYMBOLS = {
     "etp_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "etp_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "etp_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
-    "etp_combine_best": (C.c_int, [C.POINTER(Best), C.c_int, C.POINTER(Best)]),
+    "etp_combine_best": (C.c_int, [C.POINTER(Best), C.c_int, C.c_int, C.POINTER(Best)]),
 }
 
 

@@ -320,6 +320,8 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     const long long dense = (long long)s->nv * s->nt * s->nd;
     if (dense >= (1ll << 31)) ETP_FAIL(c, ETP_ERR_INVALID, "more than 2^31 candidates");
     if (s->c_begin < 0 || s->c_end > dense || s->c_begin >= s->c_end) ETP_FAIL(c, ETP_ERR_INVALID, "candidate range");
+    if (s->shard_count > 0 && (s->shard_index < 0 || s->shard_index >= s->shard_count))
+        ETP_FAIL(c, ETP_ERR_INVALID, "shard_index outside [0, shard_count)");
     if (s->c_begin % s->nd != 0 || s->c_end % s->nd != 0)
         ETP_FAIL(c, ETP_ERR_INVALID, "candidate range must be aligned to whole (v,t) profiles (multiples of nd=%d)", s->nd);
     const int Tmax = etp_tmax(s);
@@ -369,6 +371,13 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     st.nv = s->nv; st.nt = s->nt; st.nd = s->nd; st.Tmax = Tmax;
     st.c_begin = s->c_begin; st.c_end = s->c_end;
     st.p_begin = s->c_begin / s->nd; st.p_end = s->c_end / s->nd;
+    st.shard_count = s->shard_count > 0 ? s->shard_count : 1;
+    st.shard_index = s->shard_count > 0 ? s->shard_index : 0;
+    {
+        const int np_all = st.p_end - st.p_begin;
+        const int np_loc = st.shard_index < np_all ? (np_all - st.shard_index + st.shard_count - 1) / st.shard_count : 0;
+        st.n_local = np_loc * s->nd;
+    }
     st.vel_mode = s->velocity_cost_mode; st.vel_target = s->velocity_target; st.factor = s->cost_factor;
     st.knots = c->knots.as<double>(); st.cx = c->cx.as<double>(); st.cy = c->cy.as<double>(); st.nseg = c->nseg;
     const int n_prof = st.p_end - st.p_begin;
@@ -465,7 +474,7 @@ int etp_debug_counters(etp_ctx* c, uint64_t* out, int n) {
     return ETP_OK;
 }
 
-int etp_combine_best(const etp_best* b, int n, etp_best* out) {
+int etp_combine_best(const etp_best* b, int n, int consecutive_ranges, etp_best* out) {
     if (!b || !out || n < 1) return ETP_ERR_INVALID;
     int win = -1, scored_before_win = 0, scored = 0;
     for (int i = 0; i < n; ++i) {
@@ -484,7 +493,8 @@ int etp_combine_best(const etp_best* b, int n, etp_best* out) {
     }
     *out = b[win];
     out->n_scored = scored;
-    out->list_index = scored_before_win + b[win].list_index;  // shards are given in dense order
+    // interleaved shards of one range already report the global rank; consecutive ranges add the preceding counts
+    out->list_index = (consecutive_ranges ? scored_before_win : 0) + b[win].list_index;
     return ETP_OK;
 }
 

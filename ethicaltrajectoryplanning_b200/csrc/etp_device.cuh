@@ -50,6 +50,7 @@ struct DevStep {
     const int* nsamp;
     int nv, nt, nd, Tmax;
     int c_begin, c_end, p_begin, p_end;
+    int shard_index, shard_count, n_local;  // this call scores profiles p_begin + shard_index + k * shard_count
     int vel_mode;
     double vel_target, factor;
     const uint8_t* ext_level;  // device copy, indexed by dense candidate, or null

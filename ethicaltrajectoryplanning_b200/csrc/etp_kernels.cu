@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
     const int O = st.has_pred ? st.O : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpSmem<R> sm(smem_raw + (size_t)warp * warp_smem_bytes<R>(Ts, O), Ts, O);
-    const int Cs = st.c_end - st.c_begin;
+    const int Cs = st.n_local;  // candidates scored by this call: profiles p_begin + shard_index + k * shard_count
     const int On = O > 0 ? O : 1;
     Obs<R> ob(st.obs, st.O, st.Tp);
     R* o_traj = reinterpret_cast<R*>(out.traj);
@@ -613,9 +613,10 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(DevStep st, DevParam
         if (chunk0 >= Cs) break;
         const int chunk1 = min(chunk0 + kChunk, Cs);
         for (int cl = chunk0; cl < chunk1; ++cl) {
-            const int c_dense = st.c_begin + cl;
-            const int p = c_dense / st.nd, id = c_dense - p * st.nd;
-            const int pl = p - st.p_begin;
+            const int kl = cl / st.nd, id = cl - kl * st.nd;
+            const int pl = st.shard_index + kl * st.shard_count;  // row of the profile table
+            const int p = st.p_begin + pl;
+            const int c_dense = p * st.nd + id;
             const double* gp = st.prof + (size_t)pl * PF_COUNT * Ts;
             const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
             const double ds = pm[PM_DS];
@@ -1036,7 +1037,7 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     // persistent grid: every SM fully occupied, never more CTAs than there are work chunks
-    const long long chunks = ((long long)(st.c_end - st.c_begin) + kChunk - 1) / kChunk;
+    const long long chunks = ((long long)st.n_local + kChunk - 1) / kChunk;
     long long grid = (long long)num_sms * per_sm;
     const long long need = (chunks + kWarps - 1) / kWarps;
     if (grid > need) grid = need;

@@ -34,13 +34,14 @@ def scenario_shard(n_scenarios: int, rank: int, world: int):
     return list(range(rank, n_scenarios, world))
 
 
-def combine_best_records(records):
-    """Lexicographic min over shard-local etp_best records given in rank (= dense) order."""
+def combine_best_records(records, consecutive_ranges=False):
+    """Lexicographic min over shard-local etp_best records (interleaved shards of one range, or
+    consecutive candidate ranges given in dense order)."""
     n = len(records)
     arr = (_abi.Best * n)(*records)
     out = _abi.Best()
     lib = _abi.load_library()
-    rc = lib.etp_combine_best(arr, n, C.byref(out))
+    rc = lib.etp_combine_best(arr, n, int(bool(consecutive_ranges)), C.byref(out))
     return rc, out
 
 
@@ -76,7 +77,7 @@ def gather_best_records(local: "np.ndarray", dist, group=None, device=None):
     return records_from_bytes(out.cpu().numpy(), world)
 
 
-def python_combine(records):
+def python_combine(records, consecutive_ranges=False):
     """Pure-Python twin of etp_combine_best for hosts without the CUDA library (gloo tests)."""
     win, scored, before = -1, 0, 0
     for i, b in enumerate(records):
@@ -87,7 +88,7 @@ def python_combine(records):
         return None
     out = dict(records[win])
     out["n_scored"] = scored
-    out["list_index"] = before + records[win]["list_index"]
+    out["list_index"] = (before if consecutive_ranges else 0) + records[win]["list_index"]
     return out
 
 
@@ -104,9 +105,9 @@ class ShardedPlanner:
         self.world = dist.get_world_size(group)
         self._gather = None
 
-    def shard_range(self, step):
-        n_prof = len(step.v_list) * len(step.t_list)
-        return profile_shard(n_prof, len(step.d_list), self.rank, self.world)
+    def make_step_struct(self, step):
+        """Step struct of this rank: whole dense range, profiles interleaved over the ranks."""
+        return self.ctx.make_step_struct(step, shard_index=self.rank, shard_count=self.world)
 
     def launch(self, s, bufs=None):
         """Local fused launch + all-gather of the 40-byte best records (asynchronous)."""

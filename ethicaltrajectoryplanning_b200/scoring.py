@@ -280,7 +280,7 @@ class ScoringContext:
         self.set_predictions(step.predictions, step.obstacle_types)
 
     # -- one planning step --------------------------------------------------------------------
-    def make_step_struct(self, step, c_begin=None, c_end=None):
+    def make_step_struct(self, step, c_begin=None, c_end=None, shard_index=0, shard_count=1):
         v = np.ascontiguousarray(step.v_list, dtype=np.float64)
         t = np.ascontiguousarray(step.t_list, dtype=np.float64)
         d = np.ascontiguousarray(step.d_list, dtype=np.float64)
@@ -308,6 +308,7 @@ class ScoringContext:
         dense = len(v) * len(t) * len(d)
         s.c_begin = 0 if c_begin is None else int(c_begin)
         s.c_end = dense if c_end is None else int(c_end)
+        s.shard_index, s.shard_count = int(shard_index), int(shard_count)
         return s, keep, n
 
     def allocate_outputs(self, Cs, Tmax, O, traj=True, prob=True, red=True, cost=True):
@@ -384,15 +385,32 @@ class ScoringContext:
         self._check(self.lib.etp_get_trajectory(self.h, int(index), _dptr(f), C.byref(n)))
         return f, int(n.value)
 
+    @staticmethod
+    def local_candidates(s):
+        """Rows of the output tensors for a step struct: (profiles of this shard) * nd."""
+        n_prof = (s.c_end - s.c_begin) // s.nd
+        cnt = max(1, s.shard_count)
+        idx = s.shard_index if s.shard_count > 0 else 0
+        n_loc = (n_prof - idx + cnt - 1) // cnt if idx < n_prof else 0
+        return n_loc * s.nd
+
+    def local_to_dense(self, s):
+        """Dense candidate index of every local output row."""
+        cnt = max(1, s.shard_count)
+        idx = s.shard_index if s.shard_count > 0 else 0
+        rows = np.arange(self.local_candidates(s))
+        k, i = rows // s.nd, rows % s.nd
+        return (s.c_begin // s.nd + idx + k * cnt) * s.nd + i
+
     def plan(self, step: PlanningStep, materialize=True, c_begin=None, c_end=None, bufs=None,
-             configure=True) -> ScoreResult:
+             configure=True, shard_index=0, shard_count=1) -> ScoreResult:
         """calc_frenet_trajectories + sort_frenet_trajectories + selection of one step
         (frenet_planner.py:326-340, 433-457, 555-558)."""
         if configure:
             self.configure(step)
-        s, keep, n = self.make_step_struct(step, c_begin, c_end)
+        s, keep, n = self.make_step_struct(step, c_begin, c_end, shard_index, shard_count)
         Tmax = int(n.max())
-        Cs = s.c_end - s.c_begin
+        Cs = self.local_candidates(s)
         if materialize and bufs is None:
             bufs = self.allocate_outputs(Cs, Tmax, self.O)
         self.launch(s, bufs if materialize else None)

@@ -145,10 +145,13 @@ typedef struct {
     double cost_factor;             /* get_cost_factor (calc_trajectory_cost.py:349-415) */
     const uint8_t* ext_level;       /* optional [nv*nt*nd]: 1 collision, 2 boundary, else pass (pycrcc results) */
     const double* bd_harm;          /* optional [nv*nt*nd]: boundary harm (risk_costs.py:104-123) */
-    int32_t c_begin, c_end;         /* dense candidate range scored by this call (shard); must be profile aligned */
+    int32_t c_begin, c_end;         /* dense candidate range of this call; must be aligned to whole (v,t) profiles */
+    int32_t shard_index, shard_count; /* multi-GPU: score only the profiles p with (p - p_begin) % shard_count == shard_index
+                                       (interleaved, so slow and fast profiles spread evenly); shard_count 0 or 1 = all */
 } etp_step;
 
-/* Caller-allocated device tensors for the scored range [c_begin, c_end); Cs = c_end - c_begin. */
+/* Caller-allocated device tensors for the scored candidates.  Cs = (number of profiles of this shard) * nd;
+ * local row cl = k * nd + id is dense candidate (p_begin + shard_index + k * shard_count) * nd + id. */
 typedef struct {
     int32_t precision;   /* ETP_PRECISION_*; element type of traj/prob/red/cost */
     void* traj;          /* [ETP_NUM_FIELDS][Cs][Tmax]   (entries past a candidate's T are 0) */
@@ -168,7 +171,7 @@ typedef struct {
     int32_t index;       /* dense index, -1 if no candidate */
     int32_t level;
     int32_t n_scored;    /* non-skipped candidates in the range */
-    int32_t list_index;  /* position in the reference's fp_list (rank among non-skipped), shard-local count */
+    int32_t list_index;  /* position in the reference's fp_list: rank among the non-skipped candidates of [c_begin, c_end) */
 } etp_best;
 
 int etp_create(etp_ctx** ctx, int device);
@@ -215,8 +218,10 @@ int etp_get_timing(etp_ctx* ctx, float* profile_ms, float* score_ms);
 /* Diagnostics: out[0] = fp32-path evaluations that needed the fp64 fallback (|rho| > 0.55) since load. */
 int etp_debug_counters(etp_ctx* ctx, uint64_t* out, int n);
 
-/* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks) */
-int etp_combine_best(const etp_best* bests, int n, etp_best* out);
+/* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks).
+ * consecutive_ranges = 0: interleaved shards of ONE range (list_index is already global);
+ * consecutive_ranges = 1: records of consecutive candidate ranges, given in dense order. */
+int etp_combine_best(const etp_best* bests, int n, int consecutive_ranges, etp_best* out);
 
 #ifdef __cplusplus
 }

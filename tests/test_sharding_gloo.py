@@ -52,9 +52,9 @@ def test_c_combine_matches_python_combine():
                 li = int(rng.integers(0, cnt))
                 recs.append(_rec(base + li, int(rng.choice([0, 1, 2, 3, 10])), float(rng.choice([0.0, 1.5, -2.0, 7.25])), cnt, li))
             base += 10
-        rc, out = D.combine_best_records(recs)
+        rc, out = D.combine_best_records(recs, consecutive_ranges=True)
         py = D.python_combine([dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored,
-                                    list_index=b.list_index, key_hi=b.key_hi, key_lo=b.key_lo) for b in recs])
+                                    list_index=b.list_index, key_hi=b.key_hi, key_lo=b.key_lo) for b in recs], consecutive_ranges=True)
         if py is None:
             assert rc == _abi.ERR_NO_CANDIDATE
         else:
@@ -84,7 +84,7 @@ def _worker(rank, world, port, case, q):
         except ValueError:
             rec = _rec(-1, -1, 0.0, 0, -1)
         recs = D.gather_best_records(np.frombuffer(bytes(rec), dtype=np.uint8), dist)
-        rc, out = D.combine_best_records(recs)
+        rc, out = D.combine_best_records(recs, consecutive_ranges=True)
         q.put((rank, rc, out.index, out.level, out.list_index, out.n_scored))
     finally:
         dist.destroy_process_group()
