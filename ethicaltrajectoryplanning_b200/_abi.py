@@ -11,7 +11,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libetp_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_abi.cu")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_score.cu", "etp_abi.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_launch.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "etp_b200.h")]
 
@@ -88,6 +88,7 @@ class Out(C.Structure):
         ("precision", C.c_int32),
         ("traj", C.c_void_p), ("prob", C.c_void_p), ("red", C.c_void_p), ("cost", C.c_void_p),
         ("level", C.c_void_p), ("reason", C.c_void_p),
+        ("c_stride", C.c_int64),
     ]
 
 

@@ -56,6 +56,7 @@ struct PinnedBuf {
 struct etp_ctx {
     int device = 0;
     int num_sms = 0;
+    int smem_optin = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t staged = nullptr;
     bool staged_pending = false;
@@ -149,6 +150,7 @@ int etp_create(etp_ctx** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
     c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
     c->stream = c->own_stream;
     if (cudaEventCreateWithFlags(&c->staged, cudaEventDisableTiming) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
@@ -224,6 +226,12 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
     d.inv_turn_radius = 1.0 / radius;
     d.v_thr_curv = std::sqrt(p->veh_lat_a_max * radius);
     d.lat_a_max = p->veh_lat_a_max;
+    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) d.f_fcos[i] = (float)d.fcos[i];
+    for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { d.f_coef_pos[i] = (float)d.coef_pos[i]; d.f_coef_neg[i] = (float)d.coef_neg[i]; }
+    d.f_lr_speed = (float)d.lr_speed; d.f_lr1s_speed = (float)d.lr1s_speed; d.f_ped_speed = (float)d.ped_speed;
+    if (d.n_thr == 0) d.wrapfree_yaw = 1e30;
+    else if (d.coef_pos[d.n_thr] == d.coef_neg[d.n_thr]) d.wrapfree_yaw = 3.14159265358979323846 - d.thr[d.n_thr - 1] - 1e-9;
+    else d.wrapfree_yaw = -1.0;
     c->have_params = true;
     return ETP_OK;
 }
@@ -281,7 +289,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_resp.reserve(sizeof(int) * O));
-        ETP_CUDA(c, c->o_tile.reserve(sizeof(double) * (OF_COUNT + 8) * n));
+        ETP_CUDA(c, c->o_tile.reserve(Tile<double>::bytes(O, Tp)));
         ETP_CUDA(c, c->o_const.reserve(sizeof(double) * OC_COUNT * O));
         if ((r = stage_to_device(c, c->o_pos.p, o->pos, sizeof(double) * 2 * n))) return r;
         if ((r = stage_to_device(c, c->o_cov.p, o->cov, sizeof(double) * 4 * n))) return r;
@@ -394,6 +402,16 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     if (out) {
         dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
         dout.level = out->level; dout.reason = out->reason;
+        dout.c_stride = out->c_stride > 0 ? (size_t)out->c_stride : (size_t)st.n_local;
+        if (dout.c_stride < (size_t)st.n_local)
+            ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.c_stride=%lld is smaller than the %d candidates of this call",
+                     (long long)out->c_stride, st.n_local);
+    }
+    {
+        const size_t smem = score_smem_bytes(c->precision, Tmax, c->has_pred ? c->O : 0);
+        if (smem > (size_t)c->smem_optin)
+            ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "Tmax=%d samples x %d obstacles need %zu bytes of shared memory per CTA (limit %d)",
+                     Tmax, c->O, smem, c->smem_optin);
     }
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     ETP_CUDA(c, launch_profiles(st, c->pr, c->nskip.as<int>(), c->stream));

@@ -175,8 +175,9 @@ __device__ __forceinline__ float rho_correction_f(const RhoNodes<N>& n, float xl
     return acc;
 }
 
-// rectangles farther than this many standard deviations from the mean contribute < 1e-19
-#define ETP_PRUNE_SIGMA 9.0f
+// rectangles farther than this many standard deviations from the mean contribute < 1.3e-12 each (tail of the
+// nearer marginal), i.e. < 4e-12 to the stored probability: three orders below the 1e-9 absolute floor of the parity bar
+#define ETP_PRUNE_SIGMA 7.0f
 
 template <int N>
 __device__ __forceinline__ float rect_prob_nodes_f(const RhoNodes<N>& n, float xl, float xu, float yl, float yu) {

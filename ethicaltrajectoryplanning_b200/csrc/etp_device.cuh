@@ -15,18 +15,44 @@ enum { PF_S = 0, PF_S_D, PF_S_DD, PF_S_DDD, PF_GX, PF_GY, PF_YAW, PF_CURV, PF_CU
 // per-profile scalars
 enum { PM_DS = 0, PM_LOW, PM_T, PM_VEL_OK, PM_TEND, PM_COUNT };
 
-// rows of the packed obstacle tile, layout [field][t][o] (obstacle fastest: lanes map to obstacles), element type R
-enum {
-    OF_MX = 0, OF_MY,      // pos_list[t]
-    OF_EX, OF_EY,          // (length/2) * (cos, sin)(orientation_list[t+1])   (collision_probability.py:175)
-    OF_ISX, OF_ISY, OF_RHO,// 1/stdev_x, 1/stdev_y, correlation of cov_list[t] (zero matrix -> 0.1*I, :205-212)
-    OF_PSI, OF_VO,         // orientation_list[t], v_list[t]                     (harm_estimation.py:313-328)
-    OF_CPSI, OF_SPSI,      // cos / sin of orientation_list[t]
-    OF_I00, OF_I01, OF_I11,// inverse covariance (Mahalanobis mode, collision_probability.py:279)
-    OF_WRAP,               // ceil((orientation_list[t] - pi) / 2pi): turns to bring the yaw into (-pi, pi]
-    OF_COUNT
+// Packed obstacle tile, element type R (Vec4<R> = 16 or 32 bytes).  Time-major, one record per (t, o): all lanes
+// of a warp work on the same (t, o) pair (lanes are candidates), so every tile read is one uniform address.
+//   G [Tp][O][2]  gate + harm : (mx, my, ex, ey), (vo, cos psi, sin psi, wrap | psi)
+//                   m = pos_list[t];  e = (length/2)(cos, sin)(orientation_list[t+1])  (collision_probability.py:175)
+//                   vo = v_list[t], psi = orientation_list[t]                           (harm_estimation.py:313-328)
+//                   wrap = ceil((psi - pi) / 2pi): whole turns that bring psi into (-pi, pi]  (fp32 tile; fp64 keeps psi)
+//   P [Tp][O][2]  probability : (1/sx, 1/sy, rho, class), (i00, i01, i11, 0)
+//                   stdevs / correlation of cov_list[t] (zero matrix -> 0.1*I, collision_probability.py:205-212);
+//                   class = Gauss-Legendre node count class of |rho| (0: rho = 0, 1: 4 nodes, 2: 6 nodes, 3: fp64 path);
+//                   i** = inverse of cov_list[t] for the Mahalanobis mode (collision_probability.py:279)
+//   N [Tp][O][5]  float4, fp32 tile only: nodes of the rho integral s[6] | q[6] | c[6] | pad[2]
+//   C [O]         per obstacle: (m_o/(m_e+m_o), m_e/(m_e+m_o), protected, responsibility)  (harm_estimation.py:327-328)
+template <typename R> struct alignas(16) Vec4 { R x, y, z, w; };
+template <typename R> struct alignas(2 * sizeof(R)) Vec2 { R x, y; };
+
+enum { RC_ZERO = 0, RC_N4 = 1, RC_N6 = 2, RC_FP64 = 3 };
+constexpr int kNodeVecs = 5;
+
+template <typename R> struct Tile {
+    const Vec4<R>* G;
+    const Vec4<R>* P;
+    const float4* N;
+    const Vec4<R>* C;
+    int O;
+    __host__ __device__ Tile(const void* base, int O_, int Tp) : O(O_) {
+        const size_t n = (size_t)O_ * Tp;
+        G = reinterpret_cast<const Vec4<R>*>(base);
+        P = G + 2 * n;
+        N = reinterpret_cast<const float4*>(P + 2 * n);
+        C = reinterpret_cast<const Vec4<R>*>(N + kNodeVecs * n);
+    }
+    static __host__ __device__ size_t bytes(int O_, int Tp) {
+        const size_t n = (size_t)O_ * Tp;
+        return n * (4 * sizeof(Vec4<R>) + kNodeVecs * sizeof(float4)) + (size_t)O_ * sizeof(Vec4<R>);
+    }
 };
-// per-obstacle constants [o][OC_COUNT], fp64
+
+// per-obstacle constants [o][OC_COUNT], fp64 (exact inputs of the fp64 gate re-check and the principle costs)
 enum { OC_KE = 0, OC_KO, OC_PROT, OC_RESP, OC_HALFLEN, OC_COUNT };
 
 struct DevParams {
@@ -40,6 +66,12 @@ struct DevParams {
     double lr_const, lr_speed, lr1s_const, lr1s_speed, ped_const, ped_speed;
     double veh_l, veh_w, veh_m, v_max;
     double inv_turn_radius, v_thr_curv, lat_a_max;
+    // fp32 images read as constant-bank operands by the specialised scoring kernels
+    float f_fcos[ETP_MAX_ANGLE_BINS], f_coef_pos[ETP_MAX_ANGLE_BINS + 1], f_coef_neg[ETP_MAX_ANGLE_BINS + 1];
+    float f_lr_speed, f_lr1s_speed, f_ped_speed;
+    // |yaw| up to which the un-wrapped ego impact angle (quirk Q4) bins like the geometric one: pi - last threshold
+    // (negative: never; needs equal last-band coefficients on both sides)
+    double wrapfree_yaw;
 };
 
 struct DevStep {
@@ -66,7 +98,7 @@ struct DevStep {
     // obstacles
     int has_pred;  // 0: predictions is None
     int O, Tp;
-    const void* obs;         // packed tile [OF_COUNT][Tp][O] of R
+    const void* obs;         // packed obstacle tile (struct Tile<R>)
     const double* obs_const; // [O][OC_COUNT]
     const int* pred_len;     // [O]
     // raw fp64 copies for the exact gate re-check of the fp32 path
@@ -81,6 +113,7 @@ struct DevOut {
     void* cost;
     uint8_t* level;
     uint8_t* reason;
+    size_t c_stride;  // elements between rows of the candidate-minor tensors
 };
 
 struct BestRec {

@@ -1,4 +1,4 @@
-// Host-callable launchers implemented in etp_kernels.cu (internal to the shared library).
+// Host-callable launchers implemented in etp_kernels.cu / etp_score.cu (internal to the shared library).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -19,6 +19,9 @@ cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, 
 cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
                          unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                          cudaStream_t stream);
+
+// dynamic shared memory one CTA of the scoring kernel needs for (Tmax, O)
+size_t score_smem_bytes(int precision, int Tmax, int O);
 
 cudaError_t read_debug_counters(unsigned long long* out, int n);
 

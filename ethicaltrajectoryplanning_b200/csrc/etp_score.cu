@@ -1,0 +1,924 @@
+// Fused per-candidate scoring kernel of the B200-native candidate-trajectory path (sm_100a).
+//
+//   score_kernel<R> : quintic + Frenet->Cartesian + validity masks, collision probability, harm, risk maxima
+//                     over time, ethical principle costs, weighted cost, validity level, block arg-min; the
+//                     last block finishes the grid arg-min (frenet_functions.py:330-474, 529-593;
+//                     collision_probability.py:136-256; harm_estimation.py:306-332; risk_costs.py:87-101,
+//                     128-255; calc_trajectory_cost.py:103-146,279-346; validity_checks.py:31-122)
+//
+// Work decomposition ("lanes are candidates").  A tile is 32 consecutive candidates of the generation
+// order, one per lane, owned by one CTA of 8 warps for its whole life:
+//   phase 1  warps split the TIME axis: each lane generates its candidate's samples of the warp's time chunk
+//            in fp64 (masks are bit-exact), streams the 13 trajectory fields out and leaves the ego samples
+//            (x, y, cos yaw, sin yaw | v, yaw wraps) in shared memory;
+//   phase 2a warps pull (obstacle group, time segment) items: every lane walks its own candidate against the
+//            SAME (t, o) prediction sample, so each obstacle record is one uniform (broadcast) 16-byte load; the
+//            harm logits are straight-line code with running maxima in registers; (t, o) samples with a lane
+//            within reach of the 5 m gate go to a shared-memory queue;
+//   phase 2b warps pull queue entries: three-point gate, bivariate-normal probability, risk.  Neighbouring
+//            lateral targets are centimetres apart, so whole warps take this branch together, and all warps
+//            of the CTA run the same few hundred instructions of code at the same time;
+//   phase 3  warps split the OBSTACLE axis for the per-obstacle reductions, warp 0 finishes cost, level, key.
+// All materialised tensors are candidate-minor ([...][c]): every store of a warp is one contiguous 128-byte
+// line, written exactly once.
+#include "etp_bvn.cuh"
+#include "etp_device.cuh"
+#include "etp_launch.h"
+
+namespace etp {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMinBlocks = 2;  // resident CTAs per SM the register budget is sized for
+constexpr int kOB = 4;  // obstacles of one phase-2 item (register blocking: one ego load serves kOB obstacles)
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// small typed helpers
+// ---------------------------------------------------------------------------------------------
+// order-preserving integer image of a real: max over reals == max over images (shared-memory atomicMax)
+template <typename R> struct Enc;
+template <> struct Enc<float> {
+    using U = unsigned int;
+    static __device__ __forceinline__ U enc(float x) {
+        U b = __float_as_uint(x);
+        return (b >> 31) ? ~b : (b | 0x80000000u);
+    }
+    static __device__ __forceinline__ float dec(U k) {
+        U b = (k >> 31) ? (k & 0x7fffffffu) : ~k;
+        return __uint_as_float(b);
+    }
+};
+template <> struct Enc<double> {
+    using U = unsigned long long;
+    static __device__ __forceinline__ U enc(double x) {
+        U b = (U)__double_as_longlong(x);
+        return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double dec(U k) {
+        U b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        return __longlong_as_double((long long)b);
+    }
+};
+
+template <typename R> __device__ __forceinline__ Vec4<R> ldg4(const Vec4<R>* p);
+template <> __device__ __forceinline__ Vec4<float> ldg4<float>(const Vec4<float>* p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return Vec4<float>{v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Vec4<double> ldg4<double>(const Vec4<double>* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return Vec4<double>{a.x, a.y, b.x, b.y};
+}
+template <typename R> __device__ __forceinline__ R rmax_(R a, R b) { return a > b ? a : b; }
+// square root of the fp32 streaming path: MUFU.RSQ based (2 ulp); the fp64 check mode stays IEEE
+__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+__device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
+__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float exp_(float x) { return expf(x); }
+__device__ __forceinline__ double exp_(double x) { return exp(x); }
+__device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_(double x) { return fabs(x); }
+
+// Constants of the risk model in the arithmetic type R, resident in shared memory (one copy per CTA):
+// dynamic indexing into kernel parameters would force a per-thread local-memory copy of DevParams.
+template <typename R> struct Tab {
+    R thr[ETP_MAX_ANGLE_BINS], fcos[ETP_MAX_ANGLE_BINS], coef_pos[ETP_MAX_ANGLE_BINS + 1], coef_neg[ETP_MAX_ANGLE_BINS + 1];
+    R lr_speed, lr1s_speed, ped_speed, lr_const, lr1s_const, neg_ped_const;
+    R coef_max;    // largest impact-area coefficient: upper bound of the harm logit without looking at the angle
+    R hx, hy, rr;  // ego box half extents (l/6, w/2) and centre offset (l/2)(2/3)  (collision_probability.py:157,349-362)
+    int n_thr;
+};
+
+template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const DevParams& pr) {
+    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) { tb.thr[i] = (R)pr.thr[i]; tb.fcos[i] = (R)pr.fcos[i]; }
+    for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { tb.coef_pos[i] = (R)pr.coef_pos[i]; tb.coef_neg[i] = (R)pr.coef_neg[i]; }
+    R cm = tb.coef_pos[0];
+    for (int i = 0; i <= pr.n_thr; ++i) cm = rmax_(cm, rmax_(tb.coef_pos[i], tb.coef_neg[i]));
+    tb.coef_max = cm;
+    tb.lr_speed = (R)pr.lr_speed; tb.lr1s_speed = (R)pr.lr1s_speed; tb.ped_speed = (R)pr.ped_speed;
+    tb.lr_const = (R)pr.lr_const; tb.lr1s_const = (R)pr.lr1s_const; tb.neg_ped_const = (R)(-pr.ped_const);
+    tb.hx = (R)(pr.veh_l / 6); tb.hy = (R)(pr.veh_w / 2); tb.rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
+    tb.n_thr = pr.n_thr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// harm model (harm_estimation.py:313-332): harm = 1 / (1 + exp(-(const + arg))), arg = speed * dv_k + coef(angle)
+// ---------------------------------------------------------------------------------------------
+// delta_v = sqrt(v_e^2 + v_o^2 + 2 v_e v_o cos(pdof)), pdof = psi_o - psi_e + pi (harm_estimation.py:313,322-325)
+__device__ __forceinline__ float delta_v(float ec, float es, float ev, float, float ovo, float ocp, float osp, float) {
+    const float cpd = -(ocp * ec + osp * es);
+    return sqrt_fast(ev * ev + ovo * ovo + 2 * ev * ovo * cpd);
+}
+// fp64 check mode evaluates pdof with the reference's own expression
+__device__ __forceinline__ double delta_v(double, double, double ev, double eyaw, double ovo, double, double, double opsi) {
+    const double pdof = opsi - eyaw + 3.14159265358979323846;
+    return sqrt(ev * ev + ovo * ovo + 2 * ev * ovo * cos(pdof));
+}
+
+// impact-area coefficient (logistic_regression_*.py): thresholds on |angle|, sign picks the side
+template <typename R> __device__ __forceinline__ R angle_coef(const Tab<R>& pr, R angle) {
+    const R a = abs_(angle);
+    int i = 0;
+    while (i < pr.n_thr && !(a < pr.thr[i])) ++i;
+    return angle < (R)0 ? pr.coef_neg[i] : pr.coef_pos[i];
+}
+
+// Band of an impact angle given as a direction: P = |d| cos(angle), d2 = |d|^2.  |angle| < thr is
+// cos(angle) > cos(thr), compared through the sign-preserving squares P|P| > d2 * cos(thr)|cos(thr)|.
+__device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, float d2) {
+    // thresholds increase, so the tests pass from some band on: the band is the number of failed tests
+    const float fp = P * fabsf(P);
+    int band = 0;
+    for (int i = 0; i < pr.n_thr; ++i) band += (fp > d2 * pr.fcos[i]) ? 0 : 1;
+    return band;
+}
+
+// Impact-area coefficients of ego and obstacle, fp32 path.  `ewrap` / `owrap` are the whole turns that bring
+// the ego / obstacle yaw into (-pi, pi].  The reference bins the UN-wrapped angles rel - yaw_e and
+// pi + rel - psi_o (quirk Q4) with rel = atan2(dy, dx); instead of evaluating atan2, the relative direction is
+// rotated into the ego / obstacle frame (P, Q) and the number of 2 pi wraps of the un-wrapped difference is
+// recovered from the half planes of the two directions.  |angle| > pi always lands in the last ("rear") band.
+__device__ __forceinline__ void impact_coefs(const Tab<float>& pr, float ex, float ey, float ec, float es, float ewrap,
+                                             float mx, float my, float ocp, float osp, float owrap, float& ce, float& co) {
+    const float dx = mx - ex, dy = my - ey;
+    const float d2 = dx * dx + dy * dy;
+    const int last = pr.n_thr;
+    // ego: angle = rel - yaw_e
+    const float p = dx * ec + dy * es, q = dy * ec - dx * es;
+    int n0 = 0;
+    if (dy >= 0 && es < 0 && q < 0) n0 = 1;
+    if (dy < 0 && es >= 0 && q > 0) n0 = -1;
+    const int be = ((float)n0 != ewrap) ? last : direction_band(pr, p, d2);
+    ce = q < 0 ? pr.coef_neg[be] : pr.coef_pos[be];
+    // obstacle: angle = pi + rel - psi_o
+    const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
+    n0 = 0;
+    if (dy >= 0 && osp < 0 && qo < 0) n0 = 1;
+    if (dy < 0 && osp >= 0 && qo > 0) n0 = -1;
+    const float k = (float)n0 - owrap;
+    const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
+    const bool neg_side = (k == -1.0f) && (qo >= 0);
+    const int bo = (pos_side || neg_side) ? direction_band(pr, -po, d2) : last;
+    co = neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo];
+}
+__device__ __forceinline__ void impact_coefs(const Tab<double>& pr, double ex, double ey, double, double, double eyaw,
+                                             double mx, double my, double, double, double opsi, double& ce, double& co) {
+    const double rel = atan2(my - ey, mx - ex);  // harm_estimation.py:314-319
+    ce = angle_coef<double>(pr, rel - eyaw);
+    co = angle_coef<double>(pr, 3.14159265358979323846 + rel - opsi);
+}
+
+template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { return (R)1 / ((R)1 + exp_(-cst - arg)); }
+
+// ---------------------------------------------------------------------------------------------
+// harm logits of one (ego sample t, prediction sample t) pair, the streaming form of phase 2
+// ---------------------------------------------------------------------------------------------
+// Coefficient of the geometric band of a direction (fp = P|P|, d2): first threshold whose test passes.  NT
+// thresholds are compile-time; thresholds and coefficients are constant-bank operands (no loads, no loop).
+template <int NT> __device__ __forceinline__ float chain_coef(const DevParams& pr, float fp, float d2, bool neg) {
+    float coef = neg ? pr.f_coef_neg[NT] : pr.f_coef_pos[NT];
+#pragma unroll
+    for (int i = NT - 1; i >= 0; --i) {
+        const float ci = neg ? pr.f_coef_neg[i] : pr.f_coef_pos[i];
+        coef = (fp > d2 * pr.f_fcos[i]) ? ci : coef;
+    }
+    return coef;
+}
+
+constexpr float kWrapFree = 100.0f;  // marker in the ego "wrap" slot: un-wrapped and geometric ego angle bin alike
+
+// R = float, NT >= 0: specialised.  `fast_ego`: every lane's ego sample carries kWrapFree.
+template <typename R, int NT> struct Logits {
+    static __device__ __forceinline__ void eval(const DevParams& pr, const Tab<float>& tab, bool fast_ego, Vec4<float> c0,
+                                                Vec2<float> c1, Vec4<float> g0, Vec4<float> g1, bool prot, float ke,
+                                                float ko, float& ae, float& ao) {
+        const float dv = delta_v(c0.z, c0.w, c1.x, 0.0f, g1.x, g1.y, g1.z, 0.0f);
+        const float dve = ke * dv, dvo = ko * dv;
+        if (!prot) {
+            ae = pr.f_lr1s_speed * dve;
+            ao = pr.f_ped_speed * dvo;
+            return;
+        }
+        const float dx = g0.x - c0.x, dy = g0.y - c0.y;
+        const float d2 = dx * dx + dy * dy;
+        const float ec = c0.z, es = c0.w, ocp = g1.y, osp = g1.z, owrap = g1.w;
+        // ego: angle = rel - yaw_e
+        const float p = dx * ec + dy * es, q = dy * ec - dx * es;
+        float ce = chain_coef<NT>(pr, p * fabsf(p), d2, q < 0);
+        if (!fast_ego) {
+            int n0 = 0;
+            if (dy >= 0 && es < 0 && q < 0) n0 = 1;
+            if (dy < 0 && es >= 0 && q > 0) n0 = -1;
+            const float ewrap = c1.y == kWrapFree ? 0.0f : c1.y;
+            const float cl = q < 0 ? pr.f_coef_neg[NT] : pr.f_coef_pos[NT];
+            ce = ((float)n0 != ewrap) ? cl : ce;
+        }
+        // obstacle: angle = pi + rel - psi_o
+        const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
+        int n0 = 0;
+        if (dy >= 0 && osp < 0 && qo < 0) n0 = 1;
+        if (dy < 0 && osp >= 0 && qo > 0) n0 = -1;
+        const float k = (float)n0 - owrap;
+        const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
+        const bool neg_side = (k == -1.0f) && (qo >= 0);
+        float co = chain_coef<NT>(pr, -po * fabsf(po), d2, neg_side);
+        co = (pos_side || neg_side) ? co : pr.f_coef_pos[NT];
+        ae = pr.f_lr_speed * dve + ce;
+        ao = pr.f_lr_speed * dvo + co;
+    }
+};
+
+// generic form: runtime threshold count, any arithmetic type (fp64 check mode, unusual tables)
+template <typename R> struct Logits<R, -1> {
+    static __device__ __forceinline__ void eval(const DevParams&, const Tab<R>& tab, bool, Vec4<R> c0, Vec2<R> c1, Vec4<R> g0,
+                                                Vec4<R> g1, bool prot, R ke, R ko, R& ae, R& ao) {
+        const R ewrap = (sizeof(R) == 4 && c1.y == (R)kWrapFree) ? (R)0 : c1.y;
+        const R dv = delta_v(c0.z, c0.w, c1.x, ewrap, g1.x, g1.y, g1.z, g1.w);
+        const R dve = ke * dv, dvo = ko * dv;
+        if (prot) {
+            R ce, co;
+            impact_coefs(tab, c0.x, c0.y, c0.z, c0.w, ewrap, g0.x, g0.y, g1.y, g1.z, g1.w, ce, co);
+            ae = tab.lr_speed * dve + ce;
+            ao = tab.lr_speed * dvo + co;
+        } else {
+            ae = tab.lr1s_speed * dve;
+            ao = tab.ped_speed * dvo;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// collision probability of one (ego sample i = t+1, obstacle sample t) pair
+// (collision_probability.py:205-252, 329-364): 3 means x 3 axis-aligned ego boxes.
+// ---------------------------------------------------------------------------------------------
+// diagnostics: evaluations of the fp32 path that took the fp64 fallback (|rho| > 0.55 or NaN)
+__device__ unsigned long long g_fallback_evals = 0ull;
+
+struct RectDouble {
+    __device__ __forceinline__ double operator()(double xl, double xu, double yl, double yu, double r) const {
+        return rect_prob(xl, xu, yl, yu, r);
+    }
+};
+struct RectFallbackF {
+    __device__ __forceinline__ float operator()(float xl, float xu, float yl, float yu, float r) const {
+        return rect_prob_fallback_f(xl, xu, yl, yu, r);
+    }
+};
+template <int N> struct RectNodesF {
+    RhoNodes<N> n;
+    __device__ __forceinline__ float operator()(float xl, float xu, float yl, float yu, float) const {
+        return rect_prob_nodes_f<N>(n, xl, xu, yl, yu);
+    }
+};
+
+template <typename R, typename Rect>
+__device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect, R x, R y, R c, R s, R mx, R my, R ex, R ey,
+                                             R isx, R isy, R rho) {
+    const R hx = pr.hx, hy = pr.hy, rr = pr.rr;
+    R prob = 0;
+#pragma unroll 1
+    for (int km = 0; km < 3; ++km) {
+        const R sg = km == 0 ? (R)0 : (km == 1 ? (R)1 : (R)-1);
+        const R ux = mx + sg * ex, uy = my + sg * ey;
+#pragma unroll 1
+        for (int jb = 0; jb < 3; ++jb) {
+            const R sb = jb == 0 ? (R)0 : (jb == 1 ? (R)1 : (R)-1);
+            const R bx = x + sb * (rr * c), by = y + sb * (rr * s);
+            const R xl = ((bx - hx) - ux) * isx, xu = ((bx + hx) - ux) * isx;
+            const R yl = ((by - hy) - uy) * isy, yu = ((by + hy) - uy) * isy;
+            prob += rect(xl, xu, yl, yu, rho);
+        }
+    }
+    return prob / 3;
+}
+
+// `e` = ego sample (x, y, cos yaw, sin yaw), `g` = (mx, my, ex, ey), `p` = (1/sx, 1/sy, rho, class), `nd` = the
+// five node vectors of this (t, o) record.  All lanes of a warp share g, p and nd.
+__device__ __noinline__ double collision_prob(const Tab<double>& pr, Vec4<double> e, Vec4<double> g, Vec4<double> p,
+                                              const float4*) {
+    return nine_rectangles<double>(pr, RectDouble{}, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+}
+
+__device__ __noinline__ float collision_prob(const Tab<float>& pr, Vec4<float> e, Vec4<float> g, Vec4<float> p,
+                                             const float4* nd) {
+    const int cls = (int)p.w;  // warp-uniform: Gauss-Legendre node class of |rho| (pack_obstacles_kernel)
+    if (cls == RC_ZERO) {
+        RectNodesF<0> r;
+        return nine_rectangles<float>(pr, r, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+    }
+    if (cls == RC_FP64) {
+        atomicAdd(&g_fallback_evals, 1ull);
+        return nine_rectangles<float>(pr, RectFallbackF{}, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+    }
+    const float4 a = __ldg(nd), b = __ldg(nd + 1), c = __ldg(nd + 2), d = __ldg(nd + 3), f = __ldg(nd + 4);
+    // s[0..5] = a.xyzw b.xy | q[0..5] = b.zw c.xyzw | c[0..5] = d.xyzw f.xy
+    if (cls == RC_N4) {
+        RectNodesF<4> r;
+        r.n.s[0] = a.x; r.n.s[1] = a.y; r.n.s[2] = a.z; r.n.s[3] = a.w;
+        r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = c.x; r.n.q[3] = c.y;
+        r.n.c[0] = d.x; r.n.c[1] = d.y; r.n.c[2] = d.z; r.n.c[3] = d.w;
+        return nine_rectangles<float>(pr, r, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+    }
+    RectNodesF<6> r;
+    r.n.s[0] = a.x; r.n.s[1] = a.y; r.n.s[2] = a.z; r.n.s[3] = a.w; r.n.s[4] = b.x; r.n.s[5] = b.y;
+    r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = c.x; r.n.q[3] = c.y; r.n.q[4] = c.z; r.n.q[5] = c.w;
+    r.n.c[0] = d.x; r.n.c[1] = d.y; r.n.c[2] = d.z; r.n.c[3] = d.w; r.n.c[4] = f.x; r.n.c[5] = f.y;
+    return nine_rectangles<float>(pr, r, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+}
+
+// 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
+template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R mx, R my, R i00, R i01, R i11) {
+    const R dx = x - mx, dy = y - my;
+    const R m2 = dx * dx * i00 + dx * dy * i01 + dy * dy * i11;
+    return (R)1e-4 / sqrt_(m2);
+}
+
+// The 5 m gate (collision_probability.py:183-203) repeated in fp64 from the exact inputs: the fp32 path calls
+// this when its own distances are too close to the threshold to decide.  Ego sample `ti` is regenerated.
+__device__ __noinline__ bool gate_exact(const DevStep* stp, int pl, int id, int ti, int o, int t) {
+    const DevStep& st = *stp;
+    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+    const bool low = pm[PM_LOW] != 0.0;
+    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+    const TrajPoint tp = traj_point(q, low, gp, st.Tmax, ti, st.dt);
+    const double xe = tp.f[ETP_F_X], ye = tp.f[ETP_F_Y];
+    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+    const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+    const double len = 2 * st.obs_const[o * OC_COUNT + OC_HALFLEN];
+    const double fx = cos(y1) * len / 2, fy = sin(y1) * len / 2;
+    double ax = rp[0] - xe, ay = rp[1] - ye;
+    double m = sqrt(ax * ax + ay * ay);
+    ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
+    m = fmin(m, sqrt(ax * ax + ay * ay));
+    ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
+    m = fmin(m, sqrt(ax * ax + ay * ay));
+    return m > 5.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory plan of one CTA
+// ---------------------------------------------------------------------------------------------
+enum { MX_EGO_RISK = 0, MX_OBST_RISK, MX_EGO_ARG, MX_OBST_ARG, MX_COUNT };  // running maxima over time, [MX][O][32]
+enum { P1_V = 0, P1_D, P1_JL, P1_JQ, P1_TRAV, P1_COUNT };                   // phase-1 partial sums, [W][P1][32]
+enum { P3_SUM_E = 0, P3_SUM_O, P3_SUM_ABS, P3_RESP, P3_MM, P3_MAX_O, P3_COUNT };  // phase-3 partials, [W][P3][32]
+
+template <typename R> struct Smem {
+    using U = typename Enc<R>::U;
+    Vec4<R>* e0;    // [Ts][32] x, y, cos yaw, sin yaw
+    Vec2<R>* e1;    // [Ts][32] v, yaw (fp64) or its wrap count / kWrapFree (fp32)
+    double* p3;     // [kWarps][P3_COUNT][32]  -- aliases e0: the ego samples are dead once phase 2 is over
+    U* mx;          // [MX_COUNT][On][32]
+    double* p1;     // [kWarps][P1_COUNT][32]
+    int* ff;        // [kWarps][32] first failing curvature sample * 4 + kind
+    unsigned* queue;  // [(Ts-1) * On] (t << 16 | o) pairs that have a lane inside the gate's reach
+    __host__ __device__ static size_t ego_bytes(int Ts) {
+        const size_t e = 32 * (size_t)Ts * (sizeof(Vec4<R>) + sizeof(Vec2<R>));
+        const size_t p = (size_t)kWarps * P3_COUNT * 32 * sizeof(double);
+        return e > p ? e : p;
+    }
+    __host__ __device__ static size_t bytes(int Ts, int O) {
+        const size_t On = O > 0 ? O : 1;
+        return ego_bytes(Ts) + 32 * (MX_COUNT * On * sizeof(U) + kWarps * P1_COUNT * sizeof(double) + kWarps * sizeof(int)) +
+               sizeof(unsigned) * (size_t)(Ts - 1) * On;
+    }
+    __device__ __forceinline__ Smem(unsigned char* base, int Ts, int O) {
+        const size_t On = O > 0 ? O : 1;
+        e0 = reinterpret_cast<Vec4<R>*>(base);
+        e1 = reinterpret_cast<Vec2<R>*>(e0 + (size_t)Ts * 32);
+        p3 = reinterpret_cast<double*>(base);
+        p1 = reinterpret_cast<double*>(base + ego_bytes(Ts));
+        mx = reinterpret_cast<U*>(p1 + kWarps * P1_COUNT * 32);
+        ff = reinterpret_cast<int*>(mx + MX_COUNT * On * 32);
+        queue = reinterpret_cast<unsigned*>(ff + kWarps * 32);
+    }
+};
+
+struct LaneBest {
+    unsigned long long hi, lo;
+    double cost;
+    int level, scored;
+};
+
+__device__ __forceinline__ bool key_less(unsigned long long ahi, unsigned long long alo, unsigned long long bhi,
+                                         unsigned long long blo) {
+    return ahi < bhi || (ahi == bhi && alo < blo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// score_kernel
+// ---------------------------------------------------------------------------------------------
+template <typename R, int NT>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr, DevOut out,
+             BestRec* __restrict__ block_best, unsigned int* __restrict__ counters, BestRec* __restrict__ best_out,
+             const int* __restrict__ prof_nskip) {
+    using U = typename Enc<R>::U;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Ts = st.Tmax;
+    const int O = st.has_pred ? st.O : 0;
+    const int On = O > 0 ? O : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Smem<R> sm(smem_raw, Ts, O);
+    const int Cs = st.n_local;  // candidates scored by this call: profiles p_begin + shard_index + k * shard_count
+    const size_t Cp = out.c_stride;
+    const int n_tiles = (Cs + 31) / 32;
+    const Tile<R> tile(st.obs, st.O, st.Tp);
+    R* o_traj = reinterpret_cast<R*>(out.traj);
+    R* o_prob = reinterpret_cast<R*>(out.prob);
+    R* o_red = reinterpret_cast<R*>(out.red);
+    R* o_cost = reinterpret_cast<R*>(out.cost);
+    const bool mahal = pr.mahalanobis != 0;
+    const size_t mx_plane = (size_t)On * 32;
+
+    __shared__ Tab<R> tab;
+    __shared__ int s_tile, s_item, s_qn, s_qpos;
+    __shared__ BestRec wbest[kWarps];
+    __shared__ bool is_last;
+    if (tid == 0) fill_tab<R>(tab, pr);
+
+    // phase-2a items: obstacle groups of kOB x time segments, about three items per warp
+    const int n_groups = (O + kOB - 1) / kOB;
+    int n_seg = 1;
+    if (n_groups > 0) {
+        n_seg = (3 * kWarps + n_groups - 1) / n_groups;
+        const int max_seg = (Ts - 1 + 7) / 8;  // at least 8 samples per segment
+        n_seg = n_seg > max_seg ? max_seg : n_seg;
+        n_seg = n_seg < 1 ? 1 : n_seg;
+    }
+    const int seg_len = (Ts - 1 + n_seg - 1) / n_seg;
+    const int n_items = n_groups * n_seg;
+    const int chunk = (Ts + kWarps - 1) / kWarps;  // phase-1 time chunks
+
+    LaneBest lb{~0ull, ~0ull, 0.0, -1, 0};  // warp 0 only: best candidate this lane has finished
+
+    for (;;) {
+        if (tid == 0) {
+            s_tile = (int)atomicAdd(&counters[1], 1u);
+            s_item = 0;
+            s_qn = 0;
+            s_qpos = 0;
+        }
+        for (int i = tid; i < MX_COUNT * On * 32; i += kThreads) sm.mx[i] = Enc<R>::enc((R)-INFINITY);
+        __syncthreads();  // (a) tile index visible; previous tile fully consumed
+        const int tl = s_tile;
+        if (tl >= n_tiles) break;
+
+        // ---- this lane's candidate -----------------------------------------------------------------
+        const int cl = tl * 32 + lane;
+        const bool active = cl < Cs;
+        const int clc = active ? cl : Cs - 1;
+        const int kl = clc / st.nd, id = clc - kl * st.nd;
+        const int pl = st.shard_index + kl * st.shard_count;  // row of the profile table
+        const int c_dense = (st.p_begin + pl) * st.nd + id;
+        const double* gp = st.prof + (size_t)pl * PF_COUNT * Ts;
+        const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+        const double ds = pm[PM_DS];
+        const bool low = pm[PM_LOW] != 0.0;
+        const int T = (int)pm[PM_T];
+        const double dT = st.d_list[id];
+        const bool live = active && !(ds <= fabs(dT));  // frenet_functions.py:333-334
+        const int Tl = live ? T : 0;
+
+        // ---- phase 1: generation + transform, warps over time chunks --------------------------------
+        {
+            double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
+            int first_fail = 0x7fffffff;
+            const Poly5 q = lateral_poly(st, low, dT, pm[PM_TEND], ds);
+            const int ta = warp * chunk, tb = min(ta + chunk, Ts);
+            double px = 0, py = 0;
+            for (int t = ta; t < tb; ++t) {
+                if (t < Tl) {
+                    const TrajPoint tp = traj_point(q, low, gp, Ts, t, st.dt);
+                    if (o_traj) {
+#pragma unroll
+                        for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[((size_t)f * Ts + t) * Cp + cl] = (R)tp.f[f];
+                    }
+                    R w;
+                    if (sizeof(R) == 4)
+                        w = (tp.wrap == 0.0 && fabs(tp.f[ETP_F_YAW]) <= pr.wrapfree_yaw) ? (R)kWrapFree : (R)tp.wrap;
+                    else
+                        w = (R)tp.f[ETP_F_YAW];
+                    sm.e0[t * 32 + lane] = Vec4<R>{(R)tp.f[ETP_F_X], (R)tp.f[ETP_F_Y], (R)tp.cos_yaw, (R)tp.sin_yaw};
+                    sm.e1[t * 32 + lane] = Vec2<R>{(R)tp.f[ETP_F_V], w};
+                    sv += tp.f[ETP_F_V];
+                    sd += fabs(tp.f[ETP_F_D]);
+                    jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
+                    jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
+                    const int cf = curvature_fail(pr, tp.f[ETP_F_V], tp.f[ETP_F_CURV]);
+                    if (cf) first_fail = min(first_fail, t * 4 + cf);
+                    if (t > ta) {  // calc_trajectory_cost.py:739-757
+                        const double dx = px - tp.f[ETP_F_X], dy = py - tp.f[ETP_F_Y];
+                        trav += sqrt(dx * dx + dy * dy);
+                    }
+                    px = tp.f[ETP_F_X];
+                    py = tp.f[ETP_F_Y];
+                } else {
+                    sm.e0[t * 32 + lane] = Vec4<R>{(R)0, (R)0, (R)1, (R)0};
+                    sm.e1[t * 32 + lane] = Vec2<R>{(R)0, sizeof(R) == 4 ? (R)kWrapFree : (R)0};
+                    if (o_traj && active) {
+#pragma unroll
+                        for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[((size_t)f * Ts + t) * Cp + cl] = (R)0;
+                    }
+                }
+            }
+            if (tb < Tl && tb > ta) {  // segment that leaves this warp's chunk
+                const TrajPoint tp = traj_point(q, low, gp, Ts, tb, st.dt);
+                const double dx = px - tp.f[ETP_F_X], dy = py - tp.f[ETP_F_Y];
+                trav += sqrt(dx * dx + dy * dy);
+            }
+            double* p1 = sm.p1 + (size_t)warp * P1_COUNT * 32 + lane;
+            p1[P1_V * 32] = sv; p1[P1_D * 32] = sd; p1[P1_JL * 32] = jl; p1[P1_JQ * 32] = jq; p1[P1_TRAV * 32] = trav;
+            sm.ff[warp * 32 + lane] = first_fail;
+        }
+        __syncthreads();  // (b) ego samples complete
+
+        // ---- phase 2a: harm logits of every (t, o) sample, straight-line; samples inside the gate's reach are queued
+        // item = (kOB obstacles, time segment).  Sample t of the harm model pairs ego[t] with prediction[t]
+        // (harm_estimation.py:313-332); sample t of the probability pairs ego[t+1] with mean[t], covariance[t],
+        // orientation[t+1] (collision_probability.py:168-203).
+        if (O > 0) {
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&s_item, 1);
+                item = __shfl_sync(kFull, item, 0);
+                if (item >= n_items) break;
+                const int g = item % n_groups, seg = item / n_groups;
+                const int o0 = g * kOB;
+                const int t0 = seg * seg_len, t1 = min(t0 + seg_len, Ts - 1);
+                int n_pred[kOB];
+                bool prot[kOB];
+                R ke[kOB], ko[kOB], far2[kOB], hm_e[kOB], hm_o[kOB];
+#pragma unroll
+                for (int k = 0; k < kOB; ++k) {
+                    const int o = min(o0 + k, O - 1);
+                    const Vec4<R> cr = ldg4<R>(tile.C + o);
+                    n_pred[k] = (o0 + k < O) ? __ldg(st.pred_len + o) : 0;
+                    ke[k] = cr.x; ko[k] = cr.y; prot[k] = cr.z != (R)0;
+                    const R reach = (R)5.05 + (R)st.obs_const[o * OC_COUNT + OC_HALFLEN];
+                    far2[k] = reach * reach;
+                    hm_e[k] = hm_o[k] = (R)-INFINITY;
+                }
+                const Vec4<R>* gptr = tile.G + 2 * ((size_t)t0 * O + o0);
+                R* pptr = o_prob ? o_prob + ((size_t)t0 * O + o0) * Cp + cl : nullptr;
+                Vec4<R> c0 = sm.e0[t0 * 32 + lane];
+                Vec2<R> c1 = sm.e1[t0 * 32 + lane];
+                for (int t = t0; t < t1; ++t) {
+                    const Vec4<R> n0 = sm.e0[(t + 1) * 32 + lane];
+                    const Vec2<R> n1 = sm.e1[(t + 1) * 32 + lane];
+                    const bool has = t < Tl - 1;  // this lane's candidate has harm sample t (and ego sample t+1)
+                    const bool fast_ego = sizeof(R) == 4 && NT >= 0 && __all_sync(kFull, c1.y == (R)kWrapFree);
+#pragma unroll
+                    for (int k = 0; k < kOB; ++k) {
+                        if (o0 + k >= O) continue;  // uniform
+                        bool queued = false;
+                        if (t < n_pred[k]) {  // uniform: harm samples are t < min(T-1, Tp)   (harm_estimation.py:234)
+                            const Vec4<R> g0 = ldg4<R>(gptr + 2 * k), g1 = ldg4<R>(gptr + 2 * k + 1);
+                            R ae, ao;
+                            if (fast_ego)
+                                Logits<R, NT>::eval(pr, tab, true, c0, c1, g0, g1, prot[k], ke[k], ko[k], ae, ao);
+                            else
+                                Logits<R, NT>::eval(pr, tab, false, c0, c1, g0, g1, prot[k], ke[k], ko[k], ae, ao);
+                            if (has) {
+                                hm_e[k] = rmax_(hm_e[k], ae);
+                                hm_o[k] = rmax_(hm_o[k], ao);
+                            }
+                            if (t + 1 < n_pred[k]) {  // uniform
+                                // within 5 m + half length of the centre: the three-point gate has to look (phase 2b)
+                                const R dx = g0.x - n0.x, dy = g0.y - n0.y;
+                                const bool near = has && (mahal || !(dx * dx + dy * dy > far2[k]));
+                                if (__any_sync(kFull, near)) {
+                                    queued = true;
+                                    if (lane == 0) sm.queue[atomicAdd(&s_qn, 1)] = ((unsigned)t << 16) | (unsigned)(o0 + k);
+                                }
+                            }
+                        }
+                        if (pptr && active && !queued) pptr[(size_t)k * Cp] = (R)0;
+                    }
+                    c0 = n0;
+                    c1 = n1;
+                    gptr += 2 * O;
+                    if (pptr) pptr += (size_t)O * Cp;
+                }
+#pragma unroll
+                for (int k = 0; k < kOB; ++k) {
+                    if (o0 + k >= O) continue;
+                    U* m = sm.mx + (size_t)(o0 + k) * 32 + lane;
+                    if (n_seg == 1) {
+                        m[MX_EGO_ARG * mx_plane] = Enc<R>::enc(hm_e[k]);
+                        m[MX_OBST_ARG * mx_plane] = Enc<R>::enc(hm_o[k]);
+                    } else {
+                        atomicMax(m + MX_EGO_ARG * mx_plane, Enc<R>::enc(hm_e[k]));
+                        atomicMax(m + MX_OBST_ARG * mx_plane, Enc<R>::enc(hm_o[k]));
+                    }
+                }
+            }
+            __syncthreads();  // (b2) queue complete
+
+            // ---- phase 2b: queued samples: three-point gate, collision probability, risk ------------------
+            const int qn = s_qn;
+            for (;;) {
+                int e = 0;
+                if (lane == 0) e = atomicAdd(&s_qpos, 1);
+                e = __shfl_sync(kFull, e, 0);
+                if (e >= qn) break;
+                const unsigned ent = sm.queue[e];
+                const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
+                const size_t vi = (size_t)t * O + o;
+                const bool has = t < Tl - 1;
+                const Vec4<R> n0 = sm.e0[(t + 1) * 32 + lane];
+                const Vec4<R> g0 = ldg4<R>(tile.G + 2 * vi);
+                bool ungated = has;
+                if (!mahal) {
+                    const R x = n0.x, y = n0.y;
+                    R dx = g0.x - x, dy = g0.y - y;
+                    R d2 = dx * dx + dy * dy;
+                    dx = (g0.x + g0.z) - x; dy = (g0.y + g0.w) - y;
+                    d2 = fmin(d2, dx * dx + dy * dy);
+                    dx = (g0.x - g0.z) - x; dy = (g0.y - g0.w) - y;
+                    d2 = fmin(d2, dx * dx + dy * dy);
+                    if (sizeof(R) == 8) {
+                        ungated = has && !(sqrt_(d2) > (R)5.0);
+                    } else {
+                        ungated = has && !(d2 > (R)25.0);
+                        if (has && abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y)))
+                            ungated = !gate_exact(&st, pl, id, t + 1, o, t);  // fp32 cannot decide: repeat in fp64
+                    }
+                }
+                R prob = 0;
+                if (ungated) {
+                    const Vec4<R> c0 = sm.e0[t * 32 + lane];
+                    const Vec2<R> c1 = sm.e1[t * 32 + lane];
+                    const Vec4<R> g1 = ldg4<R>(tile.G + 2 * vi + 1);
+                    const Vec4<R> cr = ldg4<R>(tile.C + o);
+                    const bool prt = cr.z != (R)0;
+                    if (mahal) {
+                        const Vec4<R> p1 = ldg4<R>(tile.P + 2 * vi + 1);
+                        prob = inv_mahalanobis<R>(n0.x, n0.y, g0.x, g0.y, p1.x, p1.y, p1.z);
+                    } else {
+                        prob = collision_prob(tab, n0, g0, ldg4<R>(tile.P + 2 * vi), tile.N + kNodeVecs * vi);
+                    }
+                    R ae, ao;
+                    Logits<R, -1>::eval(pr, tab, false, c0, c1, g0, g1, prt, cr.x, cr.y, ae, ao);
+                    const R he = sigmoid_harm<R>(prt ? tab.lr_const : tab.lr1s_const, ae);
+                    const R ho = sigmoid_harm<R>(prt ? tab.lr_const : tab.neg_ped_const, ao);
+                    U* m = sm.mx + (size_t)o * 32 + lane;
+                    atomicMax(m + MX_EGO_RISK * mx_plane, Enc<R>::enc(he * prob));  // risk_costs.py:88-95
+                    atomicMax(m + MX_OBST_RISK * mx_plane, Enc<R>::enc(ho * prob));
+                }
+                if (o_prob && active) o_prob[vi * Cp + cl] = prob;
+            }
+        }
+        __syncthreads();  // (c) maxima complete, ego samples dead
+
+        // ---- phase 3a: per-obstacle reductions, warps over obstacles ----------------------------------
+        {
+            double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
+            for (int o = warp; o < O; o += kWarps) {
+                R re = 0, ro = 0, he = 0, ho = 0;
+                if (live) {
+                    const Vec4<R> cr = ldg4<R>(tile.C + o);
+                    const bool prt = cr.z != (R)0;
+                    const U* m = sm.mx + (size_t)o * 32 + lane;
+                    // every gated harm sample contributes harm * 0.0 to the maxima (risk_costs.py:88-101)
+                    re = rmax_(Enc<R>::dec(m[MX_EGO_RISK * mx_plane]), (R)0);
+                    ro = rmax_(Enc<R>::dec(m[MX_OBST_RISK * mx_plane]), (R)0);
+                    he = sigmoid_harm<R>(prt ? tab.lr_const : tab.lr1s_const, Enc<R>::dec(m[MX_EGO_ARG * mx_plane]));
+                    ho = sigmoid_harm<R>(prt ? tab.lr_const : tab.neg_ped_const, Enc<R>::dec(m[MX_OBST_ARG * mx_plane]));
+                    sum_e += (double)re;
+                    sum_o += (double)ro;
+                    sum_abs += fabs((double)re - (double)ro);
+                    resp -= st.obs_const[o * OC_COUNT + OC_RESP] * (double)ro;       // risk_costs.py:250-253
+                    mm = fmax(mm, (double)he * ((double)re < 10e-10 ? 1.0 : 0.0));  // risk_costs.py:205-206 (Q3)
+                    mm = fmax(mm, (double)ho * ((double)ro < 10e-10 ? 1.0 : 0.0));
+                    max_o = fmax(max_o, (double)ro);
+                }
+                if (o_red && active) {
+                    o_red[((size_t)ETP_R_EGO_RISK * O + o) * Cp + cl] = re;
+                    o_red[((size_t)ETP_R_OBST_RISK * O + o) * Cp + cl] = ro;
+                    o_red[((size_t)ETP_R_EGO_HARM * O + o) * Cp + cl] = he;
+                    o_red[((size_t)ETP_R_OBST_HARM * O + o) * Cp + cl] = ho;
+                }
+            }
+            double* p3 = sm.p3 + (size_t)warp * P3_COUNT * 32 + lane;
+            p3[P3_SUM_E * 32] = sum_e; p3[P3_SUM_O * 32] = sum_o; p3[P3_SUM_ABS * 32] = sum_abs;
+            p3[P3_RESP * 32] = resp; p3[P3_MM * 32] = mm; p3[P3_MAX_O * 32] = max_o;
+        }
+        __syncthreads();  // (d) partials complete
+
+        // ---- phase 3b: principles, cost, level, key (warp 0, one candidate per lane) --------------------
+        if (warp == 0) {
+            double c[ETP_NUM_COST];
+#pragma unroll
+            for (int k = 0; k < ETP_NUM_COST; ++k) c[k] = 0.0;
+            int level = ETP_LEVEL_SKIPPED, reason = ETP_REASON_NONE;
+            if (live) {
+                double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
+                double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
+                int first_fail = 0x7fffffff;
+                for (int w = 0; w < kWarps; ++w) {
+                    const double* p1 = sm.p1 + (size_t)w * P1_COUNT * 32 + lane;
+                    const double* p3 = sm.p3 + (size_t)w * P3_COUNT * 32 + lane;
+                    sv += p1[P1_V * 32]; sd += p1[P1_D * 32]; jl += p1[P1_JL * 32]; jq += p1[P1_JQ * 32];
+                    trav += p1[P1_TRAV * 32];
+                    sum_e += p3[P3_SUM_E * 32]; sum_o += p3[P3_SUM_O * 32]; sum_abs += p3[P3_SUM_ABS * 32];
+                    resp += p3[P3_RESP * 32];
+                    mm = fmax(mm, p3[P3_MM * 32]);
+                    max_o = fmax(max_o, p3[P3_MAX_O * 32]);
+                    first_fail = min(first_fail, sm.ff[w * 32 + lane]);
+                }
+                const bool vel_ok = pm[PM_VEL_OK] != 0.0;
+                const double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
+                const int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
+                if (O > 0) {
+                    c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
+                    c[ETP_C_EQUALITY] = sum_abs / (double)O;                  // :176-178
+                    c[ETP_C_MAXIMIN] = pow(fmax(mm, bd), 10.0);               // :208
+                    c[ETP_C_EGO] = sum_e + bd;                                // :226
+                    c[ETP_C_RESPONSIBILITY] = resp;
+                }
+                const bool risk_in_cost = pr.w[ETP_W_RISK_COST] > 0.0 && st.has_pred && pr.planner_mode == ETP_MODE_RISK;
+                if (risk_in_cost)  // calc_trajectory_cost.py:130-136
+                    c[ETP_C_RISK_TOTAL] = pr.w[ETP_W_BAYES] * c[ETP_C_BAYES] + pr.w[ETP_W_EQUALITY] * c[ETP_C_EQUALITY] +
+                                          pr.w[ETP_W_MAXIMIN] * c[ETP_C_MAXIMIN] +
+                                          pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES] * c[ETP_C_RESPONSIBILITY] +
+                                          pr.w[ETP_W_EGO] * c[ETP_C_EGO];
+                const double mean_v = sv / (double)T;
+                switch (st.vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
+                    case 0: c[ETP_C_VELOCITY] = fabs(st.vel_target - mean_v); break;
+                    case 1: c[ETP_C_VELOCITY] = 30.0 - mean_v; break;
+                    case 2: c[ETP_C_VELOCITY] = mean_v; break;
+                    default: c[ETP_C_VELOCITY] = 0.0;
+                }
+                c[ETP_C_DIST_TO_GLOBAL_PATH] = sd / (double)T;  // :726-736
+                c[ETP_C_LON_JERK] = jl / (double)T;             // :418-435
+                c[ETP_C_LAT_JERK] = jq / (double)T;
+                c[ETP_C_TRAVELLED_DIST] = trav;
+                c[ETP_C_FACTOR] = st.factor;
+                // validity level (validity_checks.py:31-122)
+                const int cf = first_fail == 0x7fffffff ? 0 : (first_fail & 3);
+                if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
+                else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
+                else if (ext == 1) { level = 1; reason = ETP_REASON_COLLISION; }
+                else if (st.has_pred ? (bd != 0.0) : (ext == 2)) { level = 2; reason = ETP_REASON_BOUNDARIES; }
+                else if (pr.planner_mode == ETP_MODE_RISK && st.has_pred && O > 0 &&
+                         (sum_e > pr.max_risk || max_o > pr.max_risk)) { level = 3; reason = ETP_REASON_MAX_RISK; }
+                else { level = 10; reason = ETP_REASON_NONE; }
+                // weighted sum (calc_trajectory_cost.py:321-346); risk-only weights below level 10 if requested
+                const bool risk_only = level < 10 && pr.multi_cost;
+                double cost = 0.0;
+                if (risk_in_cost) cost += pr.w[ETP_W_RISK_COST] * c[ETP_C_RISK_TOTAL];
+                if (pr.w[ETP_W_LON_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LON_JERK]) * c[ETP_C_LON_JERK];
+                if (pr.w[ETP_W_LAT_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LAT_JERK]) * c[ETP_C_LAT_JERK];
+                if (pr.w[ETP_W_VELOCITY] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_VELOCITY]) * c[ETP_C_VELOCITY];
+                if (pr.w[ETP_W_DIST_TO_GLOBAL_PATH] > 0.0)
+                    cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GLOBAL_PATH]) * c[ETP_C_DIST_TO_GLOBAL_PATH];
+                if (pr.w[ETP_W_TRAVELLED_DIST] > 0.0)
+                    cost += (risk_only ? 0.0 : pr.w[ETP_W_TRAVELLED_DIST]) * c[ETP_C_TRAVELLED_DIST];
+                c[ETP_C_TOTAL] = st.factor * cost;
+                const unsigned long long hi = make_key_hi(level, c[ETP_C_TOTAL]);
+                const unsigned long long lo = (unsigned long long)c_dense;
+                if (key_less(hi, lo, lb.hi, lb.lo)) { lb.hi = hi; lb.lo = lo; lb.cost = c[ETP_C_TOTAL]; lb.level = level; }
+                lb.scored += 1;
+            }
+            if (active) {
+                if (o_cost) {
+#pragma unroll
+                    for (int k = 0; k < ETP_NUM_COST; ++k) o_cost[(size_t)k * Cp + cl] = (R)c[k];
+                }
+                if (out.level) out.level[cl] = (uint8_t)level;
+                if (out.reason) out.reason[cl] = (uint8_t)reason;
+            }
+        }
+        // no barrier here: warp 0 reads only p1 / p3 / ff; p1 / ff are next written after barrier (a) of the next
+        // tile, p3 (aliasing the ego samples) after barrier (a) as well
+    }
+
+    // ---- block arg-min, then grid arg-min by the last block to finish ---------------------------
+    if (warp == 0) {
+        unsigned long long hi = lb.hi, lo = lb.lo;
+        double cst = lb.cost;
+        int lvl = lb.level, scored = lb.scored;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ohi = __shfl_xor_sync(kFull, hi, o), olo = __shfl_xor_sync(kFull, lo, o);
+            const double oc = __shfl_xor_sync(kFull, cst, o);
+            const int ol = __shfl_xor_sync(kFull, lvl, o);
+            scored += __shfl_xor_sync(kFull, scored, o);
+            if (key_less(ohi, olo, hi, lo)) { hi = ohi; lo = olo; cst = oc; lvl = ol; }
+        }
+        if (lane == 0) {
+            BestRec b;
+            b.key_hi = hi; b.key_lo = lo; b.cost = cst; b.level = lvl; b.n_scored = scored;
+            b.index = hi == ~0ull ? -1 : (int)lo;
+            b.list_index = -1;
+            block_best[blockIdx.x] = b;
+            __threadfence();
+            const unsigned done = atomicAdd(&counters[0], 1u);
+            is_last = (done == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        unsigned long long hi = ~0ull, lo = ~0ull;
+        double cst = 0.0;
+        int lvl = -1, scored = 0;
+        for (int b = tid; b < (int)gridDim.x; b += kThreads) {
+            const volatile BestRec* r = block_best + b;
+            const unsigned long long bhi = r->key_hi, blo = r->key_lo;
+            scored += r->n_scored;
+            if (key_less(bhi, blo, hi, lo)) { hi = bhi; lo = blo; cst = r->cost; lvl = r->level; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ohi = __shfl_xor_sync(kFull, hi, o), olo = __shfl_xor_sync(kFull, lo, o);
+            const double oc = __shfl_xor_sync(kFull, cst, o);
+            const int ol = __shfl_xor_sync(kFull, lvl, o);
+            scored += __shfl_xor_sync(kFull, scored, o);
+            if (key_less(ohi, olo, hi, lo)) { hi = ohi; lo = olo; cst = oc; lvl = ol; }
+        }
+        if (lane == 0) {
+            wbest[warp].key_hi = hi; wbest[warp].key_lo = lo; wbest[warp].cost = cst; wbest[warp].level = lvl;
+            wbest[warp].n_scored = scored;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            BestRec b = wbest[0];
+            for (int w = 1; w < kWarps; ++w) {
+                const int n = b.n_scored + wbest[w].n_scored;
+                if (key_less(wbest[w].key_hi, wbest[w].key_lo, b.key_hi, b.key_lo)) b = wbest[w];
+                b.n_scored = n;
+            }
+            b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
+            b.list_index = -1;
+            if (b.index >= 0) {
+                // rank among non-skipped candidates of this range = position in the reference's fp_list
+                const int pb = b.index / st.nd, idb = b.index % st.nd;
+                int li = 0;
+                for (int pp = st.p_begin; pp < pb; ++pp) li += st.nd - prof_nskip[pp - st.p_begin];
+                const double dsb = st.prof_meta[(size_t)(pb - st.p_begin) * PM_COUNT + PM_DS];
+                for (int id = 0; id < idb; ++id) li += (dsb <= fabs(st.d_list[id])) ? 0 : 1;
+                b.list_index = li;
+            }
+            *best_out = b;
+            counters[0] = 0;  // re-arm both counters for the next launch
+            counters[1] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launcher
+// ---------------------------------------------------------------------------------------------
+template <typename R, int NT>
+static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
+                                  unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
+                                  cudaStream_t stream) {
+    const int O = st.has_pred ? st.O : 0;
+    const size_t smem = Smem<R>::bytes(st.Tmax, O);
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT>, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    // persistent grid: every SM fully occupied, never more CTAs than there are tiles
+    const long long tiles = ((long long)st.n_local + 31) / 32;
+    long long grid = (long long)num_sms * per_sm;
+    if (grid > tiles) grid = tiles;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    if (grid < 1) grid = 1;
+    *grid_out = (int)grid;
+    score_kernel<R, NT><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
+                         unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
+                         cudaStream_t stream) {
+#define ETP_LAUNCH(R, NT) launch_score_t<R, NT>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream)
+    if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1);
+    switch (pr.n_thr) {  // the reference's models: LR1S (0 thresholds), LR4S / LR4A (2), LR12S / LR12A (6)
+        case 0: return ETP_LAUNCH(float, 0);
+        case 2: return ETP_LAUNCH(float, 2);
+        case 6: return ETP_LAUNCH(float, 6);
+        default: return ETP_LAUNCH(float, -1);
+    }
+#undef ETP_LAUNCH
+}
+
+size_t score_smem_bytes(int precision, int Tmax, int O) {
+    return precision == ETP_PRECISION_FP64 ? Smem<double>::bytes(Tmax, O) : Smem<float>::bytes(Tmax, O);
+}
+
+cudaError_t read_debug_counters(unsigned long long* out, int n) {
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_fallback_evals, sizeof(v));
+    if (n > 0) out[0] = v;
+    return e;
+}
+
+}  // namespace etp

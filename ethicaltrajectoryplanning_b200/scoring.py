@@ -174,11 +174,20 @@ class ScoreResult:
     _ctx: object = field(default=None, repr=False)
 
     def numpy(self):
+        """Host copies in the logical (candidate-major) layout: traj [13][C][T], prob [C][T-1][O],
+        red [4][C][O], cost [13][C], level [C], reason [C].  On the device every real-valued tensor is
+        candidate-minor (include/etp_b200.h, etp_out); the transposes below are views."""
         out = {}
         self._ctx.stream.synchronize()
         for k in ("traj", "prob", "red", "cost", "level", "reason"):
             v = getattr(self, k)
             out[k] = None if v is None else v.detach().cpu().numpy()
+        if out["traj"] is not None:
+            out["traj"] = out["traj"].transpose(0, 2, 1)
+        if out["prob"] is not None:
+            out["prob"] = out["prob"].transpose(2, 0, 1)
+        if out["red"] is not None:
+            out["red"] = out["red"].transpose(0, 2, 1)
         return out
 
     def best_trajectory(self):
@@ -312,13 +321,16 @@ class ScoringContext:
         return s, keep, n
 
     def allocate_outputs(self, Cs, Tmax, O, traj=True, prob=True, red=True, cost=True):
+        """Device tensors of one call, candidate-minor with the candidate stride padded to a multiple of 32
+        (etp_out in include/etp_b200.h).  The returned tensors are views of the first ``Cs`` columns."""
         torch = self.torch
         kw = dict(device=self.device, dtype=self.dtype)
+        Cp = max(32, (Cs + 31) // 32 * 32)
         bufs = dict(
-            traj=torch.empty((_abi.NUM_FIELDS, Cs, Tmax), **kw) if traj else None,
-            prob=torch.empty((Cs, Tmax - 1, O), **kw) if prob else None,  # obstacle fastest
-            red=torch.empty((_abi.NUM_RED, Cs, O), **kw) if red else None,
-            cost=torch.empty((_abi.NUM_COST, Cs), **kw) if cost else None,
+            traj=torch.empty((_abi.NUM_FIELDS, Tmax, Cp), **kw)[..., :Cs] if traj else None,
+            prob=torch.empty((Tmax - 1, O, Cp), **kw)[..., :Cs] if prob else None,
+            red=torch.empty((_abi.NUM_RED, O, Cp), **kw)[..., :Cs] if red else None,
+            cost=torch.empty((_abi.NUM_COST, Cp), **kw)[..., :Cs] if cost else None,
             level=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
             reason=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
         )
@@ -326,6 +338,7 @@ class ScoringContext:
             if t is not None:
                 t.record_stream(self.stream)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        bufs["c_stride"] = Cp
         return bufs
 
     def launch(self, s, bufs=None):
@@ -335,6 +348,7 @@ class ScoringContext:
             return
         o = _abi.Out()
         o.precision = self.precision
+        o.c_stride = int(bufs.get("c_stride", 0))
         for k in ("traj", "prob", "red", "cost", "level", "reason"):
             t = bufs.get(k)
             setattr(o, k, None if t is None else C.c_void_p(t.data_ptr()))
@@ -420,6 +434,6 @@ class ScoringContext:
         res = ScoreResult(n_dense=step.n_dense, c_begin=s.c_begin, c_end=s.c_end, Tmax=Tmax, n_samples=n,
                           obstacle_ids=list(self.obstacle_ids), best=best, _ctx=self)
         if materialize:
-            for k, v in bufs.items():
-                setattr(res, k, v)
+            for k in ("traj", "prob", "red", "cost", "level", "reason"):
+                setattr(res, k, bufs.get(k))
         return res

@@ -151,15 +151,19 @@ typedef struct {
 } etp_step;
 
 /* Caller-allocated device tensors for the scored candidates.  Cs = (number of profiles of this shard) * nd;
- * local row cl = k * nd + id is dense candidate (p_begin + shard_index + k * shard_count) * nd + id. */
+ * local column cl = k * nd + id is dense candidate (p_begin + shard_index + k * shard_count) * nd + id.
+ * Every real-valued tensor is CANDIDATE-MINOR (structure of arrays over candidates): element [..][cl] lives at
+ * row * c_stride + cl, so the 32 candidates a warp scores together are one contiguous 128-byte line per row.
+ * c_stride >= Cs; a multiple of 32 keeps every line aligned (c_stride = 0 means Cs). */
 typedef struct {
     int32_t precision;   /* ETP_PRECISION_*; element type of traj/prob/red/cost */
-    void* traj;          /* [ETP_NUM_FIELDS][Cs][Tmax]   (entries past a candidate's T are 0) */
-    void* prob;          /* [Cs][Tmax-1][O]              collision probability per timestep (obstacle fastest) */
-    void* red;           /* [ETP_NUM_RED][Cs][O] */
-    void* cost;          /* [ETP_NUM_COST][Cs] */
+    void* traj;          /* [ETP_NUM_FIELDS][Tmax][c_stride]  (entries past a candidate's T are 0) */
+    void* prob;          /* [Tmax-1][O][c_stride]             collision probability per timestep and obstacle */
+    void* red;           /* [ETP_NUM_RED][O][c_stride] */
+    void* cost;          /* [ETP_NUM_COST][c_stride] */
     uint8_t* level;      /* [Cs] validity level or ETP_LEVEL_SKIPPED */
     uint8_t* reason;     /* [Cs] ETP_REASON_* */
+    int64_t c_stride;    /* elements between consecutive rows of the tensors above */
 } etp_out;
 
 /* Selected candidate: sort by (highest non-empty level, cost, generation order)
