@@ -10,7 +10,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libetp_b200.so")
+# ETP_B200_LIB selects another build of the same sources (kernel tuning experiments); default: the in-tree library
+LIB_PATH = os.environ.get("ETP_B200_LIB") or os.path.join(HERE, "libetp_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_score.cu", "etp_abi.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_launch.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "etp_b200.h")]

@@ -19,6 +19,24 @@
 
 namespace etp {
 
+// single-instruction MUFU forms (flush-to-zero, no range fix-up code around them): arguments below -126 give
+// exactly 0, which is what the tails want
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ double phi_d(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
 
 __constant__ double kGLw[3][10] = {
@@ -99,7 +117,7 @@ __device__ __forceinline__ double rect_prob(double xl, double xu, double yl, dou
 // rectangles.
 __device__ __forceinline__ float erfc_f(float x) {
     const float z = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.5f, z, 1.0f));
+    const float t = rcp_ftz(fmaf(0.5f, z, 1.0f));
     float p = 0.17087277f;
     p = fmaf(p, t, -0.82215223f);
     p = fmaf(p, t, 1.48851587f);
@@ -112,7 +130,7 @@ __device__ __forceinline__ float erfc_f(float x) {
     p = fmaf(p, t, -1.26551223f);
     const float zz = z * z;
     const float e = fmaf(z, z, -zz);  // exact rounding residual of z*z
-    float r = t * __expf(p - zz);
+    float r = t * ex2_ftz(1.4426950408889634f * (p - zz));
     r = fmaf(-r, e, r);
     return x >= 0.0f ? r : 2.0f - r;
 }
@@ -166,10 +184,10 @@ __device__ __forceinline__ float rho_correction_f(const RhoNodes<N>& n, float xl
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const float s = n.s[i], q = n.q[i];
-        const float e_uu = exp2f(q * fmaf(s, puu, -huu));
-        const float e_lu = exp2f(q * fmaf(s, plu, -hlu));
-        const float e_ul = exp2f(q * fmaf(s, pul, -hul));
-        const float e_ll = exp2f(q * fmaf(s, pll, -hll));
+        const float e_uu = ex2_ftz(q * fmaf(s, puu, -huu));
+        const float e_lu = ex2_ftz(q * fmaf(s, plu, -hlu));
+        const float e_ul = ex2_ftz(q * fmaf(s, pul, -hul));
+        const float e_ll = ex2_ftz(q * fmaf(s, pll, -hll));
         acc = fmaf(n.c[i], (e_uu - e_lu) - (e_ul - e_ll), acc);
     }
     return acc;

@@ -29,7 +29,10 @@ namespace etp {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMinBlocks = 2;  // resident CTAs per SM the register budget is sized for
+#ifndef ETP_MIN_BLOCKS
+#define ETP_MIN_BLOCKS 2
+#endif
+constexpr int kMinBlocks = ETP_MIN_BLOCKS;  // resident CTAs per SM the register budget is sized for
 constexpr int kOB = 4;  // obstacles of one phase-2 item (register blocking: one ego load serves kOB obstacles)
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -72,7 +75,7 @@ template <> __device__ __forceinline__ Vec4<double> ldg4<double>(const Vec4<doub
 }
 template <typename R> __device__ __forceinline__ R rmax_(R a, R b) { return a > b ? a : b; }
 // square root of the fp32 streaming path: MUFU.RSQ based (2 ulp); the fp64 check mode stays IEEE
-__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrt_ftz(x) : 0.0f; }
 __device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
 __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
