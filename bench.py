@@ -318,7 +318,7 @@ def run_gpu_arm(args, step, workload_cfg):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps, "selected_index": e2e_best["index"]},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(workload_cfg["workload"]), "peak_source": peak_src,
                          "kernel": "etp::score_kernel<float>", "kernel_ms": kernel_ms, "profile_stage_ms": float(np.mean(p_ms)),

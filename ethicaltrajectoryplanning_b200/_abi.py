@@ -79,6 +79,7 @@ class Step(C.Structure):
         ("cost_factor", C.c_double),
         ("ext_level", _bp),
         ("bd_harm", _dp),
+        ("cost_factor_list", _dp),
         ("c_begin", C.c_int32), ("c_end", C.c_int32),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32),
     ]
@@ -90,6 +91,17 @@ class Out(C.Structure):
         ("traj", C.c_void_p), ("prob", C.c_void_p), ("red", C.c_void_p), ("cost", C.c_void_p),
         ("level", C.c_void_p), ("reason", C.c_void_p),
         ("c_stride", C.c_int64),
+        ("harm", C.c_void_p),
+    ]
+
+
+class Trajectories(C.Structure):
+    _fields_ = [
+        ("n_traj", C.c_int32), ("t_max", C.c_int32),
+        ("n_samples", _ip), ("fields", _dp),
+        ("velocity_cost_mode", C.c_int32),
+        ("velocity_target", C.c_double), ("cost_factor", C.c_double),
+        ("ext_level", _bp), ("bd_harm", _dp), ("cost_factor_list", _dp),
     ]
 
 
@@ -111,6 +123,8 @@ SYMBOLS = {
     "etp_set_spline": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int]),
     "etp_set_obstacles": (C.c_int, [C.c_void_p, C.POINTER(Obstacles), C.c_int]),
     "etp_plan_step": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Out)]),
+    "etp_score_trajectories": (C.c_int, [C.c_void_p, C.POINTER(Trajectories), C.POINTER(Out)]),
+    "etp_principle_costs": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, C.c_double, C.c_double, C.c_double, _dp]),
     "etp_tmax": (C.c_int, [C.POINTER(Step)]),
     "etp_get_best": (C.c_int, [C.c_void_p, C.POINTER(Best)]),
     "etp_get_trajectory": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),

@@ -71,8 +71,9 @@ struct etp_ctx {
     DevBuf o_pos, o_cov, o_yaw, o_vel, o_len, o_mass, o_plen, o_prot, o_resp, o_tile, o_const;
     int O = 0, Tp = 0, has_pred = 0;
     // step
-    DevBuf grids, ext_level, bd_harm, prof, prof_meta, nskip;
-    DevBuf block_best, counters, best_dev, traj_dev, traj_n;
+    DevBuf grids, ext_level, bd_harm, factor_list, prof, prof_meta, nskip;
+    DevBuf block_best, counters, best_dev, traj_dev, traj_n, given, given_T, prin;
+    bool last_given = false;
     PinnedBuf stage, best_host, traj_host;
     DevStep st{};
     int last_grid = 0;
@@ -169,9 +170,9 @@ int etp_destroy(etp_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
-                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->grids, &c->ext_level, &c->bd_harm,
+                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list,
                       &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
-                      &c->traj_n};
+                      &c->traj_n, &c->given, &c->given_T, &c->prin};
     for (DevBuf* b : bufs) b->release();
     c->stage.release();
     c->best_host.release();
@@ -366,6 +367,11 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
         if ((r = stage_to_device(c, c->bd_harm.p, s->bd_harm, sizeof(double) * (size_t)dense))) return r;
         st.bd_harm = c->bd_harm.as<double>();
     }
+    if (s->cost_factor_list) {
+        ETP_CUDA(c, c->factor_list.reserve(sizeof(double) * (size_t)dense));
+        if ((r = stage_to_device(c, c->factor_list.p, s->cost_factor_list, sizeof(double) * (size_t)dense))) return r;
+        st.factor_list = c->factor_list.as<double>();
+    }
     if ((r = end_staging(c))) return r;
 
     unsigned char* g = c->grids.as<unsigned char>();
@@ -401,7 +407,7 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     DevOut dout{};
     if (out) {
         dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
-        dout.level = out->level; dout.reason = out->reason;
+        dout.level = out->level; dout.reason = out->reason; dout.harm = out->harm;
         dout.c_stride = out->c_stride > 0 ? (size_t)out->c_stride : (size_t)st.n_local;
         if (dout.c_stride < (size_t)st.n_local)
             ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.c_stride=%lld is smaller than the %d candidates of this call",
@@ -420,6 +426,106 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
                              c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, &c->last_grid, c->stream));
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     c->have_step = true;
+    c->last_given = false;
+    return ETP_OK;
+}
+
+int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out* out) {
+    if (!c || !g) return ETP_ERR_INVALID;
+    if (!c->have_params || !c->have_obs)
+        ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params / etp_set_obstacles must be called before etp_score_trajectories");
+    if (g->n_traj < 1 || g->t_max < 2 || !g->n_samples || !g->fields) ETP_FAIL(c, ETP_ERR_INVALID, "empty trajectory list");
+    if (g->t_max > 256) ETP_FAIL(c, ETP_ERR_INVALID, "more than 256 samples per trajectory");
+    for (int i = 0; i < g->n_traj; ++i)
+        if (g->n_samples[i] < 2 || g->n_samples[i] > g->t_max) ETP_FAIL(c, ETP_ERR_INVALID, "n_samples[%d] outside [2, t_max]", i);
+    if (out && out->precision != c->precision)
+        ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.precision differs from the precision given to etp_set_obstacles");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    int r = begin_staging(c);
+    if (r) return r;
+    const size_t n = (size_t)g->n_traj, nf = sizeof(double) * ETP_NUM_FIELDS * g->t_max * n;
+    ETP_CUDA(c, c->given.reserve(nf));
+    ETP_CUDA(c, c->given_T.reserve(sizeof(int) * n));
+    if ((r = stage_to_device(c, c->given.p, g->fields, nf))) return r;
+    if ((r = stage_to_device(c, c->given_T.p, g->n_samples, sizeof(int) * n))) return r;
+    DevStep& st = c->st;
+    st = DevStep{};
+    if (g->ext_level) {
+        ETP_CUDA(c, c->ext_level.reserve(n));
+        if ((r = stage_to_device(c, c->ext_level.p, g->ext_level, n))) return r;
+        st.ext_level = c->ext_level.as<uint8_t>();
+    }
+    if (g->bd_harm) {
+        ETP_CUDA(c, c->bd_harm.reserve(sizeof(double) * n));
+        if ((r = stage_to_device(c, c->bd_harm.p, g->bd_harm, sizeof(double) * n))) return r;
+        st.bd_harm = c->bd_harm.as<double>();
+    }
+    if (g->cost_factor_list) {
+        ETP_CUDA(c, c->factor_list.reserve(sizeof(double) * n));
+        if ((r = stage_to_device(c, c->factor_list.p, g->cost_factor_list, sizeof(double) * n))) return r;
+        st.factor_list = c->factor_list.as<double>();
+    }
+    if ((r = end_staging(c))) return r;
+    st.given = c->given.as<double>(); st.given_T = c->given_T.as<int>(); st.given_stride = g->n_traj;
+    st.nv = 1; st.nt = 1; st.nd = g->n_traj; st.Tmax = g->t_max;
+    st.c_begin = 0; st.c_end = g->n_traj; st.p_begin = 0; st.p_end = 1;
+    st.shard_count = 1; st.shard_index = 0; st.n_local = g->n_traj;
+    st.vel_mode = g->velocity_cost_mode; st.vel_target = g->velocity_target; st.factor = g->cost_factor;
+    st.has_pred = c->has_pred; st.O = c->O; st.Tp = c->Tp;
+    st.obs = c->o_tile.p; st.obs_const = c->o_const.as<double>(); st.pred_len = c->o_plen.as<int>();
+    st.raw_pos = c->o_pos.as<double>(); st.raw_yaw = c->o_yaw.as<double>();
+    DevOut dout{};
+    if (out) {
+        dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
+        dout.level = out->level; dout.reason = out->reason; dout.harm = out->harm;
+        dout.c_stride = out->c_stride > 0 ? (size_t)out->c_stride : (size_t)st.n_local;
+        if (dout.c_stride < (size_t)st.n_local) ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.c_stride too small");
+    }
+    {
+        const size_t smem = score_smem_bytes(c->precision, st.Tmax, c->has_pred ? c->O : 0);
+        if (smem > (size_t)c->smem_optin)
+            ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "t_max=%d samples x %d obstacles need %zu bytes of shared memory per CTA (limit %d)",
+                     st.Tmax, c->O, smem, c->smem_optin);
+    }
+    ETP_CUDA(c, c->nskip.reserve(sizeof(int)));
+    if (c->timing) {
+        ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    }
+    ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, c->block_best.as<BestRec>(), c->counters.as<unsigned>(),
+                             c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, &c->last_grid, c->stream));
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    c->have_step = true;
+    c->last_given = true;
+    return ETP_OK;
+}
+
+int etp_principle_costs(etp_ctx* c, int n, const double* ego_risk, const double* obst_risk, const double* ego_harm,
+                        const double* obst_harm, const int32_t* responsibility, double boundary_harm, double maximin_eps,
+                        double maximin_scale, double* out) {
+    if (!c || !out || n < 0) return ETP_ERR_INVALID;
+    if (n > 0 && (!ego_risk || !obst_risk || !ego_harm || !obst_harm || !responsibility)) return ETP_ERR_INVALID;
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    int r = begin_staging(c);
+    if (r) return r;
+    const size_t nb = sizeof(double) * (size_t)n;
+    ETP_CUDA(c, c->prin.reserve(4 * nb + sizeof(int) * (size_t)n + 8 * sizeof(double) + 64));
+    double* vals = c->prin.as<double>();
+    double* res = vals + 4 * (size_t)n;
+    int* resp = reinterpret_cast<int*>(res + 8);
+    if (n > 0) {
+        if ((r = stage_to_device(c, vals, ego_risk, nb))) return r;
+        if ((r = stage_to_device(c, vals + n, obst_risk, nb))) return r;
+        if ((r = stage_to_device(c, vals + 2 * (size_t)n, ego_harm, nb))) return r;
+        if ((r = stage_to_device(c, vals + 3 * (size_t)n, obst_harm, nb))) return r;
+        if ((r = stage_to_device(c, resp, responsibility, sizeof(int) * (size_t)n))) return r;
+    }
+    if ((r = end_staging(c))) return r;
+    ETP_CUDA(c, launch_principles(n, vals, resp, boundary_harm, maximin_eps, maximin_scale, res, c->stream));
+    ETP_CUDA(c, c->traj_host.reserve(5 * sizeof(double)));
+    ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, res, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(out, c->traj_host.p, 5 * sizeof(double));
     return ETP_OK;
 }
 
@@ -441,6 +547,7 @@ int etp_get_trajectory(etp_ctx* c, int index, double* fields, int* n_samples) {
     if (!c || !fields) return ETP_ERR_INVALID;
     if (!c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "no planning step has run on this context");
     const DevStep& st = c->st;
+    if (c->last_given) ETP_FAIL(c, ETP_ERR_STATE, "the last call scored caller-provided trajectories: the caller holds them");
     if (index < st.c_begin || index >= st.c_end) ETP_FAIL(c, ETP_ERR_INVALID, "candidate %d outside the last scored range", index);
     ETP_CUDA(c, cudaSetDevice(c->device));
     const size_t bytes = sizeof(double) * ETP_NUM_FIELDS * st.Tmax;

@@ -87,6 +87,7 @@ struct DevStep {
     double vel_target, factor;
     const uint8_t* ext_level;  // device copy, indexed by dense candidate, or null
     const double* bd_harm;     // device copy, indexed by dense candidate, or null
+    const double* factor_list; // device copy, indexed by dense candidate, or null (then `factor`)
     // spline tables
     const double* knots;
     const double* cx;
@@ -104,6 +105,10 @@ struct DevStep {
     // raw fp64 copies for the exact gate re-check of the fp32 path
     const double* raw_pos;   // [O][Tp][2]
     const double* raw_yaw;   // [O][Tp]
+    // caller-provided trajectories instead of generated candidates (etp_score_trajectories), or null
+    const double* given;     // [ETP_NUM_FIELDS][Tmax][given_stride], fp64
+    const int* given_T;      // [n_local] samples per trajectory
+    int given_stride;
 };
 
 struct DevOut {
@@ -113,6 +118,7 @@ struct DevOut {
     void* cost;
     uint8_t* level;
     uint8_t* reason;
+    void* harm;
     size_t c_stride;  // elements between rows of the candidate-minor tensors
 };
 
@@ -237,6 +243,17 @@ __device__ __forceinline__ TrajPoint traj_point(const Poly5& q, bool low, const 
     r.f[ETP_F_CURV] = (((dpp + (krd * d + kr * dp) * z) * ((cd * cd) / om)) + kr) * (cd / om);
     r.cos_yaw = cd * cr - sd * sr;
     r.sin_yaw = sd * cr + cd * sr;
+    r.wrap = ceil((r.f[ETP_F_YAW] - 3.14159265358979323846) / 6.28318530717958647692);
+    return r;
+}
+
+// One sample of a caller-provided trajectory (etp_score_trajectories): `g` points at field 0, sample 0 of the
+// trajectory, rows are `ts` samples x `stride` trajectories.
+__device__ __forceinline__ TrajPoint given_point(const double* g, int ts, int stride, int t) {
+    TrajPoint r;
+#pragma unroll
+    for (int f = 0; f < ETP_NUM_FIELDS; ++f) r.f[f] = g[((size_t)f * ts + t) * stride];
+    sincos(r.f[ETP_F_YAW], &r.sin_yaw, &r.cos_yaw);
     r.wrap = ceil((r.f[ETP_F_YAW] - 3.14159265358979323846) / 6.28318530717958647692);
     return r;
 }

@@ -141,7 +141,7 @@ __device__ __forceinline__ double np_gradient(const double* f, const double* s, 
     return a * f[i - 1] + b * f[i] + c * f[i + 1];
 }
 
-__global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr) {
+__global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, int* __restrict__ nskip) {
     extern __shared__ double sm[];
     const int Tmax = st.Tmax;
     double* s_s = sm;
@@ -233,16 +233,18 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr) 
         pm[PM_VEL_OK] = (double)vel_ok;
         pm[PM_TEND] = Te;
     }
-}
-
-// number of skipped lateral targets per profile (frenet_functions.py:333-334)
-__global__ void profile_skip_kernel(DevStep st, int* __restrict__ nskip) {
-    const int pl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pl >= st.p_end - st.p_begin) return;
-    const double ds = st.prof_meta[(size_t)pl * PM_COUNT + PM_DS];
-    int n = 0;
-    for (int id = 0; id < st.nd; ++id) n += (ds <= fabs(st.d_list[id])) ? 1 : 0;
-    nskip[pl] = n;
+    // number of skipped lateral targets of this profile (frenet_functions.py:333-334): rank of the winner in fp_list
+    {
+        const double ds = s_s[T - 1] - s_s[0];
+        int n = 0;
+        for (int id = tid; id < st.nd; id += blockDim.x) n += (ds <= fabs(st.d_list[id])) ? 1 : 0;
+        __shared__ int s_n;
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        if (n) atomicAdd(&s_n, n);
+        __syncthreads();
+        if (tid == 0) nskip[blockIdx.x] = s_n;
+    }
 }
 
 // one candidate, all 13 fields in fp64 -> [ETP_NUM_FIELDS][Tmax]; requires its profile in st.prof
@@ -263,6 +265,40 @@ __global__ void trajectory_kernel(DevStep st, int c_dense, double* __restrict__ 
         }
     }
     if (threadIdx.x == 0) *n_out = T;
+}
+
+// principle costs of one trajectory from per-obstacle maxima (risk_costs.py:128-255); one warp
+__global__ void principles_kernel(int n, const double* __restrict__ v, const int* __restrict__ resp, double bd, double eps,
+                                  double scale, double* __restrict__ out) {
+    const int lane = threadIdx.x;
+    double sum_e = 0, sum_o = 0, sum_abs = 0, rs = 0, mm = -INFINITY;
+    for (int o = lane; o < n; o += 32) {
+        const double re = v[o], ro = v[n + o], he = v[2 * n + o], ho = v[3 * n + o];
+        sum_e += re;
+        sum_o += ro;
+        sum_abs += fabs(re - ro);
+        rs -= (double)resp[o] * ro;
+        mm = fmax(mm, he * (re < eps ? 1.0 : 0.0));  // risk_costs.py:205-206 (Q3)
+        mm = fmax(mm, ho * (ro < eps ? 1.0 : 0.0));
+    }
+    for (int k = 16; k > 0; k >>= 1) {
+        sum_e += __shfl_xor_sync(kFull, sum_e, k);
+        sum_o += __shfl_xor_sync(kFull, sum_o, k);
+        sum_abs += __shfl_xor_sync(kFull, sum_abs, k);
+        rs += __shfl_xor_sync(kFull, rs, k);
+        mm = fmax(mm, __shfl_xor_sync(kFull, mm, k));
+    }
+    if (lane == 0) {
+        if (n == 0) {  // risk_costs.py:145-146,173-174,199-200,222-223
+            for (int i = 0; i < 5; ++i) out[i] = 0.0;
+        } else {
+            out[0] = (sum_e + sum_o + bd) / (double)(n * 2);
+            out[1] = sum_abs / (double)n;
+            out[2] = pow(fmax(mm, bd), scale);
+            out[3] = rs;
+            out[4] = sum_e + bd;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -288,8 +324,13 @@ cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, 
     const int n_prof = st.p_end - st.p_begin;
     if (n_prof <= 0) return cudaSuccess;
     const size_t smem = sizeof(double) * 7 * st.Tmax;
-    profile_kernel<<<n_prof, 128, smem, stream>>>(st, pr);
-    profile_skip_kernel<<<(n_prof + 127) / 128, 128, 0, stream>>>(st, nskip);
+    profile_kernel<<<n_prof, 128, smem, stream>>>(st, pr, nskip);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_principles(int n, const double* vals, const int* resp, double bd, double eps, double scale, double* out5,
+                              cudaStream_t stream) {
+    principles_kernel<<<1, 32, 0, stream>>>(n, vals, resp, bd, eps, scale, out5);
     return cudaGetLastError();
 }
 

@@ -340,14 +340,21 @@ template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R m
 
 // The 5 m gate (collision_probability.py:183-203) repeated in fp64 from the exact inputs: the fp32 path calls
 // this when its own distances are too close to the threshold to decide.  Ego sample `ti` is regenerated.
-__device__ __noinline__ bool gate_exact(const DevStep* stp, int pl, int id, int ti, int o, int t) {
+__device__ __noinline__ bool gate_exact(const DevStep* stp, bool given, int pl, int id, int ti, int o, int t) {
     const DevStep& st = *stp;
-    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
-    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
-    const bool low = pm[PM_LOW] != 0.0;
-    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
-    const TrajPoint tp = traj_point(q, low, gp, st.Tmax, ti, st.dt);
-    const double xe = tp.f[ETP_F_X], ye = tp.f[ETP_F_Y];
+    double xe, ye;
+    if (given) {
+        xe = st.given[((size_t)ETP_F_X * st.Tmax + ti) * st.given_stride + pl];
+        ye = st.given[((size_t)ETP_F_Y * st.Tmax + ti) * st.given_stride + pl];
+    } else {
+        const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+        const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+        const bool low = pm[PM_LOW] != 0.0;
+        const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+        const TrajPoint tp = traj_point(q, low, gp, st.Tmax, ti, st.dt);
+        xe = tp.f[ETP_F_X];
+        ye = tp.f[ETP_F_Y];
+    }
     const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
     const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
     const double len = 2 * st.obs_const[o * OC_COUNT + OC_HALFLEN];
@@ -413,7 +420,7 @@ __device__ __forceinline__ bool key_less(unsigned long long ahi, unsigned long l
 // ---------------------------------------------------------------------------------------------
 // score_kernel
 // ---------------------------------------------------------------------------------------------
-template <typename R, int NT>
+template <typename R, int NT, bool kGiven>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr, DevOut out,
              BestRec* __restrict__ block_best, unsigned int* __restrict__ counters, BestRec* __restrict__ best_out,
@@ -433,6 +440,8 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     R* o_prob = reinterpret_cast<R*>(out.prob);
     R* o_red = reinterpret_cast<R*>(out.red);
     R* o_cost = reinterpret_cast<R*>(out.cost);
+    R* o_harm = reinterpret_cast<R*>(out.harm);
+    const size_t harm_plane = (size_t)(Ts - 1) * O * Cp;
     const bool mahal = pr.mahalanobis != 0;
     const size_t mx_plane = (size_t)On * 32;
 
@@ -473,28 +482,31 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         const int cl = tl * 32 + lane;
         const bool active = cl < Cs;
         const int clc = active ? cl : Cs - 1;
-        const int kl = clc / st.nd, id = clc - kl * st.nd;
-        const int pl = st.shard_index + kl * st.shard_count;  // row of the profile table
-        const int c_dense = (st.p_begin + pl) * st.nd + id;
-        const double* gp = st.prof + (size_t)pl * PF_COUNT * Ts;
+        // generated candidates: row of the profile table and lateral target; given trajectories: none of that
+        const int kl = kGiven ? 0 : clc / st.nd, id = kGiven ? 0 : clc - kl * st.nd;
+        const int pl = kGiven ? clc : st.shard_index + kl * st.shard_count;
+        const int c_dense = kGiven ? clc : (st.p_begin + pl) * st.nd + id;
+        const double* gp = kGiven ? st.given + clc : st.prof + (size_t)pl * PF_COUNT * Ts;
         const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
-        const double ds = pm[PM_DS];
-        const bool low = pm[PM_LOW] != 0.0;
-        const int T = (int)pm[PM_T];
-        const double dT = st.d_list[id];
-        const bool live = active && !(ds <= fabs(dT));  // frenet_functions.py:333-334
+        const double ds = kGiven ? 0.0 : pm[PM_DS];
+        const bool low = kGiven ? false : pm[PM_LOW] != 0.0;
+        const int T = kGiven ? st.given_T[clc] : (int)pm[PM_T];
+        const double dT = kGiven ? 0.0 : st.d_list[id];
+        const bool live = active && (kGiven || !(ds <= fabs(dT)));  // frenet_functions.py:333-334
         const int Tl = live ? T : 0;
 
         // ---- phase 1: generation + transform, warps over time chunks --------------------------------
         {
             double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
             int first_fail = 0x7fffffff;
-            const Poly5 q = lateral_poly(st, low, dT, pm[PM_TEND], ds);
+            Poly5 q{};
+            if (!kGiven) q = lateral_poly(st, low, dT, pm[PM_TEND], ds);
             const int ta = warp * chunk, tb = min(ta + chunk, Ts);
             double px = 0, py = 0;
             for (int t = ta; t < tb; ++t) {
                 if (t < Tl) {
-                    const TrajPoint tp = traj_point(q, low, gp, Ts, t, st.dt);
+                    const TrajPoint tp = kGiven ? given_point(gp, Ts, st.given_stride, t) : traj_point(q, low, gp, Ts, t, st.dt);
+                    if (kGiven && !(fabs(tp.f[ETP_F_S_D]) <= pr.v_max)) first_fail = -1;  // validity_checks.py:158
                     if (o_traj) {
 #pragma unroll
                         for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[((size_t)f * Ts + t) * Cp + cl] = (R)tp.f[f];
@@ -511,7 +523,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
                     jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
                     const int cf = curvature_fail(pr, tp.f[ETP_F_V], tp.f[ETP_F_CURV]);
-                    if (cf) first_fail = min(first_fail, t * 4 + cf);
+                    if (cf) first_fail = min(first_fail, t * 4 + cf);  // a velocity failure (-1) stays the minimum
                     if (t > ta) {  // calc_trajectory_cost.py:739-757
                         const double dx = px - tp.f[ETP_F_X], dy = py - tp.f[ETP_F_Y];
                         trav += sqrt(dx * dx + dy * dy);
@@ -528,7 +540,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 }
             }
             if (tb < Tl && tb > ta) {  // segment that leaves this warp's chunk
-                const TrajPoint tp = traj_point(q, low, gp, Ts, tb, st.dt);
+                const TrajPoint tp = kGiven ? given_point(gp, Ts, st.given_stride, tb) : traj_point(q, low, gp, Ts, tb, st.dt);
                 const double dx = px - tp.f[ETP_F_X], dy = py - tp.f[ETP_F_Y];
                 trav += sqrt(dx * dx + dy * dy);
             }
@@ -566,6 +578,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 }
                 const Vec4<R>* gptr = tile.G + 2 * ((size_t)t0 * O + o0);
                 R* pptr = o_prob ? o_prob + ((size_t)t0 * O + o0) * Cp + cl : nullptr;
+                R* hptr = o_harm ? o_harm + ((size_t)t0 * O + o0) * Cp + cl : nullptr;
                 Vec4<R> c0 = sm.e0[t0 * 32 + lane];
                 Vec2<R> c1 = sm.e1[t0 * 32 + lane];
                 for (int t = t0; t < t1; ++t) {
@@ -588,6 +601,11 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                                 hm_e[k] = rmax_(hm_e[k], ae);
                                 hm_o[k] = rmax_(hm_o[k], ao);
                             }
+                            if (hptr && active) {  // optional per-sample harm (get_harm, harm_estimation.py:202)
+                                hptr[(size_t)k * Cp] = has ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.lr1s_const, ae) : (R)0;
+                                hptr[harm_plane + (size_t)k * Cp] =
+                                    has ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.neg_ped_const, ao) : (R)0;
+                            }
                             if (t + 1 < n_pred[k]) {  // uniform
                                 // within 5 m + half length of the centre: the three-point gate has to look (phase 2b)
                                 const R dx = g0.x - n0.x, dy = g0.y - n0.y;
@@ -598,12 +616,17 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                                 }
                             }
                         }
+                        else if (hptr && active) {
+                            hptr[(size_t)k * Cp] = (R)0;
+                            hptr[harm_plane + (size_t)k * Cp] = (R)0;
+                        }
                         if (pptr && active && !queued) pptr[(size_t)k * Cp] = (R)0;
                     }
                     c0 = n0;
                     c1 = n1;
                     gptr += 2 * O;
                     if (pptr) pptr += (size_t)O * Cp;
+                    if (hptr) hptr += (size_t)O * Cp;
                 }
 #pragma unroll
                 for (int k = 0; k < kOB; ++k) {
@@ -647,7 +670,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     } else {
                         ungated = has && !(d2 > (R)25.0);
                         if (has && abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y)))
-                            ungated = !gate_exact(&st, pl, id, t + 1, o, t);  // fp32 cannot decide: repeat in fp64
+                            ungated = !gate_exact(&st, kGiven, pl, id, t + 1, o, t);  // fp32 cannot decide: repeat in fp64
                     }
                 }
                 R prob = 0;
@@ -732,7 +755,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     max_o = fmax(max_o, p3[P3_MAX_O * 32]);
                     first_fail = min(first_fail, sm.ff[w * 32 + lane]);
                 }
-                const bool vel_ok = pm[PM_VEL_OK] != 0.0;
+                const bool vel_ok = kGiven ? first_fail >= 0 : pm[PM_VEL_OK] != 0.0;
                 const double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
                 const int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
                 if (O > 0) {
@@ -759,9 +782,10 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 c[ETP_C_LON_JERK] = jl / (double)T;             // :418-435
                 c[ETP_C_LAT_JERK] = jq / (double)T;
                 c[ETP_C_TRAVELLED_DIST] = trav;
-                c[ETP_C_FACTOR] = st.factor;
+                const double factor = st.factor_list ? st.factor_list[c_dense] : st.factor;
+                c[ETP_C_FACTOR] = factor;
                 // validity level (validity_checks.py:31-122)
-                const int cf = first_fail == 0x7fffffff ? 0 : (first_fail & 3);
+                const int cf = (first_fail == 0x7fffffff || first_fail < 0) ? 0 : (first_fail & 3);
                 if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
                 else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
                 else if (ext == 1) { level = 1; reason = ETP_REASON_COLLISION; }
@@ -780,7 +804,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GLOBAL_PATH]) * c[ETP_C_DIST_TO_GLOBAL_PATH];
                 if (pr.w[ETP_W_TRAVELLED_DIST] > 0.0)
                     cost += (risk_only ? 0.0 : pr.w[ETP_W_TRAVELLED_DIST]) * c[ETP_C_TRAVELLED_DIST];
-                c[ETP_C_TOTAL] = st.factor * cost;
+                c[ETP_C_TOTAL] = factor * cost;
                 const unsigned long long hi = make_key_hi(level, c[ETP_C_TOTAL]);
                 const unsigned long long lo = (unsigned long long)c_dense;
                 if (key_less(hi, lo, lb.hi, lb.lo)) { lb.hi = hi; lb.lo = lo; lb.cost = c[ETP_C_TOTAL]; lb.level = level; }
@@ -857,7 +881,9 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             }
             b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
             b.list_index = -1;
-            if (b.index >= 0) {
+            if (kGiven) {
+                b.list_index = b.index;
+            } else if (b.index >= 0) {
                 // rank among non-skipped candidates of this range = position in the reference's fp_list
                 const int pb = b.index / st.nd, idb = b.index % st.nd;
                 int li = 0;
@@ -876,16 +902,16 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 // ---------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------
-template <typename R, int NT>
+template <typename R, int NT, bool kGiven>
 static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
                                   unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                                   cudaStream_t stream) {
     const int O = st.has_pred ? st.O : 0;
     const size_t smem = Smem<R>::bytes(st.Tmax, O);
-    cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT, kGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT>, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT, kGiven>, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     // persistent grid: every SM fully occupied, never more CTAs than there are tiles
@@ -895,14 +921,19 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
-    score_kernel<R, NT><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
+    score_kernel<R, NT, kGiven><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
     return cudaGetLastError();
 }
 
 cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
                          unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                          cudaStream_t stream) {
-#define ETP_LAUNCH(R, NT) launch_score_t<R, NT>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream)
+#define ETP_LAUNCH(R, NT) launch_score_t<R, NT, false>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream)
+    if (st.given) {  // caller-provided trajectories: the API-compatibility path, generic tables only
+        if (precision == ETP_PRECISION_FP64)
+            return launch_score_t<double, -1, true>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
+        return launch_score_t<float, -1, true>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
+    }
     if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1);
     switch (pr.n_thr) {  // the reference's models: LR1S (0 thresholds), LR4S / LR4A (2), LR12S / LR12A (6)
         case 0: return ETP_LAUNCH(float, 0);

@@ -1,0 +1,102 @@
+"""Drop-in for ``planner/Frenet/utils/calc_trajectory_cost.py``: ``calc_trajectory_costs`` (:33-346).
+
+The cost terms of the scored path (risk principles, velocity, distance to the global path, jerks, travelled
+distance) come from the fused kernel.  The goal logic behind ``get_cost_factor`` (:349-415) and the target of
+``velocity_costs`` (:438-519) is CommonRoad / pycrcc geometry and stays on the host: ``cost_context`` evaluates the
+parts that need no geometry and takes the rest from the planning problem object when it provides them.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .... import _abi, dropin
+from ....configs import RISK_COSTS_KEY
+
+COST = {name: i for i, name in enumerate(_abi.COST_NAMES)}
+
+
+def cost_context(fp_list, ego_state, planning_problem, scenario, dt, goal_area):
+    """(velocity_cost_mode, velocity_target, cost_factor) of one planning step.
+
+    * a planning problem that carries ``velocity_cost_mode / velocity_target / cost_factor`` (a pre-evaluated
+      context, e.g. from the caller's own CommonRoad code) is used as is; ``cost_factor`` may be per trajectory;
+    * otherwise the branch structure of velocity_costs (:438-519) is followed as far as it needs no geometry:
+      goal states without position -> 0.0 (mode 3); remaining time <= 0 -> ``30 - mean v`` (mode 1); else
+      ``|avg_dist / remaining_time - mean v|`` (mode 0).  Goal-area containment tests need pycrcc and default to
+      "not reached", cost factor 1.0.
+    """
+    if planning_problem is None:
+        return 3, 0.0, 1.0
+    if hasattr(planning_problem, "velocity_cost_mode"):
+        return (int(planning_problem.velocity_cost_mode), float(getattr(planning_problem, "velocity_target", 0.0)),
+                getattr(planning_problem, "cost_factor", 1.0))
+    goal = planning_problem.goal
+    state0 = goal.state_list[0]
+    centers = []
+    if getattr(goal, "lanelets_of_goal_position", None) is not None:
+        for lanelet_id in goal.lanelets_of_goal_position[0]:
+            lanelet = scenario.lanelet_network.find_lanelet_by_id(lanelet_id)
+            centers.append(lanelet.center_vertices[int(len(lanelet.center_vertices) / 2.0)])
+    elif hasattr(state0, "position"):
+        if hasattr(state0.position, "center"):
+            centers.append(state0.position.center)
+    else:
+        return 3, 0.0, 1.0
+    pos = np.asarray(ego_state.position, dtype=np.float64)
+    avg_dist = float(np.mean([np.linalg.norm(np.asarray(c, dtype=np.float64) - pos) for c in centers]))
+    remaining = (state0.time_step.end - ego_state.time_step) * dt  # calc_remaining_time_steps with t = 0
+    if remaining > 0.0:
+        return 0, avg_dist / remaining, 1.0
+    return 1, 0.0, 1.0
+
+
+def build_cost_dict(traj, c, params, validity_level, predictions):
+    """``(cost, cost_dict)`` of calc_trajectory_costs (:321-346) from the cost rows ``c`` of one candidate."""
+    weights, modes = params["weights"], params["modes"]
+    cost_dict = {}
+    if weights["risk_cost"] > 0.0 and predictions is not None:  # :103-148
+        traj.risk_dict = {"bayes": c[COST["bayes"]], "equality": c[COST["equality"]], "maximin": c[COST["maximin"]],
+                          "responsibility": c[COST["responsibility"]], "ego": c[COST["ego"]],
+                          "total": c[COST["risk_cost"]]}
+        cost_dict["risk_cost"] = traj.risk_dict["total"]
+    else:
+        traj.risk_dict = {}
+    for key in ("lon_jerk", "lat_jerk", "velocity", "dist_to_global_path", "travelled_dist"):  # :269-298
+        if weights[key] > 0.0:
+            cost_dict[key] = c[COST[key]]
+    if validity_level < 10 and modes["multiple_cost_functions"]:  # :322-327
+        curr_weights = {k: (weights[k] if k in RISK_COSTS_KEY else 0) for k in weights}
+    else:
+        curr_weights = weights
+    total = float(c[COST["total"]])
+    return total, {"risk_cost_dict": traj.risk_dict, "weights": curr_weights, "factor": float(c[COST["factor"]]),
+                   "unweighted_cost": {k: float(v) for k, v in cost_dict.items()}, "total_cost": total}
+
+
+def calc_trajectory_costs(traj, global_path, planning_problem, ego_state, validity_level, scenario, params: dict,
+                          ego_id: int, dt: float, predictions: dict, goal_area, vehicle_params,
+                          sensor_radius: float = 30.0, exec_timer=None, mode=None, reach_set=None, obstacle_types=None):
+    """Total cost of one frenet trajectory: ``(cost, cost_dict)`` (calc_trajectory_cost.py:33-346)."""
+    w = params["weights"]
+    if w.get("responsibility", 0.0) > 0.0:
+        raise NotImplementedError("reach-set responsibility is outside the scored path")
+    for k in ("visible_area", "dist_to_goal_pos", "dist_to_lane_center"):
+        if w.get(k, 0.0) > 0.0:
+            raise NotImplementedError(f"cost term {k!r} needs lanelet / sensor geometry and stays on the host")
+    types = dropin.obstacle_type_names(scenario, predictions, obstacle_types) if predictions else {}
+    vel_mode, vel_target, factor = cost_context([traj], ego_state, planning_problem, scenario, dt, goal_area)
+    bd = np.array([float(getattr(traj, "bd_harm", 0) or 0)])
+    r = dropin.score_trajectories([traj], predictions, types, vehicle_params, params, mode=(mode or "risk"), bd_harm=bd,
+                                  velocity_cost_mode=vel_mode, velocity_target=vel_target,
+                                  cost_factor=np.broadcast_to(factor, (1,)))
+    c = r.cost[:, 0].copy()
+    own_risk_only = int(r.level[0]) < 10 and bool(params["modes"]["multiple_cost_functions"])
+    want_risk_only = validity_level < 10 and bool(params["modes"]["multiple_cost_functions"])
+    if own_risk_only != want_risk_only:
+        # the caller costs this trajectory under another list level than its own (:322-327): re-weight the device's
+        # unweighted terms accordingly
+        risk = w["risk_cost"] * c[COST["risk_cost"]] if (w["risk_cost"] > 0.0 and predictions is not None) else 0.0
+        rest = 0.0 if want_risk_only else sum(
+            w[k] * c[COST[k]] for k in ("lon_jerk", "lat_jerk", "velocity", "dist_to_global_path", "travelled_dist") if w[k] > 0.0)
+        c[COST["total"]] = c[COST["factor"]] * (risk + rest)
+    return build_cost_dict(traj, c, params, validity_level, predictions)

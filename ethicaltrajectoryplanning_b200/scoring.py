@@ -314,6 +314,10 @@ class ScoringContext:
             b = np.ascontiguousarray(step.bd_harm, dtype=np.float64)
             s.bd_harm = _dptr(b)
             keep.append(b)
+        if getattr(step, "cost_factor_list", None) is not None:
+            fl = np.ascontiguousarray(step.cost_factor_list, dtype=np.float64)
+            s.cost_factor_list = _dptr(fl)
+            keep.append(fl)
         dense = len(v) * len(t) * len(d)
         s.c_begin = 0 if c_begin is None else int(c_begin)
         s.c_end = dense if c_end is None else int(c_end)

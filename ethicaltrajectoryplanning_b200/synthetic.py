@@ -130,6 +130,7 @@ class PlanningStep:
     cost_factor: float = 1.0
     ext_level: Optional[np.ndarray] = None   # per dense candidate: 1 collision, 2 boundary, else 10
     bd_harm: Optional[np.ndarray] = None     # per dense candidate boundary harm
+    cost_factor_list: Optional[np.ndarray] = None  # per dense candidate get_cost_factor result (overrides cost_factor)
 
     @property
     def n_dense(self):

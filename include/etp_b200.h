@@ -145,6 +145,8 @@ typedef struct {
     double cost_factor;             /* get_cost_factor (calc_trajectory_cost.py:349-415) */
     const uint8_t* ext_level;       /* optional [nv*nt*nd]: 1 collision, 2 boundary, else pass (pycrcc results) */
     const double* bd_harm;          /* optional [nv*nt*nd]: boundary harm (risk_costs.py:104-123) */
+    const double* cost_factor_list; /* optional [nv*nt*nd]: per-candidate get_cost_factor (goal reached / reached in time /
+                                       reached and left, calc_trajectory_cost.py:349-415); overrides cost_factor */
     int32_t c_begin, c_end;         /* dense candidate range of this call; must be aligned to whole (v,t) profiles */
     int32_t shard_index, shard_count; /* multi-GPU: score only the profiles p with (p - p_begin) % shard_count == shard_index
                                        (interleaved, so slow and fast profiles spread evenly); shard_count 0 or 1 = all */
@@ -164,7 +166,28 @@ typedef struct {
     uint8_t* level;      /* [Cs] validity level or ETP_LEVEL_SKIPPED */
     uint8_t* reason;     /* [Cs] ETP_REASON_* */
     int64_t c_stride;    /* elements between consecutive rows of the tensors above */
+    void* harm;          /* optional [2][Tmax-1][O][c_stride]: ego / obstacle harm per sample, 0 past min(T-1, Tp)
+                            (the arrays get_harm returns, harm_estimation.py:202-338) */
 } etp_out;
+
+/*
+ * Caller-provided trajectories (the reference's per-trajectory entry points: calc_risk risk_costs.py:16,
+ * get_collision_probability_fast collision_probability.py:136, get_harm harm_estimation.py:202, check_validity
+ * validity_checks.py:31, calc_trajectory_costs calc_trajectory_cost.py:33, and sort_frenet_trajectories on an
+ * arbitrary fp_list).  HOST memory, candidate-minor like the outputs.
+ */
+typedef struct {
+    int32_t n_traj;                 /* C */
+    int32_t t_max;                  /* samples of the longest trajectory (>= 2) */
+    const int32_t* n_samples;       /* [C] samples of each trajectory (>= 2) */
+    const double* fields;           /* [ETP_NUM_FIELDS][t_max][C]: FrenetTrajectory attributes, rows ETP_F_* */
+    int32_t velocity_cost_mode;     /* as in etp_step */
+    double velocity_target;
+    double cost_factor;
+    const uint8_t* ext_level;       /* optional [C] */
+    const double* bd_harm;          /* optional [C] */
+    const double* cost_factor_list; /* optional [C], overrides cost_factor */
+} etp_trajectories;
 
 /* Selected candidate: sort by (highest non-empty level, cost, generation order)
  * (frenet_functions.py:562-570, frenet_planner.py:457,555-558). */
@@ -200,6 +223,19 @@ int etp_set_obstacles(etp_ctx* ctx, const etp_obstacles* obstacles, int precisio
 /* calc_frenet_trajectories + sort_frenet_trajectories + selection for the dense range of `step`:
  * frenet_planner.py:326-340, 433-457, 555-558.  `out` may be NULL (argmin-only mode). */
 int etp_plan_step(etp_ctx* ctx, const etp_step* step, const etp_out* out);
+
+/* Scores caller-provided trajectories with the same fused kernel (generation replaced by loads); the output tensors have
+ * Tmax = t_max and Cs = n_traj; etp_get_best returns the arg-min over them (index = position in the list). */
+int etp_score_trajectories(etp_ctx* ctx, const etp_trajectories* trajectories, const etp_out* out);
+
+/* The five principle costs from per-obstacle maxima (host arrays of n values; n = 0 gives zeros):
+ * get_bayesian_costs / get_equality_costs / get_maximin_costs / get_ego_costs / get_responsibility_cost
+ * (risk_costs.py:128-255); responsibility[] are the action-space flags (responsibility.py:57-89).
+ * maximin_eps / maximin_scale are get_maximin_costs' eps and scale_factor arguments (defaults 10e-10 and 10).
+ * out[5] = bayes, equality, maximin, responsibility, ego. */
+int etp_principle_costs(etp_ctx* ctx, int n, const double* ego_risk, const double* obst_risk, const double* ego_harm,
+                        const double* obst_harm, const int32_t* responsibility, double boundary_harm, double maximin_eps,
+                        double maximin_scale, double* out);
 
 /* number of timesteps Tmax the output tensors must be strided with for `step` */
 int etp_tmax(const etp_step* step);

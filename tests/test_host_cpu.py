@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_struct_sizes_match_the_header_layout():
     assert ctypes.sizeof(_abi.Best) == 40
     assert ctypes.sizeof(_abi.Params) == 8 * 14 + 4 * 4 + 8 + 8 * 8 + 8 * 9 * 2 + 8 * 6 + 8 * 8
-    assert ctypes.sizeof(_abi.Out) == 8 + 6 * 8 + 8
+    assert ctypes.sizeof(_abi.Out) == 8 + 6 * 8 + 8 + 8
 
 
 def test_missing_library_fails_loudly(monkeypatch):
@@ -134,3 +134,104 @@ def test_pack_predictions_layout_and_ragged_lengths():
     assert pk["mass"][3] == 75.0 and pk["mass"][0] == pytest.approx(-1333.5 + 526.9 * (5.5 * 2.3) ** 0.8)
     with pytest.raises(ValueError):
         pack_predictions(s.predictions, {k: "BUILDING" for k in s.predictions})
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# call surface of the reference: same module paths, names and leading parameters
+# ---------------------------------------------------------------------------------------------------------------
+REFERENCE_SURFACE = {
+    # module (under ethicaltrajectoryplanning_b200 / EthicalTrajectoryPlanning): {function: parameters of the reference}
+    "planner.Frenet.utils.frenet_functions": {
+        # frenet_functions.py:207-221
+        "calc_frenet_trajectories": ["c_s", "c_s_d", "c_s_dd", "c_d", "c_d_d", "c_d_dd", "d_list", "t_list", "v_list", "dt",
+                                     "csp", "v_thr", "exec_timer"],
+        # frenet_functions.py:477-495
+        "sort_frenet_trajectories": ["ego_state", "fp_list", "global_path", "predictions", "mode", "params", "planning_problem",
+                                     "scenario", "vehicle_params", "ego_id", "dt", "sensor_radius", "road_boundary",
+                                     "collision_checker", "goal_area", "exec_timer", "reach_set"],
+        # frenet_functions.py:760-768
+        "get_v_list": ["v_min", "v_max", "v_cur", "v_goal_min", "v_goal_max", "n_samples", "mode"],
+    },
+    "planner.Frenet.utils.validity_checks": {
+        # validity_checks.py:31-42
+        "check_validity": ["ft", "ego_state", "scenario", "vehicle_params", "risk_params", "mode", "road_boundary",
+                           "collision_checker", "predictions", "exec_timer"],
+    },
+    "planner.Frenet.utils.calc_trajectory_cost": {
+        # calc_trajectory_cost.py:33-50
+        "calc_trajectory_costs": ["traj", "global_path", "planning_problem", "ego_state", "validity_level", "scenario", "params",
+                                  "ego_id", "dt", "predictions", "goal_area", "vehicle_params", "sensor_radius", "exec_timer",
+                                  "mode", "reach_set"],
+    },
+    "risk_assessment.risk_costs": {
+        # risk_costs.py:16-27, 128, 153, 181, 211, 229
+        "calc_risk": ["traj", "ego_state", "predictions", "scenario", "ego_id", "vehicle_params", "params", "road_boundary",
+                      "reach_set", "exec_timer"],
+        "get_bayesian_costs": ["ego_risk_max", "obst_risk_max", "boundary_harm"],
+        "get_equality_costs": ["ego_risk_max", "obst_risk_max"],
+        "get_maximin_costs": ["ego_risk_max", "obst_risk_max", "ego_harm_max", "obst_harm_max", "boundary_harm", "eps",
+                              "scale_factor"],
+        "get_ego_costs": ["ego_risk_max", "boundary_harm"],
+        "get_responsibility_cost": ["scenario", "traj", "ego_state", "obst_risk_max", "predictions", "reach_set", "mode"],
+    },
+    "risk_assessment.collision_probability": {
+        # collision_probability.py:136, 259
+        "get_collision_probability_fast": ["traj", "predictions", "vehicle_params", "safety_margin"],
+        "get_inv_mahalanobis_dist": ["traj", "predictions", "vehicle_params", "safety_margin"],
+    },
+    "risk_assessment.harm_estimation": {
+        # harm_estimation.py:202
+        "get_harm": ["scenario", "traj", "predictions", "ego_id", "vehicle_params", "modes", "coeffs", "timer"],
+    },
+}
+
+
+def test_dropin_modules_keep_the_reference_call_surface():
+    import importlib
+    import inspect
+
+    for mod, fns in REFERENCE_SURFACE.items():
+        m = importlib.import_module("ethicaltrajectoryplanning_b200." + mod)
+        for name, params in fns.items():
+            got = list(inspect.signature(getattr(m, name)).parameters)
+            assert got[:len(params)] == params, (mod, name, got)
+    # the same check against the reference sources when they are mounted (build container only)
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):
+        import ast
+
+        for mod, fns in REFERENCE_SURFACE.items():
+            tree = ast.parse(open(os.path.join(ref_root, *mod.split(".")) + ".py").read())
+            defs = {n.name: [a.arg for a in n.args.args] for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)}
+            for name, params in fns.items():
+                assert defs[name] == params, (mod, name, defs[name])
+
+
+def test_frenet_planner_and_trajectory_keep_the_reference_attributes():
+    import inspect
+
+    from ethicaltrajectoryplanning_b200.planner.Frenet.frenet_planner import FrenetPlanner
+    from ethicaltrajectoryplanning_b200.planner.Frenet.utils.frenet_functions import FrenetTrajectory
+
+    # frenet_planner.py:79-92
+    want = ["self", "scenario", "planning_problem", "ego_id", "vehicle_params", "mode", "exec_timer", "frenet_parameters",
+            "sensor_radius", "plot_frenet_trajectories", "weights", "settings"]
+    assert list(inspect.signature(FrenetPlanner.__init__).parameters)[:len(want)] == want
+    assert hasattr(FrenetPlanner, "_step_planner") and hasattr(FrenetPlanner, "step")
+    # attribute insertion order = key order of the log line (frenet_functions.py:72-102)
+    ft = FrenetTrajectory()
+    assert list(ft.__dict__) == ["t", "d", "d_d", "d_dd", "d_ddd", "s", "s_d", "s_dd", "s_ddd", "x", "y", "yaw", "v", "curv",
+                                 "valid_level", "reason_invalid", "cost", "ego_risk_dict", "obst_risk_dict"]
+
+
+def test_log_line_format_round_trip(tmp_path):
+    from ethicaltrajectoryplanning_b200.planner.Frenet.utils.logging import FrenetLogging, get_data_from_line
+
+    p = os.path.join(tmp_path, "a", "log.csv")
+    lg = FrenetLogging(p)
+    lg.log_data(3, 0.3, [{"t": np.arange(2.0), "cost": 1.5, "ego_risk_dict": {7: 0.25}}], [], {7: {"pos_list": np.zeros((1, 2))}}, 0, None)
+    txt = open(p).read().split("\n")
+    assert txt[0] == "simulation_step;time;valid_trajectories;invalid_trajectories;predictions;calc_time_avg;reach_set"
+    assert txt[1].count(";") == 6
+    d = get_data_from_line(p, 1)
+    assert d["simulation_step"] == 3 and d["valid_trajectories"][0]["ego_risk_dict"] == {"7": 0.25} and d["reach_set"] is None
