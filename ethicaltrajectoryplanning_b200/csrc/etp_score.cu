@@ -192,24 +192,20 @@ template <int NT> __device__ __forceinline__ float chain_coef(const DevParams& p
 
 constexpr float kWrapFree = 100.0f;  // marker in the ego "wrap" slot: un-wrapped and geometric ego angle bin alike
 
-// R = float, NT >= 0: specialised.  `fast_ego`: every lane's ego sample carries kWrapFree.
+// R = float, NT >= 0: specialised.  `fast_ego`: every ego sample of the tile carries kWrapFree.
 template <typename R, int NT> struct Logits {
-    static __device__ __forceinline__ void eval(const DevParams& pr, const Tab<float>& tab, bool fast_ego, Vec4<float> c0,
-                                                Vec2<float> c1, Vec4<float> g0, Vec4<float> g1, bool prot, float ke,
-                                                float ko, float& ae, float& ao) {
-        const float dv = delta_v(c0.z, c0.w, c1.x, 0.0f, g1.x, g1.y, g1.z, 0.0f);
-        const float dve = ke * dv, dvo = ko * dv;
-        if (!prot) {
-            ae = pr.f_lr1s_speed * dve;
-            ao = pr.f_ped_speed * dvo;
-            return;
-        }
+    static __device__ __forceinline__ float dv(Vec4<float> c0, Vec2<float> c1, Vec4<float> g1) {
+        return delta_v(c0.z, c0.w, c1.x, 0.0f, g1.x, g1.y, g1.z, 0.0f);
+    }
+    // impact-area coefficients of ego and obstacle for a protected obstacle; branch free
+    static __device__ __forceinline__ void coefs(const DevParams& pr, const Tab<float>&, bool fast_ego, Vec4<float> c0,
+                                                 Vec2<float> c1, Vec4<float> g0, Vec4<float> g1, float& ce, float& co) {
         const float dx = g0.x - c0.x, dy = g0.y - c0.y;
         const float d2 = dx * dx + dy * dy;
         const float ec = c0.z, es = c0.w, ocp = g1.y, osp = g1.z, owrap = g1.w;
         // ego: angle = rel - yaw_e
         const float p = dx * ec + dy * es, q = dy * ec - dx * es;
-        float ce = chain_coef<NT>(pr, p * fabsf(p), d2, q < 0);
+        ce = chain_coef<NT>(pr, p * fabsf(p), d2, q < 0);
         if (!fast_ego) {
             int n0 = 0;
             if (dy >= 0 && es < 0 && q < 0) n0 = 1;
@@ -226,31 +222,40 @@ template <typename R, int NT> struct Logits {
         const float k = (float)n0 - owrap;
         const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
         const bool neg_side = (k == -1.0f) && (qo >= 0);
-        float co = chain_coef<NT>(pr, -po * fabsf(po), d2, neg_side);
+        co = chain_coef<NT>(pr, -po * fabsf(po), d2, neg_side);
         co = (pos_side || neg_side) ? co : pr.f_coef_pos[NT];
-        ae = pr.f_lr_speed * dve + ce;
-        ao = pr.f_lr_speed * dvo + co;
     }
 };
 
 // generic form: runtime threshold count, any arithmetic type (fp64 check mode, unusual tables)
 template <typename R> struct Logits<R, -1> {
-    static __device__ __forceinline__ void eval(const DevParams&, const Tab<R>& tab, bool, Vec4<R> c0, Vec2<R> c1, Vec4<R> g0,
-                                                Vec4<R> g1, bool prot, R ke, R ko, R& ae, R& ao) {
+    static __device__ __forceinline__ R dv(Vec4<R> c0, Vec2<R> c1, Vec4<R> g1) {
         const R ewrap = (sizeof(R) == 4 && c1.y == (R)kWrapFree) ? (R)0 : c1.y;
-        const R dv = delta_v(c0.z, c0.w, c1.x, ewrap, g1.x, g1.y, g1.z, g1.w);
-        const R dve = ke * dv, dvo = ko * dv;
-        if (prot) {
-            R ce, co;
-            impact_coefs(tab, c0.x, c0.y, c0.z, c0.w, ewrap, g0.x, g0.y, g1.y, g1.z, g1.w, ce, co);
-            ae = tab.lr_speed * dve + ce;
-            ao = tab.lr_speed * dvo + co;
-        } else {
-            ae = tab.lr1s_speed * dve;
-            ao = tab.ped_speed * dvo;
-        }
+        return delta_v(c0.z, c0.w, c1.x, ewrap, g1.x, g1.y, g1.z, g1.w);
+    }
+    static __device__ __forceinline__ void coefs(const DevParams&, const Tab<R>& tab, bool, Vec4<R> c0, Vec2<R> c1, Vec4<R> g0,
+                                                 Vec4<R> g1, R& ce, R& co) {
+        const R ewrap = (sizeof(R) == 4 && c1.y == (R)kWrapFree) ? (R)0 : c1.y;
+        impact_coefs(tab, c0.x, c0.y, c0.z, c0.w, ewrap, g0.x, g0.y, g1.y, g1.z, g1.w, ce, co);
     }
 };
+
+// both logits of one sample: arg = speed * (mass ratio * dv) + impact coefficient (harm_estimation.py:322-332)
+template <typename R, int NT>
+__device__ __forceinline__ void harm_logits(const DevParams& pr, const Tab<R>& tab, bool fast_ego, Vec4<R> c0, Vec2<R> c1,
+                                            Vec4<R> g0, Vec4<R> g1, bool prot, R ke, R ko, R& ae, R& ao) {
+    const R dv = Logits<R, NT>::dv(c0, c1, g1);
+    const R dve = ke * dv, dvo = ko * dv;
+    if (prot) {
+        R ce, co;
+        Logits<R, NT>::coefs(pr, tab, fast_ego, c0, c1, g0, g1, ce, co);
+        ae = tab.lr_speed * dve + ce;
+        ao = tab.lr_speed * dvo + co;
+    } else {
+        ae = tab.lr1s_speed * dve;
+        ao = tab.ped_speed * dvo;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // collision probability of one (ego sample i = t+1, obstacle sample t) pair
@@ -392,7 +397,7 @@ template <typename R> struct Smem {
     __host__ __device__ static size_t bytes(int Ts, int O) {
         const size_t On = O > 0 ? O : 1;
         return ego_bytes(Ts) + 32 * (MX_COUNT * On * sizeof(U) + kWarps * P1_COUNT * sizeof(double) + kWarps * sizeof(int)) +
-               sizeof(unsigned) * (size_t)(Ts - 1) * On;
+               sizeof(unsigned) * (size_t)(Ts - 1) * On + sizeof(int) * On;
     }
     __device__ __forceinline__ Smem(unsigned char* base, int Ts, int O) {
         const size_t On = O > 0 ? O : 1;
@@ -415,6 +420,129 @@ struct LaneBest {
 __device__ __forceinline__ bool key_less(unsigned long long ahi, unsigned long long alo, unsigned long long bhi,
                                          unsigned long long blo) {
     return ahi < bhi || (ahi == bhi && alo < blo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2a: one item = kOB obstacles of one class x one time segment
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct Phase2a {
+    const DevStep* st;
+    const DevParams* pr;
+    const Tab<R>* tab;
+    const Smem<R>* sm;
+    const Vec4<R>* G;
+    const Vec4<R>* C;
+    R* o_prob;
+    R* o_harm;
+    const int* perm;
+    int* qn;
+    size_t Cp, harm_plane, mx_plane;
+    int O, Ts, Tl, cl, lane, seg_len, n_seg;
+    bool active, mahal;
+};
+
+// The four samples of a step are independent dependency chains in ONE basic block (loads are clamped instead of
+// branched around, masks are selects), so the scheduler can interleave them: with 16 resident warps per SM the
+// latency of a broadcast load or a MUFU op is otherwise exposed.
+template <typename R, int NT, bool kFastEgo, bool kProt>
+__device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg) {
+    using U = typename Enc<R>::U;
+    const DevParams& pr = *a.pr;
+    const Tab<R>& tab = *a.tab;
+    const int O = a.O, lane = a.lane;
+    const int t0 = seg * a.seg_len, t1 = min(t0 + a.seg_len, a.Ts - 1);
+    int ok[kOB], n_pred[kOB];
+    bool valid[kOB], prot[kOB];
+    R ke[kOB], ko[kOB], far2[kOB], hm_e[kOB], hm_o[kOB];
+#pragma unroll
+    for (int k = 0; k < kOB; ++k) {
+        valid[k] = g * kOB + k < O;
+        ok[k] = a.perm[min(g * kOB + k, O - 1)];
+        const Vec4<R> cr = ldg4<R>(a.C + ok[k]);
+        n_pred[k] = valid[k] ? __ldg(a.st->pred_len + ok[k]) : 0;
+        prot[k] = cr.z != (R)0;
+        // speed coefficient folded into the mass ratio: arg = (speed * ratio) * dv + coef
+        ke[k] = cr.x; ko[k] = cr.y;
+        const R reach = (R)5.05 + (R)a.st->obs_const[ok[k] * OC_COUNT + OC_HALFLEN];
+        far2[k] = reach * reach;
+        hm_e[k] = hm_o[k] = (R)-INFINITY;
+    }
+    R* pptr = a.o_prob ? a.o_prob + (size_t)t0 * O * a.Cp + a.cl : nullptr;
+    R* hptr = a.o_harm ? a.o_harm + (size_t)t0 * O * a.Cp + a.cl : nullptr;
+    Vec4<R> c0 = a.sm->e0[t0 * 32 + lane];
+    Vec2<R> c1 = a.sm->e1[t0 * 32 + lane];
+    for (int t = t0; t < t1; ++t) {
+        const Vec4<R> n0 = a.sm->e0[(t + 1) * 32 + lane];
+        const Vec2<R> n1 = a.sm->e1[(t + 1) * 32 + lane];
+        const bool has = t < a.Tl - 1;  // this lane's candidate has harm sample t (and ego sample t+1)
+        unsigned near_bits = 0;
+        R ae[kOB], ao[kOB];
+#pragma unroll
+        for (int k = 0; k < kOB; ++k) {
+            // harm samples are t < min(T-1, Tp) (harm_estimation.py:234); past the prediction the last record is
+            // re-read and masked out
+            const int tc = max(min(t, n_pred[k] - 1), 0);
+            const Vec4<R>* gp = a.G + 2 * ((size_t)tc * O + ok[k]);
+            const Vec4<R> g0 = ldg4<R>(gp), g1 = ldg4<R>(gp + 1);
+            const R dv = Logits<R, NT>::dv(c0, c1, g1);
+            const R dve = ke[k] * dv, dvo = ko[k] * dv;
+            if (kProt) {
+                R ce, co;
+                Logits<R, NT>::coefs(pr, tab, kFastEgo, c0, c1, g0, g1, ce, co);
+                const R pe = tab.lr_speed * dve + ce, po = tab.lr_speed * dvo + co;
+                const R ue = tab.lr1s_speed * dve, uo = tab.ped_speed * dvo;
+                ae[k] = prot[k] ? pe : ue;  // a mixed group at the class boundary
+                ao[k] = prot[k] ? po : uo;
+            } else {
+                ae[k] = tab.lr1s_speed * dve;
+                ao[k] = tab.ped_speed * dvo;
+            }
+            const bool hk = has && t < n_pred[k];
+            hm_e[k] = hk ? rmax_(hm_e[k], ae[k]) : hm_e[k];
+            hm_o[k] = hk ? rmax_(hm_o[k], ao[k]) : hm_o[k];
+            // within 5 m + half length of the centre: the three-point gate has to look (phase 2b)
+            const R dx = g0.x - n0.x, dy = g0.y - n0.y;
+            const bool near = hk && (t + 1 < n_pred[k]) && (a.mahal || !(dx * dx + dy * dy > far2[k]));
+            near_bits |= near ? (1u << k) : 0u;
+        }
+        const unsigned queued = __reduce_or_sync(kFull, near_bits);
+        if (queued && lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kOB; ++k)
+                if (queued & (1u << k)) a.sm->queue[atomicAdd(a.qn, 1)] = ((unsigned)t << 16) | (unsigned)ok[k];
+        }
+        if (pptr && a.active) {
+#pragma unroll
+            for (int k = 0; k < kOB; ++k)
+                if (valid[k] && !(queued & (1u << k))) pptr[(size_t)ok[k] * a.Cp] = (R)0;
+        }
+        if (hptr && a.active) {  // optional per-sample harm (get_harm, harm_estimation.py:202)
+#pragma unroll
+            for (int k = 0; k < kOB; ++k) {
+                if (!valid[k]) continue;
+                const bool hk = has && t < n_pred[k];
+                hptr[(size_t)ok[k] * a.Cp] = hk ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.lr1s_const, ae[k]) : (R)0;
+                hptr[a.harm_plane + (size_t)ok[k] * a.Cp] =
+                    hk ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.neg_ped_const, ao[k]) : (R)0;
+            }
+        }
+        c0 = n0;
+        c1 = n1;
+        if (pptr) pptr += (size_t)O * a.Cp;
+        if (hptr) hptr += (size_t)O * a.Cp;
+    }
+#pragma unroll
+    for (int k = 0; k < kOB; ++k) {
+        if (!valid[k]) continue;
+        U* m = a.sm->mx + (size_t)ok[k] * 32 + lane;
+        if (a.n_seg == 1) {
+            m[MX_EGO_ARG * a.mx_plane] = Enc<R>::enc(hm_e[k]);
+            m[MX_OBST_ARG * a.mx_plane] = Enc<R>::enc(hm_o[k]);
+        } else {
+            atomicMax(m + MX_EGO_ARG * a.mx_plane, Enc<R>::enc(hm_e[k]));
+            atomicMax(m + MX_OBST_ARG * a.mx_plane, Enc<R>::enc(hm_o[k]));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,7 +577,18 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     __shared__ int s_tile, s_item, s_qn, s_qpos;
     __shared__ BestRec wbest[kWarps];
     __shared__ bool is_last;
-    if (tid == 0) fill_tab<R>(tab, pr);
+    __shared__ int s_nprot;
+    int* s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);  // [On] obstacles sorted by class
+    if (tid == 0) {
+        fill_tab<R>(tab, pr);
+        // protected obstacles first: a phase-2a item then holds one class and needs no per-sample class branch
+        int n = 0;
+        for (int o = 0; o < O; ++o)
+            if (ldg4<R>(tile.C + o).z != (R)0) s_perm[n++] = o;
+        s_nprot = n;
+        for (int o = 0; o < O; ++o)
+            if (ldg4<R>(tile.C + o).z == (R)0) s_perm[n++] = o;
+    }
 
     // phase-2a items: obstacle groups of kOB x time segments, about three items per warp
     const int n_groups = (O + kOB - 1) / kOB;
@@ -496,6 +635,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         const int Tl = live ? T : 0;
 
         // ---- phase 1: generation + transform, warps over time chunks --------------------------------
+        int wf = (sizeof(R) == 4 && NT >= 0) ? 1 : 0;
         {
             double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
             int first_fail = 0x7fffffff;
@@ -518,6 +658,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                         w = (R)tp.f[ETP_F_YAW];
                     sm.e0[t * 32 + lane] = Vec4<R>{(R)tp.f[ETP_F_X], (R)tp.f[ETP_F_Y], (R)tp.cos_yaw, (R)tp.sin_yaw};
                     sm.e1[t * 32 + lane] = Vec2<R>{(R)tp.f[ETP_F_V], w};
+                    if (sizeof(R) == 4 && w != (R)kWrapFree) wf = 0;
                     sv += tp.f[ETP_F_V];
                     sd += fabs(tp.f[ETP_F_D]);
                     jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
@@ -548,98 +689,25 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             p1[P1_V * 32] = sv; p1[P1_D * 32] = sd; p1[P1_JL * 32] = jl; p1[P1_JQ * 32] = jq; p1[P1_TRAV * 32] = trav;
             sm.ff[warp * 32 + lane] = first_fail;
         }
-        __syncthreads();  // (b) ego samples complete
+        const bool tile_fast = __syncthreads_and(wf) != 0;  // (b) ego samples complete; all of them wrap-free?
 
         // ---- phase 2a: harm logits of every (t, o) sample, straight-line; samples inside the gate's reach are queued
         // item = (kOB obstacles, time segment).  Sample t of the harm model pairs ego[t] with prediction[t]
         // (harm_estimation.py:313-332); sample t of the probability pairs ego[t+1] with mean[t], covariance[t],
         // orientation[t+1] (collision_probability.py:168-203).
         if (O > 0) {
+            Phase2a<R> pa{&st, &pr, &tab, &sm, tile.G, tile.C, o_prob, o_harm, s_perm, &s_qn, Cp, harm_plane, mx_plane, O, Ts, Tl, cl, lane,
+                          seg_len, n_seg, active, mahal};
             for (;;) {
                 int item = 0;
                 if (lane == 0) item = atomicAdd(&s_item, 1);
                 item = __shfl_sync(kFull, item, 0);
                 if (item >= n_items) break;
                 const int g = item % n_groups, seg = item / n_groups;
-                const int o0 = g * kOB;
-                const int t0 = seg * seg_len, t1 = min(t0 + seg_len, Ts - 1);
-                int n_pred[kOB];
-                bool prot[kOB];
-                R ke[kOB], ko[kOB], far2[kOB], hm_e[kOB], hm_o[kOB];
-#pragma unroll
-                for (int k = 0; k < kOB; ++k) {
-                    const int o = min(o0 + k, O - 1);
-                    const Vec4<R> cr = ldg4<R>(tile.C + o);
-                    n_pred[k] = (o0 + k < O) ? __ldg(st.pred_len + o) : 0;
-                    ke[k] = cr.x; ko[k] = cr.y; prot[k] = cr.z != (R)0;
-                    const R reach = (R)5.05 + (R)st.obs_const[o * OC_COUNT + OC_HALFLEN];
-                    far2[k] = reach * reach;
-                    hm_e[k] = hm_o[k] = (R)-INFINITY;
-                }
-                const Vec4<R>* gptr = tile.G + 2 * ((size_t)t0 * O + o0);
-                R* pptr = o_prob ? o_prob + ((size_t)t0 * O + o0) * Cp + cl : nullptr;
-                R* hptr = o_harm ? o_harm + ((size_t)t0 * O + o0) * Cp + cl : nullptr;
-                Vec4<R> c0 = sm.e0[t0 * 32 + lane];
-                Vec2<R> c1 = sm.e1[t0 * 32 + lane];
-                for (int t = t0; t < t1; ++t) {
-                    const Vec4<R> n0 = sm.e0[(t + 1) * 32 + lane];
-                    const Vec2<R> n1 = sm.e1[(t + 1) * 32 + lane];
-                    const bool has = t < Tl - 1;  // this lane's candidate has harm sample t (and ego sample t+1)
-                    const bool fast_ego = sizeof(R) == 4 && NT >= 0 && __all_sync(kFull, c1.y == (R)kWrapFree);
-#pragma unroll
-                    for (int k = 0; k < kOB; ++k) {
-                        if (o0 + k >= O) continue;  // uniform
-                        bool queued = false;
-                        if (t < n_pred[k]) {  // uniform: harm samples are t < min(T-1, Tp)   (harm_estimation.py:234)
-                            const Vec4<R> g0 = ldg4<R>(gptr + 2 * k), g1 = ldg4<R>(gptr + 2 * k + 1);
-                            R ae, ao;
-                            if (fast_ego)
-                                Logits<R, NT>::eval(pr, tab, true, c0, c1, g0, g1, prot[k], ke[k], ko[k], ae, ao);
-                            else
-                                Logits<R, NT>::eval(pr, tab, false, c0, c1, g0, g1, prot[k], ke[k], ko[k], ae, ao);
-                            if (has) {
-                                hm_e[k] = rmax_(hm_e[k], ae);
-                                hm_o[k] = rmax_(hm_o[k], ao);
-                            }
-                            if (hptr && active) {  // optional per-sample harm (get_harm, harm_estimation.py:202)
-                                hptr[(size_t)k * Cp] = has ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.lr1s_const, ae) : (R)0;
-                                hptr[harm_plane + (size_t)k * Cp] =
-                                    has ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.neg_ped_const, ao) : (R)0;
-                            }
-                            if (t + 1 < n_pred[k]) {  // uniform
-                                // within 5 m + half length of the centre: the three-point gate has to look (phase 2b)
-                                const R dx = g0.x - n0.x, dy = g0.y - n0.y;
-                                const bool near = has && (mahal || !(dx * dx + dy * dy > far2[k]));
-                                if (__any_sync(kFull, near)) {
-                                    queued = true;
-                                    if (lane == 0) sm.queue[atomicAdd(&s_qn, 1)] = ((unsigned)t << 16) | (unsigned)(o0 + k);
-                                }
-                            }
-                        }
-                        else if (hptr && active) {
-                            hptr[(size_t)k * Cp] = (R)0;
-                            hptr[harm_plane + (size_t)k * Cp] = (R)0;
-                        }
-                        if (pptr && active && !queued) pptr[(size_t)k * Cp] = (R)0;
-                    }
-                    c0 = n0;
-                    c1 = n1;
-                    gptr += 2 * O;
-                    if (pptr) pptr += (size_t)O * Cp;
-                    if (hptr) hptr += (size_t)O * Cp;
-                }
-#pragma unroll
-                for (int k = 0; k < kOB; ++k) {
-                    if (o0 + k >= O) continue;
-                    U* m = sm.mx + (size_t)(o0 + k) * 32 + lane;
-                    if (n_seg == 1) {
-                        m[MX_EGO_ARG * mx_plane] = Enc<R>::enc(hm_e[k]);
-                        m[MX_OBST_ARG * mx_plane] = Enc<R>::enc(hm_o[k]);
-                    } else {
-                        atomicMax(m + MX_EGO_ARG * mx_plane, Enc<R>::enc(hm_e[k]));
-                        atomicMax(m + MX_OBST_ARG * mx_plane, Enc<R>::enc(hm_o[k]));
-                    }
-                }
+                const bool unprot = g * kOB >= s_nprot;  // groups are cut from the class-sorted obstacle order
+                if (unprot) phase2a_item<R, NT, false, false>(pa, g, seg);
+                else if (tile_fast) phase2a_item<R, NT, true, true>(pa, g, seg);
+                else phase2a_item<R, NT, false, true>(pa, g, seg);
             }
             __syncthreads();  // (b2) queue complete
 
@@ -687,7 +755,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                         prob = collision_prob(tab, n0, g0, ldg4<R>(tile.P + 2 * vi), tile.N + kNodeVecs * vi);
                     }
                     R ae, ao;
-                    Logits<R, -1>::eval(pr, tab, false, c0, c1, g0, g1, prt, cr.x, cr.y, ae, ao);
+                    harm_logits<R, -1>(pr, tab, false, c0, c1, g0, g1, prt, cr.x, cr.y, ae, ao);
                     const R he = sigmoid_harm<R>(prt ? tab.lr_const : tab.lr1s_const, ae);
                     const R ho = sigmoid_harm<R>(prt ? tab.lr_const : tab.neg_ped_const, ao);
                     U* m = sm.mx + (size_t)o * 32 + lane;

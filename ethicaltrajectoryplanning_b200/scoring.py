@@ -256,10 +256,12 @@ class ScoringContext:
 
     # -- inputs -----------------------------------------------------------------------------
     def set_params(self, params, vehicle, mode="risk"):
+        self._params_key = None
         p = make_params(params, vehicle, mode)
         self._check(self.lib.etp_set_params(self.h, C.byref(p)))
 
     def set_spline(self, csp):
+        self._spline_key = None
         csp = CubicSpline2D.from_foreign(csp)
         k = np.ascontiguousarray(csp.s, dtype=np.float64)
         cx = np.ascontiguousarray(csp.coef_x, dtype=np.float64)
@@ -283,9 +285,18 @@ class ScoringContext:
         self.obstacle_ids, self.O, self.has_pred = pk["ids"], pk["O"], True
 
     def configure(self, step: PlanningStep):
-        """params + spline + predictions of a PlanningStep."""
-        self.set_params(step.params, step.vehicle, step.mode)
-        self.set_spline(step.csp)
+        """params + spline + predictions of a PlanningStep.  Parameters and spline are uploaded again only when they
+        changed (same objects, same content fingerprint); predictions change every step and always are."""
+        pkey = (id(step.params), id(step.vehicle), step.mode, repr(sorted(step.params["weights"].items())),
+                repr(sorted((k, v) for k, v in step.params["modes"].items() if not isinstance(v, dict))))
+        if getattr(self, "_params_key", None) != pkey:
+            self.set_params(step.params, step.vehicle, step.mode)
+            self._params_key = pkey
+        csp = CubicSpline2D.from_foreign(step.csp)
+        skey = (id(step.csp), len(csp.s), float(csp.s[-1]), float(np.asarray(csp.coef_x)[0][0]), float(np.asarray(csp.coef_y)[-1][1]))
+        if getattr(self, "_spline_key", None) != skey:
+            self.set_spline(csp)
+            self._spline_key = skey
         self.set_predictions(step.predictions, step.obstacle_types)
 
     # -- one planning step --------------------------------------------------------------------

@@ -1,0 +1,35 @@
+"""cfg4 (scenario sweep) and cfg5 (closed loop) drivers: selections against the fp64 oracle, fused vs materialised
+planner, fp32 vs fp64 check mode."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sweep_selects_the_oracle_candidate_in_every_scenario():
+    from ethicaltrajectoryplanning_b200 import dropin, workloads
+    from oracle import vec
+
+    ctx = dropin.default_context()
+    ids = [0, 1, 2, 3, 4, 5, 6, 7]
+    res, n_cand, sec = workloads.run_sweep(ctx, ids)
+    assert n_cand > 0 and len(res) == len(ids)
+    for (sid, index, level, cost), (_, step) in zip(res, ((i, s) for i in ids for _, s in workloads.sweep_steps(1, i))):
+        ref = vec.score_dense(step)
+        assert index == int(ref["best"]["index"]), (sid, index, ref["best"])
+        assert level == int(ref["best"]["level"])
+        assert abs(cost - ref["best"]["cost"]) <= 1e-3 * abs(ref["best"]["cost"]) + 1e-6
+
+
+def test_closed_loop_fused_equals_materialised_and_fp64():
+    from ethicaltrajectoryplanning_b200 import workloads
+
+    _, fused = workloads.closed_loop(12, "weights_ethical.json", "cfg1", materialize=False)
+    _, mat = workloads.closed_loop(12, "weights_ethical.json", "cfg1", materialize=True)
+    _, f64 = workloads.closed_loop(12, "weights_ethical.json", "cfg1", materialize=False, precision="fp64")
+    for a, b, c in zip(fused, mat, f64):
+        np.testing.assert_allclose(a[:3], b[:3], rtol=2e-5, atol=1e-6)   # materialised path reads fp32 rows
+        np.testing.assert_allclose(a[:3], c[:3], rtol=1e-9, atol=1e-9)   # same winner => same fp64 trajectory
+        assert a[3] == c[3]
+    s = [st[0] for st in fused]
+    assert all(b > a for a, b in zip(s[:-1], s[1:]))  # the ego advances along the path
