@@ -25,7 +25,7 @@ enum { PM_DS = 0, PM_LOW, PM_T, PM_VEL_OK, PM_TEND, PM_COUNT };
 //                   stdevs / correlation of cov_list[t] (zero matrix -> 0.1*I, collision_probability.py:205-212);
 //                   class = Gauss-Legendre node count class of |rho| (0: rho = 0, 1: 4 nodes, 2: 6 nodes, 3: fp64 path);
 //                   i** = inverse of cov_list[t] for the Mahalanobis mode (collision_probability.py:279)
-//   N [Tp][O][5]  float4, fp32 tile only: nodes of the rho integral s[6] | q[6] | c[6] | pad[2]
+//   N [Tp][O][5]  float4, fp32 tile only: nodes of the rho integral s[6] | q[6] | c[6] | low parts of (mx, my)
 //   C [O]         per obstacle: (m_o/(m_e+m_o), m_e/(m_e+m_o), protected, responsibility)  (harm_estimation.py:327-328)
 template <typename R> struct alignas(16) Vec4 { R x, y, z, w; };
 template <typename R> struct alignas(2 * sizeof(R)) Vec2 { R x, y; };

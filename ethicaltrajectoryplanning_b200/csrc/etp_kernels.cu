@@ -68,6 +68,9 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
         i00 = r11 / det;
         i01 = -(r01 + r10) / det;
         i11 = r00 / det;
+        // low parts of the mean: exact mx = (float)mx + nodes[18] (fp32 tile; see nine_rectangles in etp_score.cu)
+        nodes[18] = (float)(mx - (double)(float)mx);
+        nodes[19] = (float)(my - (double)(float)my);
         // nodes of the rho integral (fp32 path, etp_bvn.cuh): theta_i on [0, asin rho]
         const float rf = (float)rho;
         const float ar = fabsf(rf);
@@ -91,7 +94,21 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
         }
     }
     G[0] = Vec4<R>{(R)mx, (R)my, (R)ex, (R)ey};
-    G[1] = Vec4<R>{(R)vo, (R)cpsi, (R)spsi, (R)(sizeof(R) == 4 ? wrap : psi)};
+    // fp32 tile: which (half plane of the ego seen from the obstacle, sign of dy) combinations give an un-wrapped
+    // impact angle pi + rel - psi inside [-pi, pi] (quirk Q4; derivation at Logits::coefs in etp_score.cu).
+    // bit (pos << 1 | a): pos = ego on the obstacle's clockwise side (angle >= 0), a = (dy >= 0)
+    int code = 0;
+    {
+        const bool u = spsi >= 0.0;
+        for (int pos = 0; pos < 2; ++pos)
+            for (int a = 0; a < 2; ++a) {
+                bool valid;
+                if (pos) valid = (wrap == 0.0) ? !(a && !u) : (wrap == 1.0 ? (a && !u) : false);
+                else valid = (wrap == 0.0) ? (!a && u) : (wrap == 1.0 ? !(!a && u) : false);
+                code |= valid ? (1 << (pos * 2 + a)) : 0;
+            }
+    }
+    G[1] = Vec4<R>{(R)vo, (R)cpsi, (R)spsi, sizeof(R) == 4 ? (R)__int_as_float(code) : (R)psi};
     P[0] = Vec4<R>{(R)isx, (R)isy, (R)rho, (R)cls};
     P[1] = Vec4<R>{(R)i00, (R)i01, (R)i11, (R)0};
     for (int k = 0; k < kNodeVecs; ++k) N[k] = make_float4(nodes[4 * k], nodes[4 * k + 1], nodes[4 * k + 2], nodes[4 * k + 3]);

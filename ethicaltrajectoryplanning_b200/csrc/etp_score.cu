@@ -21,6 +21,10 @@
 //   phase 3  warps split the OBSTACLE axis for the per-obstacle reductions, warp 0 finishes cost, level, key.
 // All materialised tensors are candidate-minor ([...][c]): every store of a warp is one contiguous 128-byte
 // line, written exactly once.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "etp_bvn.cuh"
 #include "etp_device.cuh"
 #include "etp_launch.h"
@@ -33,8 +37,12 @@ constexpr int kWarps = kThreads / 32;
 #define ETP_MIN_BLOCKS 2
 #endif
 constexpr int kMinBlocks = ETP_MIN_BLOCKS;  // resident CTAs per SM the register budget is sized for
-constexpr int kOB = 4;  // obstacles of one phase-2 item (register blocking: one ego load serves kOB obstacles)
+#ifndef ETP_OB
+#define ETP_OB 4
+#endif
+constexpr int kOB = ETP_OB;  // obstacles of one phase-2 item (register blocking: one ego load serves kOB obstacles)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr float kLoScale = 16384.0f;  // low parts of coordinates are stored as halves of (residue * 2^14)
 
 // ---------------------------------------------------------------------------------------------
 // small typed helpers
@@ -75,7 +83,10 @@ template <> __device__ __forceinline__ Vec4<double> ldg4<double>(const Vec4<doub
 }
 template <typename R> __device__ __forceinline__ R rmax_(R a, R b) { return a > b ? a : b; }
 // square root of the fp32 streaming path: MUFU.RSQ based (2 ulp); the fp64 check mode stays IEEE
-__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.0f ? x * rsqrt_ftz(x) : 0.0f; }
+__device__ __forceinline__ float sqrt_fast(float x) {
+    const float xp = fmaxf(x, 0.0f);  // rounding can leave (v_e - v_o)^2 slightly negative
+    return xp * rsqrt_ftz(fmaxf(xp, 1e-30f));
+}
 __device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
 __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
@@ -138,13 +149,13 @@ __device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, flo
     return band;
 }
 
-// Impact-area coefficients of ego and obstacle, fp32 path.  `ewrap` / `owrap` are the whole turns that bring
-// the ego / obstacle yaw into (-pi, pi].  The reference bins the UN-wrapped angles rel - yaw_e and
+// Impact-area coefficients of ego and obstacle, fp32 path.  `ewrap` are the whole turns that bring the ego yaw
+// into (-pi, pi].  The reference bins the UN-wrapped angles rel - yaw_e and
 // pi + rel - psi_o (quirk Q4) with rel = atan2(dy, dx); instead of evaluating atan2, the relative direction is
 // rotated into the ego / obstacle frame (P, Q) and the number of 2 pi wraps of the un-wrapped difference is
 // recovered from the half planes of the two directions.  |angle| > pi always lands in the last ("rear") band.
 __device__ __forceinline__ void impact_coefs(const Tab<float>& pr, float ex, float ey, float ec, float es, float ewrap,
-                                             float mx, float my, float ocp, float osp, float owrap, float& ce, float& co) {
+                                             float mx, float my, float ocp, float osp, float ocode, float& ce, float& co) {
     const float dx = mx - ex, dy = my - ey;
     const float d2 = dx * dx + dy * dy;
     const int last = pr.n_thr;
@@ -155,15 +166,12 @@ __device__ __forceinline__ void impact_coefs(const Tab<float>& pr, float ex, flo
     if (dy < 0 && es >= 0 && q > 0) n0 = -1;
     const int be = ((float)n0 != ewrap) ? last : direction_band(pr, p, d2);
     ce = q < 0 ? pr.coef_neg[be] : pr.coef_pos[be];
-    // obstacle: angle = pi + rel - psi_o
+    // obstacle: angle = pi + rel - psi_o; `ocode` is the validity table of pack_obstacles_kernel
     const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
-    n0 = 0;
-    if (dy >= 0 && osp < 0 && qo < 0) n0 = 1;
-    if (dy < 0 && osp >= 0 && qo > 0) n0 = -1;
-    const float k = (float)n0 - owrap;
-    const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
-    const bool neg_side = (k == -1.0f) && (qo >= 0);
-    const int bo = (pos_side || neg_side) ? direction_band(pr, -po, d2) : last;
+    const bool pos = qo < 0 || (qo == 0 && po >= 0);
+    const bool valid = ((__float_as_int(ocode) >> ((pos ? 2 : 0) | (dy >= 0 ? 1 : 0))) & 1) != 0;
+    const bool neg_side = !pos && valid;
+    const int bo = valid ? direction_band(pr, -po, d2) : last;
     co = neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo];
 }
 __device__ __forceinline__ void impact_coefs(const Tab<double>& pr, double ex, double ey, double, double, double eyaw,
@@ -180,11 +188,12 @@ template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { 
 // ---------------------------------------------------------------------------------------------
 // Coefficient of the geometric band of a direction (fp = P|P|, d2): first threshold whose test passes.  NT
 // thresholds are compile-time; thresholds and coefficients are constant-bank operands (no loads, no loop).
-template <int NT> __device__ __forceinline__ float chain_coef(const DevParams& pr, float fp, float d2, bool neg) {
-    float coef = neg ? pr.f_coef_neg[NT] : pr.f_coef_pos[NT];
+// kSym: both sides share one coefficient table (the symmetric models), the side is not looked at.
+template <int NT, bool kSym> __device__ __forceinline__ float chain_coef(const DevParams& pr, float fp, float d2, bool neg) {
+    float coef = (!kSym && neg) ? pr.f_coef_neg[NT] : pr.f_coef_pos[NT];
 #pragma unroll
     for (int i = NT - 1; i >= 0; --i) {
-        const float ci = neg ? pr.f_coef_neg[i] : pr.f_coef_pos[i];
+        const float ci = (!kSym && neg) ? pr.f_coef_neg[i] : pr.f_coef_pos[i];
         coef = (fp > d2 * pr.f_fcos[i]) ? ci : coef;
     }
     return coef;
@@ -193,7 +202,14 @@ template <int NT> __device__ __forceinline__ float chain_coef(const DevParams& p
 constexpr float kWrapFree = 100.0f;  // marker in the ego "wrap" slot: un-wrapped and geometric ego angle bin alike
 
 // R = float, NT >= 0: specialised.  `fast_ego`: every ego sample of the tile carries kWrapFree.
-template <typename R, int NT> struct Logits {
+//
+// Obstacle side (quirk Q4).  The reference bins a_o = pi + rel - psi_o with rel = atan2(dy, dx) in (-pi, pi] WITHOUT
+// wrapping.  With theta = angle of the ego as seen from the obstacle's heading, a_o = pi + theta + 2 pi k for an
+// integer k that depends only on the half plane of theta (sign of qo), on the sign of dy, on the sign of sin(psi_o)
+// and on the whole turns in psi_o.  |a_o| <= pi (a band other than the last) needs k = 0 with theta <= 0 or k = -1
+// with theta >= 0; the last two inputs are per prediction sample, so pack_obstacles_kernel tabulates the answer
+// for the four (half plane, sign of dy) combinations in 4 bits of the obstacle record.
+template <typename R, int NT, bool kSym = false> struct Logits {
     static __device__ __forceinline__ float dv(Vec4<float> c0, Vec2<float> c1, Vec4<float> g1) {
         return delta_v(c0.z, c0.w, c1.x, 0.0f, g1.x, g1.y, g1.z, 0.0f);
     }
@@ -202,10 +218,10 @@ template <typename R, int NT> struct Logits {
                                                  Vec2<float> c1, Vec4<float> g0, Vec4<float> g1, float& ce, float& co) {
         const float dx = g0.x - c0.x, dy = g0.y - c0.y;
         const float d2 = dx * dx + dy * dy;
-        const float ec = c0.z, es = c0.w, ocp = g1.y, osp = g1.z, owrap = g1.w;
+        const float ec = c0.z, es = c0.w, ocp = g1.y, osp = g1.z;
         // ego: angle = rel - yaw_e
         const float p = dx * ec + dy * es, q = dy * ec - dx * es;
-        ce = chain_coef<NT>(pr, p * fabsf(p), d2, q < 0);
+        ce = chain_coef<NT, kSym>(pr, p * fabsf(p), d2, q < 0);
         if (!fast_ego) {
             int n0 = 0;
             if (dy >= 0 && es < 0 && q < 0) n0 = 1;
@@ -216,19 +232,16 @@ template <typename R, int NT> struct Logits {
         }
         // obstacle: angle = pi + rel - psi_o
         const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
-        int n0 = 0;
-        if (dy >= 0 && osp < 0 && qo < 0) n0 = 1;
-        if (dy < 0 && osp >= 0 && qo > 0) n0 = -1;
-        const float k = (float)n0 - owrap;
-        const bool pos_side = (k == 0) && (qo <= 0) && !(qo == 0 && po < 0);
-        const bool neg_side = (k == -1.0f) && (qo >= 0);
-        co = chain_coef<NT>(pr, -po * fabsf(po), d2, neg_side);
-        co = (pos_side || neg_side) ? co : pr.f_coef_pos[NT];
+        const bool pos = qo < 0 || (qo == 0 && po >= 0);
+        const int code = __float_as_int(g1.w);  // validity table, stored as raw bits in the fp32 tile
+        const bool valid = ((code >> ((pos ? 2 : 0) | (dy >= 0 ? 1 : 0))) & 1) != 0;
+        co = chain_coef<NT, kSym>(pr, -po * fabsf(po), d2, !pos);
+        co = valid ? co : pr.f_coef_pos[NT];
     }
 };
 
 // generic form: runtime threshold count, any arithmetic type (fp64 check mode, unusual tables)
-template <typename R> struct Logits<R, -1> {
+template <typename R, bool kSym> struct Logits<R, -1, kSym> {
     static __device__ __forceinline__ R dv(Vec4<R> c0, Vec2<R> c1, Vec4<R> g1) {
         const R ewrap = (sizeof(R) == 4 && c1.y == (R)kWrapFree) ? (R)0 : c1.y;
         return delta_v(c0.z, c0.w, c1.x, ewrap, g1.x, g1.y, g1.z, g1.w);
@@ -281,59 +294,63 @@ template <int N> struct RectNodesF {
     }
 };
 
+// (ddx, ddy) = ego centre - obstacle mean.  Both positions are hundreds of metres from the origin, their difference
+// is a few metres and the rectangle limits are differences divided by a standard deviation that can be 0.14 m: the
+// caller forms (ddx, ddy) from split (high + low) fp32 coordinates so that the limits carry no cancellation error;
+// everything added below (box offsets, obstacle half length, half extents) is metres-sized.
 template <typename R, typename Rect>
-__device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect, R x, R y, R c, R s, R mx, R my, R ex, R ey,
-                                             R isx, R isy, R rho) {
+__device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect, R ddx, R ddy, R c, R s, R ex, R ey, R isx,
+                                             R isy, R rho) {
     const R hx = pr.hx, hy = pr.hy, rr = pr.rr;
     R prob = 0;
 #pragma unroll 1
     for (int km = 0; km < 3; ++km) {
         const R sg = km == 0 ? (R)0 : (km == 1 ? (R)1 : (R)-1);
-        const R ux = mx + sg * ex, uy = my + sg * ey;
+        const R ux = ddx - sg * ex, uy = ddy - sg * ey;  // ego centre - mean_km
 #pragma unroll 1
         for (int jb = 0; jb < 3; ++jb) {
             const R sb = jb == 0 ? (R)0 : (jb == 1 ? (R)1 : (R)-1);
-            const R bx = x + sb * (rr * c), by = y + sb * (rr * s);
-            const R xl = ((bx - hx) - ux) * isx, xu = ((bx + hx) - ux) * isx;
-            const R yl = ((by - hy) - uy) * isy, yu = ((by + hy) - uy) * isy;
+            const R bx = ux + sb * (rr * c), by = uy + sb * (rr * s);  // box centre - mean
+            const R xl = (bx - hx) * isx, xu = (bx + hx) * isx;
+            const R yl = (by - hy) * isy, yu = (by + hy) * isy;
             prob += rect(xl, xu, yl, yu, rho);
         }
     }
     return prob / 3;
 }
 
-// `e` = ego sample (x, y, cos yaw, sin yaw), `g` = (mx, my, ex, ey), `p` = (1/sx, 1/sy, rho, class), `nd` = the
-// five node vectors of this (t, o) record.  All lanes of a warp share g, p and nd.
-__device__ __noinline__ double collision_prob(const Tab<double>& pr, Vec4<double> e, Vec4<double> g, Vec4<double> p,
-                                              const float4*) {
-    return nine_rectangles<double>(pr, RectDouble{}, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+// `c`, `s` = cos / sin of the ego yaw, `g` = (mx, my, ex, ey), `p` = (1/sx, 1/sy, rho, class), `nd` = the five node
+// vectors of this (t, o) record.  All lanes of a warp share g, p and nd.
+__device__ __noinline__ double collision_prob(const Tab<double>& pr, double ddx, double ddy, double c, double s,
+                                              Vec4<double> g, Vec4<double> p, const float4*) {
+    return nine_rectangles<double>(pr, RectDouble{}, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
 }
 
-__device__ __noinline__ float collision_prob(const Tab<float>& pr, Vec4<float> e, Vec4<float> g, Vec4<float> p,
-                                             const float4* nd) {
+__device__ __noinline__ float collision_prob(const Tab<float>& pr, float ddx, float ddy, float c, float s, Vec4<float> g,
+                                             Vec4<float> p, const float4* nd) {
     const int cls = (int)p.w;  // warp-uniform: Gauss-Legendre node class of |rho| (pack_obstacles_kernel)
     if (cls == RC_ZERO) {
         RectNodesF<0> r;
-        return nine_rectangles<float>(pr, r, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+        return nine_rectangles<float>(pr, r, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
     }
     if (cls == RC_FP64) {
         atomicAdd(&g_fallback_evals, 1ull);
-        return nine_rectangles<float>(pr, RectFallbackF{}, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+        return nine_rectangles<float>(pr, RectFallbackF{}, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
     }
-    const float4 a = __ldg(nd), b = __ldg(nd + 1), c = __ldg(nd + 2), d = __ldg(nd + 3), f = __ldg(nd + 4);
-    // s[0..5] = a.xyzw b.xy | q[0..5] = b.zw c.xyzw | c[0..5] = d.xyzw f.xy
+    const float4 a = __ldg(nd), b = __ldg(nd + 1), cc = __ldg(nd + 2), d = __ldg(nd + 3), f = __ldg(nd + 4);
+    // s[0..5] = a.xyzw b.xy | q[0..5] = b.zw cc.xyzw | c[0..5] = d.xyzw f.xy | f.zw = low parts of the mean
     if (cls == RC_N4) {
         RectNodesF<4> r;
         r.n.s[0] = a.x; r.n.s[1] = a.y; r.n.s[2] = a.z; r.n.s[3] = a.w;
-        r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = c.x; r.n.q[3] = c.y;
+        r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = cc.x; r.n.q[3] = cc.y;
         r.n.c[0] = d.x; r.n.c[1] = d.y; r.n.c[2] = d.z; r.n.c[3] = d.w;
-        return nine_rectangles<float>(pr, r, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+        return nine_rectangles<float>(pr, r, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
     }
     RectNodesF<6> r;
     r.n.s[0] = a.x; r.n.s[1] = a.y; r.n.s[2] = a.z; r.n.s[3] = a.w; r.n.s[4] = b.x; r.n.s[5] = b.y;
-    r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = c.x; r.n.q[3] = c.y; r.n.q[4] = c.z; r.n.q[5] = c.w;
+    r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = cc.x; r.n.q[3] = cc.y; r.n.q[4] = cc.z; r.n.q[5] = cc.w;
     r.n.c[0] = d.x; r.n.c[1] = d.y; r.n.c[2] = d.z; r.n.c[3] = d.w; r.n.c[4] = f.x; r.n.c[5] = f.y;
-    return nine_rectangles<float>(pr, r, e.x, e.y, e.z, e.w, g.x, g.y, g.z, g.w, p.x, p.y, p.z);
+    return nine_rectangles<float>(pr, r, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
 }
 
 // 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
@@ -384,13 +401,14 @@ template <typename R> struct Smem {
     using U = typename Enc<R>::U;
     Vec4<R>* e0;    // [Ts][32] x, y, cos yaw, sin yaw
     Vec2<R>* e1;    // [Ts][32] v, yaw (fp64) or its wrap count / kWrapFree (fp32)
+    __half2* el;    // [Ts][32] low parts of x, y scaled by 2^14: exact x = e0.x + el.x / 2^14 (fp32 mode; zero in fp64 mode)
     double* p3;     // [kWarps][P3_COUNT][32]  -- aliases e0: the ego samples are dead once phase 2 is over
     U* mx;          // [MX_COUNT][On][32]
     double* p1;     // [kWarps][P1_COUNT][32]
     int* ff;        // [kWarps][32] first failing curvature sample * 4 + kind
     unsigned* queue;  // [(Ts-1) * On] (t << 16 | o) pairs that have a lane inside the gate's reach
     __host__ __device__ static size_t ego_bytes(int Ts) {
-        const size_t e = 32 * (size_t)Ts * (sizeof(Vec4<R>) + sizeof(Vec2<R>));
+        const size_t e = 32 * (size_t)Ts * (sizeof(Vec4<R>) + sizeof(Vec2<R>) + sizeof(__half2));
         const size_t p = (size_t)kWarps * P3_COUNT * 32 * sizeof(double);
         return e > p ? e : p;
     }
@@ -403,6 +421,7 @@ template <typename R> struct Smem {
         const size_t On = O > 0 ? O : 1;
         e0 = reinterpret_cast<Vec4<R>*>(base);
         e1 = reinterpret_cast<Vec2<R>*>(e0 + (size_t)Ts * 32);
+        el = reinterpret_cast<__half2*>(e1 + (size_t)Ts * 32);
         p3 = reinterpret_cast<double*>(base);
         p1 = reinterpret_cast<double*>(base + ego_bytes(Ts));
         mx = reinterpret_cast<U*>(p1 + kWarps * P1_COUNT * 32);
@@ -444,24 +463,32 @@ template <typename R> struct Phase2a {
 // The four samples of a step are independent dependency chains in ONE basic block (loads are clamped instead of
 // branched around, masks are selects), so the scheduler can interleave them: with 16 resident warps per SM the
 // latency of a broadcast load or a MUFU op is otherwise exposed.
-template <typename R, int NT, bool kFastEgo, bool kProt>
+//   kProt    : the group holds protected obstacles (impact-angle terms); a mixed group at the class boundary runs
+//              here too and selects per obstacle
+//   kFastEgo : every ego sample of the tile is wrap-free (Logits::coefs)
+//   kDense   : all 32 lanes carry live candidates of the same length, all kOB obstacles exist and their predictions
+//              cover the segment: no masks, no clamps
+template <typename R, int NT, bool kSym, bool kFastEgo, bool kProt, bool kDense>
 __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg) {
     using U = typename Enc<R>::U;
+    using L = Logits<R, NT, kSym>;
     const DevParams& pr = *a.pr;
     const Tab<R>& tab = *a.tab;
     const int O = a.O, lane = a.lane;
     const int t0 = seg * a.seg_len, t1 = min(t0 + a.seg_len, a.Ts - 1);
     int ok[kOB], n_pred[kOB];
+    // element offset of the obstacle's row in a [.][O][Cp] plane (32 bits where the dispatcher has checked they suffice)
+    typename std::conditional<kDense, unsigned, size_t>::type off[kOB];
     bool valid[kOB], prot[kOB];
     R ke[kOB], ko[kOB], far2[kOB], hm_e[kOB], hm_o[kOB];
 #pragma unroll
     for (int k = 0; k < kOB; ++k) {
-        valid[k] = g * kOB + k < O;
+        valid[k] = kDense || g * kOB + k < O;
         ok[k] = a.perm[min(g * kOB + k, O - 1)];
+        off[k] = (typename std::conditional<kDense, unsigned, size_t>::type)((size_t)ok[k] * a.Cp);
         const Vec4<R> cr = ldg4<R>(a.C + ok[k]);
         n_pred[k] = valid[k] ? __ldg(a.st->pred_len + ok[k]) : 0;
         prot[k] = cr.z != (R)0;
-        // speed coefficient folded into the mass ratio: arg = (speed * ratio) * dv + coef
         ke[k] = cr.x; ko[k] = cr.y;
         const R reach = (R)5.05 + (R)a.st->obs_const[ok[k] * OC_COUNT + OC_HALFLEN];
         far2[k] = reach * reach;
@@ -469,26 +496,26 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
     }
     R* pptr = a.o_prob ? a.o_prob + (size_t)t0 * O * a.Cp + a.cl : nullptr;
     R* hptr = a.o_harm ? a.o_harm + (size_t)t0 * O * a.Cp + a.cl : nullptr;
+    const Vec4<R>* gt = a.G + 2 * (size_t)t0 * O;  // records of sample t
     Vec4<R> c0 = a.sm->e0[t0 * 32 + lane];
     Vec2<R> c1 = a.sm->e1[t0 * 32 + lane];
     for (int t = t0; t < t1; ++t) {
         const Vec4<R> n0 = a.sm->e0[(t + 1) * 32 + lane];
         const Vec2<R> n1 = a.sm->e1[(t + 1) * 32 + lane];
-        const bool has = t < a.Tl - 1;  // this lane's candidate has harm sample t (and ego sample t+1)
+        const bool has = kDense || t < a.Tl - 1;  // this lane's candidate has harm sample t (and ego sample t+1)
         unsigned near_bits = 0;
         R ae[kOB], ao[kOB];
 #pragma unroll
         for (int k = 0; k < kOB; ++k) {
             // harm samples are t < min(T-1, Tp) (harm_estimation.py:234); past the prediction the last record is
             // re-read and masked out
-            const int tc = max(min(t, n_pred[k] - 1), 0);
-            const Vec4<R>* gp = a.G + 2 * ((size_t)tc * O + ok[k]);
+            const Vec4<R>* gp = kDense ? gt + 2 * ok[k] : a.G + 2 * ((size_t)max(min(t, n_pred[k] - 1), 0) * O + ok[k]);
             const Vec4<R> g0 = ldg4<R>(gp), g1 = ldg4<R>(gp + 1);
-            const R dv = Logits<R, NT>::dv(c0, c1, g1);
+            const R dv = L::dv(c0, c1, g1);
             const R dve = ke[k] * dv, dvo = ko[k] * dv;
             if (kProt) {
                 R ce, co;
-                Logits<R, NT>::coefs(pr, tab, kFastEgo, c0, c1, g0, g1, ce, co);
+                L::coefs(pr, tab, kFastEgo, c0, c1, g0, g1, ce, co);
                 const R pe = tab.lr_speed * dve + ce, po = tab.lr_speed * dvo + co;
                 const R ue = tab.lr1s_speed * dve, uo = tab.ped_speed * dvo;
                 ae[k] = prot[k] ? pe : ue;  // a mixed group at the class boundary
@@ -497,12 +524,12 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
                 ae[k] = tab.lr1s_speed * dve;
                 ao[k] = tab.ped_speed * dvo;
             }
-            const bool hk = has && t < n_pred[k];
+            const bool hk = kDense || (has && t < n_pred[k]);
             hm_e[k] = hk ? rmax_(hm_e[k], ae[k]) : hm_e[k];
             hm_o[k] = hk ? rmax_(hm_o[k], ao[k]) : hm_o[k];
             // within 5 m + half length of the centre: the three-point gate has to look (phase 2b)
             const R dx = g0.x - n0.x, dy = g0.y - n0.y;
-            const bool near = hk && (t + 1 < n_pred[k]) && (a.mahal || !(dx * dx + dy * dy > far2[k]));
+            const bool near = hk && (kDense || t + 1 < n_pred[k]) && (a.mahal || !(dx * dx + dy * dy > far2[k]));
             near_bits |= near ? (1u << k) : 0u;
         }
         const unsigned queued = __reduce_or_sync(kFull, near_bits);
@@ -511,23 +538,23 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
             for (int k = 0; k < kOB; ++k)
                 if (queued & (1u << k)) a.sm->queue[atomicAdd(a.qn, 1)] = ((unsigned)t << 16) | (unsigned)ok[k];
         }
-        if (pptr && a.active) {
+        if (pptr && (kDense || a.active)) {
 #pragma unroll
             for (int k = 0; k < kOB; ++k)
-                if (valid[k] && !(queued & (1u << k))) pptr[(size_t)ok[k] * a.Cp] = (R)0;
+                if (valid[k] && !(queued & (1u << k))) pptr[off[k]] = (R)0;
         }
         if (hptr && a.active) {  // optional per-sample harm (get_harm, harm_estimation.py:202)
 #pragma unroll
             for (int k = 0; k < kOB; ++k) {
                 if (!valid[k]) continue;
                 const bool hk = has && t < n_pred[k];
-                hptr[(size_t)ok[k] * a.Cp] = hk ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.lr1s_const, ae[k]) : (R)0;
-                hptr[a.harm_plane + (size_t)ok[k] * a.Cp] =
-                    hk ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.neg_ped_const, ao[k]) : (R)0;
+                hptr[off[k]] = hk ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.lr1s_const, ae[k]) : (R)0;
+                hptr[a.harm_plane + off[k]] = hk ? sigmoid_harm<R>(prot[k] ? tab.lr_const : tab.neg_ped_const, ao[k]) : (R)0;
             }
         }
         c0 = n0;
         c1 = n1;
+        gt += 2 * (size_t)O;
         if (pptr) pptr += (size_t)O * a.Cp;
         if (hptr) hptr += (size_t)O * a.Cp;
     }
@@ -545,10 +572,32 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
     }
 }
 
+// dispatch of one item to its specialisation
+template <typename R, int NT, bool kSym>
+__device__ __forceinline__ void phase2a_dispatch(const Phase2a<R>& a, int g, int seg, bool unprot, bool tile_fast,
+                                                 bool tile_full) {
+    // every obstacle of the group exists and is predicted over the whole segment?
+    bool full = tile_full && !a.o_harm && (g + 1) * kOB <= a.O;
+    if (full) {
+        const int t1 = min((seg + 1) * a.seg_len, a.Ts - 1);
+#pragma unroll
+        for (int k = 0; k < kOB; ++k) full = full && __ldg(a.st->pred_len + a.perm[g * kOB + k]) >= t1 + 1;
+    }
+    if (unprot) {
+        if (full) phase2a_item<R, NT, kSym, false, false, true>(a, g, seg);
+        else phase2a_item<R, NT, kSym, false, false, false>(a, g, seg);
+    } else if (tile_fast) {
+        if (full) phase2a_item<R, NT, kSym, true, true, true>(a, g, seg);
+        else phase2a_item<R, NT, kSym, true, true, false>(a, g, seg);
+    } else {
+        phase2a_item<R, NT, kSym, false, true, false>(a, g, seg);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // score_kernel
 // ---------------------------------------------------------------------------------------------
-template <typename R, int NT, bool kGiven>
+template <typename R, int NT, bool kSym, bool kGiven>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr, DevOut out,
              BestRec* __restrict__ block_best, unsigned int* __restrict__ counters, BestRec* __restrict__ best_out,
@@ -572,6 +621,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     const size_t harm_plane = (size_t)(Ts - 1) * O * Cp;
     const bool mahal = pr.mahalanobis != 0;
     const size_t mx_plane = (size_t)On * 32;
+    const bool small_planes = (size_t)On * Cp < (size_t)1 << 32;  // row offsets of the [.][O][Cp] planes fit 32 bits
 
     __shared__ Tab<R> tab;
     __shared__ int s_tile, s_item, s_qn, s_qpos;
@@ -658,6 +708,9 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                         w = (R)tp.f[ETP_F_YAW];
                     sm.e0[t * 32 + lane] = Vec4<R>{(R)tp.f[ETP_F_X], (R)tp.f[ETP_F_Y], (R)tp.cos_yaw, (R)tp.sin_yaw};
                     sm.e1[t * 32 + lane] = Vec2<R>{(R)tp.f[ETP_F_V], w};
+                    // rounding residue of the fp32 coordinates, at most half an ulp (3e-5 m at 500 m): kept to 11 bits
+                    sm.el[t * 32 + lane] = __floats2half2_rn((float)((tp.f[ETP_F_X] - (double)(R)tp.f[ETP_F_X]) * kLoScale),
+                                                             (float)((tp.f[ETP_F_Y] - (double)(R)tp.f[ETP_F_Y]) * kLoScale));
                     if (sizeof(R) == 4 && w != (R)kWrapFree) wf = 0;
                     sv += tp.f[ETP_F_V];
                     sd += fabs(tp.f[ETP_F_D]);
@@ -674,6 +727,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 } else {
                     sm.e0[t * 32 + lane] = Vec4<R>{(R)0, (R)0, (R)1, (R)0};
                     sm.e1[t * 32 + lane] = Vec2<R>{(R)0, sizeof(R) == 4 ? (R)kWrapFree : (R)0};
+                    sm.el[t * 32 + lane] = __floats2half2_rn(0.0f, 0.0f);
                     if (o_traj && active) {
 #pragma unroll
                         for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[((size_t)f * Ts + t) * Cp + cl] = (R)0;
@@ -690,6 +744,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             sm.ff[warp * 32 + lane] = first_fail;
         }
         const bool tile_fast = __syncthreads_and(wf) != 0;  // (b) ego samples complete; all of them wrap-free?
+        const bool tile_full = __all_sync(kFull, live && T == Ts) && small_planes;
 
         // ---- phase 2a: harm logits of every (t, o) sample, straight-line; samples inside the gate's reach are queued
         // item = (kOB obstacles, time segment).  Sample t of the harm model pairs ego[t] with prediction[t]
@@ -705,9 +760,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 if (item >= n_items) break;
                 const int g = item % n_groups, seg = item / n_groups;
                 const bool unprot = g * kOB >= s_nprot;  // groups are cut from the class-sorted obstacle order
-                if (unprot) phase2a_item<R, NT, false, false>(pa, g, seg);
-                else if (tile_fast) phase2a_item<R, NT, true, true>(pa, g, seg);
-                else phase2a_item<R, NT, false, true>(pa, g, seg);
+                phase2a_dispatch<R, NT, kSym>(pa, g, seg, unprot, tile_fast, tile_full);
             }
             __syncthreads();  // (b2) queue complete
 
@@ -752,7 +805,15 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                         const Vec4<R> p1 = ldg4<R>(tile.P + 2 * vi + 1);
                         prob = inv_mahalanobis<R>(n0.x, n0.y, g0.x, g0.y, p1.x, p1.y, p1.z);
                     } else {
-                        prob = collision_prob(tab, n0, g0, ldg4<R>(tile.P + 2 * vi), tile.N + kNodeVecs * vi);
+                        // ego centre - mean from split coordinates (see nine_rectangles)
+                        R ddx = n0.x - g0.x, ddy = n0.y - g0.y;
+                        if (sizeof(R) == 4) {
+                            const float2 lo = __half22float2(sm.el[(t + 1) * 32 + lane]);
+                            const float4 ml = __ldg(tile.N + kNodeVecs * vi + 4);
+                            ddx += (R)(lo.x * (1.0f / kLoScale) - ml.z);
+                            ddy += (R)(lo.y * (1.0f / kLoScale) - ml.w);
+                        }
+                        prob = collision_prob(tab, ddx, ddy, n0.z, n0.w, g0, ldg4<R>(tile.P + 2 * vi), tile.N + kNodeVecs * vi);
                     }
                     R ae, ao;
                     harm_logits<R, -1>(pr, tab, false, c0, c1, g0, g1, prt, cr.x, cr.y, ae, ao);
@@ -970,16 +1031,16 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 // ---------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------
-template <typename R, int NT, bool kGiven>
+template <typename R, int NT, bool kSym, bool kGiven>
 static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
                                   unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                                   cudaStream_t stream) {
     const int O = st.has_pred ? st.O : 0;
     const size_t smem = Smem<R>::bytes(st.Tmax, O);
-    cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT, kGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT, kSym, kGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT, kGiven>, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT, kSym, kGiven>, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     // persistent grid: every SM fully occupied, never more CTAs than there are tiles
@@ -989,25 +1050,27 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
-    score_kernel<R, NT, kGiven><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
+    score_kernel<R, NT, kSym, kGiven><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
     return cudaGetLastError();
 }
 
 cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
                          unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
                          cudaStream_t stream) {
-#define ETP_LAUNCH(R, NT) launch_score_t<R, NT, false>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream)
+#define ETP_LAUNCH(R, NT, SYM, GIVEN) \
+    launch_score_t<R, NT, SYM, GIVEN>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream)
     if (st.given) {  // caller-provided trajectories: the API-compatibility path, generic tables only
-        if (precision == ETP_PRECISION_FP64)
-            return launch_score_t<double, -1, true>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
-        return launch_score_t<float, -1, true>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream);
+        if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1, false, true);
+        return ETP_LAUNCH(float, -1, false, true);
     }
-    if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1);
+    if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1, false, false);
+    bool sym = true;  // LR4S / LR12S: one coefficient table for both sides
+    for (int i = 0; i <= pr.n_thr; ++i) sym = sym && pr.coef_pos[i] == pr.coef_neg[i];
     switch (pr.n_thr) {  // the reference's models: LR1S (0 thresholds), LR4S / LR4A (2), LR12S / LR12A (6)
-        case 0: return ETP_LAUNCH(float, 0);
-        case 2: return ETP_LAUNCH(float, 2);
-        case 6: return ETP_LAUNCH(float, 6);
-        default: return ETP_LAUNCH(float, -1);
+        case 0: return ETP_LAUNCH(float, 0, true, false);
+        case 2: return sym ? ETP_LAUNCH(float, 2, true, false) : ETP_LAUNCH(float, 2, false, false);
+        case 6: return sym ? ETP_LAUNCH(float, 6, true, false) : ETP_LAUNCH(float, 6, false, false);
+        default: return ETP_LAUNCH(float, -1, false, false);
     }
 #undef ETP_LAUNCH
 }
