@@ -193,6 +193,64 @@ __device__ __forceinline__ float rho_correction_f(const RhoNodes<N>& n, float xl
     return acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed (two fp32 lanes per instruction, FFMA2 / FMUL2 / FADD2 of sm_100) forms.  One un-gated evaluation is
+// 36 erfc and up to 216 exponentials; their polynomial and argument arithmetic pairs up naturally (the two ends
+// of an interval, the two x-limits of a corner pair), which halves the issue slots next to the MUFU ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
+// (Phi(xu) - Phi(xl), Phi(yu) - Phi(yl)): four erfc evaluations in two packed streams (same formula as erfc_f)
+__device__ __forceinline__ float2 dphi2_f(float xl, float xu, float yl, float yu) {
+    const float is2 = 0.70710678118654752440f;
+    const bool nx = (xl + xu) < 0.0f, ny = (yl + yu) < 0.0f;
+    // reflected so that lo + hi >= 0: hi >= |lo|, hi >= 0
+    const float lox = nx ? -xu : xl, hix = nx ? -xl : xu;
+    const float loy = ny ? -yu : yl, hiy = ny ? -yl : yu;
+    const float2 ax = make_float2(fabsf(lox), hix), ay = make_float2(fabsf(loy), hiy);
+    const float2 zx = __fmul2_rn(ax, splat2(is2)), zy = __fmul2_rn(ay, splat2(is2));
+    const float2 nzx = __fmul2_rn(ax, splat2(-is2)), nzy = __fmul2_rn(ay, splat2(-is2));
+    const float2 ux = __ffma2_rn(zx, splat2(0.5f), splat2(1.0f)), uy = __ffma2_rn(zy, splat2(0.5f), splat2(1.0f));
+    const float2 tx = make_float2(rcp_ftz(ux.x), rcp_ftz(ux.y)), ty = make_float2(rcp_ftz(uy.x), rcp_ftz(uy.y));
+    // polynomial of erfc_f scaled by log2(e): the exponential is taken as 2^(.)
+    const float L = 1.4426950408889634f;
+    float2 px = splat2(0.17087277f * L), py = px;
+#define ETP_P2(c) px = __ffma2_rn(px, tx, splat2((c) * L)); py = __ffma2_rn(py, ty, splat2((c) * L));
+    ETP_P2(-0.82215223f) ETP_P2(1.48851587f) ETP_P2(-1.13520398f) ETP_P2(0.27886807f) ETP_P2(-0.18628806f)
+    ETP_P2(0.09678418f) ETP_P2(0.37409196f) ETP_P2(1.00002368f) ETP_P2(-1.26551223f)
+#undef ETP_P2
+    const float2 zzx = __fmul2_rn(zx, zx), zzy = __fmul2_rn(zy, zy);
+    const float2 nex = __ffma2_rn(nzx, zx, zzx), ney = __ffma2_rn(nzy, zy, zzy);  // -(exact z^2 - rounded z^2)
+    const float2 gx = __ffma2_rn(splat2(-L), zzx, px), gy = __ffma2_rn(splat2(-L), zzy, py);
+    float2 rx = __fmul2_rn(tx, make_float2(ex2_ftz(gx.x), ex2_ftz(gx.y)));
+    float2 ry = __fmul2_rn(ty, make_float2(ex2_ftz(gy.x), ex2_ftz(gy.y)));
+    rx = __ffma2_rn(rx, nex, rx);
+    ry = __ffma2_rn(ry, ney, ry);
+    const float elx = lox >= 0.0f ? rx.x : 2.0f - rx.x, ely = loy >= 0.0f ? ry.x : 2.0f - ry.x;
+    return make_float2(0.5f * (elx - rx.y), 0.5f * (ely - ry.y));
+}
+
+// sum_i c_i * [E(xu,yu) - E(xl,yu) - E(xu,yl) + E(xl,yl)](theta_i), corner pairs (xl, xu) packed
+template <int N>
+__device__ __forceinline__ float rho_correction2_f(const RhoNodes<N>& n, float xl, float xu, float yl, float yu) {
+    if (N == 0) return 0.0f;
+    const float2 X = make_float2(xl, xu);
+    const float2 nxh = __fmul2_rn(__fmul2_rn(X, X), splat2(-0.5f));                 // -x^2 / 2
+    const float2 nyh = __fmul2_rn(__fmul2_rn(make_float2(yl, yu), make_float2(yl, yu)), splat2(-0.5f));
+    const float2 nhu = __fadd2_rn(nxh, splat2(nyh.y)), nhl = __fadd2_rn(nxh, splat2(nyh.x));  // -(x^2 + y^2) / 2
+    const float2 pu = __fmul2_rn(X, splat2(yu)), pl = __fmul2_rn(X, splat2(yl));    // x y
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float2 s = splat2(n.s[i]), q = splat2(n.q[i]);
+        const float2 au = __fmul2_rn(q, __ffma2_rn(s, pu, nhu)), al = __fmul2_rn(q, __ffma2_rn(s, pl, nhl));
+        const float2 eu = make_float2(ex2_ftz(au.x), ex2_ftz(au.y)), el = make_float2(ex2_ftz(al.x), ex2_ftz(al.y));
+        const float2 d = __ffma2_rn(el, splat2(-1.0f), eu);  // (E(xl,yu) - E(xl,yl), E(xu,yu) - E(xu,yl))
+        acc = fmaf(n.c[i], d.y - d.x, acc);
+    }
+    return acc;
+}
+
 // rectangles farther than this many standard deviations from the mean contribute < 1.3e-12 each (tail of the
 // nearer marginal), i.e. < 4e-12 to the stored probability: three orders below the 1e-9 absolute floor of the parity bar
 #define ETP_PRUNE_SIGMA 7.0f
@@ -200,7 +258,8 @@ __device__ __forceinline__ float rho_correction_f(const RhoNodes<N>& n, float xl
 template <int N>
 __device__ __forceinline__ float rect_prob_nodes_f(const RhoNodes<N>& n, float xl, float xu, float yl, float yu) {
     if (xl > ETP_PRUNE_SIGMA || xu < -ETP_PRUNE_SIGMA || yl > ETP_PRUNE_SIGMA || yu < -ETP_PRUNE_SIGMA) return 0.0f;
-    return dphi_f(xl, xu) * dphi_f(yl, yu) + rho_correction_f<N>(n, xl, xu, yl, yu);
+    const float2 d = dphi2_f(xl, xu, yl, yu);
+    return fmaf(d.x, d.y, rho_correction2_f<N>(n, xl, xu, yl, yu));
 }
 
 // strongly correlated predictions: fp64 Genz evaluation (kept out of line, rare)

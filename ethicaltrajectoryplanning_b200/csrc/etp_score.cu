@@ -301,16 +301,17 @@ template <int N> struct RectNodesF {
 template <typename R, typename Rect>
 __device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect, R ddx, R ddy, R c, R s, R ex, R ey, R isx,
                                              R isy, R rho) {
-    const R hx = pr.hx, hy = pr.hy, rr = pr.rr;
+    const R hx = pr.hx, hy = pr.hy;
+    const R ox = pr.rr * c, oy = pr.rr * s;  // offset of the outer boxes along the ego heading
     R prob = 0;
 #pragma unroll 1
     for (int km = 0; km < 3; ++km) {
         const R sg = km == 0 ? (R)0 : (km == 1 ? (R)1 : (R)-1);
         const R ux = ddx - sg * ex, uy = ddy - sg * ey;  // ego centre - mean_km
-#pragma unroll 1
+#pragma unroll 1  // the rectangle body stays one small loop: unrolled, its nine copies thrash the instruction cache
         for (int jb = 0; jb < 3; ++jb) {
             const R sb = jb == 0 ? (R)0 : (jb == 1 ? (R)1 : (R)-1);
-            const R bx = ux + sb * (rr * c), by = uy + sb * (rr * s);  // box centre - mean
+            const R bx = ux + sb * ox, by = uy + sb * oy;  // box centre - mean
             const R xl = (bx - hx) * isx, xu = (bx + hx) * isx;
             const R yl = (by - hy) * isy, yu = (by + hy) * isy;
             prob += rect(xl, xu, yl, yu, rho);
