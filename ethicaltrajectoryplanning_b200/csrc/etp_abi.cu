@@ -70,6 +70,8 @@ struct etp_ctx {
     // obstacles
     DevBuf o_pos, o_cov, o_yaw, o_vel, o_len, o_mass, o_plen, o_prot, o_resp, o_tile, o_const;
     int O = 0, Tp = 0, has_pred = 0;
+    double origin_x = 0.0, origin_y = 0.0;  // of the fp32 coordinates: first obstacle sample, else the spline start
+    std::vector<double> spline_pts, obs_box;  // knot positions (+ reach) and the bounding box of the predictions
     // step
     DevBuf grids, ext_level, bd_harm, factor_list, prof, prof_meta, nskip;
     DevBuf block_best, counters, best_dev, traj_dev, traj_n, given, given_T, prin;
@@ -251,6 +253,14 @@ int etp_set_spline(etp_ctx* c, const double* knots, const double* coef_x, const 
     if ((r = stage_to_device(c, c->cx.p, coef_x, sizeof(double) * 4 * n_seg))) return r;
     if ((r = stage_to_device(c, c->cy.p, coef_y, sizeof(double) * 4 * n_seg))) return r;
     c->nseg = n_seg;
+    c->spline_pts.clear();
+    for (int i = 0; i < n_seg; ++i) {
+        // knot position and the reach of the segment (|b| ds bounds the excursion to first order, doubled for slack)
+        const double ds = knots[i + 1] - knots[i];
+        c->spline_pts.push_back(coef_x[4 * i]);
+        c->spline_pts.push_back(coef_y[4 * i]);
+        c->spline_pts.push_back(2.0 * std::fmax(std::fabs(coef_x[4 * i + 1]), std::fabs(coef_y[4 * i + 1])) * ds);
+    }
     c->have_spline = true;
     return end_staging(c);
 }
@@ -261,6 +271,8 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
     if (!c->have_params) ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params must precede etp_set_obstacles (mass ratios use the ego mass)");
     ETP_CUDA(c, cudaSetDevice(c->device));
     c->precision = precision;
+    c->obs_box.clear();
+    c->origin_x = c->origin_y = 0.0;
     if (o->n_obstacles < 0) {  // predictions is None
         c->has_pred = 0; c->O = 0; c->Tp = 0; c->have_obs = true;
         return ETP_OK;
@@ -281,6 +293,15 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         int r = begin_staging(c);
         if (r) return r;
         const size_t n = (size_t)O * Tp;
+        c->origin_x = o->pos[0];
+        c->origin_y = o->pos[1];
+        c->obs_box.assign({o->pos[0], o->pos[0], o->pos[1], o->pos[1]});
+        for (int i = 0; i < O; ++i)
+            for (int t = 0; t < o->pred_len[i]; ++t) {
+                const double* q = o->pos + ((size_t)i * Tp + t) * 2;
+                c->obs_box[0] = std::fmin(c->obs_box[0], q[0]); c->obs_box[1] = std::fmax(c->obs_box[1], q[0]);
+                c->obs_box[2] = std::fmin(c->obs_box[2], q[1]); c->obs_box[3] = std::fmax(c->obs_box[3], q[1]);
+            }
         ETP_CUDA(c, c->o_pos.reserve(sizeof(double) * 2 * n));
         ETP_CUDA(c, c->o_cov.reserve(sizeof(double) * 4 * n));
         ETP_CUDA(c, c->o_yaw.reserve(sizeof(double) * n));
@@ -305,7 +326,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
                                           c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
-                                          c->o_tile.p, c->o_const.as<double>(), c->stream));
+                                          c->origin_x, c->origin_y, c->o_tile.p, c->o_const.as<double>(), c->stream));
     }
     c->O = O;
     c->Tp = Tp;
@@ -393,6 +414,24 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
         st.n_local = np_loc * s->nd;
     }
     st.vel_mode = s->velocity_cost_mode; st.vel_target = s->velocity_target; st.factor = s->cost_factor;
+    {
+        // 2 ulp (fp32) of the largest coordinate, relative to the origin, a candidate or an obstacle can take
+        double dmax = 0.0, m = 0.0;
+        for (int i = 0; i < s->nd; ++i) dmax = std::fmax(dmax, std::fabs(s->d_list[i]));
+        if (c->obs_box.empty()) {  // no obstacles: the fp32 coordinates are not used for anything position critical
+            c->origin_x = c->spline_pts.empty() ? 0.0 : c->spline_pts[0];
+            c->origin_y = c->spline_pts.empty() ? 0.0 : c->spline_pts[1];
+        } else {
+            m = std::fmax(std::fmax(std::fabs(c->obs_box[0] - c->origin_x), std::fabs(c->obs_box[1] - c->origin_x)),
+                          std::fmax(std::fabs(c->obs_box[2] - c->origin_y), std::fabs(c->obs_box[3] - c->origin_y)));
+        }
+        for (size_t i = 0; i + 2 < c->spline_pts.size(); i += 3)
+            m = std::fmax(m, std::fmax(std::fabs(c->spline_pts[i] - c->origin_x), std::fabs(c->spline_pts[i + 1] - c->origin_y)) +
+                                 c->spline_pts[i + 2]);
+        st.eps_pos = 2.4e-7 * (m + dmax + 16.0);
+        st.origin_x = c->origin_x;
+        st.origin_y = c->origin_y;
+    }
     st.knots = c->knots.as<double>(); st.cx = c->cx.as<double>(); st.cy = c->cy.as<double>(); st.nseg = c->nseg;
     const int n_prof = st.p_end - st.p_begin;
     ETP_CUDA(c, c->prof.reserve(sizeof(double) * PF_COUNT * Tmax * (size_t)n_prof));
@@ -471,6 +510,23 @@ int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out*
     st.c_begin = 0; st.c_end = g->n_traj; st.p_begin = 0; st.p_end = 1;
     st.shard_count = 1; st.shard_index = 0; st.n_local = g->n_traj;
     st.vel_mode = g->velocity_cost_mode; st.vel_target = g->velocity_target; st.factor = g->cost_factor;
+    {
+        if (c->obs_box.empty()) {
+            c->origin_x = g->fields[(size_t)ETP_F_X * g->t_max * n];
+            c->origin_y = g->fields[(size_t)ETP_F_Y * g->t_max * n];
+        }
+        double m = 0.0;
+        if (!c->obs_box.empty())
+            m = std::fmax(std::fmax(std::fabs(c->obs_box[0] - c->origin_x), std::fabs(c->obs_box[1] - c->origin_x)),
+                          std::fmax(std::fabs(c->obs_box[2] - c->origin_y), std::fabs(c->obs_box[3] - c->origin_y)));
+        const size_t plane = (size_t)g->t_max * n;
+        for (size_t i = 0; i < plane; ++i)
+            m = std::fmax(m, std::fmax(std::fabs(g->fields[ETP_F_X * plane + i] - c->origin_x),
+                                       std::fabs(g->fields[ETP_F_Y * plane + i] - c->origin_y)));
+        st.eps_pos = 2.4e-7 * (m + 16.0);
+        st.origin_x = c->origin_x;
+        st.origin_y = c->origin_y;
+    }
     st.has_pred = c->has_pred; st.O = c->O; st.Tp = c->Tp;
     st.obs = c->o_tile.p; st.obs_const = c->o_const.as<double>(); st.pred_len = c->o_plen.as<int>();
     st.raw_pos = c->o_pos.as<double>(); st.raw_yaw = c->o_yaw.as<double>();

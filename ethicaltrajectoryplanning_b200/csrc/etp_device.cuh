@@ -85,6 +85,8 @@ struct DevStep {
     int shard_index, shard_count, n_local;  // this call scores profiles p_begin + shard_index + k * shard_count
     int vel_mode;
     double vel_target, factor;
+    double eps_pos;            // fp32 rounding of a position difference in this step's coordinate range [m]
+    double origin_x, origin_y; // fp32 ego samples and the obstacle tile are relative to this point
     const uint8_t* ext_level;  // device copy, indexed by dense candidate, or null
     const double* bd_harm;     // device copy, indexed by dense candidate, or null
     const double* factor_list; // device copy, indexed by dense candidate, or null (then `factor`)

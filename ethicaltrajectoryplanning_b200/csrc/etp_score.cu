@@ -101,11 +101,12 @@ template <typename R> struct Tab {
     R thr[ETP_MAX_ANGLE_BINS], fcos[ETP_MAX_ANGLE_BINS], coef_pos[ETP_MAX_ANGLE_BINS + 1], coef_neg[ETP_MAX_ANGLE_BINS + 1];
     R lr_speed, lr1s_speed, ped_speed, lr_const, lr1s_const, neg_ped_const;
     R coef_max;    // largest impact-area coefficient: upper bound of the harm logit without looking at the angle
+    R eps_pos;     // fp32 rounding of a position difference in metres (2 ulp of the largest coordinate in play)
     R hx, hy, rr;  // ego box half extents (l/6, w/2) and centre offset (l/2)(2/3)  (collision_probability.py:157,349-362)
     int n_thr;
 };
 
-template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const DevParams& pr) {
+template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const DevParams& pr, double eps_pos) {
     for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) { tb.thr[i] = (R)pr.thr[i]; tb.fcos[i] = (R)pr.fcos[i]; }
     for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { tb.coef_pos[i] = (R)pr.coef_pos[i]; tb.coef_neg[i] = (R)pr.coef_neg[i]; }
     R cm = tb.coef_pos[0];
@@ -115,6 +116,7 @@ template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const
     tb.lr_const = (R)pr.lr_const; tb.lr1s_const = (R)pr.lr1s_const; tb.neg_ped_const = (R)(-pr.ped_const);
     tb.hx = (R)(pr.veh_l / 6); tb.hy = (R)(pr.veh_w / 2); tb.rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
     tb.n_thr = pr.n_thr;
+    tb.eps_pos = (R)eps_pos;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -141,12 +143,24 @@ template <typename R> __device__ __forceinline__ R angle_coef(const Tab<R>& pr, 
 
 // Band of an impact angle given as a direction: P = |d| cos(angle), d2 = |d|^2.  |angle| < thr is
 // cos(angle) > cos(thr), compared through the sign-preserving squares P|P| > d2 * cos(thr)|cos(thr)|.
-__device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, float d2) {
+// `tol` bounds what fp32 rounding (of the positions above all) can move a test by; a test closer to its threshold
+// than that sets `amb`, and the caller repeats the decision in fp64 from the exact inputs (band_coefs_exact).
+__device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, float d2, float tol, bool& amb) {
     // thresholds increase, so the tests pass from some band on: the band is the number of failed tests
     const float fp = P * fabsf(P);
     int band = 0;
-    for (int i = 0; i < pr.n_thr; ++i) band += (fp > d2 * pr.fcos[i]) ? 0 : 1;
+    for (int i = 0; i < pr.n_thr; ++i) {
+        const float df = fmaf(-d2, pr.fcos[i], fp);
+        band += (df > 0.0f) ? 0 : 1;
+        amb = amb || fabsf(df) < tol;
+    }
     return band;
+}
+
+// tolerance of a band test: the direction (dx, dy) carries the rounding of two positions (eps_pos metres in total),
+// which moves P|P| - d2 f by at most |d| eps_pos <= sqrt(2) max(|dx|, |dy|) eps_pos; the arithmetic adds a few ulps of d2
+__device__ __forceinline__ float band_tol(float d2, float dx, float dy, float eps_pos) {
+    return __fmaf_rn(fmaxf(fabsf(dx), fabsf(dy)), __fmul_rn(1.4143f, eps_pos), __fmul_rn(d2, 1e-6f));
 }
 
 // Impact-area coefficients of ego and obstacle, fp32 path.  `ewrap` are the whole turns that bring the ego yaw
@@ -155,27 +169,30 @@ __device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, flo
 // rotated into the ego / obstacle frame (P, Q) and the number of 2 pi wraps of the un-wrapped difference is
 // recovered from the half planes of the two directions.  |angle| > pi always lands in the last ("rear") band.
 __device__ __forceinline__ void impact_coefs(const Tab<float>& pr, float ex, float ey, float ec, float es, float ewrap,
-                                             float mx, float my, float ocp, float osp, float ocode, float& ce, float& co) {
+                                             float mx, float my, float ocp, float osp, float ocode, float& ce, float& co,
+                                             bool& amb) {
     const float dx = mx - ex, dy = my - ey;
     const float d2 = dx * dx + dy * dy;
+    const float tol = band_tol(d2, dx, dy, pr.eps_pos);
     const int last = pr.n_thr;
     // ego: angle = rel - yaw_e
     const float p = dx * ec + dy * es, q = dy * ec - dx * es;
     int n0 = 0;
     if (dy >= 0 && es < 0 && q < 0) n0 = 1;
     if (dy < 0 && es >= 0 && q > 0) n0 = -1;
-    const int be = ((float)n0 != ewrap) ? last : direction_band(pr, p, d2);
+    const int be = ((float)n0 != ewrap) ? last : direction_band(pr, p, d2, tol, amb);
     ce = q < 0 ? pr.coef_neg[be] : pr.coef_pos[be];
     // obstacle: angle = pi + rel - psi_o; `ocode` is the validity table of pack_obstacles_kernel
     const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
     const bool pos = qo < 0 || (qo == 0 && po >= 0);
     const bool valid = ((__float_as_int(ocode) >> ((pos ? 2 : 0) | (dy >= 0 ? 1 : 0))) & 1) != 0;
     const bool neg_side = !pos && valid;
-    const int bo = valid ? direction_band(pr, -po, d2) : last;
+    const int bo = valid ? direction_band(pr, -po, d2, tol, amb) : last;
     co = neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo];
 }
 __device__ __forceinline__ void impact_coefs(const Tab<double>& pr, double ex, double ey, double, double, double eyaw,
-                                             double mx, double my, double, double, double opsi, double& ce, double& co) {
+                                             double mx, double my, double, double, double opsi, double& ce, double& co,
+                                             bool&) {
     const double rel = atan2(my - ey, mx - ex);  // harm_estimation.py:314-319
     ce = angle_coef<double>(pr, rel - eyaw);
     co = angle_coef<double>(pr, 3.14159265358979323846 + rel - opsi);
@@ -184,18 +201,75 @@ __device__ __forceinline__ void impact_coefs(const Tab<double>& pr, double ex, d
 template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { return (R)1 / ((R)1 + exp_(-cst - arg)); }
 
 // ---------------------------------------------------------------------------------------------
+// exact (fp64) impact-area coefficients of one (candidate, sample, obstacle): the fp32 paths call this when a band
+// test is too close to its threshold to be decided in fp32.  Everything is recomputed from the exact inputs the way
+// the reference does it: rel = atan2(dy, dx), angles rel - yaw_e and pi + rel - psi_o, un-wrapped
+// (harm_estimation.py:313-319; logistic_regression_*.py).
+// ---------------------------------------------------------------------------------------------
+struct ExactRef {
+    const DevStep* st;
+    const DevParams* pr;
+    bool given;
+    int pl, id, t, o;
+};
+
+__device__ __forceinline__ double angle_coef_exact(const DevParams& pr, double angle) {
+    const double a = fabs(angle);
+    int i = 0;
+    while (i < pr.n_thr && !(a < pr.thr[i])) ++i;
+    return angle < 0.0 ? pr.coef_neg[i] : pr.coef_pos[i];
+}
+
+__device__ __noinline__ void band_coefs_exact(const ExactRef& r, double& ce, double& co) {
+    const DevStep& st = *r.st;
+    double xe, ye, yaw;
+    if (r.given) {
+        const double* g = st.given + r.pl;
+        xe = g[((size_t)ETP_F_X * st.Tmax + r.t) * st.given_stride];
+        ye = g[((size_t)ETP_F_Y * st.Tmax + r.t) * st.given_stride];
+        yaw = g[((size_t)ETP_F_YAW * st.Tmax + r.t) * st.given_stride];
+    } else {
+        const double* gp = st.prof + (size_t)r.pl * PF_COUNT * st.Tmax;
+        const double* pm = st.prof_meta + (size_t)r.pl * PM_COUNT;
+        const bool low = pm[PM_LOW] != 0.0;
+        const Poly5 q = lateral_poly(st, low, st.d_list[r.id], pm[PM_TEND], pm[PM_DS]);
+        const TrajPoint tp = traj_point(q, low, gp, st.Tmax, r.t, st.dt);
+        xe = tp.f[ETP_F_X];
+        ye = tp.f[ETP_F_Y];
+        yaw = tp.f[ETP_F_YAW];
+    }
+    const double* rp = st.raw_pos + ((size_t)r.o * st.Tp + r.t) * 2;
+    const double psi = st.raw_yaw[(size_t)r.o * st.Tp + r.t];
+    const double rel = atan2(rp[1] - ye, rp[0] - xe);
+    ce = angle_coef_exact(*r.pr, rel - yaw);
+    co = angle_coef_exact(*r.pr, 3.14159265358979323846 + rel - psi);
+}
+
+// ---------------------------------------------------------------------------------------------
 // harm logits of one (ego sample t, prediction sample t) pair, the streaming form of phase 2
 // ---------------------------------------------------------------------------------------------
 // Coefficient of the geometric band of a direction (fp = P|P|, d2): first threshold whose test passes.  NT
 // thresholds are compile-time; thresholds and coefficients are constant-bank operands (no loads, no loop).
 // kSym: both sides share one coefficient table (the symmetric models), the side is not looked at.
-template <int NT, bool kSym> __device__ __forceinline__ float chain_coef(const DevParams& pr, float fp, float d2, bool neg) {
+// The reference's threshold sets are symmetric about pi/2 (45/135 and 15/45/75/105/135/165 degrees), i.e.
+// fcos[NT-1-i] = -fcos[i]: the launcher checks this before it picks a specialisation.  Then the distance of fp to the
+// nearest threshold is min_j | |fp| - d2 fcos[j] | over the NT/2 positive ones: one test per pair decides whether the
+// sample is too close to call in fp32 (`amb`, see direction_band).
+template <int NT, bool kSym>
+__device__ __forceinline__ float chain_coef(const DevParams& pr, float fp, float d2, bool neg, float tol, bool& amb) {
     float coef = (!kSym && neg) ? pr.f_coef_neg[NT] : pr.f_coef_pos[NT];
+    float h[NT / 2 > 0 ? NT / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j) h[j] = __fmul_rn(d2, pr.f_fcos[j]);
 #pragma unroll
     for (int i = NT - 1; i >= 0; --i) {
         const float ci = (!kSym && neg) ? pr.f_coef_neg[i] : pr.f_coef_pos[i];
-        coef = (fp > d2 * pr.f_fcos[i]) ? ci : coef;
+        const bool pass = i < NT / 2 ? fp > h[i] : fp > -h[NT - 1 - i];
+        coef = pass ? ci : coef;
     }
+    const float af = fabsf(fp);
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j) amb = amb || fabsf(__fsub_rn(af, h[j])) < tol;
     return coef;
 }
 
@@ -214,14 +288,18 @@ template <typename R, int NT, bool kSym = false> struct Logits {
         return delta_v(c0.z, c0.w, c1.x, 0.0f, g1.x, g1.y, g1.z, 0.0f);
     }
     // impact-area coefficients of ego and obstacle for a protected obstacle; branch free
-    static __device__ __forceinline__ void coefs(const DevParams& pr, const Tab<float>&, bool fast_ego, Vec4<float> c0,
-                                                 Vec2<float> c1, Vec4<float> g0, Vec4<float> g1, float& ce, float& co) {
-        const float dx = g0.x - c0.x, dy = g0.y - c0.y;
-        const float d2 = dx * dx + dy * dy;
+    static __device__ __forceinline__ void coefs(const DevParams& pr, const Tab<float>& tab, bool fast_ego, Vec4<float> c0,
+                                                 Vec2<float> c1, Vec4<float> g0, Vec4<float> g1, float& ce, float& co,
+                                                 bool& amb) {
+        // every rounding below is spelled out (no contraction freedom): phase 2b repeats this test on the samples
+        // phase 2a flagged and must find the same lanes
+        const float dx = __fsub_rn(g0.x, c0.x), dy = __fsub_rn(g0.y, c0.y);
+        const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+        const float tol = band_tol(d2, dx, dy, tab.eps_pos);
         const float ec = c0.z, es = c0.w, ocp = g1.y, osp = g1.z;
         // ego: angle = rel - yaw_e
-        const float p = dx * ec + dy * es, q = dy * ec - dx * es;
-        ce = chain_coef<NT, kSym>(pr, p * fabsf(p), d2, q < 0);
+        const float p = __fmaf_rn(dx, ec, __fmul_rn(dy, es)), q = __fmaf_rn(dy, ec, -__fmul_rn(dx, es));
+        ce = chain_coef<NT, kSym>(pr, __fmul_rn(p, fabsf(p)), d2, q < 0, tol, amb);
         if (!fast_ego) {
             int n0 = 0;
             if (dy >= 0 && es < 0 && q < 0) n0 = 1;
@@ -231,11 +309,11 @@ template <typename R, int NT, bool kSym = false> struct Logits {
             ce = ((float)n0 != ewrap) ? cl : ce;
         }
         // obstacle: angle = pi + rel - psi_o
-        const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
+        const float po = __fmaf_rn(dx, ocp, __fmul_rn(dy, osp)), qo = __fmaf_rn(dy, ocp, -__fmul_rn(dx, osp));
         const bool pos = qo < 0 || (qo == 0 && po >= 0);
         const int code = __float_as_int(g1.w);  // validity table, stored as raw bits in the fp32 tile
         const bool valid = ((code >> ((pos ? 2 : 0) | (dy >= 0 ? 1 : 0))) & 1) != 0;
-        co = chain_coef<NT, kSym>(pr, -po * fabsf(po), d2, !pos);
+        co = chain_coef<NT, kSym>(pr, -__fmul_rn(po, fabsf(po)), d2, !pos, tol, amb);
         co = valid ? co : pr.f_coef_pos[NT];
     }
 };
@@ -247,28 +325,11 @@ template <typename R, bool kSym> struct Logits<R, -1, kSym> {
         return delta_v(c0.z, c0.w, c1.x, ewrap, g1.x, g1.y, g1.z, g1.w);
     }
     static __device__ __forceinline__ void coefs(const DevParams&, const Tab<R>& tab, bool, Vec4<R> c0, Vec2<R> c1, Vec4<R> g0,
-                                                 Vec4<R> g1, R& ce, R& co) {
+                                                 Vec4<R> g1, R& ce, R& co, bool& amb) {
         const R ewrap = (sizeof(R) == 4 && c1.y == (R)kWrapFree) ? (R)0 : c1.y;
-        impact_coefs(tab, c0.x, c0.y, c0.z, c0.w, ewrap, g0.x, g0.y, g1.y, g1.z, g1.w, ce, co);
+        impact_coefs(tab, c0.x, c0.y, c0.z, c0.w, ewrap, g0.x, g0.y, g1.y, g1.z, g1.w, ce, co, amb);
     }
 };
-
-// both logits of one sample: arg = speed * (mass ratio * dv) + impact coefficient (harm_estimation.py:322-332)
-template <typename R, int NT>
-__device__ __forceinline__ void harm_logits(const DevParams& pr, const Tab<R>& tab, bool fast_ego, Vec4<R> c0, Vec2<R> c1,
-                                            Vec4<R> g0, Vec4<R> g1, bool prot, R ke, R ko, R& ae, R& ao) {
-    const R dv = Logits<R, NT>::dv(c0, c1, g1);
-    const R dve = ke * dv, dvo = ko * dv;
-    if (prot) {
-        R ce, co;
-        Logits<R, NT>::coefs(pr, tab, fast_ego, c0, c1, g0, g1, ce, co);
-        ae = tab.lr_speed * dve + ce;
-        ao = tab.lr_speed * dvo + co;
-    } else {
-        ae = tab.lr1s_speed * dve;
-        ao = tab.ped_speed * dvo;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // collision probability of one (ego sample i = t+1, obstacle sample t) pair
@@ -322,12 +383,12 @@ __device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect,
 
 // `c`, `s` = cos / sin of the ego yaw, `g` = (mx, my, ex, ey), `p` = (1/sx, 1/sy, rho, class), `nd` = the five node
 // vectors of this (t, o) record.  All lanes of a warp share g, p and nd.
-__device__ __noinline__ double collision_prob(const Tab<double>& pr, double ddx, double ddy, double c, double s,
+__device__ __forceinline__ double collision_prob(const Tab<double>& pr, double ddx, double ddy, double c, double s,
                                               Vec4<double> g, Vec4<double> p, const float4*) {
     return nine_rectangles<double>(pr, RectDouble{}, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
 }
 
-__device__ __noinline__ float collision_prob(const Tab<float>& pr, float ddx, float ddy, float c, float s, Vec4<float> g,
+__device__ __forceinline__ float collision_prob(const Tab<float>& pr, float ddx, float ddy, float c, float s, Vec4<float> g,
                                              Vec4<float> p, const float4* nd) {
     const int cls = (int)p.w;  // warp-uniform: Gauss-Legendre node class of |rho| (pack_obstacles_kernel)
     if (cls == RC_ZERO) {
@@ -352,6 +413,26 @@ __device__ __noinline__ float collision_prob(const Tab<float>& pr, float ddx, fl
     r.n.q[0] = b.z; r.n.q[1] = b.w; r.n.q[2] = cc.x; r.n.q[3] = cc.y; r.n.q[4] = cc.z; r.n.q[5] = cc.w;
     r.n.c[0] = d.x; r.n.c[1] = d.y; r.n.c[2] = d.z; r.n.c[3] = d.w; r.n.c[4] = f.x; r.n.c[5] = f.y;
     return nine_rectangles<float>(pr, r, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
+}
+
+// The one out-of-line call of phase 2b: rectangle probability of an un-gated sample and, for the rare lane whose
+// band test fp32 could not decide (`amb`), the exact impact-area coefficients.  Keeping both behind a single call site
+// keeps the register allocation of the calling loop tight.
+template <typename R> struct ProbCoef {
+    R prob, ce, co;
+};
+template <typename R>
+__device__ __noinline__ ProbCoef<R> ungated_eval(const Tab<R>& tab, R ddx, R ddy, R c, R s, Vec4<R> g, Vec4<R> p, const float4* nd,
+                                                 bool with_prob, bool amb, ExactRef xr, R ce, R co) {
+    ProbCoef<R> r{(R)0, ce, co};
+    if (with_prob) r.prob = collision_prob(tab, ddx, ddy, c, s, g, p, nd);
+    if (amb) {
+        double a, b;
+        band_coefs_exact(xr, a, b);
+        r.ce = (R)a;
+        r.co = (R)b;
+    }
+    return r;
 }
 
 // 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
@@ -457,8 +538,8 @@ template <typename R> struct Phase2a {
     const int* perm;
     int* qn;
     size_t Cp, harm_plane, mx_plane;
-    int O, Ts, Tl, cl, lane, seg_len, n_seg;
-    bool active, mahal;
+    int O, Ts, Tl, cl, lane, seg_len, n_seg, pl, id;
+    bool active, mahal, given;
 };
 
 // The four samples of a step are independent dependency chains in ONE basic block (loads are clamped instead of
@@ -504,7 +585,7 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
         const Vec4<R> n0 = a.sm->e0[(t + 1) * 32 + lane];
         const Vec2<R> n1 = a.sm->e1[(t + 1) * 32 + lane];
         const bool has = kDense || t < a.Tl - 1;  // this lane's candidate has harm sample t (and ego sample t+1)
-        unsigned near_bits = 0;
+        unsigned near_bits = 0, amb_bits = 0;
         R ae[kOB], ao[kOB];
 #pragma unroll
         for (int k = 0; k < kOB; ++k) {
@@ -514,9 +595,15 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
             const Vec4<R> g0 = ldg4<R>(gp), g1 = ldg4<R>(gp + 1);
             const R dv = L::dv(c0, c1, g1);
             const R dve = ke[k] * dv, dvo = ko[k] * dv;
+            const bool hk = kDense || (has && t < n_pred[k]);
+            bool use = hk;  // the sample enters the running maxima here
             if (kProt) {
                 R ce, co;
-                L::coefs(pr, tab, kFastEgo, c0, c1, g0, g1, ce, co);
+                bool amb = false;
+                L::coefs(pr, tab, kFastEgo, c0, c1, g0, g1, ce, co, amb);
+                amb = amb && prot[k] && hk;
+                amb_bits |= amb ? (1u << k) : 0u;
+                use = hk && !amb;  // too close to call: redone exactly below / in phase 2b
                 const R pe = tab.lr_speed * dve + ce, po = tab.lr_speed * dvo + co;
                 const R ue = tab.lr1s_speed * dve, uo = tab.ped_speed * dvo;
                 ae[k] = prot[k] ? pe : ue;  // a mixed group at the class boundary
@@ -525,19 +612,23 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
                 ae[k] = tab.lr1s_speed * dve;
                 ao[k] = tab.ped_speed * dvo;
             }
-            const bool hk = kDense || (has && t < n_pred[k]);
-            hm_e[k] = hk ? rmax_(hm_e[k], ae[k]) : hm_e[k];
-            hm_o[k] = hk ? rmax_(hm_o[k], ao[k]) : hm_o[k];
+            hm_e[k] = use ? rmax_(hm_e[k], ae[k]) : hm_e[k];
+            hm_o[k] = use ? rmax_(hm_o[k], ao[k]) : hm_o[k];
             // within 5 m + half length of the centre: the three-point gate has to look (phase 2b)
             const R dx = g0.x - n0.x, dy = g0.y - n0.y;
             const bool near = hk && (kDense || t + 1 < n_pred[k]) && (a.mahal || !(dx * dx + dy * dy > far2[k]));
             near_bits |= near ? (1u << k) : 0u;
         }
-        const unsigned queued = __reduce_or_sync(kFull, near_bits);
+        const unsigned flags = __reduce_or_sync(kFull, near_bits | (amb_bits << kOB));
+        // queued: within reach of the gate, or a band test some lane could not decide in fp32 (left out of the maxima
+        // above, flagged, redone in fp64 in phase 2b)
+        const unsigned ambq = kProt ? (flags >> kOB) : 0u;
+        const unsigned queued = (flags | ambq) & ((1u << kOB) - 1u);
         if (queued && lane == 0) {
 #pragma unroll
             for (int k = 0; k < kOB; ++k)
-                if (queued & (1u << k)) a.sm->queue[atomicAdd(a.qn, 1)] = ((unsigned)t << 16) | (unsigned)ok[k];
+                if (queued & (1u << k))
+                    a.sm->queue[atomicAdd(a.qn, 1)] = ((unsigned)t << 16) | (((ambq >> k) & 1u) << 15) | (unsigned)ok[k];
         }
         if (pptr && (kDense || a.active)) {
 #pragma unroll
@@ -631,7 +722,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     __shared__ int s_nprot;
     int* s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);  // [On] obstacles sorted by class
     if (tid == 0) {
-        fill_tab<R>(tab, pr);
+        fill_tab<R>(tab, pr, st.eps_pos);
         // protected obstacles first: a phase-2a item then holds one class and needs no per-sample class branch
         int n = 0;
         for (int o = 0; o < O; ++o)
@@ -707,11 +798,11 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                         w = (tp.wrap == 0.0 && fabs(tp.f[ETP_F_YAW]) <= pr.wrapfree_yaw) ? (R)kWrapFree : (R)tp.wrap;
                     else
                         w = (R)tp.f[ETP_F_YAW];
-                    sm.e0[t * 32 + lane] = Vec4<R>{(R)tp.f[ETP_F_X], (R)tp.f[ETP_F_Y], (R)tp.cos_yaw, (R)tp.sin_yaw};
+                    const double xr = tp.f[ETP_F_X] - st.origin_x, yr = tp.f[ETP_F_Y] - st.origin_y;  // relative to the step origin
+                    sm.e0[t * 32 + lane] = Vec4<R>{(R)xr, (R)yr, (R)tp.cos_yaw, (R)tp.sin_yaw};
                     sm.e1[t * 32 + lane] = Vec2<R>{(R)tp.f[ETP_F_V], w};
                     // rounding residue of the fp32 coordinates, at most half an ulp (3e-5 m at 500 m): kept to 11 bits
-                    sm.el[t * 32 + lane] = __floats2half2_rn((float)((tp.f[ETP_F_X] - (double)(R)tp.f[ETP_F_X]) * kLoScale),
-                                                             (float)((tp.f[ETP_F_Y] - (double)(R)tp.f[ETP_F_Y]) * kLoScale));
+                    sm.el[t * 32 + lane] = __floats2half2_rn((float)((xr - (double)(R)xr) * kLoScale), (float)((yr - (double)(R)yr) * kLoScale));
                     if (sizeof(R) == 4 && w != (R)kWrapFree) wf = 0;
                     sv += tp.f[ETP_F_V];
                     sd += fabs(tp.f[ETP_F_D]);
@@ -753,7 +844,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         // orientation[t+1] (collision_probability.py:168-203).
         if (O > 0) {
             Phase2a<R> pa{&st, &pr, &tab, &sm, tile.G, tile.C, o_prob, o_harm, s_perm, &s_qn, Cp, harm_plane, mx_plane, O, Ts, Tl, cl, lane,
-                          seg_len, n_seg, active, mahal};
+                          seg_len, n_seg, pl, id, active, mahal, kGiven};
             for (;;) {
                 int item = 0;
                 if (lane == 0) item = atomicAdd(&s_item, 1);
@@ -773,13 +864,16 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 e = __shfl_sync(kFull, e, 0);
                 if (e >= qn) break;
                 const unsigned ent = sm.queue[e];
-                const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
+                const int t = (int)(ent >> 16), o = (int)(ent & 0x7fffu);
+                const bool amb_entry = (ent >> 15) & 1u;
                 const size_t vi = (size_t)t * O + o;
                 const bool has = t < Tl - 1;
                 const Vec4<R> n0 = sm.e0[(t + 1) * 32 + lane];
                 const Vec4<R> g0 = ldg4<R>(tile.G + 2 * vi);
-                bool ungated = has;
-                if (!mahal) {
+                // entries flagged for a band re-check may lie past the probability's range (t + 1 < Tp)
+                const bool in_range = has && t + 1 < __ldg(st.pred_len + o);
+                bool ungated = in_range;
+                if (!mahal && in_range) {
                     const R x = n0.x, y = n0.y;
                     R dx = g0.x - x, dy = g0.y - y;
                     R d2 = dx * dx + dy * dy;
@@ -788,10 +882,10 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     dx = (g0.x - g0.z) - x; dy = (g0.y - g0.w) - y;
                     d2 = fmin(d2, dx * dx + dy * dy);
                     if (sizeof(R) == 8) {
-                        ungated = has && !(sqrt_(d2) > (R)5.0);
+                        ungated = !(sqrt_(d2) > (R)5.0);
                     } else {
-                        ungated = has && !(d2 > (R)25.0);
-                        if (has && abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y)))
+                        ungated = !(d2 > (R)25.0);
+                        if (abs_(d2 - (R)25) < (R)2e-3 + (R)1e-5 * (abs_(x) + abs_(y)))
                             ungated = !gate_exact(&st, kGiven, pl, id, t + 1, o, t);  // fp32 cannot decide: repeat in fp64
                     }
                 }
@@ -802,27 +896,58 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     const Vec4<R> g1 = ldg4<R>(tile.G + 2 * vi + 1);
                     const Vec4<R> cr = ldg4<R>(tile.C + o);
                     const bool prt = cr.z != (R)0;
+                    // harm coefficients of sample t in fp32 (same code as phase 2a), `amb` if fp32 cannot decide a band
+                    R ce = 0, co = 0;
+                    bool amb = false;
+                    if (prt) Logits<R, NT, kSym>::coefs(pr, tab, tile_fast, c0, c1, g0, g1, ce, co, amb);
+                    // ego centre - mean from split coordinates (see nine_rectangles)
+                    R ddx = n0.x - g0.x, ddy = n0.y - g0.y;
+                    if (sizeof(R) == 4) {
+                        const float2 lo = __half22float2(sm.el[(t + 1) * 32 + lane]);
+                        const float4 ml = __ldg(tile.N + kNodeVecs * vi + 4);
+                        ddx += (R)(lo.x * (1.0f / kLoScale) - ml.z);
+                        ddy += (R)(lo.y * (1.0f / kLoScale) - ml.w);
+                    }
+                    const ProbCoef<R> pc = ungated_eval<R>(tab, ddx, ddy, n0.z, n0.w, g0, ldg4<R>(tile.P + 2 * vi),
+                                                           tile.N + kNodeVecs * vi, !mahal, amb,
+                                                           ExactRef{&st, &pr, kGiven, pl, id, t, o}, ce, co);
+                    prob = pc.prob;
                     if (mahal) {
                         const Vec4<R> p1 = ldg4<R>(tile.P + 2 * vi + 1);
                         prob = inv_mahalanobis<R>(n0.x, n0.y, g0.x, g0.y, p1.x, p1.y, p1.z);
-                    } else {
-                        // ego centre - mean from split coordinates (see nine_rectangles)
-                        R ddx = n0.x - g0.x, ddy = n0.y - g0.y;
-                        if (sizeof(R) == 4) {
-                            const float2 lo = __half22float2(sm.el[(t + 1) * 32 + lane]);
-                            const float4 ml = __ldg(tile.N + kNodeVecs * vi + 4);
-                            ddx += (R)(lo.x * (1.0f / kLoScale) - ml.z);
-                            ddy += (R)(lo.y * (1.0f / kLoScale) - ml.w);
-                        }
-                        prob = collision_prob(tab, ddx, ddy, n0.z, n0.w, g0, ldg4<R>(tile.P + 2 * vi), tile.N + kNodeVecs * vi);
                     }
-                    R ae, ao;
-                    harm_logits<R, -1>(pr, tab, false, c0, c1, g0, g1, prt, cr.x, cr.y, ae, ao);
+                    const R dv = Logits<R, NT, kSym>::dv(c0, c1, g1);
+                    const R ae = prt ? tab.lr_speed * (cr.x * dv) + pc.ce : tab.lr1s_speed * (cr.x * dv);
+                    const R ao = prt ? tab.lr_speed * (cr.y * dv) + pc.co : tab.ped_speed * (cr.y * dv);
                     const R he = sigmoid_harm<R>(prt ? tab.lr_const : tab.lr1s_const, ae);
                     const R ho = sigmoid_harm<R>(prt ? tab.lr_const : tab.neg_ped_const, ao);
                     U* m = sm.mx + (size_t)o * 32 + lane;
                     atomicMax(m + MX_EGO_RISK * mx_plane, Enc<R>::enc(he * prob));  // risk_costs.py:88-95
                     atomicMax(m + MX_OBST_RISK * mx_plane, Enc<R>::enc(ho * prob));
+                }
+                if (amb_entry) {
+                    // phase 2a left this sample out of some lanes' running maxima: the same test (same code, same
+                    // inputs, bit-identical outcome) finds those lanes again; their coefficients are redone in fp64
+                    const Vec4<R> c0 = sm.e0[t * 32 + lane];
+                    const Vec2<R> c1 = sm.e1[t * 32 + lane];
+                    const Vec4<R> g1 = ldg4<R>(tile.G + 2 * vi + 1);
+                    const Vec4<R> cr = ldg4<R>(tile.C + o);
+                    R ce, co;
+                    bool amb = false;
+                    Logits<R, NT, kSym>::coefs(pr, tab, tile_fast, c0, c1, g0, g1, ce, co, amb);
+                    if (amb && has && cr.z != (R)0 && t < __ldg(st.pred_len + o)) {
+                        double ced, cod;
+                        band_coefs_exact(ExactRef{&st, &pr, kGiven, pl, id, t, o}, ced, cod);
+                        const R dv = Logits<R, NT, kSym>::dv(c0, c1, g1);
+                        const R ae = tab.lr_speed * (cr.x * dv) + (R)ced, ao = tab.lr_speed * (cr.y * dv) + (R)cod;
+                        U* m = sm.mx + (size_t)o * 32 + lane;
+                        atomicMax(m + MX_EGO_ARG * mx_plane, Enc<R>::enc(ae));
+                        atomicMax(m + MX_OBST_ARG * mx_plane, Enc<R>::enc(ao));
+                        if (o_harm && active) {
+                            o_harm[vi * Cp + cl] = sigmoid_harm<R>(tab.lr_const, ae);
+                            o_harm[harm_plane + vi * Cp + cl] = sigmoid_harm<R>(tab.lr_const, ao);
+                        }
+                    }
                 }
                 if (o_prob && active) o_prob[vi * Cp + cl] = prob;
             }
@@ -1067,7 +1192,9 @@ cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, 
     if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1, false, false);
     bool sym = true;  // LR4S / LR12S: one coefficient table for both sides
     for (int i = 0; i <= pr.n_thr; ++i) sym = sym && pr.coef_pos[i] == pr.coef_neg[i];
-    switch (pr.n_thr) {  // the reference's models: LR1S (0 thresholds), LR4S / LR4A (2), LR12S / LR12A (6)
+    bool paired = true;  // thresholds symmetric about pi/2 (chain_coef)
+    for (int i = 0; i < pr.n_thr; ++i) paired = paired && pr.f_fcos[i] == -pr.f_fcos[pr.n_thr - 1 - i];
+    switch (paired ? pr.n_thr : -1) {  // the reference's models: LR1S (0 thresholds), LR4S / LR4A (2), LR12S / LR12A (6)
         case 0: return ETP_LAUNCH(float, 0, true, false);
         case 2: return sym ? ETP_LAUNCH(float, 2, true, false) : ETP_LAUNCH(float, 2, false, false);
         case 6: return sym ? ETP_LAUNCH(float, 6, true, false) : ETP_LAUNCH(float, 6, false, false);
