@@ -105,6 +105,13 @@ class Trajectories(C.Structure):
     ]
 
 
+class Scenario(C.Structure):
+    _fields_ = [
+        ("step", C.POINTER(Step)), ("obstacles", C.POINTER(Obstacles)),
+        ("knots", _dp), ("coef_x", _dp), ("coef_y", _dp), ("n_seg", C.c_int32),
+    ]
+
+
 class Best(C.Structure):
     _fields_ = [
         ("key_hi", C.c_uint64), ("key_lo", C.c_uint64), ("cost", C.c_double),
@@ -125,6 +132,7 @@ SYMBOLS = {
     "etp_plan_step": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Out)]),
     "etp_score_trajectories": (C.c_int, [C.c_void_p, C.POINTER(Trajectories), C.POINTER(Out)]),
     "etp_principle_costs": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, C.c_double, C.c_double, C.c_double, _dp]),
+    "etp_plan_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Scenario), C.c_int, C.POINTER(Best)]),
     "etp_tmax": (C.c_int, [C.POINTER(Step)]),
     "etp_get_best": (C.c_int, [C.c_void_p, C.POINTER(Best)]),
     "etp_get_trajectory": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),

@@ -81,6 +81,11 @@ struct etp_ctx {
     int last_grid = 0;
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // scenario sweep: lazily created child contexts (own stream, own buffers) and the pinned result array
+    std::vector<etp_ctx*> pool;
+    PinnedBuf batch_host;
+    const double* last_knots = nullptr;  // spline identity of the last etp_set_spline through etp_plan_batch
+    int last_nseg = 0;
 };
 
 #define ETP_FAIL(ctx, code, ...)                            \
@@ -121,20 +126,11 @@ int stage_to_device(etp_ctx* c, void* dst, const void* src, size_t bytes) {
     return ETP_OK;
 }
 
-int begin_staging(etp_ctx* c) {
-    if (c->staged_pending) {
-        ETP_CUDA(c, cudaEventSynchronize(c->staged));
-        c->staged_pending = false;
-    }
-    c->stage.used = 0;
-    return ETP_OK;
-}
+// The pinned staging area is a ring: copies stay in flight behind each other on the context's stream and the host
+// only waits (stage_to_device) when the area wraps, i.e. every few hundred small uploads.
+int begin_staging(etp_ctx*) { return ETP_OK; }
 
-int end_staging(etp_ctx* c) {
-    ETP_CUDA(c, cudaEventRecord(c->staged, c->stream));
-    c->staged_pending = true;
-    return ETP_OK;
-}
+int end_staging(etp_ctx*) { return ETP_OK; }
 
 }  // namespace
 
@@ -170,6 +166,9 @@ int etp_create(etp_ctx** out, int device) {
 int etp_destroy(etp_ctx* c) {
     if (!c) return ETP_OK;
     cudaSetDevice(c->device);
+    for (etp_ctx* k : c->pool) etp_destroy(k);
+    c->pool.clear();
+    c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
                       &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list,
@@ -582,6 +581,45 @@ int etp_principle_costs(etp_ctx* c, int n, const double* ego_risk, const double*
     ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, res, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(out, c->traj_host.p, 5 * sizeof(double));
+    return ETP_OK;
+}
+
+int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp_best* bests) {
+    if (!c || n < 0 || (n > 0 && (!sc || !bests))) return ETP_ERR_INVALID;
+    if (!c->have_params) ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params must precede etp_plan_batch");
+    if (n == 0) return ETP_OK;
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    constexpr int kPool = 8;  // scenarios in flight
+    while ((int)c->pool.size() < kPool) {
+        etp_ctx* k = nullptr;
+        const int rc = etp_create(&k, c->device);
+        if (rc != ETP_OK) ETP_FAIL(c, rc, "etp_plan_batch: could not create a child context");
+        c->pool.push_back(k);
+    }
+    ETP_CUDA(c, c->batch_host.reserve(sizeof(BestRec) * (size_t)n));
+    BestRec* host = reinterpret_cast<BestRec*>(c->batch_host.p);
+    for (int i = 0; i < n; ++i) {
+        etp_ctx* k = c->pool[i % kPool];
+        const etp_scenario& s = sc[i];
+        if (!s.step || !s.obstacles || !s.knots || !s.coef_x || !s.coef_y) ETP_FAIL(c, ETP_ERR_INVALID, "scenario %d incomplete", i);
+        k->pr = c->pr;
+        k->have_params = true;
+        int rc = ETP_OK;
+        if (k->last_knots != s.knots || k->last_nseg != s.n_seg) {  // sweeps over one map share the spline
+            if ((rc = etp_set_spline(k, s.knots, s.coef_x, s.coef_y, s.n_seg))) ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
+            k->last_knots = s.knots;
+            k->last_nseg = s.n_seg;
+        }
+        if ((rc = etp_set_obstacles(k, s.obstacles, precision))) ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
+        if ((rc = etp_plan_step(k, s.step, nullptr))) ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
+        ETP_CUDA(c, cudaMemcpyAsync(host + i, k->best_dev.p, sizeof(BestRec), cudaMemcpyDeviceToHost, k->stream));
+    }
+    for (etp_ctx* k : c->pool) ETP_CUDA(c, cudaStreamSynchronize(k->stream));
+    for (int i = 0; i < n; ++i) {
+        const BestRec& b = host[i];
+        bests[i].key_hi = b.key_hi; bests[i].key_lo = b.key_lo; bests[i].cost = b.cost; bests[i].index = b.index;
+        bests[i].level = b.level; bests[i].n_scored = b.n_scored; bests[i].list_index = b.list_index;
+    }
     return ETP_OK;
 }
 

@@ -414,6 +414,53 @@ class ScoringContext:
         self._check(self.lib.etp_get_trajectory(self.h, int(index), _dptr(f), C.byref(n)))
         return f, int(n.value)
 
+    # -- scenario sweep ---------------------------------------------------------------------------
+    def pack_scenarios(self, steps):
+        """Host-side packing of independent planning steps for ``plan_batch`` (structs + the arrays they point to).
+        All steps must share params / vehicle / mode (the context's parameters)."""
+        n = len(steps)
+        arr = (_abi.Scenario * n)()
+        keep = []
+        for i, step in enumerate(steps):
+            s, k, _ = self.make_step_struct(step)
+            o = _abi.Obstacles()
+            if step.predictions is None:
+                o.n_obstacles = -1
+                pk = None
+            else:
+                pk = pack_predictions(step.predictions, step.obstacle_types)
+                o.n_obstacles, o.max_pred = pk["O"], pk["Tp"]
+                o.pred_len = _iptr(pk["pred_len"])
+                o.pos, o.cov, o.yaw, o.vel = _dptr(pk["pos"]), _dptr(pk["cov"]), _dptr(pk["yaw"]), _dptr(pk["vel"])
+                o.length, o.width, o.mass = _dptr(pk["length"]), _dptr(pk["width"]), _dptr(pk["mass"])
+                o.is_protected, o.responsibility = _iptr(pk["prot"]), _iptr(pk["resp"])
+            csp = CubicSpline2D.from_foreign(step.csp)
+            kn = np.ascontiguousarray(csp.s, dtype=np.float64)
+            cx = np.ascontiguousarray(csp.coef_x, dtype=np.float64)
+            cy = np.ascontiguousarray(csp.coef_y, dtype=np.float64)
+            arr[i].step, arr[i].obstacles = C.pointer(s), C.pointer(o)
+            arr[i].knots, arr[i].coef_x, arr[i].coef_y, arr[i].n_seg = _dptr(kn), _dptr(cx), _dptr(cy), len(kn) - 1
+            keep.append((s, k, o, pk, kn, cx, cy))
+        return arr, keep
+
+    def plan_batch(self, steps=None, packed=None):
+        """One planning step per scenario, arg-min only (etp_plan_batch): list of best dicts, ``None`` where every
+        candidate of the scenario was skipped."""
+        if packed is None:
+            if not steps:
+                return []
+            self.set_params(steps[0].params, steps[0].vehicle, steps[0].mode)
+            packed = self.pack_scenarios(steps)
+        arr, keep = packed
+        n = len(arr)
+        bests = (_abi.Best * n)()
+        self._check(self.lib.etp_plan_batch(self.h, n, arr, self.precision, bests))
+        out = []
+        for b in bests:
+            out.append(None if b.index < 0 else dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored,
+                                                     list_index=b.list_index, key_hi=b.key_hi, key_lo=b.key_lo))
+        return out
+
     @staticmethod
     def local_candidates(s):
         """Rows of the output tensors for a step struct: (profiles of this shard) * nd."""

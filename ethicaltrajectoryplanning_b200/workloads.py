@@ -40,6 +40,25 @@ def run_sweep(ctx, scenario_ids, weights="weights_ethical.json"):
     return out, n_cand, time.perf_counter() - t0
 
 
+def run_sweep_batched(ctx, scenario_ids, weights="weights_ethical.json", chunk=256):
+    """The same sweep through ``etp_plan_batch`` (one C call per ``chunk`` scenarios, 8 scenarios in flight on the
+    device).  Returns (results, candidates, seconds of packing, seconds of the batched calls)."""
+    steps = [st for i in scenario_ids for _, st in sweep_steps(1, i, weights)]
+    if not steps:
+        return [], 0, 0.0, 0.0
+    ctx.set_params(steps[0].params, steps[0].vehicle, steps[0].mode)
+    t0 = time.perf_counter()
+    packs = [ctx.pack_scenarios(steps[i:i + chunk]) for i in range(0, len(steps), chunk)]
+    t_pack = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    bests = []
+    for pk in packs:
+        bests += ctx.plan_batch(packed=pk)
+    t_run = time.perf_counter() - t0
+    out = [(sid, b["index"], b["level"], b["cost"]) for sid, b in zip(scenario_ids, bests)]
+    return out, sum(b["n_scored"] for b in bests), t_pack, t_run
+
+
 class MovingObstacles:
     """Predictor stand-in of the closed loop: constant-velocity Gaussian predictions that advance one sample per
     cycle (``predictor.step(time_step=...)`` contract of frenet_planner.py:386-390)."""

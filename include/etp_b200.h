@@ -237,6 +237,24 @@ int etp_principle_costs(etp_ctx* ctx, int n, const double* ego_risk, const doubl
                         const double* obst_harm, const int32_t* responsibility, double boundary_harm, double maximin_eps,
                         double maximin_scale, double* out);
 
+/*
+ * Scenario sweep (planner/Frenet/plannertools/evaluatefrenet.py:16-55, planner/plannertools/evaluate.py:160-169: one
+ * planner per scenario in a process pool): n independent planning steps in one call.  Each scenario brings its own
+ * spline, predictions and sampling grid; the parameters are the context's (etp_set_params).  The steps run on a pool of
+ * internal streams so that their small launches and uploads overlap; only the arg-min of each scenario is produced
+ * (bests[i], index -1 if every candidate of scenario i was skipped).  Synchronises before returning.
+ */
+typedef struct {
+    const etp_step* step;
+    const etp_obstacles* obstacles;
+    const double* knots;     /* spline of this scenario, as in etp_set_spline */
+    const double* coef_x;
+    const double* coef_y;
+    int32_t n_seg;
+} etp_scenario;
+
+int etp_plan_batch(etp_ctx* ctx, int n, const etp_scenario* scenarios, int precision, etp_best* bests);
+
 /* number of timesteps Tmax the output tensors must be strided with for `step` */
 int etp_tmax(const etp_step* step);
 

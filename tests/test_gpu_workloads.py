@@ -21,6 +21,18 @@ def test_sweep_selects_the_oracle_candidate_in_every_scenario():
         assert abs(cost - ref["best"]["cost"]) <= 1e-3 * abs(ref["best"]["cost"]) + 1e-6
 
 
+def test_batched_sweep_equals_the_scenario_by_scenario_sweep():
+    from ethicaltrajectoryplanning_b200 import dropin, workloads
+
+    ctx = dropin.default_context()
+    ids = list(range(40))
+    one, n1, _ = workloads.run_sweep(ctx, ids)
+    bat, n2, t_pack, t_run = workloads.run_sweep_batched(ctx, ids, chunk=16)
+    assert n1 == n2 and len(one) == len(bat) == len(ids)
+    for a, b in zip(one, bat):
+        assert a[:3] == b[:3] and a[3] == b[3], (a, b)  # same kernels, same inputs: identical winners and costs
+
+
 def test_closed_loop_fused_equals_materialised_and_fp64():
     from ethicaltrajectoryplanning_b200 import workloads
 
