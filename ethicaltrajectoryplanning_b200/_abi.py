@@ -136,6 +136,7 @@ SYMBOLS = {
     "etp_tmax": (C.c_int, [C.POINTER(Step)]),
     "etp_get_best": (C.c_int, [C.c_void_p, C.POINTER(Best)]),
     "etp_get_trajectory": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),
+    "etp_get_best_trajectory": (C.c_int, [C.c_void_p, C.POINTER(Best), _dp, _ip]),
     "etp_best_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "etp_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "etp_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

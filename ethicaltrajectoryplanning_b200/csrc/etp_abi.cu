@@ -656,6 +656,28 @@ int etp_get_trajectory(etp_ctx* c, int index, double* fields, int* n_samples) {
     return ETP_OK;
 }
 
+int etp_get_best_trajectory(etp_ctx* c, etp_best* best, double* fields, int* n_samples) {
+    if (!c || !best || !fields) return ETP_ERR_INVALID;
+    if (!c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "no planning step has run on this context");
+    if (c->last_given) ETP_FAIL(c, ETP_ERR_STATE, "the last call scored caller-provided trajectories: the caller holds them");
+    const DevStep& st = c->st;
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    const size_t fbytes = sizeof(double) * ETP_NUM_FIELDS * st.Tmax, bytes = sizeof(BestRec) + 8 + fbytes;
+    ETP_CUDA(c, c->traj_dev.reserve(bytes));
+    ETP_CUDA(c, c->traj_host.reserve(bytes));
+    ETP_CUDA(c, launch_best_trajectory(st, c->best_dev.as<BestRec>(), c->traj_dev.as<unsigned char>(), c->stream));
+    ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, c->traj_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    const BestRec* b = reinterpret_cast<const BestRec*>(c->traj_host.p);
+    best->key_hi = b->key_hi; best->key_lo = b->key_lo; best->cost = b->cost; best->index = b->index;
+    best->level = b->level; best->n_scored = b->n_scored; best->list_index = b->list_index;
+    if (b->index < 0)
+        ETP_FAIL(c, ETP_ERR_NO_CANDIDATE, "every candidate of the range was skipped (ds <= |dT|); the reference raises ValueError here");
+    memcpy(fields, c->traj_host.p + sizeof(BestRec) + 8, fbytes);
+    if (n_samples) memcpy(n_samples, c->traj_host.p + sizeof(BestRec), sizeof(int));
+    return ETP_OK;
+}
+
 int etp_best_device_ptr(etp_ctx* c, void** ptr) {
     if (!c || !ptr) return ETP_ERR_INVALID;
     *ptr = c->best_dev.p;

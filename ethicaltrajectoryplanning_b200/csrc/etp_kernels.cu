@@ -320,6 +320,35 @@ __global__ void principles_kernel(int n, const double* __restrict__ v, const int
     }
 }
 
+// the winner of the last step, found on the device: [BestRec | int T | pad | fields[ETP_NUM_FIELDS][Tmax]] in one buffer
+__global__ void best_trajectory_kernel(DevStep st, const BestRec* __restrict__ best, unsigned char* __restrict__ combo) {
+    BestRec* b_out = reinterpret_cast<BestRec*>(combo);
+    int* n_out = reinterpret_cast<int*>(combo + sizeof(BestRec));
+    double* fields = reinterpret_cast<double*>(combo + sizeof(BestRec) + 8);
+    const BestRec b = *best;
+    if (threadIdx.x == 0) *b_out = b;
+    if (b.index < 0) {
+        if (threadIdx.x == 0) *n_out = 0;
+        return;
+    }
+    const int p = b.index / st.nd, id = b.index % st.nd;
+    const int pl = p - st.p_begin;
+    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+    const bool low = pm[PM_LOW] != 0.0;
+    const int T = (int)pm[PM_T];
+    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+    for (int t = threadIdx.x; t < st.Tmax; t += blockDim.x) {
+        if (t < T) {
+            const TrajPoint tp = traj_point(q, low, gp, st.Tmax, t, st.dt);
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = tp.f[f];
+        } else {
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0) *n_out = T;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from etp_abi.cpp)
 // ---------------------------------------------------------------------------------------------
@@ -350,6 +379,11 @@ cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, 
 cudaError_t launch_principles(int n, const double* vals, const int* resp, double bd, double eps, double scale, double* out5,
                               cudaStream_t stream) {
     principles_kernel<<<1, 32, 0, stream>>>(n, vals, resp, bd, eps, scale, out5);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsigned char* combo, cudaStream_t stream) {
+    best_trajectory_kernel<<<1, 64, 0, stream>>>(st, best, combo);
     return cudaGetLastError();
 }
 

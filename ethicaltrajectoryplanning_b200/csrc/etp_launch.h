@@ -28,6 +28,8 @@ cudaError_t read_debug_counters(unsigned long long* out, int n);
 cudaError_t launch_principles(int n, const double* vals /*[4][n]*/, const int* resp, double bd, double eps, double scale,
                               double* out5, cudaStream_t stream);
 
+cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsigned char* combo, cudaStream_t stream);
+
 cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream);
 
 }  // namespace etp

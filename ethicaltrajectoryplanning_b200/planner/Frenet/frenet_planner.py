@@ -171,9 +171,7 @@ class FrenetPlanner:
             ego_position=np.asarray(self.ego_state.position, dtype=np.float64), ego_orientation=float(self.ego_state.orientation),
             vehicle=self.p, params=self.params_dict, mode=self.mode, velocity_cost_mode=vel_mode,
             velocity_target=vel_target, cost_factor=float(np.ndim(factor) == 0 and factor or 1.0))
-        res = self.ctx.plan(step, materialize=False)
-        self.last_best = res.best
-        self._trajectory = res.best_trajectory()
+        self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------
     def ideal_tracking_state(self):

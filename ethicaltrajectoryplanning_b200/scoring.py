@@ -375,6 +375,16 @@ class ScoringContext:
         return dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored, list_index=b.list_index,
                     key_hi=b.key_hi, key_lo=b.key_lo)
 
+    def best_and_trajectory(self):
+        """(best dict, fields [13][Tmax] fp64, T) of the last step with one launch, one copy, one synchronisation."""
+        b = _abi.Best()
+        f = np.zeros((_abi.NUM_FIELDS, self._last_tmax), dtype=np.float64)
+        n = C.c_int32(0)
+        self._check(self.lib.etp_get_best_trajectory(self.h, C.byref(b), _dptr(f), C.byref(n)))
+        best = dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored, list_index=b.list_index,
+                    key_hi=b.key_hi, key_lo=b.key_lo)
+        return best, f, int(n.value)
+
     def best_raw(self):
         """Best record without raising on 'no candidate' (used by the sharded arg-min)."""
         b = _abi.Best()
@@ -477,6 +487,21 @@ class ScoringContext:
         rows = np.arange(self.local_candidates(s))
         k, i = rows // s.nd, rows % s.nd
         return (s.c_begin // s.nd + idx + k * cnt) * s.nd + i
+
+    def plan_winner(self, step: PlanningStep):
+        """Arg-min only planning step returning ``(best, trajectory dict)``: the 11 arrays FrenetPlanner stores in
+        ``self._trajectory`` (frenet_planner.py:564-576), one read-back."""
+        self.configure(step)
+        s, keep, n = self.make_step_struct(step)
+        self.launch(s, None)
+        self._last_tmax = int(n.max())
+        self.last_dt = step.dt
+        best, f, T = self.best_and_trajectory()
+        g = {name: f[i, :T] for i, name in enumerate(_abi.FIELD_NAMES)}
+        traj = {"s_loc_m": g["s"], "d_loc_m": g["d"], "d_d_loc_mps": g["d_d"], "d_dd_loc_mps2": g["d_dd"], "x_m": g["x"],
+                "y_m": g["y"], "psi_rad": g["yaw"], "kappa_radpm": g["curv"], "v_mps": g["s_d"], "ax_mps2": g["s_dd"],
+                "time_s": np.arange(T) * step.dt}
+        return best, traj
 
     def plan(self, step: PlanningStep, materialize=True, c_begin=None, c_end=None, bufs=None,
              configure=True, shard_index=0, shard_count=1) -> ScoreResult:

@@ -265,6 +265,10 @@ int etp_get_best(etp_ctx* ctx, etp_best* best);
  * step (recomputed in fp64) -> `self._trajectory` (frenet_planner.py:564-576). n_samples receives T. */
 int etp_get_trajectory(etp_ctx* ctx, int index, double* fields, int* n_samples);
 
+/* etp_get_best + etp_get_trajectory of the winner with one launch, one device-to-host copy and one synchronisation
+ * (the closed loop's read-back: frenet_planner.py:555-576).  Returns ETP_ERR_NO_CANDIDATE like etp_get_best. */
+int etp_get_best_trajectory(etp_ctx* ctx, etp_best* best, double* fields, int* n_samples);
+
 /* Device address of the etp_best record the last etp_plan_step wrote (for collectives on it). */
 int etp_best_device_ptr(etp_ctx* ctx, void** ptr);
 
