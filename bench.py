@@ -470,6 +470,29 @@ def latency_extras(ctx, torch):
     out["workload"] = "cfg2: 100x100 candidates, T=30, 8 obstacles; L2 flushed between steps (256 MiB write)"
     extras = {"cfg2_single_step": out}
 
+    # cfg3 in the two regimes of SURVEY.md 8d: as generated (9 % of the evaluations pass the 5 m gate and need the
+    # bivariate-normal rectangles) and with the obstacles spread 40 m laterally (0.6 %): the same bytes are written, the
+    # difference is issue-slot work; plus the arg-min-only mode (nothing materialised)
+    regimes = {}
+    for name, kw, mat in (("ungated_9pct", {}, True), ("ungated_0p6pct", {"lateral_spread": 40.0}, True),
+                          ("argmin_only", {}, False)):
+        st3 = make_step("cfg3", **kw)
+        ctx.configure(st3)
+        s3, keep3, ns3 = ctx.make_step_struct(st3)
+        b3 = ctx.allocate_outputs(st3.n_dense, int(ns3.max()), ctx.O) if mat else None
+        ctx.enable_timing(True)
+        ks = []
+        for i in range(5):
+            ctx.launch(s3, b3)
+            ks.append(ctx.timing()[1])
+        ctx.enable_timing(False)
+        k = float(np.median(ks[1:]))
+        bytes3 = st3.n_dense * algorithmic_bytes_per_candidate(int(ns3.max()), ctx.O) if mat else 0
+        regimes[name] = {"kernel_ms": k, "candidates_per_sec": st3.n_dense / (k * 1e-3), "hbm_gbs": bytes3 / (k * 1e-3) / 1e9}
+        del b3
+    torch.cuda.empty_cache()
+    extras["cfg3_regimes"] = regimes
+
     # cfg4: evaluatefrenet-style sweep (one planning step per scenario, arg-min only), this GPU's share
     from ethicaltrajectoryplanning_b200 import workloads
 

@@ -31,7 +31,10 @@
 
 namespace etp {
 
-constexpr int kThreads = 256;
+#ifndef ETP_THREADS
+#define ETP_THREADS 256
+#endif
+constexpr int kThreads = ETP_THREADS;
 constexpr int kWarps = kThreads / 32;
 #ifndef ETP_MIN_BLOCKS
 #define ETP_MIN_BLOCKS 2

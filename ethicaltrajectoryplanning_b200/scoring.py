@@ -127,13 +127,21 @@ def pack_predictions(predictions, obstacle_types=None, masses=None, protections=
     mass = np.zeros(O)
     prot = np.zeros(O, dtype=np.int32)
     resp = np.zeros(O, dtype=np.int32)
+    preds = [predictions[oid] for oid in oids]
+    uniform = O > 0 and int(lens.min()) == Tp
+    if uniform:  # equal prediction lengths (the usual case): four stacked copies instead of 4 * O sliced ones
+        pos[:] = np.stack([np.asarray(p["pos_list"], dtype=np.float64) for p in preds]).reshape(O, Tp, 2)
+        cov[:] = np.stack([np.asarray(p["cov_list"], dtype=np.float64) for p in preds]).reshape(O, Tp, 4)
+        yaw[:] = np.stack([np.asarray(p["orientation_list"], dtype=np.float64)[:Tp] for p in preds])
+        vel[:] = np.stack([np.asarray(p["v_list"], dtype=np.float64)[:Tp] for p in preds])
     for j, oid in enumerate(oids):
-        p = predictions[oid]
+        p = preds[j]
         n = lens[j]
-        pos[j, :n] = np.asarray(p["pos_list"], dtype=np.float64).reshape(n, 2)
-        cov[j, :n] = np.asarray(p["cov_list"], dtype=np.float64).reshape(n, 4)
-        yaw[j, :n] = np.asarray(p["orientation_list"], dtype=np.float64)[:n]
-        vel[j, :n] = np.asarray(p["v_list"], dtype=np.float64)[:n]
+        if not uniform:
+            pos[j, :n] = np.asarray(p["pos_list"], dtype=np.float64).reshape(n, 2)
+            cov[j, :n] = np.asarray(p["cov_list"], dtype=np.float64).reshape(n, 4)
+            yaw[j, :n] = np.asarray(p["orientation_list"], dtype=np.float64)[:n]
+            vel[j, :n] = np.asarray(p["v_list"], dtype=np.float64)[:n]
         length[j] = p["shape"]["length"]
         width[j] = p["shape"]["width"]
         resp[j] = int(p.get("responsibility", 0))

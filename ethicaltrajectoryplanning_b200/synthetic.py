@@ -25,7 +25,7 @@ _FIXED_MASS = {"TRUCK": 25000.0, "BUS": 13000.0, "BICYCLE": 90.0, "PEDESTRIAN": 
 def obstacle_mass(type_name: str, size: float) -> float:
     """Mass table of risk_assessment/helpers/properties.py:14-46 (size = length*width incl. margins)."""
     if type_name in ("CAR", "PRIORITY_VEHICLE", "PARKED_VEHICLE", "TAXI"):
-        return float(-1333.5 + 526.9 * np.power(size, 0.8))
+        return float(-1333.5 + 526.9 * np.power(size, 0.8))  # np.power like the reference (properties.py:37)
     return _FIXED_MASS.get(type_name, 0.0)
 
 
