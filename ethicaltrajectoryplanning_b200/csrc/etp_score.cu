@@ -103,7 +103,6 @@ __device__ __forceinline__ double abs_(double x) { return fabs(x); }
 template <typename R> struct Tab {
     R thr[ETP_MAX_ANGLE_BINS], fcos[ETP_MAX_ANGLE_BINS], coef_pos[ETP_MAX_ANGLE_BINS + 1], coef_neg[ETP_MAX_ANGLE_BINS + 1];
     R lr_speed, lr1s_speed, ped_speed, lr_const, lr1s_const, neg_ped_const;
-    R coef_max;    // largest impact-area coefficient: upper bound of the harm logit without looking at the angle
     R eps_pos;     // fp32 rounding of a position difference in metres (2 ulp of the largest coordinate in play)
     R hx, hy, rr;  // ego box half extents (l/6, w/2) and centre offset (l/2)(2/3)  (collision_probability.py:157,349-362)
     int n_thr;
@@ -112,9 +111,6 @@ template <typename R> struct Tab {
 template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const DevParams& pr, double eps_pos) {
     for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) { tb.thr[i] = (R)pr.thr[i]; tb.fcos[i] = (R)pr.fcos[i]; }
     for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { tb.coef_pos[i] = (R)pr.coef_pos[i]; tb.coef_neg[i] = (R)pr.coef_neg[i]; }
-    R cm = tb.coef_pos[0];
-    for (int i = 0; i <= pr.n_thr; ++i) cm = rmax_(cm, rmax_(tb.coef_pos[i], tb.coef_neg[i]));
-    tb.coef_max = cm;
     tb.lr_speed = (R)pr.lr_speed; tb.lr1s_speed = (R)pr.lr1s_speed; tb.ped_speed = (R)pr.ped_speed;
     tb.lr_const = (R)pr.lr_const; tb.lr1s_const = (R)pr.lr1s_const; tb.neg_ped_const = (R)(-pr.ped_const);
     tb.hx = (R)(pr.veh_l / 6); tb.hy = (R)(pr.veh_w / 2); tb.rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
