@@ -65,6 +65,16 @@ class Obstacles(C.Structure):
     ]
 
 
+class RawPredictions(C.Structure):
+    _fields_ = [
+        ("n_obstacles", C.c_int32), ("max_pred", C.c_int32),
+        ("pred_len", _ip), ("pos", _dp), ("cov", _dp), ("length", _dp), ("width", _dp),
+        ("init_orientation", _dp), ("init_velocity", _dp), ("mass", _dp), ("is_protected", _ip),
+        ("dt", C.c_double), ("safety_margin_length", C.c_double), ("safety_margin_width", C.c_double),
+        ("ego_x", C.c_double), ("ego_y", C.c_double), ("ego_orientation", C.c_double),
+    ]
+
+
 class Step(C.Structure):
     _fields_ = [
         ("c_s", C.c_double), ("c_s_d", C.c_double), ("c_s_dd", C.c_double),
@@ -129,6 +139,8 @@ SYMBOLS = {
     "etp_set_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
     "etp_set_spline": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int]),
     "etp_set_obstacles": (C.c_int, [C.c_void_p, C.POINTER(Obstacles), C.c_int]),
+    "etp_set_raw_predictions": (C.c_int, [C.c_void_p, C.POINTER(RawPredictions), C.c_int]),
+    "etp_get_enriched": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _ip]),
     "etp_plan_step": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Out)]),
     "etp_score_trajectories": (C.c_int, [C.c_void_p, C.POINTER(Trajectories), C.POINTER(Out)]),
     "etp_principle_costs": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, C.c_double, C.c_double, C.c_double, _dp]),

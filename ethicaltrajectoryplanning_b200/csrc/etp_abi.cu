@@ -69,6 +69,8 @@ struct etp_ctx {
     int nseg = 0;
     // obstacles
     DevBuf o_pos, o_cov, o_yaw, o_vel, o_len, o_mass, o_plen, o_prot, o_resp, o_tile, o_const;
+    DevBuf o_wid, o_rawlen, o_rawwid, o_ori0, o_vel0;  // etp_set_raw_predictions
+    PinnedBuf enr_host;
     int O = 0, Tp = 0, has_pred = 0;
     double origin_x = 0.0, origin_y = 0.0;  // of the fp32 coordinates: first obstacle sample, else the spline start
     std::vector<double> spline_pts, obs_box;  // knot positions (+ reach) and the bounding box of the predictions
@@ -171,11 +173,12 @@ int etp_destroy(etp_ctx* c) {
     c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
-                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list,
+                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list,
                       &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
                       &c->traj_n, &c->given, &c->given_T, &c->prin};
     for (DevBuf* b : bufs) b->release();
     c->stage.release();
+    c->enr_host.release();
     c->best_host.release();
     c->traj_host.release();
     if (c->staged) cudaEventDestroy(c->staged);
@@ -330,6 +333,100 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
     c->O = O;
     c->Tp = Tp;
     c->have_obs = true;
+    return ETP_OK;
+}
+
+int etp_set_raw_predictions(etp_ctx* c, const etp_raw_predictions* o, int precision) {
+    if (!c || !o) return ETP_ERR_INVALID;
+    if (precision != ETP_PRECISION_FP32 && precision != ETP_PRECISION_FP64) ETP_FAIL(c, ETP_ERR_INVALID, "precision");
+    if (!c->have_params) ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params must precede etp_set_raw_predictions");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    c->precision = precision;
+    c->obs_box.clear();
+    c->origin_x = c->origin_y = 0.0;
+    const int O = o->n_obstacles, Tp = o->max_pred;
+    if (O < 0) ETP_FAIL(c, ETP_ERR_INVALID, "n_obstacles < 0: use etp_set_obstacles for `predictions is None`");
+    c->has_pred = 1;
+    if (O > 0) {
+        if (Tp < 1 || !o->pred_len || !o->pos || !o->cov || !o->length || !o->width || !o->init_orientation || !o->init_velocity ||
+            !o->mass || !o->is_protected)
+            ETP_FAIL(c, ETP_ERR_INVALID, "raw prediction arrays missing");
+        for (int i = 0; i < O; ++i) {
+            if (o->pred_len[i] < 1 || o->pred_len[i] > Tp)
+                ETP_FAIL(c, ETP_ERR_INVALID, "pred_len[%d]=%d outside [1, max_pred]; empty predictions are dropped by the caller "
+                         "(prediction_helpers.py:98-100)", i, o->pred_len[i]);
+            if (o->is_protected[i] != 0 && o->is_protected[i] != 1)
+                ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "obstacle %d has no protection class (harm_estimation.py:52-56): unsupported input", i);
+        }
+        int r = begin_staging(c);
+        if (r) return r;
+        const size_t n = (size_t)O * Tp;
+        c->origin_x = o->pos[0];
+        c->origin_y = o->pos[1];
+        c->obs_box.assign({o->pos[0], o->pos[0], o->pos[1], o->pos[1]});
+        for (int i = 0; i < O; ++i)
+            for (int t = 0; t < o->pred_len[i]; ++t) {
+                const double* q = o->pos + ((size_t)i * Tp + t) * 2;
+                c->obs_box[0] = std::fmin(c->obs_box[0], q[0]); c->obs_box[1] = std::fmax(c->obs_box[1], q[0]);
+                c->obs_box[2] = std::fmin(c->obs_box[2], q[1]); c->obs_box[3] = std::fmax(c->obs_box[3], q[1]);
+            }
+        ETP_CUDA(c, c->o_pos.reserve(sizeof(double) * 2 * n));
+        ETP_CUDA(c, c->o_cov.reserve(sizeof(double) * 4 * n));
+        ETP_CUDA(c, c->o_yaw.reserve(sizeof(double) * n));
+        ETP_CUDA(c, c->o_vel.reserve(sizeof(double) * n));
+        DevBuf* per_o[] = {&c->o_len, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->o_mass};
+        for (DevBuf* b : per_o) ETP_CUDA(c, b->reserve(sizeof(double) * O));
+        ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_resp.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_tile.reserve(Tile<double>::bytes(O, Tp)));
+        ETP_CUDA(c, c->o_const.reserve(sizeof(double) * OC_COUNT * O));
+        if ((r = stage_to_device(c, c->o_pos.p, o->pos, sizeof(double) * 2 * n))) return r;
+        if ((r = stage_to_device(c, c->o_cov.p, o->cov, sizeof(double) * 4 * n))) return r;
+        if ((r = stage_to_device(c, c->o_rawlen.p, o->length, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_rawwid.p, o->width, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_ori0.p, o->init_orientation, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_vel0.p, o->init_velocity, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_mass.p, o->mass, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_plen.p, o->pred_len, sizeof(int) * O))) return r;
+        if ((r = stage_to_device(c, c->o_prot.p, o->is_protected, sizeof(int) * O))) return r;
+        if ((r = end_staging(c))) return r;
+        ETP_CUDA(c, launch_enrich(O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_rawlen.as<double>(), c->o_rawwid.as<double>(),
+                                  c->o_ori0.as<double>(), c->o_vel0.as<double>(), o->dt, o->safety_margin_length,
+                                  o->safety_margin_width, o->ego_x, o->ego_y, o->ego_orientation, c->o_yaw.as<double>(),
+                                  c->o_vel.as<double>(), c->o_len.as<double>(), c->o_wid.as<double>(), c->o_resp.as<int>(), c->stream));
+        ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
+                                          c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
+                                          c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
+                                          c->origin_x, c->origin_y, c->o_tile.p, c->o_const.as<double>(), c->stream));
+    }
+    c->O = O;
+    c->Tp = Tp;
+    c->have_obs = true;
+    return ETP_OK;
+}
+
+int etp_get_enriched(etp_ctx* c, double* yaw, double* vel, double* length, double* width, int32_t* responsibility) {
+    if (!c) return ETP_ERR_INVALID;
+    if (!c->have_obs || !c->has_pred) ETP_FAIL(c, ETP_ERR_STATE, "no predictions set on this context");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->O * c->Tp, O = (size_t)c->O;
+    if (O == 0) return ETP_OK;
+    const size_t bytes = sizeof(double) * (2 * n + 2 * O) + sizeof(int) * O;
+    ETP_CUDA(c, c->enr_host.reserve(bytes));
+    unsigned char* h = c->enr_host.p;
+    ETP_CUDA(c, cudaMemcpyAsync(h, c->o_yaw.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaMemcpyAsync(h + sizeof(double) * n, c->o_vel.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaMemcpyAsync(h + sizeof(double) * 2 * n, c->o_len.p, sizeof(double) * O, cudaMemcpyDeviceToHost, c->stream));
+    if (c->o_wid.p)
+        ETP_CUDA(c, cudaMemcpyAsync(h + sizeof(double) * (2 * n + O), c->o_wid.p, sizeof(double) * O, cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaMemcpyAsync(h + sizeof(double) * (2 * n + 2 * O), c->o_resp.p, sizeof(int) * O, cudaMemcpyDeviceToHost, c->stream));
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (yaw) memcpy(yaw, h, sizeof(double) * n);
+    if (vel) memcpy(vel, h + sizeof(double) * n, sizeof(double) * n);
+    if (length) memcpy(length, h + sizeof(double) * 2 * n, sizeof(double) * O);
+    if (width) memcpy(width, h + sizeof(double) * (2 * n + O), sizeof(double) * O);
+    if (responsibility) memcpy(responsibility, h + sizeof(double) * (2 * n + 2 * O), sizeof(int) * O);
     return ETP_OK;
 }
 

@@ -126,6 +126,64 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
     }
 }
 
+__device__ __forceinline__ double np_gradient(const double* f, const double* s, int i, int n);
+
+// ---------------------------------------------------------------------------------------------
+// enrich_kernel: one block per obstacle (prediction_helpers.py:75-135, responsibility.py:57-89), fp64
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
+                                                     const double* __restrict__ raw_len, const double* __restrict__ raw_wid,
+                                                     const double* __restrict__ ori0, const double* __restrict__ vel0, double dt,
+                                                     double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori,
+                                                     double* __restrict__ yaw, double* __restrict__ vel, double* __restrict__ length,
+                                                     double* __restrict__ width, int* __restrict__ resp) {
+    extern __shared__ double sm[];
+    const int o = blockIdx.x, tid = threadIdx.x;
+    const int n = pred_len[o];
+    double* s_x = sm;
+    double* s_y = sm + Tp;
+    double* s_t = sm + 2 * Tp;
+    const double* p = pos + (size_t)o * Tp * 2;
+    for (int t = tid; t < n; t += blockDim.x) {
+        s_x[t] = p[2 * t];
+        s_y[t] = p[2 * t + 1];
+        s_t[t] = 0.0 + t * dt;  // t = [0.0 + i * scenario.dt ...]  (:108)
+    }
+    __syncthreads();
+    double* yo = yaw + (size_t)o * Tp;
+    double* vo = vel + (size_t)o * Tp;
+    if (n == 1) {  // :103-105
+        if (tid == 0) {
+            yo[0] = ori0[o];
+            vo[0] = vel0[o];
+        }
+    } else {
+        // dx = np.gradient(x, t), dy = np.gradient(y, t)  (:113-114); all(dx < 0.0001) and all(dy < 0.0001)  (:117, no abs)
+        int still = 1;
+        for (int t = tid; t < n; t += blockDim.x) {
+            const double dx = np_gradient(s_x, s_t, t, n), dy = np_gradient(s_y, s_t, t, n);
+            if (!(dx < 0.0001) || !(dy < 0.0001)) still = 0;
+            vo[t] = sqrt(dx * dx + dy * dy);  // :126
+            yo[t] = atan2(dy, dx);            // :123 (overwritten below if the obstacle barely moves)
+        }
+        still = __syncthreads_and(still);
+        if (still)
+            for (int t = tid; t < n; t += blockDim.x) yo[t] = ori0[o];  // :118-119
+    }
+    for (int t = n + tid; t < Tp; t += blockDim.x) {
+        yo[t] = 0.0;
+        vo[t] = 0.0;
+    }
+    if (tid == 0) {
+        length[o] = raw_len[o] + margin_l;  // :131-134
+        width[o] = raw_wid[o] + margin_w;
+        // check_if_inside180view (responsibility.py:78-89)
+        const double ang = atan2(p[1] - ego_y, p[0] - ego_x);
+        const double quarter = 3.14159265358979323846 / 4;
+        resp[o] = (ego_ori - quarter <= ang && ang <= ego_ori + quarter) ? 0 : 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // profile_kernel: one block per (v, t) profile, everything fp64
 // ---------------------------------------------------------------------------------------------
@@ -373,6 +431,16 @@ cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, 
     if (n_prof <= 0) return cudaSuccess;
     const size_t smem = sizeof(double) * 7 * st.Tmax;
     profile_kernel<<<n_prof, 128, smem, stream>>>(st, pr, nskip);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_enrich(int O, int Tp, const int* pred_len, const double* pos, const double* raw_len, const double* raw_wid,
+                          const double* ori0, const double* vel0, double dt, double margin_l, double margin_w, double ego_x,
+                          double ego_y, double ego_ori, double* yaw, double* vel, double* length, double* width, int* resp,
+                          cudaStream_t stream) {
+    if (O <= 0) return cudaSuccess;
+    enrich_kernel<<<O, 128, sizeof(double) * 3 * Tp, stream>>>(O, Tp, pred_len, pos, raw_len, raw_wid, ori0, vel0, dt, margin_l, margin_w,
+                                                              ego_x, ego_y, ego_ori, yaw, vel, length, width, resp);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,11 @@ size_t score_smem_bytes(int precision, int Tmax, int O);
 
 cudaError_t read_debug_counters(unsigned long long* out, int n);
 
+cudaError_t launch_enrich(int O, int Tp, const int* pred_len, const double* pos, const double* raw_len, const double* raw_wid,
+                          const double* ori0, const double* vel0, double dt, double margin_l, double margin_w, double ego_x,
+                          double ego_y, double ego_ori, double* yaw, double* vel, double* length, double* width, int* resp,
+                          cudaStream_t stream);
+
 cudaError_t launch_principles(int n, const double* vals /*[4][n]*/, const int* resp, double bd, double eps, double scale,
                               double* out5, cudaStream_t stream);
 

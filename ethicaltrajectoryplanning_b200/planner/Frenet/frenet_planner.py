@@ -18,7 +18,7 @@ import numpy as np
 
 from ... import dropin
 from ...configs import load_harm_parameter_json, load_risk_json, load_weight_json
-from ...synthetic import PlanningStep, assign_responsibility_by_action_space, enrich_predictions, planner_v_list
+from ...synthetic import PlanningStep, assign_responsibility_by_action_space, planner_v_list
 from .utils.frenet_functions import calc_frenet_trajectories, sort_frenet_trajectories
 from .utils.logging import FrenetLogging
 from .utils.validity_checks import VALIDITY_LEVELS  # noqa: F401
@@ -100,15 +100,24 @@ class FrenetPlanner:
         else:
             raw = self.predictor(self.ego_state.time_step)
         predictions = copy.copy(raw)
+        self._resident = False
         if predictions and "orientation_list" not in next(iter(predictions.values())):
-            # get_orientation_velocity_and_shape_of_prediction (prediction_helpers.py:75-135)
-            shapes, ori0, vel0 = {}, {}, {}
+            # get_orientation_velocity_and_shape_of_prediction (prediction_helpers.py:75-135) and
+            # assign_responsibility_by_action_space (responsibility.py:57-89) on the device, straight into the packed tile
+            shapes, ori0, vel0, types = {}, {}, {}, {}
             for oid in predictions:
                 ob = self.scenario.obstacle_by_id(oid)
                 shapes[oid] = (ob.obstacle_shape.length, ob.obstacle_shape.width)
                 ori0[oid] = ob.initial_state.orientation
                 vel0[oid] = ob.initial_state.velocity
-            predictions = enrich_predictions(predictions, shapes, ori0, vel0, self.scenario.dt)
+            types = dropin.obstacle_type_names(self.scenario, predictions, self.obstacle_types)
+            self.ctx.ensure_params(self.params_dict, self.p, self.mode)
+            self.ctx.set_raw_predictions(predictions, shapes, ori0, vel0, types, self.scenario.dt,
+                                         np.asarray(self.ego_state.position), self.ego_state.orientation)
+            self._resident = True
+            if self.materialize:  # the log line prints the enriched dict
+                self.ctx.enriched(predictions)
+            return predictions
         # assign_responsibility_by_action_space (responsibility.py:57-89)
         return assign_responsibility_by_action_space(np.asarray(self.ego_state.position), self.ego_state.orientation,
                                                      predictions)
@@ -170,7 +179,8 @@ class FrenetPlanner:
             csp=self.reference_spline, predictions=predictions, obstacle_types=types,
             ego_position=np.asarray(self.ego_state.position, dtype=np.float64), ego_orientation=float(self.ego_state.orientation),
             vehicle=self.p, params=self.params_dict, mode=self.mode, velocity_cost_mode=vel_mode,
-            velocity_target=vel_target, cost_factor=float(np.ndim(factor) == 0 and factor or 1.0))
+            velocity_target=vel_target, cost_factor=float(np.ndim(factor) == 0 and factor or 1.0),
+            predictions_resident=getattr(self, "_resident", False))
         self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------

@@ -292,20 +292,84 @@ class ScoringContext:
         self._check(self.lib.etp_set_obstacles(self.h, C.byref(o), self.precision))
         self.obstacle_ids, self.O, self.has_pred = pk["ids"], pk["O"], True
 
+    def set_raw_predictions(self, predictions, shapes, init_orientation, init_velocity, obstacle_types, dt, ego_position,
+                            ego_orientation, safety_margin_length=1.0, safety_margin_width=0.5, masses=None, protections=None):
+        """Raw predictions ``{id: {'pos_list', 'cov_list'}}`` straight from the predictor: orientation, velocity, shape
+        margins and the action-space responsibility flag are derived on the device (prediction_helpers.py:75-135,
+        responsibility.py:57-89) and the obstacle tile is packed from them.  ``shapes[id] = (length, width)`` of the raw
+        obstacle; empty predictions are dropped like the reference does (:98-100)."""
+        oids = [oid for oid in predictions if len(predictions[oid]["pos_list"]) > 0]
+        O = len(oids)
+        lens = np.array([len(predictions[o]["pos_list"]) for o in oids], dtype=np.int32)
+        Tp = int(lens.max()) if O else 1
+        pos, cov = np.zeros((O, Tp, 2)), np.zeros((O, Tp, 4))
+        length, width, ori0, vel0, mass = (np.zeros(O) for _ in range(5))
+        prot = np.zeros(O, dtype=np.int32)
+        for j, oid in enumerate(oids):
+            n = lens[j]
+            pos[j, :n] = np.asarray(predictions[oid]["pos_list"], dtype=np.float64).reshape(n, 2)
+            cov[j, :n] = np.asarray(predictions[oid]["cov_list"], dtype=np.float64).reshape(n, 4)
+            length[j], width[j] = shapes[oid]
+            ori0[j], vel0[j] = init_orientation[oid], init_velocity[oid]
+            if masses is not None:
+                mass[j], prot[j] = masses[oid], int(protections[oid])
+            else:
+                t = getattr(obstacle_types[oid], "name", obstacle_types[oid])
+                if t in PROTECTED_TYPES:
+                    prot[j] = 1
+                elif t in UNPROTECTED_TYPES:
+                    prot[j] = 0
+                else:
+                    raise ValueError(f"obstacle type {t!r} has no protection class (harm_estimation.py:52-56)")
+                mass[j] = obstacle_mass(t, (length[j] + safety_margin_length) * (width[j] + safety_margin_width))
+        r = _abi.RawPredictions()
+        r.n_obstacles, r.max_pred = O, Tp
+        r.pred_len, r.pos, r.cov = _iptr(lens), _dptr(pos), _dptr(cov)
+        r.length, r.width, r.init_orientation, r.init_velocity = _dptr(length), _dptr(width), _dptr(ori0), _dptr(vel0)
+        r.mass, r.is_protected = _dptr(mass), _iptr(prot)
+        r.dt, r.safety_margin_length, r.safety_margin_width = float(dt), float(safety_margin_length), float(safety_margin_width)
+        r.ego_x, r.ego_y, r.ego_orientation = float(ego_position[0]), float(ego_position[1]), float(ego_orientation)
+        self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
+        self.obstacle_ids, self.O, self.has_pred = oids, O, True
+        self._raw_shape = (O, Tp, lens)
+
+    def enriched(self, predictions):
+        """Read the derived arrays of the last ``set_raw_predictions`` back into the prediction dict (what the reference's
+        log line prints): 'orientation_list', 'v_list', 'shape', 'responsibility'.  Empty predictions are deleted."""
+        O, Tp, lens = self._raw_shape
+        yaw, vel = np.zeros((O, Tp)), np.zeros((O, Tp))
+        length, width = np.zeros(O), np.zeros(O)
+        resp = np.zeros(O, dtype=np.int32)
+        self._check(self.lib.etp_get_enriched(self.h, _dptr(yaw), _dptr(vel), _dptr(length), _dptr(width), _iptr(resp)))
+        for oid in [o for o in predictions if len(predictions[o]["pos_list"]) == 0]:
+            del predictions[oid]
+        for j, oid in enumerate(self.obstacle_ids):
+            n = int(lens[j])
+            predictions[oid]["orientation_list"] = yaw[j, :n].copy()
+            predictions[oid]["v_list"] = vel[j, :n].copy()
+            predictions[oid]["shape"] = {"length": float(length[j]), "width": float(width[j])}
+            predictions[oid]["responsibility"] = int(resp[j])
+        return predictions
+
+    def ensure_params(self, params, vehicle, mode="risk"):
+        """set_params unless the same parameter objects with the same content are already on the device."""
+        pkey = (id(params), id(vehicle), mode, repr(sorted(params["weights"].items())),
+                repr(sorted((k, v) for k, v in params["modes"].items() if not isinstance(v, dict))))
+        if getattr(self, "_params_key", None) != pkey:
+            self.set_params(params, vehicle, mode)
+            self._params_key = pkey
+
     def configure(self, step: PlanningStep):
         """params + spline + predictions of a PlanningStep.  Parameters and spline are uploaded again only when they
         changed (same objects, same content fingerprint); predictions change every step and always are."""
-        pkey = (id(step.params), id(step.vehicle), step.mode, repr(sorted(step.params["weights"].items())),
-                repr(sorted((k, v) for k, v in step.params["modes"].items() if not isinstance(v, dict))))
-        if getattr(self, "_params_key", None) != pkey:
-            self.set_params(step.params, step.vehicle, step.mode)
-            self._params_key = pkey
+        self.ensure_params(step.params, step.vehicle, step.mode)
         csp = CubicSpline2D.from_foreign(step.csp)
         skey = (id(step.csp), len(csp.s), float(csp.s[-1]), float(np.asarray(csp.coef_x)[0][0]), float(np.asarray(csp.coef_y)[-1][1]))
         if getattr(self, "_spline_key", None) != skey:
             self.set_spline(csp)
             self._spline_key = skey
-        self.set_predictions(step.predictions, step.obstacle_types)
+        if not getattr(step, "predictions_resident", False):
+            self.set_predictions(step.predictions, step.obstacle_types)
 
     # -- one planning step --------------------------------------------------------------------
     def make_step_struct(self, step, c_begin=None, c_end=None, shard_index=0, shard_count=1):

@@ -131,6 +131,7 @@ class PlanningStep:
     ext_level: Optional[np.ndarray] = None   # per dense candidate: 1 collision, 2 boundary, else 10
     bd_harm: Optional[np.ndarray] = None     # per dense candidate boundary harm
     cost_factor_list: Optional[np.ndarray] = None  # per dense candidate get_cost_factor result (overrides cost_factor)
+    predictions_resident: bool = False  # the context already holds these predictions (ScoringContext.set_raw_predictions)
 
     @property
     def n_dense(self):

@@ -61,21 +61,28 @@ def run_sweep_batched(ctx, scenario_ids, weights="weights_ethical.json", chunk=2
 
 class MovingObstacles:
     """Predictor stand-in of the closed loop: constant-velocity Gaussian predictions that advance one sample per
-    cycle (``predictor.step(time_step=...)`` contract of frenet_planner.py:386-390)."""
+    cycle (``predictor.step(time_step=...)`` contract of frenet_planner.py:386-390).  Like a real predictor it returns
+    RAW predictions ({pos_list, cov_list}); orientation, velocity, shape margins and the responsibility flag are
+    derived per cycle (on the device, by the planner)."""
 
     def __init__(self, csp, n_obstacles, horizon, n_steps, dt=0.1, v0=12.0, seed=1234):
         rng = np.random.default_rng(seed)
         self.horizon = horizon
         self.full, self.types = make_obstacles(csp, rng, n_obstacles, horizon + n_steps, dt, v0, horizon * dt)
+        # raw obstacle shapes / initial states as a CommonRoad scenario holds them
+        self.shapes = {oid: (p["shape"]["length"] - 1.0, p["shape"]["width"] - 0.5) for oid, p in self.full.items()}
+        self.ori0 = {oid: float(np.asarray(p["orientation_list"])[0]) for oid, p in self.full.items()}
+        self.vel0 = {oid: float(np.asarray(p["v_list"])[0]) for oid, p in self.full.items()}
+
+    def obstacle_by_id(self, oid):
+        return SimpleNamespace(obstacle_type=SimpleNamespace(name=self.types[oid]),
+                               obstacle_shape=SimpleNamespace(length=self.shapes[oid][0], width=self.shapes[oid][1]),
+                               initial_state=SimpleNamespace(orientation=self.ori0[oid], velocity=self.vel0[oid]))
 
     def step(self, time_step, obstacle_id_list=None, scenario=None):
         h = self.horizon
-        out = {}
-        for oid, p in self.full.items():
-            out[oid] = {"pos_list": p["pos_list"][time_step:time_step + h], "cov_list": p["cov_list"][:h],
-                        "orientation_list": np.asarray(p["orientation_list"])[time_step:time_step + h],
-                        "v_list": np.asarray(p["v_list"])[time_step:time_step + h], "shape": p["shape"]}
-        return out
+        return {oid: {"pos_list": p["pos_list"][time_step:time_step + h], "cov_list": p["cov_list"][:h]}
+                for oid, p in self.full.items()}
 
 
 def closed_loop(n_steps=200, weights="weights_ethical.json", grid="cfg2", v0=12.0, n_obstacles=8, materialize=False,
@@ -92,8 +99,7 @@ def closed_loop(n_steps=200, weights="weights_ethical.json", grid="cfg2", v0=12.
     params = default_params(weights)
     fpar = {"t_list": list(t_list), "v_list_generation_mode": "linspace", "n_v_samples": nv,
             "d_list": np.linspace(-dmax, dmax, nd), "dt": 0.1, "v_thr": 3.0}
-    scenario = SimpleNamespace(dt=0.1, obstacle_by_id=lambda oid: SimpleNamespace(
-        obstacle_type=SimpleNamespace(name=pred.types[oid])))
+    scenario = SimpleNamespace(dt=0.1, obstacle_by_id=pred.obstacle_by_id)
     problem = SimpleNamespace(velocity_cost_mode=0, velocity_target=v0, cost_factor=1.0)
     x0, y0 = csp.calc_position(0.0)
     ego = SimpleNamespace(position=np.array([x0, y0]), orientation=float(csp.calc_yaw(0.0)), velocity=v0, acceleration=0.0,

@@ -220,6 +220,39 @@ int etp_set_spline(etp_ctx* ctx, const double* knots, const double* coef_x, cons
 /* replaces the `predictions` argument (frenet_functions.py:481; collision_probability.py:136; harm_estimation.py:202) */
 int etp_set_obstacles(etp_ctx* ctx, const etp_obstacles* obstacles, int precision);
 
+/*
+ * The step BEFORE the scored path, on the device: raw predictions {pos_list, cov_list} as the predictor
+ * returns them are extended by orientation, velocity, shape margins and the action-space responsibility flag, and packed,
+ * without the host ever forming the enriched dict:
+ *   get_orientation_velocity_and_shape_of_prediction (planner/Frenet/utils/prediction_helpers.py:75-135): np.gradient of
+ *     the positions over t_i = 0.0 + i * dt, "barely moves" rule (all dx < 1e-4 and all dy < 1e-4, no abs: sic) ->
+ *     initial orientation, one-sample predictions -> initial orientation / velocity, shape + safety margins;
+ *   assign_responsibility_by_action_space (planner/utils/responsibility.py:57-89): view cone of +-pi/4, no angle wrap.
+ * Replaces etp_set_obstacles for that step.  etp_get_enriched reads the derived arrays back (the log line prints them).
+ */
+typedef struct {
+    int32_t n_obstacles;            /* O */
+    int32_t max_pred;               /* row stride Tp */
+    const int32_t* pred_len;        /* [O] >= 1 (the reference deletes empty predictions, prediction_helpers.py:98-100) */
+    const double* pos;              /* [O][max_pred][2] */
+    const double* cov;              /* [O][max_pred][4] */
+    const double* length;           /* [O] obstacle_shape.length (no margin) */
+    const double* width;            /* [O] obstacle_shape.width */
+    const double* init_orientation; /* [O] obstacle.initial_state.orientation */
+    const double* init_velocity;    /* [O] obstacle.initial_state.velocity */
+    const double* mass;             /* [O] get_obstacle_mass of the shape INCLUDING margins (properties.py:14-46) */
+    const int32_t* is_protected;    /* [O] */
+    double dt;                      /* scenario.dt */
+    double safety_margin_length, safety_margin_width;
+    double ego_x, ego_y, ego_orientation;
+} etp_raw_predictions;
+
+int etp_set_raw_predictions(etp_ctx* ctx, const etp_raw_predictions* raw, int precision);
+
+/* orientation_list / v_list [O][max_pred], shape length / width incl. margins [O], responsibility [O] of the last
+ * etp_set_raw_predictions (any pointer may be NULL).  Synchronises. */
+int etp_get_enriched(etp_ctx* ctx, double* yaw, double* vel, double* length, double* width, int32_t* responsibility);
+
 /* calc_frenet_trajectories + sort_frenet_trajectories + selection for the dense range of `step`:
  * frenet_planner.py:326-340, 433-457, 555-558.  `out` may be NULL (argmin-only mode). */
 int etp_plan_step(etp_ctx* ctx, const etp_step* step, const etp_out* out);

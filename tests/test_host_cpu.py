@@ -235,3 +235,27 @@ def test_log_line_format_round_trip(tmp_path):
     assert txt[1].count(";") == 6
     d = get_data_from_line(p, 1)
     assert d["simulation_step"] == 3 and d["valid_trajectories"][0]["ego_risk_dict"] == {"7": 0.25} and d["reach_set"] is None
+
+
+def test_host_enrichment_matches_the_reference_golden_vectors():
+    """synthetic.enrich_predictions / assign_responsibility_by_action_space (host side, used by the scene generator)
+    against the vectors of the reference's own functions (tests/golden/make_golden_enrich.py)."""
+    import copy
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "enrich_cases.npz"))
+    for c in range(int(z["n_cases"])):
+        ids = [int(i) for i in z[f"c{c}_ids"]]
+        raw, shapes, ori0, vel0 = {}, {}, {}, {}
+        for j, oid in enumerate(ids):
+            pos = z[f"c{c}_{j}_pos"]
+            raw[oid] = {"pos_list": pos.copy(), "cov_list": np.zeros((len(pos), 2, 2))}
+            a = z[f"c{c}_{j}_in"]
+            shapes[oid], ori0[oid], vel0[oid] = (float(a[0]), float(a[1])), float(a[2]), float(a[3])
+        pred = synthetic.enrich_predictions(copy.deepcopy(raw), shapes, ori0, vel0, float(z[f"c{c}_dt"]))
+        ego = z[f"c{c}_ego"]
+        synthetic.assign_responsibility_by_action_space(ego[:2], float(ego[2]), pred)
+        for j, oid in enumerate(ids):
+            np.testing.assert_array_equal(np.asarray(pred[oid]["orientation_list"], dtype=np.float64), z[f"c{c}_{j}_yaw"])
+            np.testing.assert_array_equal(np.asarray(pred[oid]["v_list"], dtype=np.float64), z[f"c{c}_{j}_vel"])
+            out = z[f"c{c}_{j}_out"]
+            assert (pred[oid]["shape"]["length"], pred[oid]["shape"]["width"], pred[oid]["responsibility"]) == tuple(out)
