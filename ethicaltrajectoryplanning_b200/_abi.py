@@ -37,6 +37,10 @@ _ip = C.POINTER(C.c_int32)
 _bp = C.POINTER(C.c_uint8)
 
 
+COLLISION_HOST, COLLISION_DISCRETE, COLLISION_SWEPT = 0, 1, 2
+COLLISION_CODES = {"host": COLLISION_HOST, "discrete": COLLISION_DISCRETE, "swept": COLLISION_SWEPT}
+
+
 class Params(C.Structure):
     _fields_ = [
         ("weights", C.c_double * NUM_WEIGHTS),
@@ -54,6 +58,7 @@ class Params(C.Structure):
         ("veh_l", C.c_double), ("veh_w", C.c_double), ("veh_l_r", C.c_double), ("veh_m", C.c_double),
         ("veh_steer_max", C.c_double), ("veh_lat_a_max", C.c_double), ("veh_v_max", C.c_double),
         ("veh_a_max", C.c_double),
+        ("collision_check", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

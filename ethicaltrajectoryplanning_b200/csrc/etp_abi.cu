@@ -214,6 +214,10 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
     d.planner_mode = p->planner_mode;
     d.mahalanobis = p->fast_prob_mahalanobis;
     d.multi_cost = p->multiple_cost_functions;
+    if (p->collision_check < ETP_COLLISION_HOST || p->collision_check > ETP_COLLISION_SWEPT) ETP_FAIL(c, ETP_ERR_INVALID, "collision_check");
+    // validity_checks.py:253-268: predictions are tested in modes "WaleNet" and "risk"; "ground_truth" asks the scenario's
+    // own collision checker (host)
+    d.collision_check = p->planner_mode == ETP_MODE_GROUND_TRUTH ? ETP_COLLISION_HOST : p->collision_check;
     d.n_thr = p->n_angle_thresholds;
     d.max_risk = p->max_acceptable_risk;
     for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) {
@@ -282,7 +286,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
     c->has_pred = 1;
     const int O = o->n_obstacles, Tp = o->max_pred;
     if (O > 0) {
-        if (Tp < 1 || !o->pred_len || !o->pos || !o->cov || !o->yaw || !o->vel || !o->length || !o->mass || !o->is_protected ||
+        if (Tp < 1 || !o->pred_len || !o->pos || !o->cov || !o->yaw || !o->vel || !o->length || !o->width || !o->mass || !o->is_protected ||
             !o->responsibility)
             ETP_FAIL(c, ETP_ERR_INVALID, "obstacle arrays missing");
         for (int i = 0; i < O; ++i) {
@@ -309,6 +313,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         ETP_CUDA(c, c->o_yaw.reserve(sizeof(double) * n));
         ETP_CUDA(c, c->o_vel.reserve(sizeof(double) * n));
         ETP_CUDA(c, c->o_len.reserve(sizeof(double) * O));
+        ETP_CUDA(c, c->o_wid.reserve(sizeof(double) * O));
         ETP_CUDA(c, c->o_mass.reserve(sizeof(double) * O));
         ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
@@ -320,6 +325,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         if ((r = stage_to_device(c, c->o_yaw.p, o->yaw, sizeof(double) * n))) return r;
         if ((r = stage_to_device(c, c->o_vel.p, o->vel, sizeof(double) * n))) return r;
         if ((r = stage_to_device(c, c->o_len.p, o->length, sizeof(double) * O))) return r;
+        if ((r = stage_to_device(c, c->o_wid.p, o->width, sizeof(double) * O))) return r;
         if ((r = stage_to_device(c, c->o_mass.p, o->mass, sizeof(double) * O))) return r;
         if ((r = stage_to_device(c, c->o_plen.p, o->pred_len, sizeof(int) * O))) return r;
         if ((r = stage_to_device(c, c->o_prot.p, o->is_protected, sizeof(int) * O))) return r;
@@ -327,7 +333,7 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
         if ((r = end_staging(c))) return r;
         ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
-                                          c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
+                                          c->o_wid.as<double>(), c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
                                           c->origin_x, c->origin_y, c->o_tile.p, c->o_const.as<double>(), c->stream));
     }
     c->O = O;
@@ -397,7 +403,7 @@ int etp_set_raw_predictions(etp_ctx* c, const etp_raw_predictions* o, int precis
                                   c->o_vel.as<double>(), c->o_len.as<double>(), c->o_wid.as<double>(), c->o_resp.as<int>(), c->stream));
         ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
-                                          c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
+                                          c->o_wid.as<double>(), c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
                                           c->origin_x, c->origin_y, c->o_tile.p, c->o_const.as<double>(), c->stream));
     }
     c->O = O;

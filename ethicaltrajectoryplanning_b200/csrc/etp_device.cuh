@@ -53,11 +53,12 @@ template <typename R> struct Tile {
 };
 
 // per-obstacle constants [o][OC_COUNT], fp64 (exact inputs of the fp64 gate re-check and the principle costs)
-enum { OC_KE = 0, OC_KO, OC_PROT, OC_RESP, OC_HALFLEN, OC_COUNT };
+enum { OC_KE = 0, OC_KO, OC_PROT, OC_RESP, OC_HALFLEN, OC_HALFWID, OC_MAXSTEP, OC_COUNT };  // MAXSTEP: largest |dx| + |dy| between consecutive means
 
 struct DevParams {
     double w[ETP_NUM_WEIGHTS];
     int planner_mode, mahalanobis, multi_cost, n_thr;
+    int collision_check;  // ETP_COLLISION_*, already 0 when the planner mode does not test predictions
     double max_risk;
     double thr[ETP_MAX_ANGLE_BINS];
     double fcos[ETP_MAX_ANGLE_BINS];  // cos(thr) * |cos(thr)|: band tests on direction vectors (fp32 path)

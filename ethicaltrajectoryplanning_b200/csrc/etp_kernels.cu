@@ -21,7 +21,8 @@ template <typename R>
 __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
                                       const double* __restrict__ cov, const double* __restrict__ yaw,
                                       const double* __restrict__ vel, const double* __restrict__ length,
-                                      const double* __restrict__ mass, const int* __restrict__ prot,
+                                      const double* __restrict__ width, const double* __restrict__ mass,
+                                      const int* __restrict__ prot,
                                       const int* __restrict__ resp, double veh_m, double ox, double oy,
                                       void* __restrict__ tile_base, double* __restrict__ oconst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,6 +123,13 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
         oconst[o * OC_COUNT + OC_PROT] = prot[o] ? 1.0 : 0.0;
         oconst[o * OC_COUNT + OC_RESP] = (double)resp[o];
         oconst[o * OC_COUNT + OC_HALFLEN] = length[o] / 2;
+        oconst[o * OC_COUNT + OC_HALFWID] = width[o] / 2;
+        double step = 0.0;  // reach of the swept collision test (etp_score.cu)
+        for (int k = 0; k + 1 < n; ++k) {
+            const double* q = pos + ((size_t)o * Tp + k) * 2;
+            step = fmax(step, fabs(q[2] - q[0]) + fabs(q[3] - q[1]));
+        }
+        oconst[o * OC_COUNT + OC_MAXSTEP] = step;
         const_cast<Vec4<R>*>(tile.C)[o] = Vec4<R>{(R)ke, (R)ko, (R)(prot[o] ? 1 : 0), (R)resp[o]};
     }
 }
@@ -411,17 +419,18 @@ __global__ void best_trajectory_kernel(DevStep st, const BestRec* __restrict__ b
 // host-side launchers (called from etp_abi.cpp)
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_len, const double* pos, const double* cov,
-                                  const double* yaw, const double* vel, const double* length, const double* mass,
-                                  const int* prot, const int* resp, double veh_m, double ox, double oy, void* tile,
+                                  const double* yaw, const double* vel, const double* length, const double* width,
+                                  const double* mass, const int* prot, const int* resp, double veh_m, double ox, double oy,
+                                  void* tile,
                                   double* oconst, cudaStream_t stream) {
     const int n = O * Tp;
     if (n <= 0) return cudaSuccess;
     const int blocks = (n + 127) / 128;
     if (precision == ETP_PRECISION_FP64)
-        pack_obstacles_kernel<double><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, mass, prot, resp,
+        pack_obstacles_kernel<double><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, width, mass, prot, resp,
                                                                   veh_m, ox, oy, (double*)tile, oconst);
     else
-        pack_obstacles_kernel<float><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, mass, prot, resp,
+        pack_obstacles_kernel<float><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, width, mass, prot, resp,
                                                                  veh_m, ox, oy, (float*)tile, oconst);
     return cudaGetLastError();
 }

@@ -10,9 +10,9 @@ namespace etp {
 constexpr int kMaxGrid = 4096;  // upper bound of persistent CTAs (148 SMs x resident CTAs per SM)
 
 cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_len, const double* pos, const double* cov,
-                                  const double* yaw, const double* vel, const double* length, const double* mass,
-                                  const int* prot, const int* resp, double veh_m, double ox, double oy, void* tile,
-                                  double* oconst, cudaStream_t stream);
+                                  const double* yaw, const double* vel, const double* length, const double* width,
+                                  const double* mass, const int* prot, const int* resp, double veh_m, double ox, double oy,
+                                  void* tile, double* oconst, cudaStream_t stream);
 
 cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, cudaStream_t stream);
 

@@ -472,6 +472,73 @@ __device__ __noinline__ bool gate_exact(const DevStep* stp, bool given, int pl, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// collision of the ego box with the predicted obstacle boxes (validity level 1, ETP_COLLISION_* in etp_b200.h;
+// validity_checks.py:125-141,216-274, prediction_helpers.py:138-210)
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct Box {
+    R x, y, c, s, l, w;  // centre, local x axis (cos, sin), half extents
+};
+
+// Largest separating-axis margin of two boxes over the four face normals: > 0 <=> disjoint.
+template <typename R> __device__ __forceinline__ R sat_margin(const Box<R>& a, const Box<R>& b) {
+    const R dx = b.x - a.x, dy = b.y - a.y;
+    const R c = abs_(a.c * b.c + a.s * b.s), s = abs_(a.s * b.c - a.c * b.s);
+    const R m0 = abs_(dx * a.c + dy * a.s) - (a.l + b.l * c + b.w * s);
+    const R m1 = abs_(dy * a.c - dx * a.s) - (a.w + b.l * s + b.w * c);
+    const R m2 = abs_(dx * b.c + dy * b.s) - (b.l + a.l * c + a.w * s);
+    const R m3 = abs_(dy * b.c - dx * b.s) - (b.w + a.l * s + a.w * c);
+    return rmax_(rmax_(m0, m1), rmax_(m2, m3));
+}
+
+// The box in the frame of `a` that encloses `a` and the next box `b` of the same object (ETP_COLLISION_SWEPT).
+template <typename R> __device__ __forceinline__ Box<R> hull_box(const Box<R>& a, const Box<R>& b) {
+    const R dx = b.x - a.x, dy = b.y - a.y;
+    const R ux = dx * a.c + dy * a.s, uy = dy * a.c - dx * a.s;
+    const R c = abs_(a.c * b.c + a.s * b.s), s = abs_(a.s * b.c - a.c * b.s);
+    const R ex = b.l * c + b.w * s, ey = b.l * s + b.w * c;
+    const R xlo = ux - ex < -a.l ? ux - ex : -a.l, xhi = ux + ex > a.l ? ux + ex : a.l;
+    const R ylo = uy - ey < -a.w ? uy - ey : -a.w, yhi = uy + ey > a.w ? uy + ey : a.w;
+    const R mx = (R)0.5 * (xlo + xhi), my = (R)0.5 * (ylo + yhi);
+    return Box<R>{a.x + mx * a.c - my * a.s, a.y + mx * a.s + my * a.c, a.c, a.s, (R)0.5 * (xhi - xlo), (R)0.5 * (yhi - ylo)};
+}
+
+__device__ __forceinline__ Box<double> ego_box_exact(const DevStep& st, const DevParams& pr, bool given, int pl, int id, int ti) {
+    double xe, ye, yaw;
+    if (given) {
+        xe = st.given[((size_t)ETP_F_X * st.Tmax + ti) * st.given_stride + pl];
+        ye = st.given[((size_t)ETP_F_Y * st.Tmax + ti) * st.given_stride + pl];
+        yaw = st.given[((size_t)ETP_F_YAW * st.Tmax + ti) * st.given_stride + pl];
+    } else {
+        const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+        const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+        const bool low = pm[PM_LOW] != 0.0;
+        const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+        const TrajPoint tp = traj_point(q, low, gp, st.Tmax, ti, st.dt);
+        xe = tp.f[ETP_F_X];
+        ye = tp.f[ETP_F_Y];
+        yaw = tp.f[ETP_F_YAW];
+    }
+    return Box<double>{xe, ye, cos(yaw), sin(yaw), pr.veh_l * 0.5, pr.veh_w * 0.5};
+}
+
+__device__ __forceinline__ Box<double> obstacle_box_exact(const DevStep& st, int o, int t) {
+    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+    const double psi = st.raw_yaw[(size_t)o * st.Tp + t];
+    return Box<double>{rp[0], rp[1], cos(psi), sin(psi), st.obs_const[o * OC_COUNT + OC_HALFLEN], st.obs_const[o * OC_COUNT + OC_HALFWID]};
+}
+
+// One (ego box t + 1, prediction box t) test repeated in fp64 from the exact inputs: the fp32 path calls this when its
+// own margin is too close to zero.  `hull_e` / `hull_o`: the object is swept over its next sample.
+__device__ __noinline__ bool collide_exact(const DevStep* stp, const DevParams* prp, bool given, int pl, int id, int o, int t,
+                                           bool hull_e, bool hull_o) {
+    Box<double> e = ego_box_exact(*stp, *prp, given, pl, id, t + 1);
+    if (hull_e) e = hull_box(e, ego_box_exact(*stp, *prp, given, pl, id, t + 2));
+    Box<double> b = obstacle_box_exact(*stp, o, t);
+    if (hull_o) b = hull_box(b, obstacle_box_exact(*stp, o, t + 1));
+    return !(sat_margin(e, b) > 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // shared-memory plan of one CTA
 // ---------------------------------------------------------------------------------------------
 enum { MX_EGO_RISK = 0, MX_OBST_RISK, MX_EGO_ARG, MX_OBST_ARG, MX_COUNT };  // running maxima over time, [MX][O][32]
@@ -719,6 +786,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     __shared__ BestRec wbest[kWarps];
     __shared__ bool is_last;
     __shared__ int s_nprot;
+    __shared__ int s_hit[32];  // lane's candidate collides with a predicted box (pr.collision_check)
     int* s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);  // [On] obstacles sorted by class
     if (tid == 0) {
         fill_tab<R>(tab, pr, st.eps_pos);
@@ -753,6 +821,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             s_qn = 0;
             s_qpos = 0;
         }
+        if (tid < 32) s_hit[tid] = 0;
         for (int i = tid; i < MX_COUNT * On * 32; i += kThreads) sm.mx[i] = Enc<R>::enc((R)-INFINITY);
         __syncthreads();  // (a) tile index visible; previous tile fully consumed
         const int tl = s_tile;
@@ -950,6 +1019,76 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 }
                 if (o_prob && active) o_prob[vi * Cp + cl] = prob;
             }
+
+            // ---- collision with the predicted boxes (optional): warps over (obstacle, time segment) items ----------
+            // pair t: ego box of sample t + 1 (time step + t + 1) against prediction box t; swept mode replaces each by
+            // the hull with its successor.  One distance test against a per-item reach rejects most pairs.
+            if (pr.collision_check != ETP_COLLISION_HOST) {
+                const bool swept = pr.collision_check == ETP_COLLISION_SWEPT;
+                const R hl = (R)(pr.veh_l * 0.5), hw = (R)(pr.veh_w * 0.5);
+                const R tol = (R)1e-4 + (R)16 * tab.eps_pos;
+                R reach_e = sqrt_(hl * hl + hw * hw) + (R)1e-2;
+                if (swept) {  // largest step of this candidate
+                    R stp = 0;
+                    for (int t = 0; t + 1 < Tl; ++t) {
+                        const Vec4<R> a = sm.e0[t * 32 + lane], b = sm.e0[(t + 1) * 32 + lane];
+                        stp = rmax_(stp, abs_(b.x - a.x) + abs_(b.y - a.y));
+                    }
+                    reach_e += stp;
+                }
+                const int c_seg = (2 * kWarps + O - 1) / O, c_len = (Ts - 1 + c_seg - 1) / c_seg;
+                bool hit = false;
+                for (int item = warp; item < O * c_seg; item += kWarps) {
+                    const int o = item % O, t_lo = (item / O) * c_len, t_hi = min(t_lo + c_len, Ts - 1);
+                    const int n_o = __ldg(st.pred_len + o);
+                    const int plen = Tl < n_o ? Tl : n_o;  // prediction_helpers.py:168
+                    const bool hull_o = swept && plen >= 2;
+                    const R ol = (R)__ldg(st.obs_const + o * OC_COUNT + OC_HALFLEN), ow = (R)__ldg(st.obs_const + o * OC_COUNT + OC_HALFWID);
+                    R reach = reach_e + sqrt_(ol * ol + ow * ow);
+                    if (swept) reach += (R)__ldg(st.obs_const + o * OC_COUNT + OC_MAXSTEP);
+                    const R reach2 = reach * reach;
+                    const int t_end = min(t_hi, min(n_o, st.Tp));  // no prediction box past n_o
+                    const Vec4<R>* Go = tile.G + 2 * (size_t)o;
+                    // four pairs per round: the loads and distance tests are independent chains, the box test runs only
+                    // when one of them is within reach (a clamped tail pair is simply tested twice)
+                    for (int t4 = t_lo; t4 < t_end; t4 += 4) {
+                        unsigned near = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int t = min(t4 + k, t_end - 1);
+                            const Vec4<R> n0 = sm.e0[(t + 1) * 32 + lane];
+                            const Vec4<R> g0 = ldg4<R>(Go + 2 * (size_t)(t * O));
+                            const R dx = g0.x - n0.x, dy = g0.y - n0.y;
+                            near |= (dx * dx + dy * dy <= reach2 ? 1u : 0u) << k;
+                        }
+                        if (near == 0) continue;
+#pragma unroll 1
+                        for (int k = 0; k < 4; ++k) {
+                            const int t = min(t4 + k, t_end - 1);
+                            const bool valid = swept ? (t + 2 < Tl && (hull_o ? t + 1 < plen : t == 0)) : (t + 1 < Tl && t < plen);
+                            if (!((near >> k) & 1u) || !valid) continue;
+                            const Vec4<R> n0 = sm.e0[(t + 1) * 32 + lane];
+                            const Vec4<R> g0 = ldg4<R>(Go + 2 * (size_t)(t * O)), g1 = ldg4<R>(Go + 2 * (size_t)(t * O) + 1);
+                            Box<R> e{n0.x, n0.y, n0.z, n0.w, hl, hw};
+                            Box<R> b{g0.x, g0.y, g1.y, g1.z, ol, ow};
+                            if (swept) {
+                                const Vec4<R> n1 = sm.e0[(t + 2) * 32 + lane];
+                                e = hull_box(e, Box<R>{n1.x, n1.y, n1.z, n1.w, hl, hw});
+                                if (hull_o) {
+                                    const Vec4<R> h0 = ldg4<R>(Go + 2 * (size_t)((t + 1) * O)), h1 = ldg4<R>(Go + 2 * (size_t)((t + 1) * O) + 1);
+                                    b = hull_box(b, Box<R>{h0.x, h0.y, h1.y, h1.z, ol, ow});
+                                }
+                            }
+                            const R m = sat_margin(e, b);
+                            bool col = !(m > (R)0);
+                            if (sizeof(R) == 4 && abs_(m) < tol) col = collide_exact(&st, &pr, kGiven, pl, id, o, t, swept, hull_o);
+                            hit |= col;
+                        }
+                    }
+                    if (__all_sync(kFull, hit || !live)) break;  // nothing left to find for this warp's lanes
+                }
+                if (hit) s_hit[lane] = 1;
+            }
         }
         __syncthreads();  // (c) maxima complete, ego samples dead
 
@@ -1042,7 +1181,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 const int cf = (first_fail == 0x7fffffff || first_fail < 0) ? 0 : (first_fail & 3);
                 if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
                 else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
-                else if (ext == 1) { level = 1; reason = ETP_REASON_COLLISION; }
+                else if (ext == 1 || s_hit[lane]) { level = 1; reason = ETP_REASON_COLLISION; }
                 else if (st.has_pred ? (bd != 0.0) : (ext == 2)) { level = 2; reason = ETP_REASON_BOUNDARIES; }
                 else if (pr.planner_mode == ETP_MODE_RISK && st.has_pred && O > 0 &&
                          (sum_e > pr.max_risk || max_o > pr.max_risk)) { level = 3; reason = ETP_REASON_MAX_RISK; }

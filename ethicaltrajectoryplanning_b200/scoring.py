@@ -104,6 +104,12 @@ def make_params(params, vehicle, mode="risk") -> _abi.Params:
     p.veh_lat_a_max = vehicle.lateral_a_max
     p.veh_v_max = vehicle.longitudinal.v_max
     p.veh_a_max = vehicle.longitudinal.a_max
+    # extension key (not in the reference's risk.json): test the candidates against the predicted boxes on the device
+    # instead of taking pycrcc's answer through ext_level ("host", the default) -- ETP_COLLISION_* in etp_b200.h
+    check = modes.get("collision_check_device", "host")
+    if check not in _abi.COLLISION_CODES:
+        raise ValueError("modes['collision_check_device'] must be host, discrete or swept")
+    p.collision_check = _abi.COLLISION_CODES[check]
     return p
 
 

@@ -77,6 +77,22 @@ enum { ETP_REASON_NONE = 0, ETP_REASON_VELOCITY = 1, ETP_REASON_ACCELERATION = 2
 /* planner mode (frenet_planner.py:199-202, frenet_functions.py:524-527, validity_checks.py:287) */
 enum { ETP_MODE_RISK = 0, ETP_MODE_WALENET = 1, ETP_MODE_GROUND_TRUTH = 2 };
 
+/*
+ * Collision of the ego box with the predicted obstacle boxes (validity_checks.py:91-103,216-274;
+ * prediction_helpers.py:138-210) in planner modes "risk" and "WaleNet".  The reference asks pycrcc: ego boxes
+ * RectOBB(l/2, w/2, yaw[i], x[i], y[i]) at time steps time_step + i, prediction boxes RectOBB(length/2, width/2,
+ * orientation_list[j], pos_list[j]) at time_step + 1 + j for j < min(len(ft.t), len(pos_list)), each object first run
+ * through trajectory_preprocess_obb_sum and, if that fails, used as it is.
+ *   HOST     : the device tests nothing; pycrcc's answer arrives in etp_step.ext_level (the strict default).
+ *   DISCRETE : the un-preprocessed objects: box i = j + 1 against box j (separating-axis test).  Exact semantics
+ *              of the reference's fallback branch (validity_checks.py:136-141, prediction_helpers.py:189-194).
+ *   SWEPT    : consecutive boxes (k, k + 1) of each object are replaced by the box in the frame of box k that
+ *              encloses both, then tested pairwise.  pycrcc's hull construction is not part of the reference
+ *              sources (commonroad-drivability-checker, un-vendored): same intent, not pinned to it.
+ * A hit is OR-ed with ext_level == 1.
+ */
+enum { ETP_COLLISION_HOST = 0, ETP_COLLISION_DISCRETE = 1, ETP_COLLISION_SWEPT = 2 };
+
 /* element type of the real-valued output tensors and of the risk arithmetic */
 enum { ETP_PRECISION_FP32 = 0, ETP_PRECISION_FP64 = 1 };
 
@@ -105,6 +121,8 @@ typedef struct {
     double lr1s_const, lr1s_speed;   /* ignore-angle model: ego harm against unprotected obstacles */
     double ped_const, ped_speed;     /* harm_parameters.json "pedestrian" (harm_estimation.py:408-414) */
     double veh_l, veh_w, veh_l_r, veh_m, veh_steer_max, veh_lat_a_max, veh_v_max, veh_a_max;
+    int32_t collision_check;         /* ETP_COLLISION_*: collision with the predictions (validity level 1) on the device */
+    int32_t reserved0;
 } etp_params;
 
 /*

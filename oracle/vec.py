@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import boxes as _boxes
 from . import bvn as _bvn
 from . import port as _port
 
@@ -258,6 +259,9 @@ def score_dense(step, profiles=None):
         hv = np.where(first >= 0, ~(v[np.arange(n), np.maximum(first, 0)] < thr_v), False)
         bd = np.zeros(n) if step.bd_harm is None else np.asarray(step.bd_harm, dtype=np.float64)[p * nd + idx]
         ext = np.full(n, 10) if step.ext_level is None else np.asarray(step.ext_level)[p * nd + idx].astype(np.int64)
+        check = modes.get("collision_check_device", "host")  # product extension, see oracle/boxes.py
+        if check != "host" and preds is not None and step.mode in ("WaleNet", "risk"):
+            ext = np.where(_boxes.collision_mask(x, y, yaw, preds, vp.l, vp.w, check), 1, ext)
         # first failing test wins (validity_checks.py:63-122): apply in reverse order of precedence
         level = np.full(n, 10)
         reason = np.zeros(n, dtype=np.int64)

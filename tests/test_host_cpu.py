@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_abi_struct_sizes_match_the_header_layout():
     assert ctypes.sizeof(_abi.Best) == 40
-    assert ctypes.sizeof(_abi.Params) == 8 * 14 + 4 * 4 + 8 + 8 * 8 + 8 * 9 * 2 + 8 * 6 + 8 * 8
+    assert ctypes.sizeof(_abi.Params) == 8 * 14 + 4 * 4 + 8 + 8 * 8 + 8 * 9 * 2 + 8 * 6 + 8 * 8 + 8
     assert ctypes.sizeof(_abi.Out) == 8 + 6 * 8 + 8 + 8
 
 

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--argmin-only", action="store_true")
     ap.add_argument("--lateral-spread", type=float, default=4.0)
+    ap.add_argument("--collision", default="host", choices=["host", "discrete", "swept"])
     args = ap.parse_args()
     import torch
 
@@ -25,6 +26,10 @@ def main():
     from ethicaltrajectoryplanning_b200.synthetic import make_step
 
     step = make_step(args.workload, nv=args.nv, nd=args.nd, lateral_spread=args.lateral_spread)
+    if args.collision != "host":
+        import copy
+        step.params = copy.deepcopy(step.params)
+        step.params["modes"]["collision_check_device"] = args.collision
     ctx = ScoringContext(0, args.precision)
     ctx.configure(step)
     s, keep, nsamp = ctx.make_step_struct(step)
@@ -35,6 +40,7 @@ def main():
         print("step", i, "profile_ms %.4f score_ms %.4f" % ctx.timing(), ctx.best())
     if bufs is not None:
         print("nonzero prob fraction", float((bufs["prob"] != 0).float().mean()))
+        print("level histogram", torch.bincount(bufs["level"].to(torch.int64), minlength=11)[[0, 1, 2, 3, 10]].tolist())
     torch.cuda.synchronize()
     print("debug counters", ctx.debug_counters())
     ctx.close()
