@@ -80,6 +80,19 @@ class RawPredictions(C.Structure):
     ]
 
 
+class Goal(C.Structure):
+    _fields_ = [
+        ("has_area", C.c_int32), ("n_polygons", C.c_int32),
+        ("poly_start", _ip), ("vertices", _dp),
+        ("n_circles", C.c_int32), ("circles", _dp),
+        ("has_velocity", C.c_int32), ("velocity_start", C.c_double), ("velocity_end", C.c_double),
+        ("has_orientation", C.c_int32), ("orientation_start", C.c_double), ("orientation_end", C.c_double),
+        ("time_start", C.c_int32), ("time_end", C.c_int32), ("ego_time_step", C.c_int32),
+        ("ego_x", C.c_double), ("ego_y", C.c_double),
+        ("has_centers", C.c_int32), ("avg_goal_distance", C.c_double),
+    ]
+
+
 class Step(C.Structure):
     _fields_ = [
         ("c_s", C.c_double), ("c_s_d", C.c_double), ("c_s_dd", C.c_double),
@@ -97,6 +110,7 @@ class Step(C.Structure):
         ("cost_factor_list", _dp),
         ("c_begin", C.c_int32), ("c_end", C.c_int32),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32),
+        ("goal", C.POINTER(Goal)),
     ]
 
 
@@ -117,6 +131,7 @@ class Trajectories(C.Structure):
         ("velocity_cost_mode", C.c_int32),
         ("velocity_target", C.c_double), ("cost_factor", C.c_double),
         ("ext_level", _bp), ("bd_harm", _dp), ("cost_factor_list", _dp),
+        ("goal", C.POINTER(Goal)), ("dt", C.c_double),
     ]
 
 

@@ -75,7 +75,7 @@ struct etp_ctx {
     double origin_x = 0.0, origin_y = 0.0;  // of the fp32 coordinates: first obstacle sample, else the spline start
     std::vector<double> spline_pts, obs_box;  // knot positions (+ reach) and the bounding box of the predictions
     // step
-    DevBuf grids, ext_level, bd_harm, factor_list, prof, prof_meta, nskip;
+    DevBuf grids, ext_level, bd_harm, factor_list, goal_geom, prof, prof_meta, nskip;
     DevBuf block_best, counters, best_dev, traj_dev, traj_n, given, given_T, prin;
     bool last_given = false;
     PinnedBuf stage, best_host, traj_host;
@@ -173,7 +173,7 @@ int etp_destroy(etp_ctx* c) {
     c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
-                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list,
+                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom,
                       &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
                       &c->traj_n, &c->given, &c->given_T, &c->prin};
     for (DevBuf* b : bufs) b->release();
@@ -443,6 +443,88 @@ int etp_tmax(const etp_step* s) {
     return m;
 }
 
+// Digest an etp_goal for the device (calc_trajectory_cost.py:349-415, 438-519): stage the goal geometry, fold the
+// orientation interval the way check_orientation does (:881-932), find the first trajectory sample whose time step
+// lies in the goal's time window (reached_target_time, :639-660; calc_remaining_time_steps, :702-723) and evaluate
+// what depends on the ego state only.  Must run between begin_staging and end_staging.
+static int stage_goal(etp_ctx* c, const etp_goal* g, double dt, int Tmax, DevGoal* out) {
+    DevGoal d{};
+    if (!g) {
+        *out = d;
+        return ETP_OK;
+    }
+    if (g->n_polygons < 0 || g->n_circles < 0 || (g->n_polygons > 0 && (!g->poly_start || !g->vertices)) ||
+        (g->n_circles > 0 && !g->circles))
+        ETP_FAIL(c, ETP_ERR_INVALID, "goal geometry arrays missing");
+    if (!(dt > 0.0)) ETP_FAIL(c, ETP_ERR_INVALID, "goal context needs the scenario time step dt > 0");
+    d.on = 1;
+    d.has_area = g->has_area ? 1 : 0;
+    d.n_poly = d.has_area ? g->n_polygons : 0;
+    d.n_circ = d.has_area ? g->n_circles : 0;
+    const int n_vert = d.n_poly > 0 ? g->poly_start[d.n_poly] : 0;
+    for (int p = 0; p < d.n_poly; ++p)
+        if (g->poly_start[p + 1] - g->poly_start[p] < 3) ETP_FAIL(c, ETP_ERR_INVALID, "goal polygon %d has fewer than 3 vertices", p);
+    const size_t b_start = sizeof(int) * (size_t)(d.n_poly + 1), b_start_pad = (b_start + 7) / 8 * 8;
+    const size_t b_vert = sizeof(double) * 2 * (size_t)n_vert, b_circ = sizeof(double) * 3 * (size_t)d.n_circ;
+    ETP_CUDA(c, c->goal_geom.reserve(b_start_pad + b_vert + b_circ + 8));
+    unsigned char* base = c->goal_geom.as<unsigned char>();
+    int r;
+    if (d.n_poly > 0) {
+        if ((r = stage_to_device(c, base, g->poly_start, b_start))) return r;
+        if ((r = stage_to_device(c, base + b_start_pad, g->vertices, b_vert))) return r;
+    }
+    if (d.n_circ > 0 && (r = stage_to_device(c, base + b_start_pad + b_vert, g->circles, b_circ))) return r;
+    d.poly_start = reinterpret_cast<const int*>(base);
+    d.verts = reinterpret_cast<const double*>(base + b_start_pad);
+    d.circles = reinterpret_cast<const double*>(base + b_start_pad + b_vert);
+    d.has_vel = g->has_velocity ? 1 : 0;
+    d.v_lo = g->velocity_start;
+    d.v_hi = g->velocity_end;
+    d.vel_mid = g->velocity_start + (g->velocity_end - g->velocity_start) / 2;  // :456-463
+    d.has_ori = g->has_orientation ? 1 : 0;
+    {
+        const double PI = 3.14159265358979323846;
+        double v[2] = {g->orientation_start, g->orientation_end};
+        int n_in_range = 0;
+        for (int k = 0; k < 2; ++k) {
+            if (v[k] > PI) {
+                while (v[k] > PI) v[k] -= 2 * PI;
+            } else if (v[k] < -PI) {
+                while (v[k] < -PI) v[k] += 2 * PI;
+            } else {
+                ++n_in_range;
+            }
+        }
+        d.o_lo = std::fmin(v[0], v[1]);
+        d.o_hi = std::fmax(v[0], v[1]);
+        d.ori_invert = n_in_range == 1 ? 1 : 0;
+    }
+    d.time_first = 0x7fffffff;
+    for (int i = 0; i < Tmax; ++i) {
+        const double t = 0.0 + i * dt;                                   // traj.t = np.arange(0, tT, dt)
+        const int considered = (int)((double)g->ego_time_step + t / dt);  // int(ego_state_time + t / dt)
+        if (g->time_start - considered <= 0 && g->time_end - considered >= 0) {
+            d.time_first = i;
+            break;
+        }
+    }
+    // host-side containment of the ego position: same function, same fp64 arithmetic as the device
+    d.ego_in_goal = !d.has_area || point_in_goal(d, g->poly_start, g->vertices, g->circles, g->ego_x, g->ego_y);
+    if (!g->has_centers) {
+        d.vel_kind = 3;  // "no velocity can be proposed" (:489-490)
+    } else {
+        const double remaining = (double)(g->time_end - g->ego_time_step) * dt;  // t = 0: considered = ego time step
+        if (remaining > 0.0) {
+            d.vel_kind = 0;
+            d.vel_out = g->avg_goal_distance / remaining;
+        } else {
+            d.vel_kind = 1;
+        }
+    }
+    *out = d;
+    return ETP_OK;
+}
+
 int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     if (!c || !s) return ETP_ERR_INVALID;
     if (!c->have_params || !c->have_spline || !c->have_obs)
@@ -495,6 +577,7 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
         if ((r = stage_to_device(c, c->factor_list.p, s->cost_factor_list, sizeof(double) * (size_t)dense))) return r;
         st.factor_list = c->factor_list.as<double>();
     }
+    if ((r = stage_goal(c, s->goal, s->dt, Tmax, &st.goal))) return r;
     if ((r = end_staging(c))) return r;
 
     unsigned char* g = c->grids.as<unsigned char>();
@@ -606,6 +689,7 @@ int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out*
         if ((r = stage_to_device(c, c->factor_list.p, g->cost_factor_list, sizeof(double) * n))) return r;
         st.factor_list = c->factor_list.as<double>();
     }
+    if ((r = stage_goal(c, g->goal, g->dt, g->t_max, &st.goal))) return r;
     if ((r = end_staging(c))) return r;
     st.given = c->given.as<double>(); st.given_T = c->given_T.as<int>(); st.given_stride = g->n_traj;
     st.nv = 1; st.nt = 1; st.nd = g->n_traj; st.Tmax = g->t_max;

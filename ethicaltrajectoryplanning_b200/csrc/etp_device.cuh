@@ -75,6 +75,41 @@ struct DevParams {
     double wrapfree_yaw;
 };
 
+// goal context of a step (etp_goal, pre-digested on the host; calc_trajectory_cost.py:349-415, 438-519)
+struct DevGoal {
+    int on;                  // 0: the step's scalars / factor list are used
+    int has_area, n_poly, n_circ;
+    const int* poly_start;   // [n_poly + 1]
+    const double* verts;     // [.][2]
+    const double* circles;   // [n_circ][3]
+    int has_vel, has_ori, ori_invert;
+    double v_lo, v_hi, vel_mid;
+    double o_lo, o_hi;       // check_orientation's normalised, sorted interval; ori_invert: exactly one end was folded
+    int time_first;          // first sample index whose time step lies inside the goal's time window (INT_MAX: none)
+    int ego_in_goal;         // reached_target_position(ego_state.position)
+    int vel_kind;            // outside the goal at sample 0: 0 |vel_out - mean v|, 1 30 - mean v, 3 zero
+    double vel_out;          // avg_dist / remaining_time
+};
+
+// even-odd containment of (x, y) in the union of the goal's polygons and circles
+__host__ __device__ inline bool point_in_goal(const DevGoal& g, const int* poly_start, const double* verts, const double* circles,
+                                              double x, double y) {
+    for (int p = 0; p < g.n_poly; ++p) {
+        const int a = poly_start[p], b = poly_start[p + 1];
+        bool in = false;
+        for (int i = a, j = b - 1; i < b; j = i++) {
+            const double xi = verts[2 * i], yi = verts[2 * i + 1], xj = verts[2 * j], yj = verts[2 * j + 1];
+            if (((yi > y) != (yj > y)) && (x < (xj - xi) * (y - yi) / (yj - yi) + xi)) in = !in;
+        }
+        if (in) return true;
+    }
+    for (int k = 0; k < g.n_circ; ++k) {
+        const double dx = x - circles[3 * k], dy = y - circles[3 * k + 1], r = circles[3 * k + 2];
+        if (dx * dx + dy * dy <= r * r) return true;
+    }
+    return false;
+}
+
 struct DevStep {
     double c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd, dt, v_thr;
     const double* v_list;
@@ -91,6 +126,7 @@ struct DevStep {
     const uint8_t* ext_level;  // device copy, indexed by dense candidate, or null
     const double* bd_harm;     // device copy, indexed by dense candidate, or null
     const double* factor_list; // device copy, indexed by dense candidate, or null (then `factor`)
+    DevGoal goal;              // goal.on: velocity cost and factor derived per candidate instead
     // spline tables
     const double* knots;
     const double* cx;

@@ -752,6 +752,19 @@ __device__ __forceinline__ void phase2a_dispatch(const Phase2a<R>& a, int g, int
     }
 }
 
+// Goal bookkeeping of one trajectory sample (calc_trajectory_cost.py:553-571 reached_goal_state, :520-550
+// goal_position_reached_and_left_again, :452 velocity_costs): bit 0 = goal state reached at this sample (position,
+// velocity and orientation), bit 1 = sample outside the goal area, bit 2 = sample 0 inside the goal area.
+enum { GF_REACHED = 1, GF_OUTSIDE = 2, GF_START_INSIDE = 4 };
+__device__ __noinline__ int goal_sample_flags(const DevGoal* gp, double x, double y, double v, double yaw, int t) {
+    const DevGoal& g = *gp;
+    const bool in = !g.has_area || point_in_goal(g, g.poly_start, g.verts, g.circles, x, y);
+    const bool vok = !g.has_vel || (g.v_lo < v && v < g.v_hi);                    // helper_functions.py:408-421
+    const bool ins = g.o_lo < yaw && yaw < g.o_hi;
+    const bool ook = !g.has_ori || (g.ori_invert ? !ins : ins);                    // check_orientation, :924-931
+    return ((in && vok && ook) ? GF_REACHED : 0) | (in ? 0 : GF_OUTSIDE) | ((t == 0 && in) ? GF_START_INSIDE : 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // score_kernel
 // ---------------------------------------------------------------------------------------------
@@ -787,6 +800,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     __shared__ bool is_last;
     __shared__ int s_nprot;
     __shared__ int s_hit[32];  // lane's candidate collides with a predicted box (pr.collision_check)
+    __shared__ int s_goal[32]; // GF_* flags of the lane's candidate (st.goal.on)
     int* s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);  // [On] obstacles sorted by class
     if (tid == 0) {
         fill_tab<R>(tab, pr, st.eps_pos);
@@ -821,7 +835,10 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             s_qn = 0;
             s_qpos = 0;
         }
-        if (tid < 32) s_hit[tid] = 0;
+        if (tid < 32) {
+            s_hit[tid] = 0;
+            s_goal[tid] = 0;
+        }
         for (int i = tid; i < MX_COUNT * On * 32; i += kThreads) sm.mx[i] = Enc<R>::enc((R)-INFINITY);
         __syncthreads();  // (a) tile index visible; previous tile fully consumed
         const int tl = s_tile;
@@ -848,7 +865,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         int wf = (sizeof(R) == 4 && NT >= 0) ? 1 : 0;
         {
             double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
-            int first_fail = 0x7fffffff;
+            int first_fail = 0x7fffffff, gflags = 0;
             Poly5 q{};
             if (!kGiven) q = lateral_poly(st, low, dT, pm[PM_TEND], ds);
             const int ta = warp * chunk, tb = min(ta + chunk, Ts);
@@ -878,6 +895,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
                     const int cf = curvature_fail(pr, tp.f[ETP_F_V], tp.f[ETP_F_CURV]);
                     if (cf) first_fail = min(first_fail, t * 4 + cf);  // a velocity failure (-1) stays the minimum
+                    if (st.goal.on) gflags |= goal_sample_flags(&st.goal, tp.f[ETP_F_X], tp.f[ETP_F_Y], tp.f[ETP_F_V], tp.f[ETP_F_YAW], t);
                     if (t > ta) {  // calc_trajectory_cost.py:739-757
                         const double dx = px - tp.f[ETP_F_X], dy = py - tp.f[ETP_F_Y];
                         trav += sqrt(dx * dx + dy * dy);
@@ -902,6 +920,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             double* p1 = sm.p1 + (size_t)warp * P1_COUNT * 32 + lane;
             p1[P1_V * 32] = sv; p1[P1_D * 32] = sd; p1[P1_JL * 32] = jl; p1[P1_JQ * 32] = jq; p1[P1_TRAV * 32] = trav;
             sm.ff[warp * 32 + lane] = first_fail;
+            if (gflags) atomicOr(&s_goal[lane], gflags);
         }
         const bool tile_fast = __syncthreads_and(wf) != 0;  // (b) ego samples complete; all of them wrap-free?
         const bool tile_full = __all_sync(kFull, live && T == Ts) && small_planes;
@@ -1165,8 +1184,29 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                                           pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES] * c[ETP_C_RESPONSIBILITY] +
                                           pr.w[ETP_W_EGO] * c[ETP_C_EGO];
                 const double mean_v = sv / (double)T;
-                switch (st.vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
-                    case 0: c[ETP_C_VELOCITY] = fabs(st.vel_target - mean_v); break;
+                int vel_mode = st.vel_mode;
+                double vel_target = st.vel_target;
+                double factor = st.factor_list ? st.factor_list[c_dense] : st.factor;
+                if (st.goal.on) {
+                    const int gf = s_goal[lane];
+                    if (gf & GF_START_INSIDE) {  // inside the goal area: the goal's velocity, else slow (:452-467)
+                        vel_mode = st.goal.has_vel ? 0 : 2;
+                        vel_target = st.goal.vel_mid;
+                    } else {                     // :469-519
+                        vel_mode = st.goal.vel_kind;
+                        vel_target = st.goal.vel_out;
+                    }
+                    factor = 1.0;                // get_cost_factor, :375-415
+                    bool in_time = false;
+                    if (gf & GF_REACHED) {
+                        factor = 0.01;
+                        in_time = st.goal.time_first < T;
+                        if (in_time) factor = 0.0001;
+                    }
+                    if (!in_time && st.goal.ego_in_goal && (gf & GF_OUTSIDE)) factor = 10.0;
+                }
+                switch (vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
+                    case 0: c[ETP_C_VELOCITY] = fabs(vel_target - mean_v); break;
                     case 1: c[ETP_C_VELOCITY] = 30.0 - mean_v; break;
                     case 2: c[ETP_C_VELOCITY] = mean_v; break;
                     default: c[ETP_C_VELOCITY] = 0.0;
@@ -1175,7 +1215,6 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 c[ETP_C_LON_JERK] = jl / (double)T;             // :418-435
                 c[ETP_C_LAT_JERK] = jq / (double)T;
                 c[ETP_C_TRAVELLED_DIST] = trav;
-                const double factor = st.factor_list ? st.factor_list[c_dense] : st.factor;
                 c[ETP_C_FACTOR] = factor;
                 // validity level (validity_checks.py:31-122)
                 const int cf = (first_fail == 0x7fffffff || first_fail < 0) ? 0 : (first_fail & 3);

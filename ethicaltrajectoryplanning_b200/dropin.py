@@ -78,7 +78,7 @@ class GivenResult:
 
 def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, params, mode="risk", ext_level=None,
                        bd_harm=None, velocity_cost_mode=3, velocity_target=0.0, cost_factor=1.0, want_harm=False,
-                       masses=None, protections=None, ctx=None) -> GivenResult:
+                       masses=None, protections=None, ctx=None, goal=None, dt=0.1) -> GivenResult:
     """Score caller-provided trajectories on the device (fused kernel, generation replaced by loads).
 
     Obstacle classes come from ``obstacle_types`` ({id: ObstacleType name}) or explicit ``masses`` / ``protections``."""
@@ -102,6 +102,12 @@ def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, param
         cf = np.ascontiguousarray(cost_factor, dtype=np.float64)
         g.cost_factor, g.cost_factor_list = 1.0, _dptr(cf)
         keep.append(cf)
+    if goal is not None:  # GoalContext: velocity cost and cost factor per trajectory on the device
+        from .scoring import make_goal
+
+        gs = make_goal(goal, keep)
+        g.goal, g.dt = C.pointer(gs), float(dt)
+        keep.append(gs)
     if ext_level is not None:
         e = np.ascontiguousarray(ext_level, dtype=np.uint8)
         g.ext_level = e.ctypes.data_as(C.POINTER(C.c_uint8))

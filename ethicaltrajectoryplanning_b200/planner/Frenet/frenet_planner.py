@@ -167,7 +167,7 @@ class FrenetPlanner:
         """Same selection without materialising per-candidate Python objects: one launch, 40-byte readback, then the
         winner's 13 rows in fp64."""
         fpar = self.frenet_parameters
-        from .utils.calc_trajectory_cost import cost_context
+        from .utils.calc_trajectory_cost import cost_context, goal_context
 
         vel_mode, vel_target, factor = cost_context(None, self.ego_state, self.planning_problem, self.scenario, fpar["dt"],
                                                     self.goal_area)
@@ -180,7 +180,8 @@ class FrenetPlanner:
             ego_position=np.asarray(self.ego_state.position, dtype=np.float64), ego_orientation=float(self.ego_state.orientation),
             vehicle=self.p, params=self.params_dict, mode=self.mode, velocity_cost_mode=vel_mode,
             velocity_target=vel_target, cost_factor=float(np.ndim(factor) == 0 and factor or 1.0),
-            predictions_resident=getattr(self, "_resident", False))
+            predictions_resident=getattr(self, "_resident", False),
+            goal=goal_context(self.ego_state, self.planning_problem, self.scenario, self.goal_area))
         self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------

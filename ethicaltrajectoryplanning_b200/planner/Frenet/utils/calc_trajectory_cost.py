@@ -4,6 +4,10 @@ The cost terms of the scored path (risk principles, velocity, distance to the gl
 distance) come from the fused kernel.  The goal logic behind ``get_cost_factor`` (:349-415) and the target of
 ``velocity_costs`` (:438-519) is CommonRoad / pycrcc geometry and stays on the host: ``cost_context`` evaluates the
 parts that need no geometry and takes the rest from the planning problem object when it provides them.
+
+With a goal area given as plain geometry (``GoalArea``: polygons / circles instead of a pycrcc ShapeGroup) the whole
+goal logic runs on the device: ``goal_context`` turns planning problem + goal area + ego state into the
+``GoalContext`` that crosses the ABI as ``etp_goal``.
 """
 from __future__ import annotations
 
@@ -11,6 +15,7 @@ import numpy as np
 
 from .... import _abi, dropin
 from ....configs import RISK_COSTS_KEY
+from ....synthetic import GoalContext
 
 COST = {name: i for i, name in enumerate(_abi.COST_NAMES)}
 
@@ -48,6 +53,65 @@ def cost_context(fp_list, ego_state, planning_problem, scenario, dt, goal_area):
     if remaining > 0.0:
         return 0, avg_dist / remaining, 1.0
     return 1, 0.0, 1.0
+
+
+class GoalArea:
+    """Goal area as plain geometry: the union of simple polygons ([n, 2] vertex arrays) and circles ((x, y, r)).
+    Stands where the reference holds a pycrcc ShapeGroup (helper_functions.py:226-271)."""
+
+    def __init__(self, polygons=(), circles=()):
+        self.polygons = [np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in polygons]
+        self.circles = [tuple(float(v) for v in c) for c in circles]
+
+
+def get_goal_area_shape_group(planning_problem, scenario):
+    """helper_functions.py:226-271 without pycrcc: lanelet polygons of ``goal.lanelets_of_goal_position`` or the goal
+    states' position shapes (anything with ``vertices``; rectangles by centre / length / width / orientation; circles
+    by centre / radius); ``None`` for a survival scenario."""
+    goal = planning_problem.goal
+    if getattr(goal, "lanelets_of_goal_position", None) is not None:
+        return GoalArea([scenario.lanelet_network.find_lanelet_by_id(i).convert_to_polygon().vertices
+                         for i in goal.lanelets_of_goal_position[0]])
+    if hasattr(goal.state_list[0], "position"):
+        polygons, circles = [], []
+        for state in goal.state_list:
+            shape = state.position
+            if hasattr(shape, "radius"):
+                circles.append((shape.center[0], shape.center[1], shape.radius))
+            elif hasattr(shape, "vertices"):
+                polygons.append(shape.vertices)
+            else:
+                c, s = np.cos(shape.orientation), np.sin(shape.orientation)
+                hl, hw = shape.length / 2.0, shape.width / 2.0
+                polygons.append([(shape.center[0] + a * hl * c - b * hw * s, shape.center[1] + a * hl * s + b * hw * c)
+                                 for a, b in ((1, 1), (-1, 1), (-1, -1), (1, -1))])
+        return GoalArea(polygons, circles)
+    return None
+
+
+def goal_context(ego_state, planning_problem, scenario, goal_area):
+    """``GoalContext`` of one planning step, or ``None`` when the goal logic cannot run on the device (no planning
+    problem, a pre-evaluated context, or a goal area that is not plain geometry)."""
+    if planning_problem is None or hasattr(planning_problem, "velocity_cost_mode") or not hasattr(planning_problem, "goal"):
+        return None
+    if goal_area is not None and not isinstance(goal_area, GoalArea):
+        return None
+    goal = planning_problem.goal
+    state0 = goal.state_list[0]
+    centers = None
+    if getattr(goal, "lanelets_of_goal_position", None) is not None:  # :473-484
+        centers = []
+        for lanelet_id in goal.lanelets_of_goal_position[0]:
+            lanelet = scenario.lanelet_network.find_lanelet_by_id(lanelet_id)
+            centers.append(lanelet.center_vertices[int(len(lanelet.center_vertices) / 2.0)])
+    elif hasattr(state0, "position"):                                  # :485-488
+        centers = [state0.position.center] if hasattr(state0.position, "center") else []
+    interval = lambda name: ((getattr(state0, name).start, getattr(state0, name).end) if hasattr(state0, name) else None)  # noqa: E731
+    return GoalContext(
+        polygons=None if goal_area is None else goal_area.polygons, circles=None if goal_area is None else goal_area.circles,
+        velocity=interval("velocity"), orientation=interval("orientation"), time_step=interval("time_step") or (0, -1),
+        ego_time_step=int(ego_state.time_step), ego_position=tuple(np.asarray(ego_state.position, dtype=np.float64)[:2]),
+        goal_centers=centers)
 
 
 def build_cost_dict(traj, c, params, validity_level, predictions):
@@ -88,7 +152,8 @@ def calc_trajectory_costs(traj, global_path, planning_problem, ego_state, validi
     bd = np.array([float(getattr(traj, "bd_harm", 0) or 0)])
     r = dropin.score_trajectories([traj], predictions, types, vehicle_params, params, mode=(mode or "risk"), bd_harm=bd,
                                   velocity_cost_mode=vel_mode, velocity_target=vel_target,
-                                  cost_factor=np.broadcast_to(factor, (1,)))
+                                  cost_factor=np.broadcast_to(factor, (1,)),
+                                  goal=goal_context(ego_state, planning_problem, scenario, goal_area), dt=dt)
     c = r.cost[:, 0].copy()
     own_risk_only = int(r.level[0]) < 10 and bool(params["modes"]["multiple_cost_functions"])
     want_risk_only = validity_level < 10 and bool(params["modes"]["multiple_cost_functions"])

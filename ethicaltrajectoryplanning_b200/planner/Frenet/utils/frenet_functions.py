@@ -10,7 +10,7 @@ import numpy as np
 
 from .... import _abi, dropin
 from ....synthetic import PlanningStep, get_v_list  # noqa: F401  (get_v_list re-exported like the reference)
-from .calc_trajectory_cost import build_cost_dict, cost_context
+from .calc_trajectory_cost import build_cost_dict, cost_context, goal_context
 from .validity_checks import VALIDITY_LEVELS, host_validity_inputs
 
 
@@ -111,6 +111,7 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
     ext_level, bd_harm = host_validity_inputs(fp_list, ego_state, scenario, vehicle_params, predictions, road_boundary,
                                               collision_checker, params)
     vel_mode, vel_target, factor = cost_context(fp_list, ego_state, planning_problem, scenario, dt, goal_area)
+    goal = goal_context(ego_state, planning_problem, scenario, goal_area)  # goal logic on the device when it can
     generated = (isinstance(fp_list, FrenetTrajectoryList) and fp_list.generation is not None
                  and fp_list.dense_index is not None and len(fp_list.dense_index) == n_list)
     ctx = dropin.default_context()
@@ -136,6 +137,7 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
         fl = np.ones(n_dense)
         fl[dense] = factor
         step.cost_factor_list = fl
+        step.goal = goal
         res = ctx.plan(step)
         out = res.numpy()
         red = out["red"][:, dense].astype(np.float64)
@@ -146,7 +148,8 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
     else:
         r = dropin.score_trajectories(list(fp_list), predictions, types, vehicle_params, params, mode=mode,
                                       ext_level=ext_level, bd_harm=bd_harm, velocity_cost_mode=vel_mode,
-                                      velocity_target=vel_target, cost_factor=np.broadcast_to(factor, (n_list,)), ctx=ctx)
+                                      velocity_target=vel_target, cost_factor=np.broadcast_to(factor, (n_list,)), ctx=ctx,
+                                      goal=goal, dt=dt)
         red, cost, level, reason, oids = r.red, r.cost, r.level, r.reason, r.obstacle_ids
 
     for i, fp in enumerate(fp_list):

@@ -113,6 +113,32 @@ def make_params(params, vehicle, mode="risk") -> _abi.Params:
     return p
 
 
+def make_goal(goal, keep):
+    """GoalContext -> etp_goal; the arrays it points to are appended to ``keep``."""
+    g = _abi.Goal()
+    polys = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 2) for p in (goal.polygons or [])]
+    circles = np.ascontiguousarray(goal.circles if goal.circles else np.zeros((0, 3)), dtype=np.float64).reshape(-1, 3)
+    g.has_area = int(goal.has_area)
+    g.n_polygons, g.n_circles = len(polys), len(circles)
+    start = np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(p) for p in polys])]), dtype=np.int32)
+    verts = np.ascontiguousarray(np.concatenate(polys) if polys else np.zeros((0, 2)), dtype=np.float64)
+    g.poly_start, g.vertices, g.circles = _iptr(start), _dptr(verts), _dptr(circles)
+    keep += [start, verts, circles]
+    if goal.velocity is not None:
+        g.has_velocity, g.velocity_start, g.velocity_end = 1, float(goal.velocity[0]), float(goal.velocity[1])
+    if goal.orientation is not None:
+        g.has_orientation, g.orientation_start, g.orientation_end = 1, float(goal.orientation[0]), float(goal.orientation[1])
+    g.time_start, g.time_end = int(goal.time_step[0]), int(goal.time_step[1])
+    g.ego_time_step = int(goal.ego_time_step)
+    g.ego_x, g.ego_y = float(goal.ego_position[0]), float(goal.ego_position[1])
+    if goal.goal_centers is not None and len(goal.goal_centers) > 0:
+        pos = np.asarray(goal.ego_position, dtype=np.float64)
+        # distance() of helper_functions.py:114 is the Euclidean norm; np.mean over the list (:492-497)
+        g.has_centers = 1
+        g.avg_goal_distance = float(np.mean([np.linalg.norm(np.asarray(c, dtype=np.float64) - pos) for c in goal.goal_centers]))
+    return g
+
+
 def pack_predictions(predictions, obstacle_types=None, masses=None, protections=None):
     """`predictions` dict (SURVEY.md 8b data contract 1) -> SoA host arrays, dict order kept.
 
@@ -407,6 +433,10 @@ class ScoringContext:
             fl = np.ascontiguousarray(step.cost_factor_list, dtype=np.float64)
             s.cost_factor_list = _dptr(fl)
             keep.append(fl)
+        if getattr(step, "goal", None) is not None:
+            g = make_goal(step.goal, keep)
+            s.goal = C.pointer(g)
+            keep.append(g)
         dense = len(v) * len(t) * len(d)
         s.c_begin = 0 if c_begin is None else int(c_begin)
         s.c_end = dense if c_end is None else int(c_end)

@@ -102,6 +102,30 @@ def assign_responsibility_by_action_space(ego_position, ego_orientation, predict
 
 
 @dataclasses.dataclass
+class GoalContext:
+    """What ``get_cost_factor`` (calc_trajectory_cost.py:349-415) and ``velocity_costs`` (:438-519) read from
+    ``planning_problem.goal``, ``goal_area`` and ``ego_state`` (etp_goal in include/etp_b200.h).
+
+    ``polygons``: vertex arrays [n, 2] of the goal area (``lanelet.convert_to_polygon().vertices`` or the goal states'
+    position shapes, helper_functions.py:226-271), ``circles``: (x, y, r); both ``None`` = ``goal_area is None``
+    (survival scenario).  Intervals are (start, end) or ``None`` when the goal state has no such attribute.
+    ``goal_centers``: the points velocity_costs measures the remaining distance to (:473-489), ``None`` if it finds none."""
+
+    polygons: Optional[list] = None
+    circles: Optional[list] = None
+    velocity: Optional[tuple] = None
+    orientation: Optional[tuple] = None
+    time_step: tuple = (0, 0)
+    ego_time_step: int = 0
+    ego_position: tuple = (0.0, 0.0)
+    goal_centers: Optional[list] = None
+
+    @property
+    def has_area(self):
+        return self.polygons is not None or self.circles is not None
+
+
+@dataclasses.dataclass
 class PlanningStep:
     """All inputs of one planning step of the scored path (SURVEY.md 8b data contracts)."""
 
@@ -132,6 +156,7 @@ class PlanningStep:
     bd_harm: Optional[np.ndarray] = None     # per dense candidate boundary harm
     cost_factor_list: Optional[np.ndarray] = None  # per dense candidate get_cost_factor result (overrides cost_factor)
     predictions_resident: bool = False  # the context already holds these predictions (ScoringContext.set_raw_predictions)
+    goal: Optional[GoalContext] = None  # velocity cost and cost factor derived per candidate on the device (overrides the scalars)
 
     @property
     def n_dense(self):

@@ -147,6 +147,37 @@ typedef struct {
 } etp_obstacles;
 
 /*
+ * Goal context of one planning step: what get_cost_factor (calc_trajectory_cost.py:349-415) and
+ * velocity_costs (:438-519) read from planning_problem.goal, goal_area and ego_state.  With a goal attached to a step
+ * the device derives, per candidate, the velocity cost and the cost factor; velocity_cost_mode / velocity_target /
+ * cost_factor / cost_factor_list of the step are then ignored.
+ *   goal area  : union of simple polygons (lanelet.convert_to_polygon() / goal_state.position of
+ *                helper_functions.py:226-271) and circles; has_area = 0 stands for goal_area None (survival scenario:
+ *                every position counts as inside, calc_trajectory_cost.py:585-586).  Containment is the even-odd rule
+ *                in fp64; pycrcc's treatment of points exactly on an edge is not reproduced.
+ *   velocity / orientation : goal.state_list[0].velocity / .orientation intervals if present (open intervals,
+ *                helper_functions.py:408-421; the orientation test is check_orientation, :881-932).
+ *   time_step  : goal.state_list[0].time_step interval (the reference requires it once a goal state is reached).
+ */
+typedef struct {
+    int32_t has_area;
+    int32_t n_polygons;
+    const int32_t* poly_start;      /* [n_polygons + 1] first vertex of each polygon */
+    const double* vertices;         /* [poly_start[n_polygons]][2] */
+    int32_t n_circles;
+    const double* circles;          /* [n_circles][3] x, y, radius */
+    int32_t has_velocity;
+    double velocity_start, velocity_end;
+    int32_t has_orientation;
+    double orientation_start, orientation_end;
+    int32_t time_start, time_end;
+    int32_t ego_time_step;          /* ego_state.time_step */
+    double ego_x, ego_y;            /* ego_state.position */
+    int32_t has_centers;            /* velocity_costs found goal centre points (:473-489); 0: cost 0 outside the goal */
+    double avg_goal_distance;       /* mean distance from ego_state.position to them (:492-497) */
+} etp_goal;
+
+/*
  * Arguments of calc_frenet_trajectories (frenet_functions.py:207-221) plus the host-only
  * cost context of sort_frenet_trajectories the GPU cannot derive (last row).
  */
@@ -168,6 +199,7 @@ typedef struct {
     int32_t c_begin, c_end;         /* dense candidate range of this call; must be aligned to whole (v,t) profiles */
     int32_t shard_index, shard_count; /* multi-GPU: score only the profiles p with (p - p_begin) % shard_count == shard_index
                                        (interleaved, so slow and fast profiles spread evenly); shard_count 0 or 1 = all */
+    const etp_goal* goal;           /* optional: velocity cost and cost factor per candidate on the device */
 } etp_step;
 
 /* Caller-allocated device tensors for the scored candidates.  Cs = (number of profiles of this shard) * nd;
@@ -205,6 +237,8 @@ typedef struct {
     const uint8_t* ext_level;       /* optional [C] */
     const double* bd_harm;          /* optional [C] */
     const double* cost_factor_list; /* optional [C], overrides cost_factor */
+    const etp_goal* goal;           /* optional, like etp_step.goal; sample i of a trajectory is taken at time i * dt */
+    double dt;                      /* scenario time step, only read with a goal */
 } etp_trajectories;
 
 /* Selected candidate: sort by (highest non-empty level, cost, generation order)

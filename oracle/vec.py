@@ -15,6 +15,7 @@ import numpy as np
 
 from . import boxes as _boxes
 from . import bvn as _bvn
+from . import goal as _goal
 from . import port as _port
 
 LEVEL_SKIPPED = 255
@@ -300,6 +301,8 @@ def score_dense(step, profiles=None):
         cst[9] = np.power(d_ddd, 2).sum(axis=1) / T
         cst[10] = np.sqrt(np.diff(x, axis=1) ** 2 + np.diff(y, axis=1) ** 2).sum(axis=1)
         cst[11] = step.cost_factor
+        if getattr(step, "goal", None) is not None:  # oracle/goal.py (calc_trajectory_cost.py:349-415, 438-519)
+            cst[11], cst[6] = _goal.factor_and_velocity_cost(step.goal, x, y, v, yaw, t, step.dt)
         risk_only = (level < 10) & bool(modes["multiple_cost_functions"])
         total = np.zeros(n)
         if risk_in_cost:
@@ -307,7 +310,7 @@ def score_dense(step, profiles=None):
         for row, key in ((8, "lon_jerk"), (9, "lat_jerk"), (6, "velocity"), (7, "dist_to_global_path"), (10, "travelled_dist")):
             if weights[key] > 0.0:
                 total += np.where(risk_only, 0.0, weights[key]) * cst[row]
-        cst[12] = step.cost_factor * total
+        cst[12] = cst[11] * total
         out["cost"][:, gl] = cst
     # ---- selection: highest non-empty level, then cost, then generation order ---------------------------
     valid = out["level"] != LEVEL_SKIPPED

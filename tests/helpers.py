@@ -51,3 +51,50 @@ def rel_err(a, b, floor=0.0):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / (np.abs(b) + floor)
+
+
+def goal_cases():
+    """Planning steps with a goal context: (name, PlanningStep).  The expected cost factors and
+    velocity costs of tests/golden/goal_cases.npz were written for exactly these steps by the reference's own
+    get_cost_factor / velocity_costs (tests/golden/make_golden_goal.py)."""
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext, make_step
+
+    box = lambda x0, x1, y0, y1: [(x0, y0), (x1, y0), (x1, y1), (x0, y1)]  # noqa: E731
+    ahead = box(24.0, 60.0, 0.5, 4.2)                    # on the path ahead: fast, well-placed candidates get in
+    here = box(0.0, 17.0, -3.0, 4.0)                     # around the ego: most candidates leave it again
+    lshape = [(20.0, -1.0), (60.0, -1.0), (60.0, 6.0), (40.0, 6.0), (40.0, 2.0), (20.0, 2.0)]  # concave
+    specs = [
+        ("reached_in_time", dict(), dict(polygons=[ahead], velocity=(5.0, 30.0), orientation=(-0.5, 0.5), time_step=(10, 60),
+                                         ego_time_step=0, goal_centers=[(42.0, 2.3)])),
+        ("reached_too_early", dict(), dict(polygons=[ahead], velocity=(5.0, 30.0), time_step=(40, 90), ego_time_step=3,
+                                           goal_centers=[(42.0, 2.3)])),
+        ("velocity_window_narrow", dict(), dict(polygons=[ahead], velocity=(13.0, 16.0), orientation=(-0.3, 0.12),
+                                                time_step=(0, 25), ego_time_step=2, goal_centers=[(42.0, 2.3), (50.0, 3.0)])),
+        ("starts_inside_and_leaves", dict(), dict(polygons=[here], velocity=(0.0, 9.0), time_step=(100, 200), ego_time_step=50,
+                                                  goal_centers=[(8.0, 0.5)])),
+        ("starts_inside_no_velocity", dict(v0=6.0), dict(polygons=[here], time_step=(100, 200), ego_time_step=120,
+                                                         goal_centers=[(8.0, 0.5)])),
+        ("survival", dict(), dict(polygons=None, circles=None, time_step=(0, 300), ego_time_step=7, goal_centers=None)),
+        ("orientation_folded", dict(), dict(polygons=[ahead], orientation=(3.0, 6.5), time_step=(0, 80), ego_time_step=0,
+                                            goal_centers=[(42.0, 2.3)])),
+        ("orientation_both_folded", dict(), dict(polygons=[ahead], orientation=(6.0, 6.6), time_step=(0, 80), ego_time_step=0,
+                                                 goal_centers=[(42.0, 2.3)])),
+        ("circle_and_concave", dict(v0=20.0), dict(polygons=[lshape], circles=[(30.0, 4.5, 2.0)], velocity=(2.0, 40.0),
+                                                   time_step=(5, 12), ego_time_step=0, goal_centers=[(45.0, 3.0)])),
+        ("time_is_up", dict(), dict(polygons=[ahead], velocity=(5.0, 30.0), time_step=(0, 20), ego_time_step=20,
+                                    goal_centers=[(42.0, 2.3)])),
+        ("no_centres", dict(), dict(polygons=[ahead], time_step=(0, 20), ego_time_step=0, goal_centers=None)),
+        # int(ego_time + t / dt): sample 43 is time step 42 (4.3 / 0.1 = 42.99...), no sample is at 43 -> never "in time"
+        ("time_step_43_never", dict(t_list=(5.0,)), dict(polygons=[box(24.0, 130.0, -2.0, 9.0)], time_step=(43, 43), ego_time_step=0,
+                                                         goal_centers=[(42.0, 2.3)])),
+        ("time_step_42_twice", dict(t_list=(5.0,)), dict(polygons=[box(24.0, 130.0, -2.0, 9.0)], time_step=(42, 42), ego_time_step=0,
+                                                         goal_centers=[(42.0, 2.3)])),
+        ("two_t", dict(t_list=(2.0, 3.0)), dict(polygons=[ahead], velocity=(5.0, 30.0), time_step=(24, 60), ego_time_step=0,
+                                                goal_centers=[(42.0, 2.3)])),
+    ]
+    out = []
+    for name, kw, g in specs:
+        step = make_step("planning", seed=77, n_obstacles=4, nv=9, nd=11, **kw)
+        step.goal = GoalContext(ego_position=tuple(step.ego_position), **g)
+        out.append((name, step))
+    return out

@@ -23,7 +23,10 @@ KEYS = [
     "smsp__warp_issue_stalled_membar_per_warp_active.pct", "smsp__warp_issue_stalled_drain_per_warp_active.pct",
     "smsp__warp_issue_stalled_imc_miss_per_warp_active.pct", "smsp__warp_issue_stalled_sleeping_per_warp_active.pct",
     "smsp__warp_issue_stalled_tex_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_misc_per_warp_active.pct",
-]
+    "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+] + ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % r for r in (
+    "wait", "not_selected", "long_scoreboard", "math_pipe_throttle", "barrier", "short_scoreboard", "no_instruction",
+    "branch_resolving", "mio_throttle", "dispatch_stall", "lg_throttle")]
 
 
 def main(path):
