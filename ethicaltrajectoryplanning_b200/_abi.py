@@ -80,6 +80,10 @@ class RawPredictions(C.Structure):
     ]
 
 
+class RoadBoundary(C.Structure):
+    _fields_ = [("n_triangles", C.c_int32), ("triangles", _dp), ("check", C.c_int32)]
+
+
 class Goal(C.Structure):
     _fields_ = [
         ("has_area", C.c_int32), ("n_polygons", C.c_int32),
@@ -158,6 +162,7 @@ SYMBOLS = {
     "etp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "etp_set_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
     "etp_set_spline": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int]),
+    "etp_set_road_boundary": (C.c_int, [C.c_void_p, C.POINTER(RoadBoundary)]),
     "etp_set_obstacles": (C.c_int, [C.c_void_p, C.POINTER(Obstacles), C.c_int]),
     "etp_set_raw_predictions": (C.c_int, [C.c_void_p, C.POINTER(RawPredictions), C.c_int]),
     "etp_get_enriched": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _ip]),

@@ -76,6 +76,8 @@ struct etp_ctx {
     std::vector<double> spline_pts, obs_box;  // knot positions (+ reach) and the bounding box of the predictions
     // step
     DevBuf grids, ext_level, bd_harm, factor_list, goal_geom, prof, prof_meta, nskip;
+    DevBuf rb_tri, rb_trif, rb_start, rb_items;  // etp_set_road_boundary
+    DevBoundary boundary{};
     DevBuf block_best, counters, best_dev, traj_dev, traj_n, given, given_T, prin;
     bool last_given = false;
     PinnedBuf stage, best_host, traj_host;
@@ -173,7 +175,7 @@ int etp_destroy(etp_ctx* c) {
     c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
-                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom,
+                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom, &c->rb_tri, &c->rb_trif, &c->rb_start, &c->rb_items,
                       &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
                       &c->traj_n, &c->given, &c->given_T, &c->prin};
     for (DevBuf* b : bufs) b->release();
@@ -269,6 +271,94 @@ int etp_set_spline(etp_ctx* c, const double* knots, const double* coef_x, const 
     }
     c->have_spline = true;
     return end_staging(c);
+}
+
+int etp_set_road_boundary(etp_ctx* c, const etp_road_boundary* b) {
+    if (!c || !b) return ETP_ERR_INVALID;
+    if (b->check < ETP_COLLISION_HOST || b->check > ETP_COLLISION_SWEPT) ETP_FAIL(c, ETP_ERR_INVALID, "road boundary check mode");
+    if (b->n_triangles < 0 || (b->n_triangles > 0 && !b->triangles)) ETP_FAIL(c, ETP_ERR_INVALID, "road boundary triangles missing");
+    c->boundary = DevBoundary{};
+    if (b->n_triangles == 0 || b->check == ETP_COLLISION_HOST) return ETP_OK;
+    const int n = b->n_triangles;
+    const double* T = b->triangles;
+    double lo[2] = {T[0], T[1]}, hi[2] = {T[0], T[1]};
+    for (int i = 0; i < 3 * n; ++i)
+        for (int a = 0; a < 2; ++a) {
+            if (!std::isfinite(T[2 * i + a])) ETP_FAIL(c, ETP_ERR_INVALID, "road boundary vertex %d is not finite", i);
+            lo[a] = std::fmin(lo[a], T[2 * i + a]);
+            hi[a] = std::fmax(hi[a], T[2 * i + a]);
+        }
+    // uniform grid: cells of at least 4 m, at most 512 x 512 of them
+    double cell = std::fmax(4.0, std::fmax(hi[0] - lo[0], hi[1] - lo[1]) / 512.0);
+    const int nx = (int)std::floor((hi[0] - lo[0]) / cell) + 1, ny = (int)std::floor((hi[1] - lo[1]) / cell) + 1;
+    auto cell_of = [&](double v, int a) {
+        const int k = (int)std::floor((v - lo[a]) / cell);
+        const int m = a == 0 ? nx : ny;
+        return k < 0 ? 0 : (k >= m ? m - 1 : k);
+    };
+    // two passes over the triangles' bounding boxes: count per cell, then fill (CSR layout)
+    std::vector<int> start((size_t)nx * ny + 1, 0), items, fill;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            int run = 0;
+            for (size_t k = 0; k < start.size(); ++k) {
+                const int v = start[k];
+                start[k] = run;
+                run += v;
+            }
+            items.assign(run > 0 ? run : 1, 0);
+            fill.assign(start.begin(), start.end());
+        }
+        for (int i = 0; i < n; ++i) {
+            const double* q = T + 6 * (size_t)i;
+            const int ix0 = cell_of(std::fmin(q[0], std::fmin(q[2], q[4])), 0), ix1 = cell_of(std::fmax(q[0], std::fmax(q[2], q[4])), 0);
+            const int iy0 = cell_of(std::fmin(q[1], std::fmin(q[3], q[5])), 1), iy1 = cell_of(std::fmax(q[1], std::fmax(q[3], q[5])), 1);
+            for (int iy = iy0; iy <= iy1; ++iy)
+                for (int ix = ix0; ix <= ix1; ++ix) {
+                    // the triangle's bounding box reaches this cell; keep it only if no edge normal separates the two
+                    // (cell grown by a millimetre so that rounding can only add entries)
+                    const double cx = lo[0] + (ix + 0.5) * cell, cy = lo[1] + (iy + 0.5) * cell, h = 0.5 * cell + 1e-3;
+                    bool apart = false;
+                    for (int k = 0; k < 3 && !apart; ++k) {
+                        const int j = (k + 1) % 3, m = (k + 2) % 3;
+                        const double ex = -(q[2 * j + 1] - q[2 * k + 1]), ey = q[2 * j] - q[2 * k];  // edge normal
+                        const double a = ex * (q[2 * k] - cx) + ey * (q[2 * k + 1] - cy), bb = ex * (q[2 * m] - cx) + ey * (q[2 * m + 1] - cy);
+                        const double r = h * (std::fabs(ex) + std::fabs(ey));
+                        apart = std::fmin(a, bb) > r || std::fmax(a, bb) < -r;
+                    }
+                    if (apart) continue;
+                    if (pass == 0) ++start[(size_t)iy * nx + ix];
+                    else items[fill[(size_t)iy * nx + ix]++] = i;
+                }
+        }
+    }
+    {
+        ETP_CUDA(c, cudaSetDevice(c->device));
+        int r = begin_staging(c);
+        if (r) return r;
+        ETP_CUDA(c, c->rb_tri.reserve(sizeof(double) * 6 * (size_t)n));
+        ETP_CUDA(c, c->rb_trif.reserve(sizeof(float) * 6 * (size_t)n));
+        std::vector<float> tf(6 * (size_t)n);
+        for (size_t i = 0; i < tf.size(); ++i) tf[i] = (float)(T[i] - lo[i & 1]);
+        if ((r = stage_to_device(c, c->rb_trif.p, tf.data(), sizeof(float) * tf.size()))) return r;
+        ETP_CUDA(c, c->rb_start.reserve(sizeof(int) * start.size()));
+        ETP_CUDA(c, c->rb_items.reserve(sizeof(int) * items.size()));
+        if ((r = stage_to_device(c, c->rb_tri.p, T, sizeof(double) * 6 * (size_t)n))) return r;
+        if ((r = stage_to_device(c, c->rb_start.p, start.data(), sizeof(int) * start.size()))) return r;
+        if ((r = stage_to_device(c, c->rb_items.p, items.data(), sizeof(int) * items.size()))) return r;
+        if ((r = end_staging(c))) return r;
+    }
+    DevBoundary& d = c->boundary;
+    d.check = b->check;
+    d.n_tri = n; d.nx = nx; d.ny = ny;
+    d.x0 = lo[0]; d.y0 = lo[1]; d.inv_cell = 1.0 / cell;
+    d.tri = c->rb_tri.as<double>();
+    d.trif = c->rb_trif.as<float>();
+    // fp32 pass: vertices and box centres are rounded to fp32 relative to the grid origin (half an ulp each)
+    d.tol_f = (float)(2e-4 + 4.0 * 1.2e-7 * (std::fmax(hi[0] - lo[0], hi[1] - lo[1]) + 16.0));
+    d.cell_start = c->rb_start.as<int>();
+    d.cell_items = c->rb_items.as<int>();
+    return ETP_OK;
 }
 
 int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
@@ -625,6 +715,9 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     st.prof = c->prof.as<double>();
     st.prof_meta = c->prof_meta.as<double>();
     st.has_pred = c->has_pred; st.O = c->O; st.Tp = c->Tp;
+    st.boundary = c->boundary;
+    st.boundary.lr1s_const = c->pr.lr1s_const; st.boundary.lr1s_speed = c->pr.lr1s_speed;
+    st.boundary.off_x = st.origin_x - st.boundary.x0; st.boundary.off_y = st.origin_y - st.boundary.y0;
     st.obs = c->o_tile.p; st.obs_const = c->o_const.as<double>(); st.pred_len = c->o_plen.as<int>();
     st.raw_pos = c->o_pos.as<double>(); st.raw_yaw = c->o_yaw.as<double>();
 
@@ -714,6 +807,9 @@ int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out*
         st.origin_y = c->origin_y;
     }
     st.has_pred = c->has_pred; st.O = c->O; st.Tp = c->Tp;
+    st.boundary = c->boundary;
+    st.boundary.lr1s_const = c->pr.lr1s_const; st.boundary.lr1s_speed = c->pr.lr1s_speed;
+    st.boundary.off_x = st.origin_x - st.boundary.x0; st.boundary.off_y = st.origin_y - st.boundary.y0;
     st.obs = c->o_tile.p; st.obs_const = c->o_const.as<double>(); st.pred_len = c->o_plen.as<int>();
     st.raw_pos = c->o_pos.as<double>(); st.raw_yaw = c->o_yaw.as<double>();
     DevOut dout{};

@@ -110,6 +110,20 @@ __host__ __device__ inline bool point_in_goal(const DevGoal& g, const int* poly_
     return false;
 }
 
+// road boundary (etp_set_road_boundary): triangles in a uniform grid, fp64
+struct DevBoundary {
+    int check;                // ETP_COLLISION_*; HOST: nothing to test
+    int n_tri, nx, ny;
+    double x0, y0, inv_cell;  // cell (ix, iy) covers [x0 + ix / inv_cell, ...)
+    const double* tri;        // [n_tri][6]
+    const float* trif;        // [n_tri][6] relative to (x0, y0), fp32 (first pass of the fp32 kernels)
+    double off_x, off_y;      // step origin - (x0, y0)
+    float tol_f;              // |margin| below which the fp32 pass defers to fp64 [m]
+    const int* cell_start;    // [nx * ny + 1]
+    const int* cell_items;    // triangle indices per cell
+    double lr1s_const, lr1s_speed;
+};
+
 struct DevStep {
     double c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd, dt, v_thr;
     const double* v_list;
@@ -127,6 +141,7 @@ struct DevStep {
     const double* bd_harm;     // device copy, indexed by dense candidate, or null
     const double* factor_list; // device copy, indexed by dense candidate, or null (then `factor`)
     DevGoal goal;              // goal.on: velocity cost and factor derived per candidate instead
+    DevBoundary boundary;      // boundary.check != HOST: level 2 / boundary harm derived per candidate instead of bd_harm
     // spline tables
     const double* knots;
     const double* cx;

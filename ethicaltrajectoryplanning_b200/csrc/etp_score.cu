@@ -752,6 +752,150 @@ __device__ __forceinline__ void phase2a_dispatch(const Phase2a<R>& a, int g, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// road boundary (etp_set_road_boundary): ego boxes against the triangles outside the road, fp64
+// ---------------------------------------------------------------------------------------------
+// Largest separating-axis margin of a box and a triangle over the two box axes and the three edge normals.
+__device__ __forceinline__ double sat_margin_triangle(const Box<double>& e, const double* q) {
+    double ux[3], uy[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double dx = q[2 * k] - e.x, dy = q[2 * k + 1] - e.y;
+        ux[k] = dx * e.c + dy * e.s;  // vertex in the box frame
+        uy[k] = dy * e.c - dx * e.s;
+    }
+    double m = fmax(fmax(fmin(ux[0], fmin(ux[1], ux[2])) - e.l, -fmax(ux[0], fmax(ux[1], ux[2])) - e.l),
+                    fmax(fmin(uy[0], fmin(uy[1], uy[2])) - e.w, -fmax(uy[0], fmax(uy[1], uy[2])) - e.w));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int j = (k + 1) % 3, i = (k + 2) % 3;
+        double nx = -(uy[j] - uy[k]), ny = ux[j] - ux[k];  // normal of edge k -> j, in the box frame
+        const double len = sqrt(nx * nx + ny * ny);
+        if (!(len > 0.0)) continue;                        // degenerate edge
+        nx /= len; ny /= len;
+        const double a = nx * ux[k] + ny * uy[k];          // the edge's own offset; the third vertex lies on one side
+        const double b = nx * ux[i] + ny * uy[i];
+        const double r = e.l * fabs(nx) + e.w * fabs(ny);  // box radius along the normal (box centred at the origin)
+        m = fmax(m, fmax(fmin(a, b) - r, -fmax(a, b) - r));
+    }
+    return m;
+}
+
+// fp32 form on coordinates relative to the grid origin, normals left un-normalised (no sqrt, no division): `hit` if no
+// axis separates; `*sure` cleared when no axis separates by more than tol while one comes within tol of doing so
+__device__ __forceinline__ bool triangle_hit_f(float cx, float cy, float c, float s, float l, float w, const float* q, float tol,
+                                               bool* sure) {
+    float ux[3], uy[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float dx = __ldg(q + 2 * k) - cx, dy = __ldg(q + 2 * k + 1) - cy;
+        ux[k] = dx * c + dy * s;
+        uy[k] = dy * c - dx * s;
+    }
+    const float m0 = fmaxf(fminf(ux[0], fminf(ux[1], ux[2])) - l, -fmaxf(ux[0], fmaxf(ux[1], ux[2])) - l);
+    const float m1 = fmaxf(fminf(uy[0], fminf(uy[1], uy[2])) - w, -fmaxf(uy[0], fmaxf(uy[1], uy[2])) - w);
+    bool sep = m0 > 0.0f || m1 > 0.0f, clear = m0 > tol || m1 > tol, maybe = m0 > -tol || m1 > -tol;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int j = (k + 1) % 3, i = (k + 2) % 3;
+        const float nx = -(uy[j] - uy[k]), ny = ux[j] - ux[k];
+        const float a = nx * ux[k] + ny * uy[k], b = nx * ux[i] + ny * uy[i];
+        const float an = fabsf(nx) + fabsf(ny);  // >= |n|: a conservative scale for the tolerance
+        const float m = fmaxf(fminf(a, b), -fmaxf(a, b)) - (l * fabsf(nx) + w * fabsf(ny));
+        sep = sep || m > 0.0f;
+        clear = clear || m > tol * an;
+        maybe = maybe || m > -tol * an;
+    }
+    if (!clear && maybe) *sure = false;
+    return !sep;
+}
+
+// Does the box touch a triangle of the boundary?  kExact: fp64 on the absolute coordinates (check mode, and the
+// re-decision of the fp32 kernels); else fp32 first pass, `*sure` cleared when it cannot decide.
+template <bool kExact>
+__device__ __forceinline__ bool boundary_hit(const DevBoundary& b, const Box<double>& e, bool* sure) {
+    const double rx = e.l * fabs(e.c) + e.w * fabs(e.s), ry = e.l * fabs(e.s) + e.w * fabs(e.c);
+    const double gx = e.x - b.x0, gy = e.y - b.y0;
+    const double fx0 = floor((gx - rx) * b.inv_cell), fx1 = floor((gx + rx) * b.inv_cell);
+    const double fy0 = floor((gy - ry) * b.inv_cell), fy1 = floor((gy + ry) * b.inv_cell);
+    if (fx1 < 0.0 || fy1 < 0.0 || fx0 >= (double)b.nx || fy0 >= (double)b.ny) return false;
+    const int ix0 = fx0 < 0.0 ? 0 : (int)fx0, ix1 = fx1 >= (double)b.nx ? b.nx - 1 : (int)fx1;
+    const int iy0 = fy0 < 0.0 ? 0 : (int)fy0, iy1 = fy1 >= (double)b.ny ? b.ny - 1 : (int)fy1;
+    const float cx = (float)gx, cy = (float)gy, c = (float)e.c, s = (float)e.s, l = (float)e.l, w = (float)e.w;
+    const float ax = (float)rx + b.tol_f, ay = (float)ry + b.tol_f;
+    bool hit = false;
+    for (int iy = iy0; iy <= iy1; ++iy)
+        for (int ix = ix0; ix <= ix1; ++ix) {
+            const int c0 = __ldg(b.cell_start + iy * b.nx + ix), c1 = __ldg(b.cell_start + iy * b.nx + ix + 1);
+            for (int k = c0; k < c1; ++k) {
+                const int ti = __ldg(b.cell_items + k);
+                if (kExact) {
+                    hit = hit || !(sat_margin_triangle(e, b.tri + 6 * (size_t)ti) > 0.0);
+                } else {
+                    const float* q = b.trif + 6 * (size_t)ti;
+                    // bounding boxes first: most triangles of a cell are nowhere near the box
+                    const float x0 = __ldg(q), x1 = __ldg(q + 2), x2 = __ldg(q + 4), y0 = __ldg(q + 1), y1 = __ldg(q + 3), y2 = __ldg(q + 5);
+                    if (fminf(x0, fminf(x1, x2)) > cx + ax || fmaxf(x0, fmaxf(x1, x2)) < cx - ax ||
+                        fminf(y0, fminf(y1, y2)) > cy + ay || fmaxf(y0, fmaxf(y1, y2)) < cy - ay)
+                        continue;
+                    hit = triangle_hit_f(cx, cy, c, s, l, w, q, b.tol_f, sure) || hit;
+                }
+            }
+        }
+    return hit;
+}
+
+// Road-boundary pass of one warp (lanes = candidates): first ego box i = warp, warp + 8, ... that touches the boundary.
+// Box i of the collision object (create_collision_object, validity_checks.py:125-141) is sample i, or the hull of
+// samples i and i + 1 in swept mode.  Poses come from the shared-memory ego samples; a box the fp32 pass cannot decide
+// is rebuilt from the exact samples and tested in fp64.
+template <typename R>
+__device__ __noinline__ int boundary_pass(const DevStep* stp, const DevParams* prp, const Vec4<R>* e0, const __half2* el, int Ts, int Tl,
+                                          int lane, int warp, bool given, int pl, int id) {
+    const DevStep& st = *stp;
+    const DevBoundary& b = st.boundary;
+    const bool swept = b.check == ETP_COLLISION_SWEPT;
+    const int n_box = swept ? Tl - 1 : Tl;
+    const double hl = prp->veh_l * 0.5, hw = prp->veh_w * 0.5;
+    int first = 0x7fffffff;
+    for (int i = warp; i < n_box && i < first; i += kWarps) {
+        const Vec4<R> a = e0[i * 32 + lane];
+        const float2 lo = __half22float2(el[i * 32 + lane]);
+        Box<double> e{st.origin_x + (double)a.x + (double)lo.x * (1.0 / kLoScale), st.origin_y + (double)a.y + (double)lo.y * (1.0 / kLoScale),
+                      (double)a.z, (double)a.w, hl, hw};
+        if (swept) {
+            const Vec4<R> n = e0[(i + 1) * 32 + lane];
+            const float2 ln = __half22float2(el[(i + 1) * 32 + lane]);
+            e = hull_box(e, Box<double>{st.origin_x + (double)n.x + (double)ln.x * (1.0 / kLoScale),
+                                        st.origin_y + (double)n.y + (double)ln.y * (1.0 / kLoScale), (double)n.z, (double)n.w, hl, hw});
+        }
+        bool sure = true, hit;
+        if (sizeof(R) == 8) {
+            hit = boundary_hit<true>(b, e, &sure);
+        } else {
+            hit = boundary_hit<false>(b, e, &sure);
+            if (!sure) {
+                e = ego_box_exact(st, *prp, given, pl, id, i);
+                if (swept) e = hull_box(e, ego_box_exact(st, *prp, given, pl, id, i + 1));
+                hit = boundary_hit<true>(b, e, &sure);
+            }
+        }
+        if (hit) first = i;
+    }
+    return first;
+}
+
+// traj.v[i] of the first box that left the road (risk_costs.py:114-116), regenerated in fp64
+__device__ __noinline__ double leave_velocity(const DevStep* stp, bool given, int pl, int id, int col, int i) {
+    const DevStep& st = *stp;
+    if (given) return st.given[((size_t)ETP_F_V * st.Tmax + i) * st.given_stride + col];
+    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+    const bool low = pm[PM_LOW] != 0.0;
+    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+    return traj_point(q, low, gp, st.Tmax, i, st.dt).f[ETP_F_V];
+}
+
 // Goal bookkeeping of one trajectory sample (calc_trajectory_cost.py:553-571 reached_goal_state, :520-550
 // goal_position_reached_and_left_again, :452 velocity_costs): bit 0 = goal state reached at this sample (position,
 // velocity and orientation), bit 1 = sample outside the goal area, bit 2 = sample 0 inside the goal area.
@@ -801,6 +945,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     __shared__ int s_nprot;
     __shared__ int s_hit[32];  // lane's candidate collides with a predicted box (pr.collision_check)
     __shared__ int s_goal[32]; // GF_* flags of the lane's candidate (st.goal.on)
+    __shared__ int s_leave[32]; // first ego box of the lane's candidate that touches the road boundary (st.boundary.check)
     int* s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);  // [On] obstacles sorted by class
     if (tid == 0) {
         fill_tab<R>(tab, pr, st.eps_pos);
@@ -838,6 +983,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         if (tid < 32) {
             s_hit[tid] = 0;
             s_goal[tid] = 0;
+            s_leave[tid] = 0x7fffffff;
         }
         for (int i = tid; i < MX_COUNT * On * 32; i += kThreads) sm.mx[i] = Enc<R>::enc((R)-INFINITY);
         __syncthreads();  // (a) tile index visible; previous tile fully consumed
@@ -1109,6 +1255,11 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 if (hit) s_hit[lane] = 1;
             }
         }
+        // ---- road boundary (optional, etp_set_road_boundary): first ego box that touches it ---------------------
+        if (st.boundary.check != ETP_COLLISION_HOST) {
+            const int first = boundary_pass<R>(&st, &pr, sm.e0, sm.el, Ts, Tl, lane, warp, kGiven, pl, id);
+            if (first != 0x7fffffff) atomicMin(&s_leave[lane], first);
+        }
         __syncthreads();  // (c) maxima complete, ego samples dead
 
         // ---- phase 3a: per-obstacle reductions, warps over obstacles ----------------------------------
@@ -1168,8 +1319,21 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     first_fail = min(first_fail, sm.ff[w * 32 + lane]);
                 }
                 const bool vel_ok = kGiven ? first_fail >= 0 : pm[PM_VEL_OK] != 0.0;
-                const double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
-                const int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
+                double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
+                int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
+                if (st.boundary.check != ETP_COLLISION_HOST) {
+                    // risk_costs.py:104-123: harm of leaving the road at the speed of the first colliding box; without
+                    // predictions calc_risk does not run and boundary_valid alone decides (validity_checks.py:108-112)
+                    const int leave = s_leave[lane];
+                    bd = 0.0;
+                    if (leave != 0x7fffffff) {
+                        const double vl = leave_velocity(&st, kGiven, pl, id, clc, leave);
+                        bd = 1.0 / (1.0 + exp(-st.boundary.lr1s_const - st.boundary.lr1s_speed * vl));
+                        if (ext != 1) ext = 2;
+                    } else if (ext == 2) {
+                        ext = 10;
+                    }
+                }
                 if (O > 0) {
                     c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
                     c[ETP_C_EQUALITY] = sum_abs / (double)O;                  // :176-178

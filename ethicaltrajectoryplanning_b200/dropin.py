@@ -78,7 +78,7 @@ class GivenResult:
 
 def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, params, mode="risk", ext_level=None,
                        bd_harm=None, velocity_cost_mode=3, velocity_target=0.0, cost_factor=1.0, want_harm=False,
-                       masses=None, protections=None, ctx=None, goal=None, dt=0.1) -> GivenResult:
+                       masses=None, protections=None, ctx=None, goal=None, dt=0.1, road_boundary=None) -> GivenResult:
     """Score caller-provided trajectories on the device (fused kernel, generation replaced by loads).
 
     Obstacle classes come from ``obstacle_types`` ({id: ObstacleType name}) or explicit ``masses`` / ``protections``."""
@@ -86,6 +86,12 @@ def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, param
     torch = ctx.torch
     ctx.set_params(params, vehicle_params, mode)
     ctx.set_predictions(predictions, obstacle_types, masses, protections)
+    # (triangles, check): boundary test on the device.  A shared default context does not keep a boundary between calls;
+    # a context the caller owns keeps what the caller set.
+    if road_boundary is not None or (getattr(ctx, "_boundary_key", None) is not None and any(ctx is c for c in _CTX.values())):
+        bkey = None if road_boundary is None else (id(road_boundary[0]), len(road_boundary[0]), road_boundary[1])
+        if getattr(ctx, "_boundary_key", None) != bkey:
+            ctx.set_road_boundary(*(road_boundary if road_boundary is not None else (None,)))
     f, n = trajectory_fields(trajs)
     Cn, Tm, O = len(trajs), f.shape[1], ctx.O
     bufs = ctx.allocate_outputs(Cn, Tm, O)

@@ -168,6 +168,7 @@ class FrenetPlanner:
         winner's 13 rows in fp64."""
         fpar = self.frenet_parameters
         from .utils.calc_trajectory_cost import cost_context, goal_context
+        from .utils.validity_checks import device_road_boundary
 
         vel_mode, vel_target, factor = cost_context(None, self.ego_state, self.planning_problem, self.scenario, fpar["dt"],
                                                     self.goal_area)
@@ -181,7 +182,8 @@ class FrenetPlanner:
             vehicle=self.p, params=self.params_dict, mode=self.mode, velocity_cost_mode=vel_mode,
             velocity_target=vel_target, cost_factor=float(np.ndim(factor) == 0 and factor or 1.0),
             predictions_resident=getattr(self, "_resident", False),
-            goal=goal_context(self.ego_state, self.planning_problem, self.scenario, self.goal_area))
+            goal=goal_context(self.ego_state, self.planning_problem, self.scenario, self.goal_area),
+            road_boundary=device_road_boundary(self.road_boundary))
         self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ import numpy as np
 from .... import _abi, dropin
 from ....synthetic import PlanningStep, get_v_list  # noqa: F401  (get_v_list re-exported like the reference)
 from .calc_trajectory_cost import build_cost_dict, cost_context, goal_context
-from .validity_checks import VALIDITY_LEVELS, host_validity_inputs
+from .validity_checks import VALIDITY_LEVELS, device_road_boundary, host_validity_inputs
 
 
 class FrenetTrajectory:
@@ -138,6 +138,7 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
         fl[dense] = factor
         step.cost_factor_list = fl
         step.goal = goal
+        step.road_boundary = device_road_boundary(road_boundary)
         res = ctx.plan(step)
         out = res.numpy()
         red = out["red"][:, dense].astype(np.float64)
@@ -149,7 +150,7 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
         r = dropin.score_trajectories(list(fp_list), predictions, types, vehicle_params, params, mode=mode,
                                       ext_level=ext_level, bd_harm=bd_harm, velocity_cost_mode=vel_mode,
                                       velocity_target=vel_target, cost_factor=np.broadcast_to(factor, (n_list,)), ctx=ctx,
-                                      goal=goal, dt=dt)
+                                      goal=goal, dt=dt, road_boundary=device_road_boundary(road_boundary))
         red, cost, level, reason, oids = r.red, r.cost, r.level, r.reason, r.obstacle_ids
 
     for i, fp in enumerate(fp_list):

@@ -24,6 +24,25 @@ def set_host_checks(fn):
     _HOST_CHECKS = fn
 
 
+class RoadBoundary:
+    """Road boundary as plain triangles [n, 3, 2] (the region outside the road), standing where the reference holds the
+    pycrcc ShapeGroup of ``boundary.create_road_boundary_obstacle`` (frenet_planner.py:226-236).  Passed as
+    ``road_boundary`` it moves the boundary test (level 2, boundary harm) onto the device; ``check`` = "swept" merges
+    consecutive ego boxes like ``trajectory_preprocess_obb_sum`` (own hull), "discrete" tests them as they are."""
+
+    def __init__(self, triangles, check="swept"):
+        self.triangles = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 3, 2)
+        self.check = check
+
+    def as_step_input(self):
+        return (self.triangles, self.check)
+
+
+def device_road_boundary(road_boundary):
+    """``(triangles, check)`` for PlanningStep.road_boundary / ScoringContext.set_road_boundary, or None."""
+    return road_boundary.as_step_input() if isinstance(road_boundary, RoadBoundary) else None
+
+
 def host_validity_inputs(fp_list, ego_state, scenario, vehicle_params, predictions, road_boundary, collision_checker,
                          params):
     if _HOST_CHECKS is None:
@@ -47,5 +66,6 @@ def check_validity(ft, ego_state, scenario, vehicle_params, risk_params, mode: s
                                    collision_checker, params)
     if bd is None and getattr(ft, "bd_harm", 0):  # validity_checks.py:110-115 reads ft.bd_harm
         bd = np.array([float(ft.bd_harm)])
-    r = dropin.score_trajectories([ft], predictions, types, vehicle_params, params, mode=mode, ext_level=ext, bd_harm=bd)
+    r = dropin.score_trajectories([ft], predictions, types, vehicle_params, params, mode=mode, ext_level=ext, bd_harm=bd,
+                                  road_boundary=device_road_boundary(road_boundary))
     return int(r.level[0]), _abi.REASON_NAMES[int(r.reason[0])]

@@ -308,6 +308,16 @@ class ScoringContext:
         cy = np.ascontiguousarray(csp.coef_y, dtype=np.float64)
         self._check(self.lib.etp_set_spline(self.h, _dptr(k), _dptr(cx), _dptr(cy), len(k) - 1))
 
+    def set_road_boundary(self, triangles=None, check="swept"):
+        """Road boundary of the scenario as triangles [n, 3, 2] (the region outside the road, e.g.
+        ``boundary.create_road_boundary_obstacle(method="aligned_triangulation")``, frenet_planner.py:226-236); every
+        later step tests the candidates against it on the device (level 2 and boundary harm).  ``None`` removes it."""
+        b = _abi.RoadBoundary()
+        tri = np.zeros((0, 3, 2)) if triangles is None else np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 3, 2)
+        b.n_triangles, b.triangles, b.check = len(tri), _dptr(tri), _abi.COLLISION_CODES[check]
+        self._check(self.lib.etp_set_road_boundary(self.h, C.byref(b)))
+        self._boundary_key = None if triangles is None else (id(triangles), len(tri), check)
+
     def set_predictions(self, predictions, obstacle_types=None, masses=None, protections=None):
         o = _abi.Obstacles()
         if predictions is None:
@@ -402,6 +412,10 @@ class ScoringContext:
             self._spline_key = skey
         if not getattr(step, "predictions_resident", False):
             self.set_predictions(step.predictions, step.obstacle_types)
+        rb = getattr(step, "road_boundary", None)  # (triangles, check) or None
+        bkey = None if rb is None else (id(rb[0]), len(rb[0]), rb[1])
+        if getattr(self, "_boundary_key", None) != bkey:
+            self.set_road_boundary(*(rb if rb is not None else (None,)))
 
     # -- one planning step --------------------------------------------------------------------
     def make_step_struct(self, step, c_begin=None, c_end=None, shard_index=0, shard_count=1):

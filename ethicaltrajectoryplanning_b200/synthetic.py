@@ -157,6 +157,7 @@ class PlanningStep:
     cost_factor_list: Optional[np.ndarray] = None  # per dense candidate get_cost_factor result (overrides cost_factor)
     predictions_resident: bool = False  # the context already holds these predictions (ScoringContext.set_raw_predictions)
     goal: Optional[GoalContext] = None  # velocity cost and cost factor derived per candidate on the device (overrides the scalars)
+    road_boundary: Optional[tuple] = None  # (triangles [n, 3, 2] outside the road, "discrete" | "swept"): level 2 and boundary harm on the device
 
     @property
     def n_dense(self):
@@ -225,6 +226,30 @@ def make_obstacles(csp, rng, n_obstacles, n_pred, dt, v0, t_max, lateral_spread=
         vel0[oid] = speed
     enrich_predictions(predictions, shapes, ori0, vel0, dt)
     return predictions, types
+
+
+def road_boundary_triangles(csp, half_width=3.6, outer=12.0, ds=4.0, s_begin=None, s_end=None):
+    """Synthetic stand-in of ``boundary.create_road_boundary_obstacle`` (frenet_planner.py:226-236): the region outside
+    a road of constant half width around the reference path, two triangles per ``ds`` metres and side, [n, 3, 2]."""
+    s0 = float(csp.s[0]) if s_begin is None else s_begin
+    s1 = float(csp.s[-1]) if s_end is None else s_end
+    ss = np.arange(s0, s1, ds)
+    pts = {}
+    for side in (1.0, -1.0):
+        for name, off in (("in", half_width), ("out", outer)):
+            p = []
+            for s in ss:
+                x, y = csp.calc_position(s)
+                yaw = csp.calc_yaw(s)
+                p.append((x - side * off * np.sin(yaw), y + side * off * np.cos(yaw)))
+            pts[(side, name)] = np.array(p)
+    tris = []
+    for side in (1.0, -1.0):
+        a, b = pts[(side, "in")], pts[(side, "out")]
+        for k in range(len(ss) - 1):
+            tris.append([a[k], a[k + 1], b[k]])
+            tris.append([a[k + 1], b[k + 1], b[k]])
+    return np.ascontiguousarray(tris, dtype=np.float64)
 
 
 def make_step(name="cfg2", seed=1234, v0=12.0, weights="weights_ethical.json", c_d=0.2, c_d_d=0.0,

@@ -269,6 +269,24 @@ int etp_set_params(etp_ctx* ctx, const etp_params* params);
  * knots[n_seg+1], coef_x/coef_y[n_seg][4] with value = a + b*ds + c*ds^2 + d*ds^3 */
 int etp_set_spline(etp_ctx* ctx, const double* knots, const double* coef_x, const double* coef_y, int n_seg);
 
+/*
+ * Road boundary of the scenario as triangles (boundary.create_road_boundary_obstacle(method="aligned_triangulation"),
+ * frenet_planner.py:226-236): the region OUTSIDE the road.  With a boundary set, every planning step tests the
+ * candidates' ego boxes against it on the device (trajectories_collision_static_obstacles, validity_checks.py:232-245
+ * and risk_costs.py:104-112): the first colliding box i gives boundary_harm = LR1S(traj.v[i]) (risk_costs.py:114-121),
+ * which enters the risk costs and makes the candidate level 2 (validity_checks.py:108-115); without predictions any
+ * collision is level 2.  The device result replaces etp_step.bd_harm.  `check` = ETP_COLLISION_DISCRETE tests the boxes
+ * of create_collision_object as they are (the reference's fallback branch), ETP_COLLISION_SWEPT merges consecutive
+ * boxes first like etp_params.collision_check (not pinned to pycrcc's hull).  n_triangles = 0 or check =
+ * ETP_COLLISION_HOST removes the boundary.  Persistent across steps; a uniform grid over the triangles is built here.
+ */
+typedef struct {
+    int32_t n_triangles;
+    const double* triangles;   /* [n_triangles][3][2] */
+    int32_t check;             /* ETP_COLLISION_* */
+} etp_road_boundary;
+int etp_set_road_boundary(etp_ctx* ctx, const etp_road_boundary* boundary);
+
 /* replaces the `predictions` argument (frenet_functions.py:481; collision_probability.py:136; harm_estimation.py:202) */
 int etp_set_obstacles(etp_ctx* ctx, const etp_obstacles* obstacles, int precision);
 

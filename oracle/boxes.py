@@ -164,3 +164,81 @@ def collision_mask(x, y, yaw, predictions, vehicle_l, vehicle_w, mode="discrete"
         m = _sat_margin_v(_cut(ego, slice(1, k + 1)), tuple(v[None, :k] if isinstance(v, np.ndarray) else v for v in obs))
         hit |= (~(m > 0.0)).any(axis=1)
     return hit
+
+
+# ------------------------------------------------------------------------------------------------
+# road boundary: ego boxes against the triangles outside the road (validity_checks.py:216-245, risk_costs.py:104-123)
+# PARITY UNPINNED like the rest of this file: pycrcc's static-obstacle query is not vendored.  Restated from the
+# reference's own sources: which boxes exist (create_collision_object), that the FIRST colliding box i is reported
+# (leaving_road_at[0] - ego_state.time_step) and that the harm is LR1S(traj.v[i]).  Brute force over all triangles
+# (the product uses a uniform grid: the comparison checks the grid as well).
+# ------------------------------------------------------------------------------------------------
+def sat_margin_triangle(b, tri):
+    """Largest separating-axis margin of box ``b`` and triangle ``tri`` [3, 2]: two box axes, three edge normals."""
+    x, y, c, s, l, w = b
+    u = np.array([[(p[0] - x) * c + (p[1] - y) * s, (p[1] - y) * c - (p[0] - x) * s] for p in tri])
+    m = max(u[:, 0].min() - l, -u[:, 0].max() - l, u[:, 1].min() - w, -u[:, 1].max() - w)
+    for k in range(3):
+        j, i = (k + 1) % 3, (k + 2) % 3
+        n = np.array([-(u[j, 1] - u[k, 1]), u[j, 0] - u[k, 0]])
+        ln = np.hypot(n[0], n[1])
+        if not ln > 0.0:
+            continue
+        n = n / ln
+        a, bb = float(n @ u[k]), float(n @ u[i])
+        r = l * abs(n[0]) + w * abs(n[1])
+        m = max(m, min(a, bb) - r, -max(a, bb) - r)
+    return m
+
+
+def box_triangle_overlap_by_polygon(b, tri):
+    """Independent of the separating-axis form: a vertex of one inside the other, or two edges crossing."""
+    cb = corners(b)
+    t = [tuple(p) for p in tri]
+
+    def in_tri(p):
+        d = [(t[(k + 1) % 3][0] - t[k][0]) * (p[1] - t[k][1]) - (t[(k + 1) % 3][1] - t[k][1]) * (p[0] - t[k][0]) for k in range(3)]
+        return all(v >= 0 for v in d) or all(v <= 0 for v in d)
+
+    if any(_inside(b, p) for p in t) or any(in_tri(p) for p in cb):
+        return True
+    return any(_segments_cross(cb[i], cb[(i + 1) % 4], t[j], t[(j + 1) % 3]) for i in range(4) for j in range(3))
+
+
+def first_boundary_collision(x, y, yaw, triangles, vehicle_l, vehicle_w, mode="swept"):
+    """Index of the first ego box that touches a triangle, or -1 (trajectories_collision_static_obstacles)."""
+    T = len(x)
+    ego = _object([box(x[i], y[i], yaw[i], vehicle_l / 2, vehicle_w / 2) for i in range(T)], mode == "swept")
+    tris = np.asarray(triangles, dtype=np.float64).reshape(-1, 3, 2)
+    for i, e in enumerate(ego):
+        for tri in tris:
+            if not sat_margin_triangle(e, tri) > 0.0:
+                return i
+    return -1
+
+
+def first_boundary_collision_mask(x, y, yaw, triangles, vehicle_l, vehicle_w, mode="swept"):
+    """x, y, yaw: [n, T] -> int[n] first colliding box per candidate or -1 (vectorised over candidates and boxes)."""
+    n, T = x.shape
+    ego = (x, y, np.cos(yaw), np.sin(yaw), np.full_like(x, vehicle_l / 2), np.full_like(x, vehicle_w / 2))
+    if mode == "swept" and T >= 2:
+        ego = _hull_v(_cut(ego, slice(0, T - 1)), _cut(ego, slice(1, T)))
+    ex, ey, ec, es, el, ew = ego
+    hit = np.zeros(ex.shape, dtype=bool)
+    for tri in np.asarray(triangles, dtype=np.float64).reshape(-1, 3, 2):
+        ux = [(p[0] - ex) * ec + (p[1] - ey) * es for p in tri]
+        uy = [(p[1] - ey) * ec - (p[0] - ex) * es for p in tri]
+        m = np.maximum(np.maximum(np.minimum.reduce(ux) - el, -np.maximum.reduce(ux) - el),
+                       np.maximum(np.minimum.reduce(uy) - ew, -np.maximum.reduce(uy) - ew))
+        for k in range(3):
+            j, i = (k + 1) % 3, (k + 2) % 3
+            nx, ny = -(uy[j] - uy[k]), ux[j] - ux[k]
+            ln = np.sqrt(nx * nx + ny * ny)
+            ok = ln > 0.0
+            ln = np.where(ok, ln, 1.0)
+            nx, ny = nx / ln, ny / ln
+            a, b = nx * ux[k] + ny * uy[k], nx * ux[i] + ny * uy[i]
+            r = el * np.abs(nx) + ew * np.abs(ny)
+            m = np.where(ok, np.maximum(m, np.maximum(np.minimum(a, b) - r, -np.maximum(a, b) - r)), m)
+        hit |= ~(m > 0.0)
+    return np.where(hit.any(axis=1), hit.argmax(axis=1), -1)

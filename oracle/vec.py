@@ -260,6 +260,13 @@ def score_dense(step, profiles=None):
         hv = np.where(first >= 0, ~(v[np.arange(n), np.maximum(first, 0)] < thr_v), False)
         bd = np.zeros(n) if step.bd_harm is None else np.asarray(step.bd_harm, dtype=np.float64)[p * nd + idx]
         ext = np.full(n, 10) if step.ext_level is None else np.asarray(step.ext_level)[p * nd + idx].astype(np.int64)
+        rb = getattr(step, "road_boundary", None)
+        if rb is not None:  # product extension, see oracle/boxes.py (risk_costs.py:104-123, validity_checks.py:108-115)
+            leave = _boxes.first_boundary_collision_mask(x, y, yaw, rb[0], vp.l, vp.w, rb[1])
+            ia = coeffs["log_reg"]["ignore_angle"]
+            vl = v[np.arange(n), np.maximum(leave, 0)]
+            bd = np.where(leave >= 0, 1 / (1 + np.exp(-ia["const"] - ia["speed"] * vl)), 0.0)
+            ext = np.where(ext == 1, 1, np.where(leave >= 0, 2, 10))
         check = modes.get("collision_check_device", "host")  # product extension, see oracle/boxes.py
         if check != "host" and preds is not None and step.mode in ("WaleNet", "risk"):
             ext = np.where(_boxes.collision_mask(x, y, yaw, preds, vp.l, vp.w, check), 1, ext)

@@ -75,3 +75,34 @@ def test_loop_form_equals_vectorised_form_and_finds_collisions():
         off = vec.score_dense(_step("host"))
         assert not np.any(off["level"] == 1)
     assert found > 0
+
+
+def test_box_triangle_separating_axes_agree_with_corner_and_edge_test():
+    rng = np.random.default_rng(9)
+    n_hit = 0
+    for _ in range(4000):
+        b = boxes.box(rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-7, 7), rng.uniform(0.3, 3), rng.uniform(0.3, 1.5))
+        tri = rng.uniform(-5, 5, size=(3, 2))
+        m = boxes.sat_margin_triangle(b, tri)
+        if abs(m) < 1e-9:
+            continue
+        assert (m <= 0) == boxes.box_triangle_overlap_by_polygon(b, tri)
+        n_hit += m <= 0
+    assert 1000 < n_hit < 3500
+
+
+def test_road_boundary_loop_form_equals_vectorised_form():
+    from ethicaltrajectoryplanning_b200.synthetic import make_step, road_boundary_triangles
+    from oracle import port, vec
+
+    for mode in ("discrete", "swept"):
+        step = make_step("planning", seed=5, n_obstacles=4, nv=5, nd=11)
+        step.road_boundary = (road_boundary_triangles(step.csp, s_end=140.0), mode)
+        ref = vec.score_dense(step)
+        _, _, _, fps = port.plan_step(step)
+        lv = np.array([fp.valid_level for fp in fps])
+        live = ref["level"] != vec.LEVEL_SKIPPED
+        np.testing.assert_array_equal(ref["level"][live], lv)
+        assert 0 < np.sum(lv == 2) < len(lv)
+        bd = np.array([fp.bd_harm for fp in fps], dtype=np.float64)
+        assert np.all((bd > 0) == (lv == 2) | ((bd > 0) & (lv < 2)))

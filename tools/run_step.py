@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--argmin-only", action="store_true")
     ap.add_argument("--lateral-spread", type=float, default=4.0)
     ap.add_argument("--collision", default="host", choices=["host", "discrete", "swept"])
+    ap.add_argument("--boundary", default="host", choices=["host", "discrete", "swept"], help="synthetic road boundary on the device")
+    ap.add_argument("--goal", action="store_true", help="attach a goal context (rectangle ahead on the path)")
     args = ap.parse_args()
     import torch
 
@@ -30,6 +32,14 @@ def main():
         import copy
         step.params = copy.deepcopy(step.params)
         step.params["modes"]["collision_check_device"] = args.collision
+    if args.boundary != "host":
+        from ethicaltrajectoryplanning_b200.synthetic import road_boundary_triangles
+        step.road_boundary = (road_boundary_triangles(step.csp), args.boundary)
+    if args.goal:
+        from ethicaltrajectoryplanning_b200.synthetic import GoalContext
+        step.goal = GoalContext(polygons=[[(24.0, 0.5), (60.0, 0.5), (60.0, 4.2), (24.0, 4.2)]], velocity=(5.0, 30.0),
+                                orientation=(-0.5, 0.5), time_step=(10, 60), ego_time_step=0,
+                                ego_position=tuple(step.ego_position), goal_centers=[(42.0, 2.3)])
     ctx = ScoringContext(0, args.precision)
     ctx.configure(step)
     s, keep, nsamp = ctx.make_step_struct(step)
