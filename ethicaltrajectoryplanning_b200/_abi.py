@@ -125,6 +125,7 @@ class Out(C.Structure):
         ("level", C.c_void_p), ("reason", C.c_void_p),
         ("c_stride", C.c_int64),
         ("harm", C.c_void_p),
+        ("bd_harm", C.c_void_p),
     ]
 
 

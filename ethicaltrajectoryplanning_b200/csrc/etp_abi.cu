@@ -724,7 +724,7 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     DevOut dout{};
     if (out) {
         dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
-        dout.level = out->level; dout.reason = out->reason; dout.harm = out->harm;
+        dout.level = out->level; dout.reason = out->reason; dout.harm = out->harm; dout.bd_harm = out->bd_harm;
         dout.c_stride = out->c_stride > 0 ? (size_t)out->c_stride : (size_t)st.n_local;
         if (dout.c_stride < (size_t)st.n_local)
             ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.c_stride=%lld is smaller than the %d candidates of this call",
@@ -815,7 +815,7 @@ int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out*
     DevOut dout{};
     if (out) {
         dout.traj = out->traj; dout.prob = out->prob; dout.red = out->red; dout.cost = out->cost;
-        dout.level = out->level; dout.reason = out->reason; dout.harm = out->harm;
+        dout.level = out->level; dout.reason = out->reason; dout.harm = out->harm; dout.bd_harm = out->bd_harm;
         dout.c_stride = out->c_stride > 0 ? (size_t)out->c_stride : (size_t)st.n_local;
         if (dout.c_stride < (size_t)st.n_local) ETP_FAIL(c, ETP_ERR_INVALID, "etp_out.c_stride too small");
     }

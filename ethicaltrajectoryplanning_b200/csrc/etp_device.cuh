@@ -173,6 +173,7 @@ struct DevOut {
     uint8_t* level;
     uint8_t* reason;
     void* harm;
+    double* bd_harm;
     size_t c_stride;  // elements between rows of the candidate-minor tensors
 };
 

@@ -1303,6 +1303,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 #pragma unroll
             for (int k = 0; k < ETP_NUM_COST; ++k) c[k] = 0.0;
             int level = ETP_LEVEL_SKIPPED, reason = ETP_REASON_NONE;
+            double bd_out = 0.0;
             if (live) {
                 double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
                 double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
@@ -1334,6 +1335,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                         ext = 10;
                     }
                 }
+                bd_out = bd;
                 if (O > 0) {
                     c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
                     c[ETP_C_EQUALITY] = sum_abs / (double)O;                  // :176-178
@@ -1411,6 +1413,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 #pragma unroll
                     for (int k = 0; k < ETP_NUM_COST; ++k) o_cost[(size_t)k * Cp + cl] = (R)c[k];
                 }
+                if (out.bd_harm) out.bd_harm[cl] = bd_out;
                 if (out.level) out.level[cl] = (uint8_t)level;
                 if (out.reason) out.reason[cl] = (uint8_t)reason;
             }

@@ -124,7 +124,7 @@ def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, param
         keep.append(b)
     o = _abi.Out()
     o.precision, o.c_stride = ctx.precision, int(bufs["c_stride"])
-    for k in ("traj", "prob", "red", "cost", "level", "reason", "harm"):
+    for k in ("traj", "prob", "red", "cost", "level", "reason", "harm", "bd_harm"):
         t = bufs.get(k)
         setattr(o, k, None if t is None else C.c_void_p(t.data_ptr()))
     ctx._check(ctx.lib.etp_score_trajectories(ctx.h, C.byref(g), C.byref(o)))
@@ -138,6 +138,7 @@ def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, param
         cost=host["cost"].astype(np.float64),                           # [13][C]
         level=host["level"].astype(np.int64), reason=host["reason"].astype(np.int64),
         harm=None if harm is None else harm.transpose(0, 3, 1, 2).astype(np.float64),  # [2][C][T-1][O]
+        bd_harm=bufs["bd_harm"].detach().cpu().numpy(),                  # [C] fp64
     )
 
 

@@ -20,7 +20,7 @@ from ... import dropin
 from ...configs import load_harm_parameter_json, load_risk_json, load_weight_json
 from ...synthetic import PlanningStep, assign_responsibility_by_action_space, planner_v_list
 from .utils.frenet_functions import calc_frenet_trajectories, sort_frenet_trajectories
-from .utils.logging import FrenetLogging
+from .utils.logging import ColumnarLogging, FrenetLogging
 from .utils.validity_checks import VALIDITY_LEVELS  # noqa: F401
 
 DEFAULT_FRENET_PARAMETERS = {  # frenet_planner.py:116-128 (planning_fast.json values)
@@ -38,7 +38,7 @@ class FrenetPlanner:
                  frenet_parameters: dict = None, sensor_radius: float = 50.0, plot_frenet_trajectories: bool = False,
                  weights=None, settings=None, *, reference_spline=None, global_path=None, predictor=None, ego_state=None,
                  road_boundary=None, collision_checker=None, goal_area=None, log_path=None, obstacle_types=None,
-                 materialize=True, precision=None):
+                 materialize=True, precision=None, columnar_log_path=None):
         if mode not in ("ground_truth", "WaleNet", "risk"):
             raise ValueError("mode must be ground_truth, WaleNet, or risk")
         if reference_spline is None:
@@ -67,6 +67,8 @@ class FrenetPlanner:
         self.reach_set, self.responsibility = None, False
         self.obstacle_types = obstacle_types
         self.logger = FrenetLogging(log_path) if log_path else None
+        # binary side-car of the per-step log for the fused path (logging.ColumnarLogging; legacy line on demand)
+        self.columnar_logger = ColumnarLogging(columnar_log_path) if columnar_log_path else None
         self.materialize = materialize
         self.ctx = dropin.default_context(precision)
         self.ego_state = ego_state
@@ -184,6 +186,12 @@ class FrenetPlanner:
             predictions_resident=getattr(self, "_resident", False),
             goal=goal_context(self.ego_state, self.planning_problem, self.scenario, self.goal_area),
             road_boundary=device_road_boundary(self.road_boundary))
+        if self.columnar_logger is not None:
+            # logging needs every candidate: materialised step, tensors appended as they come off the device
+            res = self.ctx.plan(step)
+            self.columnar_logger.log_step(self.time_step, self.time_step * fpar["dt"], res, step, predictions, 0, None)
+            self.last_best, self._trajectory = res.best, res.best_trajectory()
+            return
         self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------

@@ -145,14 +145,23 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
         cost = out["cost"][:, dense].astype(np.float64)
         level = out["level"][dense].astype(np.int64)
         reason = out["reason"][dense].astype(np.int64)
+        bd_dev = out["bd_harm"][dense]
         oids = res.obstacle_ids
     else:
         r = dropin.score_trajectories(list(fp_list), predictions, types, vehicle_params, params, mode=mode,
                                       ext_level=ext_level, bd_harm=bd_harm, velocity_cost_mode=vel_mode,
                                       velocity_target=vel_target, cost_factor=np.broadcast_to(factor, (n_list,)), ctx=ctx,
                                       goal=goal, dt=dt, road_boundary=device_road_boundary(road_boundary))
-        red, cost, level, reason, oids = r.red, r.cost, r.level, r.reason, r.obstacle_ids
+        red, cost, level, reason, oids, bd_dev = r.red, r.cost, r.level, r.reason, r.obstacle_ids, r.bd_harm
+    if device_road_boundary(road_boundary) is not None:
+        bd_harm = bd_dev  # the device's own boundary harm (etp_out.bd_harm)
+    return fill_trajectories(fp_list, red, cost, level, reason, oids, predictions, bd_harm, params, mode)
 
+
+def fill_trajectories(fp_list, red, cost, level, reason, oids, predictions, bd_harm, params, mode):
+    """Per-candidate result arrays -> the attributes sort_frenet_trajectories leaves on the trajectories
+    (frenet_functions.py:529-593) and its return value.  Shared with the columnar log reader (logging.py)."""
+    validity_dict = {key: [] for key in VALIDITY_LEVELS}
     for i, fp in enumerate(fp_list):
         if predictions is not None:  # frenet_functions.py:529-542
             T = len(fp.x)

@@ -211,6 +211,7 @@ class ScoreResult:
     cost: object = None
     level: object = None
     reason: object = None
+    bd_harm: object = None
     _ctx: object = field(default=None, repr=False)
 
     def numpy(self):
@@ -219,7 +220,7 @@ class ScoreResult:
         candidate-minor (include/etp_b200.h, etp_out); the transposes below are views."""
         out = {}
         self._ctx.stream.synchronize()
-        for k in ("traj", "prob", "red", "cost", "level", "reason"):
+        for k in ("traj", "prob", "red", "cost", "level", "reason", "bd_harm"):
             v = getattr(self, k)
             out[k] = None if v is None else v.detach().cpu().numpy()
         if out["traj"] is not None:
@@ -470,6 +471,7 @@ class ScoringContext:
             cost=torch.empty((_abi.NUM_COST, Cp), **kw)[..., :Cs] if cost else None,
             level=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
             reason=torch.empty((Cs,), device=self.device, dtype=torch.uint8),
+            bd_harm=torch.empty((Cs,), device=self.device, dtype=torch.float64),
         )
         for t in bufs.values():
             if t is not None:
@@ -486,7 +488,7 @@ class ScoringContext:
         o = _abi.Out()
         o.precision = self.precision
         o.c_stride = int(bufs.get("c_stride", 0))
-        for k in ("traj", "prob", "red", "cost", "level", "reason"):
+        for k in ("traj", "prob", "red", "cost", "level", "reason", "harm", "bd_harm"):
             t = bufs.get(k)
             setattr(o, k, None if t is None else C.c_void_p(t.data_ptr()))
         self._check(self.lib.etp_plan_step(self.h, C.byref(s), C.byref(o)))
@@ -643,6 +645,6 @@ class ScoringContext:
         res = ScoreResult(n_dense=step.n_dense, c_begin=s.c_begin, c_end=s.c_end, Tmax=Tmax, n_samples=n,
                           obstacle_ids=list(self.obstacle_ids), best=best, _ctx=self)
         if materialize:
-            for k in ("traj", "prob", "red", "cost", "level", "reason"):
+            for k in ("traj", "prob", "red", "cost", "level", "reason", "bd_harm"):
                 setattr(res, k, bufs.get(k))
         return res

@@ -86,7 +86,7 @@ class MovingObstacles:
 
 
 def closed_loop(n_steps=200, weights="weights_ethical.json", grid="cfg2", v0=12.0, n_obstacles=8, materialize=False,
-                precision=None, seed=1234):
+                precision=None, seed=1234, columnar_log_path=None):
     """Replan every 0.1 s over ``n_steps`` cycles with ideal tracking.  Returns per-step wall-clock latencies [s] of
     ``FrenetPlanner.step`` (host packing + launches + readback of the winner) and the driven states."""
     from .synthetic import GRIDS
@@ -106,7 +106,7 @@ def closed_loop(n_steps=200, weights="weights_ethical.json", grid="cfg2", v0=12.
                           time_step=0)
     pl = FrenetPlanner(scenario, problem, 1, veh, "risk", frenet_parameters=fpar, weights=params["weights"],
                        settings={"risk_dict": params["modes"]}, reference_spline=csp, predictor=pred, ego_state=ego,
-                       materialize=materialize, precision=precision)
+                       materialize=materialize, precision=precision, columnar_log_path=columnar_log_path)
     lat, states = [], []
     for k in range(n_steps):
         t0 = time.perf_counter()

@@ -218,6 +218,8 @@ typedef struct {
     int64_t c_stride;    /* elements between consecutive rows of the tensors above */
     void* harm;          /* optional [2][Tmax-1][O][c_stride]: ego / obstacle harm per sample, 0 past min(T-1, Tp)
                             (the arrays get_harm returns, harm_estimation.py:202-338) */
+    double* bd_harm;     /* optional [Cs] fp64: boundary harm of each candidate (fp.bd_harm, risk_costs.py:104-123): the
+                            device's own when a road boundary is set, else the caller's etp_step.bd_harm (or 0) */
 } etp_out;
 
 /*

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_struct_sizes_match_the_header_layout():
     assert ctypes.sizeof(_abi.Best) == 40
     assert ctypes.sizeof(_abi.Params) == 8 * 14 + 4 * 4 + 8 + 8 * 8 + 8 * 9 * 2 + 8 * 6 + 8 * 8 + 8
-    assert ctypes.sizeof(_abi.Out) == 8 + 6 * 8 + 8 + 8
+    assert ctypes.sizeof(_abi.Out) == 8 + 6 * 8 + 8 + 8 + 8
     # sizeof(etp_goal), sizeof(etp_step), sizeof(etp_trajectories) as g++ lays them out (x86-64)
     assert (ctypes.sizeof(_abi.Goal), ctypes.sizeof(_abi.Step), ctypes.sizeof(_abi.Trajectories)) == (136, 192, 88)
 
