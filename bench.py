@@ -493,6 +493,43 @@ def latency_extras(ctx, torch):
     torch.cuda.empty_cache()
     extras["cfg3_regimes"] = regimes
 
+    # cfg3 with the optional device-side checks of SURVEY.md 8f switched on one at a time (N1 collision with the predicted
+    # boxes, N1 road boundary, N3 goal logic): kernel time of the same 10^6-candidate step
+    import copy
+
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext, road_boundary_triangles
+
+    checks = {}
+    for name in ("none", "collision_discrete", "collision_swept", "road_boundary_swept", "goal_context"):
+        st3 = make_step("cfg3")
+        if name.startswith("collision"):
+            st3.params = copy.deepcopy(st3.params)
+            st3.params["modes"]["collision_check_device"] = name.split("_")[1]
+        if name == "road_boundary_swept":
+            st3.road_boundary = (road_boundary_triangles(st3.csp), "swept")
+        if name == "goal_context":
+            st3.goal = GoalContext(polygons=[[(24.0, 0.5), (60.0, 0.5), (60.0, 4.2), (24.0, 4.2)]], velocity=(5.0, 30.0),
+                                   orientation=(-0.5, 0.5), time_step=(10, 60), ego_time_step=0,
+                                   ego_position=tuple(st3.ego_position), goal_centers=[(42.0, 2.3)])
+        ctx.configure(st3)
+        s3, keep3, ns3 = ctx.make_step_struct(st3)
+        b3 = ctx.allocate_outputs(st3.n_dense, int(ns3.max()), ctx.O)
+        ctx.enable_timing(True)
+        ks = []
+        for i in range(4):
+            ctx.launch(s3, b3)
+            ks.append(ctx.timing()[1])
+        ctx.enable_timing(False)
+        lv = torch.bincount(b3["level"].to(torch.int64), minlength=11)[[0, 1, 2, 3, 10]].tolist()
+        checks[name] = {"kernel_ms": float(np.median(ks[1:])), "levels_0_1_2_3_10": lv}
+        del b3
+    st3 = make_step("cfg3")
+    ctx.configure(st3)  # removes the boundary, restores the host collision mode
+    torch.cuda.empty_cache()
+    checks["workload"] = ("cfg3 (10^6 candidates, T=50, 32 obstacles) with one optional device-side check at a time; the synthetic "
+                          "obstacle boxes sit on the reference path, so the collision check marks every candidate level 1")
+    extras["cfg3_device_checks"] = checks
+
     # cfg4: evaluatefrenet-style sweep (one planning step per scenario, arg-min only), this GPU's share
     from ethicaltrajectoryplanning_b200 import workloads
 
@@ -512,6 +549,12 @@ def latency_extras(ctx, torch):
             lat = lat[5:] * 1e3
             loop[f"{grid}/{w}"] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                                    "final_s_m": states[-1][0], "final_v_mps": states[-1][2]}
+    lat, states = workloads.closed_loop(200, "weights_ethical.json", "cfg2", device_checks=True)
+    lat = lat[5:] * 1e3
+    loop["cfg2/weights_ethical.json/device_checks"] = {
+        "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "final_s_m": states[-1][0],
+        "final_v_mps": states[-1][2],
+        "note": "collision with the predicted boxes (swept), road boundary (300 triangles) and goal logic on the device as well"}
     loop["workload"] = ("FrenetPlanner.step wall clock: host packing of moving predictions + 2 launches + readback of the "
                         "winner's 13 fp64 rows; cfg1 = 5x5 grid T=20, cfg2 = 100x100 grid T=30, 8 obstacles")
     extras["cfg5_closed_loop"] = loop

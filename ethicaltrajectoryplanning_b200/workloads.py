@@ -86,9 +86,13 @@ class MovingObstacles:
 
 
 def closed_loop(n_steps=200, weights="weights_ethical.json", grid="cfg2", v0=12.0, n_obstacles=8, materialize=False,
-                precision=None, seed=1234, columnar_log_path=None):
+                precision=None, seed=1234, columnar_log_path=None, device_checks=False):
     """Replan every 0.1 s over ``n_steps`` cycles with ideal tracking.  Returns per-step wall-clock latencies [s] of
-    ``FrenetPlanner.step`` (host packing + launches + readback of the winner) and the driven states."""
+    ``FrenetPlanner.step`` (host packing + launches + readback of the winner) and the driven states.
+
+    ``device_checks``: everything the reference asks pycrcc / CommonRoad for runs on the device as well -- collision with
+    the predicted boxes (swept), a road boundary 3.6 m either side of the path, and a goal (lanelet-like polygon 150-190 m
+    down the path, velocity / orientation / time intervals) driving cost factor and velocity cost."""
     from .synthetic import GRIDS
 
     nv, nd, dmax, t_list, _ = GRIDS[grid]
@@ -101,12 +105,33 @@ def closed_loop(n_steps=200, weights="weights_ethical.json", grid="cfg2", v0=12.
             "d_list": np.linspace(-dmax, dmax, nd), "dt": 0.1, "v_thr": 3.0}
     scenario = SimpleNamespace(dt=0.1, obstacle_by_id=pred.obstacle_by_id)
     problem = SimpleNamespace(velocity_cost_mode=0, velocity_target=v0, cost_factor=1.0)
+    road_boundary = goal_area = None
+    if device_checks:
+        import copy
+
+        from .planner.Frenet.utils.calc_trajectory_cost import GoalArea
+        from .planner.Frenet.utils.validity_checks import RoadBoundary
+        from .synthetic import road_boundary_triangles
+
+        params = copy.deepcopy(params)
+        params["modes"]["collision_check_device"] = "swept"
+        road_boundary = RoadBoundary(road_boundary_triangles(csp), "swept")
+        ring = []
+        for s_, side in [(150.0, 1), (170.0, 1), (190.0, 1), (190.0, -1), (170.0, -1), (150.0, -1)]:
+            px, py = csp.calc_position(s_)
+            yaw = csp.calc_yaw(s_)
+            ring.append((px - side * 3.6 * np.sin(yaw), py + side * 3.6 * np.cos(yaw)))
+        goal_area = GoalArea([ring])
+        cx, cy = csp.calc_position(170.0)
+        state = SimpleNamespace(time_step=SimpleNamespace(start=100, end=n_steps + 150), velocity=SimpleNamespace(start=5.0, end=20.0),
+                                orientation=SimpleNamespace(start=-1.0, end=1.0), position=SimpleNamespace(center=np.array([cx, cy])))
+        problem = SimpleNamespace(goal=SimpleNamespace(state_list=[state]))
     x0, y0 = csp.calc_position(0.0)
     ego = SimpleNamespace(position=np.array([x0, y0]), orientation=float(csp.calc_yaw(0.0)), velocity=v0, acceleration=0.0,
                           time_step=0)
     pl = FrenetPlanner(scenario, problem, 1, veh, "risk", frenet_parameters=fpar, weights=params["weights"],
                        settings={"risk_dict": params["modes"]}, reference_spline=csp, predictor=pred, ego_state=ego,
-                       materialize=materialize, precision=precision, columnar_log_path=columnar_log_path)
+                       road_boundary=road_boundary, goal_area=goal_area, materialize=materialize, precision=precision, columnar_log_path=columnar_log_path)
     lat, states = [], []
     for k in range(n_steps):
         t0 = time.perf_counter()

@@ -45,3 +45,14 @@ def test_closed_loop_fused_equals_materialised_and_fp64():
         assert a[3] == c[3]
     s = [st[0] for st in fused]
     assert all(b > a for a, b in zip(s[:-1], s[1:]))  # the ego advances along the path
+
+
+def test_closed_loop_with_every_check_on_the_device():
+    """cfg5 with collision, road boundary and goal logic on the device: runs, stays on the road, moves forward."""
+    from ethicaltrajectoryplanning_b200.workloads import closed_loop
+
+    lat, states = closed_loop(n_steps=30, grid="planning", n_obstacles=4, device_checks=True)
+    s = np.array([st[0] for st in states])
+    d = np.array([st[1] for st in states])
+    assert np.all(np.diff(s) >= 0) and s[-1] > s[0] + 5.0
+    assert np.all(np.abs(d) < 3.6)
