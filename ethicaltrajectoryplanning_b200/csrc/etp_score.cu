@@ -40,6 +40,9 @@ constexpr int kWarps = kThreads / 32;
 #define ETP_MIN_BLOCKS 2
 #endif
 constexpr int kMinBlocks = ETP_MIN_BLOCKS;  // resident CTAs per SM the register budget is sized for
+#ifndef ETP_SEG_FACTOR
+#define ETP_SEG_FACTOR 2  // phase-2a items per warp (2: 17.0 ms, 3: 17.1, 4: 17.2, 6: 17.6 on the 10^6-candidate step)
+#endif
 #ifndef ETP_OB
 #define ETP_OB 4
 #endif
@@ -962,7 +965,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     const int n_groups = (O + kOB - 1) / kOB;
     int n_seg = 1;
     if (n_groups > 0) {
-        n_seg = (3 * kWarps + n_groups - 1) / n_groups;
+        n_seg = (ETP_SEG_FACTOR * kWarps + n_groups - 1) / n_groups;
         const int max_seg = (Ts - 1 + 7) / 8;  // at least 8 samples per segment
         n_seg = n_seg > max_seg ? max_seg : n_seg;
         n_seg = n_seg < 1 ? 1 : n_seg;
