@@ -881,11 +881,15 @@ int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp
     }
     ETP_CUDA(c, c->batch_host.reserve(sizeof(BestRec) * (size_t)n));
     BestRec* host = reinterpret_cast<BestRec*>(c->batch_host.p);
+    // the road boundary of this context (grid and triangles stay in its buffers) serves every scenario of the batch;
+    // its upload ran on this context's stream
+    if (c->boundary.check != ETP_COLLISION_HOST) ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) {
         etp_ctx* k = c->pool[i % kPool];
         const etp_scenario& s = sc[i];
         if (!s.step || !s.obstacles || !s.knots || !s.coef_x || !s.coef_y) ETP_FAIL(c, ETP_ERR_INVALID, "scenario %d incomplete", i);
         k->pr = c->pr;
+        k->boundary = c->boundary;
         k->have_params = true;
         int rc = ETP_OK;
         if (k->last_knots != s.knots || k->last_nseg != s.n_seg) {  // sweeps over one map share the spline

@@ -345,7 +345,8 @@ int etp_principle_costs(etp_ctx* ctx, int n, const double* ego_risk, const doubl
 /*
  * Scenario sweep (planner/Frenet/plannertools/evaluatefrenet.py:16-55, planner/plannertools/evaluate.py:160-169: one
  * planner per scenario in a process pool): n independent planning steps in one call.  Each scenario brings its own
- * spline, predictions and sampling grid; the parameters are the context's (etp_set_params).  The steps run on a pool of
+ * spline, predictions and sampling grid (and goal, etp_step.goal); the parameters and the road boundary are the context's
+ * (etp_set_params, etp_set_road_boundary).  The steps run on a pool of
  * internal streams so that their small launches and uploads overlap; only the arg-min of each scenario is produced
  * (bests[i], index -1 if every candidate of scenario i was skipped).  Synchronises before returning.
  */

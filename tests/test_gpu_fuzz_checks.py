@@ -1,0 +1,99 @@
+"""Randomised parity of the optional device-side checks switched on TOGETHER (collision with the predicted boxes, road
+boundary, goal logic) against the vectorised fp64 oracle: random paths in every direction, random boundary widths, random
+goal polygons / intervals, both box modes; plus the same scenes through the batched sweep entry point."""
+import copy
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("_rs2", os.path.join(os.path.dirname(__file__), "test_gpu_random_scenes.py"))
+_rs = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_rs)
+
+
+def scene(seed):
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext, road_boundary_triangles
+
+    rng = np.random.default_rng(10_000 + seed)
+    step = _rs.random_scene(seed)
+    step.params = copy.deepcopy(step.params)
+    mode = ("discrete", "swept")[seed % 2]
+    step.params["modes"]["collision_check_device"] = ("host", "discrete", "swept")[seed % 3]
+    step.road_boundary = (road_boundary_triangles(step.csp, half_width=float(rng.uniform(2.4, 4.5)), outer=float(rng.uniform(8.0, 15.0)),
+                                                  ds=float(rng.uniform(2.5, 7.0)), s_end=min(float(step.csp.s[-1]), step.c_s + 140.0)), mode)
+    # goal: a quadrilateral across the road somewhere ahead (sometimes around the ego), random intervals
+    s0 = step.c_s + (rng.uniform(-3.0, 3.0) if seed % 4 == 0 else rng.uniform(8.0, 45.0))
+    ring = []
+    for ds, side in ((0.0, 1), (rng.uniform(8.0, 30.0), 1), (rng.uniform(8.0, 30.0), -1), (0.0, -1)):
+        px, py = step.csp.calc_position(s0 + ds)
+        yaw = step.csp.calc_yaw(s0 + ds)
+        w = rng.uniform(1.0, 5.0)
+        ring.append((px - side * w * np.sin(yaw), py + side * w * np.cos(yaw)))
+    yaw0 = float(step.csp.calc_yaw(s0))
+    step.goal = GoalContext(
+        polygons=[ring], circles=[(ring[1][0], ring[1][1], float(rng.uniform(0.5, 3.0)))] if seed % 5 == 0 else None,
+        velocity=None if seed % 3 == 0 else tuple(sorted(rng.uniform(0.0, 30.0, size=2))),
+        orientation=None if seed % 4 == 1 else (yaw0 - rng.uniform(0.1, 1.0) + (2 * np.pi if seed % 6 == 2 else 0.0),
+                                                yaw0 + rng.uniform(0.1, 1.0) + (2 * np.pi if seed % 6 in (2, 3) else 0.0)),
+        time_step=(int(rng.integers(0, 30)), int(rng.integers(30, 80))), ego_time_step=int(rng.integers(0, 40)),
+        ego_position=tuple(step.ego_position), goal_centers=[ring[1], ring[2]] if seed % 7 else None)
+    return step
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ETP_FUZZ_SCENES", "20"))))
+def test_all_device_checks_together(seed):
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from oracle import vec
+
+    step = scene(seed)
+    ref = vec.score_dense(step)
+    live = ref["level"] != vec.LEVEL_SKIPPED
+    for precision, rtol in (("fp32", 2e-4), ("fp64", 1e-9)):
+        ctx = ScoringContext(0, precision)
+        try:
+            res = ctx.plan(step)
+            out = res.numpy()
+            np.testing.assert_array_equal(out["level"].astype(np.int64), ref["level"], err_msg=precision)
+            np.testing.assert_array_equal(out["reason"].astype(np.int64), ref["reason"], err_msg=precision)
+            np.testing.assert_array_equal(out["cost"][11, live].astype(np.float32), ref["cost"][11, live].astype(np.float32))
+            np.testing.assert_allclose(out["cost"][:, live], ref["cost"][:, live], rtol=rtol, atol=1e-6, err_msg=precision)
+            assert res.best["level"] == ref["best"]["level"]
+            if res.best["index"] != ref["best"]["index"]:
+                assert precision == "fp32"
+                d = ref["dense_index"].tolist()
+                assert abs(ref["cost"][12][d.index(res.best["index"])] - ref["best"]["cost"]) <= 1e-4 * abs(ref["best"]["cost"]) + 1e-7
+        finally:
+            ctx.close()
+
+
+def test_batched_sweep_honours_goal_and_road_boundary():
+    """etp_plan_batch: every scenario carries its own goal; the road boundary is the context's."""
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext, make_step, road_boundary_triangles
+    from oracle import vec
+
+    steps = []
+    for k in range(6):
+        st = make_step("planning", seed=40 + k, n_obstacles=3 + k % 3, nv=6, nd=9)
+        st.goal = GoalContext(polygons=[[(20.0 + k, -1.0), (60.0, -1.0), (60.0, 6.0), (20.0 + k, 6.0)]], velocity=(4.0, 25.0),
+                              time_step=(5 + k, 40), ego_time_step=k, ego_position=tuple(st.ego_position), goal_centers=[(40.0, 2.0)])
+        steps.append(st)
+    tris = road_boundary_triangles(steps[0].csp, s_end=140.0)
+    ctx = ScoringContext(0, "fp32")
+    try:
+        ctx.set_params(steps[0].params, steps[0].vehicle, steps[0].mode)
+        ctx.set_road_boundary(tris, "swept")
+        bests = ctx.plan_batch(steps)
+        for st, b in zip(steps, bests):
+            st.road_boundary = (tris, "swept")
+            ref = vec.score_dense(st)
+            assert b["level"] == ref["best"]["level"]
+            if b["index"] != ref["best"]["index"]:
+                d = ref["dense_index"].tolist()
+                assert abs(ref["cost"][12][d.index(b["index"])] - ref["best"]["cost"]) <= 1e-4 * abs(ref["best"]["cost"]) + 1e-7
+    finally:
+        ctx.close()
