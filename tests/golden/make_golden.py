@@ -213,13 +213,30 @@ def cases():
     s = mk("cfg1", seed=111)
     s.velocity_cost_mode, s.cost_factor = 1, 0.01
     out["velmode1_factor"] = s
+    # scenes of tests/test_gpu_random_scenes.py on a thinned grid: reference paths in every direction -- seeds 0, 3, 6, 9,
+    # 12 run along the +-pi cut of the heading, so the ego-side impact angle leaves (-pi, pi] (quirk Q4) --, obstacles
+    # with arbitrary headings (static ones keep an initial orientation outside (-pi, pi]), correlations up to +-0.9, all
+    # five harm models (seed % 5), ragged prediction lengths, low- and high-speed lateral modes
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_scenes", os.path.join(os.path.dirname(HERE), "test_gpu_random_scenes.py"))
+    scenes = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scenes)
+    for seed in (0, 1, 2, 3, 5, 6, 9, 12):
+        s = scenes.random_scene(seed)
+        s.v_list = np.ascontiguousarray(s.v_list[::2])
+        s.d_list = np.linspace(-3.0, 3.0, 13)
+        out[f"scene_{seed:02d}"] = s
     return out
 
 
 def main():
     if not ref_shim.available():
         raise SystemExit("reference tree not available: fixtures can only be generated in the build container")
+    only_missing = "--only-missing" in sys.argv
     for name, step in cases().items():
+        if only_missing and os.path.exists(os.path.join(HERE, f"case_{name}.npz")):
+            continue
         fp_list, valid, invalid, best, prob_log = run_reference(step)
         data = pack_inputs(step)
         data.update(densify(step, fp_list, valid, invalid, best, prob_log))

@@ -9,7 +9,9 @@ from oracle import bvn, port
 FAST = ["cfg1_ethical", "cfg1_ego", "cfg1_standard", "lowspeed_0p5", "lowspeed_2p9", "fast_30", "vmax_clamped",
         "multi_t", "short_pred", "long_pred", "no_obstacles", "max_risk_level3", "harm_lr1s", "harm_lr12s",
         "harm_lr12a", "harm_lr4a", "mahalanobis", "multi_cost_fn", "jerk_travelled", "velmode1_factor",
-        "planning_15x15"]
+        "planning_15x15",
+        # random scenes: paths in every direction (00, 03, 06, 09, 12 along the +-pi cut: un-wrapped impact angles, Q4)
+        "scene_00", "scene_01", "scene_02", "scene_03", "scene_05", "scene_06", "scene_09", "scene_12"]
 
 
 def test_every_fixture_is_listed():
