@@ -4,9 +4,11 @@ fp64 restatement of the collision test of a candidate trajectory against the pre
 level 1): ``collision_valid`` / ``create_collision_object`` (validity_checks.py:125-141, 216-274) and
 ``collision_checker_prediction`` (prediction_helpers.py:138-210).
 
-PARITY UNPINNED: the geometry itself is pycrcc's (commonroad-drivability-checker, not vendored in the reference and
-not installable here).  What the reference's own sources fix is restated exactly -- which boxes exist, their half
-extents, orientations and time steps:
+PARITY: the geometry primitives are pycrcc's (commonroad-drivability-checker, not vendored in the reference and not
+installable here) -- the box-overlap primitive and the ``swept`` hull are UNPINNED.  Everything the reference's own sources
+decide is pinned by fixtures the reference's functions wrote under oracle/ref_shim.py with stand-ins for those primitives
+only (tests/golden/make_golden_collision.py -> collision_cases.npz, make_golden_boundary.py -> boundary_cases.npz:
+``mode="discrete"``) -- which boxes exist, their half extents, orientations and time steps:
 
 * ego:  ``RectOBB(l / 2, w / 2, yaw[i], x[i], y[i])`` for every sample i of the candidate, object starts at
   ``ego_state.time_step`` (validity_checks.py:127-133);

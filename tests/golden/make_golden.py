@@ -34,7 +34,7 @@ REASONS = ("", "velocity", "acceleration", "curvature (lvc)", "curvature (hvc)",
            "boundaries", "max_risk")
 
 
-def run_reference(step):
+def run_reference(step, road_boundary=None, time_step=0, collision_checker=None):
     """One planning step through the reference's own functions; returns dense arrays."""
     ns = ref_shim.load_reference()
     ff = ns.frenet_functions
@@ -62,7 +62,7 @@ def run_reference(step):
     for i, fp in enumerate(fp_list):
         fp._gen_index = i
     scenario = ref_shim.ScenarioStub(ns, step.obstacle_types)
-    ego_state = ref_shim.EgoStateStub(step.ego_position, step.ego_orientation, 0, step.c_s_d, step.c_s_dd)
+    ego_state = ref_shim.EgoStateStub(step.ego_position, step.ego_orientation, time_step, step.c_s_d, step.c_s_dd)
     # the probability arrays are not kept by calc_risk: capture them
     prob_log = {}
     cp = ns.collision_probability
@@ -87,8 +87,8 @@ def run_reference(step):
         valid, invalid, _ = ff.sort_frenet_trajectories(
             ego_state=ego_state, fp_list=fp_list, global_path=None, predictions=step.predictions,
             mode=step.mode, params=step.params, planning_problem=None, scenario=scenario,
-            vehicle_params=vp, ego_id=1, dt=step.dt, sensor_radius=50.0, road_boundary=None,
-            collision_checker=None, goal_area=None)
+            vehicle_params=vp, ego_id=1, dt=step.dt, sensor_radius=50.0, road_boundary=road_boundary,
+            collision_checker=collision_checker, goal_area=None)
     finally:
         rc.get_collision_probability_fast = orig
         rc.get_inv_mahalanobis_dist = orig_m

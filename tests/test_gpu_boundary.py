@@ -127,3 +127,35 @@ def test_drop_in_sort_with_a_road_boundary_object():
     got = [fp.valid_level for fp in fp_list]
     assert got == [want[i] for i in sorted(want)]
     assert 0 < len(vd[2]) < len(fp_list)
+
+
+def test_against_the_reference_written_fixtures():
+    """boundary_cases.npz: the reference's own sort_frenet_trajectories with a road boundary (stand-in pycrcc primitives)
+    decided boundary harm, levels, costs and the winner."""
+    import importlib.util
+    import os
+
+    from ethicaltrajectoryplanning_b200 import _abi
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_mgb", os.path.join(here, "golden", "make_golden_boundary.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(here, "golden", "boundary_cases.npz"))
+    for name, step, _ in mod.boundary_cases():
+        for precision, rtol in (("fp32", 2e-4), ("fp64", 1e-9)):
+            ctx = ScoringContext(0, precision)
+            try:
+                res = ctx.plan(step)
+                out = res.numpy()
+                keep = out["level"] != _abi.LEVEL_SKIPPED
+                np.testing.assert_array_equal(out["level"][keep].astype(np.int64), z[f"{name}_level"], err_msg=f"{name} {precision}")
+                np.testing.assert_array_equal(out["reason"][keep].astype(np.int64), z[f"{name}_reason"], err_msg=f"{name} {precision}")
+                if step.predictions is not None:
+                    np.testing.assert_allclose(out["bd_harm"][keep], z[f"{name}_bd"], rtol=1e-12, atol=0)
+                top = z[f"{name}_level"] == z[f"{name}_level"].max()
+                np.testing.assert_allclose(out["cost"][12, keep][top], z[f"{name}_cost"][top], rtol=rtol, atol=1e-6)
+                assert res.best["list_index"] == int(z[f"{name}_best"])
+            finally:
+                ctx.close()

@@ -116,3 +116,31 @@ def test_given_trajectories_with_device_collision_check(mode):
             np.testing.assert_array_equal(np.asarray(res.level).astype(np.int64), want, err_msg=precision)
         finally:
             ctx.close()
+
+
+def test_discrete_mode_against_the_reference_written_fixtures():
+    """collision_cases.npz: the reference's own create_collision_object + collision_checker_prediction (fallback branch,
+    stand-in pycrcc primitives) decided which candidates collide."""
+    import importlib.util
+
+    from ethicaltrajectoryplanning_b200 import _abi
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_mgc", os.path.join(here, "golden", "make_golden_collision.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(here, "golden", "collision_cases.npz"))
+    for name, step, _ in mod.collision_cases():
+        want = z[name].astype(bool)
+        _with_mode(step, "discrete")
+        for precision in ("fp32", "fp64"):
+            ctx = ScoringContext(0, precision)
+            try:
+                lvl = ctx.plan(step).numpy()["level"]
+                lvl = lvl[lvl != _abi.LEVEL_SKIPPED].astype(np.int64)
+                assert len(lvl) == len(want)
+                # level 0 (velocity / curvature) is decided before the collision test
+                np.testing.assert_array_equal(lvl[lvl > 0] == 1, want[lvl > 0], err_msg=f"{name} {precision}")
+            finally:
+                ctx.close()

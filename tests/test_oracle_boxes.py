@@ -106,3 +106,71 @@ def test_road_boundary_loop_form_equals_vectorised_form():
         assert 0 < np.sum(lv == 2) < len(lv)
         bd = np.array([fp.bd_harm for fp in fps], dtype=np.float64)
         assert np.all((bd > 0) == (lv == 2) | ((bd > 0) & (lv < 2)))
+
+
+def _collision_cases():
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "_mgc", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_collision.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collision_cases.npz"))
+    return [(name, step, z[name].astype(bool)) for name, step, _ in mod.collision_cases()]
+
+
+def test_discrete_mode_matches_the_reference_s_own_call_sequence():
+    """tests/golden/collision_cases.npz was written by the reference's create_collision_object +
+    collision_checker_prediction (fallback branch) with stand-in pycrcc primitives: box set, half extents, orientations,
+    time alignment and pred_length are the reference's."""
+    from oracle import port, vec
+
+    n_hit = n_all = 0
+    for name, step, want in _collision_cases():
+        fps = port.calc_frenet_trajectories(step.c_s, step.c_s_d, step.c_s_dd, step.c_d, step.c_d_d, step.c_d_dd, step.d_list,
+                                            step.t_list, step.v_list, step.dt, step.csp, step.v_thr)
+        got = np.array([boxes.collides_with_predictions(fp.x, fp.y, fp.yaw, step.predictions, step.vehicle.l, step.vehicle.w,
+                                                        "discrete") for fp in fps])
+        np.testing.assert_array_equal(got, want, err_msg=name)
+        step.params = copy.deepcopy(step.params)
+        step.params["modes"]["collision_check_device"] = "discrete"
+        ref = vec.score_dense(step)
+        live = ref["level"] != vec.LEVEL_SKIPPED
+        lvl = ref["level"][live]
+        # level 0 (velocity / curvature) is decided before the collision test
+        np.testing.assert_array_equal(lvl[lvl > 0] == 1, want[lvl > 0], err_msg=name)
+        n_hit += int(want.sum())
+        n_all += len(want)
+    assert 0.3 < n_hit / n_all < 0.8
+
+
+def _boundary_cases():
+    import importlib.util
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_mgb", os.path.join(here, "golden", "make_golden_boundary.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(here, "golden", "boundary_cases.npz"))
+    return [(name, step, {k: z[f"{name}_{k}"] for k in ("bd", "level", "reason", "cost", "best")}) for name, step, _ in mod.boundary_cases()]
+
+
+def test_road_boundary_matches_the_reference_s_own_sort():
+    """tests/golden/boundary_cases.npz: the reference's whole sort_frenet_trajectories with a road boundary (stand-in
+    pycrcc primitives): boundary harm, level 2, costs, selection."""
+    from oracle import port, vec
+
+    for name, step, want in _boundary_cases():
+        best, valid, invalid, fps = port.plan_step(step)
+        np.testing.assert_array_equal([fp.valid_level for fp in fps], want["level"], err_msg=name)
+        np.testing.assert_array_equal([port.REASONS.index(fp.reason_invalid) for fp in fps], want["reason"], err_msg=name)
+        if step.predictions is not None:
+            np.testing.assert_allclose([float(fp.bd_harm) for fp in fps], want["bd"], rtol=1e-13, atol=0, err_msg=name)
+        np.testing.assert_allclose([float(fp.cost) for fp in fps], want["cost"], rtol=1e-12, atol=1e-14, err_msg=name)
+        assert fps.index(best) == int(want["best"])
+        ref = vec.score_dense(step)
+        live = ref["level"] != vec.LEVEL_SKIPPED
+        np.testing.assert_array_equal(ref["level"][live], want["level"], err_msg=name)
+        assert ref["best"]["list_index"] == int(want["best"])
