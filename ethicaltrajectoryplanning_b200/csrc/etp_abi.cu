@@ -567,6 +567,17 @@ static int stage_goal(etp_ctx* c, const etp_goal* g, double dt, int Tmax, DevGoa
     d.poly_start = reinterpret_cast<const int*>(base);
     d.verts = reinterpret_cast<const double*>(base + b_start_pad);
     d.circles = reinterpret_cast<const double*>(base + b_start_pad + b_vert);
+    d.bx0 = d.by0 = INFINITY;
+    d.bx1 = d.by1 = -INFINITY;
+    for (int i = 0; i < n_vert; ++i) {
+        d.bx0 = std::fmin(d.bx0, g->vertices[2 * i]); d.bx1 = std::fmax(d.bx1, g->vertices[2 * i]);
+        d.by0 = std::fmin(d.by0, g->vertices[2 * i + 1]); d.by1 = std::fmax(d.by1, g->vertices[2 * i + 1]);
+    }
+    for (int k = 0; k < d.n_circ; ++k) {
+        const double* q = g->circles + 3 * k;
+        d.bx0 = std::fmin(d.bx0, q[0] - q[2]); d.bx1 = std::fmax(d.bx1, q[0] + q[2]);
+        d.by0 = std::fmin(d.by0, q[1] - q[2]); d.by1 = std::fmax(d.by1, q[1] + q[2]);
+    }
     d.has_vel = g->has_velocity ? 1 : 0;
     d.v_lo = g->velocity_start;
     d.v_hi = g->velocity_end;

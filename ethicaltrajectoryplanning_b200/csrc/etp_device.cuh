@@ -85,21 +85,28 @@ struct DevGoal {
     int has_vel, has_ori, ori_invert;
     double v_lo, v_hi, vel_mid;
     double o_lo, o_hi;       // check_orientation's normalised, sorted interval; ori_invert: exactly one end was folded
+    double bx0, bx1, by0, by1; // bounding box of the goal area: points outside it are outside every shape
     int time_first;          // first sample index whose time step lies inside the goal's time window (INT_MAX: none)
     int ego_in_goal;         // reached_target_position(ego_state.position)
     int vel_kind;            // outside the goal at sample 0: 0 |vel_out - mean v|, 1 30 - mean v, 3 zero
     double vel_out;          // avg_dist / remaining_time
 };
 
-// even-odd containment of (x, y) in the union of the goal's polygons and circles
+// even-odd containment of (x, y) in the union of the goal's polygons and circles.  The crossing test
+// x < xi + (xj - xi) (y - yi) / (yj - yi) is evaluated without the division (multiplied through by yj - yi, the
+// inequality turned for a negative one).
 __host__ __device__ inline bool point_in_goal(const DevGoal& g, const int* poly_start, const double* verts, const double* circles,
                                               double x, double y) {
+    if (x < g.bx0 || x > g.bx1 || y < g.by0 || y > g.by1) return false;
     for (int p = 0; p < g.n_poly; ++p) {
         const int a = poly_start[p], b = poly_start[p + 1];
         bool in = false;
         for (int i = a, j = b - 1; i < b; j = i++) {
             const double xi = verts[2 * i], yi = verts[2 * i + 1], xj = verts[2 * j], yj = verts[2 * j + 1];
-            if (((yi > y) != (yj > y)) && (x < (xj - xi) * (y - yi) / (yj - yi) + xi)) in = !in;
+            if ((yi > y) != (yj > y)) {
+                const double dyj = yj - yi, lhs = (x - xi) * dyj, rhs = (xj - xi) * (y - yi);
+                if (dyj > 0.0 ? lhs < rhs : lhs > rhs) in = !in;
+            }
         }
         if (in) return true;
     }
