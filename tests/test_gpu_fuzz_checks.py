@@ -97,3 +97,47 @@ def test_batched_sweep_honours_goal_and_road_boundary():
                 assert abs(ref["cost"][12][d.index(b["index"])] - ref["best"]["cost"]) <= 1e-4 * abs(ref["best"]["cost"]) + 1e-7
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("seed,offset", [(1, (4.1e5, 5.4e6)), (3, (-7.7e5, 2.2e6)), (6, (3.3e4, -9.1e4))])
+def test_map_coordinates_far_from_the_origin(seed, offset):
+    """UTM-sized map coordinates: the fp32 path works relative to a step origin, so shifting a whole scene (path,
+    predictions, ego, boundary, goal) by hundreds of kilometres changes nothing but the absolute trajectory fields."""
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from ethicaltrajectoryplanning_b200.spline import CubicSpline2D
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext
+    from oracle import vec
+
+    step = scene(seed)
+    dx, dy = offset
+    cx, cy = step.csp.coef_x.copy(), step.csp.coef_y.copy()
+    cx[:, 0] += dx
+    cy[:, 0] += dy
+    step.csp = CubicSpline2D(knots=step.csp.s, coef_x=cx, coef_y=cy)
+    for p in step.predictions.values():
+        p["pos_list"] = np.asarray(p["pos_list"]) + np.array([dx, dy])
+    step.ego_position = np.asarray(step.ego_position) + np.array([dx, dy])
+    step.road_boundary = (step.road_boundary[0] + np.array([dx, dy]), step.road_boundary[1])
+    g = step.goal
+    step.goal = GoalContext(polygons=[np.asarray(q) + np.array([dx, dy]) for q in g.polygons],
+                            circles=None if g.circles is None else [(c[0] + dx, c[1] + dy, c[2]) for c in g.circles],
+                            velocity=g.velocity, orientation=g.orientation, time_step=g.time_step, ego_time_step=g.ego_time_step,
+                            ego_position=tuple(step.ego_position),
+                            goal_centers=None if g.goal_centers is None else [(c[0] + dx, c[1] + dy) for c in g.goal_centers])
+    ref = vec.score_dense(step)
+    live = ref["level"] != vec.LEVEL_SKIPPED
+    # at 10^6 m one fp64 ulp is 2e-10 m; the reference's chained difference quotients over millimetre arclength steps
+    # (creeping profiles) turn that into ~1e-6 rad of heading noise, i.e. ~1e-5 relative on a probability: the fp64
+    # oracle and the fp64 kernel both sit on that floor, the fp32 path must not be worse than its usual bar by more
+    for precision, rtol, ptol in (("fp32", 5e-4, 3e-4), ("fp64", 1e-4, 3e-5)):
+        ctx = ScoringContext(0, precision)
+        try:
+            res = ctx.plan(step)
+            out = res.numpy()
+            np.testing.assert_array_equal(out["level"].astype(np.int64), ref["level"], err_msg=precision)
+            bad = ~(np.abs(out["prob"] - ref["prob"]) <= ptol * np.abs(ref["prob"]) + 1e-9)
+            assert not bad.any(), (precision, np.argwhere(bad)[:4], out["prob"][bad][:4], ref["prob"][bad][:4])
+            np.testing.assert_allclose(out["cost"][:, live], ref["cost"][:, live], rtol=rtol, atol=1e-6, err_msg=precision)
+            assert res.best["level"] == ref["best"]["level"]
+        finally:
+            ctx.close()
