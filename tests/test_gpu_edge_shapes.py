@@ -105,3 +105,35 @@ def test_shapes_beyond_the_limits_fail_loudly():
             ctx.plan(make_step("planning", nv=2, nd=3, n_obstacles=300, t_list=[20.0], seed=5))
     finally:
         ctx.close()
+
+
+def test_malformed_inputs_of_the_optional_checks_fail_loudly():
+    """Bad collision mode, degenerate goal polygon, non-finite boundary vertex, goal without a time step: errors, not
+    silently ignored inputs."""
+    import copy
+
+    from ethicaltrajectoryplanning_b200.scoring import EtpError, ScoringContext
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext, make_step
+
+    ctx = ScoringContext(0, "fp32")
+    try:
+        step = make_step("cfg1", seed=5)
+        step.params = copy.deepcopy(step.params)
+        step.params["modes"]["collision_check_device"] = "sometimes"
+        with pytest.raises(ValueError, match="collision_check_device"):
+            ctx.plan(step)
+        step = make_step("cfg1", seed=5)
+        step.goal = GoalContext(polygons=[[(0.0, 0.0), (1.0, 1.0)]], time_step=(0, 10), ego_position=(0.0, 0.0))
+        with pytest.raises(EtpError, match="fewer than 3 vertices"):
+            ctx.plan(step)
+        tris = np.zeros((2, 3, 2))
+        tris[1, 2, 0] = np.nan
+        with pytest.raises(EtpError, match="not finite"):
+            ctx.set_road_boundary(tris, "swept")
+        with pytest.raises(KeyError):
+            ctx.set_road_boundary(np.zeros((1, 3, 2)), "maybe")
+        # the context still works afterwards
+        step = make_step("cfg1", seed=5)
+        assert ctx.plan(step).best["index"] >= 0
+    finally:
+        ctx.close()
