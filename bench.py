@@ -219,9 +219,12 @@ def run_gpu_arm(args, step, workload_cfg):
             r, n, wall = cpu_rate(step, cores * 64, cores, pool, seed=99)
             target = max(cores, int(r * args.cpu_seconds))
             r, n, wall = cpu_rate(step, target, cores, pool, seed=7)
+            # one core as well (SURVEY.md 8d asks for both): a few seconds on a single worker
+            r1, n1, wall1 = cpu_rate(step, max(4, int(r / cores * 4.0)), 1, pool, seed=8)
         cpu_base = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{n} uniformly sampled candidates of the same planning step in {wall:.1f} s, "
-                              f"oracle/port.py (loop-structured fp64 restatement of the reference) on {cores} processes"}
+                              f"oracle/port.py (loop-structured fp64 restatement of the reference) on {cores} processes",
+                    "one_core": {"value": r1, "unit": UNIT, "sample": f"{n1} candidates in {wall1:.1f} s on 1 process"}}
 
     ctx = ScoringContext(local_rank, "fp32")
     ctx.configure(step)
