@@ -32,9 +32,12 @@ COST_NAMES = ("bayes", "equality", "maximin", "responsibility", "ego", "risk_cos
 REASON_NAMES = ("", "velocity", "acceleration", "curvature (lvc)", "curvature (hvc)", "collision",
                 "boundaries", "max_risk")
 
-_dp = C.POINTER(C.c_double)
-_ip = C.POINTER(C.c_int32)
-_bp = C.POINTER(C.c_uint8)
+# array arguments cross as plain addresses (const double* / const int32_t* / const uint8_t* in the header): an integer
+# from ndarray.ctypes.data is several times cheaper to produce than a typed ctypes pointer, and the closed loop passes a
+# dozen of them per step
+_dp = C.c_void_p
+_ip = C.c_void_p
+_bp = C.c_void_p
 
 
 COLLISION_HOST, COLLISION_DISCRETE, COLLISION_SWEPT = 0, 1, 2

@@ -116,7 +116,7 @@ def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, param
         keep.append(gs)
     if ext_level is not None:
         e = np.ascontiguousarray(ext_level, dtype=np.uint8)
-        g.ext_level = e.ctypes.data_as(C.POINTER(C.c_uint8))
+        g.ext_level = e.ctypes.data
         keep.append(e)
     if bd_harm is not None:
         b = np.ascontiguousarray(bd_harm, dtype=np.float64)

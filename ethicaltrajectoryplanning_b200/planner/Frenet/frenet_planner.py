@@ -106,13 +106,18 @@ class FrenetPlanner:
         if predictions and "orientation_list" not in next(iter(predictions.values())):
             # get_orientation_velocity_and_shape_of_prediction (prediction_helpers.py:75-135) and
             # assign_responsibility_by_action_space (responsibility.py:57-89) on the device, straight into the packed tile
+            # shape, initial state and class of an obstacle do not change during a scenario: looked up once per id
+            static = self.__dict__.setdefault("_obstacle_static", {})
             shapes, ori0, vel0, types = {}, {}, {}, {}
             for oid in predictions:
-                ob = self.scenario.obstacle_by_id(oid)
-                shapes[oid] = (ob.obstacle_shape.length, ob.obstacle_shape.width)
-                ori0[oid] = ob.initial_state.orientation
-                vel0[oid] = ob.initial_state.velocity
-            types = dropin.obstacle_type_names(self.scenario, predictions, self.obstacle_types)
+                st = static.get(oid)
+                if st is None:
+                    ob = self.scenario.obstacle_by_id(oid)
+                    st = static[oid] = ((ob.obstacle_shape.length, ob.obstacle_shape.width), ob.initial_state.orientation,
+                                        ob.initial_state.velocity,
+                                        dropin.obstacle_type_names(self.scenario, {oid: None}, self.obstacle_types)[oid])
+                shapes[oid], ori0[oid], vel0[oid], types[oid] = st
+            self._resident_types = types
             self.ctx.ensure_params(self.params_dict, self.p, self.mode)
             self.ctx.set_raw_predictions(predictions, shapes, ori0, vel0, types, self.scenario.dt,
                                          np.asarray(self.ego_state.position), self.ego_state.orientation)
@@ -174,7 +179,10 @@ class FrenetPlanner:
 
         vel_mode, vel_target, factor = cost_context(None, self.ego_state, self.planning_problem, self.scenario, fpar["dt"],
                                                     self.goal_area)
-        types = dropin.obstacle_type_names(self.scenario, predictions, self.obstacle_types) if predictions else {}
+        if getattr(self, "_resident", False):
+            types = self._resident_types
+        else:
+            types = dropin.obstacle_type_names(self.scenario, predictions, self.obstacle_types) if predictions else {}
         step = PlanningStep(
             c_s=float(c_s), c_s_d=float(c_s_d), c_s_dd=float(c_s_dd), c_d=float(c_d), c_d_d=float(c_d_d),
             c_d_dd=float(c_d_dd), v_list=np.asarray(v_list, dtype=np.float64), t_list=np.asarray(t_list, dtype=np.float64),

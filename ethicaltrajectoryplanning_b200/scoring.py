@@ -31,11 +31,11 @@ class NoCandidateError(ValueError):
 
 
 def _dptr(a):
-    return a.ctypes.data_as(C.POINTER(C.c_double))
+    return a.ctypes.data  # address of a float64 array the caller keeps alive
 
 
 def _iptr(a):
-    return a.ctypes.data_as(C.POINTER(C.c_int32))
+    return a.ctypes.data  # address of an int32 array the caller keeps alive
 
 
 def harm_model_tables(modes, coeffs):
@@ -345,26 +345,42 @@ class ScoringContext:
         O = len(oids)
         lens = np.array([len(predictions[o]["pos_list"]) for o in oids], dtype=np.int32)
         Tp = int(lens.max()) if O else 1
-        pos, cov = np.zeros((O, Tp, 2)), np.zeros((O, Tp, 4))
-        length, width, ori0, vel0, mass = (np.zeros(O) for _ in range(5))
-        prot = np.zeros(O, dtype=np.int32)
+        if O and int(lens.min()) == Tp:  # equally long predictions (the usual predictor output): one stack each
+            pos = np.ascontiguousarray(np.stack([predictions[o]["pos_list"] for o in oids]), dtype=np.float64).reshape(O, Tp, 2)
+            cov = np.ascontiguousarray(np.stack([predictions[o]["cov_list"] for o in oids]), dtype=np.float64).reshape(O, Tp, 4)
+        else:
+            pos, cov = np.zeros((O, Tp, 2)), np.zeros((O, Tp, 4))
+            for j, oid in enumerate(oids):
+                n = lens[j]
+                pos[j, :n] = np.asarray(predictions[oid]["pos_list"], dtype=np.float64).reshape(n, 2)
+                cov[j, :n] = np.asarray(predictions[oid]["cov_list"], dtype=np.float64).reshape(n, 4)
+        # what does not change from cycle to cycle (shape, initial state, class, mass) is kept per obstacle
+        cache = self.__dict__.setdefault("_raw_static", {})
+        static = np.empty((6, O))
         for j, oid in enumerate(oids):
-            n = lens[j]
-            pos[j, :n] = np.asarray(predictions[oid]["pos_list"], dtype=np.float64).reshape(n, 2)
-            cov[j, :n] = np.asarray(predictions[oid]["cov_list"], dtype=np.float64).reshape(n, 4)
-            length[j], width[j] = shapes[oid]
-            ori0[j], vel0[j] = init_orientation[oid], init_velocity[oid]
             if masses is not None:
-                mass[j], prot[j] = masses[oid], int(protections[oid])
+                key = (shapes[oid], init_orientation[oid], init_velocity[oid], masses[oid], int(protections[oid]))
             else:
-                t = getattr(obstacle_types[oid], "name", obstacle_types[oid])
-                if t in PROTECTED_TYPES:
-                    prot[j] = 1
-                elif t in UNPROTECTED_TYPES:
-                    prot[j] = 0
+                key = (shapes[oid], init_orientation[oid], init_velocity[oid], obstacle_types[oid], safety_margin_length, safety_margin_width)
+            hit = cache.get(oid)
+            if hit is None or hit[0] != key:
+                ln, wd = shapes[oid]
+                if masses is not None:
+                    m, pr = masses[oid], int(protections[oid])
                 else:
-                    raise ValueError(f"obstacle type {t!r} has no protection class (harm_estimation.py:52-56)")
-                mass[j] = obstacle_mass(t, (length[j] + safety_margin_length) * (width[j] + safety_margin_width))
+                    t = getattr(obstacle_types[oid], "name", obstacle_types[oid])
+                    if t in PROTECTED_TYPES:
+                        pr = 1
+                    elif t in UNPROTECTED_TYPES:
+                        pr = 0
+                    else:
+                        raise ValueError(f"obstacle type {t!r} has no protection class (harm_estimation.py:52-56)")
+                    m = obstacle_mass(t, (ln + safety_margin_length) * (wd + safety_margin_width))
+                hit = (key, (ln, wd, init_orientation[oid], init_velocity[oid], m, pr))
+                cache[oid] = hit
+            static[:, j] = hit[1]
+        length, width, ori0, vel0, mass = (np.ascontiguousarray(static[k]) for k in range(5))
+        prot = static[5].astype(np.int32)
         r = _abi.RawPredictions()
         r.n_obstacles, r.max_pred = O, Tp
         r.pred_len, r.pos, r.cov = _iptr(lens), _dptr(pos), _dptr(cov)
@@ -396,8 +412,10 @@ class ScoringContext:
 
     def ensure_params(self, params, vehicle, mode="risk"):
         """set_params unless the same parameter objects with the same content are already on the device."""
-        pkey = (id(params), id(vehicle), mode, repr(sorted(params["weights"].items())),
-                repr(sorted((k, v) for k, v in params["modes"].items() if not isinstance(v, dict))))
+        # identity of the objects plus their scalar content (dict order is stable): cheap enough for every cycle of a
+        # closed loop, and an in-place edit of a weight or a mode still triggers the upload
+        pkey = (id(params), id(vehicle), mode, tuple(params["weights"].values()),
+                tuple(v for v in params["modes"].values() if not isinstance(v, dict)))
         if getattr(self, "_params_key", None) != pkey:
             self.set_params(params, vehicle, mode)
             self._params_key = pkey
@@ -438,7 +456,7 @@ class ScoringContext:
         keep = [v, t, d, n]
         if step.ext_level is not None:
             e = np.ascontiguousarray(step.ext_level, dtype=np.uint8)
-            s.ext_level = e.ctypes.data_as(C.POINTER(C.c_uint8))
+            s.ext_level = e.ctypes.data
             keep.append(e)
         if step.bd_harm is not None:
             b = np.ascontiguousarray(step.bd_harm, dtype=np.float64)
