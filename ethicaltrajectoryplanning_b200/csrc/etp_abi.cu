@@ -14,20 +14,29 @@ namespace {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool view = false;  // p points into another buffer (stage_group): not owned, never freed here
     cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (!view && bytes <= cap) return cudaSuccess;
+        if (p && !view) cudaFree(p);
         p = nullptr;
         cap = 0;
+        view = false;
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    void set_view(void* q) {
+        if (p && !view) cudaFree(p);
+        p = q;
+        cap = 0;
+        view = true;
+    }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !view) cudaFree(p);
         p = nullptr;
         cap = 0;
+        view = false;
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -77,6 +86,8 @@ struct etp_ctx {
     // step
     DevBuf grids, ext_level, bd_harm, factor_list, goal_geom, prof, prof_meta, nskip;
     DevBuf rb_tri, rb_trif, rb_start, rb_items;  // etp_set_road_boundary
+    DevBuf obs_blob;                 // the input arrays of etp_set_obstacles / etp_set_raw_predictions, one upload
+    std::vector<unsigned char> group_host;
     DevBoundary boundary{};
     DevBuf block_best, counters, best_dev, traj_dev, traj_n, given, given_T, prin;
     bool last_given = false;
@@ -136,6 +147,28 @@ int begin_staging(etp_ctx*) { return ETP_OK; }
 
 int end_staging(etp_ctx*) { return ETP_OK; }
 
+// Several small host arrays -> ONE device blob with ONE copy (a copy costs a few microseconds of host and stream time
+// whatever its size; a closed loop uploads nine arrays per cycle).  Every item becomes a view into the blob.
+struct GroupItem {
+    DevBuf* buf;
+    const void* src;
+    size_t bytes;
+};
+
+int stage_group(etp_ctx* c, DevBuf& blob, std::initializer_list<GroupItem> items) {
+    size_t total = 0;
+    for (const GroupItem& it : items) total += (it.bytes + 255) & ~size_t(255);
+    ETP_CUDA(c, blob.reserve(total));
+    c->group_host.resize(total);
+    size_t off = 0;
+    for (const GroupItem& it : items) {
+        memcpy(c->group_host.data() + off, it.src, it.bytes);
+        it.buf->set_view(static_cast<unsigned char*>(blob.p) + off);
+        off += (it.bytes + 255) & ~size_t(255);
+    }
+    return stage_to_device(c, blob.p, c->group_host.data(), total);
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,7 +208,7 @@ int etp_destroy(etp_ctx* c) {
     c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
-                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom, &c->rb_tri, &c->rb_trif, &c->rb_start, &c->rb_items,
+                      &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom, &c->rb_tri, &c->rb_trif, &c->rb_start, &c->rb_items, &c->obs_blob,
                       &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
                       &c->traj_n, &c->given, &c->given_T, &c->prin};
     for (DevBuf* b : bufs) b->release();
@@ -398,28 +431,15 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
                 c->obs_box[0] = std::fmin(c->obs_box[0], q[0]); c->obs_box[1] = std::fmax(c->obs_box[1], q[0]);
                 c->obs_box[2] = std::fmin(c->obs_box[2], q[1]); c->obs_box[3] = std::fmax(c->obs_box[3], q[1]);
             }
-        ETP_CUDA(c, c->o_pos.reserve(sizeof(double) * 2 * n));
-        ETP_CUDA(c, c->o_cov.reserve(sizeof(double) * 4 * n));
-        ETP_CUDA(c, c->o_yaw.reserve(sizeof(double) * n));
-        ETP_CUDA(c, c->o_vel.reserve(sizeof(double) * n));
-        ETP_CUDA(c, c->o_len.reserve(sizeof(double) * O));
-        ETP_CUDA(c, c->o_wid.reserve(sizeof(double) * O));
-        ETP_CUDA(c, c->o_mass.reserve(sizeof(double) * O));
-        ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
-        ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
-        ETP_CUDA(c, c->o_resp.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_tile.reserve(Tile<double>::bytes(O, Tp)));
         ETP_CUDA(c, c->o_const.reserve(sizeof(double) * OC_COUNT * O));
-        if ((r = stage_to_device(c, c->o_pos.p, o->pos, sizeof(double) * 2 * n))) return r;
-        if ((r = stage_to_device(c, c->o_cov.p, o->cov, sizeof(double) * 4 * n))) return r;
-        if ((r = stage_to_device(c, c->o_yaw.p, o->yaw, sizeof(double) * n))) return r;
-        if ((r = stage_to_device(c, c->o_vel.p, o->vel, sizeof(double) * n))) return r;
-        if ((r = stage_to_device(c, c->o_len.p, o->length, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_wid.p, o->width, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_mass.p, o->mass, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_plen.p, o->pred_len, sizeof(int) * O))) return r;
-        if ((r = stage_to_device(c, c->o_prot.p, o->is_protected, sizeof(int) * O))) return r;
-        if ((r = stage_to_device(c, c->o_resp.p, o->responsibility, sizeof(int) * O))) return r;
+        if ((r = stage_group(c, c->obs_blob,
+                             {{&c->o_pos, o->pos, sizeof(double) * 2 * n}, {&c->o_cov, o->cov, sizeof(double) * 4 * n},
+                              {&c->o_yaw, o->yaw, sizeof(double) * n}, {&c->o_vel, o->vel, sizeof(double) * n},
+                              {&c->o_len, o->length, sizeof(double) * O}, {&c->o_wid, o->width, sizeof(double) * O},
+                              {&c->o_mass, o->mass, sizeof(double) * O}, {&c->o_plen, o->pred_len, sizeof(int) * O},
+                              {&c->o_prot, o->is_protected, sizeof(int) * O}, {&c->o_resp, o->responsibility, sizeof(int) * O}})))
+            return r;
         if ((r = end_staging(c))) return r;
         ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
@@ -466,26 +486,20 @@ int etp_set_raw_predictions(etp_ctx* c, const etp_raw_predictions* o, int precis
                 c->obs_box[0] = std::fmin(c->obs_box[0], q[0]); c->obs_box[1] = std::fmax(c->obs_box[1], q[0]);
                 c->obs_box[2] = std::fmin(c->obs_box[2], q[1]); c->obs_box[3] = std::fmax(c->obs_box[3], q[1]);
             }
-        ETP_CUDA(c, c->o_pos.reserve(sizeof(double) * 2 * n));
-        ETP_CUDA(c, c->o_cov.reserve(sizeof(double) * 4 * n));
         ETP_CUDA(c, c->o_yaw.reserve(sizeof(double) * n));
         ETP_CUDA(c, c->o_vel.reserve(sizeof(double) * n));
-        DevBuf* per_o[] = {&c->o_len, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->o_mass};
-        for (DevBuf* b : per_o) ETP_CUDA(c, b->reserve(sizeof(double) * O));
-        ETP_CUDA(c, c->o_plen.reserve(sizeof(int) * O));
-        ETP_CUDA(c, c->o_prot.reserve(sizeof(int) * O));
+        ETP_CUDA(c, c->o_len.reserve(sizeof(double) * O));
+        ETP_CUDA(c, c->o_wid.reserve(sizeof(double) * O));
         ETP_CUDA(c, c->o_resp.reserve(sizeof(int) * O));
         ETP_CUDA(c, c->o_tile.reserve(Tile<double>::bytes(O, Tp)));
         ETP_CUDA(c, c->o_const.reserve(sizeof(double) * OC_COUNT * O));
-        if ((r = stage_to_device(c, c->o_pos.p, o->pos, sizeof(double) * 2 * n))) return r;
-        if ((r = stage_to_device(c, c->o_cov.p, o->cov, sizeof(double) * 4 * n))) return r;
-        if ((r = stage_to_device(c, c->o_rawlen.p, o->length, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_rawwid.p, o->width, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_ori0.p, o->init_orientation, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_vel0.p, o->init_velocity, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_mass.p, o->mass, sizeof(double) * O))) return r;
-        if ((r = stage_to_device(c, c->o_plen.p, o->pred_len, sizeof(int) * O))) return r;
-        if ((r = stage_to_device(c, c->o_prot.p, o->is_protected, sizeof(int) * O))) return r;
+        if ((r = stage_group(c, c->obs_blob,
+                             {{&c->o_pos, o->pos, sizeof(double) * 2 * n}, {&c->o_cov, o->cov, sizeof(double) * 4 * n},
+                              {&c->o_rawlen, o->length, sizeof(double) * O}, {&c->o_rawwid, o->width, sizeof(double) * O},
+                              {&c->o_ori0, o->init_orientation, sizeof(double) * O}, {&c->o_vel0, o->init_velocity, sizeof(double) * O},
+                              {&c->o_mass, o->mass, sizeof(double) * O}, {&c->o_plen, o->pred_len, sizeof(int) * O},
+                              {&c->o_prot, o->is_protected, sizeof(int) * O}})))
+            return r;
         if ((r = end_staging(c))) return r;
         ETP_CUDA(c, launch_enrich(O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_rawlen.as<double>(), c->o_rawwid.as<double>(),
                                   c->o_ori0.as<double>(), c->o_vel0.as<double>(), o->dt, o->safety_margin_length,
