@@ -56,6 +56,29 @@ def profiled_traffic(workload):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle's loop-structured port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout as
+    soon as NCCL_DEBUG is set, here or by the launcher), so the real stdout is set aside for the result line and file
+    descriptor 1 is pointed at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def _cpu_worker(sub):
     from oracle import bvn, port
 
@@ -132,7 +155,7 @@ def run_reference_arm(args, step, workload_cfg):
                                    f"({tot_n} scored in {tot_t:.1f} s), oracle/port.py on {cores} processes"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -206,7 +229,7 @@ def run_gpu_arm(args, step, workload_cfg):
             raise SystemExit("launch N > 1 with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # its banner goes to the diverted descriptor (claim_stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cpu_base = None
@@ -332,7 +355,7 @@ def run_gpu_arm(args, step, workload_cfg):
             "cpu_baseline": cpu_base,
             "extras": extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -353,7 +376,7 @@ def run_sweep_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ScoringContext(local_rank, "fp32")
     ids = scenario_shard(args.scenarios, rank, world)
@@ -409,7 +432,7 @@ def run_sweep_arm(args):
                 "e2e": {"value": float(tot[0].item()) / e2e_sec, "unit": UNIT, "scenarios_per_sec": float(tot[1].item()) / e2e_sec,
                         "note": "including the Python-side packing of the prediction dicts into the ABI structs"},
                 "timing": "wall clock around etp_plan_batch calls (uploads + 3 launches per scenario + readback), max over ranks"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -577,6 +600,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
 
     from ethicaltrajectoryplanning_b200.synthetic import GRIDS, make_step
 
