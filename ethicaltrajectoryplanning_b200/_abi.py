@@ -42,6 +42,8 @@ _bp = C.c_void_p
 
 COLLISION_HOST, COLLISION_DISCRETE, COLLISION_SWEPT = 0, 1, 2
 COLLISION_CODES = {"host": COLLISION_HOST, "discrete": COLLISION_DISCRETE, "swept": COLLISION_SWEPT}
+# ETP_RELAX_* bits (include/etp_b200.h): opt-outs of reference quirks, strict reproduction is the default
+RELAX_BITS = {"curvature_denominator": 1, "acceleration_check": 2, "maximin_gate": 4, "view_cone_wrap": 8}
 
 
 class Params(C.Structure):
@@ -61,7 +63,7 @@ class Params(C.Structure):
         ("veh_l", C.c_double), ("veh_w", C.c_double), ("veh_l_r", C.c_double), ("veh_m", C.c_double),
         ("veh_steer_max", C.c_double), ("veh_lat_a_max", C.c_double), ("veh_v_max", C.c_double),
         ("veh_a_max", C.c_double),
-        ("collision_check", C.c_int32), ("reserved0", C.c_int32),
+        ("collision_check", C.c_int32), ("relaxed_quirks", C.c_int32),
     ]
 
 

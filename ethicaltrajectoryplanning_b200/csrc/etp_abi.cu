@@ -264,6 +264,9 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
     d.lr1s_const = p->lr1s_const; d.lr1s_speed = p->lr1s_speed;
     d.ped_const = p->ped_const; d.ped_speed = p->ped_speed;
     d.veh_l = p->veh_l; d.veh_w = p->veh_w; d.veh_m = p->veh_m; d.v_max = p->veh_v_max;
+    if (p->relaxed_quirks < 0 || p->relaxed_quirks > 15) ETP_FAIL(c, ETP_ERR_INVALID, "relaxed_quirks");
+    d.relaxed = p->relaxed_quirks;
+    d.a_max = p->veh_a_max;
     // validity_checks.py:193-199
     const double tn = std::tan(p->veh_steer_max);
     const double radius = std::sqrt((p->veh_l * p->veh_l / (tn * tn)) + (p->veh_l_r * p->veh_l_r));
@@ -503,7 +506,7 @@ int etp_set_raw_predictions(etp_ctx* c, const etp_raw_predictions* o, int precis
         if ((r = end_staging(c))) return r;
         ETP_CUDA(c, launch_enrich(O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_rawlen.as<double>(), c->o_rawwid.as<double>(),
                                   c->o_ori0.as<double>(), c->o_vel0.as<double>(), o->dt, o->safety_margin_length,
-                                  o->safety_margin_width, o->ego_x, o->ego_y, o->ego_orientation, c->o_yaw.as<double>(),
+                                  o->safety_margin_width, o->ego_x, o->ego_y, o->ego_orientation, (c->pr.relaxed & ETP_RELAX_Q9_VIEW_CONE) != 0, c->o_yaw.as<double>(),
                                   c->o_vel.as<double>(), c->o_len.as<double>(), c->o_wid.as<double>(), c->o_resp.as<int>(), c->stream));
         ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
@@ -884,7 +887,7 @@ int etp_principle_costs(etp_ctx* c, int n, const double* ego_risk, const double*
         if ((r = stage_to_device(c, resp, responsibility, sizeof(int) * (size_t)n))) return r;
     }
     if ((r = end_staging(c))) return r;
-    ETP_CUDA(c, launch_principles(n, vals, resp, boundary_harm, maximin_eps, maximin_scale, res, c->stream));
+    ETP_CUDA(c, launch_principles(n, vals, resp, boundary_harm, maximin_eps, maximin_scale, (c->pr.relaxed & ETP_RELAX_Q3_MAXIMIN) != 0, res, c->stream));
     ETP_CUDA(c, c->traj_host.reserve(5 * sizeof(double)));
     ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, res, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -59,6 +59,8 @@ struct DevParams {
     double w[ETP_NUM_WEIGHTS];
     int planner_mode, mahalanobis, multi_cost, n_thr;
     int collision_check;  // ETP_COLLISION_*, already 0 when the planner mode does not test predictions
+    int relaxed;          // ETP_RELAX_* bits (0: strict reference behaviour)
+    double a_max;         // vehicle_params.longitudinal.a_max (ETP_RELAX_Q2_ACCELERATION)
     double max_risk;
     double thr[ETP_MAX_ANGLE_BINS];
     double fcos[ETP_MAX_ANGLE_BINS];  // cos(thr) * |cos(thr)|: band tests on direction vectors (fp32 path)

@@ -142,7 +142,7 @@ __device__ __forceinline__ double np_gradient(const double* f, const double* s, 
 __global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
                                                      const double* __restrict__ raw_len, const double* __restrict__ raw_wid,
                                                      const double* __restrict__ ori0, const double* __restrict__ vel0, double dt,
-                                                     double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori,
+                                                     double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori, bool wrap_view_cone,
                                                      double* __restrict__ yaw, double* __restrict__ vel, double* __restrict__ length,
                                                      double* __restrict__ width, int* __restrict__ resp) {
     extern __shared__ double sm[];
@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* _
         // check_if_inside180view (responsibility.py:78-89)
         const double ang = atan2(p[1] - ego_y, p[0] - ego_x);
         const double quarter = 3.14159265358979323846 / 4;
-        resp[o] = (ego_ori - quarter <= ang && ang <= ego_ori + quarter) ? 0 : 1;
+        double rel = ang - ego_ori;  // the reference compares ang with ego_ori -+ pi/4 as they are (quirk Q9)
+        if (wrap_view_cone) rel = remainder(rel, 2.0 * 3.14159265358979323846);  // ETP_RELAX_Q9_VIEW_CONE: modulo 2 pi
+        resp[o] = wrap_view_cone ? ((-quarter <= rel && rel <= quarter) ? 0 : 1)
+                                 : ((ego_ori - quarter <= ang && ang <= ego_ori + quarter) ? 0 : 1);
     }
 }
 
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
     const double a3 = (3.0 * b1 - b2 * Te) / (3.0 * Te * Te);
     const double a4 = (b2 * Te - 2.0 * b1) / (4.0 * Te * Te * Te);
 
-    int vel_ok = 1;
+    int vel_ok = 1, acc_ok = 1;
     for (int t = tid; t < T; t += blockDim.x) {
         const double tt = t * st.dt;
         const double t2 = tt * tt, t3 = t2 * tt, t4 = t2 * t2;
@@ -259,11 +262,14 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
         s_s[t] = s;
         pf[PF_S * Tmax + t] = s;
         pf[PF_S_D * Tmax + t] = sd;
-        pf[PF_S_DD * Tmax + t] = 2 * a2 + 6 * a3 * tt + 12 * a4 * t2;
+        const double sdd = 2 * a2 + 6 * a3 * tt + 12 * a4 * t2;
+        pf[PF_S_DD * Tmax + t] = sdd;
         pf[PF_S_DDD * Tmax + t] = 6 * a3 + 24 * a4 * tt;
         if (!(fabs(sd) <= pr.v_max)) vel_ok = 0;  // validity_checks.py:158
+        if ((pr.relaxed & ETP_RELAX_Q2_ACCELERATION) && !(fabs(sdd) <= pr.a_max)) acc_ok = 0;
     }
     vel_ok = __syncthreads_and(vel_ok);
+    acc_ok = __syncthreads_and(acc_ok);
     // reference position: one warp per abscissa, 32-ary segment search (csp.calc_position, :278)
     for (int t = warp; t < T; t += blockDim.x / 32) {
         const double s = s_s[t];
@@ -292,12 +298,12 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
         const double dddx = np_gradient(s_c, s_s, t, T), dddy = np_gradient(s_d, s_s, t, T);  // :293,296
         const double yaw = atan2(dy, dx);  // :302
         // :308-310 -- the denominator is dx^2 + (dy^2)^(3/2) in the reference (operator precedence)
-        const double curv = (dx * ddy - ddx * dy) / (dx * dx + pow(dy * dy, 1.5));
         // :316-325
         const double z = dx * ddy - ddx * dy;
         const double z_d = dx * dddy - dddx * dy;
         const double q = dx * dx + dy * dy;
         const double n = pow(q, 1.5);
+        const double curv = (pr.relaxed & ETP_RELAX_Q1_CURVATURE) ? z / n : (dx * ddy - ddx * dy) / (dx * dx + pow(dy * dy, 1.5));
         const double n_d = 1.5 * (sqrt(q) * (2 * (dx * ddx) + 2 * (dy * ddy)));
         const double curv_d = (z_d * n - z * n_d) / (n * n);
         pf[PF_GX * Tmax + t] = s_x[t];
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
         pm[PM_DS] = s_s[T - 1] - s_s[0];                                                  // :327-328
         pm[PM_LOW] = (fabs(st.c_s_d) < st.v_thr || fabs(vT) < st.v_thr) ? 1.0 : 0.0;  // :248-251
         pm[PM_T] = (double)T;
-        pm[PM_VEL_OK] = (double)vel_ok;
+        pm[PM_VEL_OK] = vel_ok ? (acc_ok ? 1.0 : -1.0) : 0.0;  // 1 fine, 0 velocity, -1 acceleration (relaxed Q2 only)
         pm[PM_TEND] = Te;
     }
     // number of skipped lateral targets of this profile (frenet_functions.py:333-334): rank of the winner in fp_list
@@ -354,7 +360,7 @@ __global__ void trajectory_kernel(DevStep st, int c_dense, double* __restrict__ 
 
 // principle costs of one trajectory from per-obstacle maxima (risk_costs.py:128-255); one warp
 __global__ void principles_kernel(int n, const double* __restrict__ v, const int* __restrict__ resp, double bd, double eps,
-                                  double scale, double* __restrict__ out) {
+                                  double scale, bool relaxed_gate, double* __restrict__ out) {
     const int lane = threadIdx.x;
     double sum_e = 0, sum_o = 0, sum_abs = 0, rs = 0, mm = -INFINITY;
     for (int o = lane; o < n; o += 32) {
@@ -363,8 +369,8 @@ __global__ void principles_kernel(int n, const double* __restrict__ v, const int
         sum_o += ro;
         sum_abs += fabs(re - ro);
         rs -= (double)resp[o] * ro;
-        mm = fmax(mm, he * (re < eps ? 1.0 : 0.0));  // risk_costs.py:205-206 (Q3)
-        mm = fmax(mm, ho * (ro < eps ? 1.0 : 0.0));
+        mm = fmax(mm, he * ((re < eps) != relaxed_gate ? 1.0 : 0.0));  // risk_costs.py:205-206 (Q3)
+        mm = fmax(mm, ho * ((ro < eps) != relaxed_gate ? 1.0 : 0.0));
     }
     for (int k = 16; k > 0; k >>= 1) {
         sum_e += __shfl_xor_sync(kFull, sum_e, k);
@@ -445,17 +451,17 @@ cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, 
 
 cudaError_t launch_enrich(int O, int Tp, const int* pred_len, const double* pos, const double* raw_len, const double* raw_wid,
                           const double* ori0, const double* vel0, double dt, double margin_l, double margin_w, double ego_x,
-                          double ego_y, double ego_ori, double* yaw, double* vel, double* length, double* width, int* resp,
+                          double ego_y, double ego_ori, bool wrap_view_cone, double* yaw, double* vel, double* length, double* width, int* resp,
                           cudaStream_t stream) {
     if (O <= 0) return cudaSuccess;
     enrich_kernel<<<O, 128, sizeof(double) * 3 * Tp, stream>>>(O, Tp, pred_len, pos, raw_len, raw_wid, ori0, vel0, dt, margin_l, margin_w,
-                                                              ego_x, ego_y, ego_ori, yaw, vel, length, width, resp);
+                                                              ego_x, ego_y, ego_ori, wrap_view_cone, yaw, vel, length, width, resp);
     return cudaGetLastError();
 }
 
-cudaError_t launch_principles(int n, const double* vals, const int* resp, double bd, double eps, double scale, double* out5,
-                              cudaStream_t stream) {
-    principles_kernel<<<1, 32, 0, stream>>>(n, vals, resp, bd, eps, scale, out5);
+cudaError_t launch_principles(int n, const double* vals, const int* resp, double bd, double eps, double scale, bool relaxed_gate,
+                              double* out5, cudaStream_t stream) {
+    principles_kernel<<<1, 32, 0, stream>>>(n, vals, resp, bd, eps, scale, relaxed_gate, out5);
     return cudaGetLastError();
 }
 

@@ -27,11 +27,11 @@ cudaError_t read_debug_counters(unsigned long long* out, int n);
 
 cudaError_t launch_enrich(int O, int Tp, const int* pred_len, const double* pos, const double* raw_len, const double* raw_wid,
                           const double* ori0, const double* vel0, double dt, double margin_l, double margin_w, double ego_x,
-                          double ego_y, double ego_ori, double* yaw, double* vel, double* length, double* width, int* resp,
+                          double ego_y, double ego_ori, bool wrap_view_cone, double* yaw, double* vel, double* length, double* width, int* resp,
                           cudaStream_t stream);
 
 cudaError_t launch_principles(int n, const double* vals /*[4][n]*/, const int* resp, double bd, double eps, double scale,
-                              double* out5, cudaStream_t stream);
+                              bool relaxed_gate, double* out5, cudaStream_t stream);
 
 cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsigned char* combo, cudaStream_t stream);
 

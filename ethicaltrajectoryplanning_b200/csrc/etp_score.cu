@@ -1022,7 +1022,10 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             for (int t = ta; t < tb; ++t) {
                 if (t < Tl) {
                     const TrajPoint tp = kGiven ? given_point(gp, Ts, st.given_stride, t) : traj_point(q, low, gp, Ts, t, st.dt);
-                    if (kGiven && !(fabs(tp.f[ETP_F_S_D]) <= pr.v_max)) first_fail = -1;  // validity_checks.py:158
+                    // validity_checks.py:158; -2 velocity, -1 acceleration (ETP_RELAX_Q2_ACCELERATION only): the minimum wins
+                    if (kGiven && (pr.relaxed & ETP_RELAX_Q2_ACCELERATION) && !(fabs(tp.f[ETP_F_S_DD]) <= pr.a_max))
+                        first_fail = min(first_fail, -1);
+                    if (kGiven && !(fabs(tp.f[ETP_F_S_D]) <= pr.v_max)) first_fail = -2;
                     if (o_traj) {
 #pragma unroll
                         for (int f = 0; f < ETP_NUM_FIELDS; ++f) o_traj[((size_t)f * Ts + t) * Cp + cl] = (R)tp.f[f];
@@ -1283,8 +1286,10 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     sum_o += (double)ro;
                     sum_abs += fabs((double)re - (double)ro);
                     resp -= st.obs_const[o * OC_COUNT + OC_RESP] * (double)ro;       // risk_costs.py:250-253
-                    mm = fmax(mm, (double)he * ((double)re < 10e-10 ? 1.0 : 0.0));  // risk_costs.py:205-206 (Q3)
-                    mm = fmax(mm, (double)ho * ((double)ro < 10e-10 ? 1.0 : 0.0));
+                    // risk_costs.py:205-206 keeps the harm where the risk is BELOW eps (Q3); ETP_RELAX_Q3_MAXIMIN turns the gate
+                    const bool gate = (pr.relaxed & ETP_RELAX_Q3_MAXIMIN) != 0;
+                    mm = fmax(mm, (double)he * ((((double)re < 10e-10) != gate) ? 1.0 : 0.0));
+                    mm = fmax(mm, (double)ho * ((((double)ro < 10e-10) != gate) ? 1.0 : 0.0));
                     max_o = fmax(max_o, (double)ro);
                 }
                 if (o_red && active) {
@@ -1322,7 +1327,8 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     max_o = fmax(max_o, p3[P3_MAX_O * 32]);
                     first_fail = min(first_fail, sm.ff[w * 32 + lane]);
                 }
-                const bool vel_ok = kGiven ? first_fail >= 0 : pm[PM_VEL_OK] != 0.0;
+                const bool vel_ok = kGiven ? first_fail != -2 : pm[PM_VEL_OK] != 0.0;
+                const bool acc_ok = kGiven ? first_fail != -1 : !(pm[PM_VEL_OK] < 0.0);  // fails only under ETP_RELAX_Q2_ACCELERATION
                 double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
                 int ext = st.ext_level ? (int)st.ext_level[c_dense] : 10;
                 if (st.boundary.check != ETP_COLLISION_HOST) {
@@ -1388,6 +1394,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 // validity level (validity_checks.py:31-122)
                 const int cf = (first_fail == 0x7fffffff || first_fail < 0) ? 0 : (first_fail & 3);
                 if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
+                else if (!acc_ok) { level = 0; reason = ETP_REASON_ACCELERATION; }
                 else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
                 else if (ext == 1 || s_hit[lane]) { level = 1; reason = ETP_REASON_COLLISION; }
                 else if (st.has_pred ? (bd != 0.0) : (ext == 2)) { level = 2; reason = ETP_REASON_BOUNDARIES; }

@@ -110,6 +110,11 @@ def make_params(params, vehicle, mode="risk") -> _abi.Params:
     if check not in _abi.COLLISION_CODES:
         raise ValueError("modes['collision_check_device'] must be host, discrete or swept")
     p.collision_check = _abi.COLLISION_CODES[check]
+    # extension key: reference quirks to opt out of; none by default = strict reference behaviour
+    for name in modes.get("relaxed_quirks", ()):
+        if name not in _abi.RELAX_BITS:
+            raise ValueError(f"modes['relaxed_quirks']: unknown quirk {name!r} (known: {sorted(_abi.RELAX_BITS)})")
+        p.relaxed_quirks |= _abi.RELAX_BITS[name]
     return p
 
 
@@ -415,7 +420,8 @@ class ScoringContext:
         # identity of the objects plus their scalar content (dict order is stable): cheap enough for every cycle of a
         # closed loop, and an in-place edit of a weight or a mode still triggers the upload
         pkey = (id(params), id(vehicle), mode, tuple(params["weights"].values()),
-                tuple(v for v in params["modes"].values() if not isinstance(v, dict)))
+                tuple(tuple(v) if isinstance(v, (list, tuple, set)) else v for v in params["modes"].values()
+                      if not isinstance(v, dict)))
         if getattr(self, "_params_key", None) != pkey:
             self.set_params(params, vehicle, mode)
             self._params_key = pkey

@@ -91,12 +91,16 @@ def enrich_predictions(predictions, shapes, init_orientation, init_velocity, dt,
     return predictions
 
 
-def assign_responsibility_by_action_space(ego_position, ego_orientation, predictions):
-    """View-cone flag of planner/utils/responsibility.py:57-89 (no angle wrap, quirk Q9)."""
+def assign_responsibility_by_action_space(ego_position, ego_orientation, predictions, wrap=False):
+    """View-cone flag of planner/utils/responsibility.py:57-89 (no angle wrap, quirk Q9; ``wrap`` = the opt-out
+    "view_cone_wrap": bearing and orientation are compared modulo 2 pi)."""
     for oid in predictions:
         pos0 = np.asarray(predictions[oid]["pos_list"])[0]
         ang = np.arctan2(pos0[1] - ego_position[1], pos0[0] - ego_position[0])
-        inside = ego_orientation - (np.pi / 4) <= ang <= ego_orientation + (np.pi / 4)
+        if wrap:
+            inside = abs(np.remainder(ang - ego_orientation + np.pi, 2 * np.pi) - np.pi) <= np.pi / 4
+        else:
+            inside = ego_orientation - (np.pi / 4) <= ang <= ego_orientation + (np.pi / 4)
         predictions[oid]["responsibility"] = 0 if inside else 1
     return predictions
 

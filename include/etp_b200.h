@@ -78,6 +78,21 @@ enum { ETP_REASON_NONE = 0, ETP_REASON_VELOCITY = 1, ETP_REASON_ACCELERATION = 2
 enum { ETP_MODE_RISK = 0, ETP_MODE_WALENET = 1, ETP_MODE_GROUND_TRUTH = 2 };
 
 /*
+ * Opt-outs of reference quirks.  Strict reproduction is the default; a bit switches ONE quirk to what its
+ * surrounding code and comments intend.  The reference cannot produce these variants: they are checked against this
+ * repository's own restatement (oracle/), not against reference fixtures.
+ *   Q1_CURVATURE   : kappa = (dx ddy - ddx dy) / (dx^2 + dy^2)^(3/2) instead of the reference's denominator
+ *                    dx^2 + (dy^2)^(3/2) (frenet_functions.py:308-310)
+ *   Q2_ACCELERATION: the "acceleration" test checks all(|s_dd| <= a_max) (level 0, reason "acceleration") instead of
+ *                    repeating the velocity test (validity_checks.py:70-75)
+ *   Q3_MAXIMIN     : the maximin principle keeps the harm of obstacles whose risk is NOT below eps ("set maximin to 0 if
+ *                    probability (or risk) is 0", risk_costs.py:204-206) instead of the inverted gate
+ *   Q9_VIEW_CONE   : the bearing of an obstacle is compared with the ego orientation modulo 2 pi in the action-space
+ *                    responsibility flag (responsibility.py:78-89; etp_set_raw_predictions)
+ */
+enum { ETP_RELAX_Q1_CURVATURE = 1, ETP_RELAX_Q2_ACCELERATION = 2, ETP_RELAX_Q3_MAXIMIN = 4, ETP_RELAX_Q9_VIEW_CONE = 8 };
+
+/*
  * Collision of the ego box with the predicted obstacle boxes (validity_checks.py:91-103,216-274;
  * prediction_helpers.py:138-210) in planner modes "risk" and "WaleNet".  The reference asks pycrcc: ego boxes
  * RectOBB(l/2, w/2, yaw[i], x[i], y[i]) at time steps time_step + i, prediction boxes RectOBB(length/2, width/2,
@@ -122,7 +137,7 @@ typedef struct {
     double ped_const, ped_speed;     /* harm_parameters.json "pedestrian" (harm_estimation.py:408-414) */
     double veh_l, veh_w, veh_l_r, veh_m, veh_steer_max, veh_lat_a_max, veh_v_max, veh_a_max;
     int32_t collision_check;         /* ETP_COLLISION_*: collision with the predictions (validity level 1) on the device */
-    int32_t reserved0;
+    int32_t relaxed_quirks;          /* ETP_RELAX_* bits; 0 = strict reference behaviour (the default) */
 } etp_params;
 
 /*

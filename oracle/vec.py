@@ -176,7 +176,7 @@ def score_dense(step, profiles=None):
         qp = _port.Quartic(xs=step.c_s, vxs=step.c_s_d, axs=step.c_s_dd, vxe=vT, axe=0.0, T=tT - step.dt)
         t = np.arange(0.0, tT, step.dt)
         s, s_d, s_dd, s_ddd = qp.p(t), qp.d1(t), qp.d2(t), qp.d3(t)
-        gx, gy, gyaw, gcurv, gcurv_d = _port.reference_path_profile(step.csp, s)
+        gx, gy, gyaw, gcurv, gcurv_d = _port.reference_path_profile(step.csp, s, _port.relaxed_quirks(step))
         ds = s[-1] - s[0]
         keep = ~(ds <= np.abs(d_list))
         idx = np.flatnonzero(keep)
@@ -283,6 +283,8 @@ def score_dense(step, profiles=None):
         m = first >= 0
         level[m] = 0
         reason[m] = np.where(hv[m], 4, 3)
+        if "acceleration_check" in _port.relaxed_quirks(step) and not bool(np.all(np.abs(s_dd) <= vp.longitudinal.a_max)):
+            level[:], reason[:] = 0, 2  # relaxed Q2: the acceleration test tests the acceleration
         if not vel_ok:
             level[:], reason[:] = 0, 1
         out["level"][gl] = level
@@ -292,7 +294,8 @@ def score_dense(step, profiles=None):
         if O > 0:
             cst[0] = (er.sum(axis=1) + orr.sum(axis=1) + bd) / (O * 2)
             cst[1] = np.abs(er - orr).sum(axis=1) / O
-            mm = np.maximum((eh * (er < 10e-10)).max(axis=1), (oh * (orr < 10e-10)).max(axis=1))
+            gate = "maximin_gate" in _port.relaxed_quirks(step)  # relaxed Q3 keeps the harm where the risk is NOT below eps
+            mm = np.maximum((eh * ((er < 10e-10) != gate)).max(axis=1), (oh * ((orr < 10e-10) != gate)).max(axis=1))
             cst[2] = np.maximum(mm, bd) ** 10
             resp = np.array([preds[o].get("responsibility", 0) for o in oids], dtype=np.float64)
             cst[3] = -(orr * resp).sum(axis=1)
