@@ -942,7 +942,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     const bool small_planes = (size_t)On * Cp < (size_t)1 << 32;  // row offsets of the [.][O][Cp] planes fit 32 bits
 
     __shared__ Tab<R> tab;
-    __shared__ int s_tile, s_item, s_qn, s_qpos;
+    __shared__ int s_tile, s_next, s_item, s_qn, s_qpos;
     __shared__ BestRec wbest[kWarps];
     __shared__ bool is_last;
     __shared__ int s_nprot;
@@ -976,9 +976,12 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 
     LaneBest lb{~0ull, ~0ull, 0.0, -1, 0};  // warp 0 only: best candidate this lane has finished
 
+    // the index of the next tile is fetched one tile ahead (by warp 1, at the start of phase 3a), so that the round trip of
+    // the global atomic is off the serial path between two tiles
+    if (tid == 0) s_next = (int)atomicAdd(&counters[1], 1u);
     for (;;) {
         if (tid == 0) {
-            s_tile = (int)atomicAdd(&counters[1], 1u);
+            s_tile = s_next;
             s_item = 0;
             s_qn = 0;
             s_qpos = 0;
@@ -1267,6 +1270,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             if (first != 0x7fffffff) atomicMin(&s_leave[lane], first);
         }
         __syncthreads();  // (c) maxima complete, ego samples dead
+        if (tid == 32) s_next = (int)atomicAdd(&counters[1], 1u);  // read by thread 0 after barrier (d)
 
         // ---- phase 3a: per-obstacle reductions, warps over obstacles ----------------------------------
         {
@@ -1348,7 +1352,10 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 if (O > 0) {
                     c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
                     c[ETP_C_EQUALITY] = sum_abs / (double)O;                  // :176-178
-                    c[ETP_C_MAXIMIN] = pow(fmax(mm, bd), 10.0);               // :208
+                    {  // max(...) ** 10 (:208) as four multiplications: pow() alone was a third of this serial section
+                        const double x = fmax(mm, bd), x2 = x * x, x4 = x2 * x2;
+                        c[ETP_C_MAXIMIN] = x4 * x4 * x2;
+                    }
                     c[ETP_C_EGO] = sum_e + bd;                                // :226
                     c[ETP_C_RESPONSIBILITY] = resp;
                 }
