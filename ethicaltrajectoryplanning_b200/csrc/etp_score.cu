@@ -1067,17 +1067,22 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     }
                 }
             }
-            if (tb < Tl && tb > ta) {  // segment that leaves this warp's chunk
-                const TrajPoint tp = kGiven ? given_point(gp, Ts, st.given_stride, tb) : traj_point(q, low, gp, Ts, tb, st.dt);
-                const double dx = px - tp.f[ETP_F_X], dy = py - tp.f[ETP_F_Y];
-                trav += sqrt(dx * dx + dy * dy);
-            }
             double* p1 = sm.p1 + (size_t)warp * P1_COUNT * 32 + lane;
             p1[P1_V * 32] = sv; p1[P1_D * 32] = sd; p1[P1_JL * 32] = jl; p1[P1_JQ * 32] = jq; p1[P1_TRAV * 32] = trav;
             sm.ff[warp * 32 + lane] = first_fail;
             if (gflags) atomicOr(&s_goal[lane], gflags);
         }
         const bool tile_fast = __syncthreads_and(wf) != 0;  // (b) ego samples complete; all of them wrap-free?
+        // travelled distance (calc_trajectory_cost.py:739-757): the segment that enters this warp's time chunk, from the
+        // neighbour's last sample in shared memory (split coordinates: exact to 1e-8 m) instead of a regenerated point
+        if (warp > 0 && warp * chunk < Tl) {
+            const int t = warp * chunk;
+            const Vec4<R> a = sm.e0[(t - 1) * 32 + lane], b = sm.e0[t * 32 + lane];
+            const float2 la = __half22float2(sm.el[(t - 1) * 32 + lane]), lb2 = __half22float2(sm.el[t * 32 + lane]);
+            const double dx = ((double)a.x - (double)b.x) + (double)(la.x - lb2.x) * (1.0 / kLoScale);
+            const double dy = ((double)a.y - (double)b.y) + (double)(la.y - lb2.y) * (1.0 / kLoScale);
+            sm.p1[((size_t)warp * P1_COUNT + P1_TRAV) * 32 + lane] += sqrt(dx * dx + dy * dy);
+        }
         const bool tile_full = __all_sync(kFull, live && T == Ts) && small_planes;
 
         // ---- phase 2a: harm logits of every (t, o) sample, straight-line; samples inside the gate's reach are queued
