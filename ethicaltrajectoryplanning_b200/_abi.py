@@ -12,8 +12,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 # ETP_B200_LIB selects another build of the same sources (kernel tuning experiments); default: the in-tree library
 LIB_PATH = os.environ.get("ETP_B200_LIB") or os.path.join(HERE, "libetp_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_score.cu", "etp_abi.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_launch.h")] + [
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_score.cu", "etp_select.cu", "etp_abi.cu")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_harm.cuh", "etp_launch.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "etp_b200.h")]
 
 NUM_WEIGHTS = 14
@@ -183,14 +183,18 @@ SYMBOLS = {
     "etp_best_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "etp_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "etp_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "etp_get_stage_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "etp_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "etp_combine_best": (C.c_int, [C.POINTER(Best), C.c_int, C.c_int, C.POINTER(Best)]),
 }
 
 
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+
+
 def nvcc_command(out_path=LIB_PATH, extra=()):
-    return ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out_path, *SOURCES, *extra]
+    """One-shot form of the build (what build_library does file by file, in parallel)."""
+    return ["nvcc", *NVCC_FLAGS, "-shared", "-o", out_path, *SOURCES, *extra]
 
 
 def library_is_stale():
@@ -200,17 +204,33 @@ def library_is_stale():
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, extra=(), out_path=None):
     """Compile the kernels + C ABI in-tree (nvcc cross-compiles sm_100a without a GPU)."""
     if not force and not library_is_stale():
         return LIB_PATH
-    cmd = nvcc_command()
+    # every translation unit on its own nvcc process (the fused kernel alone takes a minute), then one link
+    build_dir = os.path.join(HERE, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    extra = list(extra)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", "-o", obj, src]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = ""
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        log += out
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+    cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", out_path or LIB_PATH, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
-    return LIB_PATH
+        print(log + res.stdout + res.stderr)
+    return out_path or LIB_PATH
 
 
 _LIB = None

@@ -1,6 +1,7 @@
 // C ABI of the scoring path (include/etp_b200.h): context, input staging, launches, readback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -89,13 +90,16 @@ struct etp_ctx {
     DevBuf obs_blob;                 // the input arrays of etp_set_obstacles / etp_set_raw_predictions, one upload
     std::vector<unsigned char> group_host;
     DevBoundary boundary{};
-    DevBuf block_best, counters, best_dev, traj_dev, traj_n, given, given_T, prin;
+    DevBuf counters, best_dev, traj_dev, traj_n, given, given_T, prin;
+    // selection (etp_select.cu): per-candidate workspace of the fused kernel, survivors of select_kernel, their exact keys
+    DevBuf ws_cost, ws_bound, ws_meta, ws_bd, ws_gf, sel_blocks, sel_list, sel_res, sel_small;
+    bool refine_off = false;  // ETP_NO_REFINE=1: fp32 selection as it comes out of the fused kernel (kernel experiments)
     bool last_given = false;
     PinnedBuf stage, best_host, traj_host;
     DevStep st{};
     int last_grid = 0;
     bool timing = false;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // step start | profiles done | fused kernel done | selection done
     // scenario sweep: lazily created child contexts (own stream, own buffers) and the pinned result array
     std::vector<etp_ctx*> pool;
     PinnedBuf batch_host;
@@ -169,6 +173,52 @@ int stage_group(etp_ctx* c, DevBuf& blob, std::initializer_list<GroupItem> items
     return stage_to_device(c, blob.p, c->group_host.data(), total);
 }
 
+// selection workspace of a step with st.n_local candidates; fills st.ws_* / st.refine / st.raw_*
+int prepare_selection(etp_ctx* c, DevStep& st) {
+    const size_t n = st.n_local > 0 ? (size_t)st.n_local : 1;
+    ETP_CUDA(c, c->ws_cost.reserve(sizeof(double) * n));
+    ETP_CUDA(c, c->ws_meta.reserve(n));
+    st.refine = (c->precision == ETP_PRECISION_FP32 && !c->refine_off) ? 1 : 0;
+    if (st.refine) {
+        ETP_CUDA(c, c->ws_bound.reserve(sizeof(float) * n));
+        ETP_CUDA(c, c->ws_bd.reserve(sizeof(double) * n));
+        ETP_CUDA(c, c->ws_gf.reserve(n));
+        ETP_CUDA(c, c->sel_list.reserve(sizeof(int) * n));
+        ETP_CUDA(c, c->sel_res.reserve(rescore_rec_bytes(st.n_local)));
+    }
+    ETP_CUDA(c, c->sel_blocks.reserve(select_blocks_bytes(st.n_local)));
+    st.ws_cost = c->ws_cost.as<double>(); st.ws_meta = c->ws_meta.as<uint8_t>();
+    st.ws_bound = c->ws_bound.as<float>(); st.ws_bd = c->ws_bd.as<double>(); st.ws_gf = c->ws_gf.as<uint8_t>();
+    st.raw_cov = c->o_cov.as<double>(); st.raw_vel = c->o_vel.as<double>();
+    return ETP_OK;
+}
+
+SelectBufs select_bufs(etp_ctx* c) {
+    SelectBufs sb;
+    unsigned char* sm = c->sel_small.as<unsigned char>();
+    sb.blocks = c->sel_blocks.p;
+    sb.list = c->sel_list.as<int>();
+    sb.res = c->sel_res.p;
+    sb.hdr = reinterpret_cast<int*>(sm);
+    sb.counters = reinterpret_cast<unsigned*>(sm + 16);
+    sb.stats = reinterpret_cast<unsigned long long*>(sm + 32);
+    return sb;
+}
+
+// fused kernel + selection of the step in c->st
+int launch_step(etp_ctx* c, const DevOut& dout) {
+    const DevStep& st = c->st;
+    unsigned* cnt = c->counters.as<unsigned>();
+    ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, cnt, c->num_sms, &c->last_grid, c->stream));
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    const SelectBufs sb = select_bufs(c);
+    // shards of one step must compare exact keys with each other: a shard's survivor is always re-scored
+    ETP_CUDA(c, launch_select(st, sb, c->best_dev.as<BestRec>(), c->nskip.as<int>(), cnt + 1, st.given != nullptr, st.shard_count > 1, c->stream));
+    if (st.refine)
+        ETP_CUDA(c, launch_rescore(c->precision, st, c->pr, dout, sb, c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, c->stream));
+    return ETP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -191,10 +241,14 @@ int etp_create(etp_ctx** out, int device) {
     c->stream = c->own_stream;
     if (cudaEventCreateWithFlags(&c->staged, cudaEventDisableTiming) != cudaSuccess) { delete c; return ETP_ERR_CUDA; }
     bool ok = c->stage.reserve((size_t)4 << 20) == cudaSuccess && c->best_host.reserve(sizeof(BestRec)) == cudaSuccess &&
-              c->block_best.reserve(sizeof(BestRec) * kMaxGrid) == cudaSuccess &&
               c->counters.reserve(64) == cudaSuccess && c->best_dev.reserve(sizeof(BestRec)) == cudaSuccess &&
-              c->traj_n.reserve(sizeof(int)) == cudaSuccess;
-    if (ok) ok = cudaMemset(c->counters.p, 0, 64) == cudaSuccess && cudaMemset(c->best_dev.p, 0, sizeof(BestRec)) == cudaSuccess;
+              c->traj_n.reserve(sizeof(int)) == cudaSuccess && c->sel_small.reserve(256) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->counters.p, 0, 64) == cudaSuccess && cudaMemset(c->best_dev.p, 0, sizeof(BestRec)) == cudaSuccess &&
+                 cudaMemset(c->sel_small.p, 0, 256) == cudaSuccess;
+    {
+        const char* e = getenv("ETP_NO_REFINE");
+        c->refine_off = e && e[0] == '1';
+    }
     if (!ok) { etp_destroy(c); return ETP_ERR_CUDA; }
     *out = c;
     return ETP_OK;
@@ -209,15 +263,16 @@ int etp_destroy(etp_ctx* c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
                       &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom, &c->rb_tri, &c->rb_trif, &c->rb_start, &c->rb_items, &c->obs_blob,
-                      &c->prof, &c->prof_meta, &c->nskip, &c->block_best, &c->counters, &c->best_dev, &c->traj_dev,
-                      &c->traj_n, &c->given, &c->given_T, &c->prin};
+                      &c->prof, &c->prof_meta, &c->nskip, &c->counters, &c->best_dev, &c->traj_dev,
+                      &c->traj_n, &c->given, &c->given_T, &c->prin, &c->ws_cost, &c->ws_bound, &c->ws_meta, &c->ws_bd, &c->ws_gf,
+                      &c->sel_blocks, &c->sel_list, &c->sel_res, &c->sel_small};
     for (DevBuf* b : bufs) b->release();
     c->stage.release();
     c->enr_host.release();
     c->best_host.release();
     c->traj_host.release();
     if (c->staged) cudaEventDestroy(c->staged);
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -764,12 +819,12 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
             ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "Tmax=%d samples x %d obstacles need %zu bytes of shared memory per CTA (limit %d)",
                      Tmax, c->O, smem, c->smem_optin);
     }
+    if ((r = prepare_selection(c, st))) return r;
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     ETP_CUDA(c, launch_profiles(st, c->pr, c->nskip.as<int>(), c->stream));
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, c->block_best.as<BestRec>(), c->counters.as<unsigned>(),
-                             c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, &c->last_grid, c->stream));
-    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((r = launch_step(c, dout))) return r;
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     c->have_step = true;
     c->last_given = false;
     return ETP_OK;
@@ -854,13 +909,13 @@ int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out*
                      st.Tmax, c->O, smem, c->smem_optin);
     }
     ETP_CUDA(c, c->nskip.reserve(sizeof(int)));
+    if ((r = prepare_selection(c, st))) return r;
     if (c->timing) {
         ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
         ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     }
-    ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, c->block_best.as<BestRec>(), c->counters.as<unsigned>(),
-                             c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, &c->last_grid, c->stream));
-    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((r = launch_step(c, dout))) return r;
+    if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     c->have_step = true;
     c->last_given = true;
     return ETP_OK;
@@ -1003,20 +1058,25 @@ int etp_enable_timing(etp_ctx* c, int enable) {
     if (!c) return ETP_ERR_INVALID;
     ETP_CUDA(c, cudaSetDevice(c->device));
     if (enable && !c->ev[0])
-        for (int i = 0; i < 3; ++i) ETP_CUDA(c, cudaEventCreate(&c->ev[i]));
+        for (int i = 0; i < 4; ++i) ETP_CUDA(c, cudaEventCreate(&c->ev[i]));
     c->timing = enable != 0;
     return ETP_OK;
 }
 
 int etp_get_timing(etp_ctx* c, float* profile_ms, float* score_ms) {
-    if (!c) return ETP_ERR_INVALID;
+    float ms[3] = {0.f, 0.f, 0.f};
+    const int r = etp_get_stage_timing(c, ms, 3);
+    if (r) return r;
+    if (profile_ms) *profile_ms = ms[0];
+    if (score_ms) *score_ms = ms[1];
+    return ETP_OK;
+}
+
+int etp_get_stage_timing(etp_ctx* c, float* ms, int n) {
+    if (!c || !ms || n < 1) return ETP_ERR_INVALID;
     if (!c->timing || !c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "timing not enabled or no step run");
-    ETP_CUDA(c, cudaEventSynchronize(c->ev[2]));
-    float a = 0.f, b = 0.f;
-    ETP_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
-    ETP_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
-    if (profile_ms) *profile_ms = a;
-    if (score_ms) *score_ms = b;
+    ETP_CUDA(c, cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3 && i < n; ++i) ETP_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
     return ETP_OK;
 }
 
@@ -1027,6 +1087,11 @@ int etp_debug_counters(etp_ctx* c, uint64_t* out, int n) {
     unsigned long long v[1] = {0};
     ETP_CUDA(c, read_debug_counters(v, 1));
     out[0] = v[0];
+    if (n > 1) {
+        unsigned long long st[3] = {0, 0, 0};
+        ETP_CUDA(c, cudaMemcpy(st, select_bufs(c).stats, sizeof(st), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 3 && 1 + i < n; ++i) out[1 + i] = st[i];
+    }
     return ETP_OK;
 }
 

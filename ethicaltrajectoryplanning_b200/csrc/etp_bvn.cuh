@@ -39,13 +39,13 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 
 __device__ __forceinline__ double phi_d(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
 
-__constant__ double kGLw[3][10] = {
+static __constant__ double kGLw[3][10] = {
     {0.1713244923791705, 0.3607615730481384, 0.4679139345726904},
     {0.04717533638651177, 0.1069393259953183, 0.1600783285433464, 0.2031674267230659, 0.2334925365383547,
      0.2491470458134029},
     {0.01761400713915212, 0.04060142980038694, 0.06267204833410906, 0.08327674157670475, 0.1019301198172404,
      0.1181945319615184, 0.1316886384491766, 0.1420961093183821, 0.1491729864726037, 0.1527533871307259}};
-__constant__ double kGLx[3][10] = {
+static __constant__ double kGLx[3][10] = {
     {0.9324695142031522, 0.6612093864662647, 0.2386191860831970},
     {0.9815606342467191, 0.9041172563704750, 0.7699026741943050, 0.5873179542866171, 0.3678314989981802,
      0.1252334085114692},
@@ -53,7 +53,7 @@ __constant__ double kGLx[3][10] = {
      0.6360536807265150, 0.5108670019508271, 0.3737060887154196, 0.2277858511416451, 0.07652652113349733}};
 
 // Genz BVU: P(X > sh, Y > sk) for a standard bivariate normal with correlation r.
-__device__ double bvu_d(double sh, double sk, double r) {
+static __device__ double bvu_d(double sh, double sk, double r) {
     const double TWOPI = 6.283185307179586;
     int ng, lg;
     const double ar = fabs(r);
@@ -263,7 +263,7 @@ __device__ __forceinline__ float rect_prob_nodes_f(const RhoNodes<N>& n, float x
 }
 
 // strongly correlated predictions: fp64 Genz evaluation (kept out of line, rare)
-__device__ __noinline__ float rect_prob_fallback_f(float xl, float xu, float yl, float yu, float r) {
+static __device__ __noinline__ float rect_prob_fallback_f(float xl, float xu, float yl, float yu, float r) {
     return (float)rect_prob((double)xl, (double)xu, (double)yl, (double)yu, (double)r);
 }
 

@@ -168,6 +168,16 @@ struct DevStep {
     // raw fp64 copies for the exact gate re-check of the fp32 path
     const double* raw_pos;   // [O][Tp][2]
     const double* raw_yaw;   // [O][Tp]
+    const double* raw_cov;   // [O][Tp][4]  (exact re-scoring of near-tie candidates, rescore_kernel)
+    const double* raw_vel;   // [O][Tp]
+    // selection workspace, one entry per local candidate column (etp_select.cu): total cost, bound on what fp32
+    // rounding can have moved it by, level | SEL_AMB, boundary harm, goal flags
+    double* ws_cost;
+    float* ws_bound;
+    uint8_t* ws_meta;
+    double* ws_bd;
+    uint8_t* ws_gf;
+    int refine;              // 1: fp32 arithmetic, near-ties and rounding-dependent decisions are re-made in fp64
     // caller-provided trajectories instead of generated candidates (etp_score_trajectories), or null
     const double* given;     // [ETP_NUM_FIELDS][Tmax][given_stride], fp64
     const int* given_T;      // [n_local] samples per trajectory
@@ -201,8 +211,131 @@ __device__ __forceinline__ unsigned long long monotone_key(double x) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-__device__ __forceinline__ unsigned long long make_key_hi(int level, double cost) {
-    return ((unsigned long long)(4 - level_rank(level)) << 60) | (monotone_key(cost) >> 4);
+// 128-bit selection key, smaller is better: (4 - level rank | cost | index) with the full 64-bit cost image, so that the
+// key orders exactly like the reference's stable sort by cost within the highest non-empty level
+// (frenet_functions.py:562-570, frenet_planner.py:457): hi = rank' << 61 | mono >> 3, lo = (mono & 7) << 61 | index
+__host__ __device__ __forceinline__ unsigned long long make_key_hi_from(int level, unsigned long long mono) {
+    return ((unsigned long long)(4 - level_rank(level)) << 61) | (mono >> 3);
+}
+__host__ __device__ __forceinline__ unsigned long long make_key_lo_from(unsigned long long mono, unsigned long long index) {
+    return ((mono & 7ull) << 61) | index;
+}
+__device__ __forceinline__ unsigned long long make_key_hi(int level, double cost) { return make_key_hi_from(level, monotone_key(cost)); }
+__device__ __forceinline__ unsigned long long make_key_lo(double cost, unsigned long long index) {
+    return make_key_lo_from(monotone_key(cost), index);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cost assembly of one candidate (risk_costs.py:128-255, calc_trajectory_cost.py:103-148,279-346,418-519,726-757,
+// validity_checks.py:277-294), shared by the fused kernel (phase 3b) and the exact re-scoring
+// ---------------------------------------------------------------------------------------------
+enum { GF_REACHED = 1, GF_OUTSIDE = 2, GF_START_INSIDE = 4 };  // goal bookkeeping of a candidate (goal_sample_flags)
+enum { SEL_AMB = 64, SEL_SKIPPED = 255 };                       // ws_meta: level | SEL_AMB, or SEL_SKIPPED
+
+struct RiskSums {
+    double sum_e, sum_o, sum_abs, resp, mm, max_o;  // over the obstacles: ego / obstacle risk, |difference|, responsibility,
+};                                                  // gated harm maximum (Q3), largest obstacle risk
+struct CandFacts {
+    double sv, sd, jl, jq, trav;  // sums over the samples: v, |d|, s_ddd^2, d_ddd^2, travelled distance
+    int T;
+    int pre_level, pre_reason;    // validity decided before the risk: 0 / 1 / 2 with its reason, or -1
+    double bd;                    // boundary harm (risk_costs.py:104-123)
+    int gf;                       // GF_* flags (st.goal.on)
+    double factor;                // caller's cost factor (list entry or scalar), replaced by the goal logic if on
+};
+
+// what fp32 rounding of the risk terms can move a candidate's decisions and total cost by (DevStep::refine)
+constexpr double kTolRisk = 1e-4;      // relative bound of a per-obstacle risk maximum (the parity bar of the probability)
+constexpr double kTolRiskAbs = 1e-9;   // its absolute floor
+constexpr double kTolLogit = 2e-5;     // absolute bound of a harm logit (fp32 velocities and headings)
+constexpr double kTolSigmoid = 5e-7;   // relative bound of the fp32 sigmoid itself
+constexpr double kTolGate = 1e-2;      // relative bound of a risk at the maximin gate's eps = 1e-9 (risk_costs.py:204-206): rectangles
+                                       // beyond 7 sigma are dropped (< 4e-12 on the probability) and fp32 carries ~1e-4 down there
+
+__device__ __forceinline__ void assemble_costs(const DevStep& st, const DevParams& pr, int O, const CandFacts& f, const RiskSums& r,
+                                               double* c, int& level, int& reason) {
+#pragma unroll
+    for (int k = 0; k < ETP_NUM_COST; ++k) c[k] = 0.0;
+    const double bd = f.bd;
+    if (O > 0) {
+        c[ETP_C_BAYES] = (r.sum_e + r.sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
+        c[ETP_C_EQUALITY] = r.sum_abs / (double)O;                    // :176-178
+        {  // max(...) ** 10 (:208) as four multiplications
+            const double x = fmax(r.mm, bd), x2 = x * x, x4 = x2 * x2;
+            c[ETP_C_MAXIMIN] = x4 * x4 * x2;
+        }
+        c[ETP_C_EGO] = r.sum_e + bd;                                  // :226
+        c[ETP_C_RESPONSIBILITY] = r.resp;
+    }
+    const bool risk_in_cost = pr.w[ETP_W_RISK_COST] > 0.0 && st.has_pred && pr.planner_mode == ETP_MODE_RISK;
+    if (risk_in_cost)  // calc_trajectory_cost.py:130-136
+        c[ETP_C_RISK_TOTAL] = pr.w[ETP_W_BAYES] * c[ETP_C_BAYES] + pr.w[ETP_W_EQUALITY] * c[ETP_C_EQUALITY] +
+                              pr.w[ETP_W_MAXIMIN] * c[ETP_C_MAXIMIN] +
+                              pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES] * c[ETP_C_RESPONSIBILITY] +
+                              pr.w[ETP_W_EGO] * c[ETP_C_EGO];
+    const double mean_v = f.sv / (double)f.T;
+    int vel_mode = st.vel_mode;
+    double vel_target = st.vel_target;
+    double factor = f.factor;
+    if (st.goal.on) {
+        const int gf = f.gf;
+        if (gf & GF_START_INSIDE) {  // inside the goal area: the goal's velocity, else slow (:452-467)
+            vel_mode = st.goal.has_vel ? 0 : 2;
+            vel_target = st.goal.vel_mid;
+        } else {                     // :469-519
+            vel_mode = st.goal.vel_kind;
+            vel_target = st.goal.vel_out;
+        }
+        factor = 1.0;                // get_cost_factor, :375-415
+        bool in_time = false;
+        if (gf & GF_REACHED) {
+            factor = 0.01;
+            in_time = st.goal.time_first < f.T;
+            if (in_time) factor = 0.0001;
+        }
+        if (!in_time && st.goal.ego_in_goal && (gf & GF_OUTSIDE)) factor = 10.0;
+    }
+    switch (vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
+        case 0: c[ETP_C_VELOCITY] = fabs(vel_target - mean_v); break;
+        case 1: c[ETP_C_VELOCITY] = 30.0 - mean_v; break;
+        case 2: c[ETP_C_VELOCITY] = mean_v; break;
+        default: c[ETP_C_VELOCITY] = 0.0;
+    }
+    c[ETP_C_DIST_TO_GLOBAL_PATH] = f.sd / (double)f.T;  // :726-736
+    c[ETP_C_LON_JERK] = f.jl / (double)f.T;             // :418-435
+    c[ETP_C_LAT_JERK] = f.jq / (double)f.T;
+    c[ETP_C_TRAVELLED_DIST] = f.trav;
+    c[ETP_C_FACTOR] = factor;
+    // validity level (validity_checks.py:31-122): the tests before the risk have run (pre_level)
+    if (f.pre_level >= 0) { level = f.pre_level; reason = f.pre_reason; }
+    else if (pr.planner_mode == ETP_MODE_RISK && st.has_pred && O > 0 &&
+             (r.sum_e > pr.max_risk || r.max_o > pr.max_risk)) { level = 3; reason = ETP_REASON_MAX_RISK; }
+    else { level = 10; reason = ETP_REASON_NONE; }
+    // weighted sum (calc_trajectory_cost.py:321-346); risk-only weights below level 10 if requested
+    const bool risk_only = level < 10 && pr.multi_cost;
+    double cost = 0.0;
+    if (risk_in_cost) cost += pr.w[ETP_W_RISK_COST] * c[ETP_C_RISK_TOTAL];
+    if (pr.w[ETP_W_LON_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LON_JERK]) * c[ETP_C_LON_JERK];
+    if (pr.w[ETP_W_LAT_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LAT_JERK]) * c[ETP_C_LAT_JERK];
+    if (pr.w[ETP_W_VELOCITY] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_VELOCITY]) * c[ETP_C_VELOCITY];
+    if (pr.w[ETP_W_DIST_TO_GLOBAL_PATH] > 0.0)
+        cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GLOBAL_PATH]) * c[ETP_C_DIST_TO_GLOBAL_PATH];
+    if (pr.w[ETP_W_TRAVELLED_DIST] > 0.0)
+        cost += (risk_only ? 0.0 : pr.w[ETP_W_TRAVELLED_DIST]) * c[ETP_C_TRAVELLED_DIST];
+    c[ETP_C_TOTAL] = factor * cost;
+}
+
+// Bound on |fp32-path total cost - exact total cost| of a candidate from its own risk terms, and whether one of its
+// decisions (max-risk level, maximin gate) is too close to its threshold for fp32 to make (DevStep::refine).
+__device__ __forceinline__ float cost_bound(const DevParams& pr, int O, const RiskSums& r, double bd, const double* c, bool risk_in_cost) {
+    if (!risk_in_cost || O <= 0) return 0.0f;
+    const double x = fmax(r.mm, bd);
+    const double mterm = c[ETP_C_MAXIMIN];
+    const double d_risk = kTolRisk * (r.sum_e + r.sum_o) + 2.0 * O * kTolRiskAbs;  // bound of sum(d ego risk) + sum(d obstacle risk)
+    const double lin = (fabs(pr.w[ETP_W_BAYES]) / (2.0 * O) + fabs(pr.w[ETP_W_EQUALITY]) / O + fabs(pr.w[ETP_W_EGO]) +
+                        fabs(pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES])) * d_risk;
+    const double mm = fabs(pr.w[ETP_W_MAXIMIN]) * mterm * (10.0 * fmax(1.0 - x, 0.0) * kTolLogit + 10.0 * kTolSigmoid);
+    return (float)(1.0000001 * fabs(c[ETP_C_FACTOR] * pr.w[ETP_W_RISK_COST]) * (lin + mm)) ;
 }
 
 // ---------------------------------------------------------------------------------------------

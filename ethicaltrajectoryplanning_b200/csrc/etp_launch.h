@@ -16,9 +16,29 @@ cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_
 
 cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, cudaStream_t stream);
 
-cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
-                         unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
-                         cudaStream_t stream);
+// fused kernel: scores the candidates of `st`, materialises `out`, leaves the selection workspace (st.ws_*);
+// counters[1] is its tile counter (re-armed by select_kernel)
+cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
+                         int* grid_out, cudaStream_t stream);
+
+// buffers of the selection (etp_select.cu)
+struct SelectBufs {
+    void* blocks;               // per-block records of select_kernel (select_blocks_bytes)
+    int* list;                  // [n_local] columns left for the exact re-scoring
+    void* res;                  // their exact keys (rescore_rec_bytes)
+    int* hdr;                   // [0] candidates left for rescore_kernel, [1] non-skipped candidates, [2] fill of `list` during select_kernel
+    unsigned* counters;         // [2] completion counters of the two kernels
+    unsigned long long* stats;  // [0] candidates re-scored, [1] of them outside their fp32 bound, [2] largest error / bound (float bits)
+};
+size_t select_blocks_bytes(int n_local);
+size_t rescore_rec_bytes(int n_local);
+size_t rescore_smem_bytes(int Tmax, int O);
+
+// arg-min over the workspace -> *best_out, or (fp32 mode) the candidates that can still win -> rescore_kernel
+cudaError_t launch_select(const DevStep& st, const SelectBufs& sb, BestRec* best_out, const int* nskip, unsigned* tile_counter,
+                          bool given, bool always_rescore, cudaStream_t stream);
+cudaError_t launch_rescore(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, const SelectBufs& sb,
+                           BestRec* best_out, const int* nskip, int num_sms, cudaStream_t stream);
 
 // dynamic shared memory one CTA of the scoring kernel needs for (Tmax, O)
 size_t score_smem_bytes(int precision, int Tmax, int O);

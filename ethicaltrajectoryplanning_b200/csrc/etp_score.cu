@@ -27,6 +27,7 @@
 
 #include "etp_bvn.cuh"
 #include "etp_device.cuh"
+#include "etp_harm.cuh"
 #include "etp_launch.h"
 
 namespace etp {
@@ -47,160 +48,7 @@ constexpr int kMinBlocks = ETP_MIN_BLOCKS;  // resident CTAs per SM the register
 #define ETP_OB 4
 #endif
 constexpr int kOB = ETP_OB;  // obstacles of one phase-2 item (register blocking: one ego load serves kOB obstacles)
-constexpr unsigned kFull = 0xffffffffu;
 constexpr float kLoScale = 16384.0f;  // low parts of coordinates are stored as halves of (residue * 2^14)
-
-// ---------------------------------------------------------------------------------------------
-// small typed helpers
-// ---------------------------------------------------------------------------------------------
-// order-preserving integer image of a real: max over reals == max over images (shared-memory atomicMax)
-template <typename R> struct Enc;
-template <> struct Enc<float> {
-    using U = unsigned int;
-    static __device__ __forceinline__ U enc(float x) {
-        U b = __float_as_uint(x);
-        return (b >> 31) ? ~b : (b | 0x80000000u);
-    }
-    static __device__ __forceinline__ float dec(U k) {
-        U b = (k >> 31) ? (k & 0x7fffffffu) : ~k;
-        return __uint_as_float(b);
-    }
-};
-template <> struct Enc<double> {
-    using U = unsigned long long;
-    static __device__ __forceinline__ U enc(double x) {
-        U b = (U)__double_as_longlong(x);
-        return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-    }
-    static __device__ __forceinline__ double dec(U k) {
-        U b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-        return __longlong_as_double((long long)b);
-    }
-};
-
-template <typename R> __device__ __forceinline__ Vec4<R> ldg4(const Vec4<R>* p);
-template <> __device__ __forceinline__ Vec4<float> ldg4<float>(const Vec4<float>* p) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    return Vec4<float>{v.x, v.y, v.z, v.w};
-}
-template <> __device__ __forceinline__ Vec4<double> ldg4<double>(const Vec4<double>* p) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    return Vec4<double>{a.x, a.y, b.x, b.y};
-}
-template <typename R> __device__ __forceinline__ R rmax_(R a, R b) { return a > b ? a : b; }
-// square root of the fp32 streaming path: MUFU.RSQ based (2 ulp); the fp64 check mode stays IEEE
-__device__ __forceinline__ float sqrt_fast(float x) {
-    const float xp = fmaxf(x, 0.0f);  // rounding can leave (v_e - v_o)^2 slightly negative
-    return xp * rsqrt_ftz(fmaxf(xp, 1e-30f));
-}
-__device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
-__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-__device__ __forceinline__ float exp_(float x) { return expf(x); }
-__device__ __forceinline__ double exp_(double x) { return exp(x); }
-__device__ __forceinline__ float abs_(float x) { return fabsf(x); }
-__device__ __forceinline__ double abs_(double x) { return fabs(x); }
-
-// Constants of the risk model in the arithmetic type R, resident in shared memory (one copy per CTA):
-// dynamic indexing into kernel parameters would force a per-thread local-memory copy of DevParams.
-template <typename R> struct Tab {
-    R thr[ETP_MAX_ANGLE_BINS], fcos[ETP_MAX_ANGLE_BINS], coef_pos[ETP_MAX_ANGLE_BINS + 1], coef_neg[ETP_MAX_ANGLE_BINS + 1];
-    R lr_speed, lr1s_speed, ped_speed, lr_const, lr1s_const, neg_ped_const;
-    R eps_pos;     // fp32 rounding of a position difference in metres (2 ulp of the largest coordinate in play)
-    R hx, hy, rr;  // ego box half extents (l/6, w/2) and centre offset (l/2)(2/3)  (collision_probability.py:157,349-362)
-    int n_thr;
-};
-
-template <typename R> __device__ __forceinline__ void fill_tab(Tab<R>& tb, const DevParams& pr, double eps_pos) {
-    for (int i = 0; i < ETP_MAX_ANGLE_BINS; ++i) { tb.thr[i] = (R)pr.thr[i]; tb.fcos[i] = (R)pr.fcos[i]; }
-    for (int i = 0; i <= ETP_MAX_ANGLE_BINS; ++i) { tb.coef_pos[i] = (R)pr.coef_pos[i]; tb.coef_neg[i] = (R)pr.coef_neg[i]; }
-    tb.lr_speed = (R)pr.lr_speed; tb.lr1s_speed = (R)pr.lr1s_speed; tb.ped_speed = (R)pr.ped_speed;
-    tb.lr_const = (R)pr.lr_const; tb.lr1s_const = (R)pr.lr1s_const; tb.neg_ped_const = (R)(-pr.ped_const);
-    tb.hx = (R)(pr.veh_l / 6); tb.hy = (R)(pr.veh_w / 2); tb.rr = (R)((pr.veh_l / 2) * (2.0 / 3.0));
-    tb.n_thr = pr.n_thr;
-    tb.eps_pos = (R)eps_pos;
-}
-
-// ---------------------------------------------------------------------------------------------
-// harm model (harm_estimation.py:313-332): harm = 1 / (1 + exp(-(const + arg))), arg = speed * dv_k + coef(angle)
-// ---------------------------------------------------------------------------------------------
-// delta_v = sqrt(v_e^2 + v_o^2 + 2 v_e v_o cos(pdof)), pdof = psi_o - psi_e + pi (harm_estimation.py:313,322-325)
-__device__ __forceinline__ float delta_v(float ec, float es, float ev, float, float ovo, float ocp, float osp, float) {
-    const float cpd = -(ocp * ec + osp * es);
-    return sqrt_fast(ev * ev + ovo * ovo + 2 * ev * ovo * cpd);
-}
-// fp64 check mode evaluates pdof with the reference's own expression
-__device__ __forceinline__ double delta_v(double, double, double ev, double eyaw, double ovo, double, double, double opsi) {
-    const double pdof = opsi - eyaw + 3.14159265358979323846;
-    return sqrt(ev * ev + ovo * ovo + 2 * ev * ovo * cos(pdof));
-}
-
-// impact-area coefficient (logistic_regression_*.py): thresholds on |angle|, sign picks the side
-template <typename R> __device__ __forceinline__ R angle_coef(const Tab<R>& pr, R angle) {
-    const R a = abs_(angle);
-    int i = 0;
-    while (i < pr.n_thr && !(a < pr.thr[i])) ++i;
-    return angle < (R)0 ? pr.coef_neg[i] : pr.coef_pos[i];
-}
-
-// Band of an impact angle given as a direction: P = |d| cos(angle), d2 = |d|^2.  |angle| < thr is
-// cos(angle) > cos(thr), compared through the sign-preserving squares P|P| > d2 * cos(thr)|cos(thr)|.
-// `tol` bounds what fp32 rounding (of the positions above all) can move a test by; a test closer to its threshold
-// than that sets `amb`, and the caller repeats the decision in fp64 from the exact inputs (band_coefs_exact).
-__device__ __forceinline__ int direction_band(const Tab<float>& pr, float P, float d2, float tol, bool& amb) {
-    // thresholds increase, so the tests pass from some band on: the band is the number of failed tests
-    const float fp = P * fabsf(P);
-    int band = 0;
-    for (int i = 0; i < pr.n_thr; ++i) {
-        const float df = fmaf(-d2, pr.fcos[i], fp);
-        band += (df > 0.0f) ? 0 : 1;
-        amb = amb || fabsf(df) < tol;
-    }
-    return band;
-}
-
-// tolerance of a band test: the direction (dx, dy) carries the rounding of two positions (eps_pos metres in total),
-// which moves P|P| - d2 f by at most |d| eps_pos <= sqrt(2) max(|dx|, |dy|) eps_pos; the arithmetic adds a few ulps of d2
-__device__ __forceinline__ float band_tol(float d2, float dx, float dy, float eps_pos) {
-    return __fmaf_rn(fmaxf(fabsf(dx), fabsf(dy)), __fmul_rn(1.4143f, eps_pos), __fmul_rn(d2, 1e-6f));
-}
-
-// Impact-area coefficients of ego and obstacle, fp32 path.  `ewrap` are the whole turns that bring the ego yaw
-// into (-pi, pi].  The reference bins the UN-wrapped angles rel - yaw_e and
-// pi + rel - psi_o (quirk Q4) with rel = atan2(dy, dx); instead of evaluating atan2, the relative direction is
-// rotated into the ego / obstacle frame (P, Q) and the number of 2 pi wraps of the un-wrapped difference is
-// recovered from the half planes of the two directions.  |angle| > pi always lands in the last ("rear") band.
-__device__ __forceinline__ void impact_coefs(const Tab<float>& pr, float ex, float ey, float ec, float es, float ewrap,
-                                             float mx, float my, float ocp, float osp, float ocode, float& ce, float& co,
-                                             bool& amb) {
-    const float dx = mx - ex, dy = my - ey;
-    const float d2 = dx * dx + dy * dy;
-    const float tol = band_tol(d2, dx, dy, pr.eps_pos);
-    const int last = pr.n_thr;
-    // ego: angle = rel - yaw_e
-    const float p = dx * ec + dy * es, q = dy * ec - dx * es;
-    int n0 = 0;
-    if (dy >= 0 && es < 0 && q < 0) n0 = 1;
-    if (dy < 0 && es >= 0 && q > 0) n0 = -1;
-    const int be = ((float)n0 != ewrap) ? last : direction_band(pr, p, d2, tol, amb);
-    ce = q < 0 ? pr.coef_neg[be] : pr.coef_pos[be];
-    // obstacle: angle = pi + rel - psi_o; `ocode` is the validity table of pack_obstacles_kernel
-    const float po = dx * ocp + dy * osp, qo = dy * ocp - dx * osp;
-    const bool pos = qo < 0 || (qo == 0 && po >= 0);
-    const bool valid = ((__float_as_int(ocode) >> ((pos ? 2 : 0) | (dy >= 0 ? 1 : 0))) & 1) != 0;
-    const bool neg_side = !pos && valid;
-    const int bo = valid ? direction_band(pr, -po, d2, tol, amb) : last;
-    co = neg_side ? pr.coef_neg[bo] : pr.coef_pos[bo];
-}
-__device__ __forceinline__ void impact_coefs(const Tab<double>& pr, double ex, double ey, double, double, double eyaw,
-                                             double mx, double my, double, double, double opsi, double& ce, double& co,
-                                             bool&) {
-    const double rel = atan2(my - ey, mx - ex);  // harm_estimation.py:314-319
-    ce = angle_coef<double>(pr, rel - eyaw);
-    co = angle_coef<double>(pr, 3.14159265358979323846 + rel - opsi);
-}
-
-template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { return (R)1 / ((R)1 + exp_(-cst - arg)); }
 
 // ---------------------------------------------------------------------------------------------
 // exact (fp64) impact-area coefficients of one (candidate, sample, obstacle): the fp32 paths call this when a band
@@ -437,13 +285,6 @@ __device__ __noinline__ ProbCoef<R> ungated_eval(const Tab<R>& tab, R ddx, R ddy
     return r;
 }
 
-// 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
-template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R mx, R my, R i00, R i01, R i11) {
-    const R dx = x - mx, dy = y - my;
-    const R m2 = dx * dx * i00 + dx * dy * i01 + dy * dy * i11;
-    return (R)1e-4 / sqrt_(m2);
-}
-
 // The 5 m gate (collision_probability.py:183-203) repeated in fp64 from the exact inputs: the fp32 path calls
 // this when its own distances are too close to the threshold to decide.  Ego sample `ti` is regenerated.
 __device__ __noinline__ bool gate_exact(const DevStep* stp, bool given, int pl, int id, int ti, int o, int t) {
@@ -546,7 +387,7 @@ __device__ __noinline__ bool collide_exact(const DevStep* stp, const DevParams* 
 // ---------------------------------------------------------------------------------------------
 enum { MX_EGO_RISK = 0, MX_OBST_RISK, MX_EGO_ARG, MX_OBST_ARG, MX_COUNT };  // running maxima over time, [MX][O][32]
 enum { P1_V = 0, P1_D, P1_JL, P1_JQ, P1_TRAV, P1_COUNT };                   // phase-1 partial sums, [W][P1][32]
-enum { P3_SUM_E = 0, P3_SUM_O, P3_SUM_ABS, P3_RESP, P3_MM, P3_MAX_O, P3_COUNT };  // phase-3 partials, [W][P3][32]
+enum { P3_SUM_E = 0, P3_SUM_O, P3_SUM_ABS, P3_RESP, P3_MM, P3_MAX_O, P3_MM_LO, P3_MM_HI, P3_COUNT };  // phase-3 partials, [W][P3][32]
 
 template <typename R> struct Smem {
     using U = typename Enc<R>::U;
@@ -580,17 +421,6 @@ template <typename R> struct Smem {
         queue = reinterpret_cast<unsigned*>(ff + kWarps * 32);
     }
 };
-
-struct LaneBest {
-    unsigned long long hi, lo;
-    double cost;
-    int level, scored;
-};
-
-__device__ __forceinline__ bool key_less(unsigned long long ahi, unsigned long long alo, unsigned long long bhi,
-                                         unsigned long long blo) {
-    return ahi < bhi || (ahi == bhi && alo < blo);
-}
 
 // ---------------------------------------------------------------------------------------------
 // phase 2a: one item = kOB obstacles of one class x one time segment
@@ -902,7 +732,6 @@ __device__ __noinline__ double leave_velocity(const DevStep* stp, bool given, in
 // Goal bookkeeping of one trajectory sample (calc_trajectory_cost.py:553-571 reached_goal_state, :520-550
 // goal_position_reached_and_left_again, :452 velocity_costs): bit 0 = goal state reached at this sample (position,
 // velocity and orientation), bit 1 = sample outside the goal area, bit 2 = sample 0 inside the goal area.
-enum { GF_REACHED = 1, GF_OUTSIDE = 2, GF_START_INSIDE = 4 };
 __device__ __noinline__ int goal_sample_flags(const DevGoal* gp, double x, double y, double v, double yaw, int t) {
     const DevGoal& g = *gp;
     const bool in = !g.has_area || point_in_goal(g, g.poly_start, g.verts, g.circles, x, y);
@@ -918,8 +747,7 @@ __device__ __noinline__ int goal_sample_flags(const DevGoal* gp, double x, doubl
 template <typename R, int NT, bool kSym, bool kGiven>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr, DevOut out,
-             BestRec* __restrict__ block_best, unsigned int* __restrict__ counters, BestRec* __restrict__ best_out,
-             const int* __restrict__ prof_nskip) {
+             unsigned int* __restrict__ counters) {
     using U = typename Enc<R>::U;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Ts = st.Tmax;
@@ -943,8 +771,6 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 
     __shared__ Tab<R> tab;
     __shared__ int s_tile, s_next, s_item, s_qn, s_qpos;
-    __shared__ BestRec wbest[kWarps];
-    __shared__ bool is_last;
     __shared__ int s_nprot;
     __shared__ int s_hit[32];  // lane's candidate collides with a predicted box (pr.collision_check)
     __shared__ int s_goal[32]; // GF_* flags of the lane's candidate (st.goal.on)
@@ -973,8 +799,6 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     const int seg_len = (Ts - 1 + n_seg - 1) / n_seg;
     const int n_items = n_groups * n_seg;
     const int chunk = (Ts + kWarps - 1) / kWarps;  // phase-1 time chunks
-
-    LaneBest lb{~0ull, ~0ull, 0.0, -1, 0};  // warp 0 only: best candidate this lane has finished
 
     // the index of the next tile is fetched one tile ahead (by warp 1, at the start of phase 3a), so that the round trip of
     // the global atomic is off the serial path between two tiles
@@ -1280,6 +1104,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         // ---- phase 3a: per-obstacle reductions, warps over obstacles ----------------------------------
         {
             double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
+            double mm_lo = -INFINITY, mm_hi = -INFINITY;  // the gated harm maximum if every risk near eps fell outside / inside the gate
             for (int o = warp; o < O; o += kWarps) {
                 R re = 0, ro = 0, he = 0, ho = 0;
                 if (live) {
@@ -1300,6 +1125,13 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     mm = fmax(mm, (double)he * ((((double)re < 10e-10) != gate) ? 1.0 : 0.0));
                     mm = fmax(mm, (double)ho * ((((double)ro < 10e-10) != gate) ? 1.0 : 0.0));
                     max_o = fmax(max_o, (double)ro);
+                    // a risk within kTolGate of the gate's eps: fp32 cannot say on which side it lies (st.refine); it matters
+                    // only if the two readings give different maxima
+                    const double e_in = 10e-10 * (1.0 - kTolGate), e_out = 10e-10 * (1.0 + kTolGate);
+                    mm_lo = fmax(mm_lo, (double)he * ((((double)re < (gate ? e_out : e_in)) != gate) ? 1.0 : 0.0));
+                    mm_lo = fmax(mm_lo, (double)ho * ((((double)ro < (gate ? e_out : e_in)) != gate) ? 1.0 : 0.0));
+                    mm_hi = fmax(mm_hi, (double)he * ((((double)re < (gate ? e_in : e_out)) != gate) ? 1.0 : 0.0));
+                    mm_hi = fmax(mm_hi, (double)ho * ((((double)ro < (gate ? e_in : e_out)) != gate) ? 1.0 : 0.0));
                 }
                 if (o_red && active) {
                     o_red[((size_t)ETP_R_EGO_RISK * O + o) * Cp + cl] = re;
@@ -1310,32 +1142,39 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             }
             double* p3 = sm.p3 + (size_t)warp * P3_COUNT * 32 + lane;
             p3[P3_SUM_E * 32] = sum_e; p3[P3_SUM_O * 32] = sum_o; p3[P3_SUM_ABS * 32] = sum_abs;
-            p3[P3_RESP * 32] = resp; p3[P3_MM * 32] = mm; p3[P3_MAX_O * 32] = max_o;
+            p3[P3_RESP * 32] = resp; p3[P3_MM * 32] = mm; p3[P3_MAX_O * 32] = max_o; p3[P3_MM_LO * 32] = mm_lo; p3[P3_MM_HI * 32] = mm_hi;
         }
         __syncthreads();  // (d) partials complete
 
-        // ---- phase 3b: principles, cost, level, key (warp 0, one candidate per lane) --------------------
+        // ---- phase 3b: principles, cost, level (warp 0, one candidate per lane) -------------------------
         if (warp == 0) {
             double c[ETP_NUM_COST];
 #pragma unroll
             for (int k = 0; k < ETP_NUM_COST; ++k) c[k] = 0.0;
             int level = ETP_LEVEL_SKIPPED, reason = ETP_REASON_NONE;
             double bd_out = 0.0;
+            float bound = 0.0f;
+            bool amb = false;
             if (live) {
-                double sv = 0, sd = 0, jl = 0, jq = 0, trav = 0;
-                double sum_e = 0, sum_o = 0, sum_abs = 0, resp = 0, mm = -INFINITY, max_o = -INFINITY;
+                CandFacts f;
+                RiskSums r{0, 0, 0, 0, -INFINITY, -INFINITY};
+                f.sv = f.sd = f.jl = f.jq = f.trav = 0.0;
+                double mm_lo = -INFINITY, mm_hi = -INFINITY;
                 int first_fail = 0x7fffffff;
                 for (int w = 0; w < kWarps; ++w) {
                     const double* p1 = sm.p1 + (size_t)w * P1_COUNT * 32 + lane;
                     const double* p3 = sm.p3 + (size_t)w * P3_COUNT * 32 + lane;
-                    sv += p1[P1_V * 32]; sd += p1[P1_D * 32]; jl += p1[P1_JL * 32]; jq += p1[P1_JQ * 32];
-                    trav += p1[P1_TRAV * 32];
-                    sum_e += p3[P3_SUM_E * 32]; sum_o += p3[P3_SUM_O * 32]; sum_abs += p3[P3_SUM_ABS * 32];
-                    resp += p3[P3_RESP * 32];
-                    mm = fmax(mm, p3[P3_MM * 32]);
-                    max_o = fmax(max_o, p3[P3_MAX_O * 32]);
+                    f.sv += p1[P1_V * 32]; f.sd += p1[P1_D * 32]; f.jl += p1[P1_JL * 32]; f.jq += p1[P1_JQ * 32];
+                    f.trav += p1[P1_TRAV * 32];
+                    r.sum_e += p3[P3_SUM_E * 32]; r.sum_o += p3[P3_SUM_O * 32]; r.sum_abs += p3[P3_SUM_ABS * 32];
+                    r.resp += p3[P3_RESP * 32];
+                    r.mm = fmax(r.mm, p3[P3_MM * 32]);
+                    r.max_o = fmax(r.max_o, p3[P3_MAX_O * 32]);
+                    mm_lo = fmax(mm_lo, p3[P3_MM_LO * 32]);
+                    mm_hi = fmax(mm_hi, p3[P3_MM_HI * 32]);
                     first_fail = min(first_fail, sm.ff[w * 32 + lane]);
                 }
+                f.T = T;
                 const bool vel_ok = kGiven ? first_fail != -2 : pm[PM_VEL_OK] != 0.0;
                 const bool acc_ok = kGiven ? first_fail != -1 : !(pm[PM_VEL_OK] < 0.0);  // fails only under ETP_RELAX_Q2_ACCELERATION
                 double bd = st.bd_harm ? st.bd_harm[c_dense] : 0.0;
@@ -1354,81 +1193,28 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     }
                 }
                 bd_out = bd;
-                if (O > 0) {
-                    c[ETP_C_BAYES] = (sum_e + sum_o + bd) / (double)(O * 2);  // risk_costs.py:148-150
-                    c[ETP_C_EQUALITY] = sum_abs / (double)O;                  // :176-178
-                    {  // max(...) ** 10 (:208) as four multiplications: pow() alone was a third of this serial section
-                        const double x = fmax(mm, bd), x2 = x * x, x4 = x2 * x2;
-                        c[ETP_C_MAXIMIN] = x4 * x4 * x2;
-                    }
-                    c[ETP_C_EGO] = sum_e + bd;                                // :226
-                    c[ETP_C_RESPONSIBILITY] = resp;
-                }
-                const bool risk_in_cost = pr.w[ETP_W_RISK_COST] > 0.0 && st.has_pred && pr.planner_mode == ETP_MODE_RISK;
-                if (risk_in_cost)  // calc_trajectory_cost.py:130-136
-                    c[ETP_C_RISK_TOTAL] = pr.w[ETP_W_BAYES] * c[ETP_C_BAYES] + pr.w[ETP_W_EQUALITY] * c[ETP_C_EQUALITY] +
-                                          pr.w[ETP_W_MAXIMIN] * c[ETP_C_MAXIMIN] +
-                                          pr.w[ETP_W_RESPONSIBILITY] * pr.w[ETP_W_BAYES] * c[ETP_C_RESPONSIBILITY] +
-                                          pr.w[ETP_W_EGO] * c[ETP_C_EGO];
-                const double mean_v = sv / (double)T;
-                int vel_mode = st.vel_mode;
-                double vel_target = st.vel_target;
-                double factor = st.factor_list ? st.factor_list[c_dense] : st.factor;
-                if (st.goal.on) {
-                    const int gf = s_goal[lane];
-                    if (gf & GF_START_INSIDE) {  // inside the goal area: the goal's velocity, else slow (:452-467)
-                        vel_mode = st.goal.has_vel ? 0 : 2;
-                        vel_target = st.goal.vel_mid;
-                    } else {                     // :469-519
-                        vel_mode = st.goal.vel_kind;
-                        vel_target = st.goal.vel_out;
-                    }
-                    factor = 1.0;                // get_cost_factor, :375-415
-                    bool in_time = false;
-                    if (gf & GF_REACHED) {
-                        factor = 0.01;
-                        in_time = st.goal.time_first < T;
-                        if (in_time) factor = 0.0001;
-                    }
-                    if (!in_time && st.goal.ego_in_goal && (gf & GF_OUTSIDE)) factor = 10.0;
-                }
-                switch (vel_mode) {  // calc_trajectory_cost.py:438-519 outcome forms
-                    case 0: c[ETP_C_VELOCITY] = fabs(vel_target - mean_v); break;
-                    case 1: c[ETP_C_VELOCITY] = 30.0 - mean_v; break;
-                    case 2: c[ETP_C_VELOCITY] = mean_v; break;
-                    default: c[ETP_C_VELOCITY] = 0.0;
-                }
-                c[ETP_C_DIST_TO_GLOBAL_PATH] = sd / (double)T;  // :726-736
-                c[ETP_C_LON_JERK] = jl / (double)T;             // :418-435
-                c[ETP_C_LAT_JERK] = jq / (double)T;
-                c[ETP_C_TRAVELLED_DIST] = trav;
-                c[ETP_C_FACTOR] = factor;
-                // validity level (validity_checks.py:31-122)
+                f.bd = bd;
+                f.gf = s_goal[lane];
+                f.factor = st.factor_list ? st.factor_list[c_dense] : st.factor;
+                // validity tests that precede the risk (validity_checks.py:31-115)
                 const int cf = (first_fail == 0x7fffffff || first_fail < 0) ? 0 : (first_fail & 3);
-                if (!vel_ok) { level = 0; reason = ETP_REASON_VELOCITY; }
-                else if (!acc_ok) { level = 0; reason = ETP_REASON_ACCELERATION; }
-                else if (cf) { level = 0; reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
-                else if (ext == 1 || s_hit[lane]) { level = 1; reason = ETP_REASON_COLLISION; }
-                else if (st.has_pred ? (bd != 0.0) : (ext == 2)) { level = 2; reason = ETP_REASON_BOUNDARIES; }
-                else if (pr.planner_mode == ETP_MODE_RISK && st.has_pred && O > 0 &&
-                         (sum_e > pr.max_risk || max_o > pr.max_risk)) { level = 3; reason = ETP_REASON_MAX_RISK; }
-                else { level = 10; reason = ETP_REASON_NONE; }
-                // weighted sum (calc_trajectory_cost.py:321-346); risk-only weights below level 10 if requested
-                const bool risk_only = level < 10 && pr.multi_cost;
-                double cost = 0.0;
-                if (risk_in_cost) cost += pr.w[ETP_W_RISK_COST] * c[ETP_C_RISK_TOTAL];
-                if (pr.w[ETP_W_LON_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LON_JERK]) * c[ETP_C_LON_JERK];
-                if (pr.w[ETP_W_LAT_JERK] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_LAT_JERK]) * c[ETP_C_LAT_JERK];
-                if (pr.w[ETP_W_VELOCITY] > 0.0) cost += (risk_only ? 0.0 : pr.w[ETP_W_VELOCITY]) * c[ETP_C_VELOCITY];
-                if (pr.w[ETP_W_DIST_TO_GLOBAL_PATH] > 0.0)
-                    cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GLOBAL_PATH]) * c[ETP_C_DIST_TO_GLOBAL_PATH];
-                if (pr.w[ETP_W_TRAVELLED_DIST] > 0.0)
-                    cost += (risk_only ? 0.0 : pr.w[ETP_W_TRAVELLED_DIST]) * c[ETP_C_TRAVELLED_DIST];
-                c[ETP_C_TOTAL] = factor * cost;
-                const unsigned long long hi = make_key_hi(level, c[ETP_C_TOTAL]);
-                const unsigned long long lo = (unsigned long long)c_dense;
-                if (key_less(hi, lo, lb.hi, lb.lo)) { lb.hi = hi; lb.lo = lo; lb.cost = c[ETP_C_TOTAL]; lb.level = level; }
-                lb.scored += 1;
+                f.pre_level = -1; f.pre_reason = ETP_REASON_NONE;
+                if (!vel_ok) { f.pre_level = 0; f.pre_reason = ETP_REASON_VELOCITY; }
+                else if (!acc_ok) { f.pre_level = 0; f.pre_reason = ETP_REASON_ACCELERATION; }
+                else if (cf) { f.pre_level = 0; f.pre_reason = cf == 1 ? ETP_REASON_CURV_LVC : ETP_REASON_CURV_HVC; }
+                else if (ext == 1 || s_hit[lane]) { f.pre_level = 1; f.pre_reason = ETP_REASON_COLLISION; }
+                else if (st.has_pred ? (bd != 0.0) : (ext == 2)) { f.pre_level = 2; f.pre_reason = ETP_REASON_BOUNDARIES; }
+                assemble_costs(st, pr, O, f, r, c, level, reason);
+                if (st.refine) {
+                    const bool risk_in_cost = pr.w[ETP_W_RISK_COST] > 0.0 && st.has_pred && pr.planner_mode == ETP_MODE_RISK;
+                    bound = cost_bound(pr, O, r, bd, c, risk_in_cost);
+                    // decisions fp32 cannot make: the maximin gate of an obstacle, the max-risk level
+                    amb = O > 0 && fmax(mm_lo, bd) != fmax(mm_hi, bd);
+                    if (f.pre_level < 0 && pr.planner_mode == ETP_MODE_RISK && st.has_pred && O > 0) {
+                        const double tol = 2.0 * kTolRisk * pr.max_risk + O * kTolRiskAbs;
+                        amb = amb || fabs(r.sum_e - pr.max_risk) <= tol || fabs(r.max_o - pr.max_risk) <= tol;
+                    }
+                }
             }
             if (active) {
                 if (o_cost) {
@@ -1438,85 +1224,18 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                 if (out.bd_harm) out.bd_harm[cl] = bd_out;
                 if (out.level) out.level[cl] = (uint8_t)level;
                 if (out.reason) out.reason[cl] = (uint8_t)reason;
+                // selection workspace (etp_select.cu)
+                st.ws_cost[cl] = c[ETP_C_TOTAL];
+                st.ws_meta[cl] = live ? (uint8_t)(level | (amb ? SEL_AMB : 0)) : (uint8_t)SEL_SKIPPED;
+                if (st.refine) {
+                    st.ws_bound[cl] = bound;
+                    st.ws_bd[cl] = bd_out;
+                    st.ws_gf[cl] = (uint8_t)s_goal[lane];
+                }
             }
         }
         // no barrier here: warp 0 reads only p1 / p3 / ff; p1 / ff are next written after barrier (a) of the next
         // tile, p3 (aliasing the ego samples) after barrier (a) as well
-    }
-
-    // ---- block arg-min, then grid arg-min by the last block to finish ---------------------------
-    if (warp == 0) {
-        unsigned long long hi = lb.hi, lo = lb.lo;
-        double cst = lb.cost;
-        int lvl = lb.level, scored = lb.scored;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ohi = __shfl_xor_sync(kFull, hi, o), olo = __shfl_xor_sync(kFull, lo, o);
-            const double oc = __shfl_xor_sync(kFull, cst, o);
-            const int ol = __shfl_xor_sync(kFull, lvl, o);
-            scored += __shfl_xor_sync(kFull, scored, o);
-            if (key_less(ohi, olo, hi, lo)) { hi = ohi; lo = olo; cst = oc; lvl = ol; }
-        }
-        if (lane == 0) {
-            BestRec b;
-            b.key_hi = hi; b.key_lo = lo; b.cost = cst; b.level = lvl; b.n_scored = scored;
-            b.index = hi == ~0ull ? -1 : (int)lo;
-            b.list_index = -1;
-            block_best[blockIdx.x] = b;
-            __threadfence();
-            const unsigned done = atomicAdd(&counters[0], 1u);
-            is_last = (done == gridDim.x - 1);
-        }
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        unsigned long long hi = ~0ull, lo = ~0ull;
-        double cst = 0.0;
-        int lvl = -1, scored = 0;
-        for (int b = tid; b < (int)gridDim.x; b += kThreads) {
-            const volatile BestRec* r = block_best + b;
-            const unsigned long long bhi = r->key_hi, blo = r->key_lo;
-            scored += r->n_scored;
-            if (key_less(bhi, blo, hi, lo)) { hi = bhi; lo = blo; cst = r->cost; lvl = r->level; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ohi = __shfl_xor_sync(kFull, hi, o), olo = __shfl_xor_sync(kFull, lo, o);
-            const double oc = __shfl_xor_sync(kFull, cst, o);
-            const int ol = __shfl_xor_sync(kFull, lvl, o);
-            scored += __shfl_xor_sync(kFull, scored, o);
-            if (key_less(ohi, olo, hi, lo)) { hi = ohi; lo = olo; cst = oc; lvl = ol; }
-        }
-        if (lane == 0) {
-            wbest[warp].key_hi = hi; wbest[warp].key_lo = lo; wbest[warp].cost = cst; wbest[warp].level = lvl;
-            wbest[warp].n_scored = scored;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            BestRec b = wbest[0];
-            for (int w = 1; w < kWarps; ++w) {
-                const int n = b.n_scored + wbest[w].n_scored;
-                if (key_less(wbest[w].key_hi, wbest[w].key_lo, b.key_hi, b.key_lo)) b = wbest[w];
-                b.n_scored = n;
-            }
-            b.index = b.key_hi == ~0ull ? -1 : (int)b.key_lo;
-            b.list_index = -1;
-            if (kGiven) {
-                b.list_index = b.index;
-            } else if (b.index >= 0) {
-                // rank among non-skipped candidates of this range = position in the reference's fp_list
-                const int pb = b.index / st.nd, idb = b.index % st.nd;
-                int li = 0;
-                for (int pp = st.p_begin; pp < pb; ++pp) li += st.nd - prof_nskip[pp - st.p_begin];
-                const double dsb = st.prof_meta[(size_t)(pb - st.p_begin) * PM_COUNT + PM_DS];
-                for (int id = 0; id < idb; ++id) li += (dsb <= fabs(st.d_list[id])) ? 0 : 1;
-                b.list_index = li;
-            }
-            *best_out = b;
-            counters[0] = 0;  // re-arm both counters for the next launch
-            counters[1] = 0;
-        }
     }
 }
 
@@ -1524,9 +1243,8 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 // host-side launcher
 // ---------------------------------------------------------------------------------------------
 template <typename R, int NT, bool kSym, bool kGiven>
-static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
-                                  unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
-                                  cudaStream_t stream) {
+static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
+                                  int* grid_out, cudaStream_t stream) {
     const int O = st.has_pred ? st.O : 0;
     const size_t smem = Smem<R>::bytes(st.Tmax, O);
     cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT, kSym, kGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1542,15 +1260,14 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
-    score_kernel<R, NT, kSym, kGiven><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, block_best, counters, best_out, nskip);
+    score_kernel<R, NT, kSym, kGiven><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, BestRec* block_best,
-                         unsigned* counters, BestRec* best_out, const int* nskip, int num_sms, int* grid_out,
-                         cudaStream_t stream) {
+cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
+                         int* grid_out, cudaStream_t stream) {
 #define ETP_LAUNCH(R, NT, SYM, GIVEN) \
-    launch_score_t<R, NT, SYM, GIVEN>(st, pr, out, block_best, counters, best_out, nskip, num_sms, grid_out, stream)
+    launch_score_t<R, NT, SYM, GIVEN>(st, pr, out, counters, num_sms, grid_out, stream)
     if (st.given) {  // caller-provided trajectories: the API-compatibility path, generic tables only
         if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1, false, true);
         return ETP_LAUNCH(float, -1, false, true);

@@ -1,0 +1,592 @@
+// Selection of the best candidate (sm_100a): highest non-empty validity level, then cost, then generation order
+// (frenet_functions.py:562-593, frenet_planner.py:457,555-558), exact although the fused kernel scores in fp32.
+//
+//   select_kernel  : scans the per-candidate workspace the fused kernel leaves behind (total cost, a bound on what fp32
+//                    rounding can have moved it by, level, "a decision of this candidate depends on rounding").  In fp64
+//                    mode (bound 0) the minimum IS the selection.  In fp32 mode it collects every candidate that can
+//                    still be the winner: those whose decisions are ambiguous, and those of the top level whose lower
+//                    bound cost - bound does not exceed the smallest upper bound cost + bound.  One survivor, nothing
+//                    ambiguous, no other shard: it is the winner.  Otherwise:
+//   rescore_kernel : one CTA per surviving candidate re-scores it in fp64 from the exact inputs with the reference's own
+//                    formulas (atan2 impact angles, Genz' BVU in MVNDST's corner order), threads over (sample, obstacle)
+//                    pairs and over the 36 BVU evaluations of an un-gated pair; level and cost are re-decided, the
+//                    materialised rows of the candidate are overwritten, and the last CTA takes the minimum of the exact
+//                    keys.  The same idea as gate_exact / band_coefs_exact of the fused kernel, applied to the arg-min
+//                    and to the max-risk / maximin-gate decisions.
+#include "etp_harm.cuh"
+#include "etp_launch.h"
+
+namespace etp {
+
+constexpr int kSelThreads = 256;
+constexpr int kSelPer = 16;                       // workspace entries per thread
+constexpr int kSelChunk = kSelThreads * kSelPer;  // entries per block
+constexpr int kResThreads = 256;
+constexpr int kQChunk = 32;                       // un-gated pairs whose 36 BVU values are buffered at a time
+
+struct SelBlock {
+    int rank_max;         // highest level rank among the block's unambiguous candidates (-1: none)
+    int n_scored, n_amb;  // non-skipped / ambiguous candidates
+    int arg;              // column of the smallest (upper, column) at rank_max
+    double upper, lower;  // min of cost + bound / of cost - bound at rank_max
+};
+
+struct RescoreRec {
+    double cost;
+    int rank, level, cl, pad;
+};
+
+__device__ __forceinline__ double order_cost(double c) { return c != c ? INFINITY : c; }  // NaN costs never win
+
+__device__ __forceinline__ int dense_of(const DevStep& st, bool given, int cl) {
+    if (given) return cl;
+    const int kl = cl / st.nd, id = cl - kl * st.nd;
+    return (st.p_begin + st.shard_index + kl * st.shard_count) * st.nd + id;
+}
+
+// deterministic block sum (fixed tree): every thread gets the total
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w];
+    return s;
+}
+
+// rank of dense candidate `index` among the non-skipped candidates of [c_begin, c_end) = position in the reference's
+// fp_list; all threads of the block take part
+__device__ int list_index_of(const DevStep& st, const int* __restrict__ nskip, bool given, int index, double* scratch) {
+    if (given || index < 0) return index;
+    const int pb = index / st.nd, idb = index % st.nd;
+    double n = 0.0;
+    for (int pp = st.p_begin + threadIdx.x; pp < pb; pp += blockDim.x) n += (double)(st.nd - nskip[pp - st.p_begin]);
+    const double dsb = st.prof_meta[(size_t)(pb - st.p_begin) * PM_COUNT + PM_DS];
+    for (int id = threadIdx.x; id < idb; id += blockDim.x) n += (dsb <= fabs(st.d_list[id])) ? 0.0 : 1.0;
+    return (int)block_sum(n, scratch);
+}
+
+__device__ __forceinline__ void write_best(BestRec* out, int level, double cost, int index, int n_scored, int list_index) {
+    BestRec b;
+    b.key_hi = index < 0 ? ~0ull : make_key_hi(level, cost);
+    b.key_lo = index < 0 ? ~0ull : make_key_lo(cost, (unsigned long long)index);
+    b.cost = cost;
+    b.index = index;
+    b.level = level;
+    b.n_scored = n_scored;
+    b.list_index = list_index;
+    *out = b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// select_kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_constant__ DevStep st, SelectBufs sb, BestRec* __restrict__ best_out,
+                                                            const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
+                                                            int always_rescore) {
+    __shared__ int s_i[kSelThreads / 32];
+    __shared__ double s_u[kSelThreads / 32], s_l[kSelThreads / 32];
+    __shared__ int s_a[kSelThreads / 32];
+    __shared__ int s_rank, s_last, s_cnt, s_nsc, s_namb;
+    __shared__ double s_scratch[kSelThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Cs = st.n_local;
+    const bool refine = st.refine != 0;
+    SelBlock* blocks = reinterpret_cast<SelBlock*>(sb.blocks);
+    const int base = blockIdx.x * kSelChunk;
+
+    // ---- pass 1: this block's entries ------------------------------------------------------------
+    unsigned char meta[kSelPer];
+    double lo[kSelPer], up[kSelPer];
+    int rmax = -1, nsc = 0, namb = 0;
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) {
+        const int cl = base + k * kSelThreads + tid;
+        meta[k] = SEL_SKIPPED;
+        lo[k] = up[k] = INFINITY;
+        if (cl < Cs) {
+            meta[k] = st.ws_meta[cl];
+            if (meta[k] != SEL_SKIPPED) {
+                const double c = order_cost(st.ws_cost[cl]);
+                const double b = refine ? (double)st.ws_bound[cl] : 0.0;
+                lo[k] = c - b;
+                up[k] = c + b;
+                ++nsc;
+                if (meta[k] & SEL_AMB) {
+                    ++namb;
+                    sb.list[atomicAdd(&sb.hdr[2], 1)] = cl;  // re-scored whatever the threshold turns out to be
+                } else {
+                    rmax = max(rmax, level_rank(meta[k]));
+                }
+            }
+        }
+    }
+    rmax = __reduce_max_sync(kFull, rmax);
+    nsc = __reduce_add_sync(kFull, nsc);
+    namb = __reduce_add_sync(kFull, namb);
+    if (lane == 0) { s_i[warp] = rmax; s_a[warp] = nsc; s_u[warp] = (double)namb; }
+    __syncthreads();
+    if (tid == 0) {
+        int r = -1, a = 0, m = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) { r = max(r, s_i[w]); a += s_a[w]; m += (int)s_u[w]; }
+        s_rank = r; s_nsc = a; s_namb = m;
+    }
+    __syncthreads();
+    const int brank = s_rank;
+    double bu = INFINITY, bl = INFINITY;
+    int ba = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < kSelPer; ++k) {
+        if (meta[k] == SEL_SKIPPED || (meta[k] & SEL_AMB) || level_rank(meta[k]) != brank) continue;
+        const int cl = base + k * kSelThreads + tid;
+        if (up[k] < bu || (up[k] == bu && cl < ba)) { bu = up[k]; ba = cl; }
+        bl = fmin(bl, lo[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ou = __shfl_xor_sync(kFull, bu, o), ol = __shfl_xor_sync(kFull, bl, o);
+        const int oa = __shfl_xor_sync(kFull, ba, o);
+        if (ou < bu || (ou == bu && oa < ba)) { bu = ou; ba = oa; }
+        bl = fmin(bl, ol);
+    }
+    __syncthreads();
+    if (lane == 0) { s_u[warp] = bu; s_l[warp] = bl; s_a[warp] = ba; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kSelThreads / 32; ++w) {
+            if (s_u[w] < bu || (s_u[w] == bu && s_a[w] < ba)) { bu = s_u[w]; ba = s_a[w]; }
+            bl = fmin(bl, s_l[w]);
+        }
+        SelBlock r;
+        r.rank_max = brank; r.n_scored = s_nsc; r.n_amb = s_namb; r.arg = ba; r.upper = bu; r.lower = bl;
+        blocks[blockIdx.x] = r;
+        __threadfence();
+        s_last = atomicAdd(&sb.counters[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    // ---- last block: global top level and threshold ----------------------------------------------
+    const int nblk = (int)gridDim.x;
+    int hi = -1, tot = 0, amb = 0;
+    for (int b = tid; b < nblk; b += kSelThreads) {
+        const volatile SelBlock* r = blocks + b;
+        hi = max(hi, r->rank_max);
+        tot += r->n_scored;
+        amb += r->n_amb;
+    }
+    hi = __reduce_max_sync(kFull, hi);
+    tot = __reduce_add_sync(kFull, tot);
+    amb = __reduce_add_sync(kFull, amb);
+    if (lane == 0) { s_i[warp] = hi; s_a[warp] = tot; s_u[warp] = (double)amb; }
+    __syncthreads();
+    if (tid == 0) {
+        int r = -1, a = 0, m = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) { r = max(r, s_i[w]); a += s_a[w]; m += (int)s_u[w]; }
+        s_rank = r; s_nsc = a; s_namb = m; s_cnt = m;  // the list already holds the ambiguous candidates
+    }
+    __syncthreads();
+    hi = s_rank;
+    const int n_scored = s_nsc, n_amb = s_namb;
+    double thr = INFINITY;
+    int arg = 0x7fffffff;
+    for (int b = tid; b < nblk; b += kSelThreads) {
+        const volatile SelBlock* r = blocks + b;
+        if (r->rank_max != hi || hi < 0) continue;
+        const double u = r->upper;
+        const int a = r->arg;
+        if (u < thr || (u == thr && a < arg)) { thr = u; arg = a; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ou = __shfl_xor_sync(kFull, thr, o);
+        const int oa = __shfl_xor_sync(kFull, arg, o);
+        if (ou < thr || (ou == thr && oa < arg)) { thr = ou; arg = oa; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_u[warp] = thr; s_a[warp] = arg; }
+    __syncthreads();
+    for (int w = 0; w < kSelThreads / 32; ++w)
+        if (s_u[w] < thr || (s_u[w] == thr && s_a[w] < arg)) { thr = s_u[w]; arg = s_a[w]; }
+    __syncthreads();
+
+    int done_cl = -2;  // >= -1: the selection is final (column, -1 = no candidate)
+    if (n_scored == 0) done_cl = -1;
+    else if (!refine) done_cl = arg;  // exact costs: the minimum is the selection (n_amb == 0, so hi >= 0)
+    if (done_cl == -2) {
+        // ---- candidates that can still win: ambiguous ones, and the top level's within reach of the threshold --------
+        for (int b = 0; b < nblk; ++b) {
+            const volatile SelBlock* r = blocks + b;
+            const bool look = hi >= 0 && r->rank_max == hi && r->lower <= thr;
+            if (!look) continue;
+            const int bb = b * kSelChunk;
+            for (int k = 0; k < kSelPer; ++k) {
+                const int cl = bb + k * kSelThreads + tid;
+                if (cl >= Cs) continue;
+                const unsigned char m = st.ws_meta[cl];
+                if (m == SEL_SKIPPED || (m & SEL_AMB) || level_rank(m) != hi) continue;
+                if (order_cost(st.ws_cost[cl]) - (double)st.ws_bound[cl] <= thr) sb.list[atomicAdd(&s_cnt, 1)] = cl;
+            }
+        }
+        __syncthreads();
+        if (s_cnt == 1 && n_amb == 0 && !always_rescore) done_cl = sb.list[0];
+    }
+    if (done_cl != -2) {
+        const int index = done_cl < 0 ? -1 : dense_of(st, given != 0, done_cl);
+        const int li = list_index_of(st, nskip, given != 0, index, s_scratch);
+        if (tid == 0) {
+            const int level = done_cl < 0 ? -1 : (int)(st.ws_meta[done_cl] & 63);
+            write_best(best_out, level, done_cl < 0 ? 0.0 : st.ws_cost[done_cl], index, n_scored, li);
+        }
+    }
+    if (tid == 0) {
+        sb.hdr[0] = done_cl != -2 ? 0 : s_cnt;  // candidates left for rescore_kernel
+        sb.hdr[1] = n_scored;
+        sb.hdr[2] = 0;
+        sb.counters[0] = 0;  // re-arm
+        sb.counters[1] = 0;
+        *tile_counter = 0;   // the fused kernel's tile counter
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rescore_kernel
+// ---------------------------------------------------------------------------------------------
+struct ObsSample {
+    double mx, my, psi, vo, ke, ko;
+    bool prot;
+};
+
+__device__ __forceinline__ ObsSample load_obs(const DevStep& st, int o, int t) {
+    ObsSample s;
+    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+    s.mx = rp[0]; s.my = rp[1];
+    s.psi = st.raw_yaw[(size_t)o * st.Tp + t];
+    s.vo = st.raw_vel[(size_t)o * st.Tp + t];
+    s.ke = st.obs_const[o * OC_COUNT + OC_KE];
+    s.ko = st.obs_const[o * OC_COUNT + OC_KO];
+    s.prot = st.obs_const[o * OC_COUNT + OC_PROT] != 0.0;
+    return s;
+}
+
+// harm logits of (ego sample t, prediction sample t): harm_estimation.py:313-332, the reference's own expressions
+__device__ __forceinline__ void harm_logits(const Tab<double>& tab, const ObsSample& s, double ex, double ey, double eyaw, double ev,
+                                            double& ae, double& ao) {
+    const double dv = delta_v(0.0, 0.0, ev, eyaw, s.vo, 0.0, 0.0, s.psi);
+    if (s.prot) {
+        double ce, co;
+        bool amb = false;
+        impact_coefs(tab, ex, ey, 0.0, 0.0, eyaw, s.mx, s.my, 0.0, 0.0, s.psi, ce, co, amb);
+        ae = tab.lr_speed * (s.ke * dv) + ce;
+        ao = tab.lr_speed * (s.ko * dv) + co;
+    } else {
+        ae = tab.lr1s_speed * (s.ke * dv);
+        ao = tab.ped_speed * (s.ko * dv);
+    }
+}
+
+template <bool kGiven>
+__global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr,
+                                                             DevOut out, int out_f32, SelectBufs sb, BestRec* __restrict__ best_out,
+                                                             const int* __restrict__ nskip) {
+    using U = unsigned long long;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int count = sb.hdr[0];
+    if (count == 0) return;  // the selection was final
+    const int Ts = st.Tmax;
+    const int O = st.has_pred ? st.O : 0;
+    const int On = O > 0 ? O : 1;
+    const int tid = threadIdx.x;
+    double* e_x = reinterpret_cast<double*>(smem_raw);
+    double* e_y = e_x + Ts;
+    double* e_yaw = e_y + Ts;
+    double* e_v = e_yaw + Ts;
+    double* e_c = e_v + Ts;
+    double* e_s = e_c + Ts;
+    U* mx = reinterpret_cast<U*>(e_s + Ts);                       // [4][On]: ego risk, obstacle risk, ego logit, obstacle logit
+    double* buf = reinterpret_cast<double*>(mx + 4 * On);        // [kQChunk][36]
+    unsigned* queue = reinterpret_cast<unsigned*>(buf + kQChunk * 36);  // [(Ts-1) * On]
+    __shared__ Tab<double> tab;
+    __shared__ int s_qn, s_last;
+    __shared__ double s_scratch[kResThreads / 32];
+    if (tid == 0) fill_tab<double>(tab, pr, 0.0);
+    const bool mahal = pr.mahalanobis != 0;
+    RescoreRec* res = reinterpret_cast<RescoreRec*>(sb.res);
+
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        __syncthreads();  // previous candidate consumed; tab visible
+        const int cl = sb.list[i];
+        const unsigned char meta = st.ws_meta[cl];
+        const int kl = kGiven ? 0 : cl / st.nd, id = kGiven ? 0 : cl - kl * st.nd;
+        const int pl = kGiven ? cl : st.shard_index + kl * st.shard_count;
+        const int c_dense = kGiven ? cl : (st.p_begin + pl) * st.nd + id;
+        const double* gp = kGiven ? st.given + cl : st.prof + (size_t)pl * PF_COUNT * Ts;
+        const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+        const bool low = kGiven ? false : pm[PM_LOW] != 0.0;
+        const int T = kGiven ? st.given_T[cl] : (int)pm[PM_T];
+        if (tid == 0) s_qn = 0;
+        for (int k = tid; k < 4 * On; k += kResThreads) mx[k] = Enc<double>::enc(-INFINITY);
+
+        // ---- the candidate's samples and the sums of the cost terms (frenet_functions.py:336-435) ----
+        double sv = 0, sd = 0, jl = 0, jq = 0;
+        {
+            Poly5 q{};
+            if (!kGiven) q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+            for (int t = tid; t < T; t += kResThreads) {
+                const TrajPoint tp = kGiven ? given_point(gp, Ts, st.given_stride, t) : traj_point(q, low, gp, Ts, t, st.dt);
+                e_x[t] = tp.f[ETP_F_X]; e_y[t] = tp.f[ETP_F_Y]; e_yaw[t] = tp.f[ETP_F_YAW]; e_v[t] = tp.f[ETP_F_V];
+                e_c[t] = tp.cos_yaw; e_s[t] = tp.sin_yaw;
+                sv += tp.f[ETP_F_V];
+                sd += fabs(tp.f[ETP_F_D]);
+                jl += tp.f[ETP_F_S_DDD] * tp.f[ETP_F_S_DDD];
+                jq += tp.f[ETP_F_D_DDD] * tp.f[ETP_F_D_DDD];
+            }
+        }
+        CandFacts f;
+        f.sv = block_sum(sv, s_scratch);
+        f.sd = block_sum(sd, s_scratch);
+        f.jl = block_sum(jl, s_scratch);
+        f.jq = block_sum(jq, s_scratch);
+        double trav = 0;
+        for (int t = 1 + tid; t < T; t += kResThreads) {  // calc_trajectory_cost.py:739-757
+            const double dx = e_x[t - 1] - e_x[t], dy = e_y[t - 1] - e_y[t];
+            trav += sqrt(dx * dx + dy * dy);
+        }
+        f.trav = block_sum(trav, s_scratch);
+        f.T = T;
+
+        // ---- harm logits of every (t, o) sample; probability samples inside the 5 m gate are queued ----
+        for (int it = tid; it < (Ts - 1) * O; it += kResThreads) {
+            const int t = it / O, o = it - t * O;
+            const int n_pred = st.pred_len[o];
+            if (t < T - 1 && t < n_pred) {  // harm_estimation.py:234
+                const ObsSample s = load_obs(st, o, t);
+                double ae, ao;
+                harm_logits(tab, s, e_x[t], e_y[t], e_yaw[t], e_v[t], ae, ao);
+                atomicMax(mx + 2 * On + o, Enc<double>::enc(ae));
+                atomicMax(mx + 3 * On + o, Enc<double>::enc(ao));
+            }
+            if (t < T - 1 && t + 1 < n_pred) {  // collision_probability.py:194-203: ego[t+1], mean[t], orientation[t+1]
+                bool ungated = true;
+                if (!mahal) {
+                    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                    const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+                    const double len = 2 * st.obs_const[o * OC_COUNT + OC_HALFLEN];
+                    const double fx = cos(y1) * len / 2, fy = sin(y1) * len / 2;
+                    const double xe = e_x[t + 1], ye = e_y[t + 1];
+                    double ax = rp[0] - xe, ay = rp[1] - ye;
+                    double m = sqrt(ax * ax + ay * ay);
+                    ax = (rp[0] + fx) - xe; ay = (rp[1] + fy) - ye;
+                    m = fmin(m, sqrt(ax * ax + ay * ay));
+                    ax = (rp[0] - fx) - xe; ay = (rp[1] - fy) - ye;
+                    m = fmin(m, sqrt(ax * ax + ay * ay));
+                    ungated = !(m > 5.0);
+                }
+                if (ungated) queue[atomicAdd(&s_qn, 1)] = ((unsigned)t << 16) | (unsigned)o;
+            }
+        }
+        __syncthreads();
+
+        // ---- queued samples: nine rectangles x four BVU corners each (collision_probability.py:205-252) ----
+        const int qn = s_qn;
+        for (int q0 = 0; q0 < qn; q0 += kQChunk) {
+            const int qc = min(kQChunk, qn - q0);
+            if (!mahal) {
+                for (int item = tid; item < qc * 36; item += kResThreads) {
+                    const int q = item / 36, k = item - q * 36;
+                    const unsigned ent = queue[q0 + q];
+                    const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
+                    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                    const double* cv = st.raw_cov + ((size_t)o * st.Tp + t) * 4;
+                    double c00 = cv[0], c01 = cv[1], c10 = cv[2], c11 = cv[3];
+                    if (c00 == 0.0 && c01 == 0.0 && c10 == 0.0 && c11 == 0.0) { c00 = 0.1; c11 = 0.1; }  // :210-212
+                    const double sx = sqrt(c00), sy = sqrt(c11);
+                    const double isx = 1.0 / sx, isy = 1.0 / sy, rho = c10 / sy / sx;
+                    const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+                    const double len = 2 * st.obs_const[o * OC_COUNT + OC_HALFLEN];
+                    const double exo = cos(y1) * len / 2, eyo = sin(y1) * len / 2;
+                    const double ddx = e_x[t + 1] - rp[0], ddy = e_y[t + 1] - rp[1];
+                    const int r = k >> 2, km = r / 3, jb = r - km * 3, cn = k & 3;
+                    const double sg = km == 0 ? 0.0 : (km == 1 ? 1.0 : -1.0), sbx = jb == 0 ? 0.0 : (jb == 1 ? 1.0 : -1.0);
+                    const double ox = tab.rr * e_c[t + 1], oy = tab.rr * e_s[t + 1];
+                    const double ux = ddx - sg * exo, uy = ddy - sg * eyo;
+                    const double bx = ux + sbx * ox, by = uy + sbx * oy;
+                    const double xl = (bx - tab.hx) * isx, xu = (bx + tab.hx) * isx;
+                    const double yl = (by - tab.hy) * isy, yu = (by + tab.hy) * isy;
+                    buf[q * 36 + k] = bvu_d((cn & 1) ? xu : xl, (cn & 2) ? yu : yl, rho);
+                }
+                __syncthreads();
+            }
+            if (tid < qc) {
+                const unsigned ent = queue[q0 + tid];
+                const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
+                double prob = 0.0;
+                if (mahal) {
+                    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                    const double* cv = st.raw_cov + ((size_t)o * st.Tp + t) * 4;
+                    const double det = cv[0] * cv[3] - cv[1] * cv[2];
+                    prob = inv_mahalanobis<double>(e_x[t + 1], e_y[t + 1], rp[0], rp[1], cv[3] / det, -(cv[1] + cv[2]) / det, cv[0] / det);
+                } else {
+                    const double* b = buf + tid * 36;
+                    for (int r = 0; r < 9; ++r) prob += b[4 * r] - b[4 * r + 1] - b[4 * r + 2] + b[4 * r + 3];  // MVNDST's corner order
+                    prob = prob / 3;
+                }
+                const ObsSample s = load_obs(st, o, t);
+                double ae, ao;
+                harm_logits(tab, s, e_x[t], e_y[t], e_yaw[t], e_v[t], ae, ao);
+                const double he = sigmoid_harm<double>(s.prot ? tab.lr_const : tab.lr1s_const, ae);
+                const double ho = sigmoid_harm<double>(s.prot ? tab.lr_const : tab.neg_ped_const, ao);
+                atomicMax(mx + o, Enc<double>::enc(he * prob));  // risk_costs.py:88-95
+                atomicMax(mx + On + o, Enc<double>::enc(ho * prob));
+            }
+            __syncthreads();
+        }
+
+        // ---- per-obstacle maxima -> principles, level, cost (thread 0; obstacles in order) ----------
+        if (tid == 0) {
+            RiskSums r{0, 0, 0, 0, -INFINITY, -INFINITY};
+            const bool gate = (pr.relaxed & ETP_RELAX_Q3_MAXIMIN) != 0;
+            for (int o = 0; o < O; ++o) {
+                const bool prt = st.obs_const[o * OC_COUNT + OC_PROT] != 0.0;
+                const double re = fmax(Enc<double>::dec(mx[o]), 0.0), ro = fmax(Enc<double>::dec(mx[On + o]), 0.0);
+                const double he = sigmoid_harm<double>(prt ? tab.lr_const : tab.lr1s_const, Enc<double>::dec(mx[2 * On + o]));
+                const double ho = sigmoid_harm<double>(prt ? tab.lr_const : tab.neg_ped_const, Enc<double>::dec(mx[3 * On + o]));
+                r.sum_e += re;
+                r.sum_o += ro;
+                r.sum_abs += fabs(re - ro);
+                r.resp -= st.obs_const[o * OC_COUNT + OC_RESP] * ro;
+                r.mm = fmax(r.mm, he * (((re < 10e-10) != gate) ? 1.0 : 0.0));
+                r.mm = fmax(r.mm, ho * (((ro < 10e-10) != gate) ? 1.0 : 0.0));
+                r.max_o = fmax(r.max_o, ro);
+                if (out.red) {
+                    const size_t Cp = out.c_stride;
+                    const double v[4] = {re, ro, he, ho};
+                    for (int k = 0; k < 4; ++k) {
+                        if (out_f32) reinterpret_cast<float*>(out.red)[((size_t)k * O + o) * Cp + cl] = (float)v[k];
+                        else reinterpret_cast<double*>(out.red)[((size_t)k * O + o) * Cp + cl] = v[k];
+                    }
+                }
+            }
+            const int level32 = meta & 63;
+            f.pre_level = level32 <= 2 ? level32 : -1;  // the tests before the risk are exact in the fused kernel
+            f.pre_reason = ETP_REASON_NONE;
+            f.bd = st.ws_bd[cl];
+            f.gf = st.ws_gf[cl];
+            f.factor = st.factor_list ? st.factor_list[c_dense] : st.factor;
+            double c[ETP_NUM_COST];
+            int level, reason;
+            assemble_costs(st, pr, O, f, r, c, level, reason);
+            if (out.cost) {
+                const size_t Cp = out.c_stride;
+                for (int k = 0; k < ETP_NUM_COST; ++k) {
+                    if (out_f32) reinterpret_cast<float*>(out.cost)[(size_t)k * Cp + cl] = (float)c[k];
+                    else reinterpret_cast<double*>(out.cost)[(size_t)k * Cp + cl] = c[k];
+                }
+            }
+            if (f.pre_level < 0) {
+                if (out.level) out.level[cl] = (uint8_t)level;
+                if (out.reason) out.reason[cl] = (uint8_t)reason;
+            }
+            // how the fp32 pass did against its own bound (diagnostics: etp_debug_counters)
+            if (!(meta & SEL_AMB) && level == level32) {
+                const double err = fabs(c[ETP_C_TOTAL] - st.ws_cost[cl]), b = (double)st.ws_bound[cl];
+                if (err > b) atomicAdd(&sb.stats[1], 1ull);
+                if (b > 0.0) atomicMax(&sb.stats[2], (unsigned long long)__float_as_uint((float)(err / b)));
+            }
+            atomicAdd(&sb.stats[0], 1ull);
+            RescoreRec rr;
+            rr.cost = c[ETP_C_TOTAL]; rr.rank = level_rank(level); rr.level = level; rr.cl = cl; rr.pad = 0;
+            res[i] = rr;
+        }
+    }
+
+    // ---- the last CTA takes the minimum of the exact keys ----------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&sb.counters[1], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ int s_r[kResThreads / 32], s_c[kResThreads / 32];
+    __shared__ double s_k[kResThreads / 32];
+    int br = -1, bc = 0x7fffffff;
+    double bk = INFINITY;
+    for (int i = tid; i < count; i += kResThreads) {
+        const volatile RescoreRec* r = res + i;
+        const int rk = r->rank, c = r->cl;
+        const double k = order_cost(r->cost);
+        if (rk > br || (rk == br && (k < bk || (k == bk && c < bc)))) { br = rk; bk = k; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int orr = __shfl_xor_sync(kFull, br, o), oc = __shfl_xor_sync(kFull, bc, o);
+        const double ok = __shfl_xor_sync(kFull, bk, o);
+        if (orr > br || (orr == br && (ok < bk || (ok == bk && oc < bc)))) { br = orr; bk = ok; bc = oc; }
+    }
+    if ((tid & 31) == 0) { s_r[tid >> 5] = br; s_c[tid >> 5] = bc; s_k[tid >> 5] = bk; }
+    __syncthreads();
+    for (int w = 0; w < kResThreads / 32; ++w)
+        if (s_r[w] > br || (s_r[w] == br && (s_k[w] < bk || (s_k[w] == bk && s_c[w] < bc)))) { br = s_r[w]; bk = s_k[w]; bc = s_c[w]; }
+    // the winner's own record (cost as computed, level)
+    __syncthreads();
+    for (int i = tid; i < count; i += kResThreads) {
+        const volatile RescoreRec* r = res + i;
+        if (r->cl == bc) { s_k[0] = r->cost; s_r[0] = r->level; }
+    }
+    __syncthreads();
+    const double wcost = s_k[0];
+    const int wlevel = s_r[0];
+    const int index = dense_of(st, kGiven, bc);
+    const int li = list_index_of(st, nskip, kGiven, index, s_scratch);
+    if (tid == 0) {
+        write_best(best_out, wlevel, wcost, index, sb.hdr[1], li);
+        sb.hdr[0] = 0;
+        sb.counters[1] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+size_t select_blocks_bytes(int n_local) { return sizeof(SelBlock) * (size_t)((n_local + kSelChunk - 1) / kSelChunk + 1); }
+size_t rescore_rec_bytes(int n_local) { return sizeof(RescoreRec) * (size_t)(n_local > 0 ? n_local : 1); }
+
+cudaError_t launch_select(const DevStep& st, const SelectBufs& sb, BestRec* best_out, const int* nskip, unsigned* tile_counter,
+                          bool given, bool always_rescore, cudaStream_t stream) {
+    const int nblk = (st.n_local + kSelChunk - 1) / kSelChunk;
+    select_kernel<<<nblk > 0 ? nblk : 1, kSelThreads, 0, stream>>>(st, sb, best_out, nskip, tile_counter, given ? 1 : 0, always_rescore ? 1 : 0);
+    return cudaGetLastError();
+}
+
+size_t rescore_smem_bytes(int Tmax, int O) {
+    const size_t On = O > 0 ? O : 1;
+    return sizeof(double) * 6 * Tmax + sizeof(unsigned long long) * 4 * On + sizeof(double) * kQChunk * 36 +
+           sizeof(unsigned) * (size_t)(Tmax - 1) * On + 16;
+}
+
+cudaError_t launch_rescore(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, const SelectBufs& sb,
+                           BestRec* best_out, const int* nskip, int num_sms, cudaStream_t stream) {
+    const size_t smem = rescore_smem_bytes(st.Tmax, st.has_pred ? st.O : 0);
+    long long grid = 2ll * num_sms;
+    if (grid > st.n_local) grid = st.n_local;
+    if (grid < 1) grid = 1;
+    const int f32 = precision == ETP_PRECISION_FP32 ? 1 : 0;
+    cudaError_t e;
+    if (st.given) {
+        e = cudaFuncSetAttribute(rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rescore_kernel<true><<<(int)grid, kResThreads, smem, stream>>>(st, pr, out, f32, sb, best_out, nskip);
+    } else {
+        e = cudaFuncSetAttribute(rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rescore_kernel<false><<<(int)grid, kResThreads, smem, stream>>>(st, pr, out, f32, sb, best_out, nskip);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace etp

@@ -51,8 +51,9 @@ def records_from_bytes(buf: np.ndarray, n: int):
     return [_abi.Best.from_buffer_copy(raw[i * size:(i + 1) * size]) for i in range(n)]
 
 
-def key_hi_from(level: int, cost: float) -> int:
-    """Host twin of the device key: (4 - level rank) << 60 | monotone(cost) >> 4 (smaller wins)."""
+def key_from(level: int, cost: float, index: int):
+    """Host twin of the device key (etp_device.cuh: make_key_hi / make_key_lo): (key_hi, key_lo) orders like
+    (highest level first, cost, index) with the full 64-bit image of the cost; smaller wins."""
     import struct
 
     rank = 4 if level == 10 else level
@@ -61,7 +62,11 @@ def key_hi_from(level: int, cost: float) -> int:
     else:
         b = struct.unpack("<Q", struct.pack("<d", float(cost)))[0]
         mono = (~b & ((1 << 64) - 1)) if (b >> 63) else (b | (1 << 63))
-    return ((4 - rank) << 60) | (mono >> 4)
+    return ((4 - rank) << 61) | (mono >> 3), ((mono & 7) << 61) | int(index)
+
+
+def key_hi_from(level: int, cost: float) -> int:
+    return key_from(level, cost, 0)[0]
 
 
 def gather_best_records(local: "np.ndarray", dist, group=None, device=None):

@@ -89,9 +89,7 @@ def score_trajectories(trajs, predictions, obstacle_types, vehicle_params, param
     # (triangles, check): boundary test on the device.  A shared default context does not keep a boundary between calls;
     # a context the caller owns keeps what the caller set.
     if road_boundary is not None or (getattr(ctx, "_boundary_key", None) is not None and any(ctx is c for c in _CTX.values())):
-        bkey = None if road_boundary is None else (id(road_boundary[0]), len(road_boundary[0]), road_boundary[1])
-        if getattr(ctx, "_boundary_key", None) != bkey:
-            ctx.set_road_boundary(*(road_boundary if road_boundary is not None else (None,)))
+        ctx.ensure_road_boundary(road_boundary)
     f, n = trajectory_fields(trajs)
     Cn, Tm, O = len(trajs), f.shape[1], ctx.O
     bufs = ctx.allocate_outputs(Cn, Tm, O)

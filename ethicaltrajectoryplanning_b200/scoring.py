@@ -322,7 +322,23 @@ class ScoringContext:
         tri = np.zeros((0, 3, 2)) if triangles is None else np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 3, 2)
         b.n_triangles, b.triangles, b.check = len(tri), _dptr(tri), _abi.COLLISION_CODES[check]
         self._check(self.lib.etp_set_road_boundary(self.h, C.byref(b)))
-        self._boundary_key = None if triangles is None else (id(triangles), len(tri), check)
+        # what is resident: the caller's object (kept alive, so its identity cannot be recycled) and its content
+        self._boundary_key = None if triangles is None else (triangles, tri.tobytes(), check)
+
+    def ensure_road_boundary(self, rb):
+        """``rb`` = (triangles, check) or None: upload unless exactly this boundary is resident (same object and same
+        bytes, or equal bytes of another object)."""
+        cur = getattr(self, "_boundary_key", None)
+        if rb is None:
+            if cur is not None:
+                self.set_road_boundary(None)
+            return
+        tri, check = rb
+        if cur is not None and cur[2] == check:
+            raw = np.ascontiguousarray(tri, dtype=np.float64).tobytes()
+            if raw == cur[1]:
+                return
+        self.set_road_boundary(tri, check)
 
     def set_predictions(self, predictions, obstacle_types=None, masses=None, protections=None):
         o = _abi.Obstacles()
@@ -419,9 +435,13 @@ class ScoringContext:
         """set_params unless the same parameter objects with the same content are already on the device."""
         # identity of the objects plus their scalar content (dict order is stable): cheap enough for every cycle of a
         # closed loop, and an in-place edit of a weight or a mode still triggers the upload
-        pkey = (id(params), id(vehicle), mode, tuple(params["weights"].values()),
+        lr = params["harm"]["log_reg"]
+        pkey = (mode, tuple(params["weights"].values()),
                 tuple(tuple(v) if isinstance(v, (list, tuple, set)) else v for v in params["modes"].values()
-                      if not isinstance(v, dict)))
+                      if not isinstance(v, dict)),
+                tuple(tuple(t.values()) for t in lr.values()), tuple(params["harm"]["pedestrian"].values()),
+                (vehicle.l, vehicle.w, vehicle.l_r, vehicle.m, vehicle.steering.max, vehicle.lateral_a_max,
+                 vehicle.longitudinal.v_max, vehicle.longitudinal.a_max))
         if getattr(self, "_params_key", None) != pkey:
             self.set_params(params, vehicle, mode)
             self._params_key = pkey
@@ -430,17 +450,22 @@ class ScoringContext:
         """params + spline + predictions of a PlanningStep.  Parameters and spline are uploaded again only when they
         changed (same objects, same content fingerprint); predictions change every step and always are."""
         self.ensure_params(step.params, step.vehicle, step.mode)
-        csp = CubicSpline2D.from_foreign(step.csp)
-        skey = (id(step.csp), len(csp.s), float(csp.s[-1]), float(np.asarray(csp.coef_x)[0][0]), float(np.asarray(csp.coef_y)[-1][1]))
-        if getattr(self, "_spline_key", None) != skey:
+        # the resident spline is recognised by the caller's object (kept alive here, so its identity cannot be recycled by
+        # another spline) plus a content fingerprint that catches in-place edits
+        cur = getattr(self, "_spline_key", None)
+        if cur is None or cur[0] is not step.csp or cur[1] != self._spline_print(step.csp):
+            csp = CubicSpline2D.from_foreign(step.csp)
             self.set_spline(csp)
-            self._spline_key = skey
+            self._spline_key = (step.csp, self._spline_print(step.csp))
         if not getattr(step, "predictions_resident", False):
             self.set_predictions(step.predictions, step.obstacle_types)
-        rb = getattr(step, "road_boundary", None)  # (triangles, check) or None
-        bkey = None if rb is None else (id(rb[0]), len(rb[0]), rb[1])
-        if getattr(self, "_boundary_key", None) != bkey:
-            self.set_road_boundary(*(rb if rb is not None else (None,)))
+        self.ensure_road_boundary(getattr(step, "road_boundary", None))  # (triangles, check) or None
+
+    @staticmethod
+    def _spline_print(csp):
+        c = CubicSpline2D.from_foreign(csp)
+        cx, cy = np.asarray(c.coef_x), np.asarray(c.coef_y)
+        return (len(c.s), float(c.s[0]), float(c.s[-1]), float(cx[0][0]), float(cx[-1][3]), float(cy[0][1]), float(cy[-1][1]))
 
     # -- one planning step --------------------------------------------------------------------
     def make_step_struct(self, step, c_begin=None, c_end=None, shard_index=0, shard_count=1):
@@ -550,10 +575,19 @@ class ScoringContext:
         self._check(self.lib.etp_get_timing(self.h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
 
+    def stage_timing(self):
+        """(profile stage, fused scoring kernel, selection) milliseconds of the last step, from CUDA events."""
+        v = (C.c_float * 3)()
+        self._check(self.lib.etp_get_stage_timing(self.h, v, 3))
+        return float(v[0]), float(v[1]), float(v[2])
+
     def debug_counters(self):
-        v = (C.c_uint64 * 1)()
-        self._check(self.lib.etp_debug_counters(self.h, v, 1))
-        return {"fp64_fallback_evals": int(v[0])}
+        v = (C.c_uint64 * 4)()
+        self._check(self.lib.etp_debug_counters(self.h, v, 4))
+        import struct
+
+        return {"fp64_fallback_evals": int(v[0]), "rescored": int(v[1]), "bound_violations": int(v[2]),
+                "worst_error_over_bound": struct.unpack("<f", struct.pack("<I", int(v[3]) & 0xffffffff))[0]}
 
     def best_device_tensor(self):
         """uint8 view (torch) of the device-resident etp_best record, for collectives."""

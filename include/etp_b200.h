@@ -261,8 +261,8 @@ typedef struct {
 /* Selected candidate: sort by (highest non-empty level, cost, generation order)
  * (frenet_functions.py:562-570, frenet_planner.py:457,555-558). */
 typedef struct {
-    uint64_t key_hi;     /* (4 - level rank) << 60 | monotone(cost) >> 4 : smaller is better */
-    uint64_t key_lo;     /* dense candidate index */
+    uint64_t key_hi;     /* (4 - level rank) << 61 | m >> 3, m = order-preserving 64-bit image of the cost: smaller is better */
+    uint64_t key_lo;     /* (m & 7) << 61 | dense candidate index: (key_hi, key_lo) orders like (level, cost, index) exactly */
     double cost;
     int32_t index;       /* dense index, -1 if no candidate */
     int32_t level;
@@ -397,8 +397,13 @@ int etp_best_device_ptr(etp_ctx* ctx, void** ptr);
  * etp_get_timing synchronises on the recorded events and returns milliseconds of the last step. */
 int etp_enable_timing(etp_ctx* ctx, int enable);
 int etp_get_timing(etp_ctx* ctx, float* profile_ms, float* score_ms);
+/* the same per stage: ms[0] profile stage, ms[1] fused scoring kernel, ms[2] selection (arg-min and the fp64 re-decisions) */
+int etp_get_stage_timing(etp_ctx* ctx, float* ms, int n);
 
-/* Diagnostics: out[0] = fp32-path evaluations that needed the fp64 fallback (|rho| > 0.55) since load. */
+/* Diagnostics: out[0] = fp32-path evaluations that needed the fp64 fallback (|rho| > 0.55) since load;
+ * since the context was created: out[1] = candidates the selection re-scored in fp64 (near-ties of the arg-min, max-risk /
+ * maximin-gate decisions too close to call in fp32), out[2] = how many of them differed from their fp32 cost by more than the
+ * bound the fp32 pass had claimed (must stay 0), out[3] = largest such error / bound seen (float bits). */
 int etp_debug_counters(etp_ctx* ctx, uint64_t* out, int n);
 
 /* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks).

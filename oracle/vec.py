@@ -311,6 +311,8 @@ def score_dense(step, profiles=None):
         cst[9] = np.power(d_ddd, 2).sum(axis=1) / T
         cst[10] = np.sqrt(np.diff(x, axis=1) ** 2 + np.diff(y, axis=1) ** 2).sum(axis=1)
         cst[11] = step.cost_factor
+        if getattr(step, "cost_factor_list", None) is not None:  # per-candidate get_cost_factor results (etp_step.cost_factor_list)
+            cst[11] = np.asarray(step.cost_factor_list, dtype=np.float64)[p * nd + idx]
         if getattr(step, "goal", None) is not None:  # oracle/goal.py (calc_trajectory_cost.py:349-415, 438-519)
             cst[11], cst[6] = _goal.factor_and_velocity_cost(step.goal, x, y, v, yaw, t, step.dt)
         risk_only = (level < 10) & bool(modes["multiple_cost_functions"])

@@ -181,8 +181,8 @@ def test_check_validity_and_calc_trajectory_costs(name):
         if ref["has_cost"][li]:
             cost, cd = calc_trajectory_costs(trajs[li], None, _problem(step), _ego(step), list_level, scenario, step.params,
                                              1, step.dt, step.predictions, None, step.vehicle, mode=step.mode)
-            assert _close(cost, ref["cost"][li], rtol=1e-3, atol=1e-6)
-            assert _close(cd["total_cost"], ref["cost"][li], rtol=1e-3, atol=1e-6)
+            assert _close(cost, ref["cost"][li], rtol=1e-4, atol=1e-9)
+            assert _close(cd["total_cost"], ref["cost"][li], rtol=1e-4, atol=1e-9)
 
 
 def test_frenet_planner_step_and_log_line(tmp_path):

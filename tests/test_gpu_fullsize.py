@@ -36,12 +36,13 @@ def test_cfg3_argmin_equals_lexicographic_argmin_of_the_materialised_tensors(cfg
     rank = torch.where(level == _abi.LEVEL_SKIPPED, torch.full_like(level, -1), rank)
     top = int(rank.max())
     cand = torch.nonzero(rank == top).flatten()
-    # the kernel keys on the fp64 cost; the fp32 tensor may merge near-ties: the winner must be among the fp32 minima
+    # the selection is re-decided in fp64 among the near-ties (etp_select.cu): the winner's materialised cost is the
+    # smallest of its level up to the fp32 rounding of the stored tensor
     cmin = float(total[cand].min())
     winners = cand[total[cand] <= cmin * (1 + 1e-6) + 1e-9]
     assert res.best["index"] in set(winners.tolist())
     assert res.best["level"] == (10 if top == 4 else top)
-    assert abs(res.best["cost"] - cmin) <= 1e-5 * abs(cmin) + 1e-6
+    assert abs(res.best["cost"] - cmin) <= 1e-6 * abs(cmin) + 1e-9
     assert res.best["n_scored"] == int((level != _abi.LEVEL_SKIPPED).sum())
 
 
@@ -103,7 +104,7 @@ def test_cfg3_sample_of_profiles_against_the_vectorised_oracle(cfg3):
     red = res.red[:, :, sel].cpu().numpy().transpose(0, 2, 1).astype(np.float64)
     assert np.all(np.abs(red - ref["red"]) <= 1e-4 * np.abs(ref["red"]) + 1e-9)
     cost = res.cost[:, sel].cpu().numpy().astype(np.float64)
-    assert np.all(np.abs(cost - ref["cost"]) <= 1e-3 * np.abs(ref["cost"]) + 1e-6)
+    assert np.all(np.abs(cost - ref["cost"]) <= 1e-4 * np.abs(ref["cost"]) + 1e-9)
     traj = res.traj[:, :, sel].cpu().numpy().transpose(0, 2, 1).astype(np.float64)
     err = np.abs(traj - ref["traj"]) / np.maximum(np.abs(ref["traj"]), 1e-3)
     assert err.max() <= 2e-5

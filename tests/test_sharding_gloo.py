@@ -31,7 +31,7 @@ def test_key_orders_by_level_then_cost_then_index():
 
 def _rec(index, level, cost, n_scored, list_index):
     b = _abi.Best()
-    b.key_hi, b.key_lo = D.key_hi_from(level, cost), max(index, 0)
+    b.key_hi, b.key_lo = D.key_from(level, cost, max(index, 0))
     b.cost, b.index, b.level, b.n_scored, b.list_index = cost, index, level, n_scored, list_index
     if index < 0:
         b.key_hi = b.key_lo = (1 << 64) - 1

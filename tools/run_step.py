@@ -47,7 +47,7 @@ def main():
     ctx.enable_timing(True)
     for i in range(args.steps):
         ctx.launch(s, bufs)
-        print("step", i, "profile_ms %.4f score_ms %.4f" % ctx.timing(), ctx.best())
+        print("step", i, "profile_ms %.4f score_ms %.4f select_ms %.4f" % ctx.stage_timing(), ctx.best())
     if bufs is not None:
         print("nonzero prob fraction", float((bufs["prob"] != 0).float().mean()))
         print("level histogram", torch.bincount(bufs["level"].to(torch.int64), minlength=11)[[0, 1, 2, 3, 10]].tolist())
