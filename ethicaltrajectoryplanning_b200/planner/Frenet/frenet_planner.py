@@ -19,6 +19,7 @@ import numpy as np
 from ... import dropin
 from ...configs import load_harm_parameter_json, load_risk_json, load_weight_json
 from ...synthetic import PlanningStep, assign_responsibility_by_action_space, planner_v_list
+from ..utils.timers import ExecTimer, device_stages
 from .utils.frenet_functions import calc_frenet_trajectories, sort_frenet_trajectories
 from .utils.logging import ColumnarLogging, FrenetLogging
 from .utils.validity_checks import VALIDITY_LEVELS  # noqa: F401
@@ -44,7 +45,8 @@ class FrenetPlanner:
         if reference_spline is None:
             raise ValueError("reference_spline (the CubicSpline2D of planning.py:375-377) must be given")
         self.scenario, self.planning_problem, self.ego_id = scenario, planning_problem, ego_id
-        self.exec_timer = exec_timer
+        # frenet_planner.py:94-97: a disabled timer stands in when none is given
+        self.exec_timer = ExecTimer(timing_enabled=False) if exec_timer is None else exec_timer
         self.frenet_parameters = dict(DEFAULT_FRENET_PARAMETERS if frenet_parameters is None else frenet_parameters)
         self.p = vehicle_params
         self.params_harm = load_harm_parameter_json()
@@ -118,6 +120,7 @@ class FrenetPlanner:
                                         dropin.obstacle_type_names(self.scenario, {oid: None}, self.obstacle_types)[oid])
                 shapes[oid], ori0[oid], vel0[oid], types[oid] = st
             self._resident_types = types
+            self._resident_static = (shapes, ori0, vel0)  # what the enrichment on the device was given (tests replay it on the host)
             self.ctx.ensure_params(self.params_dict, self.p, self.mode)
             self.ctx.set_raw_predictions(predictions, shapes, ori0, vel0, types, self.scenario.dt,
                                          np.asarray(self.ego_state.position), self.ego_state.orientation)
@@ -130,7 +133,14 @@ class FrenetPlanner:
                                                      predictions)
 
     def _step_planner(self):
-        """Frenet Planner step function (frenet_planner.py:265-576)."""
+        """Frenet Planner step function (frenet_planner.py:265-576); timer labels as at :270-561."""
+        self.exec_timer.start_timer("simulation/total")
+        try:
+            self._step_planner_timed()
+        finally:
+            self.exec_timer.stop_timer("simulation/total")
+
+    def _step_planner_timed(self):
         fpar = self.frenet_parameters
         # find position along the reference spline (s, s_d, s_dd, d, d_d, d_dd)  (:293-299)
         c_s = self.trajectory["s_loc_m"][1]
@@ -142,25 +152,31 @@ class FrenetPlanner:
         d_list, t_list = fpar["d_list"], fpar["t_list"]
         if fpar.get("v_list_generation_mode", "linspace") != "linspace":
             raise NotImplementedError("only the linspace v-list mode is part of the scored path (SURVEY.md 8a row a2)")
-        v_list = planner_v_list(c_s_d, t_list, self.p, fpar["n_v_samples"], self.v_goal_min, self.v_goal_max)  # :301-319
-        predictions = self._predictions(t_list)
+        with self.exec_timer.time_with_cm("simulation/get v list"):
+            v_list = planner_v_list(c_s_d, t_list, self.p, fpar["n_v_samples"], self.v_goal_min, self.v_goal_max)  # :301-319
+        with self.exec_timer.time_with_cm("simulation/prediction"):
+            predictions = self._predictions(t_list)
 
         if not self.materialize:
             return self._step_fused(c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd, d_list, t_list, v_list, predictions)
 
-        ft_list = calc_frenet_trajectories(c_s=c_s, c_s_d=c_s_d, c_s_dd=c_s_dd, c_d=c_d, c_d_d=c_d_d, c_d_dd=c_d_dd,
-                                           d_list=d_list, t_list=t_list, v_list=v_list, dt=fpar["dt"],
-                                           csp=self.reference_spline, v_thr=fpar["v_thr"], exec_timer=self.exec_timer)
-        ft_list_valid, ft_list_invalid, validity_dict = sort_frenet_trajectories(
-            ego_state=self.ego_state, fp_list=ft_list, global_path=self.global_path, predictions=predictions,
-            mode=self.mode, params=self.params_dict, planning_problem=self.planning_problem, scenario=self.scenario,
-            vehicle_params=self.p, ego_id=self.ego_id, dt=fpar["dt"], sensor_radius=self.sensor_radius,
-            road_boundary=self.road_boundary, collision_checker=self.collision_checker, goal_area=self.goal_area,
-            exec_timer=self.exec_timer, reach_set=None, obstacle_types=self.obstacle_types)
-        ft_list_valid.sort(key=lambda fp: fp.cost, reverse=False)  # :457 (stable: ties keep generation order)
-        if self.logger is not None:  # :469-477
-            self.logger.log_data(self.time_step, self.time_step * fpar["dt"], [d.__dict__ for d in ft_list_valid],
-                                 [d.__dict__ for d in ft_list_invalid], predictions, 0, None)
+        with self.exec_timer.time_with_cm("simulation/calculate trajectories/total"):  # :321
+            ft_list = calc_frenet_trajectories(c_s=c_s, c_s_d=c_s_d, c_s_dd=c_s_dd, c_d=c_d, c_d_d=c_d_d, c_d_dd=c_d_dd,
+                                               d_list=d_list, t_list=t_list, v_list=v_list, dt=fpar["dt"],
+                                               csp=self.reference_spline, v_thr=fpar["v_thr"], exec_timer=self.exec_timer)
+        with self.exec_timer.time_with_cm("simulation/sort trajectories/total"):  # :430
+            ft_list_valid, ft_list_invalid, validity_dict = sort_frenet_trajectories(
+                ego_state=self.ego_state, fp_list=ft_list, global_path=self.global_path, predictions=predictions,
+                mode=self.mode, params=self.params_dict, planning_problem=self.planning_problem, scenario=self.scenario,
+                vehicle_params=self.p, ego_id=self.ego_id, dt=fpar["dt"], sensor_radius=self.sensor_radius,
+                road_boundary=self.road_boundary, collision_checker=self.collision_checker, goal_area=self.goal_area,
+                exec_timer=self.exec_timer, reach_set=None, obstacle_types=self.obstacle_types)
+            with self.exec_timer.time_with_cm("simulation/sort trajectories/sort list by costs"):  # :453-457
+                ft_list_valid.sort(key=lambda fp: fp.cost, reverse=False)  # stable: ties keep generation order
+        if self.logger is not None:  # :468-477
+            with self.exec_timer.time_with_cm("log trajectories"):
+                self.logger.log_data(self.time_step, self.time_step * fpar["dt"], [d.__dict__ for d in ft_list_valid],
+                                     [d.__dict__ for d in ft_list_invalid], predictions, 0, None)
         best = ft_list_valid[0] if len(ft_list_valid) > 0 else ft_list_invalid[0]  # :555-558
         self.validity_dict = validity_dict
         self.last_best = best
@@ -194,13 +210,20 @@ class FrenetPlanner:
             predictions_resident=getattr(self, "_resident", False),
             goal=goal_context(self.ego_state, self.planning_problem, self.scenario, self.goal_area),
             road_boundary=device_road_boundary(self.road_boundary))
-        if self.columnar_logger is not None:
-            # logging needs every candidate: materialised step, tensors appended as they come off the device
-            res = self.ctx.plan(step)
-            self.columnar_logger.log_step(self.time_step, self.time_step * fpar["dt"], res, step, predictions, 0, None)
-            self.last_best, self._trajectory = res.best, res.best_trajectory()
-            return
-        self.last_best, self._trajectory = self.ctx.plan_winner(step)
+        self.last_step = step
+        # the fused step IS "calculate trajectories" + "sort trajectories": both labels of the reference are kept, the
+        # kernels' own times go under "simulation/sort trajectories/device/..."
+        getattr(self.exec_timer, "record", lambda *a: None)("simulation/calculate trajectories/total", 0.0)
+        with self.exec_timer.time_with_cm("simulation/sort trajectories/total"), \
+                device_stages(self.ctx, self.exec_timer, "simulation/sort trajectories/"):
+            if self.columnar_logger is not None:
+                # logging needs every candidate: materialised step, tensors appended as they come off the device
+                res = self.ctx.plan(step)
+                with self.exec_timer.time_with_cm("log trajectories"):
+                    self.columnar_logger.log_step(self.time_step, self.time_step * fpar["dt"], res, step, predictions, 0, None)
+                self.last_best, self._trajectory = res.best, res.best_trajectory()
+                return
+            self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------
     def ideal_tracking_state(self):

@@ -10,6 +10,7 @@ import numpy as np
 
 from .... import _abi, dropin
 from ....synthetic import PlanningStep, get_v_list  # noqa: F401  (get_v_list re-exported like the reference)
+from ...utils.timers import device_stages, timer_or_noop
 from .calc_trajectory_cost import build_cost_dict, cost_context, goal_context
 from .validity_checks import VALIDITY_LEVELS, device_road_boundary, host_validity_inputs
 
@@ -67,8 +68,11 @@ def calc_frenet_trajectories(c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd, d_list, t_l
     s, keep, n = ctx.make_step_struct(step)
     Tmax, Cs = int(n.max()), ctx.local_candidates(s)
     bufs = ctx.allocate_outputs(Cs, Tmax, 0, prob=False, red=False, cost=False)
-    ctx.launch(s, bufs)
-    ctx.stream.synchronize()
+    # the reference times the sub-steps of its triple loop under "simulation/calculate trajectories/..." (frenet_functions.py:
+    # 255-452); here they are one launch, timed on the device
+    with device_stages(ctx, timer_or_noop(exec_timer), "simulation/calculate trajectories/"):
+        ctx.launch(s, bufs)
+        ctx.stream.synchronize()
     traj = bufs["traj"].detach().cpu().numpy().astype(np.float64)  # [13][Tmax][C]
     level = bufs["level"].detach().cpu().numpy()
     out = FrenetTrajectoryList()
@@ -139,7 +143,10 @@ def sort_frenet_trajectories(ego_state, fp_list, global_path, predictions, mode,
         step.cost_factor_list = fl
         step.goal = goal
         step.road_boundary = device_road_boundary(road_boundary)
-        res = ctx.plan(step)
+        # "simulation/sort trajectories/check validity/total" and ".../calculate costs/total" (frenet_functions.py:545,
+        # calc_trajectory_cost.py:79-344) are one fused launch here
+        with device_stages(ctx, timer_or_noop(exec_timer), "simulation/sort trajectories/"):
+            res = ctx.plan(step)
         out = res.numpy()
         red = out["red"][:, dense].astype(np.float64)
         cost = out["cost"][:, dense].astype(np.float64)

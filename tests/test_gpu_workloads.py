@@ -56,3 +56,54 @@ def test_closed_loop_with_every_check_on_the_device():
     d = np.array([st[1] for st in states])
     assert np.all(np.diff(s) >= 0) and s[-1] > s[0] + 5.0
     assert np.all(np.abs(d) < 3.6)
+
+
+@pytest.mark.parametrize("weights", ["weights_ethical.json", "weights_ego.json", "weights_standard.json"])
+def test_closed_loop_200_cycles_follow_the_oracle(weights):
+    """cfg5: 200 replanning cycles with ideal tracking (planning.py:117-131, frenet_planner.py:293-319).  Every cycle the
+    planning step the planner built is replayed through the vectorised fp64 oracle (raw predictions enriched by the host
+    twins of prediction_helpers.py:75-135 / responsibility.py:57-89): same selected candidate, same trajectory."""
+    import copy
+    from types import SimpleNamespace
+
+    from ethicaltrajectoryplanning_b200.configs import default_params
+    from ethicaltrajectoryplanning_b200.planner.Frenet.frenet_planner import FrenetPlanner
+    from ethicaltrajectoryplanning_b200.synthetic import (GRIDS, assign_responsibility_by_action_space, enrich_predictions,
+                                                         synthetic_path)
+    from ethicaltrajectoryplanning_b200.vehicleparams import VehicleParameters
+    from ethicaltrajectoryplanning_b200.workloads import MovingObstacles
+    from oracle import vec
+
+    n_steps, v0 = 200, 12.0
+    nv, nd, dmax, t_list, _ = GRIDS["cfg1"]
+    veh, csp = VehicleParameters("bmw_320i"), synthetic_path()
+    T = len(np.arange(0.0, max(t_list), 0.1))
+    pred = MovingObstacles(csp, 5, T, n_steps, v0=v0, seed=4321)
+    params = default_params(weights)
+    fpar = {"t_list": list(t_list), "v_list_generation_mode": "linspace", "n_v_samples": nv,
+            "d_list": np.linspace(-dmax, dmax, nd), "dt": 0.1, "v_thr": 3.0}
+    scenario = SimpleNamespace(dt=0.1, obstacle_by_id=pred.obstacle_by_id)
+    problem = SimpleNamespace(velocity_cost_mode=0, velocity_target=v0, cost_factor=1.0)
+    x0, y0 = csp.calc_position(0.0)
+    ego = SimpleNamespace(position=np.array([x0, y0]), orientation=float(csp.calc_yaw(0.0)), velocity=v0, acceleration=0.0, time_step=0)
+    pl = FrenetPlanner(scenario, problem, 1, veh, "risk", frenet_parameters=fpar, weights=params["weights"],
+                       settings={"risk_dict": params["modes"]}, reference_spline=csp, predictor=pred, ego_state=ego, materialize=False)
+    names = {"s_loc_m": 4, "d_loc_m": 0, "x_m": 8, "y_m": 9, "psi_rad": 10, "kappa_radpm": 12, "v_mps": 5, "ax_mps2": 6}
+    for k in range(n_steps):
+        pl.step(scenario, None, k, ego)
+        step = copy.copy(pl.last_step)
+        shapes, ori0, vel0 = pl._resident_static
+        raw = {oid: {"pos_list": np.array(p["pos_list"]), "cov_list": np.array(p["cov_list"])} for oid, p in step.predictions.items()}
+        step.predictions = assign_responsibility_by_action_space(
+            step.ego_position, step.ego_orientation, enrich_predictions(raw, shapes, ori0, vel0, 0.1))
+        step.predictions_resident = False
+        ref = vec.score_dense(step)
+        assert pl.last_best["index"] == ref["best"]["index"], (k, pl.last_best, ref["best"])
+        assert pl.last_best["level"] == ref["best"]["level"]
+        assert abs(pl.last_best["cost"] - ref["best"]["cost"]) <= 1e-4 * abs(ref["best"]["cost"]) + 1e-9
+        row = int(np.flatnonzero(ref["dense_index"] == ref["best"]["index"])[0])
+        Tn = int(ref["T"][row])
+        for name, f in names.items():
+            np.testing.assert_allclose(pl.trajectory[name], ref["traj"][f, row, :Tn], rtol=1e-6, atol=1e-9, err_msg=f"cycle {k} {name}")
+        ego = pl.ideal_tracking_state()
+    assert pl.trajectory["s_loc_m"][1] > 100.0  # 20 s at about 12 m/s
