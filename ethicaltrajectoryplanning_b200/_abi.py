@@ -19,7 +19,7 @@ HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cu
 NUM_WEIGHTS = 14
 NUM_FIELDS = 13
 NUM_RED = 4
-NUM_COST = 13
+NUM_COST = 14
 MAX_ANGLE_BINS = 8
 LEVEL_SKIPPED = 255
 PRECISION_FP32, PRECISION_FP64 = 0, 1
@@ -28,7 +28,7 @@ OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NO_CANDIDATE, ERR_STATE = 0, -1,
 FIELD_NAMES = ("d", "d_d", "d_dd", "d_ddd", "s", "s_d", "s_dd", "s_ddd", "x", "y", "yaw", "v", "curv")
 RED_NAMES = ("ego_risk", "obst_risk", "ego_harm", "obst_harm")
 COST_NAMES = ("bayes", "equality", "maximin", "responsibility", "ego", "risk_cost", "velocity",
-              "dist_to_global_path", "lon_jerk", "lat_jerk", "travelled_dist", "factor", "total")
+              "dist_to_global_path", "lon_jerk", "lat_jerk", "travelled_dist", "factor", "total", "dist_to_goal_pos")
 REASON_NAMES = ("", "velocity", "acceleration", "curvature (lvc)", "curvature (hvc)", "collision",
                 "boundaries", "max_risk")
 
@@ -99,6 +99,8 @@ class Goal(C.Structure):
         ("time_start", C.c_int32), ("time_end", C.c_int32), ("ego_time_step", C.c_int32),
         ("ego_x", C.c_double), ("ego_y", C.c_double),
         ("has_centers", C.c_int32), ("avg_goal_distance", C.c_double),
+        ("n_goal_lines", C.c_int32), ("goal_line_start", _ip), ("goal_line_vertices", _dp),
+        ("n_goal_points", C.c_int32), ("goal_points", _dp),
     ]
 
 

@@ -293,9 +293,8 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
     if (!c || !p) return ETP_ERR_INVALID;
     if (p->weights[ETP_W_RESPONSIBILITY] > 0.0)
         ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "weights['responsibility'] > 0 needs reachable sets (planner/utils/reachable_set.py): out of scope");
-    if (p->weights[ETP_W_VISIBLE_AREA] > 0.0 || p->weights[ETP_W_DIST_TO_GOAL_POS] > 0.0 ||
-        p->weights[ETP_W_DIST_TO_LANE_CENTER] > 0.0)
-        ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "visible_area / dist_to_goal_pos / dist_to_lane_center are host-side cost terms");
+    if (p->weights[ETP_W_VISIBLE_AREA] > 0.0 || p->weights[ETP_W_DIST_TO_LANE_CENTER] > 0.0)
+        ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "visible_area / dist_to_lane_center are host-side cost terms (sensor model, lanelet network)");
     if (p->n_angle_thresholds < 0 || p->n_angle_thresholds > ETP_MAX_ANGLE_BINS)
         ETP_FAIL(c, ETP_ERR_INVALID, "n_angle_thresholds out of range");
     if (p->planner_mode < ETP_MODE_RISK || p->planner_mode > ETP_MODE_GROUND_TRUTH) ETP_FAIL(c, ETP_ERR_INVALID, "planner_mode");
@@ -628,9 +627,31 @@ static int stage_goal(etp_ctx* c, const etp_goal* g, double dt, int Tmax, DevGoa
         if (g->poly_start[p + 1] - g->poly_start[p] < 3) ETP_FAIL(c, ETP_ERR_INVALID, "goal polygon %d has fewer than 3 vertices", p);
     const size_t b_start = sizeof(int) * (size_t)(d.n_poly + 1), b_start_pad = (b_start + 7) / 8 * 8;
     const size_t b_vert = sizeof(double) * 2 * (size_t)n_vert, b_circ = sizeof(double) * 3 * (size_t)d.n_circ;
-    ETP_CUDA(c, c->goal_geom.reserve(b_start_pad + b_vert + b_circ + 8));
+    // goal positions of calc_dist_to_goal_pos: centre lines, or shape centres
+    if (g->n_goal_lines < 0 || g->n_goal_points < 0 || (g->n_goal_lines > 0 && (!g->goal_line_start || !g->goal_line_vertices)) ||
+        (g->n_goal_points > 0 && !g->goal_points))
+        ETP_FAIL(c, ETP_ERR_INVALID, "goal position arrays missing");
+    d.n_lines = g->n_goal_lines;
+    d.n_pts = g->n_goal_points;
+    const int n_lv = d.n_lines > 0 ? g->goal_line_start[d.n_lines] : 0;
+    for (int l = 0; l < d.n_lines; ++l)
+        if (g->goal_line_start[l + 1] - g->goal_line_start[l] < 1) ETP_FAIL(c, ETP_ERR_INVALID, "goal centre line %d is empty", l);
+    const size_t b_ls = (sizeof(int) * (size_t)(d.n_lines + 1) + 7) / 8 * 8, b_lv = sizeof(double) * 2 * (size_t)n_lv,
+                 b_pt = sizeof(double) * 2 * (size_t)d.n_pts;
+    ETP_CUDA(c, c->goal_geom.reserve(b_start_pad + b_vert + b_circ + b_ls + b_lv + b_pt + 8));
     unsigned char* base = c->goal_geom.as<unsigned char>();
     int r;
+    {
+        unsigned char* q = base + b_start_pad + b_vert + b_circ;
+        if (d.n_lines > 0) {
+            if ((r = stage_to_device(c, q, g->goal_line_start, sizeof(int) * (size_t)(d.n_lines + 1)))) return r;
+            if ((r = stage_to_device(c, q + b_ls, g->goal_line_vertices, b_lv))) return r;
+        }
+        if (d.n_pts > 0 && (r = stage_to_device(c, q + b_ls + b_lv, g->goal_points, b_pt))) return r;
+        d.line_start = reinterpret_cast<const int*>(q);
+        d.line_verts = reinterpret_cast<const double*>(q + b_ls);
+        d.pts = reinterpret_cast<const double*>(q + b_ls + b_lv);
+    }
     if (d.n_poly > 0) {
         if ((r = stage_to_device(c, base, g->poly_start, b_start))) return r;
         if ((r = stage_to_device(c, base + b_start_pad, g->vertices, b_vert))) return r;
@@ -750,6 +771,8 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
         if ((r = stage_to_device(c, c->factor_list.p, s->cost_factor_list, sizeof(double) * (size_t)dense))) return r;
         st.factor_list = c->factor_list.as<double>();
     }
+    if (c->pr.w[ETP_W_DIST_TO_GOAL_POS] > 0.0 && !s->goal)
+        ETP_FAIL(c, ETP_ERR_INVALID, "weights['dist_to_goal_pos'] > 0 needs the goal positions of the step (etp_step.goal)");
     if ((r = stage_goal(c, s->goal, s->dt, Tmax, &st.goal))) return r;
     if ((r = end_staging(c))) return r;
 
@@ -865,6 +888,8 @@ int etp_score_trajectories(etp_ctx* c, const etp_trajectories* g, const etp_out*
         if ((r = stage_to_device(c, c->factor_list.p, g->cost_factor_list, sizeof(double) * n))) return r;
         st.factor_list = c->factor_list.as<double>();
     }
+    if (c->pr.w[ETP_W_DIST_TO_GOAL_POS] > 0.0 && !g->goal)
+        ETP_FAIL(c, ETP_ERR_INVALID, "weights['dist_to_goal_pos'] > 0 needs the goal positions (etp_trajectories.goal)");
     if ((r = stage_goal(c, g->goal, g->dt, g->t_max, &st.goal))) return r;
     if ((r = end_staging(c))) return r;
     st.given = c->given.as<double>(); st.given_T = c->given_T.as<int>(); st.given_stride = g->n_traj;

@@ -92,7 +92,48 @@ struct DevGoal {
     int ego_in_goal;         // reached_target_position(ego_state.position)
     int vel_kind;            // outside the goal at sample 0: 0 |vel_out - mean v|, 1 30 - mean v, 3 zero
     double vel_out;          // avg_dist / remaining_time
+    // calc_dist_to_goal_pos (calc_trajectory_cost.py:760-803): centre lines of the goal lanelets or centres of the goal shapes
+    int n_lines, n_pts;
+    const int* line_start;   // [n_lines + 1]
+    const double* line_verts;
+    const double* pts;       // [n_pts][2]
 };
+
+// distance of (x, y) to the closest goal position: closest point of the goal lanelets' centre lines
+// (dist_to_nearest_point, calc_trajectory_cost.py:835-853: shapely's project + interpolate, i.e. the nearest point of the
+// polyline), else the closest goal-shape centre, else 0 (survival scenario)
+__device__ inline double dist_to_goal_pos(const DevGoal& g, double x, double y) {
+    double best = INFINITY;
+    if (g.n_lines > 0) {
+        for (int l = 0; l < g.n_lines; ++l) {
+            const int a = g.line_start[l], b = g.line_start[l + 1];
+            double dl = INFINITY;
+            if (b - a == 1) {
+                const double dx = x - g.line_verts[2 * a], dy = y - g.line_verts[2 * a + 1];
+                dl = sqrt(dx * dx + dy * dy);
+            }
+            for (int i = a; i + 1 < b; ++i) {
+                const double x0 = g.line_verts[2 * i], y0 = g.line_verts[2 * i + 1];
+                const double ex = g.line_verts[2 * i + 2] - x0, ey = g.line_verts[2 * i + 3] - y0;
+                const double l2 = ex * ex + ey * ey;
+                double u = l2 > 0.0 ? ((x - x0) * ex + (y - y0) * ey) / l2 : 0.0;
+                u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+                const double dx = x - (x0 + u * ex), dy = y - (y0 + u * ey);
+                dl = fmin(dl, sqrt(dx * dx + dy * dy));
+            }
+            best = fmin(best, dl);
+        }
+        return best;
+    }
+    if (g.n_pts > 0) {
+        for (int k = 0; k < g.n_pts; ++k) {
+            const double dx = g.pts[2 * k] - x, dy = g.pts[2 * k + 1] - y;
+            best = fmin(best, sqrt(dx * dx + dy * dy));
+        }
+        return best;
+    }
+    return 0.0;
+}
 
 // even-odd containment of (x, y) in the union of the goal's polygons and circles.  The crossing test
 // x < xi + (xj - xi) (y - yi) / (yj - yi) is evaluated without the division (multiplied through by yj - yi, the
@@ -237,6 +278,7 @@ struct RiskSums {
 };                                                  // gated harm maximum (Q3), largest obstacle risk
 struct CandFacts {
     double sv, sd, jl, jq, trav;  // sums over the samples: v, |d|, s_ddd^2, d_ddd^2, travelled distance
+    double x_end, y_end;          // last position (calc_dist_to_goal_pos)
     int T;
     int pre_level, pre_reason;    // validity decided before the risk: 0 / 1 / 2 with its reason, or -1
     double bd;                    // boundary harm (risk_costs.py:104-123)
@@ -305,6 +347,7 @@ __device__ __forceinline__ void assemble_costs(const DevStep& st, const DevParam
     c[ETP_C_LON_JERK] = f.jl / (double)f.T;             // :418-435
     c[ETP_C_LAT_JERK] = f.jq / (double)f.T;
     c[ETP_C_TRAVELLED_DIST] = f.trav;
+    if (pr.w[ETP_W_DIST_TO_GOAL_POS] > 0.0 && st.goal.on) c[ETP_C_DIST_TO_GOAL_POS] = dist_to_goal_pos(st.goal, f.x_end, f.y_end);
     c[ETP_C_FACTOR] = factor;
     // validity level (validity_checks.py:31-122): the tests before the risk have run (pre_level)
     if (f.pre_level >= 0) { level = f.pre_level; reason = f.pre_reason; }
@@ -322,6 +365,8 @@ __device__ __forceinline__ void assemble_costs(const DevStep& st, const DevParam
         cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GLOBAL_PATH]) * c[ETP_C_DIST_TO_GLOBAL_PATH];
     if (pr.w[ETP_W_TRAVELLED_DIST] > 0.0)
         cost += (risk_only ? 0.0 : pr.w[ETP_W_TRAVELLED_DIST]) * c[ETP_C_TRAVELLED_DIST];
+    if (pr.w[ETP_W_DIST_TO_GOAL_POS] > 0.0)
+        cost += (risk_only ? 0.0 : pr.w[ETP_W_DIST_TO_GOAL_POS]) * c[ETP_C_DIST_TO_GOAL_POS];
     c[ETP_C_TOTAL] = factor * cost;
 }
 

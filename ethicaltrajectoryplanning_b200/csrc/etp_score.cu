@@ -386,7 +386,7 @@ __device__ __noinline__ bool collide_exact(const DevStep* stp, const DevParams* 
 // shared-memory plan of one CTA
 // ---------------------------------------------------------------------------------------------
 enum { MX_EGO_RISK = 0, MX_OBST_RISK, MX_EGO_ARG, MX_OBST_ARG, MX_COUNT };  // running maxima over time, [MX][O][32]
-enum { P1_V = 0, P1_D, P1_JL, P1_JQ, P1_TRAV, P1_COUNT };                   // phase-1 partial sums, [W][P1][32]
+enum { P1_V = 0, P1_D, P1_JL, P1_JQ, P1_TRAV, P1_XE, P1_YE, P1_COUNT };                   // phase-1 partial sums, [W][P1][32]
 enum { P3_SUM_E = 0, P3_SUM_O, P3_SUM_ABS, P3_RESP, P3_MM, P3_MAX_O, P3_MM_LO, P3_MM_HI, P3_COUNT };  // phase-3 partials, [W][P3][32]
 
 template <typename R> struct Smem {
@@ -893,6 +893,9 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             }
             double* p1 = sm.p1 + (size_t)warp * P1_COUNT * 32 + lane;
             p1[P1_V * 32] = sv; p1[P1_D * 32] = sd; p1[P1_JL * 32] = jl; p1[P1_JQ * 32] = jq; p1[P1_TRAV * 32] = trav;
+            // last position of the candidate (calc_dist_to_goal_pos): held by the warp whose chunk ends the trajectory
+            const bool last = Tl > ta && Tl <= tb;
+            p1[P1_XE * 32] = last ? px : 0.0; p1[P1_YE * 32] = last ? py : 0.0;
             sm.ff[warp * 32 + lane] = first_fail;
             if (gflags) atomicOr(&s_goal[lane], gflags);
         }
@@ -1158,7 +1161,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             if (live) {
                 CandFacts f;
                 RiskSums r{0, 0, 0, 0, -INFINITY, -INFINITY};
-                f.sv = f.sd = f.jl = f.jq = f.trav = 0.0;
+                f.sv = f.sd = f.jl = f.jq = f.trav = f.x_end = f.y_end = 0.0;
                 double mm_lo = -INFINITY, mm_hi = -INFINITY;
                 int first_fail = 0x7fffffff;
                 for (int w = 0; w < kWarps; ++w) {
@@ -1166,6 +1169,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
                     const double* p3 = sm.p3 + (size_t)w * P3_COUNT * 32 + lane;
                     f.sv += p1[P1_V * 32]; f.sd += p1[P1_D * 32]; f.jl += p1[P1_JL * 32]; f.jq += p1[P1_JQ * 32];
                     f.trav += p1[P1_TRAV * 32];
+                    f.x_end += p1[P1_XE * 32]; f.y_end += p1[P1_YE * 32];
                     r.sum_e += p3[P3_SUM_E * 32]; r.sum_o += p3[P3_SUM_O * 32]; r.sum_abs += p3[P3_SUM_ABS * 32];
                     r.resp += p3[P3_RESP * 32];
                     r.mm = fmax(r.mm, p3[P3_MM * 32]);

@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_const
         }
         f.trav = block_sum(trav, s_scratch);
         f.T = T;
+        f.x_end = e_x[T - 1];
+        f.y_end = e_y[T - 1];
 
         // ---- harm logits of every (t, o) sample; probability samples inside the 5 m gate are queued ----
         for (int it = tid; it < (Ts - 1) * O; it += kResThreads) {

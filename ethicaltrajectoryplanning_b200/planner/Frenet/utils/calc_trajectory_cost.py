@@ -98,20 +98,23 @@ def goal_context(ego_state, planning_problem, scenario, goal_area):
         return None
     goal = planning_problem.goal
     state0 = goal.state_list[0]
-    centers = None
-    if getattr(goal, "lanelets_of_goal_position", None) is not None:  # :473-484
-        centers = []
+    centers = lines = points = None
+    if getattr(goal, "lanelets_of_goal_position", None) is not None:  # :473-484, :773-786
+        centers, lines = [], []
         for lanelet_id in goal.lanelets_of_goal_position[0]:
             lanelet = scenario.lanelet_network.find_lanelet_by_id(lanelet_id)
             centers.append(lanelet.center_vertices[int(len(lanelet.center_vertices) / 2.0)])
-    elif hasattr(state0, "position"):                                  # :485-488
+            lines.append(np.asarray(lanelet.center_vertices, dtype=np.float64).reshape(-1, 2))
+    elif hasattr(state0, "position"):                                  # :485-488, :788-797
         centers = [state0.position.center] if hasattr(state0.position, "center") else []
+        if hasattr(state0.position, "center"):
+            points = [np.asarray(s.position.center, dtype=np.float64) for s in goal.state_list]
     interval = lambda name: ((getattr(state0, name).start, getattr(state0, name).end) if hasattr(state0, name) else None)  # noqa: E731
     return GoalContext(
         polygons=None if goal_area is None else goal_area.polygons, circles=None if goal_area is None else goal_area.circles,
         velocity=interval("velocity"), orientation=interval("orientation"), time_step=interval("time_step") or (0, -1),
         ego_time_step=int(ego_state.time_step), ego_position=tuple(np.asarray(ego_state.position, dtype=np.float64)[:2]),
-        goal_centers=centers)
+        goal_centers=centers, goal_lines=lines, goal_points=points)
 
 
 def build_cost_dict(traj, c, params, validity_level, predictions):
@@ -125,7 +128,7 @@ def build_cost_dict(traj, c, params, validity_level, predictions):
         cost_dict["risk_cost"] = traj.risk_dict["total"]
     else:
         traj.risk_dict = {}
-    for key in ("lon_jerk", "lat_jerk", "velocity", "dist_to_global_path", "travelled_dist"):  # :269-298
+    for key in ("lon_jerk", "lat_jerk", "velocity", "dist_to_global_path", "travelled_dist", "dist_to_goal_pos"):  # :269-305
         if weights[key] > 0.0:
             cost_dict[key] = c[COST[key]]
     if validity_level < 10 and modes["multiple_cost_functions"]:  # :322-327
@@ -144,7 +147,7 @@ def calc_trajectory_costs(traj, global_path, planning_problem, ego_state, validi
     w = params["weights"]
     if w.get("responsibility", 0.0) > 0.0:
         raise NotImplementedError("reach-set responsibility is outside the scored path")
-    for k in ("visible_area", "dist_to_goal_pos", "dist_to_lane_center"):
+    for k in ("visible_area", "dist_to_lane_center"):
         if w.get(k, 0.0) > 0.0:
             raise NotImplementedError(f"cost term {k!r} needs lanelet / sensor geometry and stays on the host")
     types = dropin.obstacle_type_names(scenario, predictions, obstacle_types) if predictions else {}
@@ -162,6 +165,7 @@ def calc_trajectory_costs(traj, global_path, planning_problem, ego_state, validi
         # unweighted terms accordingly
         risk = w["risk_cost"] * c[COST["risk_cost"]] if (w["risk_cost"] > 0.0 and predictions is not None) else 0.0
         rest = 0.0 if want_risk_only else sum(
-            w[k] * c[COST[k]] for k in ("lon_jerk", "lat_jerk", "velocity", "dist_to_global_path", "travelled_dist") if w[k] > 0.0)
+            w[k] * c[COST[k]] for k in ("lon_jerk", "lat_jerk", "velocity", "dist_to_global_path", "travelled_dist", "dist_to_goal_pos")
+            if w[k] > 0.0)
         c[COST["total"]] = c[COST["factor"]] * (risk + rest)
     return build_cost_dict(traj, c, params, validity_level, predictions)

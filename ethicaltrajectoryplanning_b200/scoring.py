@@ -141,6 +141,18 @@ def make_goal(goal, keep):
         # distance() of helper_functions.py:114 is the Euclidean norm; np.mean over the list (:492-497)
         g.has_centers = 1
         g.avg_goal_distance = float(np.mean([np.linalg.norm(np.asarray(c, dtype=np.float64) - pos) for c in goal.goal_centers]))
+    # goal positions of calc_dist_to_goal_pos (calc_trajectory_cost.py:760-803)
+    lines = [np.ascontiguousarray(l, dtype=np.float64).reshape(-1, 2) for l in (getattr(goal, "goal_lines", None) or [])]
+    if lines:
+        ls = np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(l) for l in lines])]), dtype=np.int32)
+        lv = np.ascontiguousarray(np.concatenate(lines), dtype=np.float64)
+        g.n_goal_lines, g.goal_line_start, g.goal_line_vertices = len(lines), _iptr(ls), _dptr(lv)
+        keep += [ls, lv]
+    pts = getattr(goal, "goal_points", None)
+    if pts is not None and len(pts) > 0:
+        pa = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+        g.n_goal_points, g.goal_points = len(pa), _dptr(pa)
+        keep.append(pa)
     return g
 
 

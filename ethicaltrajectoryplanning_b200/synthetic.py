@@ -123,6 +123,10 @@ class GoalContext:
     ego_time_step: int = 0
     ego_position: tuple = (0.0, 0.0)
     goal_centers: Optional[list] = None
+    # goal positions calc_dist_to_goal_pos measures the trajectory's end against (:760-803): the goal lanelets' centre lines
+    # ([n, 2] polylines) if the goal is given in lanelets, else the centres of the goal states' position shapes
+    goal_lines: Optional[list] = None
+    goal_points: Optional[list] = None
 
     @property
     def has_area(self):

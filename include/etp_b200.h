@@ -63,7 +63,7 @@ enum { ETP_R_EGO_RISK = 0, ETP_R_OBST_RISK, ETP_R_EGO_HARM, ETP_R_OBST_HARM, ETP
 enum {
     ETP_C_BAYES = 0, ETP_C_EQUALITY, ETP_C_MAXIMIN, ETP_C_RESPONSIBILITY, ETP_C_EGO, ETP_C_RISK_TOTAL,
     ETP_C_VELOCITY, ETP_C_DIST_TO_GLOBAL_PATH, ETP_C_LON_JERK, ETP_C_LAT_JERK, ETP_C_TRAVELLED_DIST,
-    ETP_C_FACTOR, ETP_C_TOTAL, ETP_NUM_COST
+    ETP_C_FACTOR, ETP_C_TOTAL, ETP_C_DIST_TO_GOAL_POS, ETP_NUM_COST
 };
 
 /* validity levels (validity_checks.py:22-28) and the slot marker for skipped candidates */
@@ -190,6 +190,15 @@ typedef struct {
     double ego_x, ego_y;            /* ego_state.position */
     int32_t has_centers;            /* velocity_costs found goal centre points (:473-489); 0: cost 0 outside the goal */
     double avg_goal_distance;       /* mean distance from ego_state.position to them (:492-497) */
+    /* calc_dist_to_goal_pos (calc_trajectory_cost.py:760-803; weights['dist_to_goal_pos'] > 0): distance of the trajectory's
+     * last position to the closest goal position.  Goal given in lanelets: their centre lines as polylines (closest point
+     * of the polyline, :835-853); goal given as shapes: the centres of goal.state_list[i].position; neither (survival
+     * scenario): 0. */
+    int32_t n_goal_lines;
+    const int32_t* goal_line_start; /* [n_goal_lines + 1] first vertex of each centre line */
+    const double* goal_line_vertices; /* [goal_line_start[n_goal_lines]][2] */
+    int32_t n_goal_points;
+    const double* goal_points;      /* [n_goal_points][2] */
 } etp_goal;
 
 /*

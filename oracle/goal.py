@@ -118,6 +118,36 @@ def velocity_costs(goal, traj, dt):
     return 30.0 - np.mean(traj.v)
 
 
+def dist_to_nearest_point(center_vertices, pos):
+    """:835-853: shapely's ``linestring.interpolate(linestring.project(point))`` is the point of the polyline closest to
+    ``pos``; restated segment by segment (shapely itself is not installed here: this branch is pinned to the published
+    semantics of project / interpolate, not to a run of the reference)."""
+    p = np.asarray(center_vertices, dtype=np.float64).reshape(-1, 2)
+    pos = np.asarray(pos, dtype=np.float64)
+    if len(p) == 1:
+        return float(np.linalg.norm(pos - p[0]))
+    best = np.inf
+    for a, b in zip(p[:-1], p[1:]):
+        e = b - a
+        l2 = float(e @ e)
+        u = 0.0 if l2 == 0.0 else min(1.0, max(0.0, float((pos - a) @ e) / l2))
+        best = min(best, float(np.linalg.norm(pos - (a + u * e))))
+    return best
+
+
+def calc_dist_to_goal_pos(goal, x_end, y_end):
+    """:760-803: distance of the trajectory's last position to the closest goal position -- centre lines of the goal
+    lanelets, else centres of the goal states' shapes, else 0 (survival scenario)."""
+    pos = np.array([x_end, y_end], dtype=np.float64)
+    lines = getattr(goal, "goal_lines", None) if goal is not None else None
+    points = getattr(goal, "goal_points", None) if goal is not None else None
+    if lines:
+        return min(dist_to_nearest_point(l, pos) for l in lines)
+    if points is not None and len(points) > 0:
+        return min(float(np.linalg.norm(np.asarray(c, dtype=np.float64) - pos)) for c in points)
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------
 # vectorised over candidates of equal length (oracle/vec.py)
 # ------------------------------------------------------------------------------------------------

@@ -315,11 +315,15 @@ def score_dense(step, profiles=None):
             cst[11] = np.asarray(step.cost_factor_list, dtype=np.float64)[p * nd + idx]
         if getattr(step, "goal", None) is not None:  # oracle/goal.py (calc_trajectory_cost.py:349-415, 438-519)
             cst[11], cst[6] = _goal.factor_and_velocity_cost(step.goal, x, y, v, yaw, t, step.dt)
+        if weights.get("dist_to_goal_pos", 0.0) > 0.0:
+            g = getattr(step, "goal", None)
+            cst[13] = [_goal.calc_dist_to_goal_pos(g, x[i, -1], y[i, -1]) for i in range(n)]
         risk_only = (level < 10) & bool(modes["multiple_cost_functions"])
         total = np.zeros(n)
         if risk_in_cost:
             total += weights["risk_cost"] * cst[5]
-        for row, key in ((8, "lon_jerk"), (9, "lat_jerk"), (6, "velocity"), (7, "dist_to_global_path"), (10, "travelled_dist")):
+        for row, key in ((8, "lon_jerk"), (9, "lat_jerk"), (6, "velocity"), (7, "dist_to_global_path"), (10, "travelled_dist"),
+                         (13, "dist_to_goal_pos")):
             if weights[key] > 0.0:
                 total += np.where(risk_only, 0.0, weights[key]) * cst[row]
         cst[12] = cst[11] * total

@@ -71,6 +71,11 @@ def main():
         vel = [ctc.velocity_costs(fp, ego, problem, scenario, step.dt, area) for fp in fps]
         out[f"{name}_factor"] = np.asarray(factor, dtype=np.float64)
         out[f"{name}_velocity"] = np.asarray(vel, dtype=np.float64)
+        if scenario is None:
+            # calc_dist_to_goal_pos (:760-803), goal-shape / survival branches; the lanelet branch measures against
+            # shapely line strings (dist_to_nearest_point, :835-853), and shapely is not installable here
+            dist = [ctc.calc_dist_to_goal_pos(fp, problem, None) for fp in fps]
+            out[f"{name}_dist_goal"] = np.asarray(dist, dtype=np.float64)
         print(name, len(fps), {f: int(np.sum(np.asarray(factor) == f)) for f in (1.0, 0.01, 0.0001, 10.0)},
               "velocity cost %.3f .. %.3f" % (min(vel), max(vel)))
     np.savez_compressed(os.path.join(HERE, "goal_cases.npz"), **out)

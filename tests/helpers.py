@@ -95,6 +95,13 @@ def goal_cases():
     out = []
     for name, kw, g in specs:
         step = make_step("planning", seed=77, n_obstacles=4, nv=9, nd=11, **kw)
+        # goal positions of calc_dist_to_goal_pos: one centre = the goal state's position shape, several = lanelet centre lines
+        # (one-vertex lines, like the lanelet network tests/golden/make_golden_goal.py hands the reference)
+        c = g.get("goal_centers")
+        if c is not None and len(c) == 1:
+            g = dict(g, goal_points=[c[0]])
+        elif c is not None:
+            g = dict(g, goal_lines=[[p] for p in c])
         step.goal = GoalContext(ego_position=tuple(step.ego_position), **g)
         out.append((name, step))
     return out

@@ -96,3 +96,51 @@ def test_given_trajectories_and_drop_in_sort():
         # the drop-in modules run the fp32 context: the factor comes back as the fp32 image of 1, 0.01, 0.0001 or 10
         np.testing.assert_array_equal(np.array([got[id(fp_list[i])] for i in top]).astype(np.float32),
                                       want[top].astype(np.float32), err_msg=name)
+
+
+def test_dist_to_goal_pos_on_the_device():
+    """weights['dist_to_goal_pos'] > 0 (calc_trajectory_cost.py:299-305, 760-803): the distance of every candidate's last
+    position to the closest goal position, against the reference's own calc_dist_to_goal_pos (goal-shape / survival
+    branches, tests/golden/goal_cases.npz) and the oracle (lanelet centre lines); it enters the weighted cost."""
+    import copy
+
+    from ethicaltrajectoryplanning_b200 import _abi
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from oracle import vec
+
+    z = _golden()
+    row = _abi.COST_NAMES.index("dist_to_goal_pos")
+    checked = 0
+    for name, base in CASES:
+        if name not in ("reached_in_time", "velocity_window_narrow", "survival", "circle_and_concave", "two_t", "no_centres"):
+            continue
+        step = copy.copy(base)
+        step.params = copy.deepcopy(base.params)
+        step.params["weights"]["dist_to_goal_pos"] = 2.5
+        ref = vec.score_dense(step)
+        for precision, rtol in (("fp32", 1e-5), ("fp64", 1e-12)):
+            ctx = ScoringContext(0, precision)
+            try:
+                res = ctx.plan(step)
+                out = res.numpy()
+                keep = out["level"] != _abi.LEVEL_SKIPPED
+                if f"{name}_dist_goal" in z.files:
+                    np.testing.assert_allclose(out["cost"][row, keep], z[f"{name}_dist_goal"], rtol=rtol, atol=1e-12, err_msg=name)
+                np.testing.assert_allclose(out["cost"][row], ref["cost"][13], rtol=rtol, atol=1e-12, err_msg=name)
+                np.testing.assert_allclose(out["cost"][12, keep], ref["cost"][12, keep], rtol=1e-4 if precision == "fp32" else 1e-9, atol=1e-9)
+                assert res.best["index"] == ref["best"]["index"], (name, precision)
+                checked += 1
+            finally:
+                ctx.close()
+    assert checked == 12
+    # weighted without goal positions: the step is refused, loudly
+    step = copy.copy(CASES[0][1])
+    step.params = copy.deepcopy(step.params)
+    step.params["weights"]["dist_to_goal_pos"] = 1.0
+    step.goal = None
+    ctx = ScoringContext(0, "fp32")
+    try:
+        with pytest.raises(Exception, match="dist_to_goal_pos"):
+            ctx.plan(step)
+    finally:
+        ctx.close()

@@ -31,7 +31,7 @@ def test_abi_struct_sizes_match_the_header_layout():
     assert ctypes.sizeof(_abi.Params) == 8 * 14 + 4 * 4 + 8 + 8 * 8 + 8 * 9 * 2 + 8 * 6 + 8 * 8 + 8
     assert ctypes.sizeof(_abi.Out) == 8 + 6 * 8 + 8 + 8 + 8
     # sizeof(etp_goal), sizeof(etp_step), sizeof(etp_trajectories) as g++ lays them out (x86-64)
-    assert (ctypes.sizeof(_abi.Goal), ctypes.sizeof(_abi.Step), ctypes.sizeof(_abi.Trajectories)) == (136, 192, 88)
+    assert (ctypes.sizeof(_abi.Goal), ctypes.sizeof(_abi.Step), ctypes.sizeof(_abi.Trajectories)) == (176, 192, 88)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

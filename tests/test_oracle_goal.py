@@ -60,3 +60,45 @@ def test_check_orientation_folding():
     assert ogoal.check_orientation(0.1, (3.0, 6.5)) and not ogoal.check_orientation(1.0, (3.0, 6.5))
     # both ends folded: plain interval again
     assert ogoal.check_orientation(0.0, (6.0, 6.6)) and not ogoal.check_orientation(1.0, (6.0, 6.6))
+
+
+def test_dist_to_goal_pos_restatement_matches_the_reference():
+    """calc_dist_to_goal_pos (calc_trajectory_cost.py:760-803): goal-shape and survival branches against the reference's own
+    function; the lanelet branch (closest point of a centre line, :835-853) against hand-checked geometry."""
+    from ethicaltrajectoryplanning_b200.synthetic import GoalContext
+
+    z = _golden()
+    n = 0
+    for name, step in goal_cases():
+        key = f"{name}_dist_goal"
+        if key not in z.files:
+            continue
+        fps = port.calc_frenet_trajectories(step.c_s, step.c_s_d, step.c_s_dd, step.c_d, step.c_d_d, step.c_d_dd, step.d_list,
+                                            step.t_list, step.v_list, step.dt, step.csp, step.v_thr)
+        got = np.array([ogoal.calc_dist_to_goal_pos(step.goal, fp.x[-1], fp.y[-1]) for fp in fps], dtype=np.float64)
+        np.testing.assert_allclose(got, z[key], rtol=1e-14, atol=0, err_msg=name)
+        n += 1
+    assert n >= 10
+    g = GoalContext(goal_lines=[[(0.0, 0.0), (10.0, 0.0), (10.0, 10.0)], [(20.0, 5.0)]])
+    assert ogoal.calc_dist_to_goal_pos(g, 4.0, 3.0) == 3.0            # foot of the perpendicular on the first segment
+    assert ogoal.calc_dist_to_goal_pos(g, -3.0, 4.0) == 5.0           # before the first vertex: the vertex itself
+    assert ogoal.calc_dist_to_goal_pos(g, 12.0, 12.0) == np.hypot(2.0, 2.0)
+    assert ogoal.calc_dist_to_goal_pos(g, 19.0, 5.0) == 1.0           # a one-vertex centre line
+
+
+def test_dist_to_goal_pos_enters_the_weighted_cost_of_both_oracles():
+    import copy
+
+    name, step = [c for c in goal_cases() if c[0] == "velocity_window_narrow"][0]   # two lanelet centre lines
+    step = copy.copy(step)
+    step.params = copy.deepcopy(step.params)
+    step.params["weights"]["dist_to_goal_pos"] = 2.5
+    ref = vec.score_dense(step)
+    best, valid, invalid, allfp = port.plan_step(step)
+    live = np.flatnonzero(ref["level"] != vec.LEVEL_SKIPPED)
+    for li, c in enumerate(live):
+        fp = allfp[li]
+        if hasattr(fp, "cost_dict"):
+            assert abs(fp.cost_dict["unweighted_cost"]["dist_to_goal_pos"] - ref["cost"][13, c]) <= 1e-12
+            assert abs(fp.cost - ref["cost"][12, c]) <= 1e-10 * abs(fp.cost)
+    assert ref["best"]["list_index"] == allfp.index(best)
