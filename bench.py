@@ -291,24 +291,27 @@ def run_gpu_arm(args, step, workload_cfg):
         ms_total = float(t.item())
     best = sharded.best() if sharded is not None else ctx.best()
 
-    # kernel-only duration of the fused scoring kernel (CUDA events around the launch, same steps)
+    # kernel-only durations (CUDA events on the context's stream around the launches, same steps): profile stage, fused
+    # scoring kernel (the roofline's kernel), selection (arg-min + fp64 re-decisions)
+    launches_before = ctx.debug_counters()["launches"]
     ctx.enable_timing(True)
-    k_ms, p_ms = [], []
+    k_ms, p_ms, s_ms = [], [], []
     for _ in range(args.steps):
         ctx.launch(s, bufs)
-        a, b = ctx.timing()
+        a, b, c3 = ctx.stage_timing()
         p_ms.append(a)
         k_ms.append(b)
+        s_ms.append(c3)
     ctx.enable_timing(False)
     kernel_ms = float(np.mean(k_ms))
+    launches_per_step = (ctx.debug_counters()["launches"] - launches_before) / args.steps
 
-    # end to end through the public API with host buffers: configure (H2D), plan, best + trajectory (D2H)
-    h2d = (8 * (len(step.csp.s) + 8 * (len(step.csp.s) - 1)) + O * ctx_tp(step) * 8 * 8 + O * (3 * 8 + 3 * 4)
-           + 8 * (len(step.v_list) + len(step.t_list) + len(step.d_list)) + 4 * len(step.t_list))
-    d2h = 40 * world + 13 * Tmax * 8 + 4
+    # end to end through the public API with host buffers: configure (H2D of the step's inputs), plan, winner +
+    # trajectory (D2H); the bytes are counted by the library as it copies them (etp_debug_counters)
     for _ in range(2):
         e2e_step(ctx, step, sharded, rank, world, bufs)
     barrier()
+    c0 = ctx.debug_counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(ctx.stream):
         e0.record()
@@ -317,6 +320,9 @@ def run_gpu_arm(args, step, workload_cfg):
         e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    c1 = ctx.debug_counters()
+    h2d = (c1["h2d_bytes"] - c0["h2d_bytes"]) / args.steps
+    d2h = (c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -347,11 +353,15 @@ def run_gpu_arm(args, step, workload_cfg):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps, "selected_index": e2e_best["index"]},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "gpu_launches_per_step": {"count": launches_per_step,
+                                      "kernels": "profile_kernel, score_kernel, select_kernel, rescore_kernel" + (", ncclAllGather, combine_best_kernel" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(workload_cfg["workload"]), "peak_source": peak_src,
+                         # dram bytes of one launch from the committed ncu capture: measured on one GPU only
+                         "traffic": profiled_traffic(workload_cfg["workload"]) if world == 1 else None, "peak_source": peak_src,
                          "kernel": "etp::score_kernel<float, 2, true, false>", "kernel_ms": kernel_ms, "profile_stage_ms": float(np.mean(p_ms)),
-                         "algorithmic_bytes_per_launch": int(bytes_per_launch)},
+                         "selection_ms": float(np.mean(s_ms)), "algorithmic_bytes_per_launch": int(bytes_per_launch)},
+            "selection": ctx.debug_counters(),
             "cpu_baseline": cpu_base,
             "extras": extras,
         }
@@ -449,13 +459,10 @@ def e2e_step(ctx, step, sharded, rank, world, bufs):
     ctx._last_tmax = int(nsamp.max())
     ctx.last_dt = step.dt
     if sharded is not None:
-        sharded.launch(s, bufs)
-        best = sharded.best()
-        ctx.trajectory(best["index"])  # every rank holds the full profile table
+        sharded.launch(s, bufs)  # fused kernel, selection, all-gather, device-side combine
     else:
         ctx.launch(s, bufs)
-        best = ctx.best()
-        ctx.trajectory(best["index"])
+    best, fields, T = ctx.best_and_trajectory()  # one read-back: the global winner and its 13 fp64 rows
     return best
 
 

@@ -188,6 +188,7 @@ SYMBOLS = {
     "etp_get_stage_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "etp_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "etp_combine_best": (C.c_int, [C.POINTER(Best), C.c_int, C.c_int, C.POINTER(Best)]),
+    "etp_combine_best_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
 }
 
 

@@ -93,6 +93,8 @@ struct etp_ctx {
     DevBuf counters, best_dev, traj_dev, traj_n, given, given_T, prin;
     // selection (etp_select.cu): per-candidate workspace of the fused kernel, survivors of select_kernel, their exact keys
     DevBuf ws_cost, ws_bound, ws_meta, ws_bd, ws_gf, sel_blocks, sel_list, sel_res, sel_small;
+    // what crossed the bus and what was launched since the context was created (etp_debug_counters)
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     bool refine_off = false;  // ETP_NO_REFINE=1: fp32 selection as it comes out of the fused kernel (kernel experiments)
     bool last_given = false;
     PinnedBuf stage, best_host, traj_host;
@@ -142,6 +144,7 @@ int stage_to_device(etp_ctx* c, void* dst, const void* src, size_t bytes) {
     memcpy(h, src, bytes);
     c->stage.used += aligned;
     ETP_CUDA(c, cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += bytes;
     return ETP_OK;
 }
 
@@ -209,13 +212,17 @@ SelectBufs select_bufs(etp_ctx* c) {
 int launch_step(etp_ctx* c, const DevOut& dout) {
     const DevStep& st = c->st;
     unsigned* cnt = c->counters.as<unsigned>();
+    c->launches += 1;
     ETP_CUDA(c, launch_score(c->precision, st, c->pr, dout, cnt, c->num_sms, &c->last_grid, c->stream));
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     const SelectBufs sb = select_bufs(c);
     // shards of one step must compare exact keys with each other: a shard's survivor is always re-scored
+    c->launches += 1;
     ETP_CUDA(c, launch_select(st, sb, c->best_dev.as<BestRec>(), c->nskip.as<int>(), cnt + 1, st.given != nullptr, st.shard_count > 1, c->stream));
-    if (st.refine)
+    if (st.refine) {
+        c->launches += 1;
         ETP_CUDA(c, launch_rescore(c->precision, st, c->pr, dout, sb, c->best_dev.as<BestRec>(), c->nskip.as<int>(), c->num_sms, c->stream));
+    }
     return ETP_OK;
 }
 
@@ -498,7 +505,8 @@ int etp_set_obstacles(etp_ctx* c, const etp_obstacles* o, int precision) {
                               {&c->o_prot, o->is_protected, sizeof(int) * O}, {&c->o_resp, o->responsibility, sizeof(int) * O}})))
             return r;
         if ((r = end_staging(c))) return r;
-        ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
+        c->launches += 1;
+    ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
                                           c->o_wid.as<double>(), c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
                                           c->origin_x, c->origin_y, c->o_tile.p, c->o_const.as<double>(), c->stream));
@@ -558,11 +566,13 @@ int etp_set_raw_predictions(etp_ctx* c, const etp_raw_predictions* o, int precis
                               {&c->o_prot, o->is_protected, sizeof(int) * O}})))
             return r;
         if ((r = end_staging(c))) return r;
-        ETP_CUDA(c, launch_enrich(O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_rawlen.as<double>(), c->o_rawwid.as<double>(),
+        c->launches += 1;
+    ETP_CUDA(c, launch_enrich(O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_rawlen.as<double>(), c->o_rawwid.as<double>(),
                                   c->o_ori0.as<double>(), c->o_vel0.as<double>(), o->dt, o->safety_margin_length,
                                   o->safety_margin_width, o->ego_x, o->ego_y, o->ego_orientation, (c->pr.relaxed & ETP_RELAX_Q9_VIEW_CONE) != 0, c->o_yaw.as<double>(),
                                   c->o_vel.as<double>(), c->o_len.as<double>(), c->o_wid.as<double>(), c->o_resp.as<int>(), c->stream));
-        ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
+        c->launches += 1;
+    ETP_CUDA(c, launch_pack_obstacles(precision, O, Tp, c->o_plen.as<int>(), c->o_pos.as<double>(), c->o_cov.as<double>(),
                                           c->o_yaw.as<double>(), c->o_vel.as<double>(), c->o_len.as<double>(),
                                           c->o_wid.as<double>(), c->o_mass.as<double>(), c->o_prot.as<int>(), c->o_resp.as<int>(), c->pr.veh_m,
                                           c->origin_x, c->origin_y, c->o_tile.p, c->o_const.as<double>(), c->stream));
@@ -588,6 +598,7 @@ int etp_get_enriched(etp_ctx* c, double* yaw, double* vel, double* length, doubl
     if (c->o_wid.p)
         ETP_CUDA(c, cudaMemcpyAsync(h + sizeof(double) * (2 * n + O), c->o_wid.p, sizeof(double) * O, cudaMemcpyDeviceToHost, c->stream));
     ETP_CUDA(c, cudaMemcpyAsync(h + sizeof(double) * (2 * n + 2 * O), c->o_resp.p, sizeof(int) * O, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += bytes;
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     if (yaw) memcpy(yaw, h, sizeof(double) * n);
     if (vel) memcpy(vel, h + sizeof(double) * n, sizeof(double) * n);
@@ -844,6 +855,7 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     }
     if ((r = prepare_selection(c, st))) return r;
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    c->launches += 1;
     ETP_CUDA(c, launch_profiles(st, c->pr, c->nskip.as<int>(), c->stream));
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if ((r = launch_step(c, dout))) return r;
@@ -967,9 +979,11 @@ int etp_principle_costs(etp_ctx* c, int n, const double* ego_risk, const double*
         if ((r = stage_to_device(c, resp, responsibility, sizeof(int) * (size_t)n))) return r;
     }
     if ((r = end_staging(c))) return r;
+    c->launches += 1;
     ETP_CUDA(c, launch_principles(n, vals, resp, boundary_harm, maximin_eps, maximin_scale, (c->pr.relaxed & ETP_RELAX_Q3_MAXIMIN) != 0, res, c->stream));
     ETP_CUDA(c, c->traj_host.reserve(5 * sizeof(double)));
     ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, res, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += 5 * sizeof(double);
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(out, c->traj_host.p, 5 * sizeof(double));
     return ETP_OK;
@@ -1023,6 +1037,7 @@ int etp_get_best(etp_ctx* c, etp_best* best) {
     if (!c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "no planning step has run on this context");
     ETP_CUDA(c, cudaSetDevice(c->device));
     ETP_CUDA(c, cudaMemcpyAsync(c->best_host.p, c->best_dev.p, sizeof(BestRec), cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += sizeof(BestRec);
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     const BestRec* b = reinterpret_cast<const BestRec*>(c->best_host.p);
     best->key_hi = b->key_hi; best->key_lo = b->key_lo; best->cost = b->cost; best->index = b->index;
@@ -1042,9 +1057,11 @@ int etp_get_trajectory(etp_ctx* c, int index, double* fields, int* n_samples) {
     const size_t bytes = sizeof(double) * ETP_NUM_FIELDS * st.Tmax;
     ETP_CUDA(c, c->traj_dev.reserve(bytes));
     ETP_CUDA(c, c->traj_host.reserve(bytes + sizeof(int)));
+    c->launches += 1;
     ETP_CUDA(c, launch_trajectory(st, index, c->traj_dev.as<double>(), c->traj_n.as<int>(), c->stream));
     ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, c->traj_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p + bytes, c->traj_n.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += bytes + sizeof(int);
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(fields, c->traj_host.p, bytes);
     if (n_samples) memcpy(n_samples, c->traj_host.p + bytes, sizeof(int));
@@ -1060,8 +1077,10 @@ int etp_get_best_trajectory(etp_ctx* c, etp_best* best, double* fields, int* n_s
     const size_t fbytes = sizeof(double) * ETP_NUM_FIELDS * st.Tmax, bytes = sizeof(BestRec) + 8 + fbytes;
     ETP_CUDA(c, c->traj_dev.reserve(bytes));
     ETP_CUDA(c, c->traj_host.reserve(bytes));
+    c->launches += 1;
     ETP_CUDA(c, launch_best_trajectory(st, c->best_dev.as<BestRec>(), c->traj_dev.as<unsigned char>(), c->stream));
     ETP_CUDA(c, cudaMemcpyAsync(c->traj_host.p, c->traj_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += bytes;
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
     const BestRec* b = reinterpret_cast<const BestRec*>(c->traj_host.p);
     best->key_hi = b->key_hi; best->key_lo = b->key_lo; best->cost = b->cost; best->index = b->index;
@@ -1117,6 +1136,19 @@ int etp_debug_counters(etp_ctx* c, uint64_t* out, int n) {
         ETP_CUDA(c, cudaMemcpy(st, select_bufs(c).stats, sizeof(st), cudaMemcpyDeviceToHost));
         for (int i = 0; i < 3 && 1 + i < n; ++i) out[1 + i] = st[i];
     }
+    if (n > 4) out[4] = c->h2d_bytes;
+    if (n > 5) out[5] = c->d2h_bytes;
+    if (n > 6) out[6] = c->launches;
+    return ETP_OK;
+}
+
+int etp_combine_best_device(etp_ctx* c, const etp_best* gathered, int n, int consecutive_ranges) {
+    if (!c || !gathered || n < 1) return ETP_ERR_INVALID;
+    if (!c->have_step) ETP_FAIL(c, ETP_ERR_STATE, "no planning step has run on this context");
+    static_assert(sizeof(etp_best) == sizeof(BestRec), "etp_best and the device record share one layout");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    c->launches += 1;
+    ETP_CUDA(c, launch_combine_best(reinterpret_cast<const BestRec*>(gathered), n, consecutive_ranges, c->best_dev.as<BestRec>(), c->stream));
     return ETP_OK;
 }
 

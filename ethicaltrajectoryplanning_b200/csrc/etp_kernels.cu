@@ -421,6 +421,31 @@ __global__ void best_trajectory_kernel(DevStep st, const BestRec* __restrict__ b
     if (threadIdx.x == 0) *n_out = T;
 }
 
+// lexicographic minimum of shard-local best records (one thread: a handful of 40-byte records), the device twin of
+// etp_combine_best
+__global__ void combine_best_kernel(const BestRec* __restrict__ recs, int n, int consecutive, BestRec* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    int win = -1, before = 0, scored = 0;
+    for (int i = 0; i < n; ++i) {
+        const BestRec b = recs[i];
+        if (b.index >= 0 && (win < 0 || b.key_hi < recs[win].key_hi || (b.key_hi == recs[win].key_hi && b.key_lo < recs[win].key_lo))) {
+            win = i;
+            before = scored;
+        }
+        scored += b.n_scored;
+    }
+    BestRec r = recs[win < 0 ? 0 : win];
+    r.n_scored = scored;
+    if (win < 0) r.index = -1;
+    else r.list_index = (consecutive ? before : 0) + r.list_index;
+    *out = r;
+}
+
+cudaError_t launch_combine_best(const BestRec* recs, int n, int consecutive, BestRec* out, cudaStream_t stream) {
+    combine_best_kernel<<<1, 32, 0, stream>>>(recs, n, consecutive, out);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from etp_abi.cpp)
 // ---------------------------------------------------------------------------------------------

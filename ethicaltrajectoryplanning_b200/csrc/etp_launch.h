@@ -53,6 +53,8 @@ cudaError_t launch_enrich(int O, int Tp, const int* pred_len, const double* pos,
 cudaError_t launch_principles(int n, const double* vals /*[4][n]*/, const int* resp, double bd, double eps, double scale,
                               bool relaxed_gate, double* out5, cudaStream_t stream);
 
+cudaError_t launch_combine_best(const BestRec* recs, int n, int consecutive, BestRec* out, cudaStream_t stream);
+
 cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsigned char* combo, cudaStream_t stream);
 
 cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream);

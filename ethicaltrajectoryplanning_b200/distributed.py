@@ -115,18 +115,29 @@ class ShardedPlanner:
         return self.ctx.make_step_struct(step, shard_index=self.rank, shard_count=self.world)
 
     def launch(self, s, bufs=None):
-        """Local fused launch + all-gather of the 40-byte best records (asynchronous)."""
+        """Local fused launch, all-gather of the 40-byte best records and their combination on the device: everything is
+        asynchronous on the context's stream; the global selection replaces the context's best record."""
         torch = self.ctx.torch
         self.ctx.launch(s, bufs)
         local = self.ctx.best_device_tensor()
         if self._gather is None:
             self._gather = torch.empty((self.world * local.numel(),), dtype=torch.uint8, device=local.device)
-        with torch.cuda.stream(self.ctx.stream):  # ordered after the fused kernel on the context's stream
+        with torch.cuda.stream(self.ctx.stream):  # ordered after the selection kernels on the context's stream
             self.dist.all_gather_into_tensor(self._gather, local, group=self.group)
+        self.ctx._check(self.ctx.lib.etp_combine_best_device(self.ctx.h, C.c_void_p(self._gather.data_ptr()), self.world, 0))
         return self._gather
 
     def best(self):
-        """Synchronise and reduce the gathered records -> global selection (same on every rank)."""
+        """Synchronise and read the global selection (same on every rank): one 40-byte read-back."""
+        return self.ctx.best()
+
+    def best_and_trajectory(self):
+        """Global selection and the winner's 13 fp64 rows, regenerated on this rank (every rank holds the whole profile
+        table): one launch, one copy, one synchronisation."""
+        return self.ctx.best_and_trajectory()
+
+    def best_from_records(self):
+        """The same selection from the gathered records on the host (etp_combine_best): cross-check of the device path."""
         with self.ctx.torch.cuda.stream(self.ctx.stream):
             host = self._gather.cpu()
         recs = records_from_bytes(host.numpy(), self.world)

@@ -594,12 +594,13 @@ class ScoringContext:
         return float(v[0]), float(v[1]), float(v[2])
 
     def debug_counters(self):
-        v = (C.c_uint64 * 4)()
-        self._check(self.lib.etp_debug_counters(self.h, v, 4))
+        v = (C.c_uint64 * 7)()
+        self._check(self.lib.etp_debug_counters(self.h, v, 7))
         import struct
 
         return {"fp64_fallback_evals": int(v[0]), "rescored": int(v[1]), "bound_violations": int(v[2]),
-                "worst_error_over_bound": struct.unpack("<f", struct.pack("<I", int(v[3]) & 0xffffffff))[0]}
+                "worst_error_over_bound": struct.unpack("<f", struct.pack("<I", int(v[3]) & 0xffffffff))[0],
+                "h2d_bytes": int(v[4]), "d2h_bytes": int(v[5]), "launches": int(v[6])}
 
     def best_device_tensor(self):
         """uint8 view (torch) of the device-resident etp_best record, for collectives."""

@@ -412,13 +412,20 @@ int etp_get_stage_timing(etp_ctx* ctx, float* ms, int n);
 /* Diagnostics: out[0] = fp32-path evaluations that needed the fp64 fallback (|rho| > 0.55) since load;
  * since the context was created: out[1] = candidates the selection re-scored in fp64 (near-ties of the arg-min, max-risk /
  * maximin-gate decisions too close to call in fp32), out[2] = how many of them differed from their fp32 cost by more than the
- * bound the fp32 pass had claimed (must stay 0), out[3] = largest such error / bound seen (float bits). */
+ * bound the fp32 pass had claimed (must stay 0), out[3] = largest such error / bound seen (float bits), out[4] / out[5] =
+ * bytes this context copied host-to-device / device-to-host (output tensors stay on the device and are not in here),
+ * out[6] = kernels it launched. */
 int etp_debug_counters(etp_ctx* ctx, uint64_t* out, int n);
 
 /* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks).
  * consecutive_ranges = 0: interleaved shards of ONE range (list_index is already global);
  * consecutive_ranges = 1: records of consecutive candidate ranges, given in dense order. */
 int etp_combine_best(const etp_best* bests, int n, int consecutive_ranges, etp_best* out);
+
+/* The same on the device: `gathered` is DEVICE memory holding n records (e.g. the output of an all-gather of
+ * etp_best_device_ptr records over the ranks, on this context's stream); the result replaces this context's best record, so
+ * that etp_get_best / etp_get_best_trajectory return the global selection with one read-back.  Asynchronous. */
+int etp_combine_best_device(etp_ctx* ctx, const etp_best* gathered, int n, int consecutive_ranges);
 
 #ifdef __cplusplus
 }
