@@ -1,4 +1,5 @@
 // C ABI of the scoring path (include/etp_b200.h): context, input staging, launches, readback.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -105,8 +106,10 @@ struct etp_ctx {
     // scenario sweep: lazily created child contexts (own stream, own buffers) and the pinned result array
     std::vector<etp_ctx*> pool;
     PinnedBuf batch_host;
-    const double* last_knots = nullptr;  // spline identity of the last etp_set_spline through etp_plan_batch
-    int last_nseg = 0;
+    // fused sweep (plan_batch_fused): device arena of a chunk, two pinned images of its input region, their copy events
+    DevBuf batch_dev;
+    PinnedBuf batch_in[2];
+    cudaEvent_t batch_ev[2] = {nullptr, nullptr};
 };
 
 #define ETP_FAIL(ctx, code, ...)                            \
@@ -268,6 +271,11 @@ int etp_destroy(etp_ctx* c) {
     c->pool.clear();
     c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    c->batch_dev.release();
+    for (int i = 0; i < 2; ++i) {
+        c->batch_in[i].release();
+        if (c->batch_ev[i]) cudaEventDestroy(c->batch_ev[i]);
+    }
     DevBuf* bufs[] = {&c->knots, &c->cx, &c->cy, &c->o_pos, &c->o_cov, &c->o_yaw, &c->o_vel, &c->o_len, &c->o_mass,
                       &c->o_plen, &c->o_prot, &c->o_resp, &c->o_tile, &c->o_const, &c->o_wid, &c->o_rawlen, &c->o_rawwid, &c->o_ori0, &c->o_vel0, &c->grids, &c->ext_level, &c->bd_harm, &c->factor_list, &c->goal_geom, &c->rb_tri, &c->rb_trif, &c->rb_start, &c->rb_items, &c->obs_blob,
                       &c->prof, &c->prof_meta, &c->nskip, &c->counters, &c->best_dev, &c->traj_dev,
@@ -831,6 +839,7 @@ int etp_plan_step(etp_ctx* c, const etp_step* s, const etp_out* out) {
     ETP_CUDA(c, c->nskip.reserve(sizeof(int) * (size_t)n_prof));
     st.prof = c->prof.as<double>();
     st.prof_meta = c->prof_meta.as<double>();
+    st.nskip = c->nskip.as<int>();
     st.has_pred = c->has_pred; st.O = c->O; st.Tp = c->Tp;
     st.boundary = c->boundary;
     st.boundary.lr1s_const = c->pr.lr1s_const; st.boundary.lr1s_speed = c->pr.lr1s_speed;
@@ -989,11 +998,269 @@ int etp_principle_costs(etp_ctx* c, int n, const double* ego_risk, const double*
     return ETP_OK;
 }
 
+namespace {
+
+// Can this scenario go through the fused sweep?  Per-candidate host arrays and goal contexts take the scenario-by-scenario
+// path; so do steps too large for one selection block.
+bool batchable(const etp_scenario& s) {
+    if (!s.step || !s.obstacles || !s.knots || !s.coef_x || !s.coef_y || s.n_seg < 1) return false;
+    const etp_step& p = *s.step;
+    if (p.ext_level || p.bd_harm || p.cost_factor_list || p.goal) return false;
+    if (p.nv < 1 || p.nt < 1 || p.nd < 1 || !p.v_list || !p.t_list || !p.d_list || !p.n_samples) return false;
+    const long long dense = (long long)p.nv * p.nt * p.nd;
+    if (dense > select_chunk() || p.c_begin != 0 || p.c_end != dense || p.shard_count > 1) return false;
+    const etp_obstacles& o = *s.obstacles;
+    if (o.n_obstacles < 0 || (o.n_obstacles > 0 && (o.max_pred < 1 || !o.pred_len || !o.pos || !o.cov || !o.yaw || !o.vel || !o.length ||
+                                                    !o.width || !o.mass || !o.is_protected || !o.responsibility)))
+        return false;
+    for (int i = 0; i < p.nt; ++i)
+        if (p.n_samples[i] < 2 || p.n_samples[i] > 256) return false;
+    for (int i = 0; i < o.n_obstacles; ++i)
+        if (o.pred_len[i] < 1 || o.pred_len[i] > o.max_pred || (o.is_protected[i] != 0 && o.is_protected[i] != 1)) return false;
+    for (int i = 0; i < s.n_seg; ++i)
+        if (!(s.knots[i + 1] > s.knots[i])) return false;
+    return true;
+}
+
+struct Arena {  // offsets into a chunk's device arena, 256-byte aligned
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~size_t(255);
+        return at;
+    }
+};
+
+// One chunk of the sweep as five launches: all inputs in one upload, pack / profile / fused scoring / selection / exact
+// re-scoring each over every scenario of the chunk, one read-back of the winners.  Asynchronous; `slot` picks the pinned
+// image (two alternate so that the next chunk is assembled while this one runs).
+int plan_chunk_fused(etp_ctx* c, int n, const etp_scenario* sc, int precision, BestRec* host_out, int slot) {
+    const size_t rsz = precision == ETP_PRECISION_FP64 ? sizeof(double) : sizeof(float);
+    (void)rsz;
+    // ---- layout -----------------------------------------------------------------------------------
+    Arena in, scratch;
+    const size_t o_steps = in.take(sizeof(DevStep) * n), o_pack = in.take(sizeof(PackArgs) * n), o_sb = in.take(sizeof(SelectBufs) * n);
+    const size_t o_first = in.take(sizeof(int) * n);
+    struct Lay {
+        size_t knots, cx, cy, v, t, d, ns, pos, cov, yaw, vel, len, wid, mass, plen, prot, resp, small;
+        size_t tile, oconst, prof, meta, nskip, wc, wb, wm, wbd, wgf, blocks, list, res;
+        int Tmax, n_prof, Cs, tiles, O, Tp;
+        bool shared_spline;
+    };
+    std::vector<Lay> lay(n);
+    long long n_tiles = 0;
+    int max_items = 0, max_prof = 0, max_T = 2, max_O = 0;
+    size_t max_smem = 0;
+    for (int i = 0; i < n; ++i) {
+        const etp_scenario& s = sc[i];
+        const etp_step& p = *s.step;
+        const etp_obstacles& o = *s.obstacles;
+        Lay& L = lay[i];
+        L.Tmax = etp_tmax(&p);
+        L.n_prof = p.nv * p.nt;
+        L.Cs = L.n_prof * p.nd;
+        L.tiles = (L.Cs + 31) / 32;
+        L.O = o.n_obstacles;
+        L.Tp = L.O > 0 ? o.max_pred : 0;
+        n_tiles += L.tiles;
+        max_items = std::max(max_items, L.O * L.Tp);
+        max_prof = std::max(max_prof, L.n_prof);
+        max_T = std::max(max_T, L.Tmax);
+        max_O = std::max(max_O, L.O);
+        const size_t smem = score_smem_bytes(precision, L.Tmax, L.O);
+        if (smem > (size_t)c->smem_optin) ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "scenario %d needs %zu bytes of shared memory per CTA", i, smem);
+        max_smem = std::max(max_smem, smem);
+        // a spline the previous scenario of the chunk brought already (sweeps over one map) is not copied again
+        L.shared_spline = i > 0 && sc[i - 1].knots == s.knots && sc[i - 1].coef_x == s.coef_x && sc[i - 1].coef_y == s.coef_y &&
+                          sc[i - 1].n_seg == s.n_seg;
+        if (L.shared_spline) {
+            L.knots = lay[i - 1].knots; L.cx = lay[i - 1].cx; L.cy = lay[i - 1].cy;
+        } else {
+            L.knots = in.take(sizeof(double) * (s.n_seg + 1));
+            L.cx = in.take(sizeof(double) * 4 * s.n_seg);
+            L.cy = in.take(sizeof(double) * 4 * s.n_seg);
+        }
+        L.v = in.take(sizeof(double) * p.nv); L.t = in.take(sizeof(double) * p.nt); L.d = in.take(sizeof(double) * p.nd);
+        L.ns = in.take(sizeof(int) * p.nt);
+        const size_t m = (size_t)L.O * L.Tp;
+        L.pos = in.take(sizeof(double) * 2 * m); L.cov = in.take(sizeof(double) * 4 * m); L.yaw = in.take(sizeof(double) * m);
+        L.vel = in.take(sizeof(double) * m);
+        L.len = in.take(sizeof(double) * L.O); L.wid = in.take(sizeof(double) * L.O); L.mass = in.take(sizeof(double) * L.O);
+        L.plen = in.take(sizeof(int) * L.O); L.prot = in.take(sizeof(int) * L.O); L.resp = in.take(sizeof(int) * L.O);
+        L.small = in.take(64);  // zeroed counters of the selection
+        L.tile = scratch.take(Tile<double>::bytes(L.O > 0 ? L.O : 1, L.Tp > 0 ? L.Tp : 1));
+        L.oconst = scratch.take(sizeof(double) * OC_COUNT * (L.O > 0 ? L.O : 1));
+        L.prof = scratch.take(sizeof(double) * PF_COUNT * L.Tmax * (size_t)L.n_prof);
+        L.meta = scratch.take(sizeof(double) * PM_COUNT * (size_t)L.n_prof);
+        L.nskip = scratch.take(sizeof(int) * (size_t)L.n_prof);
+        L.wc = scratch.take(sizeof(double) * L.Cs); L.wb = scratch.take(sizeof(float) * L.Cs); L.wm = scratch.take(L.Cs);
+        L.wbd = scratch.take(sizeof(double) * L.Cs); L.wgf = scratch.take(L.Cs);
+        L.blocks = scratch.take(select_blocks_bytes(L.Cs)); L.list = scratch.take(sizeof(int) * L.Cs);
+        L.res = scratch.take(rescore_rec_bytes(L.Cs));
+    }
+    if (n_tiles >= (1ll << 30)) ETP_FAIL(c, ETP_ERR_INVALID, "too many tiles in one chunk");
+    const size_t o_tscn = in.take(sizeof(int) * (size_t)n_tiles);
+    const size_t in_bytes = in.off;
+    const size_t o_bests = scratch.take(sizeof(BestRec) * n);
+    ETP_CUDA(c, c->batch_dev.reserve(in_bytes + scratch.off));
+    unsigned char* dev = c->batch_dev.as<unsigned char>();
+    unsigned char* sdev = dev + in_bytes;
+    // the pinned image must not be rewritten while its previous copy is in flight
+    if (!c->batch_ev[slot]) ETP_CUDA(c, cudaEventCreateWithFlags(&c->batch_ev[slot], cudaEventDisableTiming));
+    else ETP_CUDA(c, cudaEventSynchronize(c->batch_ev[slot]));
+    if (c->batch_in[slot].cap < in_bytes) ETP_CUDA(c, c->batch_in[slot].reserve(in_bytes + in_bytes / 4));
+    unsigned char* h = c->batch_in[slot].p;
+    DevStep* steps = reinterpret_cast<DevStep*>(h + o_steps);
+    PackArgs* packs = reinterpret_cast<PackArgs*>(h + o_pack);
+    SelectBufs* sbs = reinterpret_cast<SelectBufs*>(h + o_sb);
+    int* tile_first = reinterpret_cast<int*>(h + o_first);
+    int* tile_scn = reinterpret_cast<int*>(h + o_tscn);
+    const SelectBufs ctx_sb = select_bufs(c);
+    const bool refine = precision == ETP_PRECISION_FP32 && !c->refine_off;
+    int tile_at = 0;
+    // ---- fill ---------------------------------------------------------------------------------------
+    for (int i = 0; i < n; ++i) {
+        const etp_scenario& s = sc[i];
+        const etp_step& p = *s.step;
+        const etp_obstacles& o = *s.obstacles;
+        const Lay& L = lay[i];
+        if (!L.shared_spline) {
+            memcpy(h + L.knots, s.knots, sizeof(double) * (s.n_seg + 1));
+            memcpy(h + L.cx, s.coef_x, sizeof(double) * 4 * s.n_seg);
+            memcpy(h + L.cy, s.coef_y, sizeof(double) * 4 * s.n_seg);
+        }
+        memcpy(h + L.v, p.v_list, sizeof(double) * p.nv);
+        memcpy(h + L.t, p.t_list, sizeof(double) * p.nt);
+        memcpy(h + L.d, p.d_list, sizeof(double) * p.nd);
+        memcpy(h + L.ns, p.n_samples, sizeof(int) * p.nt);
+        const size_t m = (size_t)L.O * L.Tp;
+        if (L.O > 0) {
+            memcpy(h + L.pos, o.pos, sizeof(double) * 2 * m); memcpy(h + L.cov, o.cov, sizeof(double) * 4 * m);
+            memcpy(h + L.yaw, o.yaw, sizeof(double) * m); memcpy(h + L.vel, o.vel, sizeof(double) * m);
+            memcpy(h + L.len, o.length, sizeof(double) * L.O); memcpy(h + L.wid, o.width, sizeof(double) * L.O);
+            memcpy(h + L.mass, o.mass, sizeof(double) * L.O); memcpy(h + L.plen, o.pred_len, sizeof(int) * L.O);
+            memcpy(h + L.prot, o.is_protected, sizeof(int) * L.O); memcpy(h + L.resp, o.responsibility, sizeof(int) * L.O);
+        }
+        memset(h + L.small, 0, 64);
+        // step origin and the fp32 rounding of a position in this scenario's coordinate range (as in etp_plan_step)
+        double ox, oy, m_abs = 0.0, dmax = 0.0;
+        if (L.O > 0) {
+            ox = o.pos[0]; oy = o.pos[1];
+            double bx0 = ox, bx1 = ox, by0 = oy, by1 = oy;
+            for (int k = 0; k < L.O; ++k)
+                for (int t = 0; t < o.pred_len[k]; ++t) {
+                    const double* q = o.pos + ((size_t)k * L.Tp + t) * 2;
+                    bx0 = std::fmin(bx0, q[0]); bx1 = std::fmax(bx1, q[0]); by0 = std::fmin(by0, q[1]); by1 = std::fmax(by1, q[1]);
+                }
+            m_abs = std::fmax(std::fmax(std::fabs(bx0 - ox), std::fabs(bx1 - ox)), std::fmax(std::fabs(by0 - oy), std::fabs(by1 - oy)));
+        } else {
+            ox = s.coef_x[0]; oy = s.coef_y[0];
+        }
+        for (int k = 0; k < s.n_seg; ++k) {
+            const double ds = s.knots[k + 1] - s.knots[k];
+            const double reach = 2.0 * std::fmax(std::fabs(s.coef_x[4 * k + 1]), std::fabs(s.coef_y[4 * k + 1])) * ds;
+            m_abs = std::fmax(m_abs, std::fmax(std::fabs(s.coef_x[4 * k] - ox), std::fabs(s.coef_y[4 * k] - oy)) + reach);
+        }
+        for (int k = 0; k < p.nd; ++k) dmax = std::fmax(dmax, std::fabs(p.d_list[k]));
+        DevStep st{};
+        st.c_s = p.c_s; st.c_s_d = p.c_s_d; st.c_s_dd = p.c_s_dd; st.c_d = p.c_d; st.c_d_d = p.c_d_d; st.c_d_dd = p.c_d_dd;
+        st.dt = p.dt; st.v_thr = p.v_thr;
+        st.v_list = reinterpret_cast<const double*>(dev + L.v); st.t_list = reinterpret_cast<const double*>(dev + L.t);
+        st.d_list = reinterpret_cast<const double*>(dev + L.d); st.nsamp = reinterpret_cast<const int*>(dev + L.ns);
+        st.nv = p.nv; st.nt = p.nt; st.nd = p.nd; st.Tmax = L.Tmax;
+        st.c_begin = 0; st.c_end = L.Cs; st.p_begin = 0; st.p_end = L.n_prof;
+        st.shard_index = 0; st.shard_count = 1; st.n_local = L.Cs;
+        st.vel_mode = p.velocity_cost_mode; st.vel_target = p.velocity_target; st.factor = p.cost_factor;
+        st.eps_pos = 2.4e-7 * (m_abs + dmax + 16.0);
+        st.origin_x = ox; st.origin_y = oy;
+        st.boundary = c->boundary;
+        st.boundary.lr1s_const = c->pr.lr1s_const; st.boundary.lr1s_speed = c->pr.lr1s_speed;
+        st.boundary.off_x = ox - st.boundary.x0; st.boundary.off_y = oy - st.boundary.y0;
+        st.knots = reinterpret_cast<const double*>(dev + L.knots); st.cx = reinterpret_cast<const double*>(dev + L.cx);
+        st.cy = reinterpret_cast<const double*>(dev + L.cy); st.nseg = s.n_seg;
+        st.prof = reinterpret_cast<double*>(sdev + L.prof); st.prof_meta = reinterpret_cast<double*>(sdev + L.meta);
+        st.nskip = reinterpret_cast<int*>(sdev + L.nskip);
+        st.has_pred = 1; st.O = L.O; st.Tp = L.Tp;
+        st.obs = sdev + L.tile; st.obs_const = reinterpret_cast<const double*>(sdev + L.oconst);
+        st.pred_len = reinterpret_cast<const int*>(dev + L.plen);
+        st.raw_pos = reinterpret_cast<const double*>(dev + L.pos); st.raw_yaw = reinterpret_cast<const double*>(dev + L.yaw);
+        st.raw_cov = reinterpret_cast<const double*>(dev + L.cov); st.raw_vel = reinterpret_cast<const double*>(dev + L.vel);
+        st.ws_cost = reinterpret_cast<double*>(sdev + L.wc); st.ws_bound = reinterpret_cast<float*>(sdev + L.wb);
+        st.ws_meta = sdev + L.wm; st.ws_bd = reinterpret_cast<double*>(sdev + L.wbd); st.ws_gf = sdev + L.wgf;
+        st.refine = refine ? 1 : 0;
+        steps[i] = st;
+        packs[i] = PackArgs{L.O, L.Tp, st.pred_len, st.raw_pos, st.raw_cov, st.raw_yaw, st.raw_vel,
+                            reinterpret_cast<const double*>(dev + L.len), reinterpret_cast<const double*>(dev + L.wid),
+                            reinterpret_cast<const double*>(dev + L.mass), reinterpret_cast<const int*>(dev + L.prot),
+                            reinterpret_cast<const int*>(dev + L.resp), c->pr.veh_m, ox, oy, sdev + L.tile,
+                            reinterpret_cast<double*>(sdev + L.oconst)};
+        SelectBufs sb;
+        sb.blocks = sdev + L.blocks; sb.list = reinterpret_cast<int*>(sdev + L.list); sb.res = sdev + L.res;
+        sb.hdr = reinterpret_cast<int*>(dev + L.small); sb.counters = reinterpret_cast<unsigned*>(dev + L.small + 16);
+        sb.stats = ctx_sb.stats;
+        sbs[i] = sb;
+        tile_first[i] = tile_at;
+        for (int k = 0; k < L.tiles; ++k) tile_scn[tile_at + k] = i;
+        tile_at += L.tiles;
+    }
+    // ---- run ----------------------------------------------------------------------------------------
+    ETP_CUDA(c, cudaMemcpyAsync(dev, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    ETP_CUDA(c, cudaEventRecord(c->batch_ev[slot], c->stream));
+    c->h2d_bytes += in_bytes;
+    const DevStep* d_steps = reinterpret_cast<const DevStep*>(dev + o_steps);
+    const SelectBufs* d_sbs = reinterpret_cast<const SelectBufs*>(dev + o_sb);
+    BestRec* d_bests = reinterpret_cast<BestRec*>(sdev + o_bests);
+    ETP_CUDA(c, launch_pack_obstacles_batch(precision, reinterpret_cast<const PackArgs*>(dev + o_pack), n, max_items, c->stream));
+    ETP_CUDA(c, launch_profiles_batch(d_steps, c->pr, n, max_prof, max_T, c->stream));
+    BatchArgs ba{d_steps, reinterpret_cast<const int*>(dev + o_tscn), reinterpret_cast<const int*>(dev + o_first), (int)n_tiles, n};
+    unsigned* cnt = c->counters.as<unsigned>();
+    ETP_CUDA(c, launch_score(precision, DevStep{}, c->pr, DevOut{}, cnt, c->num_sms, &c->last_grid, c->stream, &ba, max_smem));
+    ETP_CUDA(c, launch_select_batch(d_steps, d_sbs, d_bests, cnt + 1, n, c->stream));
+    c->launches += 4;
+    if (refine) {
+        ETP_CUDA(c, launch_rescore_batch(d_steps, c->pr, d_sbs, d_bests, n, max_T, max_O, c->stream));
+        c->launches += 1;
+    }
+    ETP_CUDA(c, cudaMemcpyAsync(host_out, d_bests, sizeof(BestRec) * n, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += sizeof(BestRec) * n;
+    return ETP_OK;
+}
+
+}  // namespace
+
 int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp_best* bests) {
     if (!c || n < 0 || (n > 0 && (!sc || !bests))) return ETP_ERR_INVALID;
     if (!c->have_params) ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params must precede etp_plan_batch");
+    if (precision != ETP_PRECISION_FP32 && precision != ETP_PRECISION_FP64) ETP_FAIL(c, ETP_ERR_INVALID, "precision");
     if (n == 0) return ETP_OK;
     ETP_CUDA(c, cudaSetDevice(c->device));
+    {
+        bool fused = getenv("ETP_BATCH_STREAMS") == nullptr;
+        for (int i = 0; i < n && fused; ++i) fused = batchable(sc[i]);
+        if (fused) {
+            // chunks of scenarios: every stage of a chunk is ONE launch over all its scenarios, and the next chunk's inputs
+            // are assembled on the host while this one runs.  A chunk's arena is reused by the next one (stream order).
+            constexpr int kChunk = 512;
+            ETP_CUDA(c, c->batch_host.reserve(sizeof(BestRec) * (size_t)n));
+            BestRec* host = reinterpret_cast<BestRec*>(c->batch_host.p);
+            c->precision = precision;
+            int slot = 0;
+            for (int at = 0; at < n; at += kChunk, slot ^= 1) {
+                const int rc = plan_chunk_fused(c, std::min(kChunk, n - at), sc + at, precision, host + at, slot);
+                if (rc != ETP_OK) {
+                    cudaStreamSynchronize(c->stream);
+                    return rc;
+                }
+            }
+            ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < n; ++i) {
+                const BestRec& b = host[i];
+                bests[i].key_hi = b.key_hi; bests[i].key_lo = b.key_lo; bests[i].cost = b.cost; bests[i].index = b.index;
+                bests[i].level = b.level; bests[i].n_scored = b.n_scored; bests[i].list_index = b.list_index;
+            }
+            return ETP_OK;
+        }
+    }
     constexpr int kPool = 8;  // scenarios in flight
     while ((int)c->pool.size() < kPool) {
         etp_ctx* k = nullptr;
@@ -1014,13 +1281,13 @@ int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp
         k->boundary = c->boundary;
         k->have_params = true;
         int rc = ETP_OK;
-        if (k->last_knots != s.knots || k->last_nseg != s.n_seg) {  // sweeps over one map share the spline
-            if ((rc = etp_set_spline(k, s.knots, s.coef_x, s.coef_y, s.n_seg))) ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
-            k->last_knots = s.knots;
-            k->last_nseg = s.n_seg;
+        // the spline travels with every scenario (8 KB): a cache keyed on the caller's pointer would mistake a new map at a
+        // recycled address for the old one
+        if ((rc = etp_set_spline(k, s.knots, s.coef_x, s.coef_y, s.n_seg)) || (rc = etp_set_obstacles(k, s.obstacles, precision)) ||
+            (rc = etp_plan_step(k, s.step, nullptr))) {
+            for (etp_ctx* q : c->pool) cudaStreamSynchronize(q->stream);  // nothing of this call may still write into batch_host
+            ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
         }
-        if ((rc = etp_set_obstacles(k, s.obstacles, precision))) ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
-        if ((rc = etp_plan_step(k, s.step, nullptr))) ETP_FAIL(c, rc, "scenario %d: %s", i, k->err.c_str());
         ETP_CUDA(c, cudaMemcpyAsync(host + i, k->best_dev.p, sizeof(BestRec), cudaMemcpyDeviceToHost, k->stream));
     }
     for (etp_ctx* k : c->pool) ETP_CUDA(c, cudaStreamSynchronize(k->stream));

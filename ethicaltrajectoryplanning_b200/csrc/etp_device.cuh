@@ -200,6 +200,7 @@ struct DevStep {
     // per-profile table [p - p_begin][PF_COUNT][Tmax] and scalars [p - p_begin][PM_COUNT]
     double* prof;
     double* prof_meta;
+    int* nskip;              // [p - p_begin] lateral targets of the profile the reference skips (ds <= |dT|)
     // obstacles
     int has_pred;  // 0: predictions is None
     int O, Tp;
@@ -223,6 +224,25 @@ struct DevStep {
     const double* given;     // [ETP_NUM_FIELDS][Tmax][given_stride], fp64
     const int* given_T;      // [n_local] samples per trajectory
     int given_stride;
+};
+
+// arguments of pack_obstacles_kernel: the prediction arrays of one planning step (etp_obstacles, device copies)
+struct PackArgs {
+    int O, Tp;
+    const int* pred_len;
+    const double *pos, *cov, *yaw, *vel, *length, *width, *mass;
+    const int *prot, *resp;
+    double veh_m, ox, oy;
+    void* tile;
+    double* oconst;
+};
+
+// scenario sweep (etp_plan_batch): the steps of a chunk and the map from the chunk's tiles to them
+struct BatchArgs {
+    const DevStep* steps;   // [n_steps] device copies
+    const int* tile_scn;    // [n_tiles] scenario of every 32-candidate tile
+    const int* tile_first;  // [n_steps] first tile of every scenario
+    int n_tiles, n_steps;
 };
 
 struct DevOut {

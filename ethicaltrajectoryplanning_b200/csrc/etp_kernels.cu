@@ -18,15 +18,21 @@ constexpr unsigned kFull = 0xffffffffu;
 // pack_obstacles_kernel: one thread per (obstacle, prediction sample)
 // ---------------------------------------------------------------------------------------------
 template <typename R>
-__global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
-                                      const double* __restrict__ cov, const double* __restrict__ yaw,
-                                      const double* __restrict__ vel, const double* __restrict__ length,
-                                      const double* __restrict__ width, const double* __restrict__ mass,
-                                      const int* __restrict__ prot,
-                                      const int* __restrict__ resp, double veh_m, double ox, double oy,
-                                      void* __restrict__ tile_base, double* __restrict__ oconst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= O * Tp) return;
+__device__ __forceinline__ void pack_sample(const PackArgs& a, int i) {
+    const int O = a.O, Tp = a.Tp;
+    const int* __restrict__ pred_len = a.pred_len;
+    const double* __restrict__ pos = a.pos;
+    const double* __restrict__ cov = a.cov;
+    const double* __restrict__ yaw = a.yaw;
+    const double* __restrict__ vel = a.vel;
+    const double* __restrict__ length = a.length;
+    const double* __restrict__ width = a.width;
+    const double* __restrict__ mass = a.mass;
+    const int* __restrict__ prot = a.prot;
+    const int* __restrict__ resp = a.resp;
+    const double veh_m = a.veh_m, ox = a.ox, oy = a.oy;
+    void* tile_base = a.tile;
+    double* __restrict__ oconst = a.oconst;
     const int o = i / Tp, t = i % Tp;
     const int n = pred_len[o];
     const Tile<R> tile(tile_base, O, Tp);
@@ -134,6 +140,18 @@ __global__ void pack_obstacles_kernel(int O, int Tp, const int* __restrict__ pre
     }
 }
 
+template <typename R> __global__ void pack_obstacles_kernel(const PackArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.O * a.Tp) pack_sample<R>(a, i);
+}
+
+// scenario sweep: blockIdx.y = scenario
+template <typename R> __global__ void pack_obstacles_batch_kernel(const PackArgs* __restrict__ args) {
+    const PackArgs a = args[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.O * a.Tp) pack_sample<R>(a, i);
+}
+
 __device__ __forceinline__ double np_gradient(const double* f, const double* s, int i, int n);
 
 // ---------------------------------------------------------------------------------------------
@@ -229,8 +247,7 @@ __device__ __forceinline__ double np_gradient(const double* f, const double* s, 
     return a * f[i - 1] + b * f[i] + c * f[i + 1];
 }
 
-__global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, int* __restrict__ nskip) {
-    extern __shared__ double sm[];
+__device__ __forceinline__ void profile_body(const DevStep& st, const DevParams& pr, int* __restrict__ nskip, double* sm, int block) {
     const int Tmax = st.Tmax;
     double* s_s = sm;
     double* s_x = sm + Tmax;
@@ -239,12 +256,12 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
     double* s_b = sm + 4 * Tmax;  // dy   -> dddy
     double* s_c = sm + 5 * Tmax;  // ddx
     double* s_d = sm + 6 * Tmax;  // ddy
-    const int p = st.p_begin + blockIdx.x;
+    const int p = st.p_begin + block;
     const int iv = p / st.nt, it = p % st.nt;
     const double vT = st.v_list[iv], tT = st.t_list[it];
     const int T = st.nsamp[it];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* pf = st.prof + (size_t)blockIdx.x * PF_COUNT * Tmax;
+    double* pf = st.prof + (size_t)block * PF_COUNT * Tmax;
 
     // quartic_polynomial(xs=c_s, vxs=c_s_d, axs=c_s_dd, vxe=vT, axe=0, T=tT-dt)  (frenet_functions.py:258-260)
     const double Te = tT - st.dt;
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
     for (int t = T + tid; t < Tmax; t += blockDim.x)
         for (int f = 0; f < PF_COUNT; ++f) pf[f * Tmax + t] = 0.0;
     if (tid == 0) {
-        double* pm = st.prof_meta + (size_t)blockIdx.x * PM_COUNT;
+        double* pm = st.prof_meta + (size_t)block * PM_COUNT;
         pm[PM_DS] = s_s[T - 1] - s_s[0];                                                  // :327-328
         pm[PM_LOW] = (fabs(st.c_s_d) < st.v_thr || fabs(vT) < st.v_thr) ? 1.0 : 0.0;  // :248-251
         pm[PM_T] = (double)T;
@@ -334,8 +351,21 @@ __global__ void __launch_bounds__(128) profile_kernel(DevStep st, DevParams pr, 
         __syncthreads();
         if (n) atomicAdd(&s_n, n);
         __syncthreads();
-        if (tid == 0) nskip[blockIdx.x] = s_n;
+        if (tid == 0) nskip[block] = s_n;
     }
+}
+
+__global__ void __launch_bounds__(128) profile_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr, int* __restrict__ nskip) {
+    extern __shared__ double sm[];
+    profile_body(st, pr, nskip, sm, blockIdx.x);
+}
+
+// scenario sweep: blockIdx.y = scenario, blockIdx.x = profile of that scenario
+__global__ void __launch_bounds__(128) profile_batch_kernel(const DevStep* __restrict__ steps, const __grid_constant__ DevParams pr) {
+    extern __shared__ double sm[];
+    const DevStep& st = steps[blockIdx.y];
+    if ((int)blockIdx.x >= st.p_end - st.p_begin) return;
+    profile_body(st, pr, st.nskip, sm, blockIdx.x);
 }
 
 // one candidate, all 13 fields in fp64 -> [ETP_NUM_FIELDS][Tmax]; requires its profile in st.prof
@@ -457,12 +487,17 @@ cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_
     const int n = O * Tp;
     if (n <= 0) return cudaSuccess;
     const int blocks = (n + 127) / 128;
-    if (precision == ETP_PRECISION_FP64)
-        pack_obstacles_kernel<double><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, width, mass, prot, resp,
-                                                                  veh_m, ox, oy, (double*)tile, oconst);
-    else
-        pack_obstacles_kernel<float><<<blocks, 128, 0, stream>>>(O, Tp, pred_len, pos, cov, yaw, vel, length, width, mass, prot, resp,
-                                                                 veh_m, ox, oy, (float*)tile, oconst);
+    const PackArgs a{O, Tp, pred_len, pos, cov, yaw, vel, length, width, mass, prot, resp, veh_m, ox, oy, tile, oconst};
+    if (precision == ETP_PRECISION_FP64) pack_obstacles_kernel<double><<<blocks, 128, 0, stream>>>(a);
+    else pack_obstacles_kernel<float><<<blocks, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_obstacles_batch(int precision, const PackArgs* args, int n_scn, int max_items, cudaStream_t stream) {
+    if (n_scn <= 0 || max_items <= 0) return cudaSuccess;
+    const dim3 grid((max_items + 127) / 128, n_scn);
+    if (precision == ETP_PRECISION_FP64) pack_obstacles_batch_kernel<double><<<grid, 128, 0, stream>>>(args);
+    else pack_obstacles_batch_kernel<float><<<grid, 128, 0, stream>>>(args);
     return cudaGetLastError();
 }
 
@@ -471,6 +506,12 @@ cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, 
     if (n_prof <= 0) return cudaSuccess;
     const size_t smem = sizeof(double) * 7 * st.Tmax;
     profile_kernel<<<n_prof, 128, smem, stream>>>(st, pr, nskip);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_profiles_batch(const DevStep* steps, const DevParams& pr, int n_scn, int max_prof, int max_T, cudaStream_t stream) {
+    if (n_scn <= 0 || max_prof <= 0) return cudaSuccess;
+    profile_batch_kernel<<<dim3(max_prof, n_scn), 128, sizeof(double) * 7 * max_T, stream>>>(steps, pr);
     return cudaGetLastError();
 }
 

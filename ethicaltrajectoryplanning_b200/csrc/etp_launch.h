@@ -16,10 +16,16 @@ cudaError_t launch_pack_obstacles(int precision, int O, int Tp, const int* pred_
 
 cudaError_t launch_profiles(const DevStep& st, const DevParams& pr, int* nskip, cudaStream_t stream);
 
+// scenario sweep: one launch per stage for all scenarios of a chunk (arrays in device memory)
+cudaError_t launch_pack_obstacles_batch(int precision, const PackArgs* args, int n_scn, int max_items, cudaStream_t stream);
+cudaError_t launch_profiles_batch(const DevStep* steps, const DevParams& pr, int n_scn, int max_prof, int max_T, cudaStream_t stream);
+
 // fused kernel: scores the candidates of `st`, materialises `out`, leaves the selection workspace (st.ws_*);
 // counters[1] is its tile counter (re-armed by select_kernel)
+// `ba` != null: the scenario sweep -- the tiles of ba->n_tiles come from many steps (ba->steps), `st` is ignored,
+// batch_smem = the largest score_smem_bytes of the scenarios
 cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
-                         int* grid_out, cudaStream_t stream);
+                         int* grid_out, cudaStream_t stream, const BatchArgs* ba = nullptr, size_t batch_smem = 0);
 
 // buffers of the selection (etp_select.cu)
 struct SelectBufs {
@@ -37,6 +43,12 @@ size_t rescore_smem_bytes(int Tmax, int O);
 // arg-min over the workspace -> *best_out, or (fp32 mode) the candidates that can still win -> rescore_kernel
 cudaError_t launch_select(const DevStep& st, const SelectBufs& sb, BestRec* best_out, const int* nskip, unsigned* tile_counter,
                           bool given, bool always_rescore, cudaStream_t stream);
+// scenario sweep: per-scenario buffers in device arrays; every scenario has at most select_chunk() candidates
+int select_chunk();
+cudaError_t launch_select_batch(const DevStep* steps, const SelectBufs* sbs, BestRec* bests, unsigned* tile_counter, int n_scn,
+                                cudaStream_t stream);
+cudaError_t launch_rescore_batch(const DevStep* steps, const DevParams& pr, const SelectBufs* sbs, BestRec* bests, int n_scn, int max_T,
+                                 int max_O, cudaStream_t stream);
 cudaError_t launch_rescore(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, const SelectBufs& sb,
                            BestRec* best_out, const int* nskip, int num_sms, cudaStream_t stream);
 

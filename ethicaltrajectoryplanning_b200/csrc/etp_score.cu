@@ -744,30 +744,32 @@ __device__ __noinline__ int goal_sample_flags(const DevGoal* gp, double x, doubl
 // ---------------------------------------------------------------------------------------------
 // score_kernel
 // ---------------------------------------------------------------------------------------------
-template <typename R, int NT, bool kSym, bool kGiven>
+// kBatch: the grid walks the tiles of MANY planning steps (scenario sweep, etp_plan_batch): tile -> scenario through
+// ba.tile_scn, the scenario's DevStep is copied into shared memory when a CTA moves on to another scenario, and everything
+// derived from the step (shared-memory plan, obstacle order, item counts) is derived again.  Arg-min only.
+template <typename R, int NT, bool kSym, bool kGiven, bool kBatch>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr, DevOut out,
-             unsigned int* __restrict__ counters) {
+score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevParams pr, DevOut out,
+             unsigned int* __restrict__ counters, const BatchArgs ba) {
     using U = typename Enc<R>::U;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Ts = st.Tmax;
-    const int O = st.has_pred ? st.O : 0;
-    const int On = O > 0 ? O : 1;
+    __shared__ DevStep s_st;  // kBatch: the current scenario's step
+    const DevStep& st = *(kBatch ? &s_st : &stp);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Smem<R> sm(smem_raw, Ts, O);
-    const int Cs = st.n_local;  // candidates scored by this call: profiles p_begin + shard_index + k * shard_count
-    const size_t Cp = out.c_stride;
-    const int n_tiles = (Cs + 31) / 32;
-    const Tile<R> tile(st.obs, st.O, st.Tp);
+    // everything below is a function of the step: set once here, and again per scenario in a batch
+    int Ts = 2, O = 0, On = 1, Cs = 0, n_tiles = kBatch ? ba.n_tiles : 0;
+    size_t Cp = out.c_stride, harm_plane = 0, mx_plane = 32;
+    bool small_planes = true;
+    Smem<R> sm(smem_raw, 2, 0);
+    Tile<R> tile(nullptr, 0, 0);
+    int* s_perm = nullptr;  // [On] obstacles sorted by class
+    int n_groups = 0, n_seg = 1, seg_len = 1, n_items = 0, chunk = 1, chunk0 = 1;
     R* o_traj = reinterpret_cast<R*>(out.traj);
     R* o_prob = reinterpret_cast<R*>(out.prob);
     R* o_red = reinterpret_cast<R*>(out.red);
     R* o_cost = reinterpret_cast<R*>(out.cost);
     R* o_harm = reinterpret_cast<R*>(out.harm);
-    const size_t harm_plane = (size_t)(Ts - 1) * O * Cp;
     const bool mahal = pr.mahalanobis != 0;
-    const size_t mx_plane = (size_t)On * 32;
-    const bool small_planes = (size_t)On * Cp < (size_t)1 << 32;  // row offsets of the [.][O][Cp] planes fit 32 bits
 
     __shared__ Tab<R> tab;
     __shared__ int s_tile, s_next, s_item, s_qn, s_qpos;
@@ -775,8 +777,37 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
     __shared__ int s_hit[32];  // lane's candidate collides with a predicted box (pr.collision_check)
     __shared__ int s_goal[32]; // GF_* flags of the lane's candidate (st.goal.on)
     __shared__ int s_leave[32]; // first ego box of the lane's candidate that touches the road boundary (st.boundary.check)
-    int* s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);  // [On] obstacles sorted by class
-    if (tid == 0) {
+    auto derive = [&]() {
+        Ts = st.Tmax;
+        O = st.has_pred ? st.O : 0;
+        On = O > 0 ? O : 1;
+        sm = Smem<R>(smem_raw, Ts, O);
+        Cs = st.n_local;  // candidates scored by this call: profiles p_begin + shard_index + k * shard_count
+        if (!kBatch) n_tiles = (Cs + 31) / 32;
+        tile = Tile<R>(st.obs, st.O, st.Tp);
+        harm_plane = (size_t)(Ts - 1) * O * Cp;
+        mx_plane = (size_t)On * 32;
+        small_planes = (size_t)On * Cp < (size_t)1 << 32;  // row offsets of the [.][O][Cp] planes fit 32 bits
+        s_perm = reinterpret_cast<int*>(sm.queue + (size_t)(Ts - 1) * On);
+        // phase-2a items: obstacle groups of kOB x time segments, about three items per warp
+        n_groups = (O + kOB - 1) / kOB;
+        n_seg = 1;
+        if (n_groups > 0) {
+            n_seg = (ETP_SEG_FACTOR * kWarps + n_groups - 1) / n_groups;
+            const int max_seg = (Ts - 1 + 7) / 8;  // at least 8 samples per segment
+            n_seg = n_seg > max_seg ? max_seg : n_seg;
+            n_seg = n_seg < 1 ? 1 : n_seg;
+        }
+        seg_len = (Ts - 1 + n_seg - 1) / n_seg;
+        n_items = n_groups * n_seg;
+        // phase-1 time chunks: warp 0 takes about half a share, because it is the warp that still has the previous tile's
+        // phase 3b (cost assembly, one candidate per lane) to finish while the others already generate
+        chunk0 = ((Ts + kWarps - 1) / kWarps) / 2;
+        chunk0 = chunk0 < 1 ? 1 : chunk0;
+        chunk = (Ts - chunk0 + kWarps - 2) / (kWarps - 1);
+        chunk = chunk < 1 ? 1 : chunk;
+    };
+    auto sort_obstacles = [&]() {  // thread 0
         fill_tab<R>(tab, pr, st.eps_pos);
         // protected obstacles first: a phase-2a item then holds one class and needs no per-sample class branch
         int n = 0;
@@ -785,20 +816,12 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         s_nprot = n;
         for (int o = 0; o < O; ++o)
             if (ldg4<R>(tile.C + o).z == (R)0) s_perm[n++] = o;
+    };
+    int cur_scn = -1;
+    if (!kBatch) {
+        derive();
+        if (tid == 0) sort_obstacles();
     }
-
-    // phase-2a items: obstacle groups of kOB x time segments, about three items per warp
-    const int n_groups = (O + kOB - 1) / kOB;
-    int n_seg = 1;
-    if (n_groups > 0) {
-        n_seg = (ETP_SEG_FACTOR * kWarps + n_groups - 1) / n_groups;
-        const int max_seg = (Ts - 1 + 7) / 8;  // at least 8 samples per segment
-        n_seg = n_seg > max_seg ? max_seg : n_seg;
-        n_seg = n_seg < 1 ? 1 : n_seg;
-    }
-    const int seg_len = (Ts - 1 + n_seg - 1) / n_seg;
-    const int n_items = n_groups * n_seg;
-    const int chunk = (Ts + kWarps - 1) / kWarps;  // phase-1 time chunks
 
     // the index of the next tile is fetched one tile ahead (by warp 1, at the start of phase 3a), so that the round trip of
     // the global atomic is off the serial path between two tiles
@@ -819,9 +842,22 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         __syncthreads();  // (a) tile index visible; previous tile fully consumed
         const int tl = s_tile;
         if (tl >= n_tiles) break;
+        if (kBatch) {
+            const int scn = __ldg(ba.tile_scn + tl);
+            if (scn != cur_scn) {  // the same for every thread of the CTA; warp 0 is through with the previous step
+                const int* src = reinterpret_cast<const int*>(ba.steps + scn);
+                for (int i = tid; i < (int)(sizeof(DevStep) / sizeof(int)); i += kThreads) reinterpret_cast<int*>(&s_st)[i] = __ldg(src + i);
+                __syncthreads();
+                derive();
+                if (tid == 0) sort_obstacles();
+                for (int i = tid; i < MX_COUNT * On * 32; i += kThreads) sm.mx[i] = Enc<R>::enc((R)-INFINITY);
+                __syncthreads();
+                cur_scn = scn;
+            }
+        }
 
         // ---- this lane's candidate -----------------------------------------------------------------
-        const int cl = tl * 32 + lane;
+        const int cl = (kBatch ? tl - __ldg(ba.tile_first + cur_scn) : tl) * 32 + lane;
         const bool active = cl < Cs;
         const int clc = active ? cl : Cs - 1;
         // generated candidates: row of the profile table and lateral target; given trajectories: none of that
@@ -844,7 +880,7 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
             int first_fail = 0x7fffffff, gflags = 0;
             Poly5 q{};
             if (!kGiven) q = lateral_poly(st, low, dT, pm[PM_TEND], ds);
-            const int ta = warp * chunk, tb = min(ta + chunk, Ts);
+            const int ta = warp == 0 ? 0 : min(chunk0 + (warp - 1) * chunk, Ts), tb = warp == 0 ? min(chunk0, Ts) : min(ta + chunk, Ts);
             double px = 0, py = 0;
             for (int t = ta; t < tb; ++t) {
                 if (t < Tl) {
@@ -902,8 +938,8 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
         const bool tile_fast = __syncthreads_and(wf) != 0;  // (b) ego samples complete; all of them wrap-free?
         // travelled distance (calc_trajectory_cost.py:739-757): the segment that enters this warp's time chunk, from the
         // neighbour's last sample in shared memory (split coordinates: exact to 1e-8 m) instead of a regenerated point
-        if (warp > 0 && warp * chunk < Tl) {
-            const int t = warp * chunk;
+        if (warp > 0 && chunk0 + (warp - 1) * chunk < Tl) {
+            const int t = chunk0 + (warp - 1) * chunk;
             const Vec4<R> a = sm.e0[(t - 1) * 32 + lane], b = sm.e0[t * 32 + lane];
             const float2 la = __half22float2(sm.el[(t - 1) * 32 + lane]), lb2 = __half22float2(sm.el[t * 32 + lane]);
             const double dx = ((double)a.x - (double)b.x) + (double)(la.x - lb2.x) * (1.0 / kLoScale);
@@ -1246,32 +1282,71 @@ score_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevPara
 // ---------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------
-template <typename R, int NT, bool kSym, bool kGiven>
-static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
-                                  int* grid_out, cudaStream_t stream) {
-    const int O = st.has_pred ? st.O : 0;
-    const size_t smem = Smem<R>::bytes(st.Tmax, O);
-    cudaError_t e = cudaFuncSetAttribute(score_kernel<R, NT, kSym, kGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// Resident CTAs per SM of one specialisation for a dynamic shared-memory size, asked of the runtime once and remembered
+// (the attribute call and the occupancy query cost several microseconds each, which a 50 us planning step notices).
+template <typename R, int NT, bool kSym, bool kGiven, bool kBatch>
+static cudaError_t resident_ctas(size_t smem, int* per_sm_out) {
+    constexpr int kSlots = 8, kDevices = 16;
+    struct Seen {
+        size_t smem[kSlots];
+        int per_sm[kSlots];
+        int n;
+        size_t attr_smem;
+    };
+    static Seen seen[kDevices] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    Seen local{};
+    Seen& sn = (dev >= 0 && dev < kDevices) ? seen[dev] : local;
+    for (int i = 0; i < sn.n; ++i)
+        if (sn.smem[i] == smem) { *per_sm_out = sn.per_sm[i]; return cudaSuccess; }
+    if (smem > sn.attr_smem) {
+        e = cudaFuncSetAttribute(score_kernel<R, NT, kSym, kGiven, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sn.attr_smem = smem;
+    }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT, kSym, kGiven>, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_kernel<R, NT, kSym, kGiven, kBatch>, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const int slot = sn.n < kSlots ? sn.n++ : 0;
+    sn.smem[slot] = smem;
+    sn.per_sm[slot] = per_sm;
+    *per_sm_out = per_sm;
+    return cudaSuccess;
+}
+
+template <typename R, int NT, bool kSym, bool kGiven, bool kBatch = false>
+static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
+                                  int* grid_out, const BatchArgs* ba, size_t batch_smem, cudaStream_t stream) {
+    const int O = st.has_pred ? st.O : 0;
+    const size_t smem = kBatch ? batch_smem : Smem<R>::bytes(st.Tmax, O);
+    int per_sm = 0;
+    cudaError_t e = resident_ctas<R, NT, kSym, kGiven, kBatch>(smem, &per_sm);
+    if (e != cudaSuccess) return e;
     // persistent grid: every SM fully occupied, never more CTAs than there are tiles
-    const long long tiles = ((long long)st.n_local + 31) / 32;
+    const long long tiles = kBatch ? ba->n_tiles : ((long long)st.n_local + 31) / 32;
     long long grid = (long long)num_sms * per_sm;
     if (grid > tiles) grid = tiles;
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
-    score_kernel<R, NT, kSym, kGiven><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, counters);
+    score_kernel<R, NT, kSym, kGiven, kBatch><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, counters, kBatch ? *ba : BatchArgs{});
     return cudaGetLastError();
 }
 
 cudaError_t launch_score(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, unsigned* counters, int num_sms,
-                         int* grid_out, cudaStream_t stream) {
+                         int* grid_out, cudaStream_t stream, const BatchArgs* ba, size_t batch_smem) {
 #define ETP_LAUNCH(R, NT, SYM, GIVEN) \
-    launch_score_t<R, NT, SYM, GIVEN>(st, pr, out, counters, num_sms, grid_out, stream)
+    launch_score_t<R, NT, SYM, GIVEN>(st, pr, out, counters, num_sms, grid_out, ba, batch_smem, stream)
+    if (ba) {  // scenario sweep: the default model's specialisation, or the generic tables
+        if (precision == ETP_PRECISION_FP64) return launch_score_t<double, -1, false, false, true>(st, pr, out, counters, num_sms, grid_out, ba, batch_smem, stream);
+        bool lr4s = pr.n_thr == 2 && pr.f_fcos[0] == -pr.f_fcos[1];
+        for (int i = 0; i <= pr.n_thr; ++i) lr4s = lr4s && pr.coef_pos[i] == pr.coef_neg[i];
+        if (lr4s) return launch_score_t<float, 2, true, false, true>(st, pr, out, counters, num_sms, grid_out, ba, batch_smem, stream);
+        return launch_score_t<float, -1, false, false, true>(st, pr, out, counters, num_sms, grid_out, ba, batch_smem, stream);
+    }
     if (st.given) {  // caller-provided trajectories: the API-compatibility path, generic tables only
         if (precision == ETP_PRECISION_FP64) return ETP_LAUNCH(double, -1, false, true);
         return ETP_LAUNCH(float, -1, false, true);

@@ -83,9 +83,10 @@ __device__ __forceinline__ void write_best(BestRec* out, int level, double cost,
 // ---------------------------------------------------------------------------------------------
 // select_kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_constant__ DevStep st, SelectBufs sb, BestRec* __restrict__ best_out,
-                                                            const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
-                                                            int always_rescore) {
+// `blk` of `nblk` blocks work on the step `st` (the whole grid for one planning step; one block per scenario in a sweep)
+__device__ __forceinline__ void select_body(const DevStep& st, const SelectBufs& sb, BestRec* __restrict__ best_out,
+                                            const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
+                                            int always_rescore, const int blk, const int nblk) {
     __shared__ int s_i[kSelThreads / 32];
     __shared__ double s_u[kSelThreads / 32], s_l[kSelThreads / 32];
     __shared__ int s_a[kSelThreads / 32];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     const int Cs = st.n_local;
     const bool refine = st.refine != 0;
     SelBlock* blocks = reinterpret_cast<SelBlock*>(sb.blocks);
-    const int base = blockIdx.x * kSelChunk;
+    const int base = blk * kSelChunk;
 
     // ---- pass 1: this block's entries ------------------------------------------------------------
     unsigned char meta[kSelPer];
@@ -161,16 +162,15 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
         }
         SelBlock r;
         r.rank_max = brank; r.n_scored = s_nsc; r.n_amb = s_namb; r.arg = ba; r.upper = bu; r.lower = bl;
-        blocks[blockIdx.x] = r;
+        blocks[blk] = r;
         __threadfence();
-        s_last = atomicAdd(&sb.counters[0], 1u) == gridDim.x - 1;
+        s_last = atomicAdd(&sb.counters[0], 1u) == (unsigned)(nblk - 1);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
 
     // ---- last block: global top level and threshold ----------------------------------------------
-    const int nblk = (int)gridDim.x;
     int hi = -1, tot = 0, amb = 0;
     for (int b = tid; b < nblk; b += kSelThreads) {
         const volatile SelBlock* r = blocks + b;
@@ -248,8 +248,27 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
         sb.hdr[2] = 0;
         sb.counters[0] = 0;  // re-arm
         sb.counters[1] = 0;
-        *tile_counter = 0;   // the fused kernel's tile counter
+        if (tile_counter) *tile_counter = 0;  // the fused kernel's tile counter
     }
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_constant__ DevStep st, const SelectBufs sb, BestRec* __restrict__ best_out,
+                                                            const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
+                                                            int always_rescore) {
+    select_body(st, sb, best_out, nskip, tile_counter, given, always_rescore, blockIdx.x, gridDim.x);
+}
+
+// scenario sweep: one block per scenario (at most kSelChunk candidates each)
+__global__ void __launch_bounds__(kSelThreads) select_batch_kernel(const DevStep* __restrict__ steps, const SelectBufs* __restrict__ sbs,
+                                                                  BestRec* __restrict__ bests, unsigned* __restrict__ tile_counter) {
+    __shared__ DevStep s_st;
+    __shared__ SelectBufs s_sb;
+    const int scn = blockIdx.x;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevStep) / sizeof(int)); i += blockDim.x)
+        reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(steps + scn)[i];
+    if (threadIdx.x == 0) s_sb = sbs[scn];
+    __syncthreads();
+    select_body(s_st, s_sb, bests + scn, s_st.nskip, scn == 0 ? tile_counter : nullptr, 0, 0, 0, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -288,12 +307,12 @@ __device__ __forceinline__ void harm_logits(const Tab<double>& tab, const ObsSam
     }
 }
 
+// CTA `first` of `nblk` takes every nblk-th survivor of the step `st`
 template <bool kGiven>
-__global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr,
-                                                             DevOut out, int out_f32, SelectBufs sb, BestRec* __restrict__ best_out,
-                                                             const int* __restrict__ nskip) {
+__device__ __forceinline__ void rescore_body(const DevStep& st, const DevParams& pr, const DevOut& out, int out_f32, const SelectBufs& sb,
+                                             BestRec* __restrict__ best_out, const int* __restrict__ nskip, unsigned char* smem_raw,
+                                             const int first, const int nblk) {
     using U = unsigned long long;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int count = sb.hdr[0];
     if (count == 0) return;  // the selection was final
     const int Ts = st.Tmax;
@@ -316,7 +335,7 @@ __global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_const
     const bool mahal = pr.mahalanobis != 0;
     RescoreRec* res = reinterpret_cast<RescoreRec*>(sb.res);
 
-    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    for (int i = first; i < count; i += nblk) {
         __syncthreads();  // previous candidate consumed; tab visible
         const int cl = sb.list[i];
         const unsigned char meta = st.ws_meta[cl];
@@ -509,7 +528,7 @@ __global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_const
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        s_last = atomicAdd(&sb.counters[1], 1u) == gridDim.x - 1;
+        s_last = atomicAdd(&sb.counters[1], 1u) == (unsigned)(nblk - 1);
     }
     __syncthreads();
     if (!s_last) return;
@@ -552,6 +571,29 @@ __global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_const
     }
 }
 
+template <bool kGiven>
+__global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr,
+                                                             const DevOut out, int out_f32, const SelectBufs sb, BestRec* __restrict__ best_out,
+                                                             const int* __restrict__ nskip) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rescore_body<kGiven>(st, pr, out, out_f32, sb, best_out, nskip, smem_raw, blockIdx.x, gridDim.x);
+}
+
+// scenario sweep: one CTA per scenario walks that scenario's survivors (usually none)
+__global__ void __launch_bounds__(kResThreads) rescore_batch_kernel(const DevStep* __restrict__ steps, const __grid_constant__ DevParams pr,
+                                                                   const SelectBufs* __restrict__ sbs, BestRec* __restrict__ bests) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ DevStep s_st;
+    __shared__ SelectBufs s_sb;
+    const int scn = blockIdx.x;
+    if (sbs[scn].hdr[0] == 0) return;  // the selection of this scenario was final
+    for (int i = threadIdx.x; i < (int)(sizeof(DevStep) / sizeof(int)); i += blockDim.x)
+        reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(steps + scn)[i];
+    if (threadIdx.x == 0) s_sb = sbs[scn];
+    __syncthreads();
+    rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests + scn, s_st.nskip, smem_raw, 0, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
@@ -590,5 +632,28 @@ cudaError_t launch_rescore(int precision, const DevStep& st, const DevParams& pr
     }
     return cudaGetLastError();
 }
+
+cudaError_t launch_select_batch(const DevStep* steps, const SelectBufs* sbs, BestRec* bests, unsigned* tile_counter, int n_scn,
+                                cudaStream_t stream) {
+    if (n_scn <= 0) return cudaSuccess;
+    select_batch_kernel<<<n_scn, kSelThreads, 0, stream>>>(steps, sbs, bests, tile_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rescore_batch(const DevStep* steps, const DevParams& pr, const SelectBufs* sbs, BestRec* bests, int n_scn, int max_T,
+                                 int max_O, cudaStream_t stream) {
+    if (n_scn <= 0) return cudaSuccess;
+    const size_t smem = rescore_smem_bytes(max_T, max_O);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(rescore_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    rescore_batch_kernel<<<n_scn, kResThreads, smem, stream>>>(steps, pr, sbs, bests);
+    return cudaGetLastError();
+}
+
+int select_chunk() { return kSelChunk; }
 
 }  // namespace etp

@@ -35,7 +35,8 @@ def _check_against_fixture(step, res, fx, rtol):
     assert res.best["list_index"] == int(fx["winner_list_index"])
     assert res.best["level"] == int(fx["winner_level"])
     assert res.best["n_scored"] == int(fx["n_scored"])
-    assert abs(res.best["cost"] - float(fx["winner_cost"])) <= 1e-9 * abs(float(fx["winner_cost"]))  # the key's cost is the fp64 one
+    # the key's cost is the fp64 one when the winner had to be told apart from near-ties, else the fp32 pass's own
+    assert abs(res.best["cost"] - float(fx["winner_cost"])) <= (1e-9 if rtol < 1e-6 else 1e-5) * abs(float(fx["winner_cost"]))
     out = res.numpy()
     nd = len(step.d_list)
     lv = out["level"].astype(np.int64).reshape(-1, nd)

@@ -33,6 +33,48 @@ def test_batched_sweep_equals_the_scenario_by_scenario_sweep():
         assert a[:3] == b[:3] and a[3] == b[3], (a, b)  # same kernels, same inputs: identical winners and costs
 
 
+def test_fused_sweep_of_2000_scenarios_equals_the_scenario_by_scenario_sweep(monkeypatch):
+    """cfg4 (BASELINE.json configs[3]): every stage of a chunk of scenarios is one launch (etp_plan_batch); the winners are
+    those of 2000 separate planning steps, in fp32 (with the fp64 re-decisions) and in the fp64 check mode; the
+    stream-pool fallback (scenarios the fused path does not take) agrees as well."""
+    from ethicaltrajectoryplanning_b200 import workloads
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+
+    ctx = ScoringContext(0, "fp32")
+    try:
+        ids = list(range(2000))
+        one, n1, _ = workloads.run_sweep(ctx, ids)
+        launches = ctx.debug_counters()["launches"]
+        bat, n2, t_pack, t_run = workloads.run_sweep_batched(ctx, ids, chunk=2000)
+        per_scenario = (ctx.debug_counters()["launches"] - launches) / len(ids)
+        assert per_scenario < 0.05, per_scenario  # five launches per chunk of 512 scenarios, not per scenario
+        assert n1 == n2 and len(one) == len(bat) == len(ids)
+        for a, b in zip(one, bat):
+            assert a[:3] == b[:3] and a[3] == b[3], (a, b)
+        assert ctx.debug_counters()["bound_violations"] == 0
+        monkeypatch.setenv("ETP_BATCH_STREAMS", "1")
+        old, n3, _, _ = workloads.run_sweep_batched(ctx, ids[:48], chunk=48)
+        monkeypatch.delenv("ETP_BATCH_STREAMS")
+        assert old == bat[:48]
+    finally:
+        ctx.close()
+    ctx = ScoringContext(0, "fp64")
+    try:
+        ids = list(range(100))
+        one, n1, _ = workloads.run_sweep(ctx, ids)
+        bat, n2, _, _ = workloads.run_sweep_batched(ctx, ids, chunk=100)
+        assert n1 == n2 and one == bat
+        # fp32 and fp64 agree on every winner
+        c32 = ScoringContext(0, "fp32")
+        try:
+            b32, _, _, _ = workloads.run_sweep_batched(c32, ids, chunk=100)
+        finally:
+            c32.close()
+        assert [r[:3] for r in b32] == [r[:3] for r in bat]
+    finally:
+        ctx.close()
+
+
 def test_closed_loop_fused_equals_materialised_and_fp64():
     from ethicaltrajectoryplanning_b200 import workloads
 
