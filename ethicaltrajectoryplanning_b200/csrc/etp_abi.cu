@@ -1,5 +1,6 @@
 // C ABI of the scoring path (include/etp_b200.h): context, input staging, launches, readback.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1245,6 +1246,12 @@ int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp
             BestRec* host = reinterpret_cast<BestRec*>(c->batch_host.p);
             c->precision = precision;
             int slot = 0;
+            const auto t0 = std::chrono::steady_clock::now();
+            // optional CUDA-event timing of the whole sweep on the stream (etp_get_stage_timing: all of it under ms[1])
+            if (c->timing) {
+                ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+                ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+            }
             for (int at = 0; at < n; at += kChunk, slot ^= 1) {
                 const int rc = plan_chunk_fused(c, std::min(kChunk, n - at), sc + at, precision, host + at, slot);
                 if (rc != ETP_OK) {
@@ -1252,7 +1259,18 @@ int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp
                     return rc;
                 }
             }
+            if (c->timing) {
+                ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+                ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+                c->have_step = true;
+            }
+            const auto t1 = std::chrono::steady_clock::now();
             ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (getenv("ETP_BATCH_PROFILE")) {
+                const auto t2 = std::chrono::steady_clock::now();
+                fprintf(stderr, "etp_plan_batch: %d scenarios, host assembly + launches %.3f ms, then waited %.3f ms for the device\n", n,
+                        std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+            }
             for (int i = 0; i < n; ++i) {
                 const BestRec& b = host[i];
                 bests[i].key_hi = b.key_hi; bests[i].key_lo = b.key_lo; bests[i].cost = b.cost; bests[i].index = b.index;

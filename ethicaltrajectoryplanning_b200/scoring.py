@@ -30,6 +30,17 @@ class NoCandidateError(ValueError):
     """Every candidate was skipped: the reference's ``max([])`` ValueError (frenet_functions.py:562-564)."""
 
 
+def _struct_dtype(ctype):
+    """numpy record dtype with the memory layout of a ctypes Structure (pointers as unsigned 64-bit addresses)."""
+    kinds = {C.c_double: "f8", C.c_float: "f4", C.c_int32: "i4", C.c_int64: "i8", C.c_uint64: "u8", C.c_void_p: "u8"}
+    names, formats, offsets = [], [], []
+    for name, typ in ctype._fields_:
+        names.append(name)
+        formats.append(kinds.get(typ, "u8"))  # anything else in these structs is a pointer
+        offsets.append(getattr(ctype, name).offset)
+    return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": C.sizeof(ctype)})
+
+
 def _dptr(a):
     return a.ctypes.data  # address of a float64 array the caller keeps alive
 
@@ -622,7 +633,14 @@ class ScoringContext:
     # -- scenario sweep ---------------------------------------------------------------------------
     def pack_scenarios(self, steps):
         """Host-side packing of independent planning steps for ``plan_batch`` (structs + the arrays they point to).
-        All steps must share params / vehicle / mode (the context's parameters)."""
+        All steps must share params / vehicle / mode (the context's parameters).
+
+        A sweep over one planning grid (equal grid sizes, equally long predictions: the usual case) is packed array-wise --
+        one stacked copy per input field for the WHOLE batch, scenario structs pointing into it; anything else goes step
+        by step."""
+        fast = self._pack_scenarios_uniform(steps)
+        if fast is not None:
+            return fast
         n = len(steps)
         arr = (_abi.Scenario * n)()
         keep = []
@@ -646,6 +664,97 @@ class ScoringContext:
             arr[i].step, arr[i].obstacles = C.pointer(s), C.pointer(o)
             arr[i].knots, arr[i].coef_x, arr[i].coef_y, arr[i].n_seg = _dptr(kn), _dptr(cx), _dptr(cy), len(kn) - 1
             keep.append((s, k, o, pk, kn, cx, cy))
+        return arr, keep
+
+    @staticmethod
+    def _pack_scenarios_uniform(steps):
+        n = len(steps)
+        if n == 0:
+            return None
+        s0 = steps[0]
+        nv, nt, nd = len(s0.v_list), len(s0.t_list), len(s0.d_list)
+        preds, flat = [], []
+        for st in steps:
+            p = st.predictions
+            if (p is None or not p or len(st.v_list) != nv or len(st.t_list) != nt or len(st.d_list) != nd or st.ext_level is not None
+                    or st.bd_harm is not None or st.cost_factor_list is not None or st.goal is not None):
+                return None
+            vals = list(p.values())
+            preds.append((p, vals))
+            flat += vals
+        Tp = len(flat[0]["pos_list"])
+        try:
+            pos = np.array([p["pos_list"] for p in flat], dtype=np.float64)
+            cov = np.array([p["cov_list"] for p in flat], dtype=np.float64)
+            yaw = np.array([p["orientation_list"] for p in flat], dtype=np.float64)
+            vel = np.array([p["v_list"] for p in flat], dtype=np.float64)
+        except ValueError:  # ragged prediction lengths
+            return None
+        No = len(flat)
+        if pos.shape != (No, Tp, 2) or cov.shape != (No, Tp, 2, 2) or yaw.shape != (No, Tp) or vel.shape != (No, Tp):
+            return None
+        length = np.array([p["shape"]["length"] for p in flat], dtype=np.float64)
+        width = np.array([p["shape"]["width"] for p in flat], dtype=np.float64)
+        resp = np.array([p.get("responsibility", 0) for p in flat], dtype=np.int32)
+        names = [getattr(st.obstacle_types[oid], "name", st.obstacle_types[oid]) for st, (p, _) in zip(steps, preds) for oid in p]
+        prot = np.zeros(No, dtype=np.int32)
+        mass = np.zeros(No)
+        car = np.zeros(No, dtype=bool)
+        for j, t in enumerate(names):
+            if t in PROTECTED_TYPES:
+                prot[j] = 1
+            elif t not in UNPROTECTED_TYPES:
+                raise ValueError(f"obstacle type {t!r} has no protection class (harm_estimation.py:52-56)")
+            if t in ("CAR", "PRIORITY_VEHICLE", "PARKED_VEHICLE", "TAXI"):
+                car[j] = True
+            else:
+                mass[j] = obstacle_mass(t, 0.0)
+        mass[car] = -1333.5 + 526.9 * np.power((length * width)[car], 0.8)  # properties.py:37, the same ufunc as obstacle_mass
+        plen = np.full(No, Tp, dtype=np.int32)
+        v = np.array([st.v_list for st in steps], dtype=np.float64)
+        t = np.array([st.t_list for st in steps], dtype=np.float64)
+        d = np.array([st.d_list for st in steps], dtype=np.float64)
+        ns = np.array([[len(np.arange(0.0, tT, st.dt)) for tT in st.t_list] for st in steps], dtype=np.int32)
+        # the struct arrays are filled column by column through numpy views of the ctypes layouts
+        counts = np.array([len(vals) for _, vals in preds], dtype=np.int64)
+        o0 = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        idx = np.arange(n, dtype=np.int64)
+        st_arr = np.zeros(n, dtype=_struct_dtype(_abi.Step))
+        for name in ("c_s", "c_s_d", "c_s_dd", "c_d", "c_d_d", "c_d_dd", "dt", "v_thr", "velocity_target", "cost_factor"):
+            st_arr[name] = [getattr(st, name) for st in steps]
+        st_arr["velocity_cost_mode"] = [int(st.velocity_cost_mode) for st in steps]
+        st_arr["nv"], st_arr["nt"], st_arr["nd"], st_arr["c_end"], st_arr["shard_count"] = nv, nt, nd, nv * nt * nd, 1
+        st_arr["v_list"] = v.ctypes.data + 8 * nv * idx
+        st_arr["t_list"] = t.ctypes.data + 8 * nt * idx
+        st_arr["d_list"] = d.ctypes.data + 8 * nd * idx
+        st_arr["n_samples"] = ns.ctypes.data + 4 * nt * idx
+        ob_arr = np.zeros(n, dtype=_struct_dtype(_abi.Obstacles))
+        ob_arr["n_obstacles"], ob_arr["max_pred"] = counts, Tp
+        for name, a, size in (("pred_len", plen, 4), ("pos", pos, 16 * Tp), ("cov", cov, 32 * Tp), ("yaw", yaw, 8 * Tp), ("vel", vel, 8 * Tp),
+                              ("length", length, 8), ("width", width, 8), ("mass", mass, 8), ("is_protected", prot, 4),
+                              ("responsibility", resp, 4)):
+            ob_arr[name] = a.ctypes.data + size * o0
+        # splines: a table is shared by consecutive scenarios that bring the same spline object or equal tables
+        tables, knp, cxp, cyp, nsg = [], [], [], [], []
+        for st in steps:
+            if not tables or tables[-1][0] is not st.csp:
+                csp = CubicSpline2D.from_foreign(st.csp)
+                kn = np.ascontiguousarray(csp.s, dtype=np.float64)
+                cx = np.ascontiguousarray(csp.coef_x, dtype=np.float64)
+                cy = np.ascontiguousarray(csp.coef_y, dtype=np.float64)
+                if tables and np.array_equal(kn, tables[-1][1]) and np.array_equal(cx, tables[-1][2]) and np.array_equal(cy, tables[-1][3]):
+                    tables[-1] = (st.csp,) + tables[-1][1:]
+                else:
+                    tables.append((st.csp, kn, cx, cy))
+            _, kn, cx, cy = tables[-1]
+            knp.append(kn.ctypes.data); cxp.append(cx.ctypes.data); cyp.append(cy.ctypes.data); nsg.append(len(kn) - 1)
+        sc_arr = np.zeros(n, dtype=_struct_dtype(_abi.Scenario))
+        sc_arr["step"] = st_arr.ctypes.data + st_arr.itemsize * idx
+        sc_arr["obstacles"] = ob_arr.ctypes.data + ob_arr.itemsize * idx
+        sc_arr["knots"], sc_arr["coef_x"], sc_arr["coef_y"], sc_arr["n_seg"] = knp, cxp, cyp, nsg
+        arr = (_abi.Scenario * n).from_buffer(sc_arr)
+        keep = [sc_arr, st_arr, ob_arr, pos, cov, yaw, vel, length, width, mass, prot, resp, plen, v, t, d, ns, tables,
+                [tb[0] for tb in tables]]
         return arr, keep
 
     def plan_batch(self, steps=None, packed=None):
