@@ -392,7 +392,7 @@ def run_sweep_arm(args):
     ids = scenario_shard(args.scenarios, rank, world)
     steps = [st for i in ids for _, st in workloads.sweep_steps(1, i)]
     ctx.set_params(steps[0].params, steps[0].vehicle, steps[0].mode)
-    chunk = 256
+    chunk = 2048  # scenarios per etp_plan_batch call (the library cuts it into chunks of 512 and overlaps their assembly with the device)
     packs = [ctx.pack_scenarios(steps[i:i + chunk]) for i in range(0, len(steps), chunk)]
 
     def one_pass(packed):
