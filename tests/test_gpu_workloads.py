@@ -146,6 +146,8 @@ def test_closed_loop_200_cycles_follow_the_oracle(weights):
         row = int(np.flatnonzero(ref["dense_index"] == ref["best"]["index"])[0])
         Tn = int(ref["T"][row])
         for name, f in names.items():
-            np.testing.assert_allclose(pl.trajectory[name], ref["traj"][f, row, :Tn], rtol=1e-6, atol=1e-9, err_msg=f"cycle {k} {name}")
+            # the curvature of a slow profile is a third difference quotient of map coordinates: 1e-4 there
+            np.testing.assert_allclose(pl.trajectory[name], ref["traj"][f, row, :Tn], rtol=1e-4 if name == "kappa_radpm" else 1e-6,
+                                       atol=1e-9, err_msg=f"cycle {k} {name}")
         ego = pl.ideal_tracking_state()
     assert pl.trajectory["s_loc_m"][1] > 20.0  # it moved along the path
