@@ -160,6 +160,11 @@ __device__ __forceinline__ void impact_coefs(const Tab<double>& pr, double ex, d
 }
 
 template <typename R> __device__ __forceinline__ R sigmoid_harm(R cst, R arg) { return (R)1 / ((R)1 + exp_(-cst - arg)); }
+// the same with two MUFU operations (ex2, rcp): ~6e-7 relative, for the harm that only multiplies a probability
+__device__ __forceinline__ float sigmoid_risk(float cst, float arg) {
+    return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * (cst + arg)));
+}
+__device__ __forceinline__ double sigmoid_risk(double cst, double arg) { return sigmoid_harm<double>(cst, arg); }
 
 // 1e-4 / mahalanobis(ego[i], pos[i-1], inv(cov[i-1]))  (collision_probability.py:281-289)
 template <typename R> __device__ __forceinline__ R inv_mahalanobis(R x, R y, R mx, R my, R i00, R i01, R i11) {

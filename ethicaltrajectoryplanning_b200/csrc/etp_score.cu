@@ -968,11 +968,22 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
 
             // ---- phase 2b: queued samples: three-point gate, collision probability, risk ------------------
             const int qn = s_qn;
+#ifdef ETP_P2B_PIPE
+            int e_next = 0;
+            if (lane == 0) e_next = atomicAdd(&s_qpos, 1);
+#endif
             for (;;) {
+#ifdef ETP_P2B_PIPE
+                // the index of the entry after this one is on its way while this one is evaluated
+                const int e = __shfl_sync(kFull, e_next, 0);
+                if (e >= qn) break;
+                if (lane == 0) e_next = atomicAdd(&s_qpos, 1);
+#else
                 int e = 0;
                 if (lane == 0) e = atomicAdd(&s_qpos, 1);
                 e = __shfl_sync(kFull, e, 0);
                 if (e >= qn) break;
+#endif
                 const unsigned ent = sm.queue[e];
                 const int t = (int)(ent >> 16), o = (int)(ent & 0x7fffu);
                 const bool amb_entry = (ent >> 15) & 1u;
@@ -1029,8 +1040,15 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                     const R dv = Logits<R, NT, kSym>::dv(c0, c1, g1);
                     const R ae = prt ? tab.lr_speed * (cr.x * dv) + pc.ce : tab.lr1s_speed * (cr.x * dv);
                     const R ao = prt ? tab.lr_speed * (cr.y * dv) + pc.co : tab.ped_speed * (cr.y * dv);
+#ifndef ETP_EXACT_SIGMOID_2B
+                    // the risk carries the probability's 1e-5: two MUFU ops per sigmoid are accurate enough here (the harm
+                    // maxima themselves take the full-precision form in phase 3a)
+                    const R he = sigmoid_risk(prt ? tab.lr_const : tab.lr1s_const, ae);
+                    const R ho = sigmoid_risk(prt ? tab.lr_const : tab.neg_ped_const, ao);
+#else
                     const R he = sigmoid_harm<R>(prt ? tab.lr_const : tab.lr1s_const, ae);
                     const R ho = sigmoid_harm<R>(prt ? tab.lr_const : tab.neg_ped_const, ao);
+#endif
                     U* m = sm.mx + (size_t)o * 32 + lane;
                     atomicMax(m + MX_EGO_RISK * mx_plane, Enc<R>::enc(he * prob));  // risk_costs.py:88-95
                     atomicMax(m + MX_OBST_RISK * mx_plane, Enc<R>::enc(ho * prob));

@@ -458,13 +458,12 @@ class ScoringContext:
         """set_params unless the same parameter objects with the same content are already on the device."""
         # identity of the objects plus their scalar content (dict order is stable): cheap enough for every cycle of a
         # closed loop, and an in-place edit of a weight or a mode still triggers the upload
-        lr = params["harm"]["log_reg"]
-        pkey = (mode, tuple(params["weights"].values()),
-                tuple(tuple(v) if isinstance(v, (list, tuple, set)) else v for v in params["modes"].values()
-                      if not isinstance(v, dict)),
-                tuple(tuple(t.values()) for t in lr.values()), tuple(params["harm"]["pedestrian"].values()),
-                (vehicle.l, vehicle.w, vehicle.l_r, vehicle.m, vehicle.steering.max, vehicle.lateral_a_max,
-                 vehicle.longitudinal.v_max, vehicle.longitudinal.a_max))
+        # every value make_params reads, as plain lists (compared with ==, never hashed: nested dicts are fine)
+        harm = params["harm"]
+        pkey = (mode, list(params["weights"].values()), list(params["modes"].values()),
+                [list(t.values()) for t in harm["log_reg"].values()], list(harm["pedestrian"].values()),
+                vehicle.l, vehicle.w, vehicle.l_r, vehicle.m, vehicle.steering.max, vehicle.lateral_a_max,
+                vehicle.longitudinal.v_max, vehicle.longitudinal.a_max)
         if getattr(self, "_params_key", None) != pkey:
             self.set_params(params, vehicle, mode)
             self._params_key = pkey
