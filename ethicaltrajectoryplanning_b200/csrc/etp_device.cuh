@@ -45,11 +45,23 @@ template <typename R> struct Tile {
         P = G + 2 * n;
         N = reinterpret_cast<const float4*>(P + 2 * n);
         C = reinterpret_cast<const Vec4<R>*>(N + kNodeVecs * n);
+#ifdef ETP_TMA_STAGE
+        Gom = C + O_;
+#endif
     }
     static __host__ __device__ size_t bytes(int O_, int Tp) {
         const size_t n = (size_t)O_ * Tp;
-        return n * (4 * sizeof(Vec4<R>) + kNodeVecs * sizeof(float4)) + (size_t)O_ * sizeof(Vec4<R>);
+        size_t b = n * (4 * sizeof(Vec4<R>) + kNodeVecs * sizeof(float4)) + (size_t)O_ * sizeof(Vec4<R>);
+#ifdef ETP_TMA_STAGE
+        b += 2 * n * sizeof(Vec4<R>);
+#endif
+        return b;
     }
+#ifdef ETP_TMA_STAGE
+    // build variant -DETP_TMA_STAGE: a second, OBSTACLE-major copy of the G plane, [O][Tp][2], so that the records one
+    // phase-2a item reads (one obstacle, a run of samples) are one contiguous range for a bulk copy (cp.async.bulk)
+    const Vec4<R>* Gom;
+#endif
 };
 
 // per-obstacle constants [o][OC_COUNT], fp64 (exact inputs of the fp64 gate re-check and the principle costs)

@@ -118,6 +118,13 @@ __device__ __forceinline__ void pack_sample(const PackArgs& a, int i) {
             }
     }
     G[1] = Vec4<R>{(R)vo, (R)cpsi, (R)spsi, sizeof(R) == 4 ? (R)__int_as_float(code) : (R)psi};
+#ifdef ETP_TMA_STAGE
+    {
+        Vec4<R>* Gom = const_cast<Vec4<R>*>(tile.Gom) + 2 * ((size_t)o * Tp + t);
+        Gom[0] = G[0];
+        Gom[1] = G[1];
+    }
+#endif
     P[0] = Vec4<R>{(R)isx, (R)isy, (R)rho, (R)cls};
     P[1] = Vec4<R>{(R)i00, (R)i01, (R)i11, (R)0};
     for (int k = 0; k < kNodeVecs; ++k) N[k] = make_float4(nodes[4 * k], nodes[4 * k + 1], nodes[4 * k + 2], nodes[4 * k + 3]);

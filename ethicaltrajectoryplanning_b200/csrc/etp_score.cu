@@ -399,6 +399,24 @@ template <typename R> struct Smem {
     double* p1;     // [kWarps][P1_COUNT][32]
     int* ff;        // [kWarps][32] first failing curvature sample * 4 + kind
     unsigned* queue;  // [(Ts-1) * On] (t << 16 | o) pairs that have a lane inside the gate's reach
+#ifdef ETP_TMA_STAGE
+    Vec4<R>* stage;            // [kWarps][kOB][seg_len][2] G records of the item a warp works on (bulk-copied)
+    unsigned long long* bar;   // [kWarps] mbarriers of the copies
+    __host__ __device__ static int seg_len_of(int Ts, int O) {
+        const int n_groups = (O + kOB - 1) / kOB;
+        int n_seg = 1;
+        if (n_groups > 0) {
+            n_seg = (ETP_SEG_FACTOR * kWarps + n_groups - 1) / n_groups;
+            const int max_seg = (Ts - 1 + 7) / 8;
+            n_seg = n_seg > max_seg ? max_seg : n_seg;
+            n_seg = n_seg < 1 ? 1 : n_seg;
+        }
+        return (Ts - 1 + n_seg - 1) / n_seg;
+    }
+    __host__ __device__ static size_t stage_bytes(int Ts, int O) {
+        return (size_t)kWarps * kOB * seg_len_of(Ts, O) * 2 * sizeof(Vec4<R>) + kWarps * sizeof(unsigned long long);
+    }
+#endif
     __host__ __device__ static size_t ego_bytes(int Ts) {
         const size_t e = 32 * (size_t)Ts * (sizeof(Vec4<R>) + sizeof(Vec2<R>) + sizeof(__half2));
         const size_t p = (size_t)kWarps * P3_COUNT * 32 * sizeof(double);
@@ -406,8 +424,12 @@ template <typename R> struct Smem {
     }
     __host__ __device__ static size_t bytes(int Ts, int O) {
         const size_t On = O > 0 ? O : 1;
-        return ego_bytes(Ts) + 32 * (MX_COUNT * On * sizeof(U) + kWarps * P1_COUNT * sizeof(double) + kWarps * sizeof(int)) +
-               sizeof(unsigned) * (size_t)(Ts - 1) * On + sizeof(int) * On;
+        size_t b = ego_bytes(Ts) + 32 * (MX_COUNT * On * sizeof(U) + kWarps * P1_COUNT * sizeof(double) + kWarps * sizeof(int)) +
+                   sizeof(unsigned) * (size_t)(Ts - 1) * On + sizeof(int) * On;
+#ifdef ETP_TMA_STAGE
+        b = ((b + 15) & ~size_t(15)) + stage_bytes(Ts, O);
+#endif
+        return b;
     }
     __device__ __forceinline__ Smem(unsigned char* base, int Ts, int O) {
         const size_t On = O > 0 ? O : 1;
@@ -419,12 +441,49 @@ template <typename R> struct Smem {
         mx = reinterpret_cast<U*>(p1 + kWarps * P1_COUNT * 32);
         ff = reinterpret_cast<int*>(mx + MX_COUNT * On * 32);
         queue = reinterpret_cast<unsigned*>(ff + kWarps * 32);
+#ifdef ETP_TMA_STAGE
+        {
+            const size_t used = (size_t)(reinterpret_cast<unsigned char*>(queue + (size_t)(Ts - 1) * On) + sizeof(int) * On - base);
+            stage = reinterpret_cast<Vec4<R>*>(base + ((used + 15) & ~size_t(15)));
+            bar = reinterpret_cast<unsigned long long*>(stage + (size_t)kWarps * kOB * seg_len_of(Ts, O) * 2);
+        }
+#endif
     }
 };
 
 // ---------------------------------------------------------------------------------------------
 // phase 2a: one item = kOB obstacles of one class x one time segment
 // ---------------------------------------------------------------------------------------------
+#ifdef ETP_TMA_STAGE
+// bulk asynchronous copy global -> shared through the TMA engine, completion counted on an mbarrier (PTX ISA: cp.async.bulk,
+// mbarrier.*); the generic-proxy loads of the staged records follow the wait on the barrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ETP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ETP_DONE;\n"
+        "bra ETP_WAIT;\n"
+        "ETP_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
 template <typename R> struct Phase2a {
     const DevStep* st;
     const DevParams* pr;
@@ -439,6 +498,12 @@ template <typename R> struct Phase2a {
     size_t Cp, harm_plane, mx_plane;
     int O, Ts, Tl, cl, lane, seg_len, n_seg, pl, id;
     bool active, mahal, given;
+#ifdef ETP_TMA_STAGE
+    const Vec4<R>* Gom;       // obstacle-major G plane
+    Vec4<R>* stage;           // this warp's staging buffer [kOB][seg_len][2]
+    unsigned long long* bar;  // this warp's mbarrier
+    unsigned* parity;         // its phase
+#endif
 };
 
 // The four samples of a step are independent dependency chains in ONE basic block (loads are clamped instead of
@@ -475,6 +540,21 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
         far2[k] = reach * reach;
         hm_e[k] = hm_o[k] = (R)-INFINITY;
     }
+#ifdef ETP_TMA_STAGE
+    if (kDense) {
+        // the 4 x (t1 - t0) records of this item: one bulk copy per obstacle out of the obstacle-major plane
+        const unsigned bytes = (unsigned)((t1 - t0) * 2 * sizeof(Vec4<R>));
+        __syncwarp();  // the warp has finished reading the previous item's records
+        if (lane == 0) {
+            mbar_expect_tx(a.bar, kOB * bytes);
+#pragma unroll
+            for (int k = 0; k < kOB; ++k)
+                bulk_g2s(a.stage + (size_t)k * a.seg_len * 2, a.Gom + 2 * ((size_t)ok[k] * a.st->Tp + t0), bytes, a.bar);
+        }
+        mbar_wait(a.bar, *a.parity);
+        *a.parity ^= 1u;
+    }
+#endif
     R* pptr = a.o_prob ? a.o_prob + (size_t)t0 * O * a.Cp + a.cl : nullptr;
     R* hptr = a.o_harm ? a.o_harm + (size_t)t0 * O * a.Cp + a.cl : nullptr;
     const Vec4<R>* gt = a.G + 2 * (size_t)t0 * O;  // records of sample t
@@ -490,8 +570,17 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
         for (int k = 0; k < kOB; ++k) {
             // harm samples are t < min(T-1, Tp) (harm_estimation.py:234); past the prediction the last record is
             // re-read and masked out
+#ifdef ETP_TMA_STAGE
+            const Vec4<R>* gp = kDense ? a.stage + ((size_t)k * a.seg_len + (t - t0)) * 2
+                                       : a.G + 2 * ((size_t)max(min(t, n_pred[k] - 1), 0) * O + ok[k]);
+#else
             const Vec4<R>* gp = kDense ? gt + 2 * ok[k] : a.G + 2 * ((size_t)max(min(t, n_pred[k] - 1), 0) * O + ok[k]);
+#endif
+#ifdef ETP_TMA_STAGE
+            const Vec4<R> g0 = kDense ? gp[0] : ldg4<R>(gp), g1 = kDense ? gp[1] : ldg4<R>(gp + 1);  // staged: shared-memory broadcast
+#else
             const Vec4<R> g0 = ldg4<R>(gp), g1 = ldg4<R>(gp + 1);
+#endif
             const R dv = L::dv(c0, c1, g1);
             const R dve = ke[k] * dv, dvo = ko[k] * dv;
             const bool hk = kDense || (has && t < n_pred[k]);
@@ -822,6 +911,14 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         derive();
         if (tid == 0) sort_obstacles();
     }
+#ifdef ETP_TMA_STAGE
+    unsigned tma_parity = 0;  // phase of this warp's mbarrier (one barrier per warp, re-used item after item)
+    if (!kBatch) {
+        if (lane == 0) mbar_init(sm.bar + warp, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+#endif
 
     // the index of the next tile is fetched one tile ahead (by warp 1, at the start of phase 3a), so that the round trip of
     // the global atomic is off the serial path between two tiles
@@ -850,6 +947,11 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 __syncthreads();
                 derive();
                 if (tid == 0) sort_obstacles();
+#ifdef ETP_TMA_STAGE
+                if (lane == 0) mbar_init(sm.bar + warp, 1);  // the barriers move with the shared-memory plan
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                tma_parity = 0;
+#endif
                 for (int i = tid; i < MX_COUNT * On * 32; i += kThreads) sm.mx[i] = Enc<R>::enc((R)-INFINITY);
                 __syncthreads();
                 cur_scn = scn;
@@ -954,7 +1056,11 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         // orientation[t+1] (collision_probability.py:168-203).
         if (O > 0) {
             Phase2a<R> pa{&st, &pr, &tab, &sm, tile.G, tile.C, o_prob, o_harm, s_perm, &s_qn, Cp, harm_plane, mx_plane, O, Ts, Tl, cl, lane,
-                          seg_len, n_seg, pl, id, active, mahal, kGiven};
+                          seg_len, n_seg, pl, id, active, mahal, kGiven
+#ifdef ETP_TMA_STAGE
+                          , tile.Gom, sm.stage + (size_t)warp * kOB * seg_len * 2, sm.bar + warp, &tma_parity
+#endif
+            };
             for (;;) {
                 int item = 0;
                 if (lane == 0) item = atomicAdd(&s_item, 1);
