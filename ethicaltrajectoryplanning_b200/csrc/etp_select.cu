@@ -23,6 +23,7 @@ constexpr int kSelPer = 16;                       // workspace entries per threa
 constexpr int kSelChunk = kSelThreads * kSelPer;  // entries per block
 constexpr int kResThreads = 256;
 constexpr int kQChunk = 32;                       // un-gated pairs whose 36 BVU values are buffered at a time
+constexpr int kEntC = 4;                          // per-pair constants kept in shared memory
 
 struct SelBlock {
     int rank_max;         // highest level rank among the block's unambiguous candidates (-1: none)
@@ -326,8 +327,11 @@ __device__ __forceinline__ void rescore_body(const DevStep& st, const DevParams&
     double* e_c = e_v + Ts;
     double* e_s = e_c + Ts;
     U* mx = reinterpret_cast<U*>(e_s + Ts);                       // [4][On]: ego risk, obstacle risk, ego logit, obstacle logit
-    double* buf = reinterpret_cast<double*>(mx + 4 * On);        // [kQChunk][36]
-    unsigned* queue = reinterpret_cast<unsigned*>(buf + kQChunk * 36);  // [(Ts-1) * On]
+    double* buf = reinterpret_cast<double*>(mx + 4 * On);        // [kQChunk][36] BVU values
+    double* nodes = buf + kQChunk * 36;                          // [kQChunk][40] sin(theta_i) | 1 - sin^2(theta_i)
+    double* lims = nodes + kQChunk * 40;                         // [kQChunk][72] 36 rectangle limits | their normal tails
+    double* ent_c = lims + kQChunk * 72;                         // [kQChunk][kEntC] 1/sx, 1/sy, rho, asin(rho)
+    unsigned* queue = reinterpret_cast<unsigned*>(ent_c + kQChunk * kEntC);  // [(Ts-1) * On]
     __shared__ Tab<double> tab;
     __shared__ int s_qn, s_last;
     __shared__ double s_scratch[kResThreads / 32];
@@ -416,28 +420,76 @@ __device__ __forceinline__ void rescore_body(const DevStep& st, const DevParams&
         for (int q0 = 0; q0 < qn; q0 += kQChunk) {
             const int qc = min(kQChunk, qn - q0);
             if (!mahal) {
-                for (int item = tid; item < qc * 36; item += kResThreads) {
-                    const int q = item / 36, k = item - q * 36;
+                // What the 36 BVU evaluations of an entry share is computed once per entry: the Gauss-Legendre nodes of the
+                // correlation (sin and 1 - sin^2, Genz' loop takes 2 * lg of them), the 18 + 18 rectangle limits and their
+                // normal tails.  The sums below run in bvu_d's own order, so the values are the check mode's.
+                for (int q = tid; q < qc; q += kResThreads) {
                     const unsigned ent = queue[q0 + q];
                     const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
-                    const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
                     const double* cv = st.raw_cov + ((size_t)o * st.Tp + t) * 4;
                     double c00 = cv[0], c01 = cv[1], c10 = cv[2], c11 = cv[3];
                     if (c00 == 0.0 && c01 == 0.0 && c10 == 0.0 && c11 == 0.0) { c00 = 0.1; c11 = 0.1; }  // :210-212
                     const double sx = sqrt(c00), sy = sqrt(c11);
-                    const double isx = 1.0 / sx, isy = 1.0 / sy, rho = c10 / sy / sx;
-                    const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
-                    const double len = 2 * st.obs_const[o * OC_COUNT + OC_HALFLEN];
-                    const double exo = cos(y1) * len / 2, eyo = sin(y1) * len / 2;
-                    const double ddx = e_x[t + 1] - rp[0], ddy = e_y[t + 1] - rp[1];
-                    const int r = k >> 2, km = r / 3, jb = r - km * 3, cn = k & 3;
-                    const double sg = km == 0 ? 0.0 : (km == 1 ? 1.0 : -1.0), sbx = jb == 0 ? 0.0 : (jb == 1 ? 1.0 : -1.0);
-                    const double ox = tab.rr * e_c[t + 1], oy = tab.rr * e_s[t + 1];
-                    const double ux = ddx - sg * exo, uy = ddy - sg * eyo;
-                    const double bx = ux + sbx * ox, by = uy + sbx * oy;
-                    const double xl = (bx - tab.hx) * isx, xu = (bx + tab.hx) * isx;
-                    const double yl = (by - tab.hy) * isy, yu = (by + tab.hy) * isy;
-                    buf[q * 36 + k] = bvu_d((cn & 1) ? xu : xl, (cn & 2) ? yu : yl, rho);
+                    double* e = ent_c + q * kEntC;
+                    e[0] = 1.0 / sx; e[1] = 1.0 / sy; e[2] = c10 / sy / sx;
+                    e[3] = asin(e[2]);
+                }
+                __syncthreads();
+                for (int item = tid; item < qc * 56; item += kResThreads) {
+                    const int q = item / 56, m = item - q * 56;
+                    const unsigned ent = queue[q0 + q];
+                    const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
+                    const double* e = ent_c + q * kEntC;
+                    if (m < 20) {  // node m of the rho integral (only the 2 * lg first are used)
+                        const double ar = fabs(e[2]);
+                        const int ng = ar < 0.3 ? 0 : (ar < 0.75 ? 1 : 2), i = m >> 1;
+                        const double sn = sin(e[3] * (((m & 1) ? kGLx[ng][i] : -kGLx[ng][i]) + 1.0) / 2.0);
+                        nodes[q * 40 + m] = sn;
+                        nodes[q * 40 + 20 + m] = 1.0 - sn * sn;
+                    } else {       // limit m - 20: x limits of the nine rectangles (lower, upper), then the y limits
+                        const int l = m - 20, axis = l / 18, r = (l - axis * 18) >> 1, up = l & 1;
+                        const int km = r / 3, jb = r - km * 3;
+                        const double* rp = st.raw_pos + ((size_t)o * st.Tp + t) * 2;
+                        const double y1 = st.raw_yaw[(size_t)o * st.Tp + t + 1];
+                        const double len = 2 * st.obs_const[o * OC_COUNT + OC_HALFLEN];
+                        const double sg = km == 0 ? 0.0 : (km == 1 ? 1.0 : -1.0), sbx = jb == 0 ? 0.0 : (jb == 1 ? 1.0 : -1.0);
+                        double lim;
+                        if (axis == 0) {
+                            const double exo = cos(y1) * len / 2, ddx = e_x[t + 1] - rp[0], ox = tab.rr * e_c[t + 1];
+                            const double bx = (ddx - sg * exo) + sbx * ox;
+                            lim = (up ? bx + tab.hx : bx - tab.hx) * e[0];
+                        } else {
+                            const double eyo = sin(y1) * len / 2, ddy = e_y[t + 1] - rp[1], oy = tab.rr * e_s[t + 1];
+                            const double by = (ddy - sg * eyo) + sbx * oy;
+                            lim = (up ? by + tab.hy : by - tab.hy) * e[1];
+                        }
+                        lims[q * 72 + l] = lim;
+                        lims[q * 72 + 36 + l] = phi_d(-lim);
+                    }
+                }
+                __syncthreads();
+                for (int item = tid; item < qc * 36; item += kResThreads) {
+                    const int q = item / 36, k = item - q * 36;
+                    const double* e = ent_c + q * kEntC;
+                    const int r = k >> 2, cn = k & 3;
+                    const int ih = 2 * r + (cn & 1), ik = 18 + 2 * r + ((cn >> 1) & 1);
+                    const double h = lims[q * 72 + ih], kk = lims[q * 72 + ik], rho = e[2];
+                    const double ar = fabs(rho);
+                    double val;
+                    if (ar < 0.925) {  // bvu_d's first branch with the shared nodes
+                        const int ng = ar < 0.3 ? 0 : (ar < 0.75 ? 1 : 2), lg = ng == 0 ? 3 : (ng == 1 ? 6 : 10);
+                        const double hk = h * kk, hs = (h * h + kk * kk) / 2.0;
+                        const double* sn = nodes + q * 40;
+                        double bvn = 0.0;
+                        for (int i = 0; i < lg; ++i) {
+                            bvn += kGLw[ng][i] * exp((sn[2 * i] * hk - hs) / sn[20 + 2 * i]);
+                            bvn += kGLw[ng][i] * exp((sn[2 * i + 1] * hk - hs) / sn[20 + 2 * i + 1]);
+                        }
+                        val = bvn * e[3] / (2.0 * 6.283185307179586) + lims[q * 72 + 36 + ih] * lims[q * 72 + 36 + ik];
+                    } else {
+                        val = bvu_d(h, kk, rho);
+                    }
+                    buf[q * 36 + k] = val;
                 }
                 __syncthreads();
             }
@@ -609,7 +661,7 @@ cudaError_t launch_select(const DevStep& st, const SelectBufs& sb, BestRec* best
 
 size_t rescore_smem_bytes(int Tmax, int O) {
     const size_t On = O > 0 ? O : 1;
-    return sizeof(double) * 6 * Tmax + sizeof(unsigned long long) * 4 * On + sizeof(double) * kQChunk * 36 +
+    return sizeof(double) * 6 * Tmax + sizeof(unsigned long long) * 4 * On + sizeof(double) * kQChunk * (36 + 40 + 72 + kEntC) +
            sizeof(unsigned) * (size_t)(Tmax - 1) * On + 16;
 }
 
