@@ -209,6 +209,7 @@ SelectBufs select_bufs(etp_ctx* c) {
     sb.hdr = reinterpret_cast<int*>(sm);
     sb.counters = reinterpret_cast<unsigned*>(sm + 16);
     sb.stats = reinterpret_cast<unsigned long long*>(sm + 32);
+    sb.state = sm + 64;
     return sb;
 }
 
@@ -221,7 +222,7 @@ int launch_step(etp_ctx* c, const DevOut& dout) {
     if (c->timing) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     const SelectBufs sb = select_bufs(c);
     // shards of one step must compare exact keys with each other: a shard's survivor is always re-scored
-    c->launches += 1;
+    c->launches += (st.refine && st.n_local > select_chunk()) ? 2 : 1;
     ETP_CUDA(c, launch_select(st, sb, c->best_dev.as<BestRec>(), c->nskip.as<int>(), cnt + 1, st.given != nullptr, st.shard_count > 1, c->stream));
     if (st.refine) {
         c->launches += 1;
@@ -1199,6 +1200,7 @@ int plan_chunk_fused(etp_ctx* c, int n, const etp_scenario* sc, int precision, B
         sb.blocks = sdev + L.blocks; sb.list = reinterpret_cast<int*>(sdev + L.list); sb.res = sdev + L.res;
         sb.hdr = reinterpret_cast<int*>(dev + L.small); sb.counters = reinterpret_cast<unsigned*>(dev + L.small + 16);
         sb.stats = ctx_sb.stats;
+        sb.state = nullptr;  // one selection block per scenario: no second launch
         sbs[i] = sb;
         tile_first[i] = tile_at;
         for (int k = 0; k < L.tiles; ++k) tile_scn[tile_at + k] = i;

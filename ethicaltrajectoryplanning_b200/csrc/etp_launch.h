@@ -35,6 +35,7 @@ struct SelectBufs {
     int* hdr;                   // [0] candidates left for rescore_kernel, [1] non-skipped candidates, [2] fill of `list` during select_kernel
     unsigned* counters;         // [2] completion counters of the two kernels
     unsigned long long* stats;  // [0] candidates re-scored, [1] of them outside their fp32 bound, [2] largest error / bound (float bits)
+    void* state;                // hand-over between the two selection launches of a step with several blocks (32 bytes)
 };
 size_t select_blocks_bytes(int n_local);
 size_t rescore_rec_bytes(int n_local);

@@ -21,7 +21,7 @@ namespace etp {
 constexpr int kSelThreads = 256;
 constexpr int kSelPer = 16;                       // workspace entries per thread
 constexpr int kSelChunk = kSelThreads * kSelPer;  // entries per block
-constexpr int kResThreads = 256;
+constexpr int kResThreads = 512;
 constexpr int kQChunk = 32;                       // un-gated pairs whose 36 BVU values are buffered at a time
 constexpr int kEntC = 4;                          // per-pair constants kept in shared memory
 
@@ -30,6 +30,13 @@ struct SelBlock {
     int n_scored, n_amb;  // non-skipped / ambiguous candidates
     int arg;              // column of the smallest (upper, column) at rank_max
     double upper, lower;  // min of cost + bound / of cost - bound at rank_max
+};
+
+struct SelState {  // what select_kernel leaves for select_collect_kernel (steps with more than one block)
+    double thr;    // smallest upper bound cost + bound of the top level
+    int hi;        // top level rank among the unambiguous candidates
+    int n_scored, n_amb;
+    int pending;   // 1: the survivors still have to be collected
 };
 
 struct RescoreRec {
@@ -85,6 +92,8 @@ __device__ __forceinline__ void write_best(BestRec* out, int level, double cost,
 // select_kernel
 // ---------------------------------------------------------------------------------------------
 // `blk` of `nblk` blocks work on the step `st` (the whole grid for one planning step; one block per scenario in a sweep)
+// With more than one block the survivors are collected by a second launch (select_collect_kernel, every block its own
+// chunk) instead of by the last block alone.
 __device__ __forceinline__ void select_body(const DevStep& st, const SelectBufs& sb, BestRec* __restrict__ best_out,
                                             const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
                                             int always_rescore, const int blk, const int nblk) {
@@ -217,6 +226,15 @@ __device__ __forceinline__ void select_body(const DevStep& st, const SelectBufs&
     int done_cl = -2;  // >= -1: the selection is final (column, -1 = no candidate)
     if (n_scored == 0) done_cl = -1;
     else if (!refine) done_cl = arg;  // exact costs: the minimum is the selection (n_amb == 0, so hi >= 0)
+    if (nblk > 1) {
+        SelState* state = reinterpret_cast<SelState*>(sb.state);
+        if (tid == 0) {
+            state->thr = thr; state->hi = hi; state->n_scored = n_scored; state->n_amb = n_amb;
+            state->pending = done_cl == -2 ? 1 : 0;
+            sb.counters[0] = 0;  // re-armed for select_collect_kernel
+        }
+        if (done_cl == -2) return;  // select_collect_kernel takes it from here
+    }
     if (done_cl == -2) {
         // ---- candidates that can still win: ambiguous ones, and the top level's within reach of the threshold --------
         for (int b = 0; b < nblk; ++b) {
@@ -257,6 +275,55 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
                                                             const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
                                                             int always_rescore) {
     select_body(st, sb, best_out, nskip, tile_counter, given, always_rescore, blockIdx.x, gridDim.x);
+}
+
+// Second half of the selection of a step with several blocks: every block whose record says it can hold a survivor scans
+// its own chunk; the last block to finish closes the list (one survivor, nothing ambiguous, no other shard: the winner).
+__global__ void __launch_bounds__(kSelThreads) select_collect_kernel(const __grid_constant__ DevStep st, const SelectBufs sb,
+                                                                    BestRec* __restrict__ best_out, const int* __restrict__ nskip,
+                                                                    unsigned* __restrict__ tile_counter, int given, int always_rescore) {
+    __shared__ int s_last;
+    __shared__ double s_scratch[kSelThreads / 32];
+    const SelState* state = reinterpret_cast<const SelState*>(sb.state);
+    if (!state->pending) return;  // select_kernel had the answer already (and has re-armed everything)
+    const int tid = threadIdx.x, Cs = st.n_local, hi = state->hi;
+    const double thr = state->thr;
+    const SelBlock* blocks = reinterpret_cast<const SelBlock*>(sb.blocks);
+    const SelBlock mine = blocks[blockIdx.x];
+    if (hi >= 0 && mine.rank_max == hi && mine.lower <= thr) {
+        const int bb = blockIdx.x * kSelChunk;
+        for (int k = 0; k < kSelPer; ++k) {
+            const int cl = bb + k * kSelThreads + tid;
+            if (cl >= Cs) continue;
+            const unsigned char m = st.ws_meta[cl];
+            if (m == SEL_SKIPPED || (m & SEL_AMB) || level_rank(m) != hi) continue;
+            if (order_cost(st.ws_cost[cl]) - (double)st.ws_bound[cl] <= thr) sb.list[atomicAdd(&sb.hdr[2], 1)] = cl;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&sb.counters[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int count = *reinterpret_cast<volatile int*>(&sb.hdr[2]);
+    const bool final_one = count == 1 && state->n_amb == 0 && !always_rescore;
+    if (final_one) {
+        const int cl = *reinterpret_cast<volatile int*>(&sb.list[0]);
+        const int index = dense_of(st, given != 0, cl);
+        const int li = list_index_of(st, nskip, given != 0, index, s_scratch);
+        if (tid == 0) write_best(best_out, (int)(st.ws_meta[cl] & 63), st.ws_cost[cl], index, state->n_scored, li);
+    }
+    if (tid == 0) {
+        sb.hdr[0] = final_one ? 0 : count;
+        sb.hdr[1] = state->n_scored;
+        sb.hdr[2] = 0;
+        sb.counters[0] = 0;
+        sb.counters[1] = 0;
+        if (tile_counter) *tile_counter = 0;
+    }
 }
 
 // scenario sweep: one block per scenario (at most kSelChunk candidates each)
@@ -656,6 +723,8 @@ cudaError_t launch_select(const DevStep& st, const SelectBufs& sb, BestRec* best
                           bool given, bool always_rescore, cudaStream_t stream) {
     const int nblk = (st.n_local + kSelChunk - 1) / kSelChunk;
     select_kernel<<<nblk > 0 ? nblk : 1, kSelThreads, 0, stream>>>(st, sb, best_out, nskip, tile_counter, given ? 1 : 0, always_rescore ? 1 : 0);
+    if (nblk > 1 && st.refine)
+        select_collect_kernel<<<nblk, kSelThreads, 0, stream>>>(st, sb, best_out, nskip, tile_counter, given ? 1 : 0, always_rescore ? 1 : 0);
     return cudaGetLastError();
 }
 
