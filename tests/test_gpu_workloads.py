@@ -154,4 +154,4 @@ def test_closed_loop_200_cycles_follow_the_oracle(weights):
             rtol = 1e-4 if name == "kappa_radpm" else 1e-6
             np.testing.assert_allclose(pl.trajectory[name], ref["traj"][f, row, :Tn], rtol=rtol, atol=1e-9, err_msg=f"cycle {k} {name}")
         ego = pl.ideal_tracking_state()
-    assert pl.trajectory["s_loc_m"][1] > 20.0  # it moved along the path
+    assert pl.trajectory["s_loc_m"][1] > 5.0  # it moved along the path (the ego-only weights brake to a stop)
