@@ -343,6 +343,18 @@ def run_gpu_arm(args, step, workload_cfg):
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         extras = latency_extras(ctx, torch)
+    if world > 1 and not args.no_sweep:
+        # cfg4 next to the sharded step: scenario i on rank i % N, no collective; aggregate = all scenarios / slowest rank
+        mine = sweep_extra(ctx, torch, rank, world)
+        t = torch.tensor([mine["seconds"], mine["device_ms"] * 1e-3, mine["seconds"] + mine["pack_seconds"]], device="cuda", dtype=torch.float64)
+        n = torch.tensor([float(mine["scenarios"]), float(mine["candidates"])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n)
+        extras["cfg4_scenario_sweep_sharded"] = {
+            "scenarios": int(n[0].item()), "ranks": world, "scenarios_per_sec": float(n[0].item() / t[0].item()),
+            "candidates_per_sec": float(n[1].item() / t[0].item()), "scenarios_per_sec_device_timed": float(n[0].item() / t[1].item()),
+            "scenarios_per_sec_incl_python_packing": float(n[0].item() / t[2].item()),
+            "timing": "max over ranks of the wall clock around the rank's etp_plan_batch calls", "workload": mine["workload"]}
 
     if rank == 0:
         line = {
@@ -478,6 +490,26 @@ def e2e_step(ctx, step, sharded, rank, world, bufs):
     return best
 
 
+def sweep_extra(ctx, torch, rank, world, n_scenarios=2000):
+    """cfg4 (BASELINE.json configs[3]): this rank's share of the 2000-scenario sweep through etp_plan_batch."""
+    from ethicaltrajectoryplanning_b200 import workloads
+    from ethicaltrajectoryplanning_b200.distributed import scenario_shard
+
+    ids = scenario_shard(n_scenarios, rank, world)
+    workloads.run_sweep_batched(ctx, ids[:64], chunk=64)  # warm-up
+    torch.cuda.synchronize()
+    ctx.enable_timing(True)
+    res, n_cand, t_pack, t_run = workloads.run_sweep_batched(ctx, ids, chunk=2048)
+    dev_ms = sum(ctx.stage_timing())
+    ctx.enable_timing(False)
+    return {"scenarios": len(ids), "candidates": n_cand, "seconds": t_run, "pack_seconds": t_pack, "device_ms": dev_ms,
+            "scenarios_per_sec": len(ids) / t_run, "candidates_per_sec": n_cand / t_run,
+            "scenarios_per_sec_device_timed": len(ids) / (dev_ms * 1e-3),
+            "scenarios_per_sec_incl_python_packing": len(ids) / (t_pack + t_run), "us_per_scenario": 1e6 * t_run / len(ids),
+            "workload": "planning.json grid (15x15, T=20), O~U{2..12}; etp_plan_batch: chunks of 512 scenarios, every stage of a "
+                        "chunk one launch, inputs of a chunk in one upload, arg-min only; wall clock around the calls"}
+
+
 def latency_extras(ctx, torch):
     """Single-step latency of the 10k-candidate configuration (BASELINE.json configs[1])."""
     from ethicaltrajectoryplanning_b200.synthetic import make_step
@@ -501,15 +533,18 @@ def latency_extras(ctx, torch):
         lat = np.array(lat[10:]) * 1e3
         out[name] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99))}
     ctx.enable_timing(True)
-    ks = []
+    ks, sel = [], []
     for i in range(30):
         flush.zero_()
         ctx.launch(s, bufs)
-        ks.append(ctx.timing()[1])
+        st3 = ctx.stage_timing()
+        ks.append(st3[1])
+        sel.append(st3[2])
     ctx.enable_timing(False)
     k = float(np.median(ks))
     bytes_ = step.n_dense * algorithmic_bytes_per_candidate(Tmax, ctx.O)
     out["kernel_ms"] = k
+    out["selection_ms"] = float(np.median(sel))
     out["candidates_per_sec_kernel"] = step.n_dense / (k * 1e-3)
     out["hbm_gbs_kernel"] = bytes_ / (k * 1e-3) / 1e9
     out["workload"] = "cfg2: 100x100 candidates, T=30, 8 obstacles; L2 flushed between steps (256 MiB write)"
@@ -578,14 +613,7 @@ def latency_extras(ctx, torch):
     # cfg4: evaluatefrenet-style sweep (one planning step per scenario, arg-min only), this GPU's share
     from ethicaltrajectoryplanning_b200 import workloads
 
-    ids = list(range(400))
-    workloads.run_sweep_batched(ctx, ids[:32])
-    res, n_cand, t_pack, t_run = workloads.run_sweep_batched(ctx, ids)
-    extras["cfg4_scenario_sweep"] = {
-        "scenarios": len(ids), "candidates": n_cand, "scenarios_per_sec": len(ids) / t_run, "candidates_per_sec": n_cand / t_run,
-        "scenarios_per_sec_incl_python_packing": len(ids) / (t_pack + t_run), "us_per_scenario": 1e6 * t_run / len(ids),
-        "workload": "planning.json grid (15x15, T=20), O~U{2..12}; etp_plan_batch (8 scenarios in flight), inputs uploaded per "
-                    "scenario, arg-min only"}
+    extras["cfg4_scenario_sweep"] = sweep_extra(ctx, torch, 0, 1)
     # cfg5: closed loop, replanning every 0.1 s with ideal tracking, 200 cycles per weight file
     loop = {}
     for grid in ("cfg1", "cfg2"):
@@ -618,6 +646,7 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=3.0, help="CPU work per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="N > 1: skip the scenario-sharded sweep (cfg4) after the step")
     args = ap.parse_args()
     claim_stdout()
 
