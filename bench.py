@@ -496,7 +496,7 @@ def sweep_extra(ctx, torch, rank, world, n_scenarios=2000):
     from ethicaltrajectoryplanning_b200.distributed import scenario_shard
 
     ids = scenario_shard(n_scenarios, rank, world)
-    workloads.run_sweep_batched(ctx, ids[:64], chunk=64)  # warm-up
+    workloads.run_sweep_batched(ctx, ids, chunk=2048)  # warm-up: the arenas of the sweep grow to their size here
     torch.cuda.synchronize()
     ctx.enable_timing(True)
     res, n_cand, t_pack, t_run = workloads.run_sweep_batched(ctx, ids, chunk=2048)

@@ -219,7 +219,11 @@ __device__ __forceinline__ R nine_rectangles(const Tab<R>& pr, const Rect& rect,
     for (int km = 0; km < 3; ++km) {
         const R sg = km == 0 ? (R)0 : (km == 1 ? (R)1 : (R)-1);
         const R ux = ddx - sg * ex, uy = ddy - sg * ey;  // ego centre - mean_km
+#ifdef ETP_UNROLL_JB
+#pragma unroll  // build variant: the three boxes of one mean as straight-line code (three copies of the rectangle body)
+#else
 #pragma unroll 1  // the rectangle body stays one small loop: unrolled, its nine copies thrash the instruction cache
+#endif
         for (int jb = 0; jb < 3; ++jb) {
             const R sb = jb == 0 ? (R)0 : (jb == 1 ? (R)1 : (R)-1);
             const R bx = ux + sb * ox, by = uy + sb * oy;  // box centre - mean
@@ -514,7 +518,8 @@ template <typename R> struct Phase2a {
 //   kFastEgo : every ego sample of the tile is wrap-free (Logits::coefs)
 //   kDense   : all 32 lanes carry live candidates of the same length, all kOB obstacles exist and their predictions
 //              cover the segment: no masks, no clamps
-template <typename R, int NT, bool kSym, bool kFastEgo, bool kProt, bool kDense>
+//   kPure    : (build variant -DETP_PROT_PURE) every obstacle of the group is protected: no per-obstacle class select
+template <typename R, int NT, bool kSym, bool kFastEgo, bool kProt, bool kDense, bool kPure = false>
 __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg) {
     using U = typename Enc<R>::U;
     using L = Logits<R, NT, kSym>;
@@ -534,7 +539,7 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
         off[k] = (typename std::conditional<kDense, unsigned, size_t>::type)((size_t)ok[k] * a.Cp);
         const Vec4<R> cr = ldg4<R>(a.C + ok[k]);
         n_pred[k] = valid[k] ? __ldg(a.st->pred_len + ok[k]) : 0;
-        prot[k] = cr.z != (R)0;
+        prot[k] = kPure ? true : (cr.z != (R)0);
         ke[k] = cr.x; ko[k] = cr.y;
         const R reach = (R)5.05 + (R)a.st->obs_const[ok[k] * OC_COUNT + OC_HALFLEN];
         far2[k] = reach * reach;
@@ -655,7 +660,7 @@ __device__ __forceinline__ void phase2a_item(const Phase2a<R>& a, int g, int seg
 // dispatch of one item to its specialisation
 template <typename R, int NT, bool kSym>
 __device__ __forceinline__ void phase2a_dispatch(const Phase2a<R>& a, int g, int seg, bool unprot, bool tile_fast,
-                                                 bool tile_full) {
+                                                 bool tile_full, bool pure) {
     // every obstacle of the group exists and is predicted over the whole segment?
     bool full = tile_full && !a.o_harm && (g + 1) * kOB <= a.O;
     if (full) {
@@ -667,6 +672,10 @@ __device__ __forceinline__ void phase2a_dispatch(const Phase2a<R>& a, int g, int
         if (full) phase2a_item<R, NT, kSym, false, false, true>(a, g, seg);
         else phase2a_item<R, NT, kSym, false, false, false>(a, g, seg);
     } else if (tile_fast) {
+#ifdef ETP_PROT_PURE
+        if (full && pure) phase2a_item<R, NT, kSym, true, true, true, true>(a, g, seg);
+        else
+#endif
         if (full) phase2a_item<R, NT, kSym, true, true, true>(a, g, seg);
         else phase2a_item<R, NT, kSym, true, true, false>(a, g, seg);
     } else {
@@ -1068,7 +1077,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 if (item >= n_items) break;
                 const int g = item % n_groups, seg = item / n_groups;
                 const bool unprot = g * kOB >= s_nprot;  // groups are cut from the class-sorted obstacle order
-                phase2a_dispatch<R, NT, kSym>(pa, g, seg, unprot, tile_fast, tile_full);
+                phase2a_dispatch<R, NT, kSym>(pa, g, seg, unprot, tile_fast, tile_full, (g + 1) * kOB <= s_nprot);
             }
             __syncthreads();  // (b2) queue complete
 
