@@ -203,3 +203,117 @@ def test_max_risk_level_and_maximin_gate_close_to_their_thresholds():
             finally:
                 ctx.close()
     assert checked >= 6
+
+
+def _near_tie_variants(base, gaps=(1e-8, 1e-10)):
+    """Steps derived from `base` whose runner-up is a relative gap behind / ahead of the oracle's winner (per-candidate cost
+    factors), with the expected dense index."""
+    from oracle import vec
+
+    ref = vec.score_dense(base)
+    lv, cost = ref["level"], ref["cost"][12]
+    live = lv != 255
+    top_level = 10 if (lv[live] == 10).any() else int(lv[live].max())
+    top = np.flatnonzero(lv == top_level)
+    a = int(top[np.argmin(cost[top])])
+    others = [int(c) for c in top if c != a and cost[c] > 0]
+    picks = ([c for c in others if c < a][-1:] + [c for c in others if c > a][:1])[:2]
+    out = []
+    for gap in gaps:
+        for b in picks:
+            for sign in (+1, -1):
+                step = copy.copy(base)
+                fl = np.full(base.n_dense, 1e3)
+                fl[a] = 1.0
+                fl[b] = cost[a] * (1.0 + sign * gap) / cost[b]
+                step.cost_factor_list = fl
+                want = vec.score_dense(step)["best"]
+                assert want["index"] == (a if sign > 0 else b)
+                out.append((step, want))
+    return out
+
+
+def test_near_ties_with_every_optional_stage_switched_on():
+    """The exact re-scoring reproduces everything that enters a candidate's cost and level: Mahalanobis probabilities,
+    road boundary harm and collision with the predicted boxes on the device, all harm models, risk-only weights below
+    level 10, jerk / travelled-distance terms."""
+    from ethicaltrajectoryplanning_b200.synthetic import make_step, road_boundary_triangles
+
+    bases = []
+    s = make_step("planning", seed=21, lateral_spread=2.0, nv=7, nd=9)
+    s.params = copy.deepcopy(s.params)
+    s.params["modes"]["fast_prob_mahalanobis"] = True
+    for p in s.predictions.values():
+        if not np.any(p["cov_list"]):
+            p["cov_list"][:, 0, 0] = p["cov_list"][:, 1, 1] = 0.1
+    bases.append(("mahalanobis", s))
+    s = make_step("planning", seed=22, lateral_spread=5.0, nv=7, nd=9)
+    s.road_boundary = (road_boundary_triangles(s.csp, half_width=2.5), "discrete")
+    s.params = copy.deepcopy(s.params)
+    s.params["modes"]["collision_check_device"] = "discrete"
+    bases.append(("boundary_and_collision", s))
+    for name, (ign, sym, red) in {"lr1s": (True, True, True), "lr12a": (False, False, False), "lr4a": (False, False, True)}.items():
+        s = make_step("planning", seed=23, lateral_spread=1.5, nv=7, nd=9)
+        s.params = copy.deepcopy(s.params)
+        s.params["modes"].update(ignore_angle=ign, sym_angle=sym, reduced_angle_areas=red)
+        bases.append((name, s))
+    s = make_step("planning", seed=24, lateral_spread=1.0, nv=7, nd=9)
+    s.params = copy.deepcopy(s.params)
+    s.params["modes"]["multiple_cost_functions"] = True
+    s.params["modes"]["max_acceptable_risk"] = 1e-9   # everything level 3: risk-only weights
+    s.params["weights"].update(lon_jerk=0.3, lat_jerk=0.2, travelled_dist=0.1)
+    bases.append(("multi_cost_level3", s))
+    s = make_step("planning", seed=25, nv=7, nd=9, weights="weights_ego.json")
+    s.params = copy.deepcopy(s.params)
+    s.params["weights"].update(lon_jerk=0.3, lat_jerk=0.2, travelled_dist=0.1)
+    bases.append(("ego_weights_jerk", s))
+    ctx = _ctx("fp32")
+    try:
+        n = 0
+        for name, base in bases:
+            for step, want in _near_tie_variants(base):
+                res = ctx.plan(step)
+                assert res.best["index"] == want["index"], (name, res.best, want)
+                assert res.best["level"] == want["level"], name
+                assert abs(res.best["cost"] - want["cost"]) <= 1e-9 * abs(want["cost"]) + 1e-15, (name, res.best["cost"], want["cost"])
+                n += 1
+        dbg = ctx.debug_counters()
+        assert n >= 40 and dbg["rescored"] >= n and dbg["bound_violations"] == 0, dbg
+    finally:
+        ctx.close()
+
+
+def test_near_ties_among_caller_provided_trajectories():
+    """etp_score_trajectories (arbitrary fp_list): duplicates and a 1e-10 runner-up are told apart like generated candidates."""
+    from ethicaltrajectoryplanning_b200 import dropin
+    from ethicaltrajectoryplanning_b200.synthetic import make_step
+    from oracle import port, vec
+
+    step = make_step("planning", seed=31, nv=5, nd=7)
+    fps = port.calc_frenet_trajectories(step.c_s, step.c_s_d, step.c_s_dd, step.c_d, step.c_d_d, step.c_d_dd, step.d_list,
+                                        step.t_list, step.v_list, step.dt, step.csp, step.v_thr)
+    ref = vec.score_dense(step)
+    live = np.flatnonzero(ref["level"] != 255)
+    cost = ref["cost"][12][live]
+    lv = ref["level"][live]
+    top = np.flatnonzero(lv == (10 if (lv == 10).any() else lv.max()))
+    a = int(top[np.argmin(cost[top])])
+    b = int([c for c in top if c != a][0])
+    ctx = _ctx("fp32")
+    try:
+        for sign in (+1, -1):
+            factor = np.full(len(fps), 1e3)
+            factor[a] = 1.0
+            factor[b] = cost[a] * (1.0 + sign * 1e-10) / cost[b]
+            r = dropin.score_trajectories(fps, step.predictions, step.obstacle_types, step.vehicle, step.params, step.mode, ctx=ctx,
+                                          velocity_cost_mode=step.velocity_cost_mode, velocity_target=step.velocity_target,
+                                          cost_factor=factor)
+            assert r.best["index"] == (a if sign > 0 else b), (sign, r.best, a, b)
+        # the winner twice: the first of the two identical trajectories is selected
+        dup = list(fps) + [fps[a]]
+        r = dropin.score_trajectories(dup, step.predictions, step.obstacle_types, step.vehicle, step.params, step.mode, ctx=ctx,
+                                      velocity_cost_mode=step.velocity_cost_mode, velocity_target=step.velocity_target)
+        assert r.best["index"] == a and r.cost[12][a] == r.cost[12][len(fps)]
+        assert ctx.debug_counters()["bound_violations"] == 0
+    finally:
+        ctx.close()
