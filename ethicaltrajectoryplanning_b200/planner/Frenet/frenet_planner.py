@@ -110,15 +110,21 @@ class FrenetPlanner:
             # assign_responsibility_by_action_space (responsibility.py:57-89) on the device, straight into the packed tile
             # shape, initial state and class of an obstacle do not change during a scenario: looked up once per id
             static = self.__dict__.setdefault("_obstacle_static", {})
-            shapes, ori0, vel0, types = {}, {}, {}, {}
-            for oid in predictions:
-                st = static.get(oid)
-                if st is None:
-                    ob = self.scenario.obstacle_by_id(oid)
-                    st = static[oid] = ((ob.obstacle_shape.length, ob.obstacle_shape.width), ob.initial_state.orientation,
-                                        ob.initial_state.velocity,
-                                        dropin.obstacle_type_names(self.scenario, {oid: None}, self.obstacle_types)[oid])
-                shapes[oid], ori0[oid], vel0[oid], types[oid] = st
+            prev = self.__dict__.get("_static_dicts")
+            if prev is not None and prev[0] == tuple(predictions):
+                # the same obstacles as in the previous cycle: the very same description dicts (the context recognises them)
+                _, shapes, ori0, vel0, types = prev
+            else:
+                shapes, ori0, vel0, types = {}, {}, {}, {}
+                for oid in predictions:
+                    st = static.get(oid)
+                    if st is None:
+                        ob = self.scenario.obstacle_by_id(oid)
+                        st = static[oid] = ((ob.obstacle_shape.length, ob.obstacle_shape.width), ob.initial_state.orientation,
+                                            ob.initial_state.velocity,
+                                            dropin.obstacle_type_names(self.scenario, {oid: None}, self.obstacle_types)[oid])
+                    shapes[oid], ori0[oid], vel0[oid], types[oid] = st
+                self._static_dicts = (tuple(predictions), shapes, ori0, vel0, types)
             self._resident_types = types
             self._resident_static = (shapes, ori0, vel0)  # what the enrichment on the device was given (tests replay it on the host)
             self.ctx.ensure_params(self.params_dict, self.p, self.mode)

@@ -385,6 +385,23 @@ class ScoringContext:
         margins and the action-space responsibility flag are derived on the device (prediction_helpers.py:75-135,
         responsibility.py:57-89) and the obstacle tile is packed from them.  ``shapes[id] = (length, width)`` of the raw
         obstacle; empty predictions are dropped like the reference does (:98-100)."""
+        # closed loop: the same obstacles with the same static description (the caller hands over the very same dict objects,
+        # kept alive here) and equally long predictions as in the previous cycle -> only positions, covariances and the ego
+        # pose change; the struct and the static arrays of the previous cycle are used again
+        fast = getattr(self, "_raw_fast", None)
+        if (fast is not None and masses is None and fast["refs"][0] is shapes and fast["refs"][1] is init_orientation
+                and fast["refs"][2] is init_velocity and fast["refs"][3] is obstacle_types and fast["dt"] == dt
+                and fast["margins"] == (safety_margin_length, safety_margin_width) and tuple(predictions) == fast["oids"]):
+            vals = list(predictions.values())
+            Tp = fast["Tp"]
+            if all(len(p["pos_list"]) == Tp for p in vals):
+                np.stack([p["pos_list"] for p in vals], out=fast["pos"].reshape(fast["pos_shape"]))
+                np.stack([p["cov_list"] for p in vals], out=fast["cov"].reshape(fast["cov_shape"]))
+                r = fast["struct"]
+                r.ego_x, r.ego_y, r.ego_orientation = float(ego_position[0]), float(ego_position[1]), float(ego_orientation)
+                self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
+                return
+        self._raw_fast = None
         oids = [oid for oid in predictions if len(predictions[oid]["pos_list"]) > 0]
         O = len(oids)
         lens = np.array([len(predictions[o]["pos_list"]) for o in oids], dtype=np.int32)
@@ -435,6 +452,12 @@ class ScoringContext:
         self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
         self.obstacle_ids, self.O, self.has_pred = oids, O, True
         self._raw_shape = (O, Tp, lens)
+        if O and masses is None and int(lens.min()) == Tp and len(oids) == len(predictions):
+            p0 = predictions[oids[0]]
+            self._raw_fast = dict(refs=(shapes, init_orientation, init_velocity, obstacle_types), dt=dt,
+                                  margins=(safety_margin_length, safety_margin_width), oids=tuple(oids), Tp=Tp, pos=pos, cov=cov,
+                                  pos_shape=(O,) + np.shape(p0["pos_list"]), cov_shape=(O,) + np.shape(p0["cov_list"]), struct=r,
+                                  keep=(lens, length, width, ori0, vel0, mass, prot))
 
     def enriched(self, predictions):
         """Read the derived arrays of the last ``set_raw_predictions`` back into the prediction dict (what the reference's
@@ -494,7 +517,14 @@ class ScoringContext:
         v = np.ascontiguousarray(step.v_list, dtype=np.float64)
         t = np.ascontiguousarray(step.t_list, dtype=np.float64)
         d = np.ascontiguousarray(step.d_list, dtype=np.float64)
-        n = np.ascontiguousarray([len(np.arange(0.0, tT, step.dt)) for tT in t], dtype=np.int32)
+        # samples per horizon, len(np.arange(0, tT, dt)) (frenet_functions.py:267): remembered per (horizons, dt)
+        nkey = (t.tobytes(), step.dt)
+        cache = self.__dict__.setdefault("_nsamp_cache", {}) if isinstance(self, ScoringContext) else {}
+        n = cache.get(nkey)
+        if n is None:
+            n = np.ascontiguousarray([len(np.arange(0.0, tT, step.dt)) for tT in t], dtype=np.int32)
+            if len(cache) < 64:
+                cache[nkey] = n
         s = _abi.Step()
         s.c_s, s.c_s_d, s.c_s_dd = step.c_s, step.c_s_d, step.c_s_dd
         s.c_d, s.c_d_d, s.c_d_dd = step.c_d, step.c_d_d, step.c_d_dd
