@@ -498,10 +498,17 @@ def sweep_extra(ctx, torch, rank, world, n_scenarios=2000):
     ids = scenario_shard(n_scenarios, rank, world)
     workloads.run_sweep_batched(ctx, ids, chunk=2048)  # warm-up: the arenas of the sweep grow to their size here
     torch.cuda.synchronize()
-    ctx.enable_timing(True)
-    res, n_cand, t_pack, t_run = workloads.run_sweep_batched(ctx, ids, chunk=2048)
-    dev_ms = sum(ctx.stage_timing())
-    ctx.enable_timing(False)
+    import gc
+
+    gc.collect()
+    gc.disable()  # a cyclic collection in the middle of 2000 result dicts is not part of the sweep
+    try:
+        ctx.enable_timing(True)
+        res, n_cand, t_pack, t_run = workloads.run_sweep_batched(ctx, ids, chunk=2048)
+        dev_ms = sum(ctx.stage_timing())
+        ctx.enable_timing(False)
+    finally:
+        gc.enable()
     return {"scenarios": len(ids), "candidates": n_cand, "seconds": t_run, "pack_seconds": t_pack, "device_ms": dev_ms,
             "scenarios_per_sec": len(ids) / t_run, "candidates_per_sec": n_cand / t_run,
             "scenarios_per_sec_device_timed": len(ids) / (dev_ms * 1e-3),

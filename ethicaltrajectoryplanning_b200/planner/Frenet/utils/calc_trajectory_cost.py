@@ -125,6 +125,11 @@ def build_cost_dict(traj, c, params, validity_level, predictions):
         traj.risk_dict = {"bayes": c[COST["bayes"]], "equality": c[COST["equality"]], "maximin": c[COST["maximin"]],
                           "responsibility": c[COST["responsibility"]], "ego": c[COST["ego"]],
                           "total": c[COST["risk_cost"]]}
+        if len(predictions) == 0:
+            # no obstacle: the principles return the integer 0 (risk_costs.py:145-146,173-174,199-200,222-223; the
+            # responsibility loop never runs, :250-253) and the log line prints them as such
+            for key in ("bayes", "equality", "maximin", "responsibility", "ego"):
+                traj.risk_dict[key] = 0
         cost_dict["risk_cost"] = traj.risk_dict["total"]
     else:
         traj.risk_dict = {}
