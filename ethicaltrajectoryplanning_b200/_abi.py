@@ -154,6 +154,10 @@ class Scenario(C.Structure):
     ]
 
 
+class Cycle(C.Structure):
+    _fields_ = [("raw", C.POINTER(RawPredictions)), ("obstacles", C.POINTER(Obstacles)), ("step", C.POINTER(Step))]
+
+
 class Best(C.Structure):
     _fields_ = [
         ("key_hi", C.c_uint64), ("key_lo", C.c_uint64), ("cost", C.c_double),
@@ -178,6 +182,7 @@ SYMBOLS = {
     "etp_score_trajectories": (C.c_int, [C.c_void_p, C.POINTER(Trajectories), C.POINTER(Out)]),
     "etp_principle_costs": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, C.c_double, C.c_double, C.c_double, _dp]),
     "etp_plan_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Scenario), C.c_int, C.POINTER(Best)]),
+    "etp_plan_cycle": (C.c_int, [C.c_void_p, C.POINTER(Cycle), C.c_int, C.POINTER(Best), _dp, _ip]),
     "etp_tmax": (C.c_int, [C.POINTER(Step)]),
     "etp_get_best": (C.c_int, [C.c_void_p, C.POINTER(Best)]),
     "etp_get_trajectory": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),

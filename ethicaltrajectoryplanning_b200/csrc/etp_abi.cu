@@ -95,6 +95,17 @@ struct etp_ctx {
     DevBuf counters, best_dev, traj_dev, traj_n, given, given_T, prin;
     // selection (etp_select.cu): per-candidate workspace of the fused kernel, survivors of select_kernel, their exact keys
     DevBuf ws_cost, ws_bound, ws_meta, ws_bd, ws_gf, sel_blocks, sel_list, sel_res, sel_small;
+    // planning cycle (etp_plan_cycle): host copy of the spline, a version of everything the captured graph bakes in, the
+    // cycle's arena / pinned images, the captured launch sequence and the shapes it was captured for
+    std::vector<double> sp_knots, sp_cx, sp_cy;
+    unsigned long long config_version = 0;
+    DevBuf cyc_dev;
+    PinnedBuf cyc_in, cyc_out;
+    cudaGraph_t cyc_graph = nullptr;
+    cudaGraphExec_t cyc_exec = nullptr;
+    std::vector<long long> cyc_key, cyc_seen;
+    bool no_graph = false;
+    unsigned long long graph_launches = 0;
     // what crossed the bus and what was launched since the context was created (etp_debug_counters)
     unsigned long long h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     bool refine_off = false;  // ETP_NO_REFINE=1: fp32 selection as it comes out of the fused kernel (kernel experiments)
@@ -260,6 +271,8 @@ int etp_create(etp_ctx** out, int device) {
     {
         const char* e = getenv("ETP_NO_REFINE");
         c->refine_off = e && e[0] == '1';
+        e = getenv("ETP_NO_GRAPH");
+        c->no_graph = e && e[0] == '1';
     }
     if (!ok) { etp_destroy(c); return ETP_ERR_CUDA; }
     *out = c;
@@ -274,6 +287,11 @@ int etp_destroy(etp_ctx* c) {
     c->batch_host.release();
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     c->batch_dev.release();
+    c->cyc_dev.release();
+    c->cyc_in.release();
+    c->cyc_out.release();
+    if (c->cyc_exec) cudaGraphExecDestroy(c->cyc_exec);
+    if (c->cyc_graph) cudaGraphDestroy(c->cyc_graph);
     for (int i = 0; i < 2; ++i) {
         c->batch_in[i].release();
         if (c->batch_ev[i]) cudaEventDestroy(c->batch_ev[i]);
@@ -351,6 +369,7 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
     else if (d.coef_pos[d.n_thr] == d.coef_neg[d.n_thr]) d.wrapfree_yaw = 3.14159265358979323846 - d.thr[d.n_thr - 1] - 1e-9;
     else d.wrapfree_yaw = -1.0;
     c->have_params = true;
+    c->config_version++;
     return ETP_OK;
 }
 
@@ -368,6 +387,10 @@ int etp_set_spline(etp_ctx* c, const double* knots, const double* coef_x, const 
     if ((r = stage_to_device(c, c->cx.p, coef_x, sizeof(double) * 4 * n_seg))) return r;
     if ((r = stage_to_device(c, c->cy.p, coef_y, sizeof(double) * 4 * n_seg))) return r;
     c->nseg = n_seg;
+    c->sp_knots.assign(knots, knots + n_seg + 1);
+    c->sp_cx.assign(coef_x, coef_x + 4 * (size_t)n_seg);
+    c->sp_cy.assign(coef_y, coef_y + 4 * (size_t)n_seg);
+    c->config_version++;
     c->spline_pts.clear();
     for (int i = 0; i < n_seg; ++i) {
         // knot position and the reach of the segment (|b| ds bounds the excursion to first order, doubled for slack)
@@ -385,6 +408,7 @@ int etp_set_road_boundary(etp_ctx* c, const etp_road_boundary* b) {
     if (b->check < ETP_COLLISION_HOST || b->check > ETP_COLLISION_SWEPT) ETP_FAIL(c, ETP_ERR_INVALID, "road boundary check mode");
     if (b->n_triangles < 0 || (b->n_triangles > 0 && !b->triangles)) ETP_FAIL(c, ETP_ERR_INVALID, "road boundary triangles missing");
     c->boundary = DevBoundary{};
+    c->config_version++;
     if (b->n_triangles == 0 || b->check == ETP_COLLISION_HOST) return ETP_OK;
     const int n = b->n_triangles;
     const double* T = b->triangles;
@@ -1229,6 +1253,245 @@ int plan_chunk_fused(etp_ctx* c, int n, const etp_scenario* sc, int precision, B
     return ETP_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// etp_plan_cycle: one closed-loop cycle as "a sweep of one scenario" whose launch sequence is a captured graph
+// ---------------------------------------------------------------------------------------------
+bool cycle_fusable(const etp_ctx* c, const etp_cycle& cy) {
+    if (!c->have_spline || !cy.step) return false;
+    const etp_step& p = *cy.step;
+    if (p.ext_level || p.bd_harm || p.cost_factor_list || p.goal) return false;
+    if (p.nv < 1 || p.nt < 1 || p.nd < 1 || !p.v_list || !p.t_list || !p.d_list || !p.n_samples) return false;
+    const long long dense = (long long)p.nv * p.nt * p.nd;
+    if (dense > select_chunk() || p.c_begin != 0 || p.c_end != dense || p.shard_count > 1) return false;
+    for (int i = 0; i < p.nt; ++i)
+        if (p.n_samples[i] < 2 || p.n_samples[i] > 256) return false;
+    if (cy.raw) {
+        const etp_raw_predictions& o = *cy.raw;
+        if (o.n_obstacles < 1 || o.max_pred < 1 || !o.pred_len || !o.pos || !o.cov || !o.length || !o.width || !o.init_orientation ||
+            !o.init_velocity || !o.mass || !o.is_protected)
+            return false;
+        for (int i = 0; i < o.n_obstacles; ++i)
+            if (o.pred_len[i] < 1 || o.pred_len[i] > o.max_pred || (o.is_protected[i] != 0 && o.is_protected[i] != 1)) return false;
+    } else {
+        const etp_obstacles& o = *cy.obstacles;
+        if (o.n_obstacles < 0 || (o.n_obstacles > 0 && (o.max_pred < 1 || !o.pred_len || !o.pos || !o.cov || !o.yaw || !o.vel || !o.length ||
+                                                        !o.width || !o.mass || !o.is_protected || !o.responsibility)))
+            return false;
+        for (int i = 0; i < o.n_obstacles; ++i)
+            if (o.pred_len[i] < 1 || o.pred_len[i] > o.max_pred || (o.is_protected[i] != 0 && o.is_protected[i] != 1)) return false;
+    }
+    return true;
+}
+
+int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* best, double* fields, int* n_samples) {
+    const etp_step& p = *cy.step;
+    const bool raw = cy.raw != nullptr;
+    const int O = raw ? cy.raw->n_obstacles : cy.obstacles->n_obstacles;
+    const int Tp = O > 0 ? (raw ? cy.raw->max_pred : cy.obstacles->max_pred) : 0;
+    const int* plen = raw ? cy.raw->pred_len : cy.obstacles->pred_len;
+    const double* pos = raw ? cy.raw->pos : cy.obstacles->pos;
+    const double* cov = raw ? cy.raw->cov : cy.obstacles->cov;
+    const int Tmax = etp_tmax(&p), n_prof = p.nv * p.nt, Cs = n_prof * p.nd, tiles = (Cs + 31) / 32;
+    const size_t m = (size_t)O * Tp;
+    const size_t smem = score_smem_bytes(precision, Tmax, O);
+    if (smem > (size_t)c->smem_optin) ETP_FAIL(c, ETP_ERR_UNSUPPORTED, "the step needs %zu bytes of shared memory per CTA", smem);
+    const bool refine = precision == ETP_PRECISION_FP32 && !c->refine_off;
+    // ---- layout ----
+    Arena in, sc;
+    const size_t o_step = in.take(sizeof(DevStep)), o_pack = in.take(sizeof(PackArgs)), o_sb = in.take(sizeof(SelectBufs));
+    const size_t o_enr = in.take(sizeof(EnrichArgs)), o_first = in.take(sizeof(int)), o_tscn = in.take(sizeof(int) * tiles);
+    const size_t o_v = in.take(sizeof(double) * p.nv), o_t = in.take(sizeof(double) * p.nt), o_d = in.take(sizeof(double) * p.nd);
+    const size_t o_ns = in.take(sizeof(int) * p.nt);
+    const size_t o_pos = in.take(sizeof(double) * 2 * m), o_cov = in.take(sizeof(double) * 4 * m), o_plen = in.take(sizeof(int) * O);
+    const size_t o_mass = in.take(sizeof(double) * O), o_prot = in.take(sizeof(int) * O);
+    // raw: shape without margins and initial state; enriched: orientation, velocity, shape with margins, responsibility
+    const size_t o_a = in.take(sizeof(double) * (raw ? O : m)), o_b = in.take(sizeof(double) * (raw ? O : m));
+    const size_t o_c = in.take(sizeof(double) * O), o_e = in.take(sizeof(double) * O), o_resp_in = in.take(sizeof(int) * O);
+    const size_t o_small = in.take(64);
+    const size_t in_bytes = in.off;
+    const size_t s_yaw = sc.take(sizeof(double) * m), s_vel = sc.take(sizeof(double) * m), s_len = sc.take(sizeof(double) * O);
+    const size_t s_wid = sc.take(sizeof(double) * O), s_resp = sc.take(sizeof(int) * O);
+    const size_t s_tile = sc.take(Tile<double>::bytes(O > 0 ? O : 1, Tp > 0 ? Tp : 1)), s_oconst = sc.take(sizeof(double) * OC_COUNT * (O > 0 ? O : 1));
+    const size_t s_prof = sc.take(sizeof(double) * PF_COUNT * Tmax * (size_t)n_prof), s_meta = sc.take(sizeof(double) * PM_COUNT * (size_t)n_prof);
+    const size_t s_nskip = sc.take(sizeof(int) * (size_t)n_prof);
+    const size_t s_wc = sc.take(sizeof(double) * Cs), s_wb = sc.take(sizeof(float) * Cs), s_wm = sc.take(Cs), s_wbd = sc.take(sizeof(double) * Cs);
+    const size_t s_wgf = sc.take(Cs), s_blocks = sc.take(select_blocks_bytes(Cs)), s_list = sc.take(sizeof(int) * Cs);
+    const size_t s_res = sc.take(rescore_rec_bytes(Cs)), s_best = sc.take(sizeof(BestRec));
+    const size_t combo_bytes = sizeof(BestRec) + 8 + sizeof(double) * ETP_NUM_FIELDS * Tmax;
+    const size_t s_combo = sc.take(combo_bytes);
+    ETP_CUDA(c, c->cyc_dev.reserve(in_bytes + sc.off));
+    if (c->cyc_in.cap < in_bytes) ETP_CUDA(c, c->cyc_in.reserve(in_bytes + in_bytes / 4));
+    if (c->cyc_out.cap < combo_bytes) ETP_CUDA(c, c->cyc_out.reserve(combo_bytes + 256));
+    unsigned char* dev = c->cyc_dev.as<unsigned char>();
+    unsigned char* sdev = dev + in_bytes;
+    unsigned char* h = c->cyc_in.p;
+    // ---- fill the input image ----
+    memcpy(h + o_v, p.v_list, sizeof(double) * p.nv);
+    memcpy(h + o_t, p.t_list, sizeof(double) * p.nt);
+    memcpy(h + o_d, p.d_list, sizeof(double) * p.nd);
+    memcpy(h + o_ns, p.n_samples, sizeof(int) * p.nt);
+    if (O > 0) {
+        memcpy(h + o_pos, pos, sizeof(double) * 2 * m);
+        memcpy(h + o_cov, cov, sizeof(double) * 4 * m);
+        memcpy(h + o_plen, plen, sizeof(int) * O);
+        if (raw) {
+            memcpy(h + o_mass, cy.raw->mass, sizeof(double) * O); memcpy(h + o_prot, cy.raw->is_protected, sizeof(int) * O);
+            memcpy(h + o_a, cy.raw->length, sizeof(double) * O); memcpy(h + o_b, cy.raw->width, sizeof(double) * O);
+            memcpy(h + o_c, cy.raw->init_orientation, sizeof(double) * O); memcpy(h + o_e, cy.raw->init_velocity, sizeof(double) * O);
+        } else {
+            const etp_obstacles& o = *cy.obstacles;
+            memcpy(h + o_mass, o.mass, sizeof(double) * O); memcpy(h + o_prot, o.is_protected, sizeof(int) * O);
+            memcpy(h + o_a, o.yaw, sizeof(double) * m); memcpy(h + o_b, o.vel, sizeof(double) * m);
+            memcpy(h + o_c, o.length, sizeof(double) * O); memcpy(h + o_e, o.width, sizeof(double) * O);
+            memcpy(h + o_resp_in, o.responsibility, sizeof(int) * O);
+        }
+    }
+    memset(h + o_small, 0, 64);
+    double ox, oy, m_abs = 0.0, dmax = 0.0;
+    if (O > 0) {
+        ox = pos[0]; oy = pos[1];
+        double bx0 = ox, bx1 = ox, by0 = oy, by1 = oy;
+        for (int k = 0; k < O; ++k)
+            for (int t = 0; t < plen[k]; ++t) {
+                const double* q = pos + ((size_t)k * Tp + t) * 2;
+                bx0 = std::fmin(bx0, q[0]); bx1 = std::fmax(bx1, q[0]); by0 = std::fmin(by0, q[1]); by1 = std::fmax(by1, q[1]);
+            }
+        m_abs = std::fmax(std::fmax(std::fabs(bx0 - ox), std::fabs(bx1 - ox)), std::fmax(std::fabs(by0 - oy), std::fabs(by1 - oy)));
+    } else {
+        ox = c->spline_pts.empty() ? 0.0 : c->spline_pts[0];
+        oy = c->spline_pts.empty() ? 0.0 : c->spline_pts[1];
+    }
+    for (size_t i = 0; i + 2 < c->spline_pts.size(); i += 3)
+        m_abs = std::fmax(m_abs, std::fmax(std::fabs(c->spline_pts[i] - ox), std::fabs(c->spline_pts[i + 1] - oy)) + c->spline_pts[i + 2]);
+    for (int k = 0; k < p.nd; ++k) dmax = std::fmax(dmax, std::fabs(p.d_list[k]));
+    DevStep st{};
+    st.c_s = p.c_s; st.c_s_d = p.c_s_d; st.c_s_dd = p.c_s_dd; st.c_d = p.c_d; st.c_d_d = p.c_d_d; st.c_d_dd = p.c_d_dd;
+    st.dt = p.dt; st.v_thr = p.v_thr;
+    st.v_list = reinterpret_cast<const double*>(dev + o_v); st.t_list = reinterpret_cast<const double*>(dev + o_t);
+    st.d_list = reinterpret_cast<const double*>(dev + o_d); st.nsamp = reinterpret_cast<const int*>(dev + o_ns);
+    st.nv = p.nv; st.nt = p.nt; st.nd = p.nd; st.Tmax = Tmax;
+    st.c_begin = 0; st.c_end = Cs; st.p_begin = 0; st.p_end = n_prof; st.shard_index = 0; st.shard_count = 1; st.n_local = Cs;
+    st.vel_mode = p.velocity_cost_mode; st.vel_target = p.velocity_target; st.factor = p.cost_factor;
+    st.eps_pos = 2.4e-7 * (m_abs + dmax + 16.0);
+    st.origin_x = ox; st.origin_y = oy;
+    st.boundary = c->boundary;
+    st.boundary.lr1s_const = c->pr.lr1s_const; st.boundary.lr1s_speed = c->pr.lr1s_speed;
+    st.boundary.off_x = ox - st.boundary.x0; st.boundary.off_y = oy - st.boundary.y0;
+    st.knots = c->knots.as<double>(); st.cx = c->cx.as<double>(); st.cy = c->cy.as<double>(); st.nseg = c->nseg;
+    st.prof = reinterpret_cast<double*>(sdev + s_prof); st.prof_meta = reinterpret_cast<double*>(sdev + s_meta);
+    st.nskip = reinterpret_cast<int*>(sdev + s_nskip);
+    st.has_pred = 1; st.O = O; st.Tp = Tp;
+    st.obs = sdev + s_tile; st.obs_const = reinterpret_cast<const double*>(sdev + s_oconst);
+    st.pred_len = reinterpret_cast<const int*>(dev + o_plen);
+    const double* d_yaw = raw ? reinterpret_cast<const double*>(sdev + s_yaw) : reinterpret_cast<const double*>(dev + o_a);
+    const double* d_vel = raw ? reinterpret_cast<const double*>(sdev + s_vel) : reinterpret_cast<const double*>(dev + o_b);
+    const double* d_len = raw ? reinterpret_cast<const double*>(sdev + s_len) : reinterpret_cast<const double*>(dev + o_c);
+    const double* d_wid = raw ? reinterpret_cast<const double*>(sdev + s_wid) : reinterpret_cast<const double*>(dev + o_e);
+    const int* d_resp = raw ? reinterpret_cast<const int*>(sdev + s_resp) : reinterpret_cast<const int*>(dev + o_resp_in);
+    st.raw_pos = reinterpret_cast<const double*>(dev + o_pos); st.raw_yaw = d_yaw;
+    st.raw_cov = reinterpret_cast<const double*>(dev + o_cov); st.raw_vel = d_vel;
+    st.ws_cost = reinterpret_cast<double*>(sdev + s_wc); st.ws_bound = reinterpret_cast<float*>(sdev + s_wb);
+    st.ws_meta = sdev + s_wm; st.ws_bd = reinterpret_cast<double*>(sdev + s_wbd); st.ws_gf = sdev + s_wgf;
+    st.refine = refine ? 1 : 0;
+    memcpy(h + o_step, &st, sizeof(st));
+    const PackArgs pk{O, Tp, st.pred_len, st.raw_pos, st.raw_cov, d_yaw, d_vel, d_len, d_wid, reinterpret_cast<const double*>(dev + o_mass),
+                      reinterpret_cast<const int*>(dev + o_prot), d_resp, c->pr.veh_m, ox, oy, sdev + s_tile,
+                      reinterpret_cast<double*>(sdev + s_oconst)};
+    memcpy(h + o_pack, &pk, sizeof(pk));
+    if (raw) {
+        const etp_raw_predictions& o = *cy.raw;
+        const EnrichArgs ea{O, Tp, st.pred_len, st.raw_pos, reinterpret_cast<const double*>(dev + o_a), reinterpret_cast<const double*>(dev + o_b),
+                            reinterpret_cast<const double*>(dev + o_c), reinterpret_cast<const double*>(dev + o_e), o.dt,
+                            o.safety_margin_length, o.safety_margin_width, o.ego_x, o.ego_y, o.ego_orientation,
+                            (c->pr.relaxed & ETP_RELAX_Q9_VIEW_CONE) ? 1 : 0, reinterpret_cast<double*>(sdev + s_yaw),
+                            reinterpret_cast<double*>(sdev + s_vel), reinterpret_cast<double*>(sdev + s_len),
+                            reinterpret_cast<double*>(sdev + s_wid), reinterpret_cast<int*>(sdev + s_resp)};
+        memcpy(h + o_enr, &ea, sizeof(ea));
+    }
+    SelectBufs sb;
+    sb.blocks = sdev + s_blocks; sb.list = reinterpret_cast<int*>(sdev + s_list); sb.res = sdev + s_res;
+    sb.hdr = reinterpret_cast<int*>(dev + o_small); sb.counters = reinterpret_cast<unsigned*>(dev + o_small + 16);
+    sb.stats = select_bufs(c).stats; sb.state = nullptr;
+    memcpy(h + o_sb, &sb, sizeof(sb));
+    *reinterpret_cast<int*>(h + o_first) = 0;
+    for (int k = 0; k < tiles; ++k) reinterpret_cast<int*>(h + o_tscn)[k] = 0;
+
+    // ---- the launch sequence: replayed from the captured graph when nothing it bakes in has changed ----
+    const DevStep* d_step = reinterpret_cast<const DevStep*>(dev + o_step);
+    const SelectBufs* d_sb = reinterpret_cast<const SelectBufs*>(dev + o_sb);
+    BestRec* d_best = reinterpret_cast<BestRec*>(sdev + s_best);
+    unsigned char* d_combo = sdev + s_combo;
+    const int n_launch = 5 + (raw && O > 0 ? 1 : 0) + (refine ? 1 : 0);
+    const bool timed = c->timing;  // CUDA-event timing of the stages (etp_get_stage_timing): launched one by one then
+    auto enqueue = [&]() -> int {
+        ETP_CUDA(c, cudaMemcpyAsync(dev, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (raw) ETP_CUDA(c, launch_enrich_args(reinterpret_cast<const EnrichArgs*>(dev + o_enr), O, Tp, c->stream));
+        ETP_CUDA(c, launch_pack_obstacles_batch(precision, reinterpret_cast<const PackArgs*>(dev + o_pack), 1, O * Tp, c->stream));
+        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        ETP_CUDA(c, launch_profiles_batch(d_step, c->pr, 1, n_prof, Tmax, c->stream));
+        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        const BatchArgs ba{d_step, reinterpret_cast<const int*>(dev + o_tscn), reinterpret_cast<const int*>(dev + o_first), tiles, 1};
+        ETP_CUDA(c, launch_score(precision, DevStep{}, c->pr, DevOut{}, c->counters.as<unsigned>(), c->num_sms, &c->last_grid, c->stream, &ba, smem));
+        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+        ETP_CUDA(c, launch_select_batch(d_step, d_sb, d_best, c->counters.as<unsigned>() + 1, 1, c->stream));
+        if (refine) ETP_CUDA(c, launch_rescore_batch(d_step, c->pr, d_sb, d_best, 1, Tmax, O, c->stream));
+        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+        ETP_CUDA(c, launch_best_trajectory_steps(d_step, d_best, d_combo, c->stream));
+        ETP_CUDA(c, cudaMemcpyAsync(c->cyc_out.p, d_combo, combo_bytes, cudaMemcpyDeviceToHost, c->stream));
+        return ETP_OK;
+    };
+    const std::vector<long long> key = {precision, raw ? 1 : 0, O, Tp, p.nv, p.nt, p.nd, Tmax, (long long)in_bytes, (long long)(size_t)dev,
+                                        (long long)(size_t)h, (long long)(size_t)c->cyc_out.p, (long long)c->config_version, refine ? 1 : 0,
+                                        (long long)(size_t)c->stream, (long long)(size_t)c->knots.p};
+    int r = ETP_OK;
+    if (timed) {
+        if ((r = enqueue())) return r;
+    } else if (!c->no_graph && c->cyc_exec && key == c->cyc_key) {
+        ETP_CUDA(c, cudaGraphLaunch(c->cyc_exec, c->stream));
+        c->graph_launches++;
+    } else if (!c->no_graph && key == c->cyc_seen) {
+        // second cycle of this shape: capture what the first one launched directly (every one-time runtime query is done)
+        if (c->cyc_exec) { cudaGraphExecDestroy(c->cyc_exec); c->cyc_exec = nullptr; }
+        if (c->cyc_graph) { cudaGraphDestroy(c->cyc_graph); c->cyc_graph = nullptr; }
+        ETP_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        r = enqueue();
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (r != ETP_OK || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            if (r == ETP_OK) ETP_FAIL(c, ETP_ERR_CUDA, "graph capture of the planning cycle failed: %s", cudaGetErrorString(e));
+            return r;
+        }
+        c->cyc_graph = g;
+        ETP_CUDA(c, cudaGraphInstantiate(&c->cyc_exec, g, 0));
+        c->cyc_key = key;
+        ETP_CUDA(c, cudaGraphLaunch(c->cyc_exec, c->stream));
+        c->graph_launches++;
+    } else {
+        c->cyc_seen = key;
+        if ((r = enqueue())) return r;
+    }
+    c->launches += n_launch;
+    c->h2d_bytes += in_bytes;
+    c->d2h_bytes += combo_bytes;
+    ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    // the context now holds this step like after etp_plan_step (etp_get_trajectory etc. keep working on it)
+    c->st = st;
+    c->precision = precision;
+    c->has_pred = 1; c->O = O; c->Tp = Tp;
+    c->have_step = true;
+    c->last_given = false;
+    const BestRec* b = reinterpret_cast<const BestRec*>(c->cyc_out.p);
+    best->key_hi = b->key_hi; best->key_lo = b->key_lo; best->cost = b->cost; best->index = b->index;
+    best->level = b->level; best->n_scored = b->n_scored; best->list_index = b->list_index;
+    if (b->index < 0)
+        ETP_FAIL(c, ETP_ERR_NO_CANDIDATE, "every candidate of the range was skipped (ds <= |dT|); the reference raises ValueError here");
+    memcpy(fields, c->cyc_out.p + sizeof(BestRec) + 8, sizeof(double) * ETP_NUM_FIELDS * Tmax);
+    if (n_samples) memcpy(n_samples, c->cyc_out.p + sizeof(BestRec), sizeof(int));
+    return ETP_OK;
+}
+
 }  // namespace
 
 int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp_best* bests) {
@@ -1317,6 +1580,18 @@ int etp_plan_batch(etp_ctx* c, int n, const etp_scenario* sc, int precision, etp
         bests[i].level = b.level; bests[i].n_scored = b.n_scored; bests[i].list_index = b.list_index;
     }
     return ETP_OK;
+}
+
+int etp_plan_cycle(etp_ctx* c, const etp_cycle* cy, int precision, etp_best* best, double* fields, int* n_samples) {
+    if (!c || !cy || !cy->step || !best || !fields || (!cy->raw) == (!cy->obstacles)) return ETP_ERR_INVALID;
+    if (precision != ETP_PRECISION_FP32 && precision != ETP_PRECISION_FP64) ETP_FAIL(c, ETP_ERR_INVALID, "precision");
+    if (!c->have_params || !c->have_spline) ETP_FAIL(c, ETP_ERR_STATE, "etp_set_params / etp_set_spline must precede etp_plan_cycle");
+    ETP_CUDA(c, cudaSetDevice(c->device));
+    if (cycle_fusable(c, *cy)) return plan_cycle_fused(c, *cy, precision, best, fields, n_samples);
+    int r = cy->raw ? etp_set_raw_predictions(c, cy->raw, precision) : etp_set_obstacles(c, cy->obstacles, precision);
+    if (r) return r;
+    if ((r = etp_plan_step(c, cy->step, nullptr))) return r;
+    return etp_get_best_trajectory(c, best, fields, n_samples);
 }
 
 int etp_get_best(etp_ctx* c, etp_best* best) {
@@ -1426,6 +1701,7 @@ int etp_debug_counters(etp_ctx* c, uint64_t* out, int n) {
     if (n > 4) out[4] = c->h2d_bytes;
     if (n > 5) out[5] = c->d2h_bytes;
     if (n > 6) out[6] = c->launches;
+    if (n > 7) out[7] = c->graph_launches;
     return ETP_OK;
 }
 

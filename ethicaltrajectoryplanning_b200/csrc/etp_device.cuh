@@ -249,6 +249,17 @@ struct PackArgs {
     double* oconst;
 };
 
+// arguments of the prediction enrichment (enrich_kernel) as a record in device memory
+struct EnrichArgs {
+    int O, Tp;
+    const int* pred_len;
+    const double *pos, *raw_len, *raw_wid, *ori0, *vel0;
+    double dt, margin_l, margin_w, ego_x, ego_y, ego_ori;
+    int wrap_view_cone;
+    double *yaw, *vel, *length, *width;
+    int* resp;
+};
+
 // scenario sweep (etp_plan_batch): the steps of a chunk and the map from the chunk's tiles to them
 struct BatchArgs {
     const DevStep* steps;   // [n_steps] device copies

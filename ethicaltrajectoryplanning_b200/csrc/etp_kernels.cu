@@ -164,13 +164,12 @@ __device__ __forceinline__ double np_gradient(const double* f, const double* s, 
 // ---------------------------------------------------------------------------------------------
 // enrich_kernel: one block per obstacle (prediction_helpers.py:75-135, responsibility.py:57-89), fp64
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
-                                                     const double* __restrict__ raw_len, const double* __restrict__ raw_wid,
-                                                     const double* __restrict__ ori0, const double* __restrict__ vel0, double dt,
-                                                     double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori, bool wrap_view_cone,
-                                                     double* __restrict__ yaw, double* __restrict__ vel, double* __restrict__ length,
-                                                     double* __restrict__ width, int* __restrict__ resp) {
-    extern __shared__ double sm[];
+__device__ __forceinline__ void enrich_body(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
+                                            const double* __restrict__ raw_len, const double* __restrict__ raw_wid,
+                                            const double* __restrict__ ori0, const double* __restrict__ vel0, double dt,
+                                            double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori, bool wrap_view_cone,
+                                            double* __restrict__ yaw, double* __restrict__ vel, double* __restrict__ length,
+                                            double* __restrict__ width, int* __restrict__ resp, double* sm) {
     const int o = blockIdx.x, tid = threadIdx.x;
     const int n = pred_len[o];
     double* s_x = sm;
@@ -218,6 +217,26 @@ __global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* _
         resp[o] = wrap_view_cone ? ((-quarter <= rel && rel <= quarter) ? 0 : 1)
                                  : ((ego_ori - quarter <= ang && ang <= ego_ori + quarter) ? 0 : 1);
     }
+}
+
+__global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* __restrict__ pred_len, const double* __restrict__ pos,
+                                                     const double* __restrict__ raw_len, const double* __restrict__ raw_wid,
+                                                     const double* __restrict__ ori0, const double* __restrict__ vel0, double dt,
+                                                     double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori, bool wrap_view_cone,
+                                                     double* __restrict__ yaw, double* __restrict__ vel, double* __restrict__ length,
+                                                     double* __restrict__ width, int* __restrict__ resp) {
+    extern __shared__ double sm[];
+    enrich_body(O, Tp, pred_len, pos, raw_len, raw_wid, ori0, vel0, dt, margin_l, margin_w, ego_x, ego_y, ego_ori, wrap_view_cone, yaw, vel,
+                length, width, resp, sm);
+}
+
+// the same with its arguments in device memory (planning cycle as a captured graph: the launch never changes, the record does)
+__global__ void __launch_bounds__(128) enrich_args_kernel(const EnrichArgs* __restrict__ args) {
+    extern __shared__ double sm[];
+    const EnrichArgs a = *args;
+    if ((int)blockIdx.x >= a.O) return;
+    enrich_body(a.O, a.Tp, a.pred_len, a.pos, a.raw_len, a.raw_wid, a.ori0, a.vel0, a.dt, a.margin_l, a.margin_w, a.ego_x, a.ego_y, a.ego_ori,
+                a.wrap_view_cone != 0, a.yaw, a.vel, a.length, a.width, a.resp, sm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,6 +477,37 @@ __global__ void best_trajectory_kernel(DevStep st, const BestRec* __restrict__ b
     if (threadIdx.x == 0) *n_out = T;
 }
 
+// the same for step record `scn` of a device array (scenario sweep / planning cycle)
+__global__ void best_trajectory_steps_kernel(const DevStep* __restrict__ steps, const BestRec* __restrict__ best,
+                                             unsigned char* __restrict__ combo) {
+    const DevStep& st = steps[0];
+    BestRec* b_out = reinterpret_cast<BestRec*>(combo);
+    int* n_out = reinterpret_cast<int*>(combo + sizeof(BestRec));
+    double* fields = reinterpret_cast<double*>(combo + sizeof(BestRec) + 8);
+    const BestRec b = *best;
+    if (threadIdx.x == 0) *b_out = b;
+    if (b.index < 0) {
+        if (threadIdx.x == 0) *n_out = 0;
+        return;
+    }
+    const int p = b.index / st.nd, id = b.index % st.nd;
+    const int pl = p - st.p_begin;
+    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+    const bool low = pm[PM_LOW] != 0.0;
+    const int T = (int)pm[PM_T];
+    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+    for (int t = threadIdx.x; t < st.Tmax; t += blockDim.x) {
+        if (t < T) {
+            const TrajPoint tp = traj_point(q, low, gp, st.Tmax, t, st.dt);
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = tp.f[f];
+        } else {
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0) *n_out = T;
+}
+
 // lexicographic minimum of shard-local best records (one thread: a handful of 40-byte records), the device twin of
 // etp_combine_best
 __global__ void combine_best_kernel(const BestRec* __restrict__ recs, int n, int consecutive, BestRec* __restrict__ out) {
@@ -540,6 +590,17 @@ cudaError_t launch_principles(int n, const double* vals, const int* resp, double
 
 cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsigned char* combo, cudaStream_t stream) {
     best_trajectory_kernel<<<1, 64, 0, stream>>>(st, best, combo);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_enrich_args(const EnrichArgs* args, int O, int Tp, cudaStream_t stream) {
+    if (O <= 0) return cudaSuccess;
+    enrich_args_kernel<<<O, 128, sizeof(double) * 3 * Tp, stream>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_best_trajectory_steps(const DevStep* steps, const BestRec* best, unsigned char* combo, cudaStream_t stream) {
+    best_trajectory_steps_kernel<<<1, 64, 0, stream>>>(steps, best, combo);
     return cudaGetLastError();
 }
 

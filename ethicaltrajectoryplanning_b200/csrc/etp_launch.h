@@ -70,6 +70,10 @@ cudaError_t launch_combine_best(const BestRec* recs, int n, int consecutive, Bes
 
 cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsigned char* combo, cudaStream_t stream);
 
+// forms that take their step / arguments from device memory (planning cycle as a captured graph)
+cudaError_t launch_enrich_args(const EnrichArgs* args, int O, int Tp, cudaStream_t stream);
+cudaError_t launch_best_trajectory_steps(const DevStep* steps, const BestRec* best, unsigned char* combo, cudaStream_t stream);
+
 cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream);
 
 }  // namespace etp

@@ -105,6 +105,7 @@ class FrenetPlanner:
             raw = self.predictor(self.ego_state.time_step)
         predictions = copy.copy(raw)
         self._resident = False
+        self._raw_record = None
         if predictions and "orientation_list" not in next(iter(predictions.values())):
             # get_orientation_velocity_and_shape_of_prediction (prediction_helpers.py:75-135) and
             # assign_responsibility_by_action_space (responsibility.py:57-89) on the device, straight into the packed tile
@@ -128,8 +129,13 @@ class FrenetPlanner:
             self._resident_types = types
             self._resident_static = (shapes, ori0, vel0)  # what the enrichment on the device was given (tests replay it on the host)
             self.ctx.ensure_params(self.params_dict, self.p, self.mode)
-            self.ctx.set_raw_predictions(predictions, shapes, ori0, vel0, types, self.scenario.dt,
-                                         np.asarray(self.ego_state.position), self.ego_state.orientation)
+            # fused path without a log: the record is only prepared here and travels with the step (ScoringContext.plan_cycle)
+            cycle = not self.materialize and self.columnar_logger is None
+            self._raw_record = self.ctx.set_raw_predictions(predictions, shapes, ori0, vel0, types, self.scenario.dt,
+                                                            np.asarray(self.ego_state.position), self.ego_state.orientation,
+                                                            upload=not cycle)
+            if not cycle:
+                self._raw_record = None
             self._resident = True
             if self.materialize:  # the log line prints the enriched dict
                 self.ctx.enriched(predictions)
@@ -229,7 +235,12 @@ class FrenetPlanner:
                     self.columnar_logger.log_step(self.time_step, self.time_step * fpar["dt"], res, step, predictions, 0, None)
                 self.last_best, self._trajectory = res.best, res.best_trajectory()
                 return
-            self.last_best, self._trajectory = self.ctx.plan_winner(step)
+            if getattr(self, "_raw_record", None) is not None and getattr(self, "_resident", False):
+                self.last_best, self._trajectory = self.ctx.plan_cycle(step, raw=self._raw_record)
+            elif predictions is not None and not getattr(self, "_resident", False):
+                self.last_best, self._trajectory = self.ctx.plan_cycle(step)
+            else:
+                self.last_best, self._trajectory = self.ctx.plan_winner(step)
 
     # -- planning.py:117-131 -----------------------------------------------------------------------------------
     def ideal_tracking_state(self):

@@ -380,11 +380,15 @@ class ScoringContext:
         self.obstacle_ids, self.O, self.has_pred = pk["ids"], pk["O"], True
 
     def set_raw_predictions(self, predictions, shapes, init_orientation, init_velocity, obstacle_types, dt, ego_position,
-                            ego_orientation, safety_margin_length=1.0, safety_margin_width=0.5, masses=None, protections=None):
+                            ego_orientation, safety_margin_length=1.0, safety_margin_width=0.5, masses=None, protections=None,
+                            upload=True):
         """Raw predictions ``{id: {'pos_list', 'cov_list'}}`` straight from the predictor: orientation, velocity, shape
         margins and the action-space responsibility flag are derived on the device (prediction_helpers.py:75-135,
         responsibility.py:57-89) and the obstacle tile is packed from them.  ``shapes[id] = (length, width)`` of the raw
-        obstacle; empty predictions are dropped like the reference does (:98-100)."""
+        obstacle; empty predictions are dropped like the reference does (:98-100).
+
+        ``upload=False`` only prepares the ``etp_raw_predictions`` record and returns it (``plan_cycle`` hands it to the
+        library together with the step)."""
         # closed loop: the same obstacles with the same static description (the caller hands over the very same dict objects,
         # kept alive here) and equally long predictions as in the previous cycle -> only positions, covariances and the ego
         # pose change; the struct and the static arrays of the previous cycle are used again
@@ -399,8 +403,9 @@ class ScoringContext:
                 np.stack([p["cov_list"] for p in vals], out=fast["cov"].reshape(fast["cov_shape"]))
                 r = fast["struct"]
                 r.ego_x, r.ego_y, r.ego_orientation = float(ego_position[0]), float(ego_position[1]), float(ego_orientation)
-                self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
-                return
+                if upload:
+                    self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
+                return r
         self._raw_fast = None
         oids = [oid for oid in predictions if len(predictions[oid]["pos_list"]) > 0]
         O = len(oids)
@@ -449,15 +454,18 @@ class ScoringContext:
         r.mass, r.is_protected = _dptr(mass), _iptr(prot)
         r.dt, r.safety_margin_length, r.safety_margin_width = float(dt), float(safety_margin_length), float(safety_margin_width)
         r.ego_x, r.ego_y, r.ego_orientation = float(ego_position[0]), float(ego_position[1]), float(ego_orientation)
-        self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
+        if upload:
+            self._check(self.lib.etp_set_raw_predictions(self.h, C.byref(r), self.precision))
         self.obstacle_ids, self.O, self.has_pred = oids, O, True
         self._raw_shape = (O, Tp, lens)
+        self._raw_keep = (r, lens, pos, cov, length, width, ori0, vel0, mass, prot)
         if O and masses is None and int(lens.min()) == Tp and len(oids) == len(predictions):
             p0 = predictions[oids[0]]
             self._raw_fast = dict(refs=(shapes, init_orientation, init_velocity, obstacle_types), dt=dt,
                                   margins=(safety_margin_length, safety_margin_width), oids=tuple(oids), Tp=Tp, pos=pos, cov=cov,
                                   pos_shape=(O,) + np.shape(p0["pos_list"]), cov_shape=(O,) + np.shape(p0["cov_list"]), struct=r,
                                   keep=(lens, length, width, ori0, vel0, mass, prot))
+        return r
 
     def enriched(self, predictions):
         """Read the derived arrays of the last ``set_raw_predictions`` back into the prediction dict (what the reference's
@@ -634,13 +642,13 @@ class ScoringContext:
         return float(v[0]), float(v[1]), float(v[2])
 
     def debug_counters(self):
-        v = (C.c_uint64 * 7)()
-        self._check(self.lib.etp_debug_counters(self.h, v, 7))
+        v = (C.c_uint64 * 8)()
+        self._check(self.lib.etp_debug_counters(self.h, v, 8))
         import struct
 
         return {"fp64_fallback_evals": int(v[0]), "rescored": int(v[1]), "bound_violations": int(v[2]),
                 "worst_error_over_bound": struct.unpack("<f", struct.pack("<I", int(v[3]) & 0xffffffff))[0],
-                "h2d_bytes": int(v[4]), "d2h_bytes": int(v[5]), "launches": int(v[6])}
+                "h2d_bytes": int(v[4]), "d2h_bytes": int(v[5]), "launches": int(v[6]), "graph_launches": int(v[7])}
 
     def best_device_tensor(self):
         """uint8 view (torch) of the device-resident etp_best record, for collectives."""
@@ -835,6 +843,58 @@ class ScoringContext:
                 "y_m": g["y"], "psi_rad": g["yaw"], "kappa_radpm": g["curv"], "v_mps": g["s_d"], "ax_mps2": g["s_dd"],
                 "time_s": np.arange(T) * step.dt}
         return best, traj
+
+    def plan_cycle(self, step: PlanningStep, raw=None):
+        """One closed-loop cycle through ``etp_plan_cycle``: this cycle's predictions (``raw``: the record of
+        ``set_raw_predictions(..., upload=False)``; else the enriched dict of ``step.predictions``), the step, and back the
+        winner with its trajectory -- one library call, one upload, a replayed CUDA graph of the cycle's launches, one
+        read-back.  Returns ``(best, trajectory dict)`` like ``plan_winner``."""
+        self.ensure_params(step.params, step.vehicle, step.mode)
+        cur = getattr(self, "_spline_key", None)
+        if cur is None or cur[0] is not step.csp or cur[1] != self._spline_print(step.csp):
+            self.set_spline(CubicSpline2D.from_foreign(step.csp))
+            self._spline_key = (step.csp, self._spline_print(step.csp))
+        self.ensure_road_boundary(getattr(step, "road_boundary", None))
+        s, keep, n = self.make_step_struct(step)
+        cy = _abi.Cycle()
+        cy.step = C.pointer(s)
+        if raw is not None:
+            cy.raw = C.pointer(raw)
+        else:
+            o = _abi.Obstacles()
+            if step.predictions is None:
+                # `predictions is None` (no risk assessment at all) is not a cycle of the closed loop: the regular path
+                self.set_predictions(None)
+                self.launch(s, None)
+                self._last_tmax, self.last_dt = int(n.max()), step.dt
+                best, f, T = self.best_and_trajectory()
+                return best, self._trajectory_dict(f, T, step.dt)
+            pk = pack_predictions(step.predictions, step.obstacle_types)
+            o.n_obstacles, o.max_pred = pk["O"], pk["Tp"]
+            o.pred_len = _iptr(pk["pred_len"])
+            o.pos, o.cov, o.yaw, o.vel = _dptr(pk["pos"]), _dptr(pk["cov"]), _dptr(pk["yaw"]), _dptr(pk["vel"])
+            o.length, o.width, o.mass = _dptr(pk["length"]), _dptr(pk["width"]), _dptr(pk["mass"])
+            o.is_protected, o.responsibility = _iptr(pk["prot"]), _iptr(pk["resp"])
+            cy.obstacles = C.pointer(o)
+            self.obstacle_ids, self.O, self.has_pred = pk["ids"], pk["O"], True
+            keep.append((o, pk))
+        Tmax = int(n.max())
+        self._last_tmax, self.last_dt = Tmax, step.dt
+        b = _abi.Best()
+        f = np.zeros((_abi.NUM_FIELDS, Tmax), dtype=np.float64)
+        T = C.c_int32(0)
+        self._check(self.lib.etp_plan_cycle(self.h, C.byref(cy), self.precision, C.byref(b), _dptr(f), C.byref(T)))
+        best = dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored, list_index=b.list_index,
+                    key_hi=b.key_hi, key_lo=b.key_lo)
+        return best, self._trajectory_dict(f, int(T.value), step.dt)
+
+    @staticmethod
+    def _trajectory_dict(f, T, dt):
+        """The 11 arrays FrenetPlanner stores in ``self._trajectory`` (frenet_planner.py:564-576; ``v_mps`` is ``s_d``, Q7)."""
+        g = {name: f[i, :T] for i, name in enumerate(_abi.FIELD_NAMES)}
+        return {"s_loc_m": g["s"], "d_loc_m": g["d"], "d_d_loc_mps": g["d_d"], "d_dd_loc_mps2": g["d_dd"], "x_m": g["x"],
+                "y_m": g["y"], "psi_rad": g["yaw"], "kappa_radpm": g["curv"], "v_mps": g["s_d"], "ax_mps2": g["s_dd"],
+                "time_s": np.arange(T) * dt}
 
     def plan(self, step: PlanningStep, materialize=True, c_begin=None, c_end=None, bufs=None,
              configure=True, shard_index=0, shard_count=1) -> ScoreResult:

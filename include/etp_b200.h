@@ -385,6 +385,24 @@ typedef struct {
 
 int etp_plan_batch(etp_ctx* ctx, int n, const etp_scenario* scenarios, int precision, etp_best* bests);
 
+/*
+ * One planning cycle of the closed loop in ONE call (frenet_planner.py:265-576 between "predictions in hand" and
+ * `self._trajectory`): predictions of this cycle -> (enrichment) -> obstacle tile -> profiles -> fused scoring -> exact
+ * selection -> the winner's 13 fp64 rows.  Exactly one of `raw` (predictor output, enriched on the device like
+ * etp_set_raw_predictions) and `obstacles` (the enriched dict, like etp_set_obstacles) is given; parameters, spline and road
+ * boundary are the context's.  All inputs of the cycle travel in one upload, every kernel takes its step from device
+ * memory, and the launch sequence of a cycle whose shapes equal the previous cycle's is replayed as a captured CUDA graph
+ * (ETP_NO_GRAPH=1: launched one by one).  Steps with per-candidate host arrays, a goal context or more than 4096 candidates
+ * run as etp_set_*_predictions + etp_plan_step + etp_get_best_trajectory inside the same call.  Arg-min only (no etp_out).
+ * Returns like etp_get_best_trajectory.
+ */
+typedef struct {
+    const etp_raw_predictions* raw;
+    const etp_obstacles* obstacles;
+    const etp_step* step;
+} etp_cycle;
+int etp_plan_cycle(etp_ctx* ctx, const etp_cycle* cycle, int precision, etp_best* best, double* fields, int* n_samples);
+
 /* number of timesteps Tmax the output tensors must be strided with for `step` */
 int etp_tmax(const etp_step* step);
 
@@ -414,7 +432,7 @@ int etp_get_stage_timing(etp_ctx* ctx, float* ms, int n);
  * maximin-gate decisions too close to call in fp32), out[2] = how many of them differed from their fp32 cost by more than the
  * bound the fp32 pass had claimed (must stay 0), out[3] = largest such error / bound seen (float bits), out[4] / out[5] =
  * bytes this context copied host-to-device / device-to-host (output tensors stay on the device and are not in here),
- * out[6] = kernels it launched. */
+ * out[6] = kernels it launched (directly or through a replayed graph), out[7] = graph replays (etp_plan_cycle). */
 int etp_debug_counters(etp_ctx* ctx, uint64_t* out, int n);
 
 /* combine shard-local bests (e.g. after an all-gather of etp_best records across ranks).

@@ -155,3 +155,49 @@ def test_closed_loop_200_cycles_follow_the_oracle(weights):
             np.testing.assert_allclose(pl.trajectory[name], ref["traj"][f, row, :Tn], rtol=rtol, atol=1e-9, err_msg=f"cycle {k} {name}")
         ego = pl.ideal_tracking_state()
     assert pl.trajectory["s_loc_m"][1] > 5.0  # it moved along the path (the ego-only weights brake to a stop)
+
+
+def test_plan_cycle_replays_a_graph_and_equals_the_step_by_step_path():
+    """etp_plan_cycle (one call per closed-loop cycle: one upload, the cycle's launches as a replayed CUDA graph, one
+    read-back) against configure + plan_step + best_and_trajectory on the same inputs: enriched predictions, raw predictions,
+    a change of the obstacle count in between (the graph is captured again), and the fp64 check mode."""
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from ethicaltrajectoryplanning_b200.synthetic import make_step
+    from ethicaltrajectoryplanning_b200.workloads import MovingObstacles
+
+    for precision in ("fp32", "fp64"):
+        ctx, ref_ctx = ScoringContext(0, precision), ScoringContext(0, precision)
+        try:
+            g0 = ctx.debug_counters()["graph_launches"]
+            for k, (seed, nobs) in enumerate([(1, 5), (2, 5), (3, 5), (4, 5), (5, 7), (6, 7), (7, 7), (8, 5)]):
+                step = make_step("cfg1", seed=100 + seed, n_obstacles=nobs, v0=8.0 + seed)
+                best, traj = ctx.plan_cycle(step)
+                want_best, want_traj = ref_ctx.plan_winner(step)
+                assert (best["index"], best["level"], best["list_index"], best["n_scored"]) == \
+                    (want_best["index"], want_best["level"], want_best["list_index"], want_best["n_scored"]), (k, best, want_best)
+                assert best["cost"] == want_best["cost"]
+                for name in want_traj:
+                    np.testing.assert_array_equal(traj[name], want_traj[name], err_msg=f"{precision} cycle {k} {name}")
+            # cycles 2, 3 replay the graph of (5 obstacles), 6 the one of (7 obstacles); 7 sees the first shape again: launched
+            # directly, a capture follows only when a shape comes twice in a row
+            assert ctx.debug_counters()["graph_launches"] - g0 >= 4
+            # raw predictions: enrichment on the device inside the same graph
+            csp = make_step("cfg1").csp
+            pred = MovingObstacles(csp, 6, 20, 12, v0=12.0, seed=77)
+            shapes, ori0, vel0, types = pred.shapes, pred.ori0, pred.vel0, pred.types
+            for k in range(5):
+                raw = pred.step(k)
+                step = make_step("cfg1", seed=1, v0=12.0)
+                step.predictions, step.obstacle_types, step.predictions_resident = raw, types, True
+                ego = (float(step.ego_position[0]) + 0.3 * k, float(step.ego_position[1]))
+                rec = ctx.set_raw_predictions(raw, shapes, ori0, vel0, types, 0.1, ego, 0.05 * k, upload=False)
+                best, traj = ctx.plan_cycle(step, raw=rec)
+                ref_ctx.ensure_params(step.params, step.vehicle, step.mode)
+                ref_ctx.set_raw_predictions(raw, shapes, ori0, vel0, types, 0.1, ego, 0.05 * k)
+                want_best, want_traj = ref_ctx.plan_winner(step)
+                assert best["index"] == want_best["index"] and best["cost"] == want_best["cost"], (k, best, want_best)
+                np.testing.assert_array_equal(traj["x_m"], want_traj["x_m"])
+            assert ctx.debug_counters()["bound_violations"] == 0
+        finally:
+            ctx.close()
+            ref_ctx.close()
