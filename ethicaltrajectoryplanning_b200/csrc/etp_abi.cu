@@ -104,7 +104,9 @@ struct etp_ctx {
     cudaGraph_t cyc_graph = nullptr;
     cudaGraphExec_t cyc_exec = nullptr;
     std::vector<long long> cyc_key, cyc_seen;
-    bool no_graph = false;
+    bool no_graph = false, cycle_profile = false;
+    double cyc_prof[3] = {0.0, 0.0, 0.0};
+    int cyc_prof_n = 0;
     unsigned long long graph_launches = 0;
     // what crossed the bus and what was launched since the context was created (etp_debug_counters)
     unsigned long long h2d_bytes = 0, d2h_bytes = 0, launches = 0;
@@ -273,6 +275,7 @@ int etp_create(etp_ctx** out, int device) {
         c->refine_off = e && e[0] == '1';
         e = getenv("ETP_NO_GRAPH");
         c->no_graph = e && e[0] == '1';
+        c->cycle_profile = getenv("ETP_CYCLE_PROFILE") != nullptr;
     }
     if (!ok) { etp_destroy(c); return ETP_ERR_CUDA; }
     *out = c;
@@ -1285,6 +1288,7 @@ bool cycle_fusable(const etp_ctx* c, const etp_cycle& cy) {
 }
 
 int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* best, double* fields, int* n_samples) {
+    const auto t_enter = std::chrono::steady_clock::now();
     const etp_step& p = *cy.step;
     const bool raw = cy.raw != nullptr;
     const int O = raw ? cy.raw->n_obstacles : cy.obstacles->n_obstacles;
@@ -1417,6 +1421,7 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     *reinterpret_cast<int*>(h + o_first) = 0;
     for (int k = 0; k < tiles; ++k) reinterpret_cast<int*>(h + o_tscn)[k] = 0;
 
+    const auto t_filled = std::chrono::steady_clock::now();
     // ---- the launch sequence: replayed from the captured graph when nothing it bakes in has changed ----
     const DevStep* d_step = reinterpret_cast<const DevStep*>(dev + o_step);
     const SelectBufs* d_sb = reinterpret_cast<const SelectBufs*>(dev + o_sb);
@@ -1475,7 +1480,20 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     c->launches += n_launch;
     c->h2d_bytes += in_bytes;
     c->d2h_bytes += combo_bytes;
+    const auto t_launched = std::chrono::steady_clock::now();
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->cycle_profile) {
+        const auto t_done = std::chrono::steady_clock::now();
+        c->cyc_prof[0] += std::chrono::duration<double, std::micro>(t_filled - t_enter).count();
+        c->cyc_prof[1] += std::chrono::duration<double, std::micro>(t_launched - t_filled).count();
+        c->cyc_prof[2] += std::chrono::duration<double, std::micro>(t_done - t_launched).count();
+        if (++c->cyc_prof_n == 50) {
+            fprintf(stderr, "etp_plan_cycle (mean of 50): input image %.1f us, launches %.1f us, wait for the device %.1f us, graph launches so far %llu\n",
+                    c->cyc_prof[0] / 50, c->cyc_prof[1] / 50, c->cyc_prof[2] / 50, c->graph_launches);
+            c->cyc_prof[0] = c->cyc_prof[1] = c->cyc_prof[2] = 0.0;
+            c->cyc_prof_n = 0;
+        }
+    }
     // the context now holds this step like after etp_plan_step (etp_get_trajectory etc. keep working on it)
     c->st = st;
     c->precision = precision;

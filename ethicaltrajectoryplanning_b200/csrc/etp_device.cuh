@@ -266,6 +266,7 @@ struct BatchArgs {
     const int* tile_scn;    // [n_tiles] scenario of every 32-candidate tile
     const int* tile_first;  // [n_steps] first tile of every scenario
     int n_tiles, n_steps;
+    int dbg_min_len;        // experiment knob (ETP_CLUSTER_MINLEN): samples per phase-2a segment in cluster mode, 0 = default
 };
 
 struct DevOut {

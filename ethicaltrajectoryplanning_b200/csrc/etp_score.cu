@@ -21,6 +21,10 @@
 //   phase 3  warps split the OBSTACLE axis for the per-obstacle reductions, warp 0 finishes cost, level, key.
 // All materialised tensors are candidate-minor ([...][c]): every store of a warp is one contiguous 128-byte
 // line, written exactly once.
+#ifdef ETP_PHASE_CLOCK
+#include <cstdio>
+#endif
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include <type_traits>
@@ -776,20 +780,20 @@ __device__ __forceinline__ bool boundary_hit(const DevBoundary& b, const Box<dou
     return hit;
 }
 
-// Road-boundary pass of one warp (lanes = candidates): first ego box i = warp, warp + 8, ... that touches the boundary.
+// Road-boundary pass of one warp (lanes = candidates): first ego box i = warp, warp + stride, ... that touches the boundary.
 // Box i of the collision object (create_collision_object, validity_checks.py:125-141) is sample i, or the hull of
 // samples i and i + 1 in swept mode.  Poses come from the shared-memory ego samples; a box the fp32 pass cannot decide
 // is rebuilt from the exact samples and tested in fp64.
 template <typename R>
 __device__ __noinline__ int boundary_pass(const DevStep* stp, const DevParams* prp, const Vec4<R>* e0, const __half2* el, int Ts, int Tl,
-                                          int lane, int warp, bool given, int pl, int id) {
+                                          int lane, int warp, int stride, bool given, int pl, int id) {
     const DevStep& st = *stp;
     const DevBoundary& b = st.boundary;
     const bool swept = b.check == ETP_COLLISION_SWEPT;
     const int n_box = swept ? Tl - 1 : Tl;
     const double hl = prp->veh_l * 0.5, hw = prp->veh_w * 0.5;
     int first = 0x7fffffff;
-    for (int i = warp; i < n_box && i < first; i += kWarps) {
+    for (int i = warp; i < n_box && i < first; i += stride) {
         const Vec4<R> a = e0[i * 32 + lane];
         const float2 lo = __half22float2(el[i * 32 + lane]);
         Box<double> e{st.origin_x + (double)a.x + (double)lo.x * (1.0 / kLoScale), st.origin_y + (double)a.y + (double)lo.y * (1.0 / kLoScale),
@@ -840,8 +844,36 @@ __device__ __noinline__ int goal_sample_flags(const DevGoal* gp, double x, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// thread-block cluster helpers (kBatch kernels of a step with few tiles: one tile per cluster, see score_kernel)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_count_x() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (own shared memory) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ unsigned dsmem_addr(const void* p, unsigned rank) {
+    unsigned a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(rank));
+    return a;
+}
+// plain loads and stores only: a 64-bit max is no native shared-memory atomic (the local one is a compare-and-swap loop), and
+// concurrent remote 64-bit reductions on one word lost updates in the fp64 check mode
+__device__ __forceinline__ unsigned dsmem_ld(unsigned a, unsigned) { unsigned v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long dsmem_ld(unsigned a, unsigned long long) { unsigned long long v; asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void dsmem_st(unsigned a, unsigned v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void dsmem_st(unsigned a, unsigned long long v) { asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // score_kernel
 // ---------------------------------------------------------------------------------------------
+// A kBatch launch of few tiles (a closed-loop planning cycle: 1 .. 18 tiles on 148 SMs) runs as thread-block clusters, ONE
+// TILE PER CLUSTER: every CTA of the cluster generates the tile's ego samples (phase 1, redundantly: it is the latency of a
+// handful of time steps either way), the phase-2 items -- and with them the queue of collision-probability samples -- are
+// dealt round-robin to the cluster's CTAs, each CTA's maxima are folded into CTA 0's through distributed shared memory, and
+// CTA 0 alone runs phase 3.  csize == 1 (every other launch) is the plain kernel.
 // kBatch: the grid walks the tiles of MANY planning steps (scenario sweep, etp_plan_batch): tile -> scenario through
 // ba.tile_scn, the scenario's DevStep is copied into shared memory when a CTA moves on to another scenario, and everything
 // derived from the step (shared-memory plan, obstacle order, item counts) is derived again.  Arg-min only.
@@ -854,6 +886,10 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
     __shared__ DevStep s_st;  // kBatch: the current scenario's step
     const DevStep& st = *(kBatch ? &s_st : &stp);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // position in the thread-block cluster (kBatch launches of few tiles; 0 of 1 otherwise) and this warp's place among the
+    // cluster's warps
+    const int crank = kBatch ? (int)cluster_ctarank() : 0, csize = kBatch ? (int)cluster_nctarank() : 1;
+    const int gwarp = warp * csize + crank, gwarps = kWarps * csize;
     // everything below is a function of the step: set once here, and again per scenario in a batch
     int Ts = 2, O = 0, On = 1, Cs = 0, n_tiles = kBatch ? ba.n_tiles : 0;
     size_t Cp = out.c_stride, harm_plane = 0, mx_plane = 32;
@@ -891,12 +927,16 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         n_groups = (O + kOB - 1) / kOB;
         n_seg = 1;
         if (n_groups > 0) {
-            n_seg = (ETP_SEG_FACTOR * kWarps + n_groups - 1) / n_groups;
-            const int max_seg = (Ts - 1 + 7) / 8;  // at least 8 samples per segment
+            n_seg = (ETP_SEG_FACTOR * gwarps + n_groups - 1) / n_groups;
+            int min_len = csize > 1 ? (csize >= 8 ? 1 : 8 / csize) : 8;  // at least 8 samples per segment; a cluster cuts finer
+            if (kBatch && csize > 1 && ba.dbg_min_len > 0) min_len = ba.dbg_min_len;
+            const int max_seg = (Ts - 1 + min_len - 1) / min_len;
             n_seg = n_seg > max_seg ? max_seg : n_seg;
             n_seg = n_seg < 1 ? 1 : n_seg;
         }
         seg_len = (Ts - 1 + n_seg - 1) / n_seg;
+        n_seg = seg_len > 0 ? (Ts - 1 + seg_len - 1) / seg_len : 1;  // no empty trailing segments
+        n_seg = n_seg < 1 ? 1 : n_seg;
         n_items = n_groups * n_seg;
         // phase-1 time chunks: warp 0 takes about half a share, because it is the warp that still has the previous tile's
         // phase 3b (cost assembly, one candidate per lane) to finish while the others already generate
@@ -916,10 +956,20 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
             if (ldg4<R>(tile.C + o).z == (R)0) s_perm[n++] = o;
     };
     int cur_scn = -1;
+#ifdef ETP_PHASE_CLOCK
+    // debug variant: SM cycle count at the barriers of CTA 0's first tile, printed at the end (tools/build_variants.py)
+    long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int pclk_tiles = 0;
+#define ETP_PCLK(k) do { if (tid == 0 && blockIdx.x == 0 && pclk[k] == 0) pclk[k] = clock64(); } while (0)
+#else
+#define ETP_PCLK(k) do { } while (0)
+#endif
+    ETP_PCLK(0);
     if (!kBatch) {
         derive();
         if (tid == 0) sort_obstacles();
     }
+    ETP_PCLK(1);
 #ifdef ETP_TMA_STAGE
     unsigned tma_parity = 0;  // phase of this warp's mbarrier (one barrier per warp, re-used item after item)
     if (!kBatch) {
@@ -931,7 +981,8 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
 
     // the index of the next tile is fetched one tile ahead (by warp 1, at the start of phase 3a), so that the round trip of
     // the global atomic is off the serial path between two tiles
-    if (tid == 0) s_next = (int)atomicAdd(&counters[1], 1u);
+    // (a cluster takes the tiles cluster id, cluster id + clusters, ...: its CTAs must agree without talking)
+    if (tid == 0) s_next = csize > 1 ? (int)cluster_id_x() : (int)atomicAdd(&counters[1], 1u);
     for (;;) {
         if (tid == 0) {
             s_tile = s_next;
@@ -948,6 +999,9 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         __syncthreads();  // (a) tile index visible; previous tile fully consumed
         const int tl = s_tile;
         if (tl >= n_tiles) break;
+#ifdef ETP_PHASE_CLOCK
+        ++pclk_tiles;
+#endif
         if (kBatch) {
             const int scn = __ldg(ba.tile_scn + tl);
             if (scn != cur_scn) {  // the same for every thread of the CTA; warp 0 is through with the previous step
@@ -967,6 +1021,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
             }
         }
 
+        ETP_PCLK(2);
         // ---- this lane's candidate -----------------------------------------------------------------
         const int cl = (kBatch ? tl - __ldg(ba.tile_first + cur_scn) : tl) * 32 + lane;
         const bool active = cl < Cs;
@@ -1047,6 +1102,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
             if (gflags) atomicOr(&s_goal[lane], gflags);
         }
         const bool tile_fast = __syncthreads_and(wf) != 0;  // (b) ego samples complete; all of them wrap-free?
+        ETP_PCLK(3);
         // travelled distance (calc_trajectory_cost.py:739-757): the segment that enters this warp's time chunk, from the
         // neighbour's last sample in shared memory (split coordinates: exact to 1e-8 m) instead of a regenerated point
         if (warp > 0 && chunk0 + (warp - 1) * chunk < Tl) {
@@ -1074,12 +1130,14 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 int item = 0;
                 if (lane == 0) item = atomicAdd(&s_item, 1);
                 item = __shfl_sync(kFull, item, 0);
+                if (kBatch && csize > 1) item = item * csize + crank;  // the cluster's items go round-robin to its CTAs
                 if (item >= n_items) break;
                 const int g = item % n_groups, seg = item / n_groups;
                 const bool unprot = g * kOB >= s_nprot;  // groups are cut from the class-sorted obstacle order
                 phase2a_dispatch<R, NT, kSym>(pa, g, seg, unprot, tile_fast, tile_full, (g + 1) * kOB <= s_nprot);
             }
             __syncthreads();  // (b2) queue complete
+            ETP_PCLK(4);
 
             // ---- phase 2b: queued samples: three-point gate, collision probability, risk ------------------
             const int qn = s_qn;
@@ -1211,9 +1269,9 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                     }
                     reach_e += stp;
                 }
-                const int c_seg = (2 * kWarps + O - 1) / O, c_len = (Ts - 1 + c_seg - 1) / c_seg;
+                const int c_seg = (2 * gwarps + O - 1) / O, c_len = (Ts - 1 + c_seg - 1) / c_seg;
                 bool hit = false;
-                for (int item = warp; item < O * c_seg; item += kWarps) {
+                for (int item = gwarp; item < O * c_seg; item += gwarps) {
                     const int o = item % O, t_lo = (item / O) * c_len, t_hi = min(t_lo + c_len, Ts - 1);
                     const int n_o = __ldg(st.pred_len + o);
                     const int plen = Tl < n_o ? Tl : n_o;  // prediction_helpers.py:168
@@ -1267,11 +1325,40 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         }
         // ---- road boundary (optional, etp_set_road_boundary): first ego box that touches it ---------------------
         if (st.boundary.check != ETP_COLLISION_HOST) {
-            const int first = boundary_pass<R>(&st, &pr, sm.e0, sm.el, Ts, Tl, lane, warp, kGiven, pl, id);
+            const int first = boundary_pass<R>(&st, &pr, sm.e0, sm.el, Ts, Tl, lane, gwarp, gwarps, kGiven, pl, id);
             if (first != 0x7fffffff) atomicMin(&s_leave[lane], first);
         }
         __syncthreads();  // (c) maxima complete, ego samples dead
-        if (tid == 32) s_next = (int)atomicAdd(&counters[1], 1u);  // read by thread 0 after barrier (d)
+        ETP_PCLK(5);
+        if (tid == 32) s_next = csize > 1 ? s_tile + (int)cluster_count_x() : (int)atomicAdd(&counters[1], 1u);  // read by thread 0 after barrier (d)
+        if (kBatch && csize > 1) {
+            // every CTA of the cluster holds the maxima of its share of the samples: folded into CTA 0's planes, which then
+            // assembles the costs alone
+            cluster_sync_all();  // every CTA's maxima are complete
+            // word i of the planes is folded by CTA (i / kThreads) % csize: it reads the word from every CTA and leaves the
+            // maximum in CTA 0 -- plain distributed-shared-memory loads and one store, every word touched by one thread only
+            for (int i = crank * kThreads + tid; i < MX_COUNT * On * 32; i += kThreads * csize) {
+                U v = sm.mx[i];
+                for (int r = 0; r < csize; ++r) {
+                    if (r == crank) continue;
+                    const U w = dsmem_ld(dsmem_addr(sm.mx + i, (unsigned)r), U{});
+                    v = w > v ? w : v;
+                }
+                if (crank == 0) sm.mx[i] = v;
+                else dsmem_st(dsmem_addr(sm.mx + i, 0u), v);
+            }
+            if (crank == 0 && tid < 32) {
+                int hit = s_hit[tid], leave = s_leave[tid];
+                for (int r = 1; r < csize; ++r) {
+                    hit |= (int)dsmem_ld(dsmem_addr(&s_hit[tid], (unsigned)r), 0u);
+                    leave = min(leave, (int)dsmem_ld(dsmem_addr(&s_leave[tid], (unsigned)r), 0u));
+                }
+                s_hit[tid] = hit;
+                s_leave[tid] = leave;
+            }
+            cluster_sync_all();  // folded values in CTA 0; nobody touches another CTA's shared memory past this point
+            if (crank != 0) continue;
+        }
 
         // ---- phase 3a: per-obstacle reductions, warps over obstacles ----------------------------------
         {
@@ -1317,6 +1404,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
             p3[P3_RESP * 32] = resp; p3[P3_MM * 32] = mm; p3[P3_MAX_O * 32] = max_o; p3[P3_MM_LO * 32] = mm_lo; p3[P3_MM_HI * 32] = mm_hi;
         }
         __syncthreads();  // (d) partials complete
+        ETP_PCLK(6);
 
         // ---- phase 3b: principles, cost, level (warp 0, one candidate per lane) -------------------------
         if (warp == 0) {
@@ -1407,9 +1495,16 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 }
             }
         }
+        ETP_PCLK(7);
         // no barrier here: warp 0 reads only p1 / p3 / ff; p1 / ff are next written after barrier (a) of the next
         // tile, p3 (aliasing the ego samples) after barrier (a) as well
     }
+#ifdef ETP_PHASE_CLOCK
+    if (tid == 0 && blockIdx.x == 0)
+        printf("score_kernel CTA 0: %d tiles; cycles setup %lld, to tile start %lld, phase 1 %lld, phase 2a %lld, phase 2b %lld, phase 3a %lld, "
+               "phase 3b %lld, whole %lld\n", pclk_tiles, pclk[1] - pclk[0], pclk[2] - pclk[1], pclk[3] - pclk[2], pclk[4] - pclk[3],
+               pclk[5] - pclk[4], pclk[6] - pclk[5], pclk[7] - pclk[6], clock64() - pclk[0]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1465,6 +1560,32 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid < 1) grid = 1;
     *grid_out = (int)grid;
+    if (kBatch) {
+        // few tiles (a planning cycle, not a sweep): one tile per thread-block cluster, as many CTAs per tile as leave every
+        // CTA an SM of its own
+        int csize = 1;
+        static const bool no_cluster = getenv("ETP_NO_CLUSTER") != nullptr;
+        static const int max_cluster = getenv("ETP_CLUSTER_MAX") ? atoi(getenv("ETP_CLUSTER_MAX")) : 8;
+        static const int dbg_min_len = getenv("ETP_CLUSTER_MINLEN") ? atoi(getenv("ETP_CLUSTER_MINLEN")) : 0;
+        for (int k = 8; k > 1 && !no_cluster; k >>= 1)
+            if (k <= max_cluster && tiles * k <= num_sms) { csize = k; break; }
+        if (csize > 1) {
+            BatchArgs b2 = *ba;
+            b2.dbg_min_len = dbg_min_len;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(tiles * csize));
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            *grid_out = (int)(tiles * csize);
+            return cudaLaunchKernelEx(&cfg, score_kernel<R, NT, kSym, kGiven, kBatch>, st, pr, out, counters, b2);
+        }
+    }
     score_kernel<R, NT, kSym, kGiven, kBatch><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, counters, kBatch ? *ba : BatchArgs{});
     return cudaGetLastError();
 }

@@ -733,25 +733,40 @@ class ScoringContext:
         length = np.array([p["shape"]["length"] for p in flat], dtype=np.float64)
         width = np.array([p["shape"]["width"] for p in flat], dtype=np.float64)
         resp = np.array([p.get("responsibility", 0) for p in flat], dtype=np.int32)
-        names = [getattr(st.obstacle_types[oid], "name", st.obstacle_types[oid]) for st, (p, _) in zip(steps, preds) for oid in p]
-        prot = np.zeros(No, dtype=np.int32)
-        mass = np.zeros(No)
-        car = np.zeros(No, dtype=bool)
-        for j, t in enumerate(names):
-            if t in PROTECTED_TYPES:
-                prot[j] = 1
-            elif t not in UNPROTECTED_TYPES:
-                raise ValueError(f"obstacle type {t!r} has no protection class (harm_estimation.py:52-56)")
-            if t in ("CAR", "PRIORITY_VEHICLE", "PARKED_VEHICLE", "TAXI"):
-                car[j] = True
-            else:
-                mass[j] = obstacle_mass(t, 0.0)
+        # class of every obstacle -> (protected, mass or None for the area formula), looked up once per class name
+        classes = {}
+        prot_l, mass_l = [], []
+        for st, (p, _) in zip(steps, preds):
+            ot = st.obstacle_types
+            for oid in p:
+                t = ot[oid]
+                c = classes.get(t)
+                if c is None:
+                    name = getattr(t, "name", t)
+                    if name not in PROTECTED_TYPES and name not in UNPROTECTED_TYPES:
+                        raise ValueError(f"obstacle type {name!r} has no protection class (harm_estimation.py:52-56)")
+                    by_area = name in ("CAR", "PRIORITY_VEHICLE", "PARKED_VEHICLE", "TAXI")
+                    c = classes[t] = (1 if name in PROTECTED_TYPES else 0, np.nan if by_area else obstacle_mass(name, 0.0))
+                prot_l.append(c[0])
+                mass_l.append(c[1])
+        prot = np.array(prot_l, dtype=np.int32)
+        mass = np.array(mass_l, dtype=np.float64)
+        car = np.isnan(mass)
         mass[car] = -1333.5 + 526.9 * np.power((length * width)[car], 0.8)  # properties.py:37, the same ufunc as obstacle_mass
         plen = np.full(No, Tp, dtype=np.int32)
         v = np.array([st.v_list for st in steps], dtype=np.float64)
         t = np.array([st.t_list for st in steps], dtype=np.float64)
         d = np.array([st.d_list for st in steps], dtype=np.float64)
-        ns = np.array([[len(np.arange(0.0, tT, st.dt)) for tT in st.t_list] for st in steps], dtype=np.int32)
+        # samples per horizon, len(np.arange(0, tT, dt)) (frenet_functions.py:267): computed once per distinct (tT, dt)
+        nsamp = {}
+        ns = np.empty((n, nt), dtype=np.int32)
+        for i, st in enumerate(steps):
+            for k, tT in enumerate(st.t_list):
+                key = (float(tT), st.dt)
+                c = nsamp.get(key)
+                if c is None:
+                    c = nsamp[key] = len(np.arange(0.0, tT, st.dt))
+                ns[i, k] = c
         # the struct arrays are filled column by column through numpy views of the ctypes layouts
         counts = np.array([len(vals) for _, vals in preds], dtype=np.int64)
         o0 = np.concatenate([[0], np.cumsum(counts)[:-1]])
@@ -773,18 +788,19 @@ class ScoringContext:
             ob_arr[name] = a.ctypes.data + size * o0
         # splines: a table is shared by consecutive scenarios that bring the same spline object or equal tables
         tables, knp, cxp, cyp, nsg = [], [], [], [], []
+        f64 = lambda a: a if (type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous) \
+            else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
         for st in steps:
             if not tables or tables[-1][0] is not st.csp:
                 csp = CubicSpline2D.from_foreign(st.csp)
-                kn = np.ascontiguousarray(csp.s, dtype=np.float64)
-                cx = np.ascontiguousarray(csp.coef_x, dtype=np.float64)
-                cy = np.ascontiguousarray(csp.coef_y, dtype=np.float64)
-                if tables and np.array_equal(kn, tables[-1][1]) and np.array_equal(cx, tables[-1][2]) and np.array_equal(cy, tables[-1][3]):
+                kn, cx, cy = f64(csp.s), f64(csp.coef_x), f64(csp.coef_y)
+                sig = (kn.tobytes(), cx.tobytes(), cy.tobytes())
+                if tables and sig == tables[-1][4]:
                     tables[-1] = (st.csp,) + tables[-1][1:]
                 else:
-                    tables.append((st.csp, kn, cx, cy))
-            _, kn, cx, cy = tables[-1]
-            knp.append(kn.ctypes.data); cxp.append(cx.ctypes.data); cyp.append(cy.ctypes.data); nsg.append(len(kn) - 1)
+                    tables.append((st.csp, kn, cx, cy, sig, (kn.ctypes.data, cx.ctypes.data, cy.ctypes.data, len(kn) - 1)))
+            ptr = tables[-1][5]
+            knp.append(ptr[0]); cxp.append(ptr[1]); cyp.append(ptr[2]); nsg.append(ptr[3])
         sc_arr = np.zeros(n, dtype=_struct_dtype(_abi.Scenario))
         sc_arr["step"] = st_arr.ctypes.data + st_arr.itemsize * idx
         sc_arr["obstacles"] = ob_arr.ctypes.data + ob_arr.itemsize * idx

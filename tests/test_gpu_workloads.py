@@ -171,6 +171,7 @@ def test_plan_cycle_replays_a_graph_and_equals_the_step_by_step_path():
             g0 = ctx.debug_counters()["graph_launches"]
             for k, (seed, nobs) in enumerate([(1, 5), (2, 5), (3, 5), (4, 5), (5, 7), (6, 7), (7, 7), (8, 5)]):
                 step = make_step("cfg1", seed=100 + seed, n_obstacles=nobs, v0=8.0 + seed)
+                step.csp = csp0 = step.csp if k == 0 else csp0  # one reference path object, as in a closed loop
                 best, traj = ctx.plan_cycle(step)
                 want_best, want_traj = ref_ctx.plan_winner(step)
                 assert (best["index"], best["level"], best["list_index"], best["n_scored"]) == \
@@ -182,12 +183,12 @@ def test_plan_cycle_replays_a_graph_and_equals_the_step_by_step_path():
             # directly, a capture follows only when a shape comes twice in a row
             assert ctx.debug_counters()["graph_launches"] - g0 >= 4
             # raw predictions: enrichment on the device inside the same graph
-            csp = make_step("cfg1").csp
-            pred = MovingObstacles(csp, 6, 20, 12, v0=12.0, seed=77)
+            pred = MovingObstacles(csp0, 6, 20, 12, v0=12.0, seed=77)
             shapes, ori0, vel0, types = pred.shapes, pred.ori0, pred.vel0, pred.types
             for k in range(5):
                 raw = pred.step(k)
                 step = make_step("cfg1", seed=1, v0=12.0)
+                step.csp = csp0
                 step.predictions, step.obstacle_types, step.predictions_resident = raw, types, True
                 ego = (float(step.ego_position[0]) + 0.3 * k, float(step.ego_position[1]))
                 rec = ctx.set_raw_predictions(raw, shapes, ori0, vel0, types, 0.1, ego, 0.05 * k, upload=False)
