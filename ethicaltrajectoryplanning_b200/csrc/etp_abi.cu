@@ -104,9 +104,12 @@ struct etp_ctx {
     cudaGraph_t cyc_graph = nullptr;
     cudaGraphExec_t cyc_exec = nullptr;
     std::vector<long long> cyc_key, cyc_seen;
-    bool no_graph = false, cycle_profile = false;
+    bool no_graph = false, cycle_profile = false, cycle_split = false;
     double cyc_prof[3] = {0.0, 0.0, 0.0};
     int cyc_prof_n = 0;
+    cudaEvent_t cyc_ev[12] = {};  // ETP_CYCLE_PROFILE=2: one event between any two operations of a cycle
+    double cyc_stage[12] = {};
+    int cyc_stage_n = 0;
     unsigned long long graph_launches = 0;
     // what crossed the bus and what was launched since the context was created (etp_debug_counters)
     unsigned long long h2d_bytes = 0, d2h_bytes = 0, launches = 0;
@@ -276,6 +279,9 @@ int etp_create(etp_ctx** out, int device) {
         e = getenv("ETP_NO_GRAPH");
         c->no_graph = e && e[0] == '1';
         c->cycle_profile = getenv("ETP_CYCLE_PROFILE") != nullptr;
+        c->cycle_split = getenv("ETP_CYCLE_SPLIT") != nullptr;
+        if (c->cycle_profile && getenv("ETP_CYCLE_PROFILE")[0] == '2')
+            for (auto& e2 : c->cyc_ev) ok = ok && cudaEventCreate(&e2) == cudaSuccess;
     }
     if (!ok) { etp_destroy(c); return ETP_ERR_CUDA; }
     *out = c;
@@ -293,6 +299,7 @@ int etp_destroy(etp_ctx* c) {
     c->cyc_dev.release();
     c->cyc_in.release();
     c->cyc_out.release();
+    for (auto& e2 : c->cyc_ev) if (e2) cudaEventDestroy(e2);
     if (c->cyc_exec) cudaGraphExecDestroy(c->cyc_exec);
     if (c->cyc_graph) cudaGraphDestroy(c->cyc_graph);
     for (int i = 0; i < 2; ++i) {
@@ -1427,30 +1434,61 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     const SelectBufs* d_sb = reinterpret_cast<const SelectBufs*>(dev + o_sb);
     BestRec* d_best = reinterpret_cast<BestRec*>(sdev + s_best);
     unsigned char* d_combo = sdev + s_combo;
-    const int n_launch = 5 + (raw && O > 0 ? 1 : 0) + (refine ? 1 : 0);
+    const int n_launch = c->cycle_split ? 5 + (raw && O > 0 ? 1 : 0) + (refine ? 1 : 0) : 4;
     const bool timed = c->timing;  // CUDA-event timing of the stages (etp_get_stage_timing): launched one by one then
+    const bool staged = c->cyc_ev[0] != nullptr;  // ETP_CYCLE_PROFILE=2
+#define ETP_STAGE_EV(k) do { if (staged) ETP_CUDA(c, cudaEventRecord(c->cyc_ev[k], c->stream)); } while (0)
+    // the result lands in pinned host memory straight from the last kernel (unified addressing: the device writes through the
+    // host pointer), so the cycle is one upload and four launches: head | fused scoring | selection | tail
+    unsigned char* h_combo = c->cyc_out.p;
     auto enqueue = [&]() -> int {
+        ETP_STAGE_EV(0);
         ETP_CUDA(c, cudaMemcpyAsync(dev, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
-        if (raw) ETP_CUDA(c, launch_enrich_args(reinterpret_cast<const EnrichArgs*>(dev + o_enr), O, Tp, c->stream));
-        ETP_CUDA(c, launch_pack_obstacles_batch(precision, reinterpret_cast<const PackArgs*>(dev + o_pack), 1, O * Tp, c->stream));
-        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-        ETP_CUDA(c, launch_profiles_batch(d_step, c->pr, 1, n_prof, Tmax, c->stream));
-        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        ETP_STAGE_EV(1);
         const BatchArgs ba{d_step, reinterpret_cast<const int*>(dev + o_tscn), reinterpret_cast<const int*>(dev + o_first), tiles, 1};
+        if (c->cycle_split) {  // ETP_CYCLE_SPLIT=1: the stages as separate launches (measurement aid)
+            if (raw) ETP_CUDA(c, launch_enrich_args(reinterpret_cast<const EnrichArgs*>(dev + o_enr), O, Tp, c->stream));
+            ETP_STAGE_EV(2);
+            ETP_CUDA(c, launch_pack_obstacles_batch(precision, reinterpret_cast<const PackArgs*>(dev + o_pack), 1, O * Tp, c->stream));
+            if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+            ETP_STAGE_EV(3);
+            ETP_CUDA(c, launch_profiles_batch(d_step, c->pr, 1, n_prof, Tmax, c->stream));
+        } else {
+            ETP_STAGE_EV(2);
+            if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+            ETP_STAGE_EV(3);
+            ETP_CUDA(c, launch_cycle_head(precision, d_step, c->pr, reinterpret_cast<const PackArgs*>(dev + o_pack),
+                                          raw ? reinterpret_cast<const EnrichArgs*>(dev + o_enr) : nullptr, n_prof, O, Tp, Tmax, c->stream));
+        }
+        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        ETP_STAGE_EV(4);
         ETP_CUDA(c, launch_score(precision, DevStep{}, c->pr, DevOut{}, c->counters.as<unsigned>(), c->num_sms, &c->last_grid, c->stream, &ba, smem));
         if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+        ETP_STAGE_EV(5);
         ETP_CUDA(c, launch_select_batch(d_step, d_sb, d_best, c->counters.as<unsigned>() + 1, 1, c->stream));
-        if (refine) ETP_CUDA(c, launch_rescore_batch(d_step, c->pr, d_sb, d_best, 1, Tmax, O, c->stream));
-        if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-        ETP_CUDA(c, launch_best_trajectory_steps(d_step, d_best, d_combo, c->stream));
-        ETP_CUDA(c, cudaMemcpyAsync(c->cyc_out.p, d_combo, combo_bytes, cudaMemcpyDeviceToHost, c->stream));
+        ETP_STAGE_EV(6);
+        if (c->cycle_split) {
+            if (refine) ETP_CUDA(c, launch_rescore_batch(d_step, c->pr, d_sb, d_best, 1, Tmax, O, c->stream));
+            if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+            ETP_STAGE_EV(7);
+            ETP_CUDA(c, launch_best_trajectory_steps(d_step, d_best, d_combo, c->stream));
+            ETP_STAGE_EV(8);
+            ETP_CUDA(c, cudaMemcpyAsync(c->cyc_out.p, d_combo, combo_bytes, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            ETP_STAGE_EV(7);
+            ETP_CUDA(c, launch_cycle_tail(d_step, c->pr, d_sb, d_best, h_combo, refine, Tmax, O, c->stream));
+            if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+            ETP_STAGE_EV(8);
+        }
+        ETP_STAGE_EV(9);
         return ETP_OK;
     };
+#undef ETP_STAGE_EV
     const std::vector<long long> key = {precision, raw ? 1 : 0, O, Tp, p.nv, p.nt, p.nd, Tmax, (long long)in_bytes, (long long)(size_t)dev,
                                         (long long)(size_t)h, (long long)(size_t)c->cyc_out.p, (long long)c->config_version, refine ? 1 : 0,
-                                        (long long)(size_t)c->stream, (long long)(size_t)c->knots.p};
+                                        (long long)(size_t)c->stream, (long long)(size_t)c->knots.p, c->cycle_split ? 1 : 0};
     int r = ETP_OK;
-    if (timed) {
+    if (timed || staged) {
         if ((r = enqueue())) return r;
     } else if (!c->no_graph && c->cyc_exec && key == c->cyc_key) {
         ETP_CUDA(c, cudaGraphLaunch(c->cyc_exec, c->stream));
@@ -1479,9 +1517,23 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     }
     c->launches += n_launch;
     c->h2d_bytes += in_bytes;
-    c->d2h_bytes += combo_bytes;
+    c->d2h_bytes += combo_bytes;  // written by the device into pinned host memory, or copied (ETP_CYCLE_SPLIT)
     const auto t_launched = std::chrono::steady_clock::now();
     ETP_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (staged) {
+        static const char* names[9] = {"upload", "enrich", "pack", "profiles|head", "score", "select", "rescore", "trajectory|tail", "read-back"};
+        for (int k = 0; k < 9; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->cyc_ev[k], c->cyc_ev[k + 1]);
+            c->cyc_stage[k] += ms * 1e3;
+        }
+        if (++c->cyc_stage_n == 50) {
+            fprintf(stderr, "etp_plan_cycle stages (mean of 50, us, launched one by one):");
+            for (int k = 0; k < 9; ++k) { fprintf(stderr, " %s %.1f", names[k], c->cyc_stage[k] / 50); c->cyc_stage[k] = 0.0; }
+            fprintf(stderr, "\n");
+            c->cyc_stage_n = 0;
+        }
+    }
     if (c->cycle_profile) {
         const auto t_done = std::chrono::steady_clock::now();
         c->cyc_prof[0] += std::chrono::duration<double, std::micro>(t_filled - t_enter).count();

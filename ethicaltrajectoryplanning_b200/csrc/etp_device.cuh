@@ -533,6 +533,35 @@ __device__ __forceinline__ TrajPoint traj_point(const Poly5& q, bool low, const 
     return r;
 }
 
+// The winner of a step with its trajectory, all threads of the block: [BestRec | int T | pad | fields[ETP_NUM_FIELDS][Tmax]]
+// (frenet_planner.py:564-576 reads these rows); requires the winner's profile in st.prof.
+__device__ __forceinline__ void best_trajectory_body(const DevStep& st, const BestRec& b, unsigned char* __restrict__ combo) {
+    BestRec* b_out = reinterpret_cast<BestRec*>(combo);
+    int* n_out = reinterpret_cast<int*>(combo + sizeof(BestRec));
+    double* fields = reinterpret_cast<double*>(combo + sizeof(BestRec) + 8);
+    if (threadIdx.x == 0) *b_out = b;
+    if (b.index < 0) {
+        if (threadIdx.x == 0) *n_out = 0;
+        return;
+    }
+    const int p = b.index / st.nd, id = b.index % st.nd;
+    const int pl = p - st.p_begin;
+    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
+    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
+    const bool low = pm[PM_LOW] != 0.0;
+    const int T = (int)pm[PM_T];
+    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
+    for (int t = threadIdx.x; t < st.Tmax; t += blockDim.x) {
+        if (t < T) {
+            const TrajPoint tp = traj_point(q, low, gp, st.Tmax, t, st.dt);
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = tp.f[f];
+        } else {
+            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0) *n_out = T;
+}
+
 // One sample of a caller-provided trajectory (etp_score_trajectories): `g` points at field 0, sample 0 of the
 // trajectory, rows are `ts` samples x `stride` trajectories.
 __device__ __forceinline__ TrajPoint given_point(const double* g, int ts, int stride, int t) {

@@ -169,8 +169,8 @@ __device__ __forceinline__ void enrich_body(int O, int Tp, const int* __restrict
                                             const double* __restrict__ ori0, const double* __restrict__ vel0, double dt,
                                             double margin_l, double margin_w, double ego_x, double ego_y, double ego_ori, bool wrap_view_cone,
                                             double* __restrict__ yaw, double* __restrict__ vel, double* __restrict__ length,
-                                            double* __restrict__ width, int* __restrict__ resp, double* sm) {
-    const int o = blockIdx.x, tid = threadIdx.x;
+                                            double* __restrict__ width, int* __restrict__ resp, double* sm, const int o) {
+    const int tid = threadIdx.x;
     const int n = pred_len[o];
     double* s_x = sm;
     double* s_y = sm + Tp;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) enrich_kernel(int O, int Tp, const int* _
                                                      double* __restrict__ width, int* __restrict__ resp) {
     extern __shared__ double sm[];
     enrich_body(O, Tp, pred_len, pos, raw_len, raw_wid, ori0, vel0, dt, margin_l, margin_w, ego_x, ego_y, ego_ori, wrap_view_cone, yaw, vel,
-                length, width, resp, sm);
+                length, width, resp, sm, blockIdx.x);
 }
 
 // the same with its arguments in device memory (planning cycle as a captured graph: the launch never changes, the record does)
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128) enrich_args_kernel(const EnrichArgs* __re
     const EnrichArgs a = *args;
     if ((int)blockIdx.x >= a.O) return;
     enrich_body(a.O, a.Tp, a.pred_len, a.pos, a.raw_len, a.raw_wid, a.ori0, a.vel0, a.dt, a.margin_l, a.margin_w, a.ego_x, a.ego_y, a.ego_ori,
-                a.wrap_view_cone != 0, a.yaw, a.vel, a.length, a.width, a.resp, sm);
+                a.wrap_view_cone != 0, a.yaw, a.vel, a.length, a.width, a.resp, sm, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -394,6 +394,31 @@ __global__ void __launch_bounds__(128) profile_batch_kernel(const DevStep* __res
     profile_body(st, pr, st.nskip, sm, blockIdx.x);
 }
 
+// Planning cycle (etp_plan_cycle): everything that precedes the fused kernel in ONE launch.  Blocks [0, n_prof) generate the
+// longitudinal profiles; block n_prof + o derives obstacle o's orientation, velocity, shape and responsibility flag from its
+// raw prediction (`enrich`, optional) and packs that obstacle's rows of the tile -- a sample of the tile needs nothing of
+// another obstacle, so the two steps meet at a block barrier instead of at a kernel boundary.
+template <typename R>
+__global__ void __launch_bounds__(128) cycle_head_kernel(const DevStep* __restrict__ steps, const __grid_constant__ DevParams pr,
+                                                         const PackArgs* __restrict__ pack, const EnrichArgs* __restrict__ enrich, int n_prof) {
+    extern __shared__ double sm[];
+    if ((int)blockIdx.x < n_prof) {
+        const DevStep& st = steps[0];
+        profile_body(st, pr, st.nskip, sm, blockIdx.x);
+        return;
+    }
+    const int o = blockIdx.x - n_prof;
+    const PackArgs a = *pack;
+    if (o >= a.O) return;
+    if (enrich) {
+        const EnrichArgs e = *enrich;
+        enrich_body(e.O, e.Tp, e.pred_len, e.pos, e.raw_len, e.raw_wid, e.ori0, e.vel0, e.dt, e.margin_l, e.margin_w, e.ego_x, e.ego_y, e.ego_ori,
+                    e.wrap_view_cone != 0, e.yaw, e.vel, e.length, e.width, e.resp, sm, o);
+        __syncthreads();  // this block's orientation / velocity rows and shape are what its own samples read
+    }
+    for (int t = threadIdx.x; t < a.Tp; t += blockDim.x) pack_sample<R>(a, o * a.Tp + t);
+}
+
 // one candidate, all 13 fields in fp64 -> [ETP_NUM_FIELDS][Tmax]; requires its profile in st.prof
 __global__ void trajectory_kernel(DevStep st, int c_dense, double* __restrict__ fields, int* __restrict__ n_out) {
     const int p = c_dense / st.nd, id = c_dense % st.nd;
@@ -450,62 +475,13 @@ __global__ void principles_kernel(int n, const double* __restrict__ v, const int
 
 // the winner of the last step, found on the device: [BestRec | int T | pad | fields[ETP_NUM_FIELDS][Tmax]] in one buffer
 __global__ void best_trajectory_kernel(DevStep st, const BestRec* __restrict__ best, unsigned char* __restrict__ combo) {
-    BestRec* b_out = reinterpret_cast<BestRec*>(combo);
-    int* n_out = reinterpret_cast<int*>(combo + sizeof(BestRec));
-    double* fields = reinterpret_cast<double*>(combo + sizeof(BestRec) + 8);
-    const BestRec b = *best;
-    if (threadIdx.x == 0) *b_out = b;
-    if (b.index < 0) {
-        if (threadIdx.x == 0) *n_out = 0;
-        return;
-    }
-    const int p = b.index / st.nd, id = b.index % st.nd;
-    const int pl = p - st.p_begin;
-    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
-    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
-    const bool low = pm[PM_LOW] != 0.0;
-    const int T = (int)pm[PM_T];
-    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
-    for (int t = threadIdx.x; t < st.Tmax; t += blockDim.x) {
-        if (t < T) {
-            const TrajPoint tp = traj_point(q, low, gp, st.Tmax, t, st.dt);
-            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = tp.f[f];
-        } else {
-            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = 0.0;
-        }
-    }
-    if (threadIdx.x == 0) *n_out = T;
+    best_trajectory_body(st, *best, combo);
 }
 
 // the same for step record `scn` of a device array (scenario sweep / planning cycle)
 __global__ void best_trajectory_steps_kernel(const DevStep* __restrict__ steps, const BestRec* __restrict__ best,
                                              unsigned char* __restrict__ combo) {
-    const DevStep& st = steps[0];
-    BestRec* b_out = reinterpret_cast<BestRec*>(combo);
-    int* n_out = reinterpret_cast<int*>(combo + sizeof(BestRec));
-    double* fields = reinterpret_cast<double*>(combo + sizeof(BestRec) + 8);
-    const BestRec b = *best;
-    if (threadIdx.x == 0) *b_out = b;
-    if (b.index < 0) {
-        if (threadIdx.x == 0) *n_out = 0;
-        return;
-    }
-    const int p = b.index / st.nd, id = b.index % st.nd;
-    const int pl = p - st.p_begin;
-    const double* gp = st.prof + (size_t)pl * PF_COUNT * st.Tmax;
-    const double* pm = st.prof_meta + (size_t)pl * PM_COUNT;
-    const bool low = pm[PM_LOW] != 0.0;
-    const int T = (int)pm[PM_T];
-    const Poly5 q = lateral_poly(st, low, st.d_list[id], pm[PM_TEND], pm[PM_DS]);
-    for (int t = threadIdx.x; t < st.Tmax; t += blockDim.x) {
-        if (t < T) {
-            const TrajPoint tp = traj_point(q, low, gp, st.Tmax, t, st.dt);
-            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = tp.f[f];
-        } else {
-            for (int f = 0; f < ETP_NUM_FIELDS; ++f) fields[f * st.Tmax + t] = 0.0;
-        }
-    }
-    if (threadIdx.x == 0) *n_out = T;
+    best_trajectory_body(steps[0], *best, combo);
 }
 
 // lexicographic minimum of shard-local best records (one thread: a handful of 40-byte records), the device twin of
@@ -596,6 +572,15 @@ cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsig
 cudaError_t launch_enrich_args(const EnrichArgs* args, int O, int Tp, cudaStream_t stream) {
     if (O <= 0) return cudaSuccess;
     enrich_args_kernel<<<O, 128, sizeof(double) * 3 * Tp, stream>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cycle_head(int precision, const DevStep* steps, const DevParams& pr, const PackArgs* pack, const EnrichArgs* enrich,
+                              int n_prof, int O, int Tp, int Tmax, cudaStream_t stream) {
+    const int ma = 7 * Tmax, mb = 3 * Tp;
+    const size_t smem = sizeof(double) * (size_t)(ma > mb ? ma : mb);
+    if (precision == ETP_PRECISION_FP64) cycle_head_kernel<double><<<n_prof + O, 128, smem, stream>>>(steps, pr, pack, enrich, n_prof);
+    else cycle_head_kernel<float><<<n_prof + O, 128, smem, stream>>>(steps, pr, pack, enrich, n_prof);
     return cudaGetLastError();
 }
 

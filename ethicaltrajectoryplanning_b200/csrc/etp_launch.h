@@ -72,6 +72,11 @@ cudaError_t launch_best_trajectory(const DevStep& st, const BestRec* best, unsig
 
 // forms that take their step / arguments from device memory (planning cycle as a captured graph)
 cudaError_t launch_enrich_args(const EnrichArgs* args, int O, int Tp, cudaStream_t stream);
+// planning cycle: [profiles | enrich + pack per obstacle] in one launch; [re-score survivors | winner's trajectory] in one launch
+cudaError_t launch_cycle_head(int precision, const DevStep* steps, const DevParams& pr, const PackArgs* pack, const EnrichArgs* enrich,
+                              int n_prof, int O, int Tp, int Tmax, cudaStream_t stream);
+cudaError_t launch_cycle_tail(const DevStep* steps, const DevParams& pr, const SelectBufs* sbs, BestRec* bests, unsigned char* combo,
+                              bool refine, int Tmax, int O, cudaStream_t stream);
 cudaError_t launch_best_trajectory_steps(const DevStep* steps, const BestRec* best, unsigned char* combo, cudaStream_t stream);
 
 cudaError_t launch_trajectory(const DevStep& st, int c_dense, double* fields, int* n_out, cudaStream_t stream);

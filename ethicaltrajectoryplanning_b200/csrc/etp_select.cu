@@ -376,13 +376,14 @@ __device__ __forceinline__ void harm_logits(const Tab<double>& tab, const ObsSam
 }
 
 // CTA `first` of `nblk` takes every nblk-th survivor of the step `st`
+// Returns true in the CTA that closed the selection (it wrote *best_out).
 template <bool kGiven>
-__device__ __forceinline__ void rescore_body(const DevStep& st, const DevParams& pr, const DevOut& out, int out_f32, const SelectBufs& sb,
+__device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams& pr, const DevOut& out, int out_f32, const SelectBufs& sb,
                                              BestRec* __restrict__ best_out, const int* __restrict__ nskip, unsigned char* smem_raw,
                                              const int first, const int nblk) {
     using U = unsigned long long;
     const int count = sb.hdr[0];
-    if (count == 0) return;  // the selection was final
+    if (count == 0) return false;  // the selection was final
     const int Ts = st.Tmax;
     const int O = st.has_pred ? st.O : 0;
     const int On = O > 0 ? O : 1;
@@ -650,7 +651,7 @@ __device__ __forceinline__ void rescore_body(const DevStep& st, const DevParams&
         s_last = atomicAdd(&sb.counters[1], 1u) == (unsigned)(nblk - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     __threadfence();
     __shared__ int s_r[kResThreads / 32], s_c[kResThreads / 32];
     __shared__ double s_k[kResThreads / 32];
@@ -688,6 +689,7 @@ __device__ __forceinline__ void rescore_body(const DevStep& st, const DevParams&
         sb.hdr[0] = 0;
         sb.counters[1] = 0;
     }
+    return true;
 }
 
 template <bool kGiven>
@@ -711,6 +713,31 @@ __global__ void __launch_bounds__(kResThreads) rescore_batch_kernel(const DevSte
     if (threadIdx.x == 0) s_sb = sbs[scn];
     __syncthreads();
     rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests + scn, s_st.nskip, smem_raw, 0, 1);
+}
+
+// Planning cycle (etp_plan_cycle): what follows the selection in ONE launch.  The survivors of the fp32 selection are
+// re-scored in fp64 by the grid's CTAs (one survivor each, round-robin); the CTA that closes the selection -- CTA 0 when
+// nothing had to be re-scored -- generates the winner's trajectory and writes [BestRec | T | 13 rows] to `combo`, which may
+// be pinned host memory (the cycle's only result: no separate read-back).
+__global__ void __launch_bounds__(kResThreads) cycle_tail_kernel(const DevStep* __restrict__ steps, const __grid_constant__ DevParams pr,
+                                                                const SelectBufs* __restrict__ sbs, BestRec* __restrict__ bests,
+                                                                unsigned char* __restrict__ combo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ DevStep s_st;
+    __shared__ SelectBufs s_sb;
+    __shared__ BestRec s_best;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevStep) / sizeof(int)); i += blockDim.x)
+        reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(steps)[i];
+    if (threadIdx.x == 0) s_sb = sbs[0];
+    __syncthreads();
+    bool closing;
+    if (s_sb.hdr[0] == 0) closing = blockIdx.x == 0;  // uniform over the grid: every CTA reads the count before any can reset it
+    else closing = rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests, s_st.nskip, smem_raw, blockIdx.x, gridDim.x);
+    if (!closing) return;
+    __syncthreads();  // the record thread 0 wrote
+    if (threadIdx.x == 0) s_best = *bests;
+    __syncthreads();
+    best_trajectory_body(s_st, s_best, combo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -772,6 +799,19 @@ cudaError_t launch_rescore_batch(const DevStep* steps, const DevParams& pr, cons
         attr = smem;
     }
     rescore_batch_kernel<<<n_scn, kResThreads, smem, stream>>>(steps, pr, sbs, bests);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cycle_tail(const DevStep* steps, const DevParams& pr, const SelectBufs* sbs, BestRec* bests, unsigned char* combo,
+                              bool refine, int Tmax, int O, cudaStream_t stream) {
+    const size_t smem = refine ? rescore_smem_bytes(Tmax, O) : 0;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(cycle_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    cycle_tail_kernel<<<refine ? 8 : 1, kResThreads, smem, stream>>>(steps, pr, sbs, bests, combo);
     return cudaGetLastError();
 }
 
