@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ETP_B200_LIB selects another build of the same sources (kernel tuning experiments); default: the in-tree library
 LIB_PATH = os.environ.get("ETP_B200_LIB") or os.path.join(HERE, "libetp_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("etp_kernels.cu", "etp_score.cu", "etp_select.cu", "etp_abi.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_harm.cuh", "etp_launch.h")] + [
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("etp_device.cuh", "etp_bvn.cuh", "etp_harm.cuh", "etp_select.cuh", "etp_launch.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "etp_b200.h")]
 
 NUM_WEIGHTS = 14

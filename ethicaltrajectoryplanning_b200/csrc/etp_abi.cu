@@ -1434,18 +1434,23 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     const SelectBufs* d_sb = reinterpret_cast<const SelectBufs*>(dev + o_sb);
     BestRec* d_best = reinterpret_cast<BestRec*>(sdev + s_best);
     unsigned char* d_combo = sdev + s_combo;
-    const int n_launch = c->cycle_split ? 5 + (raw && O > 0 ? 1 : 0) + (refine ? 1 : 0) : 4;
+    const int n_launch = c->cycle_split ? 5 + (raw && O > 0 ? 1 : 0) + (refine ? 1 : 0) : 3;
     const bool timed = c->timing;  // CUDA-event timing of the stages (etp_get_stage_timing): launched one by one then
     const bool staged = c->cyc_ev[0] != nullptr;  // ETP_CYCLE_PROFILE=2
 #define ETP_STAGE_EV(k) do { if (staged) ETP_CUDA(c, cudaEventRecord(c->cyc_ev[k], c->stream)); } while (0)
     // the result lands in pinned host memory straight from the last kernel (unified addressing: the device writes through the
-    // host pointer), so the cycle is one upload and four launches: head | fused scoring | selection | tail
+    // host pointer), so the cycle is one upload and three launches: head | fused scoring + selection | tail
     unsigned char* h_combo = c->cyc_out.p;
     auto enqueue = [&]() -> int {
         ETP_STAGE_EV(0);
         ETP_CUDA(c, cudaMemcpyAsync(dev, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
         ETP_STAGE_EV(1);
-        const BatchArgs ba{d_step, reinterpret_cast<const int*>(dev + o_tscn), reinterpret_cast<const int*>(dev + o_first), tiles, 1};
+        BatchArgs ba{d_step, reinterpret_cast<const int*>(dev + o_tscn), reinterpret_cast<const int*>(dev + o_first), tiles, 1};
+        if (!c->cycle_split) {  // the selection runs in the fused kernel's last CTA
+            ba.sel = d_sb;
+            ba.best = d_best;
+            ba.done = c->counters.as<unsigned>() + 4;
+        }
         if (c->cycle_split) {  // ETP_CYCLE_SPLIT=1: the stages as separate launches (measurement aid)
             if (raw) ETP_CUDA(c, launch_enrich_args(reinterpret_cast<const EnrichArgs*>(dev + o_enr), O, Tp, c->stream));
             ETP_STAGE_EV(2);
@@ -1465,7 +1470,7 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
         ETP_CUDA(c, launch_score(precision, DevStep{}, c->pr, DevOut{}, c->counters.as<unsigned>(), c->num_sms, &c->last_grid, c->stream, &ba, smem));
         if (timed) ETP_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
         ETP_STAGE_EV(5);
-        ETP_CUDA(c, launch_select_batch(d_step, d_sb, d_best, c->counters.as<unsigned>() + 1, 1, c->stream));
+        if (c->cycle_split) ETP_CUDA(c, launch_select_batch(d_step, d_sb, d_best, c->counters.as<unsigned>() + 1, 1, c->stream));
         ETP_STAGE_EV(6);
         if (c->cycle_split) {
             if (refine) ETP_CUDA(c, launch_rescore_batch(d_step, c->pr, d_sb, d_best, 1, Tmax, O, c->stream));

@@ -261,12 +261,17 @@ struct EnrichArgs {
 };
 
 // scenario sweep (etp_plan_batch): the steps of a chunk and the map from the chunk's tiles to them
+struct BestRec;
 struct BatchArgs {
     const DevStep* steps;   // [n_steps] device copies
     const int* tile_scn;    // [n_tiles] scenario of every 32-candidate tile
     const int* tile_first;  // [n_steps] first tile of every scenario
     int n_tiles, n_steps;
     int dbg_min_len;        // experiment knob (ETP_CLUSTER_MINLEN): samples per phase-2a segment in cluster mode, 0 = default
+    // planning cycle (one step, at most one selection block of candidates): the CTA that finishes last runs the selection
+    const void* sel;        // SelectBufs of the step, or null: selection by its own launch
+    BestRec* best;
+    unsigned* done;         // completion counter of the grid (zero between launches)
 };
 
 struct DevOut {

@@ -33,6 +33,7 @@
 #include "etp_device.cuh"
 #include "etp_harm.cuh"
 #include "etp_launch.h"
+#include "etp_select.cuh"
 
 namespace etp {
 
@@ -1485,7 +1486,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 if (out.bd_harm) out.bd_harm[cl] = bd_out;
                 if (out.level) out.level[cl] = (uint8_t)level;
                 if (out.reason) out.reason[cl] = (uint8_t)reason;
-                // selection workspace (etp_select.cu)
+                // selection workspace (etp_select.cuh)
                 st.ws_cost[cl] = c[ETP_C_TOTAL];
                 st.ws_meta[cl] = live ? (uint8_t)(level | (amb ? SEL_AMB : 0)) : (uint8_t)SEL_SKIPPED;
                 if (st.refine) {
@@ -1498,6 +1499,30 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         ETP_PCLK(7);
         // no barrier here: warp 0 reads only p1 / p3 / ff; p1 / ff are next written after barrier (a) of the next
         // tile, p3 (aliasing the ego samples) after barrier (a) as well
+    }
+    if (kBatch && ba.sel) {
+        // planning cycle: the CTA that finishes last has every candidate's workspace entry in front of it and runs the
+        // selection right here (one block of kSelThreads == kThreads threads) instead of in a launch of its own
+        static_assert(kSelThreads == kThreads, "the fused kernel's CTA runs select_body as it is");
+        __shared__ int s_closing;
+        __syncthreads();  // this CTA's workspace entries are written (warp 0)
+        if (tid == 0) {
+            __threadfence();
+            s_closing = atomicAdd(ba.done, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_closing) {
+            __threadfence();
+            const int* src = reinterpret_cast<const int*>(ba.steps);
+            for (int i = tid; i < (int)(sizeof(DevStep) / sizeof(int)); i += kThreads) reinterpret_cast<int*>(&s_st)[i] = __ldg(src + i);
+            __shared__ SelectBufs s_sb;
+            if (tid == 0) {
+                s_sb = *reinterpret_cast<const SelectBufs*>(ba.sel);
+                *ba.done = 0;
+            }
+            __syncthreads();
+            select_body(s_st, s_sb, ba.best, s_st.nskip, &counters[1], 0, 0, 0, 1);
+        }
     }
 #ifdef ETP_PHASE_CLOCK
     if (tid == 0 && blockIdx.x == 0)

@@ -128,9 +128,11 @@ class FrenetPlanner:
                 self._static_dicts = (tuple(predictions), shapes, ori0, vel0, types)
             self._resident_types = types
             self._resident_static = (shapes, ori0, vel0)  # what the enrichment on the device was given (tests replay it on the host)
-            self.ctx.ensure_params(self.params_dict, self.p, self.mode)
-            # fused path without a log: the record is only prepared here and travels with the step (ScoringContext.plan_cycle)
+            # fused path without a log: the record is only prepared here and travels with the step (ScoringContext.plan_cycle,
+            # which also makes sure of the parameters)
             cycle = not self.materialize and self.columnar_logger is None
+            if not cycle:
+                self.ctx.ensure_params(self.params_dict, self.p, self.mode)
             self._raw_record = self.ctx.set_raw_predictions(predictions, shapes, ori0, vel0, types, self.scenario.dt,
                                                             np.asarray(self.ego_state.position), self.ego_state.orientation,
                                                             upload=not cycle)

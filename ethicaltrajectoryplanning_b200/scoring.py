@@ -399,8 +399,12 @@ class ScoringContext:
             vals = list(predictions.values())
             Tp = fast["Tp"]
             if all(len(p["pos_list"]) == Tp for p in vals):
-                np.stack([p["pos_list"] for p in vals], out=fast["pos"].reshape(fast["pos_shape"]))
-                np.stack([p["cov_list"] for p in vals], out=fast["cov"].reshape(fast["cov_shape"]))
+                try:  # arrays of one shape (the usual predictor output): one concatenate each into the resident arrays
+                    np.concatenate([p["pos_list"] for p in vals], out=fast["pos2"])
+                    np.concatenate([p["cov_list"] for p in vals], out=fast["cov2"])
+                except (ValueError, TypeError):  # lists, or another layout of the same data
+                    np.stack([p["pos_list"] for p in vals], out=fast["pos"].reshape(fast["pos_shape"]))
+                    np.stack([p["cov_list"] for p in vals], out=fast["cov"].reshape(fast["cov_shape"]))
                 r = fast["struct"]
                 r.ego_x, r.ego_y, r.ego_orientation = float(ego_position[0]), float(ego_position[1]), float(ego_orientation)
                 if upload:
@@ -464,6 +468,8 @@ class ScoringContext:
             self._raw_fast = dict(refs=(shapes, init_orientation, init_velocity, obstacle_types), dt=dt,
                                   margins=(safety_margin_length, safety_margin_width), oids=tuple(oids), Tp=Tp, pos=pos, cov=cov,
                                   pos_shape=(O,) + np.shape(p0["pos_list"]), cov_shape=(O,) + np.shape(p0["cov_list"]), struct=r,
+                                  pos2=pos.reshape((O * Tp,) + np.shape(p0["pos_list"])[1:]),
+                                  cov2=cov.reshape((O * Tp,) + np.shape(p0["cov_list"])[1:]),
                                   keep=(lens, length, width, ori0, vel0, mass, prot))
         return r
 
@@ -871,6 +877,9 @@ class ScoringContext:
             self.set_spline(CubicSpline2D.from_foreign(step.csp))
             self._spline_key = (step.csp, self._spline_print(step.csp))
         self.ensure_road_boundary(getattr(step, "road_boundary", None))
+        if (raw is not None and step.ext_level is None and step.bd_harm is None and getattr(step, "cost_factor_list", None) is None
+                and getattr(step, "goal", None) is None):
+            return self._plan_cycle_resident(step, raw)
         s, keep, n = self.make_step_struct(step)
         cy = _abi.Cycle()
         cy.step = C.pointer(s)
@@ -903,6 +912,43 @@ class ScoringContext:
         best = dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored, list_index=b.list_index,
                     key_hi=b.key_hi, key_lo=b.key_lo)
         return best, self._trajectory_dict(f, int(T.value), step.dt)
+
+    def _plan_cycle_resident(self, step, raw):
+        """``plan_cycle`` of the closed loop proper (raw predictions, nothing pre-evaluated on the host): the records handed to
+        the library live as long as the grid keeps its shape -- the sample lists are copied into their arrays, the six state
+        scalars are set, nothing is allocated but the result rows."""
+        nv, nt, nd = len(step.v_list), len(step.t_list), len(step.d_list)
+        cs = self.__dict__.get("_cycle_state")
+        if cs is None or cs["shape"] != (nv, nt, nd):
+            v, t, d = np.empty(nv), np.empty(nt), np.empty(nd)
+            n = np.empty(nt, dtype=np.int32)
+            st = _abi.Step()
+            st.v_list, st.nv, st.t_list, st.nt, st.d_list, st.nd, st.n_samples = _dptr(v), nv, _dptr(t), nt, _dptr(d), nd, _iptr(n)
+            st.c_begin, st.c_end, st.shard_index, st.shard_count = 0, nv * nt * nd, 0, 1
+            cy = _abi.Cycle()
+            cy.step = C.pointer(st)
+            cs = self._cycle_state = dict(shape=(nv, nt, nd), v=v, t=t, d=d, n=n, st=st, cy=cy, best=_abi.Best(), T=C.c_int32(0),
+                                          tkey=None, Tmax=0)
+        cs["v"][:] = step.v_list
+        cs["t"][:] = step.t_list
+        cs["d"][:] = step.d_list
+        tkey = (cs["t"].tobytes(), step.dt)
+        if tkey != cs["tkey"]:  # samples per horizon, len(np.arange(0, tT, dt)) (frenet_functions.py:267)
+            cs["n"][:] = [len(np.arange(0.0, tT, step.dt)) for tT in cs["t"]]
+            cs["tkey"], cs["Tmax"] = tkey, int(cs["n"].max())
+        st, cy, b, T, Tmax = cs["st"], cs["cy"], cs["best"], cs["T"], cs["Tmax"]
+        st.c_s, st.c_s_d, st.c_s_dd, st.c_d, st.c_d_d, st.c_d_dd = step.c_s, step.c_s_d, step.c_s_dd, step.c_d, step.c_d_d, step.c_d_dd
+        st.dt, st.v_thr = step.dt, step.v_thr
+        st.velocity_cost_mode, st.velocity_target, st.cost_factor = int(step.velocity_cost_mode), float(step.velocity_target), float(step.cost_factor)
+        if cs.get("raw") is not raw:
+            cy.raw = C.pointer(raw)
+            cs["raw"] = raw
+        self._last_tmax, self.last_dt = Tmax, step.dt
+        f = np.empty((_abi.NUM_FIELDS, Tmax), dtype=np.float64)
+        self._check(self.lib.etp_plan_cycle(self.h, C.byref(cy), self.precision, C.byref(b), _dptr(f), C.byref(T)))
+        best = dict(index=b.index, level=b.level, cost=b.cost, n_scored=b.n_scored, list_index=b.list_index,
+                    key_hi=b.key_hi, key_lo=b.key_lo)
+        return best, self._trajectory_dict(f, T.value, step.dt)
 
     @staticmethod
     def _trajectory_dict(f, T, dt):

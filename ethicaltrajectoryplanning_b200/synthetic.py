@@ -29,6 +29,9 @@ def obstacle_mass(type_name: str, size: float) -> float:
     return _FIXED_MASS.get(type_name, 0.0)
 
 
+_RAMPS = {}
+
+
 def get_v_list(v_min, v_max, v_cur, v_goal_min=None, v_goal_max=None, n_samples=3, mode="linspace"):
     """End-velocity samples, ``linspace`` mode of frenet_functions.py:760-807.
 
@@ -43,10 +46,30 @@ def get_v_list(v_min, v_max, v_cur, v_goal_min=None, v_goal_max=None, n_samples=
     if mode != "linspace":
         raise ValueError("only the linspace v-list mode is part of the scored path")
     if v_goal_min is None:
-        v_list = np.linspace(v_min, v_max, n_samples - 1)
+        lo, hi = v_min, v_max
     else:
-        v_list = np.linspace(max(min(v_goal_min, v_min), 0.001), max(v_goal_max, v_max), n_samples - 1)
-    return np.append(v_list, v_cur)
+        lo, hi = max(min(v_goal_min, v_min), 0.001), max(v_goal_max, v_max)
+    # np.append(np.linspace(lo, hi, n_samples - 1), v_cur) without the two calls' overhead (a planning cycle pays for it every
+    # 0.1 s): numpy's own arithmetic, arange(n) * step + start with the last sample set to the stop value
+    n = n_samples - 1
+    out = np.empty(n_samples, dtype=np.float64)
+    if n == 1:
+        out[0] = lo
+    elif n > 1:
+        lo, hi = float(lo), float(hi)
+        step = (hi - lo) / (n - 1)
+        ramp = _RAMPS.get(n)
+        if ramp is None:
+            ramp = _RAMPS[n] = np.arange(0, n, dtype=np.float64)
+        if step == 0.0:
+            np.multiply(ramp, hi - lo, out=out[:n])
+            out[:n] /= n - 1
+        else:
+            np.multiply(ramp, step, out=out[:n])
+        out[:n] += lo
+        out[n - 1] = hi
+    out[n] = v_cur
+    return out
 
 
 def planner_v_list(v_cur, t_list, vehicle, n_samples, v_goal_min=None, v_goal_max=None):
