@@ -1267,13 +1267,17 @@ int plan_chunk_fused(etp_ctx* c, int n, const etp_scenario* sc, int precision, B
 // ---------------------------------------------------------------------------------------------
 // etp_plan_cycle: one closed-loop cycle as "a sweep of one scenario" whose launch sequence is a captured graph
 // ---------------------------------------------------------------------------------------------
+// a planning cycle's selection runs in ONE CTA (the fused kernel's last), block after block: bounded so that it stays short
+constexpr long long kCycleMaxCandidates = 16 * 4096;
+
 bool cycle_fusable(const etp_ctx* c, const etp_cycle& cy) {
     if (!c->have_spline || !cy.step) return false;
     const etp_step& p = *cy.step;
     if (p.ext_level || p.bd_harm || p.cost_factor_list || p.goal) return false;
     if (p.nv < 1 || p.nt < 1 || p.nd < 1 || !p.v_list || !p.t_list || !p.d_list || !p.n_samples) return false;
     const long long dense = (long long)p.nv * p.nt * p.nd;
-    if (dense > select_chunk() || p.c_begin != 0 || p.c_end != dense || p.shard_count > 1) return false;
+    if (c->cycle_split && dense > select_chunk()) return false;  // the measurement aid launches the one-block selection
+    if (dense > kCycleMaxCandidates || p.c_begin != 0 || p.c_end != dense || p.shard_count > 1) return false;
     for (int i = 0; i < p.nt; ++i)
         if (p.n_samples[i] < 2 || p.n_samples[i] > 256) return false;
     if (cy.raw) {
@@ -1329,6 +1333,7 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     const size_t s_wc = sc.take(sizeof(double) * Cs), s_wb = sc.take(sizeof(float) * Cs), s_wm = sc.take(Cs), s_wbd = sc.take(sizeof(double) * Cs);
     const size_t s_wgf = sc.take(Cs), s_blocks = sc.take(select_blocks_bytes(Cs)), s_list = sc.take(sizeof(int) * Cs);
     const size_t s_res = sc.take(rescore_rec_bytes(Cs)), s_best = sc.take(sizeof(BestRec));
+    const size_t s_state = sc.take(64);  // SelState: hand-over between the two halves of a selection over several blocks
     const size_t combo_bytes = sizeof(BestRec) + 8 + sizeof(double) * ETP_NUM_FIELDS * Tmax;
     const size_t s_combo = sc.take(combo_bytes);
     ETP_CUDA(c, c->cyc_dev.reserve(in_bytes + sc.off));
@@ -1423,7 +1428,7 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     SelectBufs sb;
     sb.blocks = sdev + s_blocks; sb.list = reinterpret_cast<int*>(sdev + s_list); sb.res = sdev + s_res;
     sb.hdr = reinterpret_cast<int*>(dev + o_small); sb.counters = reinterpret_cast<unsigned*>(dev + o_small + 16);
-    sb.stats = select_bufs(c).stats; sb.state = nullptr;
+    sb.stats = select_bufs(c).stats; sb.state = sdev + s_state;
     memcpy(h + o_sb, &sb, sizeof(sb));
     *reinterpret_cast<int*>(h + o_first) = 0;
     for (int k = 0; k < tiles; ++k) reinterpret_cast<int*>(h + o_tscn)[k] = 0;

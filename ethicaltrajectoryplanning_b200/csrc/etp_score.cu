@@ -1521,7 +1521,18 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 *ba.done = 0;
             }
             __syncthreads();
-            select_body(s_st, s_sb, ba.best, s_st.nskip, &counters[1], 0, 0, 0, 1);
+            // more candidates than one selection block holds: this CTA walks the blocks one after the other (the records
+            // the blocks exchange go through global memory either way)
+            const int nblk = (s_st.n_local + kSelChunk - 1) / kSelChunk;
+            for (int b = 0; b < (nblk > 0 ? nblk : 1); ++b) {
+                select_body(s_st, s_sb, ba.best, s_st.nskip, &counters[1], 0, 0, b, nblk > 0 ? nblk : 1);
+                __syncthreads();
+            }
+            if (nblk > 1 && s_st.refine)
+                for (int b = 0; b < nblk; ++b) {
+                    select_collect_body(s_st, s_sb, ba.best, s_st.nskip, &counters[1], 0, 0, b, nblk);
+                    __syncthreads();
+                }
         }
     }
 #ifdef ETP_PHASE_CLOCK

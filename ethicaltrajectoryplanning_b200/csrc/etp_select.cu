@@ -23,53 +23,10 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     select_body(st, sb, best_out, nskip, tile_counter, given, always_rescore, blockIdx.x, gridDim.x);
 }
 
-// Second half of the selection of a step with several blocks: every block whose record says it can hold a survivor scans
-// its own chunk; the last block to finish closes the list (one survivor, nothing ambiguous, no other shard: the winner).
 __global__ void __launch_bounds__(kSelThreads) select_collect_kernel(const __grid_constant__ DevStep st, const SelectBufs sb,
                                                                     BestRec* __restrict__ best_out, const int* __restrict__ nskip,
                                                                     unsigned* __restrict__ tile_counter, int given, int always_rescore) {
-    __shared__ int s_last;
-    __shared__ double s_scratch[kSelThreads / 32];
-    const SelState* state = reinterpret_cast<const SelState*>(sb.state);
-    if (!state->pending) return;  // select_kernel had the answer already (and has re-armed everything)
-    const int tid = threadIdx.x, Cs = st.n_local, hi = state->hi;
-    const double thr = state->thr;
-    const SelBlock* blocks = reinterpret_cast<const SelBlock*>(sb.blocks);
-    const SelBlock mine = blocks[blockIdx.x];
-    if (hi >= 0 && mine.rank_max == hi && mine.lower <= thr) {
-        const int bb = blockIdx.x * kSelChunk;
-        for (int k = 0; k < kSelPer; ++k) {
-            const int cl = bb + k * kSelThreads + tid;
-            if (cl >= Cs) continue;
-            const unsigned char m = st.ws_meta[cl];
-            if (m == SEL_SKIPPED || (m & SEL_AMB) || level_rank(m) != hi) continue;
-            if (order_cost(st.ws_cost[cl]) - (double)st.ws_bound[cl] <= thr) sb.list[atomicAdd(&sb.hdr[2], 1)] = cl;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        s_last = atomicAdd(&sb.counters[0], 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int count = *reinterpret_cast<volatile int*>(&sb.hdr[2]);
-    const bool final_one = count == 1 && state->n_amb == 0 && !always_rescore;
-    if (final_one) {
-        const int cl = *reinterpret_cast<volatile int*>(&sb.list[0]);
-        const int index = dense_of(st, given != 0, cl);
-        const int li = list_index_of(st, nskip, given != 0, index, s_scratch);
-        if (tid == 0) write_best(best_out, (int)(st.ws_meta[cl] & 63), st.ws_cost[cl], index, state->n_scored, li);
-    }
-    if (tid == 0) {
-        sb.hdr[0] = final_one ? 0 : count;
-        sb.hdr[1] = state->n_scored;
-        sb.hdr[2] = 0;
-        sb.counters[0] = 0;
-        sb.counters[1] = 0;
-        if (tile_counter) *tile_counter = 0;
-    }
+    select_collect_body(st, sb, best_out, nskip, tile_counter, given, always_rescore, blockIdx.x, gridDim.x);
 }
 
 // scenario sweep: one block per scenario (at most kSelChunk candidates each)

@@ -77,6 +77,28 @@ __device__ __forceinline__ void write_best(BestRec* out, int level, double cost,
     *out = b;
 }
 
+// Survivors that are one and the same computation: the current velocity is appended to the linspace of end velocities
+// (frenet_functions.py:760-807) and coincides with a sample whenever the ego drives at a limit of the range, so two profiles
+// -- and with them whole rows of candidates -- are bit-identical in every input.  Whatever their exact cost, the first in
+// generation order wins (stable sort, frenet_planner.py:457).  Returns that column if every survivor duplicates it, else -1.
+// One thread; `count` is small.
+__device__ inline int duplicate_winner(const DevStep& st, const volatile int* list, int count) {
+    if (st.ext_level || st.bd_harm || st.factor_list) return -1;  // per-candidate inputs of the host
+    int m = list[0];
+    for (int i = 1; i < count; ++i) m = min(m, list[i]);
+    const int klm = m / st.nd, idm = m - klm * st.nd;
+    const int pm = st.p_begin + st.shard_index + klm * st.shard_count;
+    const double vm = st.v_list[pm / st.nt], tm = st.t_list[pm % st.nt];
+    for (int i = 0; i < count; ++i) {
+        const int cl = list[i];
+        if (cl == m) continue;
+        const int kl = cl / st.nd, id = cl - kl * st.nd;
+        const int p = st.p_begin + st.shard_index + kl * st.shard_count;
+        if (id != idm || st.v_list[p / st.nt] != vm || st.t_list[p % st.nt] != tm) return -1;
+    }
+    return m;
+}
+
 // ---------------------------------------------------------------------------------------------
 // select_kernel
 // ---------------------------------------------------------------------------------------------
@@ -89,7 +111,7 @@ __device__ __forceinline__ void select_body(const DevStep& st, const SelectBufs&
     __shared__ int s_i[kSelThreads / 32];
     __shared__ double s_u[kSelThreads / 32], s_l[kSelThreads / 32];
     __shared__ int s_a[kSelThreads / 32];
-    __shared__ int s_rank, s_last, s_cnt, s_nsc, s_namb;
+    __shared__ int s_rank, s_last, s_cnt, s_nsc, s_namb, s_dup;
     __shared__ double s_scratch[kSelThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Cs = st.n_local;
@@ -241,6 +263,11 @@ __device__ __forceinline__ void select_body(const DevStep& st, const SelectBufs&
         }
         __syncthreads();
         if (s_cnt == 1 && n_amb == 0 && !always_rescore) done_cl = sb.list[0];
+        else if (s_cnt > 1 && s_cnt <= 64 && n_amb == 0 && !always_rescore && !given) {
+            if (tid == 0) s_dup = duplicate_winner(st, sb.list, s_cnt);
+            __syncthreads();
+            if (s_dup >= 0) done_cl = s_dup;
+        }
     }
     if (done_cl != -2) {
         const int index = done_cl < 0 ? -1 : dense_of(st, given != 0, done_cl);
@@ -257,6 +284,62 @@ __device__ __forceinline__ void select_body(const DevStep& st, const SelectBufs&
         sb.counters[0] = 0;  // re-arm
         sb.counters[1] = 0;
         if (tile_counter) *tile_counter = 0;  // the fused kernel's tile counter
+    }
+}
+
+// Second half of the selection of a step with several blocks: every block whose record says it can hold a survivor scans
+// its own chunk; the last block to finish closes the list (one survivor, nothing ambiguous, no other shard: the winner).
+__device__ __forceinline__ void select_collect_body(const DevStep& st, const SelectBufs& sb, BestRec* __restrict__ best_out,
+                                                    const int* __restrict__ nskip, unsigned* __restrict__ tile_counter, int given,
+                                                    int always_rescore, const int blk, const int nblk) {
+    __shared__ int s_last;
+    __shared__ double s_scratch[kSelThreads / 32];
+    const SelState* state = reinterpret_cast<const SelState*>(sb.state);
+    if (!state->pending) return;  // select_kernel had the answer already (and has re-armed everything)
+    const int tid = threadIdx.x, Cs = st.n_local, hi = state->hi;
+    const double thr = state->thr;
+    const SelBlock* blocks = reinterpret_cast<const SelBlock*>(sb.blocks);
+    const SelBlock mine = blocks[blk];
+    if (hi >= 0 && mine.rank_max == hi && mine.lower <= thr) {
+        const int bb = blk * kSelChunk;
+        for (int k = 0; k < kSelPer; ++k) {
+            const int cl = bb + k * kSelThreads + tid;
+            if (cl >= Cs) continue;
+            const unsigned char m = st.ws_meta[cl];
+            if (m == SEL_SKIPPED || (m & SEL_AMB) || level_rank(m) != hi) continue;
+            if (order_cost(st.ws_cost[cl]) - (double)st.ws_bound[cl] <= thr) sb.list[atomicAdd(&sb.hdr[2], 1)] = cl;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&sb.counters[0], 1u) == (unsigned)(nblk - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int count = *reinterpret_cast<volatile int*>(&sb.hdr[2]);
+    bool final_one = count == 1 && state->n_amb == 0 && !always_rescore;
+    int cl_one = final_one ? *reinterpret_cast<volatile int*>(&sb.list[0]) : -1;
+    if (count > 1 && count <= 64 && state->n_amb == 0 && !always_rescore && !given) {  // survivors that are one computation
+        __shared__ int s_dup;
+        if (tid == 0) s_dup = duplicate_winner(st, sb.list, count);
+        __syncthreads();
+        if (s_dup >= 0) { final_one = true; cl_one = s_dup; }
+    }
+    if (final_one) {
+        const int cl = cl_one;
+        const int index = dense_of(st, given != 0, cl);
+        const int li = list_index_of(st, nskip, given != 0, index, s_scratch);
+        if (tid == 0) write_best(best_out, (int)(st.ws_meta[cl] & 63), st.ws_cost[cl], index, state->n_scored, li);
+    }
+    if (tid == 0) {
+        sb.hdr[0] = final_one ? 0 : count;
+        sb.hdr[1] = state->n_scored;
+        sb.hdr[2] = 0;
+        sb.counters[0] = 0;
+        sb.counters[1] = 0;
+        if (tile_counter) *tile_counter = 0;
     }
 }
 

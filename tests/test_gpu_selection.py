@@ -164,6 +164,14 @@ def test_bit_identical_duplicates_go_to_the_lower_index():
             total = res.numpy()["cost"][12]
             dup = (len(step.v_list) - 1) * len(step.t_list) * len(step.d_list) + ref["best"]["index"] % len(step.d_list)
             assert total[dup] == total[ref["best"]["index"]]
+            # survivors that are one and the same computation are settled by generation order, without an fp64 re-scoring --
+            # unless a third candidate is within the fp32 bound as well
+            before = ctx.debug_counters()["rescored"]
+            best, _ = ctx.plan_winner(step)
+            assert best["index"] == ref["best"]["index"] and best["list_index"] == ref["best"]["list_index"]
+            assert ctx.debug_counters()["rescored"] - before in (0, 3)
+            best, _ = ctx.plan_cycle(step)
+            assert best["index"] == ref["best"]["index"] and best["list_index"] == ref["best"]["list_index"]
         finally:
             ctx.close()
 

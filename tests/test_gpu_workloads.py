@@ -198,6 +198,15 @@ def test_plan_cycle_replays_a_graph_and_equals_the_step_by_step_path():
                 want_best, want_traj = ref_ctx.plan_winner(step)
                 assert best["index"] == want_best["index"] and best["cost"] == want_best["cost"], (k, best, want_best)
                 np.testing.assert_array_equal(traj["x_m"], want_traj["x_m"])
+            # more candidates than one selection block holds (100 x 100): the closing CTA walks the blocks
+            for seed in (3, 4, 5):
+                step = make_step("cfg2", seed=200 + seed, v0=6.0 + 3 * seed)
+                step.csp = csp0
+                best, traj = ctx.plan_cycle(step)
+                want_best, want_traj = ref_ctx.plan_winner(step)
+                assert (best["index"], best["level"], best["list_index"], best["n_scored"], best["cost"]) == \
+                    (want_best["index"], want_best["level"], want_best["list_index"], want_best["n_scored"], want_best["cost"])
+                np.testing.assert_array_equal(traj["y_m"], want_traj["y_m"])
             assert ctx.debug_counters()["bound_violations"] == 0
         finally:
             ctx.close()
