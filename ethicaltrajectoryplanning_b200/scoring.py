@@ -834,6 +834,25 @@ class ScoringContext:
                                                      list_index=b.list_index, key_hi=b.key_hi, key_lo=b.key_lo))
         return out
 
+    def plan_batch_pipelined(self, steps, chunk=512):
+        """``plan_batch`` over ``steps`` in chunks of ``chunk`` scenarios with the host work overlapped: the prediction dicts
+        of chunk k + 1 are packed on the calling thread while the library call of chunk k (ctypes releases the GIL for its
+        duration) runs on a worker thread.  Same results, in order."""
+        if not steps:
+            return []
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.set_params(steps[0].params, steps[0].vehicle, steps[0].mode)
+        out, pending = [], None
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            for i in range(0, len(steps), chunk):
+                packed = self.pack_scenarios(steps[i:i + chunk])
+                if pending is not None:
+                    out += pending.result()
+                pending = pool.submit(self.plan_batch, None, packed)
+            out += pending.result()
+        return out
+
     @staticmethod
     def local_candidates(s):
         """Rows of the output tensors for a step struct: (profiles of this shard) * nd."""

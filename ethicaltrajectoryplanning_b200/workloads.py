@@ -59,6 +59,19 @@ def run_sweep_batched(ctx, scenario_ids, weights="weights_ethical.json", chunk=2
     return out, sum(b["n_scored"] for b in bests), t_pack, t_run
 
 
+def run_sweep_pipelined(ctx, scenario_ids, weights="weights_ethical.json", chunk=500):
+    """The sweep from prediction dicts to winners with packing and scoring overlapped (``plan_batch_pipelined``).  Returns
+    (results, candidates, wall-clock seconds from the first dict to the last winner)."""
+    steps = [st for i in scenario_ids for _, st in sweep_steps(1, i, weights)]
+    if not steps:
+        return [], 0, 0.0
+    t0 = time.perf_counter()
+    bests = ctx.plan_batch_pipelined(steps, chunk=chunk)
+    t = time.perf_counter() - t0
+    out = [(sid, b["index"], b["level"], b["cost"]) for sid, b in zip(scenario_ids, bests)]
+    return out, sum(b["n_scored"] for b in bests), t
+
+
 class MovingObstacles:
     """Predictor stand-in of the closed loop: constant-velocity Gaussian predictions that advance one sample per
     cycle (``predictor.step(time_step=...)`` contract of frenet_planner.py:386-390).  Like a real predictor it returns

@@ -31,6 +31,9 @@ def test_batched_sweep_equals_the_scenario_by_scenario_sweep():
     assert n1 == n2 and len(one) == len(bat) == len(ids)
     for a, b in zip(one, bat):
         assert a[:3] == b[:3] and a[3] == b[3], (a, b)  # same kernels, same inputs: identical winners and costs
+    # packing of a chunk on this thread while the chunk before it is scored on a worker thread: the same results, in order
+    pip, n3, _ = workloads.run_sweep_pipelined(ctx, ids, chunk=7)
+    assert n3 == n1 and pip == bat
 
 
 def test_fused_sweep_of_2000_scenarios_equals_the_scenario_by_scenario_sweep(monkeypatch):
