@@ -344,6 +344,11 @@ int etp_set_params(etp_ctx* c, const etp_params* p) {
         ETP_FAIL(c, ETP_ERR_INVALID, "n_angle_thresholds out of range");
     if (p->planner_mode < ETP_MODE_RISK || p->planner_mode > ETP_MODE_GROUND_TRUTH) ETP_FAIL(c, ETP_ERR_INVALID, "planner_mode");
     DevParams& d = c->pr;
+    // the packed obstacle tile holds the mass ratios m_o / (m_e + m_o) (harm_estimation.py:327-328) and, for raw predictions,
+    // the responsibility flag under the Q9 rule: a change of either makes the tile stale -- the obstacles have to be set again
+    if (c->have_params && c->have_obs && c->has_pred &&
+        (d.veh_m != p->veh_m || ((d.relaxed ^ p->relaxed_quirks) & ETP_RELAX_Q9_VIEW_CONE)))
+        c->have_obs = false;
     for (int i = 0; i < ETP_NUM_WEIGHTS; ++i) d.w[i] = p->weights[i];
     d.planner_mode = p->planner_mode;
     d.mahalanobis = p->fast_prob_mahalanobis;
@@ -759,7 +764,11 @@ static int stage_goal(etp_ctx* c, const etp_goal* g, double dt, int Tmax, DevGoa
     }
     // host-side containment of the ego position: same function, same fp64 arithmetic as the device
     d.ego_in_goal = !d.has_area || point_in_goal(d, g->poly_start, g->vertices, g->circles, g->ego_x, g->ego_y);
-    if (!g->has_centers) {
+    if (g->has_centers < 0 && c->pr.w[ETP_W_VELOCITY] > 0.0)  // velocity_costs runs only with a positive weight (:279)
+        ETP_FAIL(c, ETP_ERR_UNSUPPORTED,
+                 "the goal has a position but no centre point: the reference's velocity cost is the mean of an empty list (NaN) here "
+                 "(calc_trajectory_cost.py:473-497)");
+    if (g->has_centers <= 0) {
         d.vel_kind = 3;  // "no velocity can be proposed" (:489-490)
     } else {
         const double remaining = (double)(g->time_end - g->ego_time_step) * dt;  // t = 0: considered = ego time step

@@ -152,6 +152,8 @@ def make_goal(goal, keep):
         # distance() of helper_functions.py:114 is the Euclidean norm; np.mean over the list (:492-497)
         g.has_centers = 1
         g.avg_goal_distance = float(np.mean([np.linalg.norm(np.asarray(c, dtype=np.float64) - pos) for c in goal.goal_centers]))
+    elif goal.goal_centers is not None:
+        g.has_centers = -1  # a goal position without centre points: NaN in the reference (:492-497), refused by the library
     # goal positions of calc_dist_to_goal_pos (calc_trajectory_cost.py:760-803)
     lines = [np.ascontiguousarray(l, dtype=np.float64).reshape(-1, 2) for l in (getattr(goal, "goal_lines", None) or [])]
     if lines:

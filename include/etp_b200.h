@@ -188,7 +188,9 @@ typedef struct {
     int32_t time_start, time_end;
     int32_t ego_time_step;          /* ego_state.time_step */
     double ego_x, ego_y;            /* ego_state.position */
-    int32_t has_centers;            /* velocity_costs found goal centre points (:473-489); 0: cost 0 outside the goal */
+    int32_t has_centers;            /* velocity_costs found goal centre points (:473-489); 0: survival scenario, cost 0 outside the
+                                     * goal; -1: a goal position without a centre point -- the reference averages an empty list
+                                     * (NaN) there, the call fails with ETP_ERR_UNSUPPORTED */
     double avg_goal_distance;       /* mean distance from ego_state.position to them (:492-497) */
     /* calc_dist_to_goal_pos (calc_trajectory_cost.py:760-803; weights['dist_to_goal_pos'] > 0): distance of the trajectory's
      * last position to the closest goal position.  Goal given in lanelets: their centre lines as polylines (closest point
@@ -288,7 +290,10 @@ const char* etp_version(void);
  * (void*)-1 restores the context's own non-blocking stream. */
 int etp_set_stream(etp_ctx* ctx, void* cuda_stream);
 
-/* replaces params_dict / vehicle_params arguments of sort_frenet_trajectories (frenet_functions.py:477-495) */
+/* replaces params_dict / vehicle_params arguments of sort_frenet_trajectories (frenet_functions.py:477-495).
+ * The packed obstacle tile depends on veh_m (mass ratios, harm_estimation.py:327-328) and, for raw predictions, on
+ * ETP_RELAX_Q9_VIEW_CONE: when a later call changes either, the obstacles have to be set again -- etp_plan_step returns
+ * ETP_ERR_STATE until they are, instead of scoring against a stale tile. */
 int etp_set_params(etp_ctx* ctx, const etp_params* params);
 
 /* replaces the `csp` argument of calc_frenet_trajectories (frenet_functions.py:218,278):

@@ -144,3 +144,26 @@ def test_dist_to_goal_pos_on_the_device():
             ctx.plan(step)
     finally:
         ctx.close()
+
+
+def test_goal_position_without_a_centre_is_refused():
+    """A goal state whose position has no centre point and no goal lanelets: the reference's velocity cost averages an empty
+    list of distances (calc_trajectory_cost.py:473-497, NaN).  The library refuses the step instead of diverging silently --
+    unless the velocity weight is zero, where the reference never evaluates that term (:279)."""
+    import copy
+    import dataclasses
+
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+
+    name, step = CASES[0]
+    step = copy.deepcopy(step)
+    step.goal = dataclasses.replace(step.goal, goal_centers=[], goal_points=None, goal_lines=None)
+    ctx = ScoringContext(0, "fp32")
+    try:
+        assert step.params["weights"]["velocity"] > 0.0
+        with pytest.raises(NotImplementedError, match="no centre point"):  # ETP_ERR_UNSUPPORTED
+            ctx.plan(step, materialize=False)
+        step.params["weights"]["velocity"] = 0.0
+        assert ctx.plan(step, materialize=False).best["index"] >= 0
+    finally:
+        ctx.close()

@@ -214,3 +214,29 @@ def test_plan_cycle_replays_a_graph_and_equals_the_step_by_step_path():
         finally:
             ctx.close()
             ref_ctx.close()
+
+
+def test_a_new_vehicle_mass_invalidates_the_packed_obstacles():
+    """The tile holds m_o / (m_e + m_o): etp_set_params with another vehicle mass after etp_set_obstacles makes
+    etp_plan_step fail loudly until the obstacles are set again, and the step then equals a fresh context's."""
+    import copy
+
+    from ethicaltrajectoryplanning_b200.scoring import EtpError, ScoringContext
+    from ethicaltrajectoryplanning_b200.synthetic import make_step
+
+    step = make_step("cfg1", seed=3)
+    heavy = copy.deepcopy(step)
+    heavy.vehicle.m = step.vehicle.m * 1.5
+    ctx, fresh = ScoringContext(0, "fp32"), ScoringContext(0, "fp32")
+    try:
+        ctx.plan(step, materialize=False)
+        ctx.set_params(heavy.params, heavy.vehicle, heavy.mode)   # the obstacles of `step` stay packed with the old mass
+        s, keep, n = ctx.make_step_struct(heavy)
+        with pytest.raises(EtpError):
+            ctx.launch(s, None)
+        got = ctx.plan(heavy, materialize=False).best                 # configure() sets the predictions again
+        want = fresh.plan(heavy, materialize=False).best
+        assert (got["index"], got["level"], got["cost"]) == (want["index"], want["level"], want["cost"])
+    finally:
+        ctx.close()
+        fresh.close()
