@@ -255,7 +255,10 @@ __device__ __forceinline__ float collision_prob(const Tab<float>& pr, float ddx,
         return nine_rectangles<float>(pr, r, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
     }
     if (cls == RC_FP64) {
-        atomicAdd(&g_fallback_evals, 1ull);
+        {   // diagnostics (etp_debug_counters): one atomic per warp -- cls is warp-uniform, the active lanes are counted by their leader
+            const unsigned act = __activemask();
+            if ((int)(threadIdx.x & 31) == __ffs(act) - 1) atomicAdd(&g_fallback_evals, (unsigned long long)__popc(act));
+        }
         return nine_rectangles<float>(pr, RectFallbackF{}, ddx, ddy, c, s, g.z, g.w, p.x, p.y, p.z);
     }
     const float4 a = __ldg(nd), b = __ldg(nd + 1), cc = __ldg(nd + 2), d = __ldg(nd + 3), f = __ldg(nd + 4);

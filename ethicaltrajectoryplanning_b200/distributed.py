@@ -2,8 +2,10 @@
 
 Two shardings, as the path offers them:
 
-* candidate sharding inside one planning step: the dense (v,t,d) index space is split into
-  contiguous ranges of whole (v,t) profiles; every rank scores its range with the fused kernel
+* candidate sharding inside one planning step: whole (v,t) profiles of the dense (v,t,d) index
+  space are dealt to the ranks round-robin (profile p on rank ``p % world``: neighbouring
+  profiles cost about the same, so the shards do too); every rank scores its profiles with the
+  fused kernel
   and the shard-local arg-min records (40 bytes, level|cost|index key) are exchanged with one
   all-gather and reduced lexicographically -- the "min-reduce of (cost, index)".  The validity
   level is part of the key, so the reference's "highest non-empty level" rule
@@ -22,7 +24,8 @@ from . import _abi
 
 
 def profile_shard(n_profiles: int, nd: int, rank: int, world: int):
-    """Dense candidate range [c_begin, c_end) of ``rank``: contiguous, aligned to whole profiles."""
+    """Dense candidate range [c_begin, c_end) of ``rank`` when the profiles are cut into contiguous blocks instead (the
+    C ABI's ``c_begin`` / ``c_end``; ``ShardedPlanner`` interleaves, see ``etp_step.shard_index``)."""
     base, rem = divmod(n_profiles, world)
     p0 = rank * base + min(rank, rem)
     p1 = p0 + base + (1 if rank < rem else 0)

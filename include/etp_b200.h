@@ -15,6 +15,10 @@
  *     memory: they are small (KBs) and are staged through pinned memory by the library;
  *   - OUTPUT tensors in etp_out are caller-allocated DEVICE memory (e.g. torch tensors'
  *     data_ptr()); any of them may be NULL, in which case that tensor is not materialised;
+ *   - the library's own device buffers (profile table, selection workspace, arenas of a sweep
+ *     or a planning cycle) live in the context and GROW on demand: a call that meets a larger
+ *     grid, more obstacles or more scenarios than any before it allocates (cudaMalloc, a
+ *     synchronising call); repeated calls of one shape allocate nothing;
  *   - etp_plan_step() is asynchronous on the context's stream; etp_get_best() /
  *     etp_get_trajectory() synchronise and read back a few hundred bytes.
  *

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run a few planning steps of a synthetic workload (used under ncu / compute-sanitizer)."""
+"""Run a few planning steps of a synthetic workload (used under ncu)."""
 import argparse
 import os
 import sys
