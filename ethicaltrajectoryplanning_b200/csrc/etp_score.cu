@@ -864,7 +864,7 @@ __device__ __forceinline__ unsigned dsmem_addr(const void* p, unsigned rank) {
     return a;
 }
 // plain loads and stores only: a 64-bit max is no native shared-memory atomic (the local one is a compare-and-swap loop), and
-// concurrent remote 64-bit reductions on one word lost updates in the fp64 check mode
+// with remote red.max pushes the fp64 check mode selected another candidate once in a dozen cycles of the closed-loop test
 __device__ __forceinline__ unsigned dsmem_ld(unsigned a, unsigned) { unsigned v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ unsigned long long dsmem_ld(unsigned a, unsigned long long) { unsigned long long v; asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void dsmem_st(unsigned a, unsigned v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
