@@ -3,6 +3,7 @@
  * etp_set_params / etp_set_spline / etp_set_obstacles / etp_plan_step (arg-min only) and prints the selection and the
  * first samples of the selected trajectory.  Build:  gcc abi_demo.c -I include -L <dir of the .so> -letp_b200 */
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 
 #include "etp_b200.h"
@@ -107,6 +108,18 @@ int main(int argc, char** argv) {
     printf("traj %d", n);
     for (int t = 0; t < 3 && t < n; ++t) printf(" %.17g %.17g", fields[ETP_F_X * tmax + t], fields[ETP_F_Y * tmax + t]);
     printf("\n%s\n", etp_version());
+    /* the same step as one planning cycle (etp_plan_cycle: predictions + step in, winner + trajectory out), three times:
+     * launched directly, captured, replayed */
+    etp_cycle cyc;
+    memset(&cyc, 0, sizeof(cyc));
+    cyc.obstacles = &o;
+    cyc.step = &s;
+    etp_best bc;
+    int nc = 0;
+    for (int k = 0; k < 3; ++k) CHECK(etp_plan_cycle(ctx, &cyc, ETP_PRECISION_FP32, &bc, fields, &nc));
+    printf("cycle %d %d %d %d %.17g %d", bc.index, bc.list_index, bc.level, bc.n_scored, bc.cost, nc);
+    for (int t = 0; t < 3 && t < nc; ++t) printf(" %.17g %.17g", fields[ETP_F_X * tmax + t], fields[ETP_F_Y * tmax + t]);
+    printf("\n");
     CHECK(etp_destroy(ctx));
     return 0;
 }

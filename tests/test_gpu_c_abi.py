@@ -64,5 +64,11 @@ def test_plain_c_program_selects_the_same_trajectory(tmp_path):
             np.testing.assert_array_equal(got[0::2], traj["x_m"][:3])
             np.testing.assert_array_equal(got[1::2], traj["y_m"][:3])
             assert "sm_100a" in lines[2]
+            cyc = lines[3].split()
+            assert cyc[0] == "cycle" and [int(v) for v in cyc[1:5]] == [want.best[k] for k in ("index", "list_index", "level", "n_scored")]
+            assert float(cyc[5]) == want.best["cost"] and int(cyc[6]) == len(traj["x_m"])
+            got = [float(v) for v in cyc[7:]]
+            np.testing.assert_array_equal(got[0::2], traj["x_m"][:3])
+            np.testing.assert_array_equal(got[1::2], traj["y_m"][:3])
     finally:
         ctx.close()

@@ -240,3 +240,46 @@ def test_a_new_vehicle_mass_invalidates_the_packed_obstacles():
     finally:
         ctx.close()
         fresh.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_plan_cycle_clustered_tiles_of_every_cluster_size_and_with_device_checks(precision):
+    """The planning cycle's fused kernel runs one tile per thread-block cluster of 8 / 4 / 2 CTAs (tiles x cluster <= 148),
+    each CTA a share of the tile's (t, o) items, maxima / collision flags / first road-boundary contacts folded into CTA 0
+    through distributed shared memory: grids of 1 .. 80 tiles, no obstacle at all, one obstacle, collision with the predicted
+    boxes (discrete / swept) and the road boundary on the device -- always the step-by-step path's selection, bit for bit."""
+    import copy
+
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext
+    from ethicaltrajectoryplanning_b200.synthetic import make_step, road_boundary_triangles
+
+    ctx, ref_ctx = ScoringContext(0, precision), ScoringContext(0, precision)
+    try:
+        csp0 = None
+        cases = []
+        for nv, nd, nobs in [(3, 5, 4), (15, 15, 8), (12, 48, 6), (20, 33, 12), (40, 40, 5), (50, 51, 3), (9, 9, 0), (9, 9, 1)]:
+            cases.append((dict(nv=nv, nd=nd, n_obstacles=nobs), None, None))      # 1, 8, 18, 21, 50, 80 tiles; O = 0, 1
+        for check in ("discrete", "swept"):
+            cases.append((dict(nv=15, nd=15, n_obstacles=8, lateral_spread=1.0), check, None))
+            cases.append((dict(nv=6, nd=30, n_obstacles=8, lateral_spread=2.0), check, check))
+        for k, (kw, collision, boundary) in enumerate(cases):
+            step = make_step("planning", seed=300 + k, v0=7.0 + k, **kw)
+            csp0 = step.csp if csp0 is None else csp0
+            step.csp = csp0
+            if collision:
+                step.params = copy.deepcopy(step.params)
+                step.params["modes"]["collision_check_device"] = collision
+            if boundary:
+                step.road_boundary = (road_boundary_triangles(csp0, half_width=2.4), boundary)
+            for rep in range(3):  # direct launch, capture, replay
+                best, traj = ctx.plan_cycle(step)
+            want_best, want_traj = ref_ctx.plan_winner(step)
+            assert (best["index"], best["level"], best["list_index"], best["n_scored"], best["cost"]) == \
+                (want_best["index"], want_best["level"], want_best["list_index"], want_best["n_scored"], want_best["cost"]), \
+                (kw, collision, boundary, best, want_best)
+            np.testing.assert_array_equal(traj["x_m"], want_traj["x_m"])
+        assert ctx.debug_counters()["graph_launches"] > 0
+        assert ctx.debug_counters()["bound_violations"] == 0
+    finally:
+        ctx.close()
+        ref_ctx.close()
