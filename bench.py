@@ -643,8 +643,8 @@ def latency_extras(ctx, torch):
         "note": "collision with the predicted boxes (swept), road boundary (300 triangles) and goal logic on the device as well"}
     loop["workload"] = ("FrenetPlanner.step wall clock: host packing of moving predictions + one etp_plan_cycle call (one upload, "
                         "a replayed CUDA graph of 3 launches -- head | fused scoring + selection | re-scoring + trajectory -- the "
-                        "winner's 13 fp64 rows written into pinned host memory); the device_checks case carries a goal and takes "
-                        "the step-by-step path; cfg1 = 5x5 grid T=20, cfg2 = 100x100 grid T=30, 8 obstacles")
+                        "winner's 13 fp64 rows written into pinned host memory); cfg1 = 5x5 grid T=20, cfg2 = 100x100 grid T=30, "
+                        "8 obstacles")
     extras["cfg5_closed_loop"] = loop
     return extras
 

@@ -104,6 +104,8 @@ struct etp_ctx {
     cudaGraph_t cyc_graph = nullptr;
     cudaGraphExec_t cyc_exec = nullptr;
     std::vector<long long> cyc_key, cyc_seen;
+    std::vector<unsigned char> goal_img, goal_img_next;  // goal geometry resident in goal_geom (stage_goal)
+    const void* goal_img_base = nullptr;
     bool no_graph = false, cycle_profile = false, cycle_split = false;
     double cyc_prof[3] = {0.0, 0.0, 0.0};
     int cyc_prof_n = 0;
@@ -698,28 +700,38 @@ static int stage_goal(etp_ctx* c, const etp_goal* g, double dt, int Tmax, DevGoa
         if (g->goal_line_start[l + 1] - g->goal_line_start[l] < 1) ETP_FAIL(c, ETP_ERR_INVALID, "goal centre line %d is empty", l);
     const size_t b_ls = (sizeof(int) * (size_t)(d.n_lines + 1) + 7) / 8 * 8, b_lv = sizeof(double) * 2 * (size_t)n_lv,
                  b_pt = sizeof(double) * 2 * (size_t)d.n_pts;
-    ETP_CUDA(c, c->goal_geom.reserve(b_start_pad + b_vert + b_circ + b_ls + b_lv + b_pt + 8));
+    // the geometry of a goal rarely changes between steps: one image [polygon starts | vertices | circles | line starts | line
+    // vertices | points], uploaded with one copy and only when its bytes (or the buffer) differ from what is resident
+    const size_t total = b_start_pad + b_vert + b_circ + b_ls + b_lv + b_pt;
+    ETP_CUDA(c, c->goal_geom.reserve(total + 8));
     unsigned char* base = c->goal_geom.as<unsigned char>();
-    int r;
     {
-        unsigned char* q = base + b_start_pad + b_vert + b_circ;
-        if (d.n_lines > 0) {
-            if ((r = stage_to_device(c, q, g->goal_line_start, sizeof(int) * (size_t)(d.n_lines + 1)))) return r;
-            if ((r = stage_to_device(c, q + b_ls, g->goal_line_vertices, b_lv))) return r;
+        std::vector<unsigned char>& img = c->goal_img_next;
+        img.assign(total, 0);
+        if (d.n_poly > 0) {
+            memcpy(img.data(), g->poly_start, b_start);
+            memcpy(img.data() + b_start_pad, g->vertices, b_vert);
         }
-        if (d.n_pts > 0 && (r = stage_to_device(c, q + b_ls + b_lv, g->goal_points, b_pt))) return r;
-        d.line_start = reinterpret_cast<const int*>(q);
-        d.line_verts = reinterpret_cast<const double*>(q + b_ls);
-        d.pts = reinterpret_cast<const double*>(q + b_ls + b_lv);
+        if (d.n_circ > 0) memcpy(img.data() + b_start_pad + b_vert, g->circles, b_circ);
+        unsigned char* q = img.data() + b_start_pad + b_vert + b_circ;
+        if (d.n_lines > 0) {
+            memcpy(q, g->goal_line_start, sizeof(int) * (size_t)(d.n_lines + 1));
+            memcpy(q + b_ls, g->goal_line_vertices, b_lv);
+        }
+        if (d.n_pts > 0) memcpy(q + b_ls + b_lv, g->goal_points, b_pt);
+        if (total > 0 && (base != c->goal_img_base || img != c->goal_img)) {
+            const int r = stage_to_device(c, base, img.data(), total);
+            if (r) return r;
+            c->goal_img.swap(img);
+            c->goal_img_base = base;
+        }
     }
-    if (d.n_poly > 0) {
-        if ((r = stage_to_device(c, base, g->poly_start, b_start))) return r;
-        if ((r = stage_to_device(c, base + b_start_pad, g->vertices, b_vert))) return r;
-    }
-    if (d.n_circ > 0 && (r = stage_to_device(c, base + b_start_pad + b_vert, g->circles, b_circ))) return r;
     d.poly_start = reinterpret_cast<const int*>(base);
     d.verts = reinterpret_cast<const double*>(base + b_start_pad);
     d.circles = reinterpret_cast<const double*>(base + b_start_pad + b_vert);
+    d.line_start = reinterpret_cast<const int*>(base + b_start_pad + b_vert + b_circ);
+    d.line_verts = reinterpret_cast<const double*>(base + b_start_pad + b_vert + b_circ + b_ls);
+    d.pts = reinterpret_cast<const double*>(base + b_start_pad + b_vert + b_circ + b_ls + b_lv);
     d.bx0 = d.by0 = INFINITY;
     d.bx1 = d.by1 = -INFINITY;
     for (int i = 0; i < n_vert; ++i) {
@@ -1282,7 +1294,7 @@ constexpr long long kCycleMaxCandidates = 16 * 4096;
 bool cycle_fusable(const etp_ctx* c, const etp_cycle& cy) {
     if (!c->have_spline || !cy.step) return false;
     const etp_step& p = *cy.step;
-    if (p.ext_level || p.bd_harm || p.cost_factor_list || p.goal) return false;
+    if (p.ext_level || p.bd_harm || p.cost_factor_list) return false;  // per-candidate host arrays: the step-by-step path
     if (p.nv < 1 || p.nt < 1 || p.nd < 1 || !p.v_list || !p.t_list || !p.d_list || !p.n_samples) return false;
     const long long dense = (long long)p.nv * p.nt * p.nd;
     if (c->cycle_split && dense > select_chunk()) return false;  // the measurement aid launches the one-block selection
@@ -1419,6 +1431,14 @@ int plan_cycle_fused(etp_ctx* c, const etp_cycle& cy, int precision, etp_best* b
     st.ws_cost = reinterpret_cast<double*>(sdev + s_wc); st.ws_bound = reinterpret_cast<float*>(sdev + s_wb);
     st.ws_meta = sdev + s_wm; st.ws_bd = reinterpret_cast<double*>(sdev + s_wbd); st.ws_gf = sdev + s_wgf;
     st.refine = refine ? 1 : 0;
+    // goal context of the step (cost factor, velocity cost, distance to the goal positions per candidate): its per-cycle part
+    // travels in the step record, its geometry is uploaded when it differs from what is resident
+    if (c->pr.w[ETP_W_DIST_TO_GOAL_POS] > 0.0 && !p.goal)
+        ETP_FAIL(c, ETP_ERR_INVALID, "weights['dist_to_goal_pos'] > 0 needs the goal positions of the step (etp_step.goal)");
+    {
+        const int rg = stage_goal(c, p.goal, p.dt, Tmax, &st.goal);
+        if (rg) return rg;
+    }
     memcpy(h + o_step, &st, sizeof(st));
     const PackArgs pk{O, Tp, st.pred_len, st.raw_pos, st.raw_cov, d_yaw, d_vel, d_len, d_wid, reinterpret_cast<const double*>(dev + o_mass),
                       reinterpret_cast<const int*>(dev + o_prot), d_resp, c->pr.veh_m, ox, oy, sdev + s_tile,

@@ -898,8 +898,7 @@ class ScoringContext:
             self.set_spline(CubicSpline2D.from_foreign(step.csp))
             self._spline_key = (step.csp, self._spline_print(step.csp))
         self.ensure_road_boundary(getattr(step, "road_boundary", None))
-        if (raw is not None and step.ext_level is None and step.bd_harm is None and getattr(step, "cost_factor_list", None) is None
-                and getattr(step, "goal", None) is None):
+        if raw is not None and step.ext_level is None and step.bd_harm is None and getattr(step, "cost_factor_list", None) is None:
             return self._plan_cycle_resident(step, raw)
         s, keep, n = self.make_step_struct(step)
         cy = _abi.Cycle()
@@ -964,6 +963,15 @@ class ScoringContext:
         if cs.get("raw") is not raw:
             cy.raw = C.pointer(raw)
             cs["raw"] = raw
+        goal = getattr(step, "goal", None)
+        if goal is not None:  # ego state and time step of this cycle: a new record per cycle, the geometry arrays with it
+            keep = []
+            g = make_goal(goal, keep)
+            st.goal = C.pointer(g)
+            cs["goal"] = (g, keep)
+        elif cs.get("goal") is not None:
+            st.goal = None
+            cs["goal"] = None
         self._last_tmax, self.last_dt = Tmax, step.dt
         f = np.empty((_abi.NUM_FIELDS, Tmax), dtype=np.float64)
         self._check(self.lib.etp_plan_cycle(self.h, C.byref(cy), self.precision, C.byref(b), _dptr(f), C.byref(T)))

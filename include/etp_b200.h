@@ -399,11 +399,15 @@ int etp_plan_batch(etp_ctx* ctx, int n, const etp_scenario* scenarios, int preci
  * `self._trajectory`): predictions of this cycle -> (enrichment) -> obstacle tile -> profiles -> fused scoring -> exact
  * selection -> the winner's 13 fp64 rows.  Exactly one of `raw` (predictor output, enriched on the device like
  * etp_set_raw_predictions) and `obstacles` (the enriched dict, like etp_set_obstacles) is given; parameters, spline and road
- * boundary are the context's.  All inputs of the cycle travel in one upload, every kernel takes its step from device
- * memory, and the launch sequence of a cycle whose shapes equal the previous cycle's is replayed as a captured CUDA graph
- * (ETP_NO_GRAPH=1: launched one by one).  Steps with per-candidate host arrays, a goal context or more than 4096 candidates
+ * boundary are the context's; the step may carry a goal context (etp_step.goal).  All inputs of the cycle travel in one
+ * upload, every kernel takes its step from device memory, the launch sequence of a cycle whose shapes equal the previous
+ * cycle's is replayed as a captured CUDA graph (ETP_NO_GRAPH=1: launched one by one) -- three launches: profiles +
+ * enrichment + tile | fused scoring (a small step's tile spread over a thread-block cluster) + selection | exact
+ * re-scoring + the winner's trajectory --, and the result is written into pinned host memory by the last kernel.  Steps
+ * with per-candidate host arrays (ext_level, bd_harm, cost_factor_list), a sharded range or more than 65536 candidates
  * run as etp_set_*_predictions + etp_plan_step + etp_get_best_trajectory inside the same call.  Arg-min only (no etp_out).
- * Returns like etp_get_best_trajectory.
+ * Returns like etp_get_best_trajectory.  Afterwards the context holds the step (etp_get_trajectory etc. work), but the
+ * obstacles live in the cycle's arena: etp_plan_step needs etp_set_obstacles / etp_set_raw_predictions again.
  */
 typedef struct {
     const etp_raw_predictions* raw;

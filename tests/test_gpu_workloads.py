@@ -101,6 +101,10 @@ def test_closed_loop_with_every_check_on_the_device():
     d = np.array([st[1] for st in states])
     assert np.all(np.diff(s) >= 0) and s[-1] > s[0] + 5.0
     assert np.all(np.abs(d) < 3.6)
+    # the cycle path (one call per cycle, goal context in the cycle's step record) drives exactly like the materialised path
+    _, mat = closed_loop(n_steps=30, grid="planning", n_obstacles=4, device_checks=True, materialize=True)
+    for a, b in zip(states, mat):
+        np.testing.assert_allclose(a[:3], b[:3], rtol=2e-5, atol=1e-6)  # the materialised path reads fp32 rows
 
 
 @pytest.mark.parametrize("weights", ["weights_ethical.json", "weights_ego.json", "weights_standard.json"])
@@ -211,6 +215,16 @@ def test_plan_cycle_replays_a_graph_and_equals_the_step_by_step_path():
                     (want_best["index"], want_best["level"], want_best["list_index"], want_best["n_scored"], want_best["cost"])
                 np.testing.assert_array_equal(traj["y_m"], want_traj["y_m"])
             assert ctx.debug_counters()["bound_violations"] == 0
+            # steps with a goal context (cost factor, velocity cost, distance to the goal positions per candidate)
+            from helpers import goal_cases
+
+            for name, step in goal_cases():
+                for rep in range(2):
+                    best, traj = ctx.plan_cycle(step)
+                want_best, want_traj = ref_ctx.plan_winner(step)
+                assert (best["index"], best["level"], best["list_index"], best["cost"]) == \
+                    (want_best["index"], want_best["level"], want_best["list_index"], want_best["cost"]), name
+                np.testing.assert_array_equal(traj["x_m"], want_traj["x_m"])
         finally:
             ctx.close()
             ref_ctx.close()
