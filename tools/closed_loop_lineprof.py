@@ -1,4 +1,4 @@
-"""Per-statement wall time of the closed loop's Python methods (development aid, GPU box)."""
+"""Per-statement wall time of the closed loop's Python methods (development aid, GPU box: python tools/closed_loop_lineprof.py [cfg1|cfg2])."""
 import inspect, os, sys, textwrap, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
