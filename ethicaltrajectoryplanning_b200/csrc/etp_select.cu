@@ -13,6 +13,9 @@
 //                    materialised rows of the candidate are overwritten, and the last CTA takes the minimum of the exact
 //                    keys.  The same idea as gate_exact / band_coefs_exact of the fused kernel, applied to the arg-min
 //                    and to the max-risk / maximin-gate decisions.
+#ifdef ETP_PHASE_CLOCK
+#include <cstdio>
+#endif
 #include "etp_select.cuh"
 
 namespace etp {
@@ -101,17 +104,25 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
     double* buf = reinterpret_cast<double*>(mx + 4 * On);        // [kQChunk][36] BVU values
     double* nodes = buf + kQChunk * 36;                          // [kQChunk][40] sin(theta_i) | 1 - sin^2(theta_i)
     double* lims = nodes + kQChunk * 40;                         // [kQChunk][72] 36 rectangle limits | their normal tails
-    double* ent_c = lims + kQChunk * 72;                         // [kQChunk][kEntC] 1/sx, 1/sy, rho, asin(rho)
+    double* ent_c = lims + kQChunk * 72;                         // [kQChunk][kEntC] 1/sx, 1/sy, rho, asin(rho), ego harm, obstacle harm
     unsigned* queue = reinterpret_cast<unsigned*>(ent_c + kQChunk * kEntC);  // [(Ts-1) * On]
     __shared__ Tab<double> tab;
     __shared__ int s_qn, s_last;
     __shared__ double s_scratch[kResThreads / 32];
+    __shared__ double s_sum5[5 * (kResThreads / 32)];
     if (tid == 0) fill_tab<double>(tab, pr, 0.0);
     const bool mahal = pr.mahalanobis != 0;
     RescoreRec* res = reinterpret_cast<RescoreRec*>(sb.res);
 
+#ifdef ETP_PHASE_CLOCK
+    long long rclk[6] = {0, 0, 0, 0, 0, 0};
+#define ETP_RCLK(k) do { if (tid == 0 && first == 0 && rclk[k] == 0) rclk[k] = clock64(); } while (0)
+#else
+#define ETP_RCLK(k) do { } while (0)
+#endif
     for (int i = first; i < count; i += nblk) {
         __syncthreads();  // previous candidate consumed; tab visible
+        ETP_RCLK(0);
         const int cl = sb.list[i];
         const unsigned char meta = st.ws_meta[cl];
         const int kl = kGiven ? 0 : cl / st.nd, id = kGiven ? 0 : cl - kl * st.nd;
@@ -140,20 +151,22 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
             }
         }
         CandFacts f;
-        f.sv = block_sum(sv, s_scratch);
-        f.sd = block_sum(sd, s_scratch);
-        f.jl = block_sum(jl, s_scratch);
-        f.jq = block_sum(jq, s_scratch);
+        __syncthreads();  // every sample is in shared memory (the travelled distance reads a neighbour's)
         double trav = 0;
         for (int t = 1 + tid; t < T; t += kResThreads) {  // calc_trajectory_cost.py:739-757
             const double dx = e_x[t - 1] - e_x[t], dy = e_y[t - 1] - e_y[t];
             trav += sqrt(dx * dx + dy * dy);
         }
-        f.trav = block_sum(trav, s_scratch);
+        {
+            double sums[5] = {sv, sd, jl, jq, trav};
+            block_sum_n<5>(sums, s_sum5);  // the fixed tree of block_sum, one pair of barriers for the five sums
+            f.sv = sums[0]; f.sd = sums[1]; f.jl = sums[2]; f.jq = sums[3]; f.trav = sums[4];
+        }
         f.T = T;
         f.x_end = e_x[T - 1];
         f.y_end = e_y[T - 1];
 
+        ETP_RCLK(1);
         // ---- harm logits of every (t, o) sample; probability samples inside the 5 m gate are queued ----
         for (int it = tid; it < (Ts - 1) * O; it += kResThreads) {
             const int t = it / O, o = it - t * O;
@@ -186,6 +199,7 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
         }
         __syncthreads();
 
+        ETP_RCLK(2);
         // ---- queued samples: nine rectangles x four BVU corners each (collision_probability.py:205-252) ----
         const int qn = s_qn;
         for (int q0 = 0; q0 < qn; q0 += kQChunk) {
@@ -205,6 +219,21 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
                     e[0] = 1.0 / sx; e[1] = 1.0 / sy; e[2] = c10 / sy / sx;
                     e[3] = asin(e[2]);
                 }
+            }
+            // harm of the pair's sample (risk = harm x probability, risk_costs.py:88-95): one thread per entry, next to the
+            // entry constants instead of after the barrier that closes the BVU values
+            static_assert(2 * kQChunk <= kResThreads, "entry constants and entry harms are computed by disjoint threads");
+            for (int q = tid - kResThreads / 2; q >= 0 && q < qc; q += kResThreads) {  // the upper half of the block: runs next to the constants
+                const unsigned ent = queue[q0 + q];
+                const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
+                const ObsSample s = load_obs(st, o, t);
+                double ae, ao;
+                harm_logits(tab, s, e_x[t], e_y[t], e_yaw[t], e_v[t], ae, ao);
+                double* e = ent_c + q * kEntC;
+                e[4] = sigmoid_harm<double>(s.prot ? tab.lr_const : tab.lr1s_const, ae);
+                e[5] = sigmoid_harm<double>(s.prot ? tab.lr_const : tab.neg_ped_const, ao);
+            }
+            if (!mahal) {
                 __syncthreads();
                 for (int item = tid; item < qc * 56; item += kResThreads) {
                     const int q = item / 56, m = item - q * 56;
@@ -264,6 +293,7 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
                 }
                 __syncthreads();
             }
+            if (mahal) __syncthreads();  // the entries' harm values
             if (tid < qc) {
                 const unsigned ent = queue[q0 + tid];
                 const int t = (int)(ent >> 16), o = (int)(ent & 0xffffu);
@@ -278,26 +308,38 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
                     for (int r = 0; r < 9; ++r) prob += b[4 * r] - b[4 * r + 1] - b[4 * r + 2] + b[4 * r + 3];  // MVNDST's corner order
                     prob = prob / 3;
                 }
-                const ObsSample s = load_obs(st, o, t);
-                double ae, ao;
-                harm_logits(tab, s, e_x[t], e_y[t], e_yaw[t], e_v[t], ae, ao);
-                const double he = sigmoid_harm<double>(s.prot ? tab.lr_const : tab.lr1s_const, ae);
-                const double ho = sigmoid_harm<double>(s.prot ? tab.lr_const : tab.neg_ped_const, ao);
+                const double he = ent_c[tid * kEntC + 4], ho = ent_c[tid * kEntC + 5];
                 atomicMax(mx + o, Enc<double>::enc(he * prob));  // risk_costs.py:88-95
                 atomicMax(mx + On + o, Enc<double>::enc(ho * prob));
             }
             __syncthreads();
         }
 
-        // ---- per-obstacle maxima -> principles, level, cost (thread 0; obstacles in order) ----------
+        ETP_RCLK(3);
+        // ---- per-obstacle maxima -> principles, level, cost: the harm sigmoids by one thread per obstacle, the sums by
+        // thread 0 with the obstacles in order ----------
+        double* ob = buf;  // [4][On] ego risk, obstacle risk, ego harm, obstacle harm (the BVU buffer is free again)
+        for (int o = tid; o < O; o += kResThreads) {
+            const bool prt = st.obs_const[o * OC_COUNT + OC_PROT] != 0.0;
+            const double re = fmax(Enc<double>::dec(mx[o]), 0.0), ro = fmax(Enc<double>::dec(mx[On + o]), 0.0);
+            const double he = sigmoid_harm<double>(prt ? tab.lr_const : tab.lr1s_const, Enc<double>::dec(mx[2 * On + o]));
+            const double ho = sigmoid_harm<double>(prt ? tab.lr_const : tab.neg_ped_const, Enc<double>::dec(mx[3 * On + o]));
+            ob[o] = re; ob[On + o] = ro; ob[2 * On + o] = he; ob[3 * On + o] = ho;
+            if (out.red) {
+                const size_t Cp = out.c_stride;
+                const double v[4] = {re, ro, he, ho};
+                for (int k = 0; k < 4; ++k) {
+                    if (out_f32) reinterpret_cast<float*>(out.red)[((size_t)k * O + o) * Cp + cl] = (float)v[k];
+                    else reinterpret_cast<double*>(out.red)[((size_t)k * O + o) * Cp + cl] = v[k];
+                }
+            }
+        }
+        __syncthreads();
         if (tid == 0) {
             RiskSums r{0, 0, 0, 0, -INFINITY, -INFINITY};
             const bool gate = (pr.relaxed & ETP_RELAX_Q3_MAXIMIN) != 0;
             for (int o = 0; o < O; ++o) {
-                const bool prt = st.obs_const[o * OC_COUNT + OC_PROT] != 0.0;
-                const double re = fmax(Enc<double>::dec(mx[o]), 0.0), ro = fmax(Enc<double>::dec(mx[On + o]), 0.0);
-                const double he = sigmoid_harm<double>(prt ? tab.lr_const : tab.lr1s_const, Enc<double>::dec(mx[2 * On + o]));
-                const double ho = sigmoid_harm<double>(prt ? tab.lr_const : tab.neg_ped_const, Enc<double>::dec(mx[3 * On + o]));
+                const double re = ob[o], ro = ob[On + o], he = ob[2 * On + o], ho = ob[3 * On + o];
                 r.sum_e += re;
                 r.sum_o += ro;
                 r.sum_abs += fabs(re - ro);
@@ -305,14 +347,6 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
                 r.mm = fmax(r.mm, he * (((re < 10e-10) != gate) ? 1.0 : 0.0));
                 r.mm = fmax(r.mm, ho * (((ro < 10e-10) != gate) ? 1.0 : 0.0));
                 r.max_o = fmax(r.max_o, ro);
-                if (out.red) {
-                    const size_t Cp = out.c_stride;
-                    const double v[4] = {re, ro, he, ho};
-                    for (int k = 0; k < 4; ++k) {
-                        if (out_f32) reinterpret_cast<float*>(out.red)[((size_t)k * O + o) * Cp + cl] = (float)v[k];
-                        else reinterpret_cast<double*>(out.red)[((size_t)k * O + o) * Cp + cl] = v[k];
-                    }
-                }
             }
             const int level32 = meta & 63;
             f.pre_level = level32 <= 2 ? level32 : -1;  // the tests before the risk are exact in the fused kernel
@@ -345,6 +379,12 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
             rr.cost = c[ETP_C_TOTAL]; rr.rank = level_rank(level); rr.level = level; rr.cl = cl; rr.pad = 0;
             res[i] = rr;
         }
+        ETP_RCLK(4);
+#ifdef ETP_PHASE_CLOCK
+        if (tid == 0 && first == 0 && i == 0)
+            printf("rescore CTA 0, first survivor: %d queued pairs; cycles samples+sums %lld, harm logits + gate %lld, probabilities %lld, assembly %lld\n",
+                   s_qn, rclk[1] - rclk[0], rclk[2] - rclk[1], rclk[3] - rclk[2], rclk[4] - rclk[3]);
+#endif
     }
 
     // ---- the last CTA takes the minimum of the exact keys ----------------------------------------

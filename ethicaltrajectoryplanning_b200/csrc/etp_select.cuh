@@ -11,8 +11,8 @@ constexpr int kSelThreads = 256;
 constexpr int kSelPer = 16;                       // workspace entries per thread
 constexpr int kSelChunk = kSelThreads * kSelPer;  // entries per block
 constexpr int kResThreads = 512;
-constexpr int kQChunk = 32;                       // un-gated pairs whose 36 BVU values are buffered at a time
-constexpr int kEntC = 4;                          // per-pair constants kept in shared memory
+constexpr int kQChunk = 128;                      // un-gated pairs whose 36 BVU values are buffered at a time (1.2 KB each)
+constexpr int kEntC = 6;                          // per-pair constants kept in shared memory
 
 struct SelBlock {
     int rank_max;         // highest level rank among the block's unambiguous candidates (-1: none)
@@ -51,6 +51,27 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w];
     return s;
+}
+
+// the same for several values at once (one pair of barriers for all of them); scratch holds N x (threads / 32) doubles
+template <int N> __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
+    const int nw = (int)(blockDim.x >> 5);
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(kFull, v[k], o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) scratch[k * nw + (threadIdx.x >> 5)] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += scratch[k * nw + w];
+        v[k] = s;
+    }
 }
 
 // rank of dense candidate `index` among the non-skipped candidates of [c_begin, c_end) = position in the reference's
