@@ -86,7 +86,7 @@ __device__ __forceinline__ void harm_logits(const Tab<double>& tab, const ObsSam
 template <bool kGiven>
 __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams& pr, const DevOut& out, int out_f32, const SelectBufs& sb,
                                              BestRec* __restrict__ best_out, const int* __restrict__ nskip, unsigned char* smem_raw,
-                                             const int first, const int nblk) {
+                                             const int first, const int nblk, const int qcap = kQChunk) {
     using U = unsigned long long;
     const int count = sb.hdr[0];
     if (count == 0) return false;  // the selection was final
@@ -102,10 +102,10 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
     double* e_s = e_c + Ts;
     U* mx = reinterpret_cast<U*>(e_s + Ts);                       // [4][On]: ego risk, obstacle risk, ego logit, obstacle logit
     double* buf = reinterpret_cast<double*>(mx + 4 * On);        // [kQChunk][36] BVU values
-    double* nodes = buf + kQChunk * 36;                          // [kQChunk][40] sin(theta_i) | 1 - sin^2(theta_i)
-    double* lims = nodes + kQChunk * 40;                         // [kQChunk][72] 36 rectangle limits | their normal tails
-    double* ent_c = lims + kQChunk * 72;                         // [kQChunk][kEntC] 1/sx, 1/sy, rho, asin(rho), ego harm, obstacle harm
-    unsigned* queue = reinterpret_cast<unsigned*>(ent_c + kQChunk * kEntC);  // [(Ts-1) * On]
+    double* nodes = buf + qcap * 36;                          // [kQChunk][40] sin(theta_i) | 1 - sin^2(theta_i)
+    double* lims = nodes + qcap * 40;                         // [kQChunk][72] 36 rectangle limits | their normal tails
+    double* ent_c = lims + qcap * 72;                         // [kQChunk][kEntC] 1/sx, 1/sy, rho, asin(rho), ego harm, obstacle harm
+    unsigned* queue = reinterpret_cast<unsigned*>(ent_c + qcap * kEntC);  // [(Ts-1) * On]
     __shared__ Tab<double> tab;
     __shared__ int s_qn, s_last;
     __shared__ double s_scratch[kResThreads / 32];
@@ -202,8 +202,8 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
         ETP_RCLK(2);
         // ---- queued samples: nine rectangles x four BVU corners each (collision_probability.py:205-252) ----
         const int qn = s_qn;
-        for (int q0 = 0; q0 < qn; q0 += kQChunk) {
-            const int qc = min(kQChunk, qn - q0);
+        for (int q0 = 0; q0 < qn; q0 += qcap) {  // qcap <= kQChunk pairs at a time (the sweep's kernel keeps its footprint small)
+            const int qc = min(qcap, qn - q0);
             if (!mahal) {
                 // What the 36 BVU evaluations of an entry share is computed once per entry: the Gauss-Legendre nodes of the
                 // correlation (sin and 1 - sin^2, Genz' loop takes 2 * lg of them), the 18 + 18 rectangle limits and their
@@ -318,7 +318,7 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
         ETP_RCLK(3);
         // ---- per-obstacle maxima -> principles, level, cost: the harm sigmoids by one thread per obstacle, the sums by
         // thread 0 with the obstacles in order ----------
-        double* ob = buf;  // [4][On] ego risk, obstacle risk, ego harm, obstacle harm (the BVU buffer is free again)
+        double* ob = buf;  // [4][On] ego risk, obstacle risk, ego harm, obstacle harm (the BVU buffer is free again; 4 On <= 36 qcap by the launcher)
         for (int o = tid; o < O; o += kResThreads) {
             const bool prt = st.obs_const[o * OC_COUNT + OC_PROT] != 0.0;
             const double re = fmax(Enc<double>::dec(mx[o]), 0.0), ro = fmax(Enc<double>::dec(mx[On + o]), 0.0);
@@ -438,9 +438,9 @@ __device__ __forceinline__ bool rescore_body(const DevStep& st, const DevParams&
 template <bool kGiven>
 __global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_constant__ DevStep st, const __grid_constant__ DevParams pr,
                                                              const DevOut out, int out_f32, const SelectBufs sb, BestRec* __restrict__ best_out,
-                                                             const int* __restrict__ nskip) {
+                                                             const int* __restrict__ nskip, int qcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    rescore_body<kGiven>(st, pr, out, out_f32, sb, best_out, nskip, smem_raw, blockIdx.x, gridDim.x);
+    rescore_body<kGiven>(st, pr, out, out_f32, sb, best_out, nskip, smem_raw, blockIdx.x, gridDim.x, qcap);
 }
 
 // scenario sweep: one CTA per scenario walks that scenario's survivors (usually none)
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kResThreads) rescore_batch_kernel(const DevSte
         reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(steps + scn)[i];
     if (threadIdx.x == 0) s_sb = sbs[scn];
     __syncthreads();
-    rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests + scn, s_st.nskip, smem_raw, 0, 1);
+    rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests + scn, s_st.nskip, smem_raw, 0, 1, kQChunkBatch);
 }
 
 // Planning cycle (etp_plan_cycle): what follows the selection in ONE launch.  The survivors of the fp32 selection are
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kResThreads) rescore_batch_kernel(const DevSte
 // be pinned host memory (the cycle's only result: no separate read-back).
 __global__ void __launch_bounds__(kResThreads) cycle_tail_kernel(const DevStep* __restrict__ steps, const __grid_constant__ DevParams pr,
                                                                 const SelectBufs* __restrict__ sbs, BestRec* __restrict__ bests,
-                                                                unsigned char* __restrict__ combo) {
+                                                                unsigned char* __restrict__ combo, int qcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevStep s_st;
     __shared__ SelectBufs s_sb;
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kResThreads) cycle_tail_kernel(const DevStep* 
     __syncthreads();
     bool closing;
     if (s_sb.hdr[0] == 0) closing = blockIdx.x == 0;  // uniform over the grid: every CTA reads the count before any can reset it
-    else closing = rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests, s_st.nskip, smem_raw, blockIdx.x, gridDim.x);
+    else closing = rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests, s_st.nskip, smem_raw, blockIdx.x, gridDim.x, qcap);
     if (!closing) return;
     __syncthreads();  // the record thread 0 wrote
     if (threadIdx.x == 0) s_best = *bests;
@@ -498,15 +498,27 @@ cudaError_t launch_select(const DevStep& st, const SelectBufs& sb, BestRec* best
     return cudaGetLastError();
 }
 
-size_t rescore_smem_bytes(int Tmax, int O) {
+static size_t rescore_smem_for(int Tmax, int O, int qcap) {
     const size_t On = O > 0 ? O : 1;
-    return sizeof(double) * 6 * Tmax + sizeof(unsigned long long) * 4 * On + sizeof(double) * kQChunk * (36 + 40 + 72 + kEntC) +
+    if ((size_t)qcap * 36 < 4 * On) qcap = (int)((4 * On + 35) / 36);  // the assembly's per-obstacle values reuse the BVU buffer
+    return sizeof(double) * 6 * Tmax + sizeof(unsigned long long) * 4 * On + sizeof(double) * qcap * (36 + 40 + 72 + kEntC) +
            sizeof(unsigned) * (size_t)(Tmax - 1) * On + 16;
 }
 
+// pairs per chunk of a re-scoring CTA: as many as the shared memory a CTA may have allows (a long horizon with many obstacles
+// needs most of it for the pair queue)
+static int rescore_chunk(int Tmax, int O) {
+    int q = kQChunk;
+    while (q > kQChunkBatch && rescore_smem_for(Tmax, O, q) > (size_t)200 * 1024) q >>= 1;
+    return q;
+}
+
+size_t rescore_smem_bytes(int Tmax, int O) { return rescore_smem_for(Tmax, O, rescore_chunk(Tmax, O)); }
+
 cudaError_t launch_rescore(int precision, const DevStep& st, const DevParams& pr, const DevOut& out, const SelectBufs& sb,
                            BestRec* best_out, const int* nskip, int num_sms, cudaStream_t stream) {
-    const size_t smem = rescore_smem_bytes(st.Tmax, st.has_pred ? st.O : 0);
+    const int qcap = rescore_chunk(st.Tmax, st.has_pred ? st.O : 0);
+    const size_t smem = rescore_smem_for(st.Tmax, st.has_pred ? st.O : 0, qcap);
     long long grid = 2ll * num_sms;
     if (grid > st.n_local) grid = st.n_local;
     if (grid < 1) grid = 1;
@@ -515,11 +527,11 @@ cudaError_t launch_rescore(int precision, const DevStep& st, const DevParams& pr
     if (st.given) {
         e = cudaFuncSetAttribute(rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        rescore_kernel<true><<<(int)grid, kResThreads, smem, stream>>>(st, pr, out, f32, sb, best_out, nskip);
+        rescore_kernel<true><<<(int)grid, kResThreads, smem, stream>>>(st, pr, out, f32, sb, best_out, nskip, qcap);
     } else {
         e = cudaFuncSetAttribute(rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        rescore_kernel<false><<<(int)grid, kResThreads, smem, stream>>>(st, pr, out, f32, sb, best_out, nskip);
+        rescore_kernel<false><<<(int)grid, kResThreads, smem, stream>>>(st, pr, out, f32, sb, best_out, nskip, qcap);
     }
     return cudaGetLastError();
 }
@@ -534,7 +546,7 @@ cudaError_t launch_select_batch(const DevStep* steps, const SelectBufs* sbs, Bes
 cudaError_t launch_rescore_batch(const DevStep* steps, const DevParams& pr, const SelectBufs* sbs, BestRec* bests, int n_scn, int max_T,
                                  int max_O, cudaStream_t stream) {
     if (n_scn <= 0) return cudaSuccess;
-    const size_t smem = rescore_smem_bytes(max_T, max_O);
+    const size_t smem = rescore_smem_for(max_T, max_O, kQChunkBatch);
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(rescore_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -547,14 +559,15 @@ cudaError_t launch_rescore_batch(const DevStep* steps, const DevParams& pr, cons
 
 cudaError_t launch_cycle_tail(const DevStep* steps, const DevParams& pr, const SelectBufs* sbs, BestRec* bests, unsigned char* combo,
                               bool refine, int Tmax, int O, cudaStream_t stream) {
-    const size_t smem = refine ? rescore_smem_bytes(Tmax, O) : 0;
+    const int qcap = rescore_chunk(Tmax, O);
+    const size_t smem = refine ? rescore_smem_for(Tmax, O, qcap) : 0;
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(cycle_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    cycle_tail_kernel<<<refine ? 8 : 1, kResThreads, smem, stream>>>(steps, pr, sbs, bests, combo);
+    cycle_tail_kernel<<<refine ? 8 : 1, kResThreads, smem, stream>>>(steps, pr, sbs, bests, combo, qcap);
     return cudaGetLastError();
 }
 

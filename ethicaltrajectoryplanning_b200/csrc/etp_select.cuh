@@ -12,6 +12,7 @@ constexpr int kSelPer = 16;                       // workspace entries per threa
 constexpr int kSelChunk = kSelThreads * kSelPer;  // entries per block
 constexpr int kResThreads = 512;
 constexpr int kQChunk = 128;                      // un-gated pairs whose 36 BVU values are buffered at a time (1.2 KB each)
+constexpr int kQChunkBatch = 32;                  // the same in the sweep's kernel (one CTA per scenario: several resident per SM)
 constexpr int kEntC = 6;                          // per-pair constants kept in shared memory
 
 struct SelBlock {
