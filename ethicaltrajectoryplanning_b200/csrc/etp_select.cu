@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kResThreads) rescore_kernel(const __grid_const
     rescore_body<kGiven>(st, pr, out, out_f32, sb, best_out, nskip, smem_raw, blockIdx.x, gridDim.x, qcap);
 }
 
-// scenario sweep: one CTA per scenario walks that scenario's survivors (usually none)
+// scenario sweep: gridDim.y CTAs per scenario share that scenario's survivors (usually none: they leave at once)
 __global__ void __launch_bounds__(kResThreads) rescore_batch_kernel(const DevStep* __restrict__ steps, const __grid_constant__ DevParams pr,
                                                                    const SelectBufs* __restrict__ sbs, BestRec* __restrict__ bests) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kResThreads) rescore_batch_kernel(const DevSte
         reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(steps + scn)[i];
     if (threadIdx.x == 0) s_sb = sbs[scn];
     __syncthreads();
-    rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests + scn, s_st.nskip, smem_raw, 0, 1, kQChunkBatch);
+    rescore_body<false>(s_st, pr, DevOut{}, 1, s_sb, bests + scn, s_st.nskip, smem_raw, blockIdx.y, gridDim.y, kQChunkBatch);
 }
 
 // Planning cycle (etp_plan_cycle): what follows the selection in ONE launch.  The survivors of the fp32 selection are
@@ -553,7 +553,7 @@ cudaError_t launch_rescore_batch(const DevStep* steps, const DevParams& pr, cons
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    rescore_batch_kernel<<<n_scn, kResThreads, smem, stream>>>(steps, pr, sbs, bests);
+    rescore_batch_kernel<<<dim3(n_scn, 4), kResThreads, smem, stream>>>(steps, pr, sbs, bests);
     return cudaGetLastError();
 }
 
