@@ -201,8 +201,10 @@ class FrenetPlanner:
         }
 
     def _step_fused(self, c_s, c_s_d, c_s_dd, c_d, c_d_d, c_d_dd, d_list, t_list, v_list, predictions):
-        """Same selection without materialising per-candidate Python objects: one launch, 40-byte readback, then the
-        winner's 13 rows in fp64."""
+        """Same selection without materialising per-candidate Python objects: the whole cycle is one library call
+        (``ScoringContext.plan_cycle`` = ``etp_plan_cycle``: this cycle's predictions and step in one upload, three launches
+        replayed as a CUDA graph, winner and its 13 fp64 rows written into pinned host memory); with a columnar log the
+        materialised step."""
         fpar = self.frenet_parameters
         from .utils.calc_trajectory_cost import cost_context, goal_context
         from .utils.validity_checks import device_road_boundary
