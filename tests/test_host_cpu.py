@@ -309,3 +309,76 @@ def test_exec_timer_keeps_the_reference_surface_and_label_structure():
             assert hasattr(ExecTimer, fn.name), fn.name
             got = list(inspect.signature(getattr(ExecTimer, fn.name)).parameters)
             assert got == [a.arg for a in fn.args.args], (fn.name, got)
+
+
+def test_velocity_samples_equal_numpy_linspace_bit_for_bit():
+    """get_v_list writes the linspace of frenet_functions.py:760-807 by hand (a planning cycle pays for it every 0.1 s): the
+    same bits as np.append(np.linspace(...), v_cur) for every sample count, degenerate ranges and goal-velocity clamps."""
+    from ethicaltrajectoryplanning_b200.synthetic import get_v_list
+
+    rng = np.random.default_rng(7)
+    for _ in range(5000):
+        lo, hi = sorted(rng.uniform(0.0, 40.0, 2))
+        n = int(rng.integers(2, 60))
+        v_cur = float(rng.uniform(0.0, 40.0))
+        if rng.random() < 0.1:
+            hi = lo
+        if rng.random() < 0.5:
+            want = np.append(np.linspace(lo, hi, n - 1), v_cur)
+            got = get_v_list(lo, hi, v_cur, None, None, n)
+        else:
+            g0, g1 = sorted(rng.uniform(0.0, 40.0, 2))
+            want = np.append(np.linspace(max(min(g0, lo), 0.001), max(g1, hi), n - 1), v_cur)
+            got = get_v_list(lo, hi, v_cur, g0, g1, n)
+        assert got.dtype == np.float64 and got.tobytes() == want.tobytes(), (lo, hi, n)
+    assert get_v_list(1.0, 2.0, 1.5, None, None, 2).tolist() == [1.0, 1.5]  # a single sample plus the current velocity
+    with pytest.raises(ValueError):
+        get_v_list(1.0, 2.0, 1.5, None, None, 0)
+
+
+def test_array_wise_sweep_packer_equals_the_per_scenario_packing():
+    """ScoringContext.pack_scenarios for a sweep over one grid shape fills the ABI structs array-wise (one stacked copy per
+    input field, struct columns through numpy views of the ctypes layouts, one class table per obstacle type, spline tables
+    shared when their bytes are equal): every record it hands to etp_plan_batch equals what the per-scenario packing gives."""
+    import ctypes as C
+
+    from ethicaltrajectoryplanning_b200.scoring import ScoringContext, pack_predictions
+    from ethicaltrajectoryplanning_b200.spline import CubicSpline2D
+    from ethicaltrajectoryplanning_b200.workloads import sweep_steps
+
+    steps = [st for _, st in sweep_steps(9)]
+    steps[4].csp = steps[3].csp  # the same spline object twice in a row
+    arr, keep = ScoringContext._pack_scenarios_uniform(steps)
+    assert len(arr) == len(steps)
+
+    def view(ptr, shape, dtype):
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype=dtype)
+        ct = C.c_double if dtype == np.float64 else C.c_int32
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).reshape(shape).copy()
+
+    for sc, st in zip(arr, steps):
+        o, s = sc.obstacles.contents, sc.step.contents
+        pk = pack_predictions(st.predictions, st.obstacle_types)
+        O, Tp = pk["O"], pk["Tp"]
+        assert (o.n_obstacles, o.max_pred) == (O, Tp)
+        np.testing.assert_array_equal(view(o.pred_len, (O,), np.int32), pk["pred_len"])
+        for name, shape in (("pos", (O, Tp, 2)), ("cov", (O, Tp, 4)), ("yaw", (O, Tp)), ("vel", (O, Tp)), ("length", (O,)),
+                            ("width", (O,)), ("mass", (O,))):
+            np.testing.assert_array_equal(view(getattr(o, name), shape, np.float64), np.asarray(pk[name]).reshape(shape), err_msg=name)
+        np.testing.assert_array_equal(view(o.is_protected, (O,), np.int32), pk["prot"])
+        np.testing.assert_array_equal(view(o.responsibility, (O,), np.int32), pk["resp"])
+        assert (s.nv, s.nt, s.nd) == (len(st.v_list), len(st.t_list), len(st.d_list))
+        assert (s.c_begin, s.c_end, s.shard_count) == (0, s.nv * s.nt * s.nd, 1)
+        for name in ("c_s", "c_s_d", "c_s_dd", "c_d", "c_d_d", "c_d_dd", "dt", "v_thr", "velocity_target", "cost_factor"):
+            assert getattr(s, name) == getattr(st, name), name
+        np.testing.assert_array_equal(view(s.v_list, (s.nv,), np.float64), st.v_list)
+        np.testing.assert_array_equal(view(s.t_list, (s.nt,), np.float64), st.t_list)
+        np.testing.assert_array_equal(view(s.d_list, (s.nd,), np.float64), st.d_list)
+        np.testing.assert_array_equal(view(s.n_samples, (s.nt,), np.int32), [len(np.arange(0.0, tT, st.dt)) for tT in st.t_list])
+        csp = CubicSpline2D.from_foreign(st.csp)
+        assert sc.n_seg == len(csp.s) - 1
+        np.testing.assert_array_equal(view(sc.knots, (sc.n_seg + 1,), np.float64), csp.s)
+        np.testing.assert_array_equal(view(sc.coef_x, (sc.n_seg, 4), np.float64), csp.coef_x)
+        np.testing.assert_array_equal(view(sc.coef_y, (sc.n_seg, 4), np.float64), csp.coef_y)
