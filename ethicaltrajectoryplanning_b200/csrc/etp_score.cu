@@ -949,15 +949,25 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
         chunk = (Ts - chunk0 + kWarps - 2) / (kWarps - 1);
         chunk = chunk < 1 ? 1 : chunk;
     };
-    auto sort_obstacles = [&]() {  // thread 0
-        fill_tab<R>(tab, pr, st.eps_pos);
-        // protected obstacles first: a phase-2a item then holds one class and needs no per-sample class branch
-        int n = 0;
-        for (int o = 0; o < O; ++o)
-            if (ldg4<R>(tile.C + o).z != (R)0) s_perm[n++] = o;
-        s_nprot = n;
-        for (int o = 0; o < O; ++o)
-            if (ldg4<R>(tile.C + o).z == (R)0) s_perm[n++] = o;
+    auto sort_obstacles = [&]() {  // every thread calls it; a barrier follows at the call sites
+        if (tid == 0) fill_tab<R>(tab, pr, st.eps_pos);
+        // protected obstacles first, each class in its original order: a phase-2a item then holds one class and needs no
+        // per-sample class branch.  One warp, 32 obstacles per round: a ballot and a prefix count instead of a chain of
+        // dependent loads in one thread (the order is the serial loop's).
+        if (warp == kWarps - 1) {
+            int n = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int base = 0; base < O; base += 32) {
+                    const int o = base + lane;
+                    const bool prot_o = o < O && ldg4<R>(tile.C + o).z != (R)0;
+                    const bool mine = o < O && (pass == 0 ? prot_o : !prot_o);
+                    const unsigned m = __ballot_sync(kFull, mine);
+                    if (mine) s_perm[n + __popc(m & ((1u << lane) - 1u))] = o;
+                    n += __popc(m);
+                }
+                if (pass == 0 && lane == 0) s_nprot = n;
+            }
+        }
     };
     int cur_scn = -1;
 #ifdef ETP_PHASE_CLOCK
@@ -971,7 +981,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
     ETP_PCLK(0);
     if (!kBatch) {
         derive();
-        if (tid == 0) sort_obstacles();
+        sort_obstacles();
     }
     ETP_PCLK(1);
 #ifdef ETP_TMA_STAGE
@@ -1013,7 +1023,7 @@ score_kernel(const __grid_constant__ DevStep stp, const __grid_constant__ DevPar
                 for (int i = tid; i < (int)(sizeof(DevStep) / sizeof(int)); i += kThreads) reinterpret_cast<int*>(&s_st)[i] = __ldg(src + i);
                 __syncthreads();
                 derive();
-                if (tid == 0) sort_obstacles();
+                sort_obstacles();
 #ifdef ETP_TMA_STAGE
                 if (lane == 0) mbar_init(sm.bar + warp, 1);  // the barriers move with the shared-memory plan
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
