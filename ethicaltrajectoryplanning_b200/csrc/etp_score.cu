@@ -1616,7 +1616,8 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
         static const bool no_cluster = getenv("ETP_NO_CLUSTER") != nullptr;
         static const int max_cluster = getenv("ETP_CLUSTER_MAX") ? atoi(getenv("ETP_CLUSTER_MAX")) : 8;
         static const int dbg_min_len = getenv("ETP_CLUSTER_MINLEN") ? atoi(getenv("ETP_CLUSTER_MINLEN")) : 0;
-        for (int k = 8; k > 1 && !no_cluster; k >>= 1)
+        static bool cluster_refused = false;  // a cluster launch failed once on this device: plain launches from then on
+        for (int k = 8; k > 1 && !no_cluster && !cluster_refused; k >>= 1)
             if (k <= max_cluster && tiles * k <= num_sms) { csize = k; break; }
         if (csize > 1) {
             BatchArgs b2 = *ba;
@@ -1631,8 +1632,18 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
             at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            *grid_out = (int)(tiles * csize);
-            return cudaLaunchKernelEx(&cfg, score_kernel<R, NT, kSym, kGiven, kBatch>, st, pr, out, counters, b2);
+            const cudaError_t ce = cudaLaunchKernelEx(&cfg, score_kernel<R, NT, kSym, kGiven, kBatch>, st, pr, out, counters, b2);
+            if (ce == cudaSuccess) {
+                *grid_out = (int)(tiles * csize);
+                return ce;
+            }
+            // the first cycle of a shape is always launched outside a capture, so a device (partition) that cannot co-schedule
+            // the cluster is found out here: one CTA per tile instead
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone) return ce;
+            (void)cudaGetLastError();
+            cluster_refused = true;
         }
     }
     score_kernel<R, NT, kSym, kGiven, kBatch><<<(int)grid, kThreads, smem, stream>>>(st, pr, out, counters, kBatch ? *ba : BatchArgs{});
