@@ -1619,6 +1619,8 @@ static cudaError_t launch_score_t(const DevStep& st, const DevParams& pr, const 
         static bool cluster_refused = false;  // a cluster launch failed once on this device: plain launches from then on
         for (int k = 8; k > 1 && !no_cluster && !cluster_refused; k >>= 1)
             if (k <= max_cluster && tiles * k <= num_sms) { csize = k; break; }
+        static const int force_cluster = getenv("ETP_CLUSTER_FORCE") ? atoi(getenv("ETP_CLUSTER_FORCE")) : 0;  // experiments
+        if (force_cluster > 1 && !cluster_refused) csize = force_cluster;
         if (csize > 1) {
             BatchArgs b2 = *ba;
             b2.dbg_min_len = dbg_min_len;
